@@ -1,0 +1,198 @@
+/*
+ * qo100net.h -- C-ABI of libqo100net: B200-native (sm_100a) frequency-swept
+ * evaluation of 2-port RF networks and component-tolerance Monte-Carlo yield.
+ *
+ * Drop-in boundary.  The reference tree (vankxr/qo-100-tools) has NO code, FFI
+ * or plugin interface for this path: its util/ directory holds the inputs and
+ * outputs of external GUI tools.  The boundary this library replaces is
+ * therefore the *file formats* on the input side and Qucs-dataset-shaped
+ * arrays on the output side; each entry point cites the reference artefact
+ * (relative to the reference root) whose tool action it replaces.
+ *
+ * Conventions: every function returns 0 (QO_OK) or a negative qo_status and
+ * never aborts.  All array arguments are HOST pointers owned by the caller
+ * unless the name says "_dev"; the library does its own H2D / D2H.  Opaque
+ * handles are owned by the library and released with the matching *_free /
+ * *_destroy.  A qo_ctx is single-caller (not re-entrant); distinct contexts
+ * are independent.  There is NO CPU fallback: compute entry points fail with
+ * QO_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef QO100NET_H
+#define QO100NET_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QO_OK = 0,
+    QO_ERR_ARG = -1,
+    QO_ERR_IO = -2,
+    QO_ERR_PARSE = -3,
+    QO_ERR_UNSUPPORTED = -4,
+    QO_ERR_NOMEM = -5,
+    QO_ERR_NO_DEVICE = -6,
+    QO_ERR_CUDA = -7,
+    QO_ERR_NCCL = -8,
+    QO_ERR_RANGE = -9
+} qo_status;
+
+typedef struct qo_net qo_net;   /* immutable element list + terminations */
+typedef struct qo_ctx qo_ctx;   /* owns the device(s), stream(s), scratch buffers */
+typedef struct qo_plan qo_plan; /* a Monte-Carlo job resident in HBM */
+typedef struct { double re, im; } qo_c64;
+
+/* ---- element list ------------------------------------------------------ */
+typedef enum {
+    QO_SER_R = 1, QO_SHUNT_R = 2,            /* p0 = R                                   */
+    QO_SER_L = 3, QO_SHUNT_L = 4,            /* p0 = L, p1 = ESR, p2 = Cp  (Z=(R+jwL)||1/jwCp) */
+    QO_SER_C = 5, QO_SHUNT_C = 6,            /* p0 = C, p1 = ESR, p2 = ESL (Z=R+jwLs+1/jwC)    */
+    QO_SER_LC_SER = 7,                       /* p0 = L, p1 = C : Z = jwL + 1/(jwC)       */
+    QO_SER_LC_PAR = 8,                       /*                 Z = 1/(jwC + 1/(jwL))    */
+    QO_SHUNT_LC_SER = 9,                     /*                 Y = 1/(jwL + 1/(jwC))    */
+    QO_SHUNT_LC_PAR = 10,                    /*                 Y = jwC + 1/(jwL)        */
+    QO_TLINE = 11,                           /* p0 = Z0, p1 = angle[deg] at p2 = f0 (lossless) */
+    QO_CPL_THRU = 12,                        /* coupled line, through path, far ports in Zt:
+                                                p0=Z0e p1=Z0o p2=ang_e p3=ang_o [deg] p4=f0 p5=Zt */
+    QO_SUBST = 13,                           /* p = er, h, t, tand, rho, D (Qucs SUBST)  */
+    QO_MLIN = 14,                            /* p0 = W, p1 = L                           */
+    QO_MCORN = 15,                           /* p0 = W                                   */
+    QO_MTEE = 16,                            /* p0 = Wa, p1 = Wb, p2 = W2; opens the side arm:
+                                                the following elements, junction outward, up to */
+    QO_MOPEN = 17                            /* p0 = W; open end closing the side arm    */
+} qo_kind;
+#define QO_NPARAM 6
+typedef struct { int32_t kind; int32_t flags; double p[QO_NPARAM]; } qo_elem;
+
+/* rf-tools.com LC-filter export (SVG).  Replaces the rf-tools analysis of
+ * util/if-bandpass-filter/schematic.svg:174-217, util/gpsdo-ouput-filters/10M/
+ * schematic.svg:174-231, docs/gpsdo-filters/{15M,40M,60M}.svg:174-241,
+ * docs/upconverter/upconverter-lol-filter.svg:174-249. */
+int qo_net_load_rftools_svg(const char *path, qo_net **out);
+/* Qucs 0.0.19 schematic: components, properties, Eqn constants and the
+ * cascade recovered from wire/pin coordinates.  Replaces the Qucs netlister
+ * for util/pa-lpf-simulation/pa-lpf-simulation.sch:19-61 (2-port microstrip
+ * cascades with MTEE side stubs ending in MOPEN). */
+int qo_net_load_qucs_sch(const char *path, qo_net **out);
+/* the .SP sweep of a Qucs schematic (pa-lpf-simulation.sch:59): type 0=lin 1=log */
+int qo_qucs_sch_sweep(const char *path, int *type, double *f0, double *f1, int *n);
+/* QucsTranscalc CoupledMicrostrip save file (util/directional-couplers/ *.trc:5-21).
+ * phys (nullable) = { Er, H, H_t, T, W, S, L, Tand } in SI units. */
+int qo_cpl_load_trc(const char *path, double *z0e, double *z0o, double *ang_deg, double *f0_hz, double phys[8]);
+/* QucsTranscalc "analyze" for CoupledMicrostrip (physical -> electrical), the
+ * action that produced *.trc:18-20.  SI units; angles in degrees. */
+int qo_cpl_analyze(double w, double s, double h, double t, double er, double ht, double f, double len,
+                   double *z0e, double *z0o, double *ang_e_deg, double *ang_o_deg);
+
+int qo_net_from_elements(const qo_elem *e, int n, double rs, double rl, qo_net **out);
+/* pcb/generic-filter (README.md:13; qo-100-generic-filter.sch:1450-1488,1703-1995):
+ * up-to-11th-order ladders, 6 series + 5 shunt branches, series first. */
+int qo_net_cheby_lpf(int order, double ripple_db, double fc, double z0, int series_first, qo_net **out);
+int qo_net_butter_lpf(int order, double fc, double z0, int series_first, qo_net **out);
+/* ESR/SRF parasitics: L: R = wc*L/q_l, Cp s.t. SRF = srf_l_mult*fc;
+ * C: ESR = esr_c, ESL s.t. SRF = srf_c_mult*fc (model evidenced by
+ * util/pa-bias-simulation/pa-bias-simulation.sch:19-34 and the Coilcraft .s2p) */
+int qo_net_add_parasitics(qo_net *net, double fc, double q_l, double srf_l_mult, double esr_c, double srf_c_mult);
+int qo_net_concat(const qo_net *a, const qo_net *b, qo_net **out); /* a then b; terminations rs(a), rl(b) */
+int qo_net_num_elements(const qo_net *net);
+int qo_net_get_elements(const qo_net *net, qo_elem *out, int cap); /* returns count */
+int qo_net_terminations(const qo_net *net, double *rs, double *rl);
+/* free-text title lines found by the loader (e.g. "Cutoff Frequency = 15.00 MHz") */
+const char *qo_net_title(const qo_net *net);
+void qo_net_free(qo_net *net);
+
+/* f_k = f0 + k*((f1-f0)/(n-1)) with no FMA -- bit-exact vs
+ * util/pa-lpf-simulation/pa-lpf-simulation.dat:6-5005 */
+int qo_grid_lin(double f0, double f1, int n, double *f);
+int qo_grid_log(double f0, double f1, int n, double *f);
+
+/* ---- compute ----------------------------------------------------------- */
+/* ngpus devices 0..ngpus-1 in ONE process (samples sharded, counters combined
+ * by NCCL all-reduce when libnccl is loadable).  One process
+ * per GPU (torchrun) uses qo_ctx_create_on_device + qo_plan_launch with a
+ * caller-owned device counter buffer that torch.distributed all-reduces. */
+int qo_ctx_create(int ngpus, qo_ctx **out);
+int qo_ctx_create_on_device(int device, qo_ctx **out);
+int qo_ctx_set_stream(qo_ctx *ctx, void *cuda_stream); /* cudaStream_t of device 0 of the ctx; NULL = own */
+int qo_ctx_num_devices(const qo_ctx *ctx);
+void qo_ctx_destroy(qo_ctx *ctx);
+
+/* nominal sweep (Qucs ".SP" + "S[i,j]" + "dB()" of pa-lpf-simulation.sch:59-60);
+ * precision 64 or 32; every output pointer nullable; gd = -d(arg S21)/dw [s] */
+int qo_sweep(qo_ctx *ctx, const qo_net *net, const double *f, int nf, int precision,
+             qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22, double *gd);
+
+typedef enum { QO_SPEC_S21_MIN_DB = 1, QO_SPEC_S21_MAX_DB = 2, QO_SPEC_S11_MAX_DB = 3, QO_SPEC_GD_MAX = 4 } qo_spec_kind;
+typedef struct { int32_t kind; int32_t pad; double f_lo, f_hi, limit; } qo_spec; /* applies to grid f in [f_lo,f_hi] */
+#define QO_MAX_SPEC 8
+
+typedef enum { QO_DIST_UNIFORM = 0, QO_DIST_GAUSS3S = 1 } qo_dist;
+typedef enum { QO_TOL_REL = 0, QO_TOL_ABS = 1 } qo_tol_mode;
+/* one perturbed parameter: p[param] of element elem is nominal*(1+tol*x) (REL)
+ * or nominal+tol*x (ABS), x in [-1,1] drawn for random variable `var`
+ * (entries sharing a var share the draw, e.g. one etch delta per board) */
+typedef struct { int32_t elem, param, var, mode; double tol; } qo_tol;
+typedef enum { QO_MODE_REDUCE_ONLY = 0, QO_MODE_FULL_S = 1 } qo_mc_mode;
+
+typedef struct {
+    uint64_t seed, sample_offset, n_samples;
+    int32_t dist, n_tol;
+    const qo_tol *tol;
+    int32_t mode, precision;        /* qo_mc_mode; 64 | 32 */
+    int32_t hist_bins, hist_spec;   /* histogram of the worst value of spec hist_spec, in its unit */
+    double hist_lo, hist_hi;
+} qo_mc_cfg;
+
+typedef struct {
+    uint64_t n_pass, n_total;
+    uint64_t *fail_per_spec;   /* caller array [nspec], nullable */
+    uint64_t *hist;            /* caller array [hist_bins], nullable */
+    double seconds;            /* device time of the kernel(s), CUDA events */
+    double evals_per_s;        /* n_total * nf / seconds */
+    double flops_per_eval;     /* ALG-v1 count for this network */
+} qo_mc_result;
+
+/* Monte-Carlo yield with HOST buffers.  full_s (nullable unless mode==FULL_S):
+ * planes [4][n_samples][nf] in the order S11, S21, S12, S22. */
+int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec,
+              const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
+
+/* The same job kept resident in HBM (tables, grid, specs uploaded once):
+ *   counters layout (uint64): [0]=n_pass [1]=n_total [2..2+nspec)=fail_per_spec, then hist[hist_bins].
+ * qo_plan_launch is asynchronous on the ctx stream and ADDS into counters_dev
+ * (NULL = the plan's own buffer, zeroed by qo_plan_reset). full_s_dev: device
+ * buffer of planes [4][n_samples][nf] for FULL_S, else NULL. */
+int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec,
+                   const qo_mc_cfg *cfg, qo_plan **out);
+int qo_plan_num_counters(const qo_plan *plan);
+int qo_plan_reset(qo_plan *plan);
+int qo_plan_launch(qo_plan *plan, uint64_t sample_offset, uint64_t n_samples, uint64_t *counters_dev, qo_c64 *full_s_dev);
+int qo_plan_read(qo_plan *plan, qo_mc_result *res);   /* synchronises, combines across the ctx's GPUs */
+double qo_plan_flops_per_eval(const qo_plan *plan);
+int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far by this plan */
+void qo_plan_destroy(qo_plan *plan);
+
+/* ---- reference stream: host-callable, bit-exact twins of the device code -- */
+void   qo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+double qo_variate(uint64_t seed, uint64_t sample, uint32_t var, int dist);          /* x in [-1,1] */
+double qo_perturb_factor(uint64_t seed, uint64_t sample, uint32_t var, int dist, double tol);
+/* the device's own stream, for the bit-exactness test: out[n_samples][n_var] = 1+tol*x */
+int qo_device_perturb_factors(qo_ctx *ctx, uint64_t seed, uint64_t sample_offset, uint64_t n_samples,
+                              int n_var, int dist, double tol, double *out);
+
+/* the kernels' fast reciprocal (MUFU.RCP64H + one cubic step) applied to in[0..n), for accuracy tests */
+int qo_device_rcp(qo_ctx *ctx, const double *in, size_t n, double *out);
+
+/* measured FP64 FMA peak of device 0 of the ctx (dependency-free DFMA loop), TFLOP/s */
+int qo_measure_dfma_peak(qo_ctx *ctx, double *tflops);
+
+const char *qo_strerror(int status);
+const char *qo_last_error(void);  /* thread-local detail of the last failure ("" if none) */
+const char *qo_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,754 @@
+/*
+ * qo_cuda.cu -- contexts, plans and the compute entry points of libqo100net.
+ * Everything numerical happens in the kernels of qo_lumped.cuh / qo_ustrip.cuh;
+ * this file compiles networks into device programs, owns HBM buffers and
+ * launches.  There is no CPU evaluation path: without a device every compute
+ * call returns QO_ERR_NO_DEVICE.
+ */
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "qo_internal.h"
+#include "qo_lumped.cuh"
+#include "qo_ustrip.cuh"
+
+#define CU(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            qo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? QO_ERR_NO_DEVICE : QO_ERR_CUDA; \
+        }                                                                                             \
+    } while (0)
+
+/* ---- NCCL, loaded at run time (only the single-process multi-GPU ctx uses it) */
+typedef struct ncclComm *ncclComm_t;
+struct NcclApi {
+    void *h;
+    int (*CommInitAll)(ncclComm_t *, int, const int *);
+    int (*CommDestroy)(ncclComm_t);
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+    int (*GroupStart)(void);
+    int (*GroupEnd)(void);
+    const char *(*GetErrorString)(int);
+};
+static int nccl_load(NcclApi *a)
+{
+    memset(a, 0, sizeof *a);
+    const char *names[] = { "libnccl.so.2", "libnccl.so", NULL };
+    for (int i = 0; names[i] && !a->h; i++) a->h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!a->h) return 0;
+    a->CommInitAll = (int (*)(ncclComm_t *, int, const int *))dlsym(a->h, "ncclCommInitAll");
+    a->CommDestroy = (int (*)(ncclComm_t))dlsym(a->h, "ncclCommDestroy");
+    a->AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(a->h, "ncclAllReduce");
+    a->GroupStart = (int (*)(void))dlsym(a->h, "ncclGroupStart");
+    a->GroupEnd = (int (*)(void))dlsym(a->h, "ncclGroupEnd");
+    a->GetErrorString = (const char *(*)(int))dlsym(a->h, "ncclGetErrorString");
+    return a->CommInitAll && a->CommDestroy && a->AllReduce && a->GroupStart && a->GroupEnd;
+}
+enum { QO_NCCL_UINT64 = 5, QO_NCCL_SUM = 0 };   /* ncclUint64, ncclSum (nccl.h enum values) */
+
+struct DevCtx {
+    int device;
+    cudaStream_t stream;
+    int own_stream;
+    int sm_count;
+    cudaEvent_t ev0, ev1;
+};
+
+struct qo_ctx {
+    int ndev;
+    DevCtx d[8];
+    NcclApi nccl;
+    ncclComm_t comm[8];
+    int have_nccl;
+};
+
+struct DevPlan {
+    DevProg *prog;
+    void *w2, *wi2;            /* double2 or float2 [npairs] */
+    uchar2 *m2;
+    double *fgrid;             /* generic kernel */
+    unsigned char *mask;
+    unsigned long long *counters;
+    unsigned long long n_launched;
+    float ms;
+};
+
+struct qo_plan {
+    qo_ctx *ctx;
+    DevProg hp;                /* host copy of the program */
+    int nf, npairs, ncnt, precision, mode, generic;
+    double flops_per_eval;
+    int launches;
+    unsigned long long n_total_launched;
+    DevPlan d[8];
+    std::vector<double> f;
+    std::vector<unsigned char> maskv;
+};
+
+/* ---- ctx ---------------------------------------------------------------- */
+static int devctx_init(DevCtx *d, int device)
+{
+    memset(d, 0, sizeof *d);
+    d->device = device;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+    d->own_stream = 1;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    d->sm_count = prop.multiProcessorCount;
+    CU(cudaEventCreate(&d->ev0));
+    CU(cudaEventCreate(&d->ev1));
+    return QO_OK;
+}
+
+static int device_count(int *n)
+{
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess || *n <= 0) {
+        cudaGetLastError();
+        qo_set_error("no usable CUDA device (%s); libqo100net has no CPU fallback", e == cudaSuccess ? "count is 0" : cudaGetErrorString(e));
+        return QO_ERR_NO_DEVICE;
+    }
+    return QO_OK;
+}
+
+extern "C" int qo_ctx_create_on_device(int device, qo_ctx **out)
+{
+    qo_clear_error();
+    if (!out || device < 0) return QO_ERR_ARG;
+    int n, rc = device_count(&n);
+    if (rc) return rc;
+    if (device >= n) { qo_set_error("device %d out of range (%d visible)", device, n); return QO_ERR_ARG; }
+    qo_ctx *c = (qo_ctx *)calloc(1, sizeof(qo_ctx));
+    if (!c) return QO_ERR_NOMEM;
+    c->ndev = 1;
+    rc = devctx_init(&c->d[0], device);
+    if (rc) { free(c); return rc; }
+    *out = c;
+    return QO_OK;
+}
+
+extern "C" int qo_ctx_create(int ngpus, qo_ctx **out)
+{
+    qo_clear_error();
+    if (!out || !(ngpus == 1 || ngpus == 2 || ngpus == 4 || ngpus == 8)) { qo_set_error("ngpus must be 1, 2, 4 or 8"); return QO_ERR_ARG; }
+    int n, rc = device_count(&n);
+    if (rc) return rc;
+    if (ngpus > n) { qo_set_error("%d GPUs requested, %d visible", ngpus, n); return QO_ERR_NO_DEVICE; }
+    qo_ctx *c = (qo_ctx *)calloc(1, sizeof(qo_ctx));
+    if (!c) return QO_ERR_NOMEM;
+    c->ndev = ngpus;
+    for (int g = 0; g < ngpus; g++) {
+        rc = devctx_init(&c->d[g], g);
+        if (rc) { free(c); return rc; }
+    }
+    if (ngpus > 1) {
+        /* the only collective on this path: one all-reduce of the u64 counters */
+        if (!nccl_load(&c->nccl)) { free(c); qo_set_error("libnccl.so.2 not loadable: %s", dlerror()); return QO_ERR_NCCL; }
+        int devs[8];
+        for (int g = 0; g < ngpus; g++) devs[g] = g;
+        int r = c->nccl.CommInitAll(c->comm, ngpus, devs);
+        if (r != 0) { qo_set_error("ncclCommInitAll: %s", c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); free(c); return QO_ERR_NCCL; }
+        c->have_nccl = 1;
+    }
+    *out = c;
+    return QO_OK;
+}
+
+extern "C" int qo_ctx_set_stream(qo_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return QO_ERR_ARG;
+    DevCtx *d = &ctx->d[0];
+    CU(cudaSetDevice(d->device));
+    if (d->own_stream) { cudaStreamDestroy(d->stream); d->own_stream = 0; }
+    if (cuda_stream) d->stream = (cudaStream_t)cuda_stream;
+    else { CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)); d->own_stream = 1; }
+    return QO_OK;
+}
+
+extern "C" int qo_ctx_num_devices(const qo_ctx *ctx) { return ctx ? ctx->ndev : QO_ERR_ARG; }
+
+extern "C" void qo_ctx_destroy(qo_ctx *ctx)
+{
+    if (!ctx) return;
+    for (int g = 0; g < ctx->ndev; g++) {
+        cudaSetDevice(ctx->d[g].device);
+        if (ctx->have_nccl && ctx->comm[g]) ctx->nccl.CommDestroy(ctx->comm[g]);
+        if (ctx->d[g].own_stream) cudaStreamDestroy(ctx->d[g].stream);
+        cudaEventDestroy(ctx->d[g].ev0);
+        cudaEventDestroy(ctx->d[g].ev1);
+    }
+    free(ctx);
+}
+
+/* ---- network -> device program ------------------------------------------ */
+static int touches(const qo_mc_cfg *cfg, int elem, int param)
+{
+    if (!cfg) return 0;
+    for (int i = 0; i < cfg->n_tol; i++)
+        if (cfg->tol[i].elem == elem && cfg->tol[i].param == param && cfg->tol[i].tol != 0.0) return 1;
+    return 0;
+}
+
+/* ALG-v1 algorithmic flops per eval: immittance + chain step per element, +26 for ABCD->|S|^2 */
+static double alg_flops(int opcode)
+{
+    switch (opcode) {
+    case OP_SER_R: case OP_SHUNT_G: return 0 + 8;
+    case OP_SER_L: case OP_SER_C: case OP_SHUNT_C: case OP_SHUNT_L: return 1 + 8;
+    case OP_SER_LCS: case OP_SHUNT_LCP: return 3 + 8;
+    case OP_SER_LCP: case OP_SHUNT_LCS: return 4 + 8;
+    case OP_SER_LOSSY_L: case OP_SHUNT_LOSSY_L: return 17 + 16;
+    case OP_SER_LOSSY_C: return 3 + 16;
+    case OP_SHUNT_LOSSY_C: return 9 + 16;
+    case OP_TLINE: return 56 + 10;
+    case OP_CPL: return 56 + 40;
+    default: return 0;
+    }
+}
+
+static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec, const qo_mc_cfg *cfg,
+                      DevProg *hp, int *generic, double *flops, std::vector<unsigned char> *mask)
+{
+    memset(hp, 0, sizeof *hp);
+    if (net->n > QO_MAX_OPS) { qo_set_error("network has %d elements, limit %d", net->n, QO_MAX_OPS); return QO_ERR_RANGE; }
+    if (nspec < 0 || nspec > QO_NSPEC_MAX) { qo_set_error("at most %d specs", QO_NSPEC_MAX); return QO_ERR_RANGE; }
+    hp->n_ops = net->n;
+    hp->rs = net->rs; hp->rl = net->rl; hp->rsrl = net->rs * net->rl; hp->k21 = 2.0 * sqrt(net->rs * net->rl);
+    hp->seed = cfg ? cfg->seed : 0;
+    hp->dist = cfg ? cfg->dist : 0;
+    if (hp->dist != QO_DIST_UNIFORM && hp->dist != QO_DIST_GAUSS3S) { qo_set_error("unknown distribution %d", hp->dist); return QO_ERR_ARG; }
+    int coff = 0, ustrip = 0, trig = 0;
+    double fl = 26.0;
+    for (int e = 0; e < net->n; e++) {
+        const qo_elem *el = &net->e[e];
+        for (int k = 0; k < 6; k++) { hp->nom[e][k] = el->p[k]; hp->tvar[e][k] = -1; }
+        hp->kind[e] = el->kind;
+        int op = OP_NOP, nco = 0;
+        int lossy = el->p[1] != 0.0 || el->p[2] != 0.0 || touches(cfg, e, 1) || touches(cfg, e, 2);
+        switch (el->kind) {
+        case QO_SER_R: op = OP_SER_R; nco = 1; break;
+        case QO_SHUNT_R: op = OP_SHUNT_G; nco = 1; break;
+        case QO_SER_L: op = lossy ? OP_SER_LOSSY_L : OP_SER_L; nco = lossy ? 4 : 1; break;
+        case QO_SHUNT_L: op = lossy ? OP_SHUNT_LOSSY_L : OP_SHUNT_L; nco = lossy ? 4 : 1; break;
+        case QO_SER_C: op = lossy ? OP_SER_LOSSY_C : OP_SER_C; nco = lossy ? 4 : 1; break;
+        case QO_SHUNT_C: op = lossy ? OP_SHUNT_LOSSY_C : OP_SHUNT_C; nco = lossy ? 4 : 1; break;
+        case QO_SER_LC_SER: op = OP_SER_LCS; nco = 2; break;
+        case QO_SER_LC_PAR: op = OP_SER_LCP; nco = 2; break;
+        case QO_SHUNT_LC_SER: op = OP_SHUNT_LCS; nco = 2; break;
+        case QO_SHUNT_LC_PAR: op = OP_SHUNT_LCP; nco = 2; break;
+        case QO_TLINE: op = OP_TLINE; nco = 3; trig = 1; break;
+        case QO_CPL_THRU: op = OP_CPL; nco = 8; trig = 1; break;
+        case QO_SUBST: op = OP_SUBST; ustrip = 1; break;
+        case QO_MLIN: op = OP_MLIN; ustrip = 1; break;
+        case QO_MCORN: op = OP_MCORN; ustrip = 1; break;
+        case QO_MTEE: op = OP_MTEE; ustrip = 1; break;
+        case QO_MOPEN: op = OP_MOPEN; ustrip = 1; break;
+        default: qo_set_error("element %d: unsupported kind %d", e, el->kind); return QO_ERR_UNSUPPORTED;
+        }
+        hp->opcode[e] = op;
+        hp->coff[e] = coff;
+        coff += (nco + 1) & ~1;          /* keep every record 16-byte aligned */
+        fl += alg_flops(op);
+    }
+    if (coff > QO_MAX_COEF) { qo_set_error("coefficient table too large"); return QO_ERR_RANGE; }
+    hp->n_coef = coff;
+    hp->has_trig = trig;
+    hp->has_ustrip = ustrip;
+    *generic = ustrip;
+    *flops = ustrip ? 0.0 : fl;
+
+    /* tolerances -> per (element, parameter) random variable */
+    int nvar = 0;
+    if (cfg) {
+        if (cfg->n_tol < 0 || (cfg->n_tol > 0 && !cfg->tol)) return QO_ERR_ARG;
+        for (int i = 0; i < cfg->n_tol; i++) {
+            const qo_tol *t = &cfg->tol[i];
+            if (t->elem < 0 || t->elem >= net->n || t->param < 0 || t->param >= 6) { qo_set_error("tolerance %d: element/param out of range", i); return QO_ERR_ARG; }
+            if (t->var < 0 || t->var >= QO_MAX_VAR) { qo_set_error("tolerance %d: random variable index must be in [0,%d)", i, QO_MAX_VAR); return QO_ERR_RANGE; }
+            if (hp->tvar[t->elem][t->param] >= 0) { qo_set_error("tolerance %d: parameter perturbed twice", i); return QO_ERR_ARG; }
+            hp->tvar[t->elem][t->param] = (int16_t)t->var;
+            hp->tmode[t->elem][t->param] = (uint8_t)(t->mode == QO_TOL_ABS);
+            hp->ttol[t->elem][t->param] = t->tol;
+            if (t->var + 1 > nvar) nvar = t->var + 1;
+        }
+    }
+    hp->n_var = nvar;
+
+    /* specs -> canonical linear thresholds + per-frequency bit mask */
+    hp->nspec = nspec;
+    mask->assign((size_t)nf + 1, 0);
+    for (int s = 0; s < nspec; s++) {
+        const qo_spec *sp = &spec[s];
+        double lin = pow(10.0, sp->limit / 10.0);
+        hp->spec_user_kind[s] = sp->kind;
+        hp->spec_limit[s] = sp->limit;
+        switch (sp->kind) {
+        case QO_SPEC_S21_MIN_DB: hp->spec_kind[s] = SK_DEN2_MAX; hp->spec_thr[s] = ustrip ? lin : hp->k21 * hp->k21 / lin; break;
+        case QO_SPEC_S21_MAX_DB: hp->spec_kind[s] = SK_DEN2_MIN; hp->spec_thr[s] = ustrip ? lin : hp->k21 * hp->k21 / lin; break;
+        case QO_SPEC_S11_MAX_DB: hp->spec_kind[s] = SK_S11_MAX; hp->spec_thr[s] = lin; hp->need_s11 = 1; break;
+        case QO_SPEC_GD_MAX: qo_set_error("QO_SPEC_GD_MAX is not implemented in the Monte-Carlo kernels yet"); return QO_ERR_UNSUPPORTED;
+        default: qo_set_error("spec %d: unknown kind %d", s, sp->kind); return QO_ERR_ARG;
+        }
+        int hits = 0;
+        for (int k = 0; k < nf; k++)
+            if (f[k] >= sp->f_lo && f[k] <= sp->f_hi) { (*mask)[k] |= (unsigned char)(1u << s); hits++; }
+        if (cfg && cfg->hist_bins > 0 && cfg->hist_spec == s && hits == 0) { qo_set_error("histogram spec %d covers no grid frequency", s); return QO_ERR_ARG; }
+    }
+    if (cfg && cfg->hist_bins > 0) {
+        if (cfg->hist_bins > QO_MAX_HIST || cfg->hist_spec < 0 || cfg->hist_spec >= nspec || !(cfg->hist_hi > cfg->hist_lo)) { qo_set_error("bad histogram configuration"); return QO_ERR_ARG; }
+        hp->hist_bins = cfg->hist_bins; hp->hist_spec = cfg->hist_spec; hp->hist_lo = cfg->hist_lo; hp->hist_hi = cfg->hist_hi;
+    }
+    return QO_OK;
+}
+
+/* ---- plan ---------------------------------------------------------------- */
+extern "C" void qo_plan_destroy(qo_plan *p)
+{
+    if (!p) return;
+    for (int g = 0; g < p->ctx->ndev; g++) {
+        cudaSetDevice(p->ctx->d[g].device);
+        DevPlan *d = &p->d[g];
+        cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->m2);
+        cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters);
+    }
+    delete p;
+}
+
+extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec,
+                              const qo_mc_cfg *cfg, qo_plan **out)
+{
+    qo_clear_error();
+    if (!ctx || !net || !f || nf <= 0 || !out || (nspec > 0 && !spec)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    for (int k = 0; k < nf; k++)
+        if (!(f[k] > 0.0) || !isfinite(f[k])) { qo_set_error("frequency %d is not a positive finite number", k); return QO_ERR_ARG; }
+    qo_plan *p = new (std::nothrow) qo_plan();
+    if (!p) return QO_ERR_NOMEM;
+    p->ctx = ctx;
+    p->nf = nf;
+    p->npairs = (nf + 1) / 2;
+    p->precision = cfg && cfg->precision == 32 ? 32 : 64;
+    p->mode = cfg ? cfg->mode : QO_MODE_FULL_S;
+    p->launches = 0;
+    memset(p->d, 0, sizeof p->d);
+    int rc = build_prog(net, f, nf, spec, nspec, cfg, &p->hp, &p->generic, &p->flops_per_eval, &p->maskv);
+    if (rc) { delete p; return rc; }
+    if (p->generic && p->precision == 32) { delete p; qo_set_error("FP32 mode covers lumped/TL networks only"); return QO_ERR_UNSUPPORTED; }
+    p->ncnt = 2 + nspec + p->hp.hist_bins;
+    p->f.assign(f, f + nf);
+
+    /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
+    const double two_pi = 6.283185307179586476925286766559;
+    const int np = p->npairs;
+    std::vector<double> w(2 * (size_t)np), wi(2 * (size_t)np);
+    std::vector<float> wf(2 * (size_t)np), wif(2 * (size_t)np);
+    std::vector<unsigned char> m(2 * (size_t)np, 0);
+    for (int k = 0; k < 2 * np; k++) {
+        double fk = f[k < nf ? k : nf - 1];
+        w[k] = two_pi * fk; wi[k] = 1.0 / w[k];
+        wf[k] = (float)w[k]; wif[k] = (float)wi[k];
+        m[k] = k < nf ? p->maskv[k] : 0;
+    }
+    for (int g = 0; g < ctx->ndev; g++) {
+        DevPlan *d = &p->d[g];
+        rc = QO_ERR_CUDA;
+#define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); qo_plan_destroy(p); return QO_ERR_CUDA; } } while (0)
+        CUP(cudaSetDevice(ctx->d[g].device));
+        cudaStream_t st = ctx->d[g].stream;
+        CUP(cudaMalloc(&d->prog, sizeof(DevProg)));
+        CUP(cudaMemcpyAsync(d->prog, &p->hp, sizeof(DevProg), cudaMemcpyHostToDevice, st));
+        if (!p->generic) {
+            size_t esz = p->precision == 32 ? sizeof(float) : sizeof(double);
+            CUP(cudaMalloc(&d->w2, 2 * (size_t)np * esz));
+            CUP(cudaMalloc(&d->wi2, 2 * (size_t)np * esz));
+            CUP(cudaMalloc(&d->m2, 2 * (size_t)np));
+            if (p->precision == 32) {
+                CUP(cudaMemcpyAsync(d->w2, wf.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                CUP(cudaMemcpyAsync(d->wi2, wif.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+            } else {
+                CUP(cudaMemcpyAsync(d->w2, w.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                CUP(cudaMemcpyAsync(d->wi2, wi.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+            }
+            CUP(cudaMemcpyAsync(d->m2, m.data(), 2 * (size_t)np, cudaMemcpyHostToDevice, st));
+        } else {
+            CUP(cudaMalloc(&d->fgrid, (size_t)nf * sizeof(double)));
+            CUP(cudaMalloc(&d->mask, (size_t)nf));
+            CUP(cudaMemcpyAsync(d->fgrid, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
+            CUP(cudaMemcpyAsync(d->mask, p->maskv.data(), (size_t)nf, cudaMemcpyHostToDevice, st));
+        }
+        CUP(cudaMalloc(&d->counters, (size_t)p->ncnt * sizeof(unsigned long long)));
+        CUP(cudaMemsetAsync(d->counters, 0, (size_t)p->ncnt * sizeof(unsigned long long), st));
+        CUP(cudaStreamSynchronize(st));   /* the host staging vectors die at return */
+    }
+    *out = p;
+    return QO_OK;
+}
+
+extern "C" int qo_plan_num_counters(const qo_plan *p) { return p ? p->ncnt : QO_ERR_ARG; }
+extern "C" double qo_plan_flops_per_eval(const qo_plan *p) { return p ? p->flops_per_eval : 0.0; }
+extern "C" int qo_plan_launches(const qo_plan *p) { return p ? p->launches : QO_ERR_ARG; }
+
+extern "C" int qo_plan_reset(qo_plan *p)
+{
+    if (!p) return QO_ERR_ARG;
+    for (int g = 0; g < p->ctx->ndev; g++) {
+        CU(cudaSetDevice(p->ctx->d[g].device));
+        CU(cudaMemsetAsync(p->d[g].counters, 0, (size_t)p->ncnt * sizeof(unsigned long long), p->ctx->d[g].stream));
+        p->d[g].n_launched = 0;
+    }
+    p->n_total_launched = 0;
+    return QO_OK;
+}
+
+template <typename T>
+static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    DevPlan *d = &p->d[g];
+    typedef typename QoVec2<T>::type V2;
+    const int resident = dc->sm_count * 2;                  /* __launch_bounds__(256, 2) */
+    const unsigned long long warps_resident = (unsigned long long)resident * QO_WARPS;
+    /* split the frequency axis only when there are too few samples to fill the GPU (sweeps) */
+    int nchunks = 1, ppc = p->npairs;
+    if (full_s && n < warps_resident) {
+        unsigned long long want = (warps_resident + n - 1) / n;
+        int maxc = (p->npairs + 31) / 32;
+        nchunks = (int)(want < (unsigned long long)maxc ? want : (unsigned long long)maxc);
+        if (nchunks < 1) nchunks = 1;
+        ppc = ((p->npairs + nchunks - 1) / nchunks + 31) / 32 * 32;
+        nchunks = (p->npairs + ppc - 1) / ppc;
+    }
+    unsigned long long units = n * (unsigned long long)nchunks;
+    unsigned long long blocks = (units + QO_WARPS - 1) / QO_WARPS;
+    int grid = (int)(blocks < (unsigned long long)resident ? blocks : (unsigned long long)resident);
+    if (grid < 1) grid = 1;
+#define QO_LAUNCH(FS, TR)                                                                                       \
+    qo_mc_lumped_kernel<T, FS, TR><<<grid, QO_TPB, 0, dc->stream>>>(d->prog, (const V2 *)d->w2, (const V2 *)d->wi2, \
+                                                                     d->m2, p->nf, p->npairs, ppc, nchunks, off, n, cnt, pl)
+    if (full_s) { if (p->hp.has_trig) QO_LAUNCH(true, true); else QO_LAUNCH(true, false); }
+    else { if (p->hp.has_trig) QO_LAUNCH(false, true); else QO_LAUNCH(false, false); }
+#undef QO_LAUNCH
+    CU(cudaGetLastError());
+    return QO_OK;
+}
+
+static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    DevPlan *d = &p->d[g];
+    int sb, f_chunk = p->nf, n_fchunks = 1;
+    if (full_s) {
+        /* no per-sample reduction: cut (sample, frequency) space into ~QO_G_TPB-item tiles */
+        if (p->nf >= QO_G_TPB) { sb = 1; f_chunk = QO_G_TPB; n_fchunks = (p->nf + f_chunk - 1) / f_chunk; }
+        else sb = (QO_G_TPB + p->nf - 1) / p->nf;
+    } else {
+        sb = (2 * QO_G_TPB + p->nf - 1) / p->nf;
+        if (sb < 1) sb = 1;
+    }
+    if (sb > QO_G_SB) sb = QO_G_SB;
+    unsigned long long tiles = ((n + sb - 1) / sb) * (unsigned long long)n_fchunks;
+    unsigned long long cap = (unsigned long long)dc->sm_count * 8;
+    int grid = (int)(tiles < cap ? tiles : cap);
+    if (grid < 1) grid = 1;
+    qo_mc_generic_kernel<<<grid, QO_G_TPB, 0, dc->stream>>>(d->prog, d->fgrid, d->mask, p->nf, f_chunk, n_fchunks, sb, off, n, cnt, pl, full_s);
+    CU(cudaGetLastError());
+    return QO_OK;
+}
+
+static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, qo_c64 *full_s_dev,
+                           unsigned long long plane_samples, unsigned long long plane_first)
+{
+    if (n == 0) return QO_OK;
+    CU(cudaSetDevice(p->ctx->d[g].device));
+    int full_s = p->mode == QO_MODE_FULL_S;
+    QoPlanes pl = { NULL, NULL, NULL, NULL };
+    if (full_s) {
+        if (!full_s_dev) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
+        size_t plane = (size_t)plane_samples * (size_t)p->nf;
+        double2 *base = (double2 *)full_s_dev + (size_t)plane_first * (size_t)p->nf;
+        pl.s11 = base; pl.s21 = base + plane; pl.s12 = base + 2 * plane; pl.s22 = base + 3 * plane;
+    }
+    int rc;
+    if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
+    else if (p->precision == 32) rc = launch_lumped<float>(p, g, off, n, cnt, pl, full_s);
+    else rc = launch_lumped<double>(p, g, off, n, cnt, pl, full_s);
+    if (rc == QO_OK) { p->launches++; p->d[g].n_launched += n; }
+    return rc;
+}
+
+extern "C" int qo_plan_launch(qo_plan *p, uint64_t sample_offset, uint64_t n_samples, uint64_t *counters_dev, qo_c64 *full_s_dev)
+{
+    qo_clear_error();
+    if (!p) return QO_ERR_ARG;
+    qo_ctx *c = p->ctx;
+    if (c->ndev == 1) {
+        unsigned long long *cnt = counters_dev ? (unsigned long long *)counters_dev : p->d[0].counters;
+        int rc = plan_launch_dev(p, 0, sample_offset, n_samples, cnt, full_s_dev, n_samples, 0);
+        if (rc == QO_OK) p->n_total_launched += n_samples;
+        return rc;
+    }
+    if (counters_dev || full_s_dev) { qo_set_error("caller-owned device buffers need a single-device ctx"); return QO_ERR_ARG; }
+    /* shard the contiguous global sample range; Philox counters carry the GLOBAL index */
+    for (int g = 0; g < c->ndev; g++) {
+        unsigned long long a = n_samples * (unsigned long long)g / c->ndev, b = n_samples * (unsigned long long)(g + 1) / c->ndev;
+        int rc = plan_launch_dev(p, g, sample_offset + a, b - a, p->d[g].counters, NULL, 0, 0);
+        if (rc) return rc;
+    }
+    p->n_total_launched += n_samples;
+    return QO_OK;
+}
+
+extern "C" int qo_plan_read(qo_plan *p, qo_mc_result *res)
+{
+    qo_clear_error();
+    if (!p || !res) return QO_ERR_ARG;
+    qo_ctx *c = p->ctx;
+    std::vector<unsigned long long> h((size_t)p->ncnt, 0), tmp((size_t)p->ncnt);
+    if (c->ndev > 1 && c->have_nccl) {
+        /* the path's only collective: sum of u64 counters (integers => result independent of GPU count) */
+        c->nccl.GroupStart();
+        for (int g = 0; g < c->ndev; g++) {
+            cudaSetDevice(c->d[g].device);
+            int r = c->nccl.AllReduce(p->d[g].counters, p->d[g].counters, (size_t)p->ncnt, QO_NCCL_UINT64, QO_NCCL_SUM, c->comm[g], c->d[g].stream);
+            if (r) { c->nccl.GroupEnd(); qo_set_error("ncclAllReduce failed (%d)", r); return QO_ERR_NCCL; }
+        }
+        if (c->nccl.GroupEnd()) { qo_set_error("ncclGroupEnd failed"); return QO_ERR_NCCL; }
+        for (int g = 0; g < c->ndev; g++) { CU(cudaSetDevice(c->d[g].device)); CU(cudaStreamSynchronize(c->d[g].stream)); }
+        CU(cudaSetDevice(c->d[0].device));
+        CU(cudaMemcpy(h.data(), p->d[0].counters, (size_t)p->ncnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        /* counters now hold the global sum on every device: keep only device 0's copy as the accumulator */
+        for (int g = 1; g < c->ndev; g++) { CU(cudaSetDevice(c->d[g].device)); CU(cudaMemset(p->d[g].counters, 0, (size_t)p->ncnt * sizeof(unsigned long long))); }
+    } else {
+        for (int g = 0; g < c->ndev; g++) {
+            CU(cudaSetDevice(c->d[g].device));
+            CU(cudaStreamSynchronize(c->d[g].stream));
+            CU(cudaMemcpy(tmp.data(), p->d[g].counters, (size_t)p->ncnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < p->ncnt; i++) h[i] += tmp[i];
+        }
+    }
+    res->n_pass = h[0];
+    res->n_total = h[1];
+    if (res->fail_per_spec) for (int s = 0; s < p->hp.nspec; s++) res->fail_per_spec[s] = h[2 + s];
+    if (res->hist) for (int b = 0; b < p->hp.hist_bins; b++) res->hist[b] = h[2 + p->hp.nspec + b];
+    res->flops_per_eval = p->flops_per_eval;
+    return QO_OK;
+}
+
+/* ---- one-shot host-buffer entry points ------------------------------------ */
+extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec,
+                         const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s)
+{
+    qo_clear_error();
+    if (!ctx || !cfg || !res) return QO_ERR_ARG;
+    if (cfg->mode == QO_MODE_FULL_S && !full_s) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
+    qo_plan *p = NULL;
+    int rc = qo_plan_create(ctx, net, f, nf, spec, nspec, cfg, &p);
+    if (rc) return rc;
+    const int fs = cfg->mode == QO_MODE_FULL_S;
+    const unsigned long long N = cfg->n_samples;
+    qo_c64 *dbuf[8] = { 0 };
+    unsigned long long a[9];
+    for (int g = 0; g <= ctx->ndev; g++) a[g] = N * (unsigned long long)g / ctx->ndev;
+    for (int g = 0; g < ctx->ndev && rc == QO_OK; g++) {
+        cudaSetDevice(ctx->d[g].device);
+        cudaEventRecord(ctx->d[g].ev0, ctx->d[g].stream);
+        unsigned long long n = a[g + 1] - a[g];
+        if (fs && n) {
+            if (cudaMalloc(&dbuf[g], 4 * (size_t)n * nf * sizeof(qo_c64)) != cudaSuccess) { cudaGetLastError(); qo_set_error("cannot allocate %zu bytes for FULL_S output", 4 * (size_t)n * nf * sizeof(qo_c64)); rc = QO_ERR_NOMEM; break; }
+        }
+        rc = plan_launch_dev(p, g, cfg->sample_offset + a[g], n, p->d[g].counters, dbuf[g], n, 0);
+        cudaEventRecord(ctx->d[g].ev1, ctx->d[g].stream);
+    }
+    if (rc == QO_OK) rc = qo_plan_read(p, res);
+    if (rc == QO_OK) {
+        float worst = 0;
+        for (int g = 0; g < ctx->ndev; g++) {
+            float ms = 0;
+            cudaSetDevice(ctx->d[g].device);
+            cudaEventSynchronize(ctx->d[g].ev1);
+            cudaEventElapsedTime(&ms, ctx->d[g].ev0, ctx->d[g].ev1);
+            if (ms > worst) worst = ms;
+        }
+        res->seconds = worst * 1e-3;
+        res->evals_per_s = res->seconds > 0 ? (double)N * nf / res->seconds : 0.0;
+        if (fs) {
+            res->n_total = N;
+            /* planes [4][N][nf] on the host; each device holds [4][n_g][nf] */
+            for (int g = 0; g < ctx->ndev && rc == QO_OK; g++) {
+                unsigned long long n = a[g + 1] - a[g];
+                if (!n) continue;
+                cudaSetDevice(ctx->d[g].device);
+                for (int pl = 0; pl < 4; pl++) {
+                    cudaError_t e = cudaMemcpy(full_s + ((size_t)pl * N + a[g]) * nf, dbuf[g] + (size_t)pl * n * nf,
+                                               (size_t)n * nf * sizeof(qo_c64), cudaMemcpyDeviceToHost);
+                    if (e != cudaSuccess) { qo_set_error("D2H of FULL_S failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; break; }
+                }
+            }
+        }
+    }
+    for (int g = 0; g < ctx->ndev; g++) if (dbuf[g]) { cudaSetDevice(ctx->d[g].device); cudaFree(dbuf[g]); }
+    qo_plan_destroy(p);
+    return rc;
+}
+
+__global__ void qo_gd_kernel(const double2 *__restrict__ s21, const double *__restrict__ f3, int nf, double *__restrict__ gd)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nf) return;
+    /* tau = -d(arg S21)/dw, central difference over the two bracketing points */
+    double2 a = s21[nf + k], b = s21[2 * nf + k];
+    double re = a.x * b.x + a.y * b.y, im = a.y * b.x - a.x * b.y;      /* a * conj(b) */
+    double dw = 6.283185307179586476925286766559 * (f3[nf + k] - f3[2 * nf + k]);
+    gd[k] = -atan2(im, re) / dw;
+}
+
+extern "C" int qo_sweep(qo_ctx *ctx, const qo_net *net, const double *f, int nf, int precision,
+                        qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22, double *gd)
+{
+    qo_clear_error();
+    if (!ctx || !net || !f || nf <= 0) return QO_ERR_ARG;
+    if (precision != 64 && precision != 32) { qo_set_error("precision must be 64 or 32"); return QO_ERR_ARG; }
+    /* group delay: evaluate f, f(1+1e-6), f(1-1e-6) in the same launch */
+    const int nft = gd ? 3 * nf : nf;
+    std::vector<double> f3;
+    const double *fg = f;
+    if (gd) {
+        f3.resize((size_t)nft);
+        for (int k = 0; k < nf; k++) { double df = f[k] * 1e-6; f3[k] = f[k]; f3[nf + k] = f[k] + df; f3[2 * nf + k] = f[k] - df; }
+        fg = f3.data();
+    }
+    qo_mc_cfg cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.n_samples = 1; cfg.mode = QO_MODE_FULL_S; cfg.precision = precision;
+    /* device 0 of the ctx only: a nominal sweep has nothing to shard */
+    qo_ctx one = *ctx;
+    one.ndev = 1;
+    qo_plan *p = NULL;
+    int rc = qo_plan_create(&one, net, fg, nft, NULL, 0, &cfg, &p);
+    if (rc) return rc;
+    DevCtx *dc = &ctx->d[0];
+    double2 *buf = NULL;
+    double *dgd = NULL, *df3 = NULL;
+    cudaSetDevice(dc->device);
+    do {
+        if (cudaMalloc(&buf, 4 * (size_t)nft * sizeof(double2)) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
+        rc = plan_launch_dev(p, 0, 0, 1, p->d[0].counters, (qo_c64 *)buf, 1, 0);
+        if (rc) break;
+        if (gd) {
+            if (cudaMalloc(&dgd, (size_t)nf * sizeof(double)) != cudaSuccess || cudaMalloc(&df3, (size_t)nft * sizeof(double)) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
+            cudaMemcpyAsync(df3, fg, (size_t)nft * sizeof(double), cudaMemcpyHostToDevice, dc->stream);
+            qo_gd_kernel<<<(nf + 127) / 128, 128, 0, dc->stream>>>(buf + (size_t)nft, df3, nf, dgd);
+            p->launches++;
+        }
+        cudaError_t e = cudaStreamSynchronize(dc->stream);
+        if (e != cudaSuccess) { qo_set_error("sweep kernel failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; break; }
+        qo_c64 *outs[4] = { s11, s21, s12, s22 };
+        for (int pl = 0; pl < 4; pl++)
+            if (outs[pl]) cudaMemcpy(outs[pl], buf + (size_t)pl * nft, (size_t)nf * sizeof(double2), cudaMemcpyDeviceToHost);
+        if (gd) cudaMemcpy(gd, dgd, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { qo_set_error("sweep copy failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; }
+    } while (0);
+    cudaFree(buf); cudaFree(dgd); cudaFree(df3);
+    qo_plan_destroy(p);
+    return rc;
+}
+
+/* ---- the device's perturbation stream, for the bit-exactness test --------- */
+__global__ void qo_factor_kernel(unsigned long long seed, unsigned long long off, unsigned long long n, int nvar, int dist, double tol, double *out)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * (unsigned long long)nvar) return;
+    unsigned long long s = i / (unsigned long long)nvar;
+    uint32_t v = (uint32_t)(i - s * (unsigned long long)nvar);
+    out[i] = QO_FMA(tol, qo_stream_variate(seed, off + s, v, dist), 1.0);
+}
+
+extern "C" int qo_device_perturb_factors(qo_ctx *ctx, uint64_t seed, uint64_t sample_offset, uint64_t n_samples,
+                                         int n_var, int dist, double tol, double *out)
+{
+    qo_clear_error();
+    if (!ctx || !out || n_var <= 0 || n_samples == 0) return QO_ERR_ARG;
+    DevCtx *dc = &ctx->d[0];
+    CU(cudaSetDevice(dc->device));
+    size_t n = (size_t)n_samples * (size_t)n_var;
+    double *d = NULL;
+    CU(cudaMalloc(&d, n * sizeof(double)));
+    qo_factor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, dc->stream>>>(seed, sample_offset, n_samples, n_var, dist, tol, d);
+    cudaError_t e = cudaStreamSynchronize(dc->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { qo_set_error("factor kernel: %s", cudaGetErrorString(e)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
+/* ---- the kernel's reciprocal, exposed so that its accuracy can be tested ---- */
+__global__ void qo_rcp_kernel(const double *in, double *out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = qrcp(in[i]);
+}
+extern "C" int qo_device_rcp(qo_ctx *ctx, const double *in, size_t n, double *out)
+{
+    qo_clear_error();
+    if (!ctx || !in || !out || !n) return QO_ERR_ARG;
+    DevCtx *dc = &ctx->d[0];
+    CU(cudaSetDevice(dc->device));
+    double *di = NULL, *dout = NULL;
+    CU(cudaMalloc(&di, n * sizeof(double)));
+    CU(cudaMalloc(&dout, n * sizeof(double)));
+    cudaMemcpyAsync(di, in, n * sizeof(double), cudaMemcpyHostToDevice, dc->stream);
+    qo_rcp_kernel<<<(unsigned)((n + 255) / 256), 256, 0, dc->stream>>>(di, dout, n);
+    cudaError_t e = cudaStreamSynchronize(dc->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(di); cudaFree(dout);
+    if (e != cudaSuccess) { qo_set_error("rcp kernel: %s", cudaGetErrorString(e)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
+/* ---- FP64 FMA peak: dependency-free DFMA loop (roofline denominator) ------- */
+__global__ void __launch_bounds__(256) qo_dfma_peak_kernel(double *out, int iters, double x, double y)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+            a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int qo_measure_dfma_peak(qo_ctx *ctx, double *tflops)
+{
+    qo_clear_error();
+    if (!ctx || !tflops) return QO_ERR_ARG;
+    DevCtx *dc = &ctx->d[0];
+    CU(cudaSetDevice(dc->device));
+    const int blocks = dc->sm_count * 8, iters = 4096;
+    double *d = NULL;
+    CU(cudaMalloc(&d, (size_t)blocks * 256 * sizeof(double)));
+    double best = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(dc->ev0, dc->stream);
+        qo_dfma_peak_kernel<<<blocks, 256, 0, dc->stream>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(dc->ev1, dc->stream);
+        cudaError_t e = cudaEventSynchronize(dc->ev1);
+        if (e != cudaSuccess) { cudaFree(d); qo_set_error("dfma kernel: %s", cudaGetErrorString(e)); return QO_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
+        double tf = (double)blocks * 256 * iters * 64 * 2 / (ms * 1e-3) * 1e-12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(d);
+    *tflops = best;
+    return QO_OK;
+}

@@ -1,0 +1,390 @@
+/*
+ * qo_lumped.cuh -- the FP64-FMA-bound hot kernel (sm_100a).
+ *
+ * One warp owns one Monte-Carlo sample at a time; each lane owns that sample's
+ * (sample, frequency) points two at a time (one double2 load = two adjacent grid
+ * frequencies) and chains the complex 2x2 ABCD products of all elements in
+ * registers.  Per sample the warp first derives the perturbed, hoisted element
+ * coefficients (Philox -> value -> 1/C, L*Cp, ...) into a shared-memory table
+ * that all lanes then read by broadcast.  |S21|^2 / |S11|^2 are compared against
+ * the specs in linear power (no log in the loop); pass/fail and the histogram
+ * variable are reduced with warp shuffles, then shared-memory atomics, then one
+ * global atomic per counter per block.
+ *
+ * ABCD conventions: series Z: B += A*Z, D += C*Z;
+ * shunt Y: A += B*Y, C += D*Y; product runs source -> load.
+ */
+#pragma once
+#include "qo_device.cuh"
+#include "qo_stream.h"
+
+#define QO_TPB 256
+#define QO_WARPS (QO_TPB / 32)
+
+/* ---- scalar helpers, generic over double / float ------------------------- */
+__device__ __forceinline__ double qfma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float qfma(float a, float b, float c) { return fmaf(a, b, c); }
+
+/* 1/x: MUFU.RCP64H seed (>= 20 good bits) + one cubic step: e = 1 - x*r0,
+ * r = r0*(1 + e + e^2); relative error ~e^3 + 1 rounding (validated on device in
+ * tests/test_gpu_parity.py::test_rcp_accuracy). 3 DFMA instead of the 4 of two
+ * Newton steps, and no slow-path branch. */
+__device__ __forceinline__ double qrcp(double x)
+{
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    double e = fma(-x, r0, 1.0);
+    double t = fma(e, e, e);
+    return fma(r0, t, r0);
+}
+__device__ __forceinline__ float qrcp(float x) { return __frcp_rn(x); }
+
+__device__ __forceinline__ void qsincos(double x, double *s, double *c) { sincos(x, s, c); }
+__device__ __forceinline__ void qsincos(float x, float *s, float *c) { sincosf(x, s, c); }
+
+template <typename T> struct QoVec2;
+template <> struct QoVec2<double> { typedef double2 type; };
+template <> struct QoVec2<float> { typedef float2 type; };
+
+/* two (sample, frequency) points per thread */
+template <typename T> struct Abcd2 {
+    T ar[2], ai[2], br[2], bi[2], cr[2], ci[2], dr[2], di[2];
+};
+
+#define QO_P2 _Pragma("unroll") for (int p = 0; p < 2; p++)
+
+template <typename T> __device__ __forceinline__ void ser_cplx(Abcd2<T> &m, int p, T zr, T zi)
+{
+    m.br[p] = qfma(m.ar[p], zr, m.br[p]); m.br[p] = qfma(-m.ai[p], zi, m.br[p]);
+    m.bi[p] = qfma(m.ar[p], zi, m.bi[p]); m.bi[p] = qfma(m.ai[p], zr, m.bi[p]);
+    m.dr[p] = qfma(m.cr[p], zr, m.dr[p]); m.dr[p] = qfma(-m.ci[p], zi, m.dr[p]);
+    m.di[p] = qfma(m.cr[p], zi, m.di[p]); m.di[p] = qfma(m.ci[p], zr, m.di[p]);
+}
+template <typename T> __device__ __forceinline__ void shunt_cplx(Abcd2<T> &m, int p, T yr, T yi)
+{
+    m.ar[p] = qfma(m.br[p], yr, m.ar[p]); m.ar[p] = qfma(-m.bi[p], yi, m.ar[p]);
+    m.ai[p] = qfma(m.br[p], yi, m.ai[p]); m.ai[p] = qfma(m.bi[p], yr, m.ai[p]);
+    m.cr[p] = qfma(m.dr[p], yr, m.cr[p]); m.cr[p] = qfma(-m.di[p], yi, m.cr[p]);
+    m.ci[p] = qfma(m.dr[p], yi, m.ci[p]); m.ci[p] = qfma(m.di[p], yr, m.ci[p]);
+}
+template <typename T> __device__ __forceinline__ void ser_imag(Abcd2<T> &m, int p, T x)
+{
+    m.br[p] = qfma(-m.ai[p], x, m.br[p]); m.bi[p] = qfma(m.ar[p], x, m.bi[p]);
+    m.dr[p] = qfma(-m.ci[p], x, m.dr[p]); m.di[p] = qfma(m.cr[p], x, m.di[p]);
+}
+template <typename T> __device__ __forceinline__ void shunt_imag(Abcd2<T> &m, int p, T y)
+{
+    m.ar[p] = qfma(-m.bi[p], y, m.ar[p]); m.ai[p] = qfma(m.br[p], y, m.ai[p]);
+    m.cr[p] = qfma(-m.di[p], y, m.cr[p]); m.ci[p] = qfma(m.dr[p], y, m.ci[p]);
+}
+/* M <- M * [a b; c d] with a general complex 2x2 (TLINE / coupled line blocks) */
+template <typename T>
+__device__ __forceinline__ void mul_full(Abcd2<T> &m, int p, T ar, T ai, T br, T bi, T cr, T ci, T dr, T di)
+{
+    T Ar = m.ar[p], Ai = m.ai[p], Br = m.br[p], Bi = m.bi[p];
+    m.ar[p] = qfma(Ar, ar, qfma(-Ai, ai, qfma(Br, cr, -Bi * ci)));
+    m.ai[p] = qfma(Ar, ai, qfma(Ai, ar, qfma(Br, ci, Bi * cr)));
+    m.br[p] = qfma(Ar, br, qfma(-Ai, bi, qfma(Br, dr, -Bi * di)));
+    m.bi[p] = qfma(Ar, bi, qfma(Ai, br, qfma(Br, di, Bi * dr)));
+    T Cr = m.cr[p], Ci = m.ci[p], Dr = m.dr[p], Di = m.di[p];
+    m.cr[p] = qfma(Cr, ar, qfma(-Ci, ai, qfma(Dr, cr, -Di * ci)));
+    m.ci[p] = qfma(Cr, ai, qfma(Ci, ar, qfma(Dr, ci, Di * cr)));
+    m.dr[p] = qfma(Cr, br, qfma(-Ci, bi, qfma(Dr, dr, -Di * di)));
+    m.di[p] = qfma(Cr, bi, qfma(Ci, br, qfma(Dr, di, Di * dr)));
+}
+
+/* ---- the element chain for two points ------------------------------------ */
+template <typename T, bool TRIG>
+__device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const int *__restrict__ s_coff,
+                                          const T *__restrict__ coef, int n_ops, const T (&w)[2], const T (&wi)[2],
+                                          Abcd2<T> &m)
+{
+    QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
+            m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
+    T w2[2];
+    QO_P2 w2[p] = w[p] * w[p];
+    for (int e = 0; e < n_ops; e++) {
+        const T *cf = coef + s_coff[e];
+        switch (s_op[e]) {
+        case OP_SER_LOSSY_L: {   /* Z = (R + jwL) / (1 - w^2 L Cp + j w R Cp) */
+            T L = cf[0], LCp = cf[1], R = cf[2], RCp = cf[3];
+            QO_P2 {
+                T dre = qfma(-w2[p], LCp, T(1)), dim = w[p] * RCp, xl = w[p] * L;
+                T r = qrcp(qfma(dre, dre, dim * dim));
+                T qr = dre * r, qi = -dim * r;
+                ser_cplx(m, p, qfma(R, qr, -xl * qi), qfma(R, qi, xl * qr));
+            }
+            break;
+        }
+        case OP_SHUNT_LOSSY_C: {  /* Y = 1 / (R + j(w Ls - 1/(wC))) */
+            T Ci = cf[0], Ls = cf[1], R = cf[2], R2 = cf[3];
+            QO_P2 {
+                T x = qfma(w[p], Ls, -wi[p] * Ci);
+                T r = qrcp(qfma(x, x, R2));
+                shunt_cplx(m, p, R * r, -x * r);
+            }
+            break;
+        }
+        case OP_SER_LOSSY_C: {
+            T Ci = cf[0], Ls = cf[1], R = cf[2];
+            QO_P2 ser_cplx(m, p, R, qfma(w[p], Ls, -wi[p] * Ci));
+            break;
+        }
+        case OP_SHUNT_LOSSY_L: {  /* Y = (1 - w^2 L Cp + j w R Cp) / (R + jwL) */
+            T L = cf[0], LCp = cf[1], R = cf[2], RCp = cf[3];
+            QO_P2 {
+                T dre = qfma(-w2[p], LCp, T(1)), dim = w[p] * RCp, xl = w[p] * L;
+                T r = qrcp(qfma(xl, xl, R * R));
+                T qr = R * r, qi = -xl * r;
+                shunt_cplx(m, p, qfma(dre, qr, -dim * qi), qfma(dre, qi, dim * qr));
+            }
+            break;
+        }
+        case OP_SER_R: { T r = cf[0]; QO_P2 {
+            m.br[p] = qfma(m.ar[p], r, m.br[p]); m.bi[p] = qfma(m.ai[p], r, m.bi[p]);
+            m.dr[p] = qfma(m.cr[p], r, m.dr[p]); m.di[p] = qfma(m.ci[p], r, m.di[p]); } break; }
+        case OP_SHUNT_G: { T g = cf[0]; QO_P2 {
+            m.ar[p] = qfma(m.br[p], g, m.ar[p]); m.ai[p] = qfma(m.bi[p], g, m.ai[p]);
+            m.cr[p] = qfma(m.dr[p], g, m.cr[p]); m.ci[p] = qfma(m.di[p], g, m.ci[p]); } break; }
+        case OP_SER_L: { T c0 = cf[0]; QO_P2 ser_imag(m, p, w[p] * c0); break; }
+        case OP_SER_C: { T c0 = cf[0]; QO_P2 ser_imag(m, p, -wi[p] * c0); break; }
+        case OP_SER_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
+        case OP_SHUNT_C: { T c0 = cf[0]; QO_P2 shunt_imag(m, p, w[p] * c0); break; }
+        case OP_SHUNT_L: { T c0 = cf[0]; QO_P2 shunt_imag(m, p, -wi[p] * c0); break; }
+        case OP_SHUNT_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
+        case OP_SER_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
+        case OP_SHUNT_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
+        default:
+            if (TRIG) {
+                if (s_op[e] == OP_TLINE) {
+                    T z0 = cf[0], y0 = cf[1], kt = cf[2];
+                    QO_P2 {
+                        T s, c;
+                        qsincos(kt * w[p], &s, &c);
+                        mul_full(m, p, c, T(0), T(0), z0 * s, T(0), s * y0, c, T(0));
+                    }
+                } else if (s_op[e] == OP_CPL) {
+                    /* even/odd-mode lines in a Zt system */
+                    T cE = cf[0], dE = cf[1], cO = cf[2], dO = cf[3], ke = cf[4], ko = cf[5], zt = cf[6], yt = cf[7];
+                    QO_P2 {
+                        T se, ce, so, co;
+                        qsincos(ke * w[p], &se, &ce);
+                        qsincos(ko * w[p], &so, &co);
+                        /* 1/den_e, 1/den_o ; den = 2c + j s cX */
+                        T er_ = ce + ce, ei_ = se * cE, or_ = co + co, oi_ = so * cO;
+                        T re = qrcp(qfma(er_, er_, ei_ * ei_)), ro = qrcp(qfma(or_, or_, oi_ * oi_));
+                        T ier = er_ * re, iei = -ei_ * re, ior = or_ * ro, ioi = -oi_ * ro;
+                        /* s21 = (Te+To)/2 = ie + io ; s11 = (j se dE ie + j so dO io)/2 */
+                        T s21r = ier + ior, s21i = iei + ioi;
+                        T ge = T(0.5) * se * dE, go = T(0.5) * so * dO;
+                        T s11r = -(ge * iei + go * ioi), s11i = ge * ier + go * ior;
+                        /* symmetric S -> ABCD at Zt */
+                        T q2r = s21r * s21r - s21i * s21i, q2i = T(2) * s21r * s21i;      /* s21^2 */
+                        T p2r = s11r * s11r - s11i * s11i, p2i = T(2) * s11r * s11i;      /* s11^2 */
+                        T dr_ = s21r + s21r, di_ = s21i + s21i;
+                        T rd = qrcp(qfma(dr_, dr_, di_ * di_));
+                        T idr = dr_ * rd, idi = -di_ * rd;                                /* 1/(2 s21) */
+                        T nar = T(1) - p2r + q2r, nai = q2i - p2i;                        /* 1 - s11^2 + s21^2 */
+                        T nbr = T(1) + s11r + s11r + p2r - q2r, nbi = s11i + s11i + p2i - q2i; /* (1+s11)^2 - s21^2 */
+                        T ncr = T(1) - s11r - s11r + p2r - q2r, nci = -s11i - s11i + p2i - q2i;
+                        T Ar = nar * idr - nai * idi, Ai = nar * idi + nai * idr;
+                        T Br = zt * (nbr * idr - nbi * idi), Bi = zt * (nbr * idi + nbi * idr);
+                        T Cr = yt * (ncr * idr - nci * idi), Ci2 = yt * (ncr * idi + nci * idr);
+                        mul_full(m, p, Ar, Ai, Br, Bi, Cr, Ci2, Ar, Ai);
+                    }
+                }
+            }
+            break;
+        }
+    }
+}
+
+/* ---- per-sample coefficient derivation (one lane per element) ------------- */
+template <typename T>
+__device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out)
+{
+    double p[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        p[k] = prog->nom[e][k];
+        int tv = prog->tvar[e][k];
+        if (tv >= 0) p[k] = qo_stream_apply(p[k], prog->ttol[e][k], x[tv], prog->tmode[e][k]);
+    }
+    switch (prog->opcode[e]) {
+    case OP_SER_R: out[0] = T(p[0]); break;
+    case OP_SHUNT_G: out[0] = T(1.0 / p[0]); break;
+    case OP_SER_L: out[0] = T(p[0]); break;
+    case OP_SER_C: out[0] = T(1.0 / p[0]); break;
+    case OP_SHUNT_C: out[0] = T(p[0]); break;
+    case OP_SHUNT_L: out[0] = T(1.0 / p[0]); break;
+    case OP_SER_LCS: case OP_SHUNT_LCS: out[0] = T(p[0]); out[1] = T(1.0 / p[1]); break;   /* (L, 1/C) */
+    case OP_SER_LCP: case OP_SHUNT_LCP: out[0] = T(p[1]); out[1] = T(1.0 / p[0]); break;   /* (C, 1/L) */
+    case OP_SER_LOSSY_L: case OP_SHUNT_LOSSY_L:
+        out[0] = T(p[0]); out[1] = T(p[0] * p[2]); out[2] = T(p[1]); out[3] = T(p[1] * p[2]); break;
+    case OP_SER_LOSSY_C: case OP_SHUNT_LOSSY_C:
+        out[0] = T(1.0 / p[0]); out[1] = T(p[2]); out[2] = T(p[1]); out[3] = T(p[1] * p[1]); break;
+    case OP_TLINE: out[0] = T(p[0]); out[1] = T(1.0 / p[0]); out[2] = T(p[1] / (360.0 * p[2])); break;
+    case OP_CPL: {
+        double a = p[0] / p[5], b = p[1] / p[5];
+        out[0] = T(a + 1.0 / a); out[1] = T(a - 1.0 / a); out[2] = T(b + 1.0 / b); out[3] = T(b - 1.0 / b);
+        out[4] = T(p[2] / (360.0 * p[4])); out[5] = T(p[3] / (360.0 * p[4])); out[6] = T(p[5]); out[7] = T(1.0 / p[5]);
+        break;
+    }
+    default: break;
+    }
+}
+
+struct QoPlanes { double2 *s11, *s21, *s12, *s22; };
+
+/* ---- the kernel ----------------------------------------------------------- */
+template <typename T, bool FULL_S, bool TRIG>
+__global__ void __launch_bounds__(QO_TPB, 2)
+qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::type *__restrict__ w2,
+                    const typename QoVec2<T>::type *__restrict__ wi2, const uchar2 *__restrict__ m2, int nf, int npairs,
+                    int pairs_per_chunk, int nchunks, unsigned long long sample_offset, unsigned long long nsamples,
+                    unsigned long long *__restrict__ counters, QoPlanes planes)
+{
+    __shared__ int s_op[QO_MAX_OPS], s_coff[QO_MAX_OPS];
+    __shared__ __align__(16) T s_coef[QO_WARPS][QO_MAX_COEF];
+    __shared__ double s_x[QO_WARPS][QO_MAX_VAR];
+    __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
+    __shared__ T s_thr[QO_NSPEC_MAX];
+    __shared__ int s_sk[QO_NSPEC_MAX];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_ops = prog->n_ops, n_var = prog->n_var, nspec = prog->nspec;
+    const int hist_spec = prog->hist_bins > 0 ? prog->hist_spec : -1;
+    const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
+    const bool need_s11 = FULL_S || prog->need_s11;
+    for (int i = threadIdx.x; i < n_ops; i += QO_TPB) { s_op[i] = prog->opcode[i]; s_coff[i] = prog->coff[i]; }
+    for (int i = threadIdx.x; i < ncnt; i += QO_TPB) s_cnt[i] = 0;
+    if (threadIdx.x < QO_NSPEC_MAX) { s_thr[threadIdx.x] = T(prog->spec_thr[threadIdx.x]); s_sk[threadIdx.x] = prog->spec_kind[threadIdx.x]; }
+    __syncthreads();
+
+    const T rs = T(prog->rs), rl = T(prog->rl), rsrl = T(prog->rsrl), k21 = T(prog->k21);
+    const int hist_kind = hist_spec >= 0 ? prog->spec_kind[hist_spec] : 0;
+    const unsigned long long seed = prog->seed;
+    const int dist = prog->dist;
+    T *coefw = s_coef[warp];
+    double *xw = s_x[warp];
+
+    const unsigned long long total_warps = (unsigned long long)gridDim.x * QO_WARPS;
+    const unsigned long long n_units = nsamples * (unsigned long long)nchunks;
+    for (unsigned long long u = (unsigned long long)blockIdx.x * QO_WARPS + warp; u < n_units; u += total_warps) {
+        const unsigned long long s = nchunks == 1 ? u : u / (unsigned long long)nchunks;
+        const int chunk = nchunks == 1 ? 0 : (int)(u - s * (unsigned long long)nchunks);
+        /* 1. this sample's random variables, one lane each (Philox is counter-based: no state) */
+        for (int v = lane; v < n_var; v += 32) xw[v] = qo_stream_variate(seed, sample_offset + s, (uint32_t)v, dist);
+        __syncwarp();
+        /* 2. perturbed + hoisted element coefficients -> shared table */
+        for (int e = lane; e < n_ops; e += 32) qo_derive<T>(prog, e, xw, coefw + s_coff[e]);
+        __syncwarp();
+
+        /* 3. frequency loop: two points per lane per iteration */
+        unsigned int fail = 0;
+        T wn = T(0), wd = T(1);
+        const int lo = chunk * pairs_per_chunk;
+        const int hi = min(npairs, lo + pairs_per_chunk);
+        int j = lo + lane;
+        typename QoVec2<T>::type wv, wiv;
+        uchar2 mv = make_uchar2(0, 0);
+        if (j < hi) { wv = w2[j]; wiv = wi2[j]; if (!FULL_S) mv = m2[j]; }
+        while (j < hi) {
+            const T w[2] = { wv.x, wv.y }, wi[2] = { wiv.x, wiv.y };
+            const unsigned int mk[2] = { mv.x, mv.y };
+            const int jn = j + 32;
+            if (jn < hi) { wv = w2[jn]; wiv = wi2[jn]; if (!FULL_S) mv = m2[jn]; }   /* prefetch next pair */
+            Abcd2<T> m;
+            qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, w, wi, m);
+            QO_P2 {
+                /* den = A Rl + B + C Rs Rl + D Rs ; n11 = A Rl + B - C Rs Rl - D Rs */
+                T den_r, den_i, n_r = T(0), n_i = T(0), num2 = T(0);
+                if (need_s11) {
+                    T pr = qfma(m.ar[p], rl, m.br[p]), pi_ = qfma(m.ai[p], rl, m.bi[p]);
+                    T qr = qfma(m.cr[p], rsrl, m.dr[p] * rs), qi = qfma(m.ci[p], rsrl, m.di[p] * rs);
+                    den_r = pr + qr; den_i = pi_ + qi; n_r = pr - qr; n_i = pi_ - qi;
+                    num2 = qfma(n_r, n_r, n_i * n_i);
+                } else {
+                    den_r = qfma(m.dr[p], rs, qfma(m.cr[p], rsrl, qfma(m.ar[p], rl, m.br[p])));
+                    den_i = qfma(m.di[p], rs, qfma(m.ci[p], rsrl, qfma(m.ai[p], rl, m.bi[p])));
+                }
+                const T den2 = qfma(den_r, den_r, den_i * den_i);
+                if (FULL_S) {
+                    const int k = 2 * j + p;
+                    if (k < nf) {
+                        const T r = qrcp(den2);
+                        const T ir = den_r * r, ii = -den_i * r;
+                        const size_t o = (size_t)s * (size_t)nf + (size_t)k;
+                        const T s21r = k21 * ir, s21i = k21 * ii;
+                        if (planes.s21) planes.s21[o] = make_double2((double)s21r, (double)s21i);
+                        if (planes.s11) planes.s11[o] = make_double2((double)(n_r * ir - n_i * ii), (double)(n_r * ii + n_i * ir));
+                        if (planes.s22) {
+                            /* n22 = -A Rl + B - C Rs Rl + D Rs */
+                            T ur = qfma(-m.ar[p], rl, m.br[p]), ui = qfma(-m.ai[p], rl, m.bi[p]);
+                            T vr = qfma(-m.cr[p], rsrl, m.dr[p] * rs), vi = qfma(-m.ci[p], rsrl, m.di[p] * rs);
+                            T xr = ur + vr, xi = ui + vi;
+                            planes.s22[o] = make_double2((double)(xr * ir - xi * ii), (double)(xr * ii + xi * ir));
+                        }
+                        /* S12 = S21 (AD - BC) with AD - BC == 1 exactly: all elements are reciprocal, and
+                         * the numerical determinant cancels catastrophically in a deep stop band */
+                        if (planes.s12) planes.s12[o] = make_double2((double)s21r, (double)s21i);
+                    }
+                } else {
+                    const unsigned int mb = mk[p];
+#pragma unroll
+                    for (int sp = 0; sp < QO_NSPEC_MAX; sp++) {
+                        if (sp < nspec) {
+                            const int sk = s_sk[sp];
+                            const T thr = s_thr[sp];
+                            bool bad = sk == SK_DEN2_MAX ? (den2 > thr) : sk == SK_DEN2_MIN ? (den2 < thr) : (num2 > thr * den2);
+                            if (bad && ((mb >> sp) & 1u)) fail |= 1u << sp;
+                        }
+                    }
+                    if (hist_spec >= 0 && ((mb >> hist_spec) & 1u)) {
+                        /* track the worst value as a ratio a/b ("larger is worse") without dividing */
+                        T a = hist_kind == SK_DEN2_MAX ? den2 : hist_kind == SK_DEN2_MIN ? T(1) : num2;
+                        T b = hist_kind == SK_DEN2_MAX ? T(1) : den2;
+                        if (a * wd > wn * b) { wn = a; wd = b; }
+                    }
+                }
+            }
+            j = jn;
+        }
+
+        if (!FULL_S) {
+            /* 4. warp-shuffle reduction, then block-level shared atomics */
+            fail = __reduce_or_sync(0xffffffffu, fail);
+            if (hist_spec >= 0) {
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    T on = __shfl_xor_sync(0xffffffffu, wn, off), od = __shfl_xor_sync(0xffffffffu, wd, off);
+                    if (on * wd > wn * od) { wn = on; wd = od; }
+                }
+            }
+            if (lane == 0) {
+                atomicAdd(&s_cnt[0], fail == 0 ? 1u : 0u);
+                atomicAdd(&s_cnt[1], 1u);
+                for (int sp = 0; sp < nspec; sp++)
+                    if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
+                if (hist_spec >= 0) {
+                    double ratio = (double)wn / (double)wd;
+                    double lin = hist_kind == SK_S11_MAX ? ratio
+                               : hist_kind == SK_DEN2_MAX ? (double)k21 * (double)k21 / ratio
+                                                          : (double)k21 * (double)k21 * ratio;
+                    double v = 10.0 * log10(lin);
+                    double xb = (v - prog->hist_lo) / (prog->hist_hi - prog->hist_lo) * (double)prog->hist_bins;
+                    long long b = (long long)floor(xb);
+                    if (!(xb >= 0.0)) b = 0;
+                    if (b >= prog->hist_bins) b = prog->hist_bins - 1;
+                    atomicAdd(&s_cnt[2 + nspec + (int)b], 1u);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (!FULL_S) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncnt; i += QO_TPB)
+            if (s_cnt[i]) atomicAdd(&counters[i], (unsigned long long)s_cnt[i]);
+    }
+}

@@ -1,0 +1,417 @@
+/*
+ * qo_ustrip.cuh -- generic kernel: every element kind including the Qucs 0.0.19
+ * microstrip models (MLIN / MCORN / MTEE / MOPEN on a SUBST), as used by
+ * util/pa-lpf-simulation/pa-lpf-simulation.sch:19-61.  One thread owns one
+ * (sample, frequency) point; the work per point is dominated by pow/exp/log/atan
+ * and complex cosh/sinh (MUFU + polynomial bound, not FMA bound), so the design
+ * goal here is fidelity to the Qucs models and not repeating the
+ * per-width line model: each thread keeps a small cache keyed by strip width.
+ */
+#pragma once
+#include "qo_device.cuh"
+#include "qo_stream.h"
+
+#define QO_G_TPB 128
+#define QO_G_SB 256          /* max samples per block tile */
+
+struct cd { double re, im; };
+__device__ __forceinline__ cd cmk(double a, double b) { cd z; z.re = a; z.im = b; return z; }
+__device__ __forceinline__ cd cadd(cd a, cd b) { return cmk(a.re + b.re, a.im + b.im); }
+__device__ __forceinline__ cd csub(cd a, cd b) { return cmk(a.re - b.re, a.im - b.im); }
+__device__ __forceinline__ cd cmul(cd a, cd b) { return cmk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re); }
+__device__ __forceinline__ cd cscale(cd a, double s) { return cmk(a.re * s, a.im * s); }
+__device__ __forceinline__ cd cinv(cd b) { double d = 1.0 / (b.re * b.re + b.im * b.im); return cmk(b.re * d, -b.im * d); }
+__device__ __forceinline__ cd cdiv(cd a, cd b) { return cmul(a, cinv(b)); }
+
+struct M2 { cd a, b, c, d; };
+__device__ __forceinline__ M2 m2_ident() { M2 m; m.a = cmk(1, 0); m.b = cmk(0, 0); m.c = cmk(0, 0); m.d = cmk(1, 0); return m; }
+__device__ __forceinline__ M2 m2_mul(const M2 &x, const M2 &y)
+{
+    M2 r;
+    r.a = cadd(cmul(x.a, y.a), cmul(x.b, y.c));
+    r.b = cadd(cmul(x.a, y.b), cmul(x.b, y.d));
+    r.c = cadd(cmul(x.c, y.a), cmul(x.d, y.c));
+    r.d = cadd(cmul(x.c, y.b), cmul(x.d, y.d));
+    return r;
+}
+__device__ __forceinline__ void m2_series(M2 &m, cd z) { m.b = cadd(m.b, cmul(m.a, z)); m.d = cadd(m.d, cmul(m.c, z)); }
+__device__ __forceinline__ void m2_shunt(M2 &m, cd y) { m.a = cadd(m.a, cmul(m.b, y)); m.c = cadd(m.c, cmul(m.d, y)); }
+
+#define QO_PI 3.14159265358979323846
+#define QO_C0 299792458.0
+#define QO_MU0 12.566370614e-7
+#define QO_ZF0 376.73031346958504364963
+
+struct MsSub { double er, h, t, tand, rho, D; };
+
+/* Hammerstad-Jensen quasi-static line (Qucs "Hammerstad"), SURVEY A.1 */
+__device__ __noinline__ void ms_quasi(double W, const MsSub &s, double &Z, double &E, double &Weff)
+{
+    const double u = W / s.h;
+    double du1 = 0.0, dur = 0.0;
+    if (s.t > 0.0) {
+        const double tau = s.t / s.h;
+        const double th = tanh(sqrt(6.517 * u));
+        du1 = (tau / QO_PI) * log(1.0 + 4.0 * 2.7182818284590452354 * th * th / tau);
+        dur = 0.5 * du1 * (1.0 + 1.0 / cosh(sqrt(s.er - 1.0)));
+    }
+    const double uu[2] = { u + dur, u + du1 };
+    double zh[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const double x = uu[i];
+        const double F = 6.0 + (2.0 * QO_PI - 6.0) * exp(-pow(30.666 / x, 0.7528));
+        zh[i] = QO_ZF0 / (2.0 * QO_PI) * log(F / x + sqrt(1.0 + 4.0 / (x * x)));
+    }
+    const double x = uu[0], x2 = x * x, x4 = x2 * x2;
+    const double a = 1.0 + log((x4 + x2 / 2704.0) / (x4 + 0.432)) / 49.0 + log(1.0 + (x / 18.1) * (x / 18.1) * (x / 18.1)) / 18.7;
+    const double b = 0.564 * pow((s.er - 0.9) / (s.er + 3.0), 0.053);
+    const double eps = 0.5 * (s.er + 1.0) + 0.5 * (s.er - 1.0) * pow(1.0 + 10.0 / x, -a * b);
+    const double ratio = zh[1] / zh[0];
+    Z = zh[0] / sqrt(eps);
+    E = eps * ratio * ratio;
+    Weff = uu[0] * s.h;
+}
+
+/* Kirschning-Jansen dispersion (Qucs "Kirschning"), SURVEY A.2 */
+__device__ __noinline__ void ms_disp(double W, const MsSub &s, double Z, double E, double f, double &Zf, double &Ef)
+{
+    const double er = s.er, u = W / s.h, fn = f * s.h * 1e-6;
+    const double P1 = 0.27488 + (0.6315 + 0.525 / pow(1.0 + 0.0157 * fn, 20.0)) * u - 0.065683 * exp(-8.7513 * u);
+    const double P2 = 0.33622 * (1.0 - exp(-0.03442 * er));
+    const double P3 = 0.0363 * exp(-4.6 * u) * (1.0 - exp(-pow(fn / 38.7, 4.97)));
+    const double P4 = 1.0 + 2.751 * (1.0 - exp(-pow(er / 15.916, 8.0)));
+    const double Pf = P1 * P2 * pow((P3 * P4 + 0.1844) * fn, 1.5763);
+    Ef = er - (er - E) / (1.0 + Pf);
+    const double R1 = 0.03891 * pow(er, 1.4);
+    const double R2 = 0.267 * pow(u, 7.0);
+    const double R3 = 4.766 * exp(-3.228 * pow(u, 0.641));
+    const double R4 = 0.016 + pow(0.0514 * er, 4.524);
+    const double R5 = pow(fn / 28.843, 12.0);
+    const double R6 = 22.20 * pow(u, 1.92);
+    const double R7 = 1.206 - 0.3144 * exp(-R1) * (1.0 - exp(-R2));
+    const double R8 = 1.0 + 1.275 * (1.0 - exp(-0.004625 * R3 * pow(er, 1.674) * pow(fn / 18.365, 2.745)));
+    const double e6 = pow(er - 1.0, 6.0);
+    const double R9 = 5.086 * R4 * R5 / (0.3838 + 0.386 * R4) * exp(-R6) / (1.0 + 1.2992 * R5) * e6 / (1.0 + 10.0 * e6);
+    const double R10 = 0.00044 * pow(er, 2.136) + 0.0184;
+    const double t6 = pow(fn / 19.47, 6.0);
+    const double R11 = t6 / (1.0 + 0.0962 * t6);
+    const double R12 = 1.0 / (1.0 + 0.00245 * u * u);
+    const double R13 = 0.9408 * pow(Ef, R8) - 0.9603;
+    const double R14 = (0.9408 - R9) * pow(E, R8) - 0.9603;
+    const double R15 = 0.707 * R10 * pow(fn / 12.3, 1.097);
+    const double R16 = 1.0 + 0.0503 * er * er * R11 * (1.0 - exp(-pow(u / 15.0, 6.0)));
+    const double R17 = R7 * (1.0 - 1.1241 * R12 / R16 * exp(-0.026 * pow(fn, 1.15656) - R15));
+    Zf = Z * pow(R13 / R14, R17);
+}
+
+/* per-thread cache of the line model, keyed by (perturbed) strip width */
+struct MsLine { double W, Z, E, Weff, Zf, Ef, alpha; };
+struct MsCache {
+    MsLine e[4];
+    int n, next;
+};
+
+__device__ __forceinline__ const MsLine &ms_line(MsCache &c, double W, const MsSub &s, double f)
+{
+    for (int i = 0; i < c.n; i++)
+        if (c.e[i].W == W) return c.e[i];
+    int slot = c.n < 4 ? c.n++ : (c.next = (c.next + 1) & 3);
+    MsLine &l = c.e[slot];
+    l.W = W;
+    ms_quasi(W, s, l.Z, l.E, l.Weff);
+    ms_disp(W, s, l.Z, l.E, f, l.Zf, l.Ef);
+    /* Hammerstad loss with the STATIC Z and E */
+    const double Rs = sqrt(QO_PI * f * QO_MU0 * s.rho);
+    const double dd = s.D * Rs / s.rho;                 /* D / skin depth */
+    const double Ki = exp(-1.2 * pow(l.Z / QO_ZF0, 0.7));
+    const double Kr = 1.0 + (2.0 / QO_PI) * atan(1.4 * dd * dd);
+    const double ac = Rs / (l.Z * W) * Ki * Kr;
+    const double ad = QO_PI * s.er / (s.er - 1.0) * (l.E - 1.0) / sqrt(l.E) * s.tand * f / QO_C0;
+    l.alpha = ac + ad;
+    return l;
+}
+
+/* MLIN(W, L): [cosh gL, Zf sinh gL; sinh gL / Zf, cosh gL]; L may be < 0 */
+__device__ __forceinline__ M2 ms_mlin(MsCache &c, double W, double L, const MsSub &s, double f)
+{
+    const MsLine &l = ms_line(c, W, s, f);
+    const double a = l.alpha * L, b = 2.0 * QO_PI * f * sqrt(l.Ef) / QO_C0 * L;
+    double sb, cb;
+    sincos(b, &sb, &cb);
+    const double ch = cosh(a), sh = sinh(a);
+    M2 m;
+    m.a = cmk(ch * cb, sh * sb);
+    m.d = m.a;
+    const cd shc = cmk(sh * cb, ch * sb);
+    m.b = cscale(shc, l.Zf);
+    m.c = cscale(shc, 1.0 / l.Zf);
+    return m;
+}
+
+/* MCORN(W): Kirschning-Jansen-Koster bend as a T network, SURVEY A.5 */
+__device__ __forceinline__ M2 ms_mcorn(double W, const MsSub &s, double f)
+{
+    const double wh = W / s.h;
+    const double CpF = W * ((10.35 * s.er + 2.5) * wh + 2.6 * s.er + 5.64);
+    const double LnH = 220.0 * s.h * (1.0 - 1.35 * exp(-0.18 * pow(wh, 1.39)));
+    const double x21 = -0.5e12 / (QO_PI * f * CpF);          /* z21 = j x21 */
+    const double x11 = 2e-9 * QO_PI * f * LnH + x21;          /* z11 = j x11 */
+    M2 m;
+    m.a = cmk(x11 / x21, 0.0);
+    m.d = m.a;
+    m.b = cmk(0.0, (x11 * x11 - x21 * x21) / x21);            /* (z11^2 - z21^2)/z21 = j (x11^2-x21^2)/x21 */
+    m.c = cmk(0.0, -1.0 / x21);
+    return m;
+}
+
+/* MOPEN(W): Kirschning open-end extension, dispersion taken at Weff; returns B of Y = jB */
+__device__ __forceinline__ double ms_mopen(double W, const MsSub &s, double f)
+{
+    double Z, E, Weff, Zf, Ef;
+    ms_quasi(W, s, Z, E, Weff);
+    ms_disp(Weff, s, Z, E, f, Zf, Ef);
+    const double w = W / s.h, er = s.er;
+    const double Q6 = pow(Ef, 0.81), Q7 = pow(w, 0.8544);
+    const double Q1 = 0.434907 * (Q6 + 0.26) / (Q6 - 0.189) * (Q7 + 0.236) / (Q7 + 0.87);
+    const double Q2 = pow(w, 0.371) / (2.358 * er + 1.0) + 1.0;
+    const double Q3 = atan(0.084 * pow(w, 1.9413 / Q2)) * 0.5274 / pow(Ef, 0.9236) + 1.0;
+    const double Q4 = 0.0377 * (6.0 - 5.0 * exp(0.036 * (1.0 - er))) * atan(0.067 * pow(w, 1.456)) + 1.0;
+    const double Q5 = 1.0 - 0.218 * exp(-7.5 * w);
+    const double dl = Q1 * Q3 * Q5 / Q4 * s.h;
+    return 2.0 * QO_PI * f * dl * sqrt(Ef) / (QO_C0 * Zf);
+}
+
+struct MsTee { double La, Lb, L2, Ta2, Tb2, Bt; };
+/* MTEE(Wa, Wb, W2): Hammerstad T junction, SURVEY A.5 */
+__device__ __forceinline__ void ms_mtee(MsCache &c, double Wa, double Wb, double W2, const MsSub &s, double f, MsTee &o)
+{
+    const MsLine la = ms_line(c, Wa, s, f);
+    const MsLine lb = ms_line(c, Wb, s, f);
+    const MsLine l2 = ms_line(c, W2, s, f);
+    const double h = s.h, er = s.er;
+    const double Da = QO_ZF0 / la.Zf * h / sqrt(la.Ef), Db = QO_ZF0 / lb.Zf * h / sqrt(lb.Ef), D2 = QO_ZF0 / l2.Zf * h / sqrt(l2.Ef);
+    const double fpa = 0.4e6 * la.Zf / h, fpb = 0.4e6 * lb.Zf / h;
+    const double lda = QO_C0 / sqrt(la.Ef) / f, ldb = QO_C0 / sqrt(lb.Ef) / f;
+    const double ra = la.Zf / l2.Zf, rb = lb.Zf / l2.Zf;
+    const double fa2 = (f / fpa) * (f / fpa), fb2 = (f / fpb) * (f / fpb);
+    const double da = 0.055 * D2 * ra * (1.0 - 2.0 * ra * fa2);
+    const double db = 0.055 * D2 * rb * (1.0 - 2.0 * rb * fb2);
+    o.La = 0.5 * W2 - da;
+    o.Lb = 0.5 * W2 - db;
+    const double r = sqrt(la.Zf * lb.Zf) / l2.Zf;
+    const double q = f * f / (fpa * fpb);
+    const double lr = log(r);
+    const double d2 = sqrt(Da * Db) * (0.5 - r * (0.05 + 0.7 * exp(-1.6 * r) + 0.25 * r * q - 0.17 * lr));
+    o.L2 = 0.5 * fmax(Wa, Wb) - d2;
+    double ta = 1.0 - QO_PI * fa2 * (ra * ra / 12.0 + (0.5 - d2 / Da) * (0.5 - d2 / Da));
+    double tb = 1.0 - QO_PI * fb2 * (rb * rb / 12.0 + (0.5 - d2 / Db) * (0.5 - d2 / Db));
+    ta = fmax(ta, 1e-18);
+    tb = fmax(tb, 1e-18);
+    o.Ta2 = ta; o.Tb2 = tb;
+    o.Bt = 5.5 * sqrt(Da * Db / (lda * ldb)) * (er + 2.0) / er / l2.Zf / sqrt(ta * tb) * sqrt(da * db) / D2 *
+           (1.0 + 0.9 * lr + 4.5 * r * q - 4.4 * exp(-1.3 * r) - 20.0 * (l2.Zf / QO_ZF0) * (l2.Zf / QO_ZF0));
+}
+
+/* ideal coupled line, through path with the far ports in Zt */
+__device__ __forceinline__ M2 g_cpl(const double *p, double f)
+{
+    const double zt = p[5];
+    const double te = p[2] / 360.0 * (2.0 * QO_PI * f) / p[4], to = p[3] / 360.0 * (2.0 * QO_PI * f) / p[4];
+    double se, ce, so, co;
+    sincos(te, &se, &ce);
+    sincos(to, &so, &co);
+    const double ae = p[0] / zt, ao = p[1] / zt;
+    const cd ie = cinv(cmk(2.0 * ce, se * (ae + 1.0 / ae))), io = cinv(cmk(2.0 * co, so * (ao + 1.0 / ao)));
+    const cd s21 = cadd(ie, io);
+    const cd s11 = cscale(cadd(cmul(cmk(0.0, se * (ae - 1.0 / ae)), ie), cmul(cmk(0.0, so * (ao - 1.0 / ao)), io)), 0.5);
+    const cd one = cmk(1.0, 0.0), pp = cadd(one, s11), mm = csub(one, s11), q2 = cmul(s21, s21);
+    const cd i2 = cinv(cscale(s21, 2.0));
+    M2 r;
+    r.a = cmul(cadd(cmul(pp, mm), q2), i2);
+    r.d = r.a;
+    r.b = cscale(cmul(csub(cmul(pp, pp), q2), i2), zt);
+    r.c = cscale(cmul(csub(cmul(mm, mm), q2), i2), 1.0 / zt);
+    return r;
+}
+
+/* the full cascade at one frequency for one sample's variates x[] */
+__device__ __noinline__ void qo_generic_abcd(const DevProg *__restrict__ prog, const double *x, double f, M2 &out)
+{
+    const double w = 2.0 * QO_PI * f;
+    M2 M = m2_ident(), Mmain = m2_ident();
+    MsSub sub = { 1.0, 1.0, 0.0, 0.0, 0.0, 0.0 };
+    MsCache cache;
+    cache.n = 0; cache.next = 3;
+    MsTee tee = { 0, 0, 0, 1, 1, 0 };
+    double teeWa = 0.0, teeWb = 0.0;
+    const int n_ops = prog->n_ops;
+    for (int e = 0; e < n_ops; e++) {
+        double p[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            p[k] = prog->nom[e][k];
+            const int tv = prog->tvar[e][k];
+            if (tv >= 0) p[k] = qo_stream_apply(p[k], prog->ttol[e][k], x[tv], prog->tmode[e][k]);
+        }
+        switch (prog->kind[e]) {
+        case 1: m2_series(M, cmk(p[0], 0.0)); break;
+        case 2: m2_shunt(M, cmk(1.0 / p[0], 0.0)); break;
+        case 3: case 4: {   /* inductor with ESR and parallel Cp */
+            const cd z = cdiv(cmk(p[1], w * p[0]), cmk(1.0 - w * w * p[0] * p[2], w * p[1] * p[2]));
+            if (prog->kind[e] == 3) m2_series(M, z); else m2_shunt(M, cinv(z));
+            break;
+        }
+        case 5: case 6: {   /* capacitor with ESR and ESL */
+            const cd z = cmk(p[1], w * p[2] - 1.0 / (w * p[0]));
+            if (prog->kind[e] == 5) m2_series(M, z); else m2_shunt(M, cinv(z));
+            break;
+        }
+        case 7: m2_series(M, cmk(0.0, w * p[0] - 1.0 / (w * p[1]))); break;
+        case 8: m2_series(M, cmk(0.0, -1.0 / (w * p[1] - 1.0 / (w * p[0])))); break;
+        case 9: m2_shunt(M, cmk(0.0, -1.0 / (w * p[0] - 1.0 / (w * p[1])))); break;
+        case 10: m2_shunt(M, cmk(0.0, w * p[1] - 1.0 / (w * p[0]))); break;
+        case 11: {
+            double s, c;
+            sincos(p[1] / 360.0 * w / p[2], &s, &c);
+            M2 t;
+            t.a = cmk(c, 0.0); t.d = t.a; t.b = cmk(0.0, p[0] * s); t.c = cmk(0.0, s / p[0]);
+            M = m2_mul(M, t);
+            break;
+        }
+        case 12: M = m2_mul(M, g_cpl(p, f)); break;
+        case 13:
+            sub.er = p[0]; sub.h = p[1]; sub.t = p[2]; sub.tand = p[3]; sub.rho = p[4]; sub.D = p[5];
+            cache.n = 0;
+            break;
+        case 14: M = m2_mul(M, ms_mlin(cache, p[0], p[1], sub, f)); break;
+        case 15: M = m2_mul(M, ms_mcorn(p[0], sub, f)); break;
+        case 16:
+            ms_mtee(cache, p[0], p[1], p[2], sub, f, tee);
+            teeWa = p[0]; teeWb = p[1];
+            Mmain = M;
+            M = ms_mlin(cache, p[2], tee.L2, sub, f);     /* arm 2, junction outward */
+            break;
+        case 17: {
+            const cd yo = cmk(0.0, ms_mopen(p[0], sub, f));
+            const cd yin = cdiv(cadd(M.c, cmul(M.d, yo)), cadd(M.a, cmul(M.b, yo)));
+            const double sa = sqrt(tee.Ta2), sb = sqrt(tee.Tb2);
+            M = m2_mul(Mmain, ms_mlin(cache, teeWa, tee.La, sub, f));
+            /* ideal transformers around the junction node and the shunt j Bt + Y_stub */
+            M.a = cscale(M.a, 1.0 / sa); M.c = cscale(M.c, 1.0 / sa);
+            M.b = cscale(M.b, sa); M.d = cscale(M.d, sa);
+            m2_shunt(M, cmk(yin.re, yin.im + tee.Bt));
+            M.a = cscale(M.a, sb); M.c = cscale(M.c, sb);
+            M.b = cscale(M.b, 1.0 / sb); M.d = cscale(M.d, 1.0 / sb);
+            M = m2_mul(M, ms_mlin(cache, teeWb, tee.Lb, sub, f));
+            break;
+        }
+        default: break;
+        }
+    }
+    out = M;
+}
+
+__device__ __forceinline__ void qo_generic_s(const DevProg *__restrict__ prog, const M2 &M, cd &s11, cd &s21, cd &s12, cd &s22)
+{
+    const double rs = prog->rs, rl = prog->rl;
+    const cd arl = cscale(M.a, rl), crr = cscale(M.c, rs * rl), drs = cscale(M.d, rs);
+    const cd p = cadd(arl, M.b), q = cadd(crr, drs);
+    const cd iden = cinv(cadd(p, q));
+    s11 = cmul(csub(p, q), iden);
+    s21 = cscale(iden, prog->k21);
+    s22 = cmul(csub(cadd(M.b, drs), cadd(arl, crr)), iden);
+    s12 = s21;   /* reciprocal cascade: AD - BC == 1 (see qo_lumped.cuh) */
+}
+
+__device__ __forceinline__ unsigned long long d2key(double v) { return (unsigned long long)__double_as_longlong(v); }
+
+/* tile = (sample tile, frequency chunk).  REDUCE mode requires n_fchunks == 1. */
+__global__ void __launch_bounds__(QO_G_TPB)
+qo_mc_generic_kernel(const DevProg *__restrict__ prog, const double *__restrict__ fgrid, const unsigned char *__restrict__ mask,
+                     int nf, int f_chunk, int n_fchunks, int sb, unsigned long long sample_offset, unsigned long long nsamples,
+                     unsigned long long *__restrict__ counters, QoPlanes planes, int full_s)
+{
+    __shared__ unsigned int s_fail[QO_G_SB];
+    __shared__ unsigned long long s_worst[QO_G_SB];
+    __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
+    const int nspec = prog->nspec, n_var = prog->n_var;
+    const int hist_spec = prog->hist_bins > 0 ? prog->hist_spec : -1;
+    const int hist_kind = hist_spec >= 0 ? prog->spec_user_kind[hist_spec] : 0;
+    const bool hist_min = hist_kind == 1;     /* QO_SPEC_S21_MIN_DB: worst = smallest */
+    const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
+    for (int i = threadIdx.x; i < ncnt; i += QO_G_TPB) s_cnt[i] = 0;
+
+    const unsigned long long n_stiles = (nsamples + (unsigned long long)sb - 1) / (unsigned long long)sb;
+    const unsigned long long n_tiles = n_stiles * (unsigned long long)n_fchunks;
+    for (unsigned long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const unsigned long long st = tile / (unsigned long long)n_fchunks;
+        const int fc = (int)(tile - st * (unsigned long long)n_fchunks);
+        const unsigned long long s0 = st * (unsigned long long)sb;
+        const int ns = (int)min((unsigned long long)sb, nsamples - s0);
+        const int k0 = fc * f_chunk, nk = min(f_chunk, nf - k0);
+        __syncthreads();
+        if (!full_s)
+            for (int i = threadIdx.x; i < ns; i += QO_G_TPB) { s_fail[i] = 0; s_worst[i] = hist_min ? ~0ull : 0ull; }
+        __syncthreads();
+        const int items = ns * nk;
+        for (int it = threadIdx.x; it < items; it += QO_G_TPB) {
+            const int sl = it / nk, k = k0 + (it - sl * nk);
+            const unsigned long long s = s0 + (unsigned long long)sl;
+            double x[QO_MAX_VAR];
+            for (int v = 0; v < n_var; v++) x[v] = qo_stream_variate(prog->seed, sample_offset + s, (uint32_t)v, prog->dist);
+            const double f = fgrid[k];
+            M2 M;
+            qo_generic_abcd(prog, x, f, M);
+            cd s11, s21, s12, s22;
+            qo_generic_s(prog, M, s11, s21, s12, s22);
+            if (full_s) {
+                const size_t o = (size_t)s * (size_t)nf + (size_t)k;
+                if (planes.s11) planes.s11[o] = make_double2(s11.re, s11.im);
+                if (planes.s21) planes.s21[o] = make_double2(s21.re, s21.im);
+                if (planes.s12) planes.s12[o] = make_double2(s12.re, s12.im);
+                if (planes.s22) planes.s22[o] = make_double2(s22.re, s22.im);
+            } else {
+                const unsigned int mb = mask[k];
+                const double p21 = s21.re * s21.re + s21.im * s21.im, p11 = s11.re * s11.re + s11.im * s11.im;
+                unsigned int fail = 0;
+                for (int sp = 0; sp < nspec; sp++) {
+                    if (!((mb >> sp) & 1u)) continue;
+                    const int uk = prog->spec_user_kind[sp];
+                    const double lim = prog->spec_thr[sp];      /* linear power limit in this kernel */
+                    const bool bad = uk == 1 ? (p21 < lim) : uk == 2 ? (p21 > lim) : (p11 > lim);
+                    if (bad) fail |= 1u << sp;
+                    if (sp == hist_spec) {
+                        const double v = uk == 3 ? p11 : p21;
+                        if (hist_min) atomicMin(&s_worst[sl], d2key(v)); else atomicMax(&s_worst[sl], d2key(v));
+                    }
+                }
+                if (fail) atomicOr(&s_fail[sl], fail);
+            }
+        }
+        if (!full_s) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < ns; i += QO_G_TPB) {
+                const unsigned int fail = s_fail[i];
+                atomicAdd(&s_cnt[0], fail == 0 ? 1u : 0u);
+                atomicAdd(&s_cnt[1], 1u);
+                for (int sp = 0; sp < nspec; sp++)
+                    if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
+                if (hist_spec >= 0) {
+                    const double lin = __longlong_as_double((long long)s_worst[i]);
+                    const double v = 10.0 * log10(lin);
+                    const double xb = (v - prog->hist_lo) / (prog->hist_hi - prog->hist_lo) * (double)prog->hist_bins;
+                    long long b = (long long)floor(xb);
+                    if (!(xb >= 0.0)) b = 0;
+                    if (b >= prog->hist_bins) b = prog->hist_bins - 1;
+                    atomicAdd(&s_cnt[2 + nspec + (int)b], 1u);
+                }
+            }
+        }
+    }
+    if (!full_s) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < ncnt; i += QO_G_TPB)
+            if (s_cnt[i]) atomicAdd(&counters[i], (unsigned long long)s_cnt[i]);
+    }
+}

@@ -1,0 +1,232 @@
+"""Host side of the product (loader, synthesis, grids, stream twins, C-ABI surface) -- CPU only.
+No compute entry point is exercised here beyond checking that it refuses to run without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE, ROOT
+
+have_ref = os.path.isdir(REFERENCE)
+
+
+def test_abi_exports_every_declared_symbol(Q):
+    """The shared library loads and exports every function include/qo100net.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "qo100net.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(qo_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 38
+    lib = ctypes.CDLL(Q.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(Q.EXPORTS), declared ^ set(Q.EXPORTS)
+
+
+def test_no_torch_types_or_oracle_in_product(Q):
+    """The product never links, imports or calls the oracle (it must fail loudly instead of falling back)."""
+    import subprocess
+    out = subprocess.run(["ldd", Q.LIB_PATH], capture_output=True, text=True).stdout
+    assert "qo100ref" not in out and "torch" not in out
+    for dirpath, _d, files in os.walk(os.path.join(ROOT, "qo-100-tools_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".c", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, fn), errors="replace").read()
+                assert "refbind" not in src and "qo100ref" not in src, fn
+
+
+@pytest.mark.skipif(__import__("torch").cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_compute_refuses_without_gpu(Q):
+    with pytest.raises(Q.QoError) as ei:
+        Q.Context(device=0)
+    assert ei.value.status == Q.ERR_NO_DEVICE
+    with pytest.raises(Q.QoError) as ei:
+        Q.Context(ngpus=2)
+    assert ei.value.status == Q.ERR_NO_DEVICE
+
+
+def test_golden_networks_match_survey_tables(golden_nets):
+    """Element lists the loader produced from the reference files == SURVEY §2 tables."""
+    n = golden_nets["util/if-bandpass-filter/schematic.svg"]
+    assert (n["rs"], n["rl"]) == (50.0, 50.0)
+    assert [e[0] for e in n["elements"]] == [7, 10, 7]
+    assert n["elements"][0][1][:2] == [33e-9, 4.7e-12] and n["elements"][1][1][:2] == [4.7e-9, 33e-12]
+    n = golden_nets["util/gpsdo-ouput-filters/10M/schematic.svg"]
+    assert (n["rs"], n["rl"]) == (100.0, 50.0)
+    assert [e[1][0] for e in n["elements"]] == [430e-12, 1.3e-6, 620e-12, 1.3e-6, 560e-12, 1.1e-6, 240e-12]
+    assert [e[0] for e in n["elements"]] == [6, 3, 6, 3, 6, 3, 6]
+    n = golden_nets["docs/gpsdo-filters/15M.svg"]
+    assert [e[0] for e in n["elements"]] == [3, 9, 3, 9, 3, 9, 3]
+    assert n["elements"][1][1][:2] == [82e-9, 270e-12]
+    n = golden_nets["docs/upconverter/upconverter-lol-filter.svg"]
+    assert [e[0] for e in n["elements"]] == [4, 8, 4, 8, 4, 8, 4, 5]
+    assert n["elements"][1][1][:2] == [12e-9, 1.2e-12] and n["elements"][7][1][0] == 1.5e-12
+    assert "2.100 GHz" in n["title"]
+    n = golden_nets["util/pa-lpf-simulation/pa-lpf-simulation.sch"]
+    kinds = [e[0] for e in n["elements"]]
+    assert kinds.count(14) == 19 and kinds.count(15) == 12 and kinds.count(16) == 2 and kinds.count(17) == 2 and kinds[0] == 13
+    assert n["elements"][0][1] == [4.5, 0.6e-3, 34.79e-6, 0.045, 1.68e-8, 0.15e-6]
+    assert n["sweep"] == ["lin", 1e7, 1e10, 5000]
+    # SURVEY App. A.6 cascade: main-line lengths in mm, in order
+    main, side, in_side = [], [], False
+    for k, p in n["elements"][1:]:
+        if k == 16:
+            in_side = True
+        elif k == 17:
+            in_side = False
+        elif k == 14:
+            (side if in_side else main).append(round(p[1] * 1e3, 5))
+    assert main == [1.65, 1.40415, 1.65, 1.40415, 0.95, 0.95, 2.5, 3.45, 1.55, 0.95, 0.95, 0.8, 1.6, 1.75, 5.95]
+    assert side == [0.15, 4.35, 2.5, 3.0]
+    t = golden_nets["util/directional-couplers/dir_cpl_2.4g_20dB.trc"]
+    assert (t["z0e"], t["z0o"], t["ang"], t["f0"]) == (55.2771, 45.2267, 95.4225, 2.4e9)
+    t = golden_nets["util/directional-couplers/dir_cpl_2.4g_35dB_pa_250W.trc"]
+    assert (t["ht"], t["f0"], t["s"]) == (15e-3, 2.4e9, 4e-3)
+
+
+@pytest.mark.skipif(not have_ref, reason="reference tree not mounted (GPU box)")
+def test_loader_reads_every_reference_file(Q, golden_nets):
+    for key, g in golden_nets.items():
+        path = os.path.join(REFERENCE, key)
+        if key.endswith(".svg"):
+            n = Q.Net.from_rftools_svg(path)
+        elif key.endswith(".sch"):
+            n = Q.Net.from_qucs_sch(path)
+            assert list(Q.qucs_sch_sweep(path)) == g["sweep"]
+        else:
+            assert Q.load_trc(path) == g
+            continue
+        assert n.terminations == (g["rs"], g["rl"])
+        assert [[k, p] for k, p in n.elements] == g["elements"]
+
+
+def test_workload_networks_equal_loaded_ones(Q, W, golden_nets):
+    """The hard-coded BASELINE workloads are the reference files' element lists."""
+    assert [[k, p] for k, p in W.if_bpf_net().elements] == golden_nets["util/if-bandpass-filter/schematic.svg"]["elements"]
+    assert [[k, p] for k, p in W.pa_lpf_net().elements] == golden_nets["util/pa-lpf-simulation/pa-lpf-simulation.sch"]["elements"]
+    bank = {name: net for name, net, _fc in W.gpsdo_bank()}
+    assert [[k, p] for k, p in bank["10M"].elements] == golden_nets["util/gpsdo-ouput-filters/10M/schematic.svg"]["elements"]
+    for nm in ("15M", "40M", "60M"):
+        assert [[k, p] for k, p in bank[nm].elements] == golden_nets["docs/gpsdo-filters/%s.svg" % nm]["elements"]
+
+
+def test_loader_errors(Q, tmp_path):
+    with pytest.raises(Q.QoError) as ei:
+        Q.Net.from_rftools_svg(str(tmp_path / "missing.svg"))
+    assert ei.value.status == Q.ERR_IO
+    p = tmp_path / "bad.svg"
+    p.write_text("<svg><defs></defs><use xlink:href=\"#q_branch_weird\"/></svg>")
+    with pytest.raises(Q.QoError) as ei:
+        Q.Net.from_rftools_svg(str(p))
+    assert ei.value.status == Q.ERR_UNSUPPORTED
+    p.write_text("<svg>nothing</svg>")
+    with pytest.raises(Q.QoError) as ei:
+        Q.Net.from_rftools_svg(str(p))
+    assert ei.value.status == Q.ERR_PARSE
+    p = tmp_path / "x.sch"
+    p.write_text("hello")
+    with pytest.raises(Q.QoError) as ei:
+        Q.Net.from_qucs_sch(str(p))
+    assert ei.value.status == Q.ERR_PARSE
+    p = tmp_path / "x.trc"
+    p.write_text("<Microstrip>\n</Microstrip>\n")
+    with pytest.raises(Q.QoError):
+        Q.load_trc(str(p))
+    with pytest.raises(Q.QoError):
+        Q.Net.from_elements([(99, [1.0])])
+    with pytest.raises(Q.QoError):
+        Q.Net.from_elements([(Q.MLIN, [1e-3, 1e-3])])              # microstrip without SUBST
+    with pytest.raises(Q.QoError):
+        Q.Net.from_elements([(Q.SUBST, [4.5, 1e-3, 0, 0, 0, 0]), (Q.MTEE, [1e-3] * 3)])   # side arm not closed
+    with pytest.raises(Q.QoError):
+        Q.Net.cheby_lpf(10, 0.1, 1e6)                               # even order needs unequal terminations
+
+
+def test_small_svg_and_sch_round_trip(Q, tmp_path):
+    """A minimal hand-written rf-tools export and Qucs schematic (the formats, not the reference files)."""
+    svg = ('<svg><defs><symbol id="x"><use xlink:href="#l_branch_series"/></symbol></defs>'
+           '<use xlink:href="#s_branch_voltage" x="0"/><use xlink:href="#r_branch_series"/>'
+           '<use xlink:href="#c_branch_shunt"/><use xlink:href="#lc_branch_series_parallel"/>'
+           '<use xlink:href="#l_branch_shunt_half"/><use xlink:href="#r_branch_shunt"/>'
+           '<text x="1">RS</text><text>75.00 Ω</text><text>C1</text><text>10.00 pF</text>'
+           '<text>C2</text><text>1.500 nF</text><text>L2</text><text>2.200 uH</text>'
+           '<text>L3</text><text>47.00 mH</text><text>RL</text><text>1.000 kΩ</text>'
+           '<text>rf-tools.com | today</text><text>Demo filter</text></svg>')
+    p = tmp_path / "t.svg"
+    p.write_text(svg, encoding="utf-8")
+    n = Q.Net.from_rftools_svg(str(p))
+    assert n.terminations == (75.0, 1000.0) and n.title == "Demo filter"
+    assert [(k, pp[:2]) for k, pp in n.elements] == [(Q.SHUNT_C, [10e-12, 0.0]), (Q.SER_LC_PAR, [2.2e-6, 1.5e-9]), (Q.SHUNT_L, [47e-3, 0.0])]
+    sch = """<Qucs Schematic 0.0.19>
+<Components>
+  <Pac P1 1 100 100 18 -26 0 1 "1" 1 "75 Ohm" 1>
+  <GND * 1 100 130 0 0 0 0>
+  <MLIN MS1 1 160 70 -26 15 0 0 "S1" 1 "w0" 1 "2 mm" 1>
+  <MCORN MS2 1 220 70 -26 15 0 0 "S1" 1 "w0" 1>
+  <MLIN MS3 1 220 130 15 -26 0 1 "S1" 1 "1 mm" 1 "3.5 mm" 1>
+  <Pac P2 1 220 190 18 -26 0 1 "2" 1 "50 Ohm" 1>
+  <GND * 1 220 220 0 0 0 0>
+  <SUBST S1 1 0 0 0 0 0 0 "3.5" 1 "0.762 mm" 1 "35 um" 1 "0.0013" 1 "2.4e-8" 1 "0" 1>
+  <.SP SP1 1 0 0 0 0 0 0 "log" 1 "1 MHz" 1 "2 GHz" 1 "201" 1>
+  <Eqn Eqn1 1 0 0 0 0 0 0 "w0=1.5e-3" 1 "foo=dB(S[2,1])" 1 "yes" 0>
+</Components>
+<Wires>
+  <100 70 130 70 "" 0 0 0 "">
+</Wires>
+"""
+    p = tmp_path / "t.sch"
+    p.write_text(sch)
+    n = Q.Net.from_qucs_sch(str(p))
+    assert n.terminations == (75.0, 50.0)
+    el = n.elements
+    assert [k for k, _ in el] == [Q.SUBST, Q.MLIN, Q.MCORN, Q.MLIN]
+    assert el[0][1] == [3.5, 0.762e-3, 35e-6, 0.0013, 2.4e-8, 0.0]
+    assert el[1][1][:2] == [1.5e-3, 2e-3] and el[2][1][0] == 1.5e-3 and el[3][1][:2] == [1e-3, 3.5e-3]
+    assert Q.qucs_sch_sweep(str(p)) == ("log", 1e6, 2e9, 201)
+
+
+def test_synthesis_matches_oracle(Q, R):
+    for order in (3, 5, 7, 11):
+        net = Q.Net.cheby_lpf(order, 0.1, 10e6, 50.0).add_parasitics(10e6)
+        ref = R.elems_to_list(R.ladder_lpf(R.cheby_g(order, 0.1), 10e6, 50.0, True, (60, 30, 0.1, 50)))
+        for (k1, p1), (k2, p2) in zip(net.elements, ref):
+            assert k1 == k2 and np.allclose(p1, p2, rtol=4e-16, atol=0)
+    net = Q.Net.butter_lpf(11, 3e9, 50.0, series_first=False)
+    ref = R.elems_to_list(R.ladder_lpf(R.butter_g(11), 3e9, 50.0, False))
+    assert [k for k, _ in net.elements] == [k for k, _ in ref] and net.elements[0][0] == Q.SHUNT_C
+    assert np.allclose([p[0] for _, p in net.elements], [p[0] for _, p in ref], rtol=4e-16)
+    a, b = Q.Net.cheby_lpf(3, 0.5, 1e6, 75.0), Q.Net.butter_lpf(2, 1e6, 50.0)
+    c = a.concat(b)
+    assert len(c) == 5 and c.terminations == (75.0, 50.0)
+
+
+def test_grids_bit_exact(Q, R, golden_dat):
+    assert np.array_equal(Q.grid_lin(1e7, 1e10, 5000), golden_dat["frequency"])
+    assert np.array_equal(Q.grid_log(4e6, 62.5e6, 4096), R.grid_log(4e6, 62.5e6, 4096))
+    assert np.array_equal(Q.grid_lin(70e6, 4000e6, 4096), R.grid_lin(70e6, 4000e6, 4096))
+    assert abs(Q.grid_lin(70e6, 4000e6, 4096)[2428] - 2400168498.17) < 0.01      # SURVEY §8d cfg 5
+    assert Q.grid_lin(5.0, 9.0, 1)[0] == 5.0
+
+
+def test_host_stream_twin_bit_exact_vs_oracle(Q, R):
+    """qo_philox4x32_10 / qo_variate / qo_perturb_factor (product host twins) == the oracle's C stream."""
+    assert Q.philox([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert Q.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert Q.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    rng = np.random.default_rng(5)
+    for _ in range(5000):
+        seed, s, v = int(rng.integers(0, 2 ** 63)) * 2 + 1, int(rng.integers(0, 2 ** 40)), int(rng.integers(0, 64))
+        for dist in (0, 1):
+            assert Q.variate(seed, s, v, dist) == R.lib().ref_variate(seed, s, v, dist)
+            assert Q.perturb_factor(seed, s, v, dist, 0.05) == R.lib().ref_perturb_factor(seed, s, v, dist, 0.05)
+
+
+def test_lc_tolerances_helper(Q, W):
+    w = W.cfg2(1000, 64)
+    assert len(w.tols) == 11 and [t[2] for t in w.tols] == list(range(11))
+    assert [t[4] for t in w.tols] == [0.05, 0.02] * 5 + [0.05]
+    w5 = W.cfg5(1000, 4096)
+    assert len(w5.net) == 12 and max(t[2] for t in w5.tols) == 13 and len(w5.specs) == 3
+    assert sum(1 for f in w5.f if 2.3e9 <= f <= 2.5e9) == 209 and sum(1 for f in w5.f if f >= 3.9e9) == 105

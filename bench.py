@@ -256,7 +256,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": "qo_mc_lumped_kernel<double,false,false>",
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": plan.kernel_name,
                      "kernel_ms": kernel_ms,
                      "peak_source": "measured in this run: qo_measure_dfma_peak (8 independent DFMA chains/thread, "
                                     "best of 5); MEASURED_PEAKS.json has no FP64 figure (nominal 37.2 TFLOP/s)"},

@@ -172,6 +172,10 @@ int qo_plan_launch(qo_plan *plan, uint64_t sample_offset, uint64_t n_samples, ui
 int qo_plan_read(qo_plan *plan, qo_mc_result *res);   /* synchronises, combines across the ctx's GPUs */
 double qo_plan_flops_per_eval(const qo_plan *plan);
 int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far by this plan */
+/* which kernel the plan launches: "qo_mc_ladder_kernel" (straight-line ladder family of
+ * pcb/generic-filter), "qo_mc_lumped_kernel" (opcode interpreter) or "qo_mc_generic_kernel"
+ * (microstrip).  QO100NET_KERNEL=interp in the environment forces the interpreter. */
+const char *qo_plan_kernel_name(const qo_plan *plan);
 void qo_plan_destroy(qo_plan *plan);
 
 /* ---- reference stream: host-callable, bit-exact twins of the device code -- */

@@ -15,6 +15,8 @@
 
 #include "qo_internal.h"
 #include "qo_lumped.cuh"
+#include "qo_ladder.cuh"
+#include "qo_ladder_launch.h"
 #include "qo_ustrip.cuh"
 
 #define CU(call)                                                                                      \
@@ -72,10 +74,12 @@ struct qo_ctx {
 struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
+    void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
     uchar2 *m2;
     double *fgrid;             /* generic kernel */
     unsigned char *mask;
     unsigned long long *counters;
+    unsigned long long *ticket;  /* ladder kernel: dynamic sample hand-out */
     unsigned long long n_launched;
     float ms;
 };
@@ -84,6 +88,8 @@ struct qo_plan {
     qo_ctx *ctx;
     DevProg hp;                /* host copy of the program */
     int nf, npairs, ncnt, precision, mode, generic;
+    int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
+    const char *kernel_name;
     double flops_per_eval;
     int launches;
     unsigned long long n_total_launched;
@@ -309,6 +315,39 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
     return QO_OK;
 }
 
+/* The straight-line ladder kernel covers: reduce-only FP64 jobs whose specs are all on |S21|, on a
+ * network that is an alternating series-inductor / shunt-capacitor ladder of 1..11 elements
+ * (pcb/generic-filter), optionally behind one coupled-line block.  QO100NET_KERNEL=interp forces the
+ * opcode interpreter (A/B runs, parity tests of both paths). */
+static int ladder_eligible(const DevProg *hp, int mode, int precision, int generic, int *n, int *first, int *cpl)
+{
+    const char *force = getenv("QO100NET_KERNEL");
+    if (force && strcmp(force, "interp") == 0) return 0;
+    if (generic || mode != QO_MODE_REDUCE_ONLY || precision != 64 || hp->need_s11 || hp->need_gd) return 0;
+    if (hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) return 0;
+    for (int s = 0; s < hp->nspec; s++)
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN) return 0;
+    int e0 = 0;
+    *cpl = 0;
+    if (hp->n_ops > 0 && hp->opcode[0] == OP_CPL) { *cpl = 1; e0 = 1; }
+    const int nl = hp->n_ops - e0;
+    if (nl < 1 || nl > QO_LAD_MAXN) return 0;
+    const int op0 = hp->opcode[e0];
+    if (op0 == OP_SER_LOSSY_L || op0 == OP_SER_L) *first = 0;
+    else if (op0 == OP_SHUNT_LOSSY_C || op0 == OP_SHUNT_C) *first = 1;
+    else return 0;
+    int any_lossy = 0;
+    for (int e = 0; e < nl; e++) {
+        const int op = hp->opcode[e0 + e];
+        const int series = ((e + *first) & 1) == 0;
+        if (series ? !(op == OP_SER_LOSSY_L || op == OP_SER_L) : !(op == OP_SHUNT_LOSSY_C || op == OP_SHUNT_C)) return 0;
+        if (op == OP_SER_LOSSY_L || op == OP_SHUNT_LOSSY_C) any_lossy = 1;
+    }
+    if (!any_lossy && !*cpl) return 0;    /* ideal ladders: the interpreter's imaginary-immittance path is cheaper */
+    *n = nl;
+    return 1;
+}
+
 /* ---- plan ---------------------------------------------------------------- */
 extern "C" void qo_plan_destroy(qo_plan *p)
 {
@@ -316,8 +355,8 @@ extern "C" void qo_plan_destroy(qo_plan *p)
     for (int g = 0; g < p->ctx->ndev; g++) {
         cudaSetDevice(p->ctx->d[g].device);
         DevPlan *d = &p->d[g];
-        cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->m2);
-        cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters);
+        cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->wsq2); cudaFree(d->m2);
+        cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters); cudaFree(d->ticket);
     }
     delete p;
 }
@@ -343,16 +382,22 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     if (p->generic && p->precision == 32) { delete p; qo_set_error("FP32 mode covers lumped/TL networks only"); return QO_ERR_UNSUPPORTED; }
     p->ncnt = 2 + nspec + p->hp.hist_bins;
     p->f.assign(f, f + nf);
+    p->ladder = ladder_eligible(&p->hp, p->mode, p->precision, p->generic, &p->lad_n, &p->lad_first, &p->lad_cpl);
+    {
+        const char *v = getenv("QO100NET_LAD_VARIANT");
+        p->lad_variant = v ? atoi(v) : 0;
+    }
+    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
     const double two_pi = 6.283185307179586476925286766559;
     const int np = p->npairs;
-    std::vector<double> w(2 * (size_t)np), wi(2 * (size_t)np);
+    std::vector<double> w(2 * (size_t)np), wi(2 * (size_t)np), wsq(2 * (size_t)np);
     std::vector<float> wf(2 * (size_t)np), wif(2 * (size_t)np);
     std::vector<unsigned char> m(2 * (size_t)np, 0);
     for (int k = 0; k < 2 * np; k++) {
         double fk = f[k < nf ? k : nf - 1];
-        w[k] = two_pi * fk; wi[k] = 1.0 / w[k];
+        w[k] = two_pi * fk; wi[k] = 1.0 / w[k]; wsq[k] = w[k] * w[k];
         wf[k] = (float)w[k]; wif[k] = (float)wi[k];
         m[k] = k < nf ? p->maskv[k] : 0;
     }
@@ -377,6 +422,11 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 CUP(cudaMemcpyAsync(d->wi2, wi.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
             }
             CUP(cudaMemcpyAsync(d->m2, m.data(), 2 * (size_t)np, cudaMemcpyHostToDevice, st));
+            if (p->ladder) {
+                CUP(cudaMalloc(&d->wsq2, 2 * (size_t)np * sizeof(double)));
+                CUP(cudaMemcpyAsync(d->wsq2, wsq.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                CUP(cudaMalloc(&d->ticket, sizeof(unsigned long long)));
+            }
         } else {
             CUP(cudaMalloc(&d->fgrid, (size_t)nf * sizeof(double)));
             CUP(cudaMalloc(&d->mask, (size_t)nf));
@@ -394,6 +444,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
 extern "C" int qo_plan_num_counters(const qo_plan *p) { return p ? p->ncnt : QO_ERR_ARG; }
 extern "C" double qo_plan_flops_per_eval(const qo_plan *p) { return p ? p->flops_per_eval : 0.0; }
 extern "C" int qo_plan_launches(const qo_plan *p) { return p ? p->launches : QO_ERR_ARG; }
+extern "C" const char *qo_plan_kernel_name(const qo_plan *p) { return p ? p->kernel_name : ""; }
 
 extern "C" int qo_plan_reset(qo_plan *p)
 {
@@ -439,6 +490,35 @@ static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned lon
     return QO_OK;
 }
 
+static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    DevPlan *d = &p->d[g];
+    const DevProg *hp = &p->hp;
+    LadParams P;
+    memset(&P, 0, sizeof P);
+    P.prog = d->prog;
+    P.wt = (const double2 *)d->w2; P.wit = (const double2 *)d->wi2; P.wsqt = (const double2 *)d->wsq2; P.m2 = d->m2;
+    P.counters = cnt;
+    P.ticket = d->ticket;
+    CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
+    P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
+    P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
+    for (int s = 0; s < QO_LAD_NSPEC; s++) {
+        const int neg = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
+        P.sgn[s] = neg ? 0x80000000u : 0u;
+        P.thr[s] = s < hp->nspec ? (neg ? -hp->spec_thr[s] : hp->spec_thr[s]) : 0.0;
+    }
+    P.npairs = p->npairs; P.n_var = hp->n_var; P.n_ops = hp->n_ops; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.hist_bins = hp->hist_bins;
+    P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
+    P.hist_kind = hp->hist_bins > 0 ? hp->spec_kind[hp->hist_spec] : 0;
+    int rc = qo_ladder_launch(p->lad_n, p->lad_first, p->lad_cpl, p->lad_variant, dc->sm_count, &P, dc->stream, NULL);
+    if (rc < 0) { qo_set_error("no ladder kernel instantiation for n=%d first=%d cpl=%d", p->lad_n, p->lad_first, p->lad_cpl); return QO_ERR_UNSUPPORTED; }
+    if (rc) { qo_set_error("ladder kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
 static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
 {
     DevCtx *dc = &p->ctx->d[g];
@@ -477,6 +557,7 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     }
     int rc;
     if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
+    else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt);
     else if (p->precision == 32) rc = launch_lumped<float>(p, g, off, n, cnt, pl, full_s);
     else rc = launch_lumped<double>(p, g, off, n, cnt, pl, full_s);
     if (rc == QO_OK) { p->launches++; p->d[g].n_launched += n; }

@@ -64,7 +64,7 @@ def build(verbose=False):
     """Compile libqo100net.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     env = dict(os.environ)
     env.pop("CC", None)
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True, env=env)
+    r = subprocess.run(["make", "-j", "4", "-C", CSRC], capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError("building libqo100net.so failed:\n" + r.stdout + r.stderr)
     if verbose:
@@ -80,6 +80,7 @@ EXPORTS = [
     "qo_grid_lin", "qo_grid_log", "qo_ctx_create", "qo_ctx_create_on_device", "qo_ctx_set_stream",
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
+    "qo_plan_kernel_name",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
     "qo_device_rcp", "qo_measure_dfma_peak", "qo_strerror", "qo_last_error", "qo_version",
 ]
@@ -127,6 +128,7 @@ def lib():
         "qo_plan_read": (C.c_int, [vp, C.POINTER(McResult)]),
         "qo_plan_flops_per_eval": (C.c_double, [vp]),
         "qo_plan_launches": (C.c_int, [vp]),
+        "qo_plan_kernel_name": (C.c_char_p, [vp]),
         "qo_plan_destroy": (None, [vp]),
         "qo_philox4x32_10": (None, [C.POINTER(C.c_uint32)] * 3),
         "qo_variate": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]),
@@ -360,6 +362,11 @@ class Plan:
     @property
     def launches(self):
         return _check(lib().qo_plan_launches(self._h))
+
+    @property
+    def kernel_name(self):
+        """Which kernel this plan launches (ladder / interpreter / microstrip)."""
+        return lib().qo_plan_kernel_name(self._h).decode()
 
     def reset(self):
         _check(lib().qo_plan_reset(self._h))

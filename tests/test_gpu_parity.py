@@ -301,3 +301,84 @@ def test_properties_at_baseline_size(Q, W, ctx):
     wl = W.cfg2(0)
     s = ctx.mc_run(wl.net, wl.f, [], 1, 64, wl.tols, mode=Q.MODE_FULL_S)["s"]
     assert np.all(np.abs(s[0]) ** 2 + np.abs(s[1]) ** 2 <= 1.0 + 1e-12)      # lossy: passive
+
+
+# ---- the straight-line ladder kernel (qo_ladder.cuh) ---------------------------------------------
+def _ladder_workload(Q, W, order, series_first, coupler, butter=False, fc=10e6, nf=1000):
+    """An order-N pcb/generic-filter ladder with the cfg-2 parasitic model, specs placed around its own
+    nominal response so that the yield is neither 0 nor 1."""
+    net = (Q.Net.butter_lpf(order, fc, 50.0, series_first) if butter else Q.Net.cheby_lpf(order, 0.1, fc, 50.0, series_first))
+    net = net.add_parasitics(fc, 60.0, 30.0, 0.1, 50.0)
+    tols = Q.lc_tolerances(net, 0.05, 0.02)
+    if coupler:
+        cpl = Q.Net.from_elements([(Q.CPL_THRU, [55.2771, 45.2267, 95.4225, 91.0, 4 * fc, 50.0])], 50.0, 50.0)
+        net = cpl.concat(net)
+        tols = [(0, 0, 0, Q.TOL_REL, 0.02), (0, 1, 1, Q.TOL_REL, 0.02), (0, 2, 2, Q.TOL_REL, 0.01), (0, 3, 2, Q.TOL_REL, 0.01)] + \
+               [(e + 1, p, v + 3, m, t) for (e, p, v, m, t) in tols]
+    f = Q.grid_log(fc / 2.5, fc * 6.25, nf)
+    return net, f, tols
+
+
+@pytest.mark.parametrize("order,series_first,coupler", [(1, True, False), (1, False, False), (2, True, False), (2, False, True),
+                                                        (3, False, False), (4, True, True), (5, True, False), (6, False, False),
+                                                        (7, False, True), (8, True, False), (9, False, False), (10, True, False),
+                                                        (10, False, True), (11, True, False), (11, False, False), (11, True, True)])
+def test_ladder_kernel_family_vs_oracle_and_interpreter(Q, R, W, ctx, monkeypatch, order, series_first, coupler):
+    """Every instantiation family (order, series/shunt first, coupler block) gives the oracle's integer
+    counters, and the same counters as the opcode interpreter forced with QO100NET_KERNEL=interp."""
+    fc = 10e6
+    net, f, tols = _ladder_workload(Q, W, order, series_first, coupler, butter=order % 2 == 0)   # even-order Chebyshev needs Rs != Rl
+    db = 20 * np.log10(np.abs(ctx.sweep(net, f)[1]))
+    pb, sb = f <= 0.8 * fc, f >= 3.0 * fc
+    specs = [(Q.SPEC_S21_MIN_DB, 0.0, 0.8 * fc, float(db[pb].min()) - 0.02),
+             (Q.SPEC_S21_MAX_DB, 3.0 * fc, 1e99, float(db[sb].max()) + 0.2)]
+    hist = dict(hist_bins=32, hist_spec=order % 2, hist_lo=float(db[pb].min()) - 1.0 if order % 2 == 0 else float(db[sb].max()) - 3.0,
+                hist_hi=0.0 if order % 2 == 0 else float(db[sb].max()) + 3.0)
+    n = 700
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    plan = Q.Plan(ctx, net, f, specs, seed=77 + order, tols=tols, **hist)
+    assert plan.kernel_name == "qo_mc_ladder_kernel"
+    plan.launch(5, n)
+    got = plan.read()
+    plan.close()
+    rs, rl = net.terminations
+    ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(77 + order, n, tols, sample_offset=5, **hist), nthreads=8)
+    _assert_counts_equal(ref, got)
+    if order >= 3:
+        assert 0 < got["n_pass"] < n, "degenerate spec placement"
+    monkeypatch.setenv("QO100NET_KERNEL", "interp")
+    plan = Q.Plan(ctx, net, f, specs, seed=77 + order, tols=tols, **hist)
+    assert plan.kernel_name == "qo_mc_lumped_kernel"
+    plan.launch(5, n)
+    itp = plan.read()
+    plan.close()
+    _assert_counts_equal(itp, got)
+
+
+def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
+    """Which jobs take the straight-line kernel; odd grid sizes, 3-4 specs, gaussian tolerances, Butterworth."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    w = W.cfg2()
+    mk = lambda specs, **kw: Q.Plan(ctx, w.net, w.f, specs, seed=1, tols=w.tols, **kw)
+    p = mk(w.specs); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()
+    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()      # |S11| needs the 2x2 chain
+    p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
+    p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode
+    p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()
+    w1 = W.cfg1()
+    p = Q.Plan(ctx, w1.net, w1.f, [(Q.SPEC_S21_MIN_DB, 3.5e8, 4.5e8, -1.0)], seed=1, tols=Q.lc_tolerances(w1.net, 0.05, 0.05))
+    assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                                      # LC-tank branches
+    for nf, butter, dist in ((1, False, Q.DIST_UNIFORM), (2, False, Q.DIST_UNIFORM), (63, True, Q.DIST_GAUSS3S),
+                             (130, False, Q.DIST_GAUSS3S), (257, True, Q.DIST_UNIFORM)):
+        fc = 10e6
+        net, f, tols = _ladder_workload(Q, W, 7, True, False, butter=butter, nf=max(nf, 2))
+        f = f[:nf]
+        specs = [(Q.SPEC_S21_MIN_DB, 0.0, 0.7 * fc, -1.0), (Q.SPEC_S21_MAX_DB, 2.5 * fc, 1e99, -60.0),
+                 (Q.SPEC_S21_MIN_DB, 0.0, 0.5 * fc, -0.9), (Q.SPEC_S21_MAX_DB, 0.9 * fc, 1.1 * fc, -0.5)]
+        hist = dict(hist_bins=16, hist_spec=3, hist_lo=-6.0, hist_hi=0.0) if nf >= 130 else {}
+        if hist and not np.any((f >= 0.9 * fc) & (f <= 1.1 * fc)):
+            hist = {}
+        rs, rl = net.terminations
+        got = ctx.mc_run(net, f, specs, 5, 300, tols, dist=dist, **hist)
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(5, 300, tols, dist=dist, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)

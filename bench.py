@@ -37,9 +37,21 @@ METRIC = "Monte Carlo network evals/s (samples x freq pts)"
 UNIT = "evals/s"
 SAMPLES_PER_GPU = 1000000
 NF = 4096
-# dram bytes (read+write) per launch of the dominant kernel from the committed ncu --set full capture
-# (profiles/); None until a capture exists for the current kernel
-NCU_TRAFFIC_BYTES_PER_LAUNCH = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+# ncu --set full capture (profiles/r01c_ladder_raw_metrics.txt): 154 KB read (tables + program), 0 written
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 154368
+
+
+def sass_fp64_per_eval(plan_kernel, wl_name):
+    """FP64-pipe instructions the ladder kernel EXECUTES per eval (static SASS census of the shipped .so,
+    tools/sass_count.py -> profiles/sass_counts.json); None for other kernels."""
+    if plan_kernel != "qo_mc_ladder_kernel":
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
+        return d["n11_first0_cpl1" if wl_name.startswith("cfg5") else "n11_first0_cpl0"]["fp64_pipe_instr_per_eval"]
+    except Exception:
+        return None
 
 
 def workload(name, n_samples):
@@ -242,6 +254,9 @@ def main():
     flops = plan.flops_per_eval
     peak = ctx.measure_dfma_peak()                      # TFLOP/s, measured now on this GPU
     achieved = flops * nspg * nf / (kernel_ms * 1e-3) * 1e-12
+    fp64_ipe = sass_fp64_per_eval(plan.kernel_name, wl.name)
+    # executed FP64-pipe instructions/s against the measured DFMA issue rate (peak TFLOP/s / 2)
+    pipe_util = fp64_ipe * nspg * nf / (kernel_ms * 1e-3) / (peak * 0.5e12) if fp64_ipe else None
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -258,6 +273,11 @@ def main():
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": plan.kernel_name,
                      "kernel_ms": kernel_ms,
+                     "fp64_pipe_instr_per_eval_sass": fp64_ipe, "pipe_util_from_sass": pipe_util,
+                     "note": "achieved = ALG-v1 algorithmic flops (SURVEY 8d: 2x2 chain + complex divides) / kernel time; "
+                             "the kernel executes fewer operations than ALG-v1 counts (row-vector chain, division-free "
+                             "immittances), so frac can exceed the FP64-pipe utilisation, which is pipe_util_from_sass "
+                             "(and sm__pipe_fp64_cycles_active in profiles/)",
                      "peak_source": "measured in this run: qo_measure_dfma_peak (8 independent DFMA chains/thread, "
                                     "best of 5); MEASURED_PEAKS.json has no FP64 figure (nominal 37.2 TFLOP/s)"},
     }

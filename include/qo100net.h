@@ -108,6 +108,26 @@ void qo_net_free(qo_net *net);
 int qo_grid_lin(double f0, double f1, int n, double *f);
 int qo_grid_log(double f0, double f1, int n, double *f);
 
+/* ---- Qucs dataset (.dat) reader / writer --------------------------------- */
+/* The layout Qucs 0.0.19 writes for util/pa-lpf-simulation/pa-lpf-simulation.dat:1-35018:
+ * "<indep NAME N>" / "<dep NAME INDEP>" blocks of "%+.20e" reals or "%+.20e+j%.20e" complex values.
+ * qo_dat_read -> qo_dat_write reproduces that file byte for byte; qo_dat_from_sweep builds the dataset
+ * Qucs would write for a 2-port .SP sweep with the dB() equations of pa-lpf-simulation.sch:59-60
+ * (frequency, S11_dB, S21_dB, S[1,1], S[1,2], S[2,1], S[2,2]). */
+typedef struct qo_dat qo_dat;
+int qo_dat_create(qo_dat **out);
+int qo_dat_read(const char *path, qo_dat **out);
+int qo_dat_write(const qo_dat *dat, const char *path);
+int qo_dat_add_indep(qo_dat *dat, const char *name, const double *v, int n);
+int qo_dat_add_dep(qo_dat *dat, const char *name, const char *indep, const double *re, const double *im /* NULL = real */, int n);
+int qo_dat_count(const qo_dat *dat);
+/* variable i: name, the independent it hangs on ("" for an independent variable), points, complex? */
+int qo_dat_info(const qo_dat *dat, int i, const char **name, const char **indep, int *n, int *is_complex);
+/* copies up to cap values (im nullable); returns the variable's point count */
+int qo_dat_get(const qo_dat *dat, const char *name, double *re, double *im, int cap);
+int qo_dat_from_sweep(const double *f, int nf, const qo_c64 *s11, const qo_c64 *s12, const qo_c64 *s21, const qo_c64 *s22, qo_dat **out);
+void qo_dat_free(qo_dat *dat);
+
 /* ---- compute ----------------------------------------------------------- */
 /* ngpus devices 0..ngpus-1 in ONE process (samples sharded, counters combined
  * by NCCL all-reduce when libnccl is loadable).  One process

@@ -257,7 +257,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
         double trk[QO_LAD_NSPEC];
 #pragma unroll
         for (int sp = 0; sp < QO_LAD_NSPEC; sp++) trk[sp] = __hiloint2double((int)QO_LAD_NEG_HUGE_HI, 0);
-        for (int j0 = lane; j0 < npairs; j0 += 32 * PP) {
+        /* warp-uniform trip count (the tracker vote below is a full-warp collective): lanes past the end of
+         * the grid re-evaluate the last pair with all-zero masks */
+        for (int jb = 0; jb < npairs; jb += 32 * PP) {
+            const int j0 = jb + lane;
             double w[PTS], wi[PTS], w2[PTS];
             unsigned int mk[PTS];
 #pragma unroll

@@ -81,6 +81,8 @@ EXPORTS = [
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
     "qo_plan_kernel_name",
+    "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
+    "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
     "qo_device_rcp", "qo_measure_dfma_peak", "qo_strerror", "qo_last_error", "qo_version",
 ]
@@ -129,6 +131,16 @@ def lib():
         "qo_plan_flops_per_eval": (C.c_double, [vp]),
         "qo_plan_launches": (C.c_int, [vp]),
         "qo_plan_kernel_name": (C.c_char_p, [vp]),
+        "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
+        "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "qo_dat_write": (C.c_int, [vp, C.c_char_p]),
+        "qo_dat_add_indep": (C.c_int, [vp, C.c_char_p, dp, C.c_int]),
+        "qo_dat_add_dep": (C.c_int, [vp, C.c_char_p, C.c_char_p, dp, dp, C.c_int]),
+        "qo_dat_count": (C.c_int, [vp]),
+        "qo_dat_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), ip, ip]),
+        "qo_dat_get": (C.c_int, [vp, C.c_char_p, dp, dp, C.c_int]),
+        "qo_dat_from_sweep": (C.c_int, [dp, C.c_int, vp, vp, vp, vp, C.POINTER(vp)]),
+        "qo_dat_free": (None, [vp]),
         "qo_plan_destroy": (None, [vp]),
         "qo_philox4x32_10": (None, [C.POINTER(C.c_uint32)] * 3),
         "qo_variate": (C.c_double, [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]),
@@ -258,6 +270,71 @@ def load_trc(path):
     _check(lib().qo_cpl_load_trc(os.fsencode(path), C.byref(z0e), C.byref(z0o), C.byref(ang), C.byref(f0), phys))
     keys = ["er", "h", "ht", "t", "w", "s", "l", "tand"]
     return dict(z0e=z0e.value, z0o=z0o.value, ang=ang.value, f0=f0.value, **{k: phys[i] for i, k in enumerate(keys)})
+
+
+class Dataset:
+    """A Qucs dataset (qo_dat*): ordered variables, each a real or complex numpy array."""
+
+    def __init__(self, handle=None):
+        self._h = handle or C.c_void_p()
+        if not handle:
+            _check(lib().qo_dat_create(C.byref(self._h)))
+
+    @classmethod
+    def read(cls, path):
+        h = C.c_void_p()
+        _check(lib().qo_dat_read(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_sweep(cls, f, s11, s12, s21, s22):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        arrs = [np.ascontiguousarray(a, dtype=np.complex128) for a in (s11, s12, s21, s22)]
+        h = C.c_void_p()
+        _check(lib().qo_dat_from_sweep(_dp(f), len(f), *[a.ctypes.data_as(C.c_void_p) for a in arrs], C.byref(h)))
+        return cls(h)
+
+    def add_indep(self, name, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        _check(lib().qo_dat_add_indep(self._h, name.encode(), _dp(v), len(v)))
+
+    def add_dep(self, name, indep, v):
+        v = np.asarray(v)
+        re = np.ascontiguousarray(v.real, dtype=np.float64)
+        im = np.ascontiguousarray(v.imag, dtype=np.float64) if np.iscomplexobj(v) else None
+        _check(lib().qo_dat_add_dep(self._h, name.encode(), indep.encode(), _dp(re), _dp(im), len(re)))
+
+    def write(self, path):
+        _check(lib().qo_dat_write(self._h, os.fsencode(path)))
+
+    def variables(self):
+        """[(name, indep or '', n, is_complex)] in file order."""
+        out = []
+        for i in range(_check(lib().qo_dat_count(self._h))):
+            name, indep, n, cx = C.c_char_p(), C.c_char_p(), C.c_int(), C.c_int()
+            _check(lib().qo_dat_info(self._h, i, C.byref(name), C.byref(indep), C.byref(n), C.byref(cx)))
+            out.append((name.value.decode(), indep.value.decode(), n.value, bool(cx.value)))
+        return out
+
+    def __getitem__(self, name):
+        info = {v[0]: v for v in self.variables()}
+        if name not in info:
+            raise KeyError(name)
+        n, cx = info[name][2], info[name][3]
+        re, im = np.empty(n), np.empty(n)
+        _check(lib().qo_dat_get(self._h, name.encode(), _dp(re), _dp(im), n))
+        return re + 1j * im if cx else re
+
+    def close(self):
+        if self._h:
+            lib().qo_dat_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def cpl_analyze(w, s, h, t, er, ht, f, length):

@@ -382,3 +382,17 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
         got = ctx.mc_run(net, f, specs, 5, 300, tols, dist=dist, **hist)
         ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(5, 300, tols, dist=dist, **hist), nthreads=8)
         _assert_counts_equal(ref, got)
+
+
+def test_gpu_sweep_to_qucs_dataset(Q, W, ctx, golden_dat, tmp_path):
+    """Row N2 end to end: the PA-LPF sweep computed on the GPU, written as a Qucs dataset, read back, and
+    compared with the reference dataset's values (tests/golden/pa_lpf_dat.npz)."""
+    f = golden_dat["frequency"]
+    s11, s21, s12, s22 = ctx.sweep(W.pa_lpf_net(), f)
+    d = Q.Dataset.from_sweep(f, s11, s12, s21, s22)
+    d.write(str(tmp_path / "gpu.dat"))
+    r = Q.Dataset.read(str(tmp_path / "gpu.dat"))
+    assert np.array_equal(r["S[2,1]"], s21) and np.array_equal(r["frequency"], f)
+    assert relerr(r["S[2,1]"], golden_dat["S21"]) <= TOL64 and relerr(r["S[1,2]"], golden_dat["S12"]) <= TOL64
+    assert np.max(np.abs(r["S21_dB"] - golden_dat["S21_dB"])) <= 1e-9
+    assert np.all(np.abs(r["S[1,1]"] - golden_dat["S11"]) <= TOL64 * np.maximum(np.abs(golden_dat["S11"]), 0.02))

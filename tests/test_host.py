@@ -230,3 +230,79 @@ def test_lc_tolerances_helper(Q, W):
     w5 = W.cfg5(1000, 4096)
     assert len(w5.net) == 12 and max(t[2] for t in w5.tols) == 13 and len(w5.specs) == 3
     assert sum(1 for f in w5.f if 2.3e9 <= f <= 2.5e9) == 209 and sum(1 for f in w5.f if f >= 3.9e9) == 105
+
+
+def test_cpl_analyze_reproduces_trc_files_and_oracle(Q, R, golden_nets):
+    """Row N1: QucsTranscalc CoupledMicrostrip analysis.  The product's host routine reproduces
+    Z0e, Z0o, Ang_l of all four util/directional-couplers/*.trc:18-20 to the files' 6 digits and agrees
+    with the oracle's independent restatement to rounding; derived checks: coupling k and sqrt(Z0e Z0o)."""
+    n = 0
+    for key, t in golden_nets.items():
+        if not key.endswith(".trc"):
+            continue
+        n += 1
+        args = (t["w"], t["s"], t["h"], t["t"], t["er"], t["ht"], t["f0"], t["l"])
+        ze, zo, ae, ao = Q.cpl_analyze(*args)
+        assert abs(ze / t["z0e"] - 1) < 5e-6 and abs(zo / t["z0o"] - 1) < 5e-6
+        assert abs(np.sqrt(ae * ao) / t["ang"] - 1) < 5e-6
+        assert ae > ao                                   # even mode is slower (more field in the dielectric)
+        assert np.allclose([ze, zo, ae, ao], R.cpl_analyze(*args), rtol=1e-12, atol=0)
+    assert n == 4
+    t = golden_nets["util/directional-couplers/dir_cpl_2.4g_20dB.trc"]
+    ze, zo, _, _ = Q.cpl_analyze(t["w"], t["s"], t["h"], t["t"], t["er"], t["ht"], t["f0"], t["l"])
+    assert abs(20 * np.log10((ze - zo) / (ze + zo)) + 20.0) < 1e-3 and abs(np.sqrt(ze * zo) - 50.0) < 1e-3
+    # zero strip thickness is a valid input; bad geometry is refused
+    assert all(np.isfinite(Q.cpl_analyze(1.7e-3, 1e-3, 0.762e-3, 0.0, 3.5, 0.2, 2.4e9, 20e-3)))
+    with pytest.raises(Q.QoError):
+        Q.cpl_analyze(-1.0, 1e-3, 0.762e-3, 35e-6, 3.5, 0.2, 2.4e9, 20e-3)
+    with pytest.raises(Q.QoError):
+        Q.cpl_analyze(1.7e-3, 1e-3, 0.762e-3, 35e-6, 1.0, 0.2, 2.4e9, 20e-3)
+
+
+def test_qucs_dataset_round_trip(Q, golden_dat, tmp_path):
+    """Row N2: Qucs dataset writer/reader.  A dataset built from the golden arrays is written in the layout of
+    util/pa-lpf-simulation/pa-lpf-simulation.dat and read back bit-exactly; with the reference tree mounted,
+    read -> write reproduces the reference file byte for byte."""
+    f = golden_dat["frequency"]
+    names = {"S[1,1]": "S11", "S[1,2]": "S12", "S[2,1]": "S21", "S[2,2]": "S22"}
+    d = Q.Dataset.from_sweep(f, golden_dat["S11"], golden_dat["S12"], golden_dat["S21"], golden_dat["S22"])
+    assert [v[0] for v in d.variables()] == ["frequency", "S11_dB", "S21_dB", "S[1,1]", "S[1,2]", "S[2,1]", "S[2,2]"]
+    assert d.variables()[3] == ("S[1,1]", "frequency", 5000, True) and d.variables()[0] == ("frequency", "", 5000, False)
+    p = tmp_path / "out.dat"
+    d.write(str(p))
+    head = open(p).read().split("\n")[:3]
+    assert head[0] == "<Qucs Dataset 0.0.19>" and head[1] == "<indep frequency 5000>" and head[2] == "  +1.00000000000000000000e+07"
+    r = Q.Dataset.read(str(p))
+    assert np.array_equal(r["frequency"], f)
+    for k, g in names.items():
+        assert np.array_equal(r[k], golden_dat[g])
+    # dB traces recomputed by the writer agree with Qucs' own to rounding
+    assert np.max(np.abs(r["S21_dB"] - golden_dat["S21_dB"])) < 1e-12
+    assert np.max(np.abs(r["S11_dB"] - golden_dat["S11_dB"])) < 1e-11
+    # generic builder + error paths
+    e = Q.Dataset()
+    e.add_indep("zw", [0.75e-3])
+    e.add_indep("frequency", f[:7])
+    e.add_dep("gain", "frequency", np.arange(7.0))
+    e.add_dep("S[2,1]", "frequency", golden_dat["S21"][:7])
+    with pytest.raises(Q.QoError):
+        e.add_dep("bad", "frequency", np.arange(3.0))          # length mismatch
+    with pytest.raises(Q.QoError):
+        e.add_dep("gain", "frequency", np.arange(7.0))         # duplicate
+    with pytest.raises(Q.QoError):
+        e.add_dep("x", "nope", np.arange(7.0))                 # unknown independent
+    e.write(str(tmp_path / "e.dat"))
+    r2 = Q.Dataset.read(str(tmp_path / "e.dat"))
+    assert r2.variables() == e.variables() and np.array_equal(r2["S[2,1]"], golden_dat["S21"][:7]) and r2["zw"][0] == 0.75e-3
+    (tmp_path / "junk.dat").write_text("<Qucs Dataset 0.0.19>\n<indep f 2>\n  +1.0e+00\n</indep>\n")
+    with pytest.raises(Q.QoError):
+        Q.Dataset.read(str(tmp_path / "junk.dat"))             # fewer values than the header says
+    with pytest.raises(Q.QoError):
+        Q.Dataset.read(str(tmp_path / "missing.dat"))
+    ref = os.path.join(REFERENCE, "util/pa-lpf-simulation/pa-lpf-simulation.dat")
+    if os.path.exists(ref):
+        rd = Q.Dataset.read(ref)
+        assert [v[0] for v in rd.variables()] == ["zw", "frequency", "S11_dB", "S21_dB", "S[1,1]", "S[1,2]", "S[2,1]", "S[2,2]"]
+        assert np.array_equal(rd["S[2,1]"], golden_dat["S21"]) and np.array_equal(rd["S11_dB"], golden_dat["S11_dB"])
+        rd.write(str(tmp_path / "ref_copy.dat"))
+        assert open(tmp_path / "ref_copy.dat", "rb").read() == open(ref, "rb").read()

@@ -236,6 +236,12 @@ __device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int 
 
 struct QoPlanes { double2 *s11, *s21, *s12, *s22; };
 
+/* 32 contiguous bytes (two complex doubles) in one 256-bit store; p must be 32-byte aligned */
+__device__ __forceinline__ void qo_st256(double2 *p, double2 a, double2 b)
+{
+    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+}
+
 /* ---- the kernel ----------------------------------------------------------- */
 template <typename T, bool FULL_S, bool TRIG>
 __global__ void __launch_bounds__(QO_TPB, 2)
@@ -256,6 +262,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
     const int hist_spec = prog->hist_bins > 0 ? prog->hist_spec : -1;
     const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
     const bool need_s11 = FULL_S || prog->need_s11;
+    const bool planes_al32 = ((((size_t)planes.s11) | ((size_t)planes.s21) | ((size_t)planes.s12) | ((size_t)planes.s22)) & 31) == 0;
     for (int i = threadIdx.x; i < n_ops; i += QO_TPB) { s_op[i] = prog->opcode[i]; s_coff[i] = prog->coff[i]; }
     for (int i = threadIdx.x; i < ncnt; i += QO_TPB) s_cnt[i] = 0;
     if (threadIdx.x < QO_NSPEC_MAX) { s_thr[threadIdx.x] = T(prog->spec_thr[threadIdx.x]); s_sk[threadIdx.x] = prog->spec_kind[threadIdx.x]; }
@@ -296,6 +303,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
             if (jn < hi) { wv = w2[jn]; wiv = wi2[jn]; if (!FULL_S) mv = m2[jn]; }   /* prefetch next pair */
             Abcd2<T> m;
             qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, w, wi, m);
+            double2 o11[2], o21[2], o22[2];
             QO_P2 {
                 /* den = A Rl + B + C Rs Rl + D Rs ; n11 = A Rl + B - C Rs Rl - D Rs */
                 T den_r, den_i, n_r = T(0), n_i = T(0), num2 = T(0);
@@ -310,25 +318,15 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                 }
                 const T den2 = qfma(den_r, den_r, den_i * den_i);
                 if (FULL_S) {
-                    const int k = 2 * j + p;
-                    if (k < nf) {
-                        const T r = qrcp(den2);
-                        const T ir = den_r * r, ii = -den_i * r;
-                        const size_t o = (size_t)s * (size_t)nf + (size_t)k;
-                        const T s21r = k21 * ir, s21i = k21 * ii;
-                        if (planes.s21) planes.s21[o] = make_double2((double)s21r, (double)s21i);
-                        if (planes.s11) planes.s11[o] = make_double2((double)(n_r * ir - n_i * ii), (double)(n_r * ii + n_i * ir));
-                        if (planes.s22) {
-                            /* n22 = -A Rl + B - C Rs Rl + D Rs */
-                            T ur = qfma(-m.ar[p], rl, m.br[p]), ui = qfma(-m.ai[p], rl, m.bi[p]);
-                            T vr = qfma(-m.cr[p], rsrl, m.dr[p] * rs), vi = qfma(-m.ci[p], rsrl, m.di[p] * rs);
-                            T xr = ur + vr, xi = ui + vi;
-                            planes.s22[o] = make_double2((double)(xr * ir - xi * ii), (double)(xr * ii + xi * ir));
-                        }
-                        /* S12 = S21 (AD - BC) with AD - BC == 1 exactly: all elements are reciprocal, and
-                         * the numerical determinant cancels catastrophically in a deep stop band */
-                        if (planes.s12) planes.s12[o] = make_double2((double)s21r, (double)s21i);
-                    }
+                    const T r = qrcp(den2);
+                    const T ir = den_r * r, ii = -den_i * r;
+                    o21[p] = make_double2((double)(k21 * ir), (double)(k21 * ii));
+                    o11[p] = make_double2((double)(n_r * ir - n_i * ii), (double)(n_r * ii + n_i * ir));
+                    /* n22 = -A Rl + B - C Rs Rl + D Rs */
+                    T ur = qfma(-m.ar[p], rl, m.br[p]), ui = qfma(-m.ai[p], rl, m.bi[p]);
+                    T vr = qfma(-m.cr[p], rsrl, m.dr[p] * rs), vi = qfma(-m.ci[p], rsrl, m.di[p] * rs);
+                    T xr = ur + vr, xi = ui + vi;
+                    o22[p] = make_double2((double)(xr * ir - xi * ii), (double)(xr * ii + xi * ir));
                 } else {
                     const unsigned int mb = mk[p];
 #pragma unroll
@@ -345,6 +343,30 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                         T a = hist_kind == SK_DEN2_MAX ? den2 : hist_kind == SK_DEN2_MIN ? T(1) : num2;
                         T b = hist_kind == SK_DEN2_MAX ? T(1) : den2;
                         if (a * wd > wn * b) { wn = a; wd = b; }
+                    }
+                }
+            }
+            if (FULL_S) {
+                /* A lane owns two ADJACENT points = 32 contiguous bytes per plane: one 256-bit store per plane
+                 * (STG.E.ENL2.256) makes every warp store a full 1 KB run.  Two 16-byte stores per lane leave
+                 * every 32-byte sector half written per instruction (ncu r01d: 16 of 32 bytes per sector used,
+                 * DRAM at 41 % of peak).  S12 = S21 (AD - BC) with AD - BC == 1 exactly: every element is
+                 * reciprocal, and the numerical determinant cancels catastrophically in a deep stop band. */
+                const int k = 2 * j;
+                const size_t o = (size_t)s * (size_t)nf + (size_t)k;
+                if (k + 1 < nf && ((o & 1) == 0) && planes_al32) {
+                    if (planes.s21) qo_st256(planes.s21 + o, o21[0], o21[1]);
+                    if (planes.s11) qo_st256(planes.s11 + o, o11[0], o11[1]);
+                    if (planes.s22) qo_st256(planes.s22 + o, o22[0], o22[1]);
+                    if (planes.s12) qo_st256(planes.s12 + o, o21[0], o21[1]);
+                } else {
+                    QO_P2 {
+                        if (k + p < nf) {
+                            if (planes.s21) planes.s21[o + p] = o21[p];
+                            if (planes.s11) planes.s11[o + p] = o11[p];
+                            if (planes.s22) planes.s22[o + p] = o22[p];
+                            if (planes.s12) planes.s12[o + p] = o21[p];
+                        }
                     }
                 }
             }

@@ -75,6 +75,7 @@ struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
     void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
+    void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
     uchar2 *m2;
     double *fgrid;             /* generic kernel */
     unsigned char *mask;
@@ -89,6 +90,7 @@ struct qo_plan {
     DevProg hp;                /* host copy of the program */
     int nf, npairs, ncnt, precision, mode, generic;
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
+    int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
     const char *kernel_name;
     double flops_per_eval;
     int launches;
@@ -356,6 +358,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         cudaSetDevice(p->ctx->d[g].device);
         DevPlan *d = &p->d[g];
         cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->wsq2); cudaFree(d->m2);
+        for (int t = 0; t < 4; t++) cudaFree(d->cpl_tab[t]);
         cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters); cudaFree(d->ticket);
     }
     delete p;
@@ -401,6 +404,40 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         wf[k] = (float)w[k]; wif[k] = (float)wi[k];
         m[k] = k < nf ? p->maskv[k] : 0;
     }
+    /* coupler block of the ladder kernel: sin/cos of the NOMINAL mode angles per grid point, usable when
+     * every sample's angle stays within 0.05 rad of nominal over the whole grid (qo_ladder.cuh::lad_cpl_first) */
+    std::vector<double> ctab[4];
+    p->cpl_fast = p->cpl_same = 0;
+    if (p->ladder && p->lad_cpl) {
+        const DevProg *hp = &p->hp;
+        double lo[6], hi[6];
+        for (int k = 0; k < 6; k++) {
+            const double nomv = hp->nom[0][k], t = hp->tvar[0][k] >= 0 ? fabs(hp->ttol[0][k]) : 0.0;
+            const double dlt = hp->tmode[0][k] ? t : fabs(nomv) * t;
+            lo[k] = nomv - dlt; hi[k] = nomv + dlt;
+        }
+        double wmax = 0;
+        for (int k = 0; k < 2 * np; k++) if (w[k] > wmax) wmax = w[k];
+        double worst = 0;
+        int ok = lo[4] > 0;
+        for (int m = 0; m < 2 && ok; m++) {
+            const double kn = hp->nom[0][2 + m] / (360.0 * hp->nom[0][4]);
+            const double kmax = hi[2 + m] / (360.0 * lo[4]), kmin = lo[2 + m] / (360.0 * hi[4]);
+            const double dk = fmax(kmax - kn, kn - kmin);
+            if (dk * wmax > worst) worst = dk * wmax;
+        }
+        p->cpl_fast = ok && worst <= 0.05 && !getenv("QO100NET_CPL_SINCOS");
+        p->cpl_same = hp->nom[0][2] == hp->nom[0][3] && hp->tvar[0][2] == hp->tvar[0][3] && hp->ttol[0][2] == hp->ttol[0][3] &&
+                      hp->tmode[0][2] == hp->tmode[0][3];
+        if (p->cpl_fast) {
+            for (int t = 0; t < 4; t++) ctab[t].resize(2 * (size_t)np);
+            const double ke = hp->nom[0][2] / (360.0 * hp->nom[0][4]), ko = hp->nom[0][3] / (360.0 * hp->nom[0][4]);
+            for (int k = 0; k < 2 * np; k++) {
+                ctab[0][k] = sin(ke * w[k]); ctab[1][k] = cos(ke * w[k]);
+                ctab[2][k] = sin(ko * w[k]); ctab[3][k] = cos(ko * w[k]);
+            }
+        }
+    }
     for (int g = 0; g < ctx->ndev; g++) {
         DevPlan *d = &p->d[g];
         rc = QO_ERR_CUDA;
@@ -426,6 +463,11 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 CUP(cudaMalloc(&d->wsq2, 2 * (size_t)np * sizeof(double)));
                 CUP(cudaMemcpyAsync(d->wsq2, wsq.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
                 CUP(cudaMalloc(&d->ticket, sizeof(unsigned long long)));
+                if (p->cpl_fast)
+                    for (int t = 0; t < 4; t++) {
+                        CUP(cudaMalloc(&d->cpl_tab[t], 2 * (size_t)np * sizeof(double)));
+                        CUP(cudaMemcpyAsync(d->cpl_tab[t], ctab[t].data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                    }
             }
         } else {
             CUP(cudaMalloc(&d->fgrid, (size_t)nf * sizeof(double)));
@@ -500,6 +542,9 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     P.prog = d->prog;
     P.wt = (const double2 *)d->w2; P.wit = (const double2 *)d->wi2; P.wsqt = (const double2 *)d->wsq2; P.m2 = d->m2;
     P.counters = cnt;
+    P.cse = (const double2 *)d->cpl_tab[0]; P.cce = (const double2 *)d->cpl_tab[1];
+    P.cso = (const double2 *)d->cpl_tab[2]; P.cco = (const double2 *)d->cpl_tab[3];
+    P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same;
     P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
     P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;

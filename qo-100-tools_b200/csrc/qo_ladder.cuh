@@ -37,7 +37,7 @@
 #define QO_LAD_MAXN 11
 #define QO_LAD_NSPEC 4               /* trackers kept in registers; more specs -> interpreter */
 #define QO_LAD_STRIDE 6              /* doubles per element record (16-byte aligned) */
-#define QO_LAD_CPL 8                 /* doubles of the coupler record that precedes the ladder records */
+#define QO_LAD_CPL 10                /* doubles of the coupler record that precedes the ladder records */
 #define QO_LAD_NEG_HUGE_HI 0xFFEFFFFFu   /* high word of a huge negative finite double: "no point seen yet" */
 
 template <int PTS> struct LadRow { double ar[PTS], ai[PTS], br[PTS], bi[PTS]; };
@@ -122,45 +122,68 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double 
     }
 }
 
-/* coupled-line through section as the FIRST block: u = [1 Rs] . [A B; C A]
- * record = { z0e/zt + zt/z0e, z0e/zt - zt/z0e, (same for odd), te/w, to/w, zt, 1/zt }   */
-template <int PTS>
-__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const double (&w)[PTS], double rs, LadRow<PTS> &u)
+/* Coupled-line through section as the FIRST block, division-free.
+ * Mode lines normalised to Zt: D_m = 2 cos(t_m) + j sin(t_m) (z_m + 1/z_m), n_m = j sin(t_m) (z_m - 1/z_m);
+ * S21 = Sg/Pi, S11 = Nu/Pi with Pi = D_e D_o, Sg = D_e + D_o, Nu = (n_e D_o + n_o D_e)/2.  Symmetric S -> ABCD:
+ *   A = (Pi^2 - Nu^2 + Sg^2)/k,  B = Zt ((Pi + Nu)^2 - Sg^2)/k,  C = ((Pi - Nu)^2 - Sg^2)/(Zt k),  k = 2 Sg Pi.
+ * The complex scalar 1/k multiplies the whole matrix, hence den, so the chain runs on k*[A B; C A] and
+ * |den|^2 is rescaled by 1/|k|^2 at the end (one batched real reciprocal instead of three complex divides).
+ * record = { z_e + 1/z_e, (z_e - 1/z_e)/2, (odd: same two), te/w, to/w, Zt, Rs/Zt, te/w - nominal, to/w - nominal }
+ *
+ * Angles: t_m = k_m w.  When the plan could bound the perturbation |k_m - k_m,nominal| w_max <= 0.05 rad
+ * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
+ * short Taylor polynomials (|d|^10/10! < 3e-20, |d|^9/9! < 6e-18) -- 14 FP64 instructions instead of the ~30 of
+ * a general sincos; otherwise sincos() is called. */
+template <int PTS, bool FAST>
+__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
+                                              const double (&tso)[PTS], const double (&tco)[PTS], double rs, LadRow<PTS> &u,
+                                              double (&scale)[PTS])
 {
-    const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16), c45 = lad_lds2(cf + 32), c67 = lad_lds2(cf + 48);
-    const double cE = c01.x, dE = c01.y, cO = c23.x, dO = c23.y, ke = c45.x, ko = c45.y, zt = c67.x, yt = c67.y;
-    double se[PTS], ce[PTS], so[PTS], co[PTS], er_[PTS], ei_[PTS], or_[PTS], oi_[PTS], qe[PTS], qo[PTS], re[PTS], ro[PTS];
+    const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16), c45 = lad_lds2(cf + 32), c67 = lad_lds2(cf + 48), c89 = lad_lds2(cf + 64);
+    const double cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y, ke = c45.x, ko = c45.y, zt = c67.x, rz = c67.y;
+    const bool same = ke == ko;
+    double se[PTS], ce[PTS], so[PTS], co[PTS], kap2[PTS];
     QO_PTS {
-        sincos(ke * w[p], &se[p], &ce[p]);
-        if (ke == ko) { so[p] = se[p]; co[p] = ce[p]; } else sincos(ko * w[p], &so[p], &co[p]);
-        er_[p] = ce[p] + ce[p]; ei_[p] = se[p] * cE; or_[p] = co[p] + co[p]; oi_[p] = so[p] * cO;
-        qe[p] = fma(er_[p], er_[p], ei_[p] * ei_[p]); qo[p] = fma(or_[p], or_[p], oi_[p] * oi_[p]);
+        if (FAST) {
+            {
+                const double d = c89.x * w[p], z = d * d;
+                const double cd = fma(fma(fma(fma(1.0 / 40320.0, z, -1.0 / 720.0), z, 1.0 / 24.0), z, -0.5), z, 1.0);
+                const double sd = d * fma(fma(fma(-1.0 / 5040.0, z, 1.0 / 120.0), z, -1.0 / 6.0), z, 1.0);
+                se[p] = fma(tse[p], cd, tce[p] * sd); ce[p] = fma(tce[p], cd, -tse[p] * sd);
+            }
+            if (same) { so[p] = se[p]; co[p] = ce[p]; }
+            else {
+                const double d = c89.y * w[p], z = d * d;
+                const double cd = fma(fma(fma(fma(1.0 / 40320.0, z, -1.0 / 720.0), z, 1.0 / 24.0), z, -0.5), z, 1.0);
+                const double sd = d * fma(fma(fma(-1.0 / 5040.0, z, 1.0 / 120.0), z, -1.0 / 6.0), z, 1.0);
+                so[p] = fma(tso[p], cd, tco[p] * sd); co[p] = fma(tco[p], cd, -tso[p] * sd);
+            }
+        } else {
+            sincos(ke * w[p], &se[p], &ce[p]);
+            if (same) { so[p] = se[p]; co[p] = ce[p]; } else sincos(ko * w[p], &so[p], &co[p]);
+        }
     }
-    lad_rcp_batch<PTS>(qe, re);
-    lad_rcp_batch<PTS>(qo, ro);
-    double s21r[PTS], s21i[PTS], s11r[PTS], s11i[PTS], dr_[PTS], di_[PTS], qd[PTS], rd[PTS];
     QO_PTS {
-        const double ier = er_[p] * re[p], iei = -ei_[p] * re[p], ior = or_[p] * ro[p], ioi = -oi_[p] * ro[p];
-        s21r[p] = ier + ior; s21i[p] = iei + ioi;
-        const double ge = 0.5 * se[p] * dE, go = 0.5 * so[p] * dO;
-        s11r[p] = -(ge * iei + go * ioi); s11i[p] = ge * ier + go * ior;
-        dr_[p] = s21r[p] + s21r[p]; di_[p] = s21i[p] + s21i[p];
-        qd[p] = fma(dr_[p], dr_[p], di_[p] * di_[p]);
+        const double a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;        /* D_e, D_o */
+        const double Pr = fma(a1, a2, -b1 * b2), Pi = fma(a1, b2, a2 * b1);                              /* Pi */
+        const double Sr = a1 + a2, Si = b1 + b2;                                                         /* Sg */
+        const double pe = se[p] * hE, po = so[p] * hO;
+        const double Nr = -fma(pe, b2, po * b1), Ni = fma(pe, a2, po * a1);                              /* Nu */
+        const double Xr = fma(Pr, Pr, -Pi * Pi), Xi = (Pr + Pr) * Pi;                                    /* Pi^2 */
+        const double Yr = fma(Nr, Nr, -Ni * Ni), Yi = (Nr + Nr) * Ni;                                    /* Nu^2 */
+        const double Wr = fma(Sr, Sr, -Si * Si), Wi = (Sr + Sr) * Si;                                    /* Sg^2 */
+        const double Vr = fma(Pr, Nr, -Pi * Ni), Vi = fma(Pr, Ni, Pi * Nr);                              /* Pi Nu */
+        const double Tr = Xr + Yr - Wr, Ti = Xi + Yi - Wi;
+        const double Ar = Xr - Yr + Wr, Ai = Xi - Yi + Wi;                                               /* k A */
+        const double Br = fma(2.0, Vr, Tr), Bi = fma(2.0, Vi, Ti);                                       /* k B / Zt */
+        const double Cr = fma(-2.0, Vr, Tr), Ci = fma(-2.0, Vi, Ti);                                     /* k C Zt */
+        const double Kr = fma(Sr, Pr, -Si * Pi), Ki = fma(Sr, Pi, Si * Pr);                              /* k / 2 */
+        kap2[p] = fma(Kr, Kr, Ki * Ki);
+        u.ar[p] = fma(rz, Cr, Ar); u.ai[p] = fma(rz, Ci, Ai);                                            /* k (A + Rs C) */
+        u.br[p] = fma(rs, Ar, zt * Br); u.bi[p] = fma(rs, Ai, zt * Bi);                                  /* k (B + Rs A) */
     }
-    lad_rcp_batch<PTS>(qd, rd);
-    QO_PTS {
-        const double q2r = s21r[p] * s21r[p] - s21i[p] * s21i[p], q2i = 2.0 * s21r[p] * s21i[p];
-        const double p2r = s11r[p] * s11r[p] - s11i[p] * s11i[p], p2i = 2.0 * s11r[p] * s11i[p];
-        const double idr = dr_[p] * rd[p], idi = -di_[p] * rd[p];
-        const double nar = 1.0 - p2r + q2r, nai = q2i - p2i;
-        const double nbr = 1.0 + s11r[p] + s11r[p] + p2r - q2r, nbi = s11i[p] + s11i[p] + p2i - q2i;
-        const double ncr = 1.0 - s11r[p] - s11r[p] + p2r - q2r, nci = -s11i[p] - s11i[p] + p2i - q2i;
-        const double Ar = nar * idr - nai * idi, Ai = nar * idi + nai * idr;
-        const double Br = zt * (nbr * idr - nbi * idi), Bi = zt * (nbr * idi + nbi * idr);
-        const double Cr = yt * (ncr * idr - nci * idi), Ci = yt * (ncr * idi + nci * idr);
-        u.ar[p] = fma(rs, Cr, Ar); u.ai[p] = fma(rs, Ci, Ai);
-        u.br[p] = fma(rs, Ar, Br); u.bi[p] = fma(rs, Ai, Bi);
-    }
+    lad_rcp_batch<PTS>(kap2, scale);
+    QO_PTS scale[p] *= 0.25;                                                                             /* 1/|k|^2 */
 }
 
 /* per-sample coefficient records, one lane per element (perturbation is the shared bit-exact stream) */
@@ -184,8 +207,9 @@ __device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int
         break;
     case OP_CPL: {
         const double a = p[0] / p[5], b = p[1] / p[5];
-        out[0] = a + 1.0 / a; out[1] = a - 1.0 / a; out[2] = b + 1.0 / b; out[3] = b - 1.0 / b;
-        out[4] = p[2] / (360.0 * p[4]); out[5] = p[3] / (360.0 * p[4]); out[6] = p[5]; out[7] = 1.0 / p[5];
+        out[0] = a + 1.0 / a; out[1] = 0.5 * (a - 1.0 / a); out[2] = b + 1.0 / b; out[3] = 0.5 * (b - 1.0 / b);
+        out[4] = p[2] / (360.0 * p[4]); out[5] = p[3] / (360.0 * p[4]); out[6] = p[5]; out[7] = prog->rs / p[5];
+        out[8] = out[4] - prog->nom[e][2] / (360.0 * prog->nom[e][4]); out[9] = out[5] - prog->nom[e][3] / (360.0 * prog->nom[e][4]);
         break;
     }
     default: break;
@@ -198,6 +222,7 @@ struct LadParams {
     const DevProg *prog;
     const double2 *wt, *wit, *wsqt;          /* w, 1/w, w^2 per grid point, two points per entry */
     const uchar2 *m2;                        /* per-point spec bit masks */
+    const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the NOMINAL even/odd angle per grid point (cpl_fast) */
     unsigned long long *counters;
     unsigned long long *ticket;              /* next unclaimed sample of this launch (zeroed on the stream before it) */
     unsigned long long sample_offset, nsamples, seed;
@@ -205,6 +230,7 @@ struct LadParams {
     double thr[QO_LAD_NSPEC];                /* sign-adjusted thresholds: FAIL iff tracker > thr */
     unsigned int sgn[QO_LAD_NSPEC];          /* 0x80000000 for "max dB" specs (tracker holds -|den|^2) */
     int npairs, n_var, n_ops, nspec, dist, hist_spec, hist_bins, hist_kind;
+    int cpl_fast, cpl_same;                  /* small-angle table path usable; nominal even and odd angles identical */
 };
 
 /*
@@ -273,8 +299,28 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 mk[2 * q] = j < npairs ? m.x : 0u; mk[2 * q + 1] = j < npairs ? m.y : 0u;
             }
             LadRow<PTS> u;
-            QO_PTS { u.ar[p] = 1.0; u.ai[p] = 0.0; u.br[p] = rs; u.bi[p] = 0.0; }
-            if (CPL) lad_cpl_first<PTS>(coefs, w, rs, u);
+            double cscale[PTS];
+            QO_PTS { u.ar[p] = 1.0; u.ai[p] = 0.0; u.br[p] = rs; u.bi[p] = 0.0; cscale[p] = 1.0; }
+            if (CPL) {
+                double tse[PTS], tce[PTS], tso[PTS], tco[PTS];
+                QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
+                if (P.cpl_fast) {
+#pragma unroll
+                    for (int q = 0; q < PP; q++) {
+                        const int j = j0 + 32 * q;
+                        const int jc = j < npairs ? j : npairs - 1;
+                        const double2 a = P.cse[jc], b = P.cce[jc];
+                        tse[2 * q] = a.x; tse[2 * q + 1] = a.y; tce[2 * q] = b.x; tce[2 * q + 1] = b.y;
+                        if (!P.cpl_same) {
+                            const double2 c = P.cso[jc], d = P.cco[jc];
+                            tso[2 * q] = c.x; tso[2 * q + 1] = c.y; tco[2 * q] = d.x; tco[2 * q + 1] = d.y;
+                        }
+                    }
+                    lad_cpl_first<PTS, true>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                } else {
+                    lad_cpl_first<PTS, false>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                }
+            }
             const unsigned int lad = coefs + (CPL ? QO_LAD_CPL : 0) * 8u;
 #pragma unroll
             for (int e = 0; e < N; e++) {
@@ -293,6 +339,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
             QO_PTS {
                 const double den_r = fma(u.ar[p], rl, u.br[p]), den_i = fma(u.ai[p], rl, u.bi[p]);
                 den2[p] = fma(den_r, den_r, den_i * den_i);
+                if (CPL) den2[p] *= cscale[p];
             }
             /* Trackers.  Spec bands are contiguous in frequency, so nearly every warp-iteration sees ONE
              * mask value on all its points: a warp vote picks the fast path (a plain running max per active

@@ -396,3 +396,32 @@ def test_gpu_sweep_to_qucs_dataset(Q, W, ctx, golden_dat, tmp_path):
     assert relerr(r["S[2,1]"], golden_dat["S21"]) <= TOL64 and relerr(r["S[1,2]"], golden_dat["S12"]) <= TOL64
     assert np.max(np.abs(r["S21_dB"] - golden_dat["S21_dB"])) <= 1e-9
     assert np.all(np.abs(r["S[1,1]"] - golden_dat["S11"]) <= TOL64 * np.maximum(np.abs(golden_dat["S11"]), 0.02))
+
+
+def test_single_process_multi_gpu_ctx_matches_one_gpu(Q, W, ctx):
+    """qo_ctx_create(N): one process, samples sharded over N GPUs, counters combined by ncclAllReduce --
+    identical u64 counters to the one-GPU run, reduce-only and FULL_S.  Needs >= 2 visible GPUs."""
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
+    w = W.cfg5()
+    n = 20001
+    one = ctx.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, **w.hist)
+    for g in [x for x in (2, 4, 8) if x <= ng]:
+        c = Q.Context(ngpus=g)
+        assert c.num_devices == g
+        got = c.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, **w.hist)
+        assert got["n_pass"] == one["n_pass"] and got["n_total"] == n
+        assert np.array_equal(got["fail_per_spec"], one["fail_per_spec"]) and np.array_equal(got["hist"], one["hist"])
+        plan = Q.Plan(c, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+        plan.launch(0, 7000)
+        plan.launch(7000, n - 7000)
+        acc = plan.read()
+        assert acc["n_pass"] == one["n_pass"] and np.array_equal(acc["hist"], one["hist"])
+        plan.close()
+        w4 = W.cfg4(33, 257)[1]
+        a = ctx.mc_run(w4.net, w4.f, [], w4.seed, 33, w4.tols, mode=Q.MODE_FULL_S)["s"]
+        b = c.mc_run(w4.net, w4.f, [], w4.seed, 33, w4.tols, mode=Q.MODE_FULL_S)["s"]
+        assert np.array_equal(a, b)
+        c.close()

@@ -61,7 +61,9 @@ typedef enum {
     QO_MCORN = 15,                           /* p0 = W                                   */
     QO_MTEE = 16,                            /* p0 = Wa, p1 = Wb, p2 = W2; opens the side arm:
                                                 the following elements, junction outward, up to */
-    QO_MOPEN = 17                            /* p0 = W; open end closing the side arm    */
+    QO_MOPEN = 17,                           /* p0 = W; open end closing the side arm    */
+    QO_SBLOCK = 18                           /* measured two-port (Touchstone): p0 = block index in the net,
+                                                p1 = 1 polar / 0 rectangular interpolation (Qucs SPfile)   */
 } qo_kind;
 #define QO_NPARAM 6
 typedef struct { int32_t kind; int32_t flags; double p[QO_NPARAM]; } qo_elem;
@@ -107,6 +109,30 @@ void qo_net_free(qo_net *net);
  * util/pa-lpf-simulation/pa-lpf-simulation.dat:6-5005 */
 int qo_grid_lin(double f0, double f1, int n, double *f);
 int qo_grid_log(double f0, double f1, int n, double *f);
+
+/* ---- Touchstone two-port blocks (Qucs "SPfile") ------------------------- */
+/* The measured inductors the reference's bias schematics pull in with
+ *   <SPfile ... "11SQ39N.S2P" ... "polar" "linear">  util/pa-bias-simulation/pa-bias-simulation.sch:39
+ *   <SPfile ... "06HP47N.s2p" ... "polar" "linear">  util/preamp-bias-simulation/preamp-bias-simulation.sch:32
+ * and docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p.  Touchstone v1, 2 ports, "# HZ|KHZ|MHZ|GHZ S MA|DB|RI R z0". */
+typedef struct qo_s2p qo_s2p;
+int qo_s2p_load(const char *path, qo_s2p **out);
+int qo_s2p_from_arrays(const double *f, int n, const qo_c64 *s11, const qo_c64 *s21, const qo_c64 *s12, const qo_c64 *s22,
+                       double z0, qo_s2p **out);
+int qo_s2p_num_points(const qo_s2p *blk);
+double qo_s2p_z0(const qo_s2p *blk);
+int qo_s2p_get(const qo_s2p *blk, double *f, qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22, int cap); /* returns n */
+/* S at arbitrary frequencies: linear in f between the bracketing points, on (|S|, phase along the shorter arc)
+ * when polar != 0 else on (re, im); end values held outside the measured range.  Host routine (the kernels
+ * use the same routine at plan creation to build the per-frequency ABCD table of the block). */
+int qo_s2p_interp(const qo_s2p *blk, const double *f, int nf, int polar, qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22);
+/* least-squares fit of the ESR/SRF inductor model Z = (r0 + r1 sqrt(f) + jwL) || 1/(jwCp) to a block measured
+ * in series between its ports, over [fmin, fmax]; srf and rms_rel nullable */
+int qo_s2p_fit_inductor(const qo_s2p *blk, double fmin, double fmax, double *L, double *r0, double *r1, double *cp,
+                        double *srf, double *rms_rel);
+void qo_s2p_free(qo_s2p *blk);
+/* a one-element network holding a copy of the block; combine with qo_net_concat */
+int qo_net_from_sblock(const qo_s2p *blk, int polar, double rs, double rl, qo_net **out);
 
 /* ---- Qucs dataset (.dat) reader / writer --------------------------------- */
 /* The layout Qucs 0.0.19 writes for util/pa-lpf-simulation/pa-lpf-simulation.dat:1-35018:

@@ -474,8 +474,75 @@ static cx z_cap(double C, double R, double Ls, double w)
 }
 
 /* evaluate the whole cascade at one frequency: ABCD, left (source) to right (load) */
-static int eval_abcd(const ref_elem *e, int n, double f, m22 *out)
+/* ------------------------------------------------------------------ */
+/* Measured two-port blocks (Qucs SPfile): util/pa-bias-simulation/     */
+/* pa-bias-simulation.sch:39, util/preamp-bias-simulation/...sch:32     */
+/* ("polar" "linear").  Blocks are registered by index before a sweep.  */
+/* ------------------------------------------------------------------ */
+#define REF_MAX_BLK 8
+static struct { int n; double z0; double *f; double *s; } g_blk[REF_MAX_BLK];
+
+void ref_sblock_clear(void)
 {
+    for (int i = 0; i < REF_MAX_BLK; i++) { free(g_blk[i].f); free(g_blk[i].s); memset(&g_blk[i], 0, sizeof g_blk[i]); }
+}
+
+/* s: n x 8 doubles = (re, im) of S11, S21, S12, S22 per point */
+int ref_sblock_register(int idx, const double *f, const double *s, int n, double z0)
+{
+    if (idx < 0 || idx >= REF_MAX_BLK || n < 1 || !(z0 > 0)) return -1;
+    free(g_blk[idx].f); free(g_blk[idx].s);
+    g_blk[idx].f = (double *)malloc((size_t)n * sizeof(double));
+    g_blk[idx].s = (double *)malloc((size_t)n * 8 * sizeof(double));
+    if (!g_blk[idx].f || !g_blk[idx].s) return -5;
+    memcpy(g_blk[idx].f, f, (size_t)n * sizeof(double));
+    memcpy(g_blk[idx].s, s, (size_t)n * 8 * sizeof(double));
+    g_blk[idx].n = n; g_blk[idx].z0 = z0;
+    return 0;
+}
+
+/* linear interpolation in frequency of one S entry, polar (|S| and phase along the shorter arc) or rectangular;
+ * the end values are held outside the measured range */
+static cx blk_entry(int idx, int j, double f, int polar)
+{
+    const int n = g_blk[idx].n;
+    const double *F = g_blk[idx].f, *S = g_blk[idx].s;
+    int k = 0;
+    if (f <= F[0] || n == 1) return cx_mk(S[2 * j], S[2 * j + 1]);
+    if (f >= F[n - 1]) return cx_mk(S[8 * (size_t)(n - 1) + 2 * j], S[8 * (size_t)(n - 1) + 2 * j + 1]);
+    while (k + 2 < n && F[k + 1] <= f) k++;
+    const cx a = cx_mk(S[8 * (size_t)k + 2 * j], S[8 * (size_t)k + 2 * j + 1]);
+    const cx b = cx_mk(S[8 * (size_t)(k + 1) + 2 * j], S[8 * (size_t)(k + 1) + 2 * j + 1]);
+    const double t = (f - F[k]) / (F[k + 1] - F[k]);
+    if (!polar) return cx_mk(a.re + t * (b.re - a.re), a.im + t * (b.im - a.im));
+    double pa = atan2(a.im, a.re), dp = atan2(b.im, b.re) - pa;
+    if (dp > PI) dp -= 2.0 * PI;
+    if (dp < -PI) dp += 2.0 * PI;
+    const double ma = sqrt(cx_abs2(a)), mb = sqrt(cx_abs2(b));
+    const double m = ma + t * (mb - ma), ph = pa + t * dp;
+    return cx_mk(m * cos(ph), m * sin(ph));
+}
+
+/* S (reference z0) -> chain matrix; *det = S12 / S21 */
+static int blk_abcd(int idx, double f, int polar, m22 *M, cx *det)
+{
+    if (idx < 0 || idx >= REF_MAX_BLK || g_blk[idx].n == 0) return -1;
+    const double z0 = g_blk[idx].z0;
+    const cx s11 = blk_entry(idx, 0, f, polar), s21 = blk_entry(idx, 1, f, polar);
+    const cx s12 = blk_entry(idx, 2, f, polar), s22 = blk_entry(idx, 3, f, polar);
+    if (s21.re == 0.0 && s21.im == 0.0) return -9;
+    const cx one = cx_mk(1, 0), p = cx_mul(s12, s21), d2 = cx_scale(s21, 2.0);
+    M->a = cx_div(cx_add(cx_mul(cx_add(one, s11), cx_sub(one, s22)), p), d2);
+    M->b = cx_scale(cx_div(cx_sub(cx_mul(cx_add(one, s11), cx_add(one, s22)), p), d2), z0);
+    M->c = cx_scale(cx_div(cx_sub(cx_mul(cx_sub(one, s11), cx_sub(one, s22)), p), d2), 1.0 / z0);
+    M->d = cx_div(cx_add(cx_mul(cx_sub(one, s11), cx_add(one, s22)), p), d2);
+    *det = cx_div(s12, s21);
+    return 0;
+}
+
+static int eval_abcd_det(const ref_elem *e, int n, double f, m22 *out, cx *det_out)
+{
+    cx det = cx_mk(1, 0);
     double w = 2.0 * PI * f;
     m22 M = m_ident(), Mmain = m_ident();
     subst_t sub = { 0, 0, 0, 0, 0, 0 };
@@ -505,6 +572,15 @@ static int eval_abcd(const ref_elem *e, int n, double f, m22 *out)
             break;
         }
         case REF_CPL_THRU: M = m_mul(M, cpl_thru(p[0], p[1], p[2], p[3], p[4], p[5], f)); break;
+        case REF_SBLOCK: {
+            m22 B;
+            cx bd;
+            int rc = blk_abcd((int)p[0], f, p[1] != 0.0, &B, &bd);
+            if (rc) return rc;
+            M = m_mul(M, B);
+            det = cx_mul(det, bd);
+            break;
+        }
         case REF_SUBST:
             sub.er = p[0]; sub.h = p[1]; sub.t = p[2]; sub.tand = p[3]; sub.rho = p[4]; sub.D = p[5];
             have_sub = 1;
@@ -546,12 +622,13 @@ static int eval_abcd(const ref_elem *e, int n, double f, m22 *out)
     }
     if (in_side) return -4;
     *out = M;
+    *det_out = det;
     return 0;
 }
 
 /* ABCD -> power-wave S for real terminations; SURVEY B.1 / A.6;
  * pa-lpf-simulation.sch:19,49 (Pac 50 Ohm), :60 (dB) */
-static void abcd_to_s(const m22 *M, double rs, double rl, cx *s11, cx *s21, cx *s12, cx *s22)
+static void abcd_to_s_det(const m22 *M, cx det, double rs, double rl, cx *s11, cx *s21, cx *s12, cx *s22)
 {
     cx arl = cx_scale(M->a, rl), crr = cx_scale(M->c, rs * rl), drs = cx_scale(M->d, rs);
     cx den = cx_add(cx_add(arl, M->b), cx_add(crr, drs));
@@ -560,19 +637,21 @@ static void abcd_to_s(const m22 *M, double rs, double rl, cx *s11, cx *s21, cx *
     /* S12 = S21 * (AD - BC).  Every supported element is reciprocal, so the cascade
      * determinant is identically 1; evaluating AD - BC numerically instead loses all
      * digits deep in a stop band (|AD| ~ 1e22 against a difference of 1), so the
-     * exact value 1 is used.  (.dat S[1,2] still matches to 3.8e-12.) */
+     * exact value 1 is used.  (.dat S[1,2] still matches to 3.8e-12.)  Measured blocks may be
+     * non-reciprocal: their determinants S12/S21 are carried separately in `det`. */
     *s11 = cx_div(n11, den);
     *s21 = cx_div(cx_mk(2.0 * sqrt(rs * rl), 0), den);
-    *s12 = *s21;
+    *s12 = cx_mul(*s21, det);
     *s22 = cx_div(n22, den);
 }
 
 static int eval_s(const ref_elem *e, int n, double rs, double rl, double f, cx *s11, cx *s21, cx *s12, cx *s22)
 {
     m22 M;
-    int rc = eval_abcd(e, n, f, &M);
+    cx det;
+    int rc = eval_abcd_det(e, n, f, &M, &det);
     if (rc) return rc;
-    abcd_to_s(&M, rs, rl, s11, s21, s12, s22);
+    abcd_to_s_det(&M, det, rs, rl, s11, s21, s12, s22);
     return 0;
 }
 

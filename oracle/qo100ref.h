@@ -49,7 +49,8 @@ enum {
     REF_MLIN = 14,                         /* p0=W p1=L */
     REF_MCORN = 15,                        /* p0=W */
     REF_MTEE = 16,                         /* p0=Wa p1=Wb p2=W2 ; opens the side arm */
-    REF_MOPEN = 17                         /* p0=W ; closes the side arm */
+    REF_MOPEN = 17,                        /* p0=W ; closes the side arm */
+    REF_SBLOCK = 18                        /* measured two-port: p0 = registered block index, p1 = 1 polar / 0 rectangular */
 };
 
 typedef struct { int32_t kind; int32_t flags; double p[6]; } ref_elem;
@@ -86,6 +87,10 @@ int ref_cheby_g(int n, double ripple_db, double *g);      /* g[0..n-1] */
 int ref_butter_g(int n, double *g);
 int ref_ladder_lpf(const double *g, int n, double fc, double z0, int series_first, ref_elem *out);
 void ref_add_parasitics(ref_elem *e, int n, double fc, double q_l, double srf_l_mult, double esr_c, double srf_c_mult);
+
+/* measured two-port blocks (Touchstone data handed over by the tests); s = n x 8 doubles, (re,im) of S11,S21,S12,S22 */
+int ref_sblock_register(int idx, const double *f, const double *s, int n, double z0);
+void ref_sblock_clear(void);
 
 /* nominal sweep; s?? are interleaved (re,im) arrays of 2*nf doubles, nullable; gd nullable */
 int ref_sweep(const ref_elem *e, int n, double rs, double rl, const double *f, int nf,

@@ -87,6 +87,8 @@ def lib():
         L.ref_ms_quasi.argtypes = [C.c_double] * 4 + [dp] * 3
         L.ref_ms_disp.argtypes = [C.c_double] * 6 + [dp] * 2
         L.ref_cpl_analyze.argtypes = [C.c_double] * 8 + [dp] * 4
+        L.ref_sblock_register.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double]
+        L.ref_sblock_clear.argtypes = []
         _lib = L
     return _lib
 
@@ -104,6 +106,22 @@ def make_elems(items):
         for k, v in enumerate(p):
             arr[i].p[k] = float(v)
     return arr
+
+
+def sblock_register(idx, f, s11, s21, s12, s22, z0=50.0):
+    """Hand a measured two-port to the oracle under block index idx (REF_SBLOCK elements refer to it by p0)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    s = np.empty((len(f), 8))
+    for j, a in enumerate((s11, s21, s12, s22)):
+        a = np.asarray(a, dtype=np.complex128)
+        s[:, 2 * j], s[:, 2 * j + 1] = a.real, a.imag
+    rc = lib().ref_sblock_register(int(idx), _dp(f), _dp(np.ascontiguousarray(s)), len(f), float(z0))
+    if rc:
+        raise RuntimeError("ref_sblock_register failed: %d" % rc)
+
+
+def sblock_clear():
+    lib().ref_sblock_clear()
 
 
 def elems_to_list(arr, n=None):

@@ -75,6 +75,7 @@ struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
     void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
+    double2 *sblk, *sdet;      /* OP_SBLOCK: ABCD per (block, grid point); product of block determinants per point */
     void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
     uchar2 *m2;
     double *fgrid;             /* generic kernel */
@@ -218,6 +219,7 @@ static double alg_flops(int opcode)
     case OP_SHUNT_LOSSY_C: return 9 + 16;
     case OP_TLINE: return 56 + 10;
     case OP_CPL: return 56 + 40;
+    case OP_SBLOCK: return 56;
     default: return 0;
     }
 }
@@ -254,6 +256,10 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
         case QO_SHUNT_LC_PAR: op = OP_SHUNT_LCP; nco = 2; break;
         case QO_TLINE: op = OP_TLINE; nco = 3; trig = 1; break;
         case QO_CPL_THRU: op = OP_CPL; nco = 8; trig = 1; break;
+        case QO_SBLOCK:
+            op = OP_SBLOCK; nco = 1; trig = 1;
+            if (el->p[0] < 0 || el->p[0] >= net->nblk) { qo_set_error("element %d: S-parameter block %g is not in the net", e, el->p[0]); return QO_ERR_ARG; }
+            break;
         case QO_SUBST: op = OP_SUBST; ustrip = 1; break;
         case QO_MLIN: op = OP_MLIN; ustrip = 1; break;
         case QO_MCORN: op = OP_MCORN; ustrip = 1; break;
@@ -360,6 +366,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->wsq2); cudaFree(d->m2);
         for (int t = 0; t < 4; t++) cudaFree(d->cpl_tab[t]);
         cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters); cudaFree(d->ticket);
+        cudaFree(d->sblk); cudaFree(d->sdet);
     }
     delete p;
 }
@@ -403,6 +410,42 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         w[k] = two_pi * fk; wi[k] = 1.0 / w[k]; wsq[k] = w[k] * w[k];
         wf[k] = (float)w[k]; wif[k] = (float)wi[k];
         m[k] = k < nf ? p->maskv[k] : 0;
+    }
+    /* measured two-port blocks: interpolate every block at every grid point (Qucs SPfile "linear"), convert to
+     * ABCD at the file's reference impedance; blocks carry no tolerances, so this happens once per plan */
+    std::vector<double2> sblk, sdet;
+    int nonrecip = 0;
+    if (net->nblk > 0 && !p->generic) {
+        int polar[QO_MAX_BLK];
+        for (int b = 0; b < net->nblk; b++) polar[b] = 1;
+        int used = 0;
+        for (int e = 0; e < net->n; e++)
+            if (net->e[e].kind == QO_SBLOCK) { polar[(int)net->e[e].p[0]] = net->e[e].p[1] != 0.0; used = 1; }
+        if (used) {
+            const int npts = 2 * np;
+            sblk.resize((size_t)net->nblk * npts * 4);
+            sdet.assign((size_t)npts, make_double2(1.0, 0.0));
+            for (int b = 0; b < net->nblk; b++)
+                for (int k = 0; k < npts; k++) {
+                    qo_c64 sv[4], m[4];
+                    qo_s2p_eval(net->blk[b], f[k < nf ? k : nf - 1], polar[b], sv);
+                    if (!qo_s_to_abcd(sv, net->blk[b]->z0, m)) {
+                        qo_set_error("S-parameter block %d has S21 = 0 at %g Hz: no chain matrix", b, f[k < nf ? k : nf - 1]);
+                        delete p; return QO_ERR_RANGE;
+                    }
+                    for (int q = 0; q < 4; q++) sblk[((size_t)b * npts + k) * 4 + q] = make_double2(m[q].re, m[q].im);
+                    /* det(ABCD) = S12 / S21 */
+                    const double d = sv[1].re * sv[1].re + sv[1].im * sv[1].im;
+                    const double dr = (sv[2].re * sv[1].re + sv[2].im * sv[1].im) / d, di = (sv[2].im * sv[1].re - sv[2].re * sv[1].im) / d;
+                    if (fabs(dr - 1.0) > 1e-12 || fabs(di) > 1e-12) nonrecip = 1;
+                    const double2 o = sdet[k];
+                    sdet[k] = make_double2(o.x * dr - o.y * di, o.x * di + o.y * dr);
+                }
+        }
+    }
+    if (net->nblk > 0 && p->generic) {
+        for (int e = 0; e < net->n; e++)
+            if (net->e[e].kind == QO_SBLOCK) { qo_set_error("S-parameter blocks cannot be mixed with microstrip elements yet"); delete p; return QO_ERR_UNSUPPORTED; }
     }
     /* coupler block of the ladder kernel: sin/cos of the NOMINAL mode angles per grid point, usable when
      * every sample's angle stays within 0.05 rad of nominal over the whole grid (qo_ladder.cuh::lad_cpl_first) */
@@ -459,6 +502,14 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 CUP(cudaMemcpyAsync(d->wi2, wi.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
             }
             CUP(cudaMemcpyAsync(d->m2, m.data(), 2 * (size_t)np, cudaMemcpyHostToDevice, st));
+            if (!sblk.empty()) {
+                CUP(cudaMalloc(&d->sblk, sblk.size() * sizeof(double2)));
+                CUP(cudaMemcpyAsync(d->sblk, sblk.data(), sblk.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+                if (nonrecip) {
+                    CUP(cudaMalloc(&d->sdet, sdet.size() * sizeof(double2)));
+                    CUP(cudaMemcpyAsync(d->sdet, sdet.data(), sdet.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+                }
+            }
             if (p->ladder) {
                 CUP(cudaMalloc(&d->wsq2, 2 * (size_t)np * sizeof(double)));
                 CUP(cudaMemcpyAsync(d->wsq2, wsq.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -593,7 +644,7 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     if (n == 0) return QO_OK;
     CU(cudaSetDevice(p->ctx->d[g].device));
     int full_s = p->mode == QO_MODE_FULL_S;
-    QoPlanes pl = { NULL, NULL, NULL, NULL };
+    QoPlanes pl = { NULL, NULL, NULL, NULL, p->d[g].sblk, p->d[g].sdet, 2 * p->npairs };
     if (full_s) {
         if (!full_s_dev) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
         size_t plane = (size_t)plane_samples * (size_t)p->nf;

@@ -28,6 +28,7 @@ enum {
     OP_SER_LOSSY_C, OP_SHUNT_LOSSY_C,        /* (1/C, Ls, R, R*R)  */
     OP_TLINE,                                /* (Z0, 1/Z0, theta/w) */
     OP_CPL,                                  /* (z0e/zt, zt/z0e, z0o/zt, zt/z0o, te/w, to/w, zt, 1/zt) */
+    OP_SBLOCK,                               /* (block index): per-frequency ABCD table of a measured two-port */
     /* distributed microstrip opcodes: generic kernel only */
     OP_SUBST, OP_MLIN, OP_MCORN, OP_MTEE, OP_MOPEN
 };

@@ -9,12 +9,23 @@ extern "C" {
 
 #define QO_MAX_ELEMS 96
 #define QO_TITLE_MAX 512
+#define QO_MAX_BLK 8
+
+/* a Touchstone two-port: n points, s[4*k + {0,1,2,3}] = S11, S21, S12, S22 at f[k] (file order) */
+struct qo_s2p {
+    int n;
+    double z0;
+    double *f;
+    qo_c64 *s;
+};
 
 struct qo_net {
     int n;
     double rs, rl;
     qo_elem e[QO_MAX_ELEMS];
     char title[QO_TITLE_MAX];
+    int nblk;                          /* S-parameter blocks referenced by QO_SBLOCK elements (owned copies) */
+    struct qo_s2p *blk[QO_MAX_BLK];
 };
 
 /* thread-local error detail */
@@ -25,6 +36,12 @@ void qo_clear_error(void);
 char *qo_read_file(const char *path, size_t *len);                 /* malloc'd, NUL-terminated */
 int qo_parse_value(const char *s, double *out, const char **unit); /* "4.700 pF" / "0.6 mm" / ".75e-3" */
 qo_net *qo_net_alloc(void);
+
+/* qo_s2p.c */
+qo_s2p *qo_s2p_alloc(int n);
+qo_s2p *qo_s2p_clone(const qo_s2p *a);
+void qo_s2p_eval(const qo_s2p *b, double f, int polar, qo_c64 s[4]);      /* SPfile "linear" interpolation */
+int qo_s_to_abcd(const qo_c64 s[4], double z0, qo_c64 abcd[4]);           /* 0 when S21 == 0 */
 
 #ifdef __cplusplus
 }

@@ -94,10 +94,18 @@ __device__ __forceinline__ void mul_full(Abcd2<T> &m, int p, T ar, T ai, T br, T
 }
 
 /* ---- the element chain for two points ------------------------------------ */
+struct QoPlanes {
+    double2 *s11, *s21, *s12, *s22;
+    /* measured two-port blocks (OP_SBLOCK): ABCD per (block, grid point) as four double2, and the product of the
+     * blocks' determinants per grid point (NULL when every block is reciprocal) */
+    const double2 *sblk, *sdet;
+    int npts;
+};
+
 template <typename T, bool TRIG>
 __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const int *__restrict__ s_coff,
                                           const T *__restrict__ coef, int n_ops, const T (&w)[2], const T (&wi)[2],
-                                          Abcd2<T> &m)
+                                          Abcd2<T> &m, const QoPlanes &planes, int k0)
 {
     QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
             m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
@@ -192,6 +200,14 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
                         T Cr = yt * (ncr * idr - nci * idi), Ci2 = yt * (ncr * idi + nci * idr);
                         mul_full(m, p, Ar, Ai, Br, Bi, Cr, Ci2, Ar, Ai);
                     }
+                } else if (s_op[e] == OP_SBLOCK) {
+                    const int blk = (int)cf[0];
+                    QO_P2 {
+                        const int k = min(k0 + p, planes.npts - 1);
+                        const double2 *t = planes.sblk + ((size_t)blk * (size_t)planes.npts + (size_t)k) * 4;
+                        const double2 a = t[0], b = t[1], c = t[2], d = t[3];
+                        mul_full(m, p, T(a.x), T(a.y), T(b.x), T(b.y), T(c.x), T(c.y), T(d.x), T(d.y));
+                    }
                 }
             }
             break;
@@ -224,6 +240,7 @@ __device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int 
     case OP_SER_LOSSY_C: case OP_SHUNT_LOSSY_C:
         out[0] = T(1.0 / p[0]); out[1] = T(p[2]); out[2] = T(p[1]); out[3] = T(p[1] * p[1]); break;
     case OP_TLINE: out[0] = T(p[0]); out[1] = T(1.0 / p[0]); out[2] = T(p[1] / (360.0 * p[2])); break;
+    case OP_SBLOCK: out[0] = T(p[0]); break;
     case OP_CPL: {
         double a = p[0] / p[5], b = p[1] / p[5];
         out[0] = T(a + 1.0 / a); out[1] = T(a - 1.0 / a); out[2] = T(b + 1.0 / b); out[3] = T(b - 1.0 / b);
@@ -233,8 +250,6 @@ __device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int 
     default: break;
     }
 }
-
-struct QoPlanes { double2 *s11, *s21, *s12, *s22; };
 
 /* 32 contiguous bytes (two complex doubles) in one 256-bit store; p must be 32-byte aligned */
 __device__ __forceinline__ void qo_st256(double2 *p, double2 a, double2 b)
@@ -302,7 +317,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
             const int jn = j + 32;
             if (jn < hi) { wv = w2[jn]; wiv = wi2[jn]; if (!FULL_S) mv = m2[jn]; }   /* prefetch next pair */
             Abcd2<T> m;
-            qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, w, wi, m);
+            qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, w, wi, m, planes, 2 * j);
             double2 o11[2], o21[2], o22[2];
             QO_P2 {
                 /* den = A Rl + B + C Rs Rl + D Rs ; n11 = A Rl + B - C Rs Rl - D Rs */
@@ -354,18 +369,25 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                  * reciprocal, and the numerical determinant cancels catastrophically in a deep stop band. */
                 const int k = 2 * j;
                 const size_t o = (size_t)s * (size_t)nf + (size_t)k;
+                double2 o12[2] = { o21[0], o21[1] };
+                if (TRIG && planes.sdet) {       /* non-reciprocal measured blocks: S12 = S21 * prod det(block) */
+                    QO_P2 {
+                        const double2 dt = planes.sdet[min(k + p, planes.npts - 1)];
+                        o12[p] = make_double2(o21[p].x * dt.x - o21[p].y * dt.y, o21[p].x * dt.y + o21[p].y * dt.x);
+                    }
+                }
                 if (k + 1 < nf && ((o & 1) == 0) && planes_al32) {
                     if (planes.s21) qo_st256(planes.s21 + o, o21[0], o21[1]);
                     if (planes.s11) qo_st256(planes.s11 + o, o11[0], o11[1]);
                     if (planes.s22) qo_st256(planes.s22 + o, o22[0], o22[1]);
-                    if (planes.s12) qo_st256(planes.s12 + o, o21[0], o21[1]);
+                    if (planes.s12) qo_st256(planes.s12 + o, o12[0], o12[1]);
                 } else {
                     QO_P2 {
                         if (k + p < nf) {
                             if (planes.s21) planes.s21[o + p] = o21[p];
                             if (planes.s11) planes.s11[o + p] = o11[p];
                             if (planes.s22) planes.s22[o + p] = o22[p];
-                            if (planes.s12) planes.s12[o + p] = o21[p];
+                            if (planes.s12) planes.s12[o + p] = o12[p];
                         }
                     }
                 }

@@ -116,9 +116,34 @@ qo_net *qo_net_alloc(void)
     return n;
 }
 
-void qo_net_free(qo_net *net) { free(net); }
+void qo_net_free(qo_net *net)
+{
+    if (!net) return;
+    for (int i = 0; i < net->nblk; i++) qo_s2p_free(net->blk[i]);
+    free(net);
+}
 
+/* QO_SBLOCK elements enter a network only through qo_net_from_sblock / qo_net_concat (they carry an index
+ * into the net's own block list), never through a raw element list */
 static int kind_ok(int k) { return k >= QO_SER_R && k <= QO_MOPEN; }
+
+int qo_net_from_sblock(const qo_s2p *blk, int polar, double rs, double rl, qo_net **out)
+{
+    qo_clear_error();
+    if (!blk || !out || !(rs > 0) || !(rl > 0)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    qo_net *net = qo_net_alloc();
+    if (!net) return QO_ERR_NOMEM;
+    net->blk[0] = qo_s2p_clone(blk);
+    if (!net->blk[0]) { free(net); return QO_ERR_NOMEM; }
+    net->nblk = 1;
+    net->n = 1; net->rs = rs; net->rl = rl;
+    net->e[0].kind = QO_SBLOCK;
+    net->e[0].p[0] = 0.0;
+    net->e[0].p[1] = polar ? 1.0 : 0.0;
+    snprintf(net->title, sizeof net->title, "S-parameter block, %d points, z0 %g", blk->n, blk->z0);
+    *out = net;
+    return QO_OK;
+}
 
 int qo_net_from_elements(const qo_elem *e, int n, double rs, double rl, qo_net **out)
 {
@@ -163,10 +188,18 @@ int qo_net_concat(const qo_net *a, const qo_net *b, qo_net **out)
     qo_clear_error();
     if (!a || !b || !out) return QO_ERR_ARG;
     if (a->n + b->n > QO_MAX_ELEMS) { qo_set_error("too many elements"); return QO_ERR_RANGE; }
+    if (a->nblk + b->nblk > QO_MAX_BLK) { qo_set_error("too many S-parameter blocks (%d > %d)", a->nblk + b->nblk, QO_MAX_BLK); return QO_ERR_RANGE; }
     qo_net *net = qo_net_alloc();
     if (!net) return QO_ERR_NOMEM;
     memcpy(net->e, a->e, (size_t)a->n * sizeof(qo_elem));
     memcpy(net->e + a->n, b->e, (size_t)b->n * sizeof(qo_elem));
+    for (int i = 0; i < a->nblk + b->nblk; i++) {
+        net->blk[i] = qo_s2p_clone(i < a->nblk ? a->blk[i] : b->blk[i - a->nblk]);
+        if (!net->blk[i]) { net->nblk = i; qo_net_free(net); return QO_ERR_NOMEM; }
+    }
+    net->nblk = a->nblk + b->nblk;
+    for (int i = 0; i < b->n; i++)           /* b's blocks follow a's in the merged list */
+        if (net->e[a->n + i].kind == QO_SBLOCK) net->e[a->n + i].p[0] += (double)a->nblk;
     net->n = a->n + b->n; net->rs = a->rs; net->rl = b->rl;
     snprintf(net->title, sizeof net->title, "%.200s | %.200s", a->title, b->title);
     *out = net;

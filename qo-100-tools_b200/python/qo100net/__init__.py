@@ -20,7 +20,7 @@ OK, ERR_ARG, ERR_IO, ERR_PARSE, ERR_UNSUPPORTED, ERR_NOMEM, ERR_NO_DEVICE, ERR_C
     0, -1, -2, -3, -4, -5, -6, -7, -8, -9
 SER_R, SHUNT_R, SER_L, SHUNT_L, SER_C, SHUNT_C = 1, 2, 3, 4, 5, 6
 SER_LC_SER, SER_LC_PAR, SHUNT_LC_SER, SHUNT_LC_PAR = 7, 8, 9, 10
-TLINE, CPL_THRU, SUBST, MLIN, MCORN, MTEE, MOPEN = 11, 12, 13, 14, 15, 16, 17
+TLINE, CPL_THRU, SUBST, MLIN, MCORN, MTEE, MOPEN, SBLOCK = 11, 12, 13, 14, 15, 16, 17, 18
 SPEC_S21_MIN_DB, SPEC_S21_MAX_DB, SPEC_S11_MAX_DB, SPEC_GD_MAX = 1, 2, 3, 4
 DIST_UNIFORM, DIST_GAUSS3S = 0, 1
 TOL_REL, TOL_ABS = 0, 1
@@ -81,6 +81,8 @@ EXPORTS = [
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
     "qo_plan_kernel_name",
+    "qo_s2p_load", "qo_s2p_from_arrays", "qo_s2p_num_points", "qo_s2p_z0", "qo_s2p_get", "qo_s2p_interp",
+    "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
@@ -131,6 +133,15 @@ def lib():
         "qo_plan_flops_per_eval": (C.c_double, [vp]),
         "qo_plan_launches": (C.c_int, [vp]),
         "qo_plan_kernel_name": (C.c_char_p, [vp]),
+        "qo_s2p_load": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "qo_s2p_from_arrays": (C.c_int, [dp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(vp)]),
+        "qo_s2p_num_points": (C.c_int, [vp]),
+        "qo_s2p_z0": (C.c_double, [vp]),
+        "qo_s2p_get": (C.c_int, [vp, dp, vp, vp, vp, vp, C.c_int]),
+        "qo_s2p_interp": (C.c_int, [vp, dp, C.c_int, C.c_int, vp, vp, vp, vp]),
+        "qo_s2p_fit_inductor": (C.c_int, [vp, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp]),
+        "qo_s2p_free": (None, [vp]),
+        "qo_net_from_sblock": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
         "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
         "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
         "qo_dat_write": (C.c_int, [vp, C.c_char_p]),
@@ -270,6 +281,72 @@ def load_trc(path):
     _check(lib().qo_cpl_load_trc(os.fsencode(path), C.byref(z0e), C.byref(z0o), C.byref(ang), C.byref(f0), phys))
     keys = ["er", "h", "ht", "t", "w", "s", "l", "tand"]
     return dict(z0e=z0e.value, z0o=z0o.value, ang=ang.value, f0=f0.value, **{k: phys[i] for i, k in enumerate(keys)})
+
+
+class SBlock:
+    """A measured two-port (Touchstone v1 .s2p; qo_s2p*)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def load(cls, path):
+        h = C.c_void_p()
+        _check(lib().qo_s2p_load(os.fsencode(path), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_arrays(cls, f, s11, s21, s12, s22, z0=50.0):
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        arrs = [np.ascontiguousarray(a, dtype=np.complex128) for a in (s11, s21, s12, s22)]
+        h = C.c_void_p()
+        _check(lib().qo_s2p_from_arrays(_dp(f), len(f), *[a.ctypes.data_as(C.c_void_p) for a in arrs], z0, C.byref(h)))
+        return cls(h)
+
+    @property
+    def z0(self):
+        return lib().qo_s2p_z0(self._h)
+
+    def __len__(self):
+        return _check(lib().qo_s2p_num_points(self._h))
+
+    def data(self):
+        """(f, s11, s21, s12, s22) as stored."""
+        n = len(self)
+        f = np.empty(n)
+        s = [np.empty(n, dtype=np.complex128) for _ in range(4)]
+        _check(lib().qo_s2p_get(self._h, _dp(f), *[a.ctypes.data_as(C.c_void_p) for a in s], n))
+        return (f,) + tuple(s)
+
+    def interp(self, f, polar=True):
+        """Qucs SPfile 'linear' interpolation at the frequencies f -> (s11, s21, s12, s22)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        s = [np.empty(len(f), dtype=np.complex128) for _ in range(4)]
+        _check(lib().qo_s2p_interp(self._h, _dp(f), len(f), int(bool(polar)), *[a.ctypes.data_as(C.c_void_p) for a in s]))
+        return tuple(s)
+
+    def fit_inductor(self, fmin, fmax):
+        """Least-squares fit of Z = (r0 + r1 sqrt(f) + jwL) || 1/(jwCp) -> dict(L, r0, r1, cp, srf, rms_rel)."""
+        v = [C.c_double() for _ in range(6)]
+        _check(lib().qo_s2p_fit_inductor(self._h, fmin, fmax, *[C.byref(x) for x in v]))
+        return dict(zip(("L", "r0", "r1", "cp", "srf", "rms_rel"), [x.value for x in v]))
+
+    def as_net(self, polar=True, rs=50.0, rl=50.0):
+        """A one-element network holding a copy of this block (combine with Net.concat)."""
+        h = C.c_void_p()
+        _check(lib().qo_net_from_sblock(self._h, int(bool(polar)), rs, rl, C.byref(h)))
+        return Net(h)
+
+    def close(self):
+        if self._h:
+            lib().qo_s2p_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Dataset:

@@ -44,6 +44,32 @@ def golden_dat():
 
 
 @pytest.fixture(scope="session")
+def golden_s2p():
+    return np.load(os.path.join(GOLDEN, "touchstone.npz"))
+
+
+def np_spfile(f, fd, sd, polar=True):
+    """Independent numpy restatement of Qucs SPfile 'linear' interpolation (third implementation next to the
+    product's and the oracle's): sd is [n,4] complex (S11 S21 S12 S22) at fd; end values held."""
+    f = np.asarray(f, dtype=float)
+    k = np.clip(np.searchsorted(fd, f, side="right") - 1, 0, len(fd) - 2)
+    t = np.clip((f - fd[k]) / (fd[k + 1] - fd[k]), 0.0, 1.0)[:, None]
+    a, b = sd[k], sd[k + 1]
+    if not polar:
+        return a + t * (b - a)
+    dp = np.angle(b) - np.angle(a)
+    dp = np.where(dp > np.pi, dp - 2 * np.pi, np.where(dp < -np.pi, dp + 2 * np.pi, dp))
+    return (np.abs(a) + t * (np.abs(b) - np.abs(a))) * np.exp(1j * (np.angle(a) + t * dp))
+
+
+def np_s_to_abcd(s, z0):
+    s11, s21, s12, s22 = s[:, 0], s[:, 1], s[:, 2], s[:, 3]
+    d = 2 * s21
+    return np.stack([((1 + s11) * (1 - s22) + s12 * s21) / d, z0 * ((1 + s11) * (1 + s22) - s12 * s21) / d,
+                     ((1 - s11) * (1 - s22) - s12 * s21) / d / z0, ((1 - s11) * (1 + s22) + s12 * s21) / d], axis=1)
+
+
+@pytest.fixture(scope="session")
 def golden_nets():
     return json.load(open(os.path.join(GOLDEN, "networks.json")))
 

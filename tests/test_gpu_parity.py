@@ -425,3 +425,76 @@ def test_single_process_multi_gpu_ctx_matches_one_gpu(Q, W, ctx):
         b = c.mc_run(w4.net, w4.f, [], w4.seed, 33, w4.tols, mode=Q.MODE_FULL_S)["s"]
         assert np.array_equal(a, b)
         c.close()
+
+
+def test_touchstone_blocks_in_cascade(Q, R, W, ctx, golden_s2p):
+    """Row N3 on the GPU: measured two-ports (the reference's Coilcraft inductors, pa-bias-simulation.sch:39 /
+    preamp-bias-simulation.sch:32, and the non-reciprocal driver measurement) cascaded with lumped elements:
+    nominal sweep and FULL_S Monte Carlo vs the oracle and vs an independent numpy restatement."""
+    from conftest import np_s_to_abcd, np_spfile
+    blk = {}
+    for i, key in enumerate(("11SQ39N", "06HP47N", "pa_20W")):
+        fd, sd, z0 = golden_s2p[key + "_f"], golden_s2p[key + "_s"], float(golden_s2p[key + "_z0"])
+        blk[key] = (Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0), fd, sd, z0)
+    R.sblock_clear()
+    # bias-tee like cascade: DC-block C (2.2 pF + 3 Ohm ESR, pa-bias-simulation.sch:28,32) - series inductor block -
+    # shunt C - second inductor block (rectangular interpolation) - series R
+    lumped1 = Q.Net.from_elements([(Q.SER_C, [12e-12, 0.6, 0.0])], 50, 50)
+    lumped2 = Q.Net.from_elements([(Q.SHUNT_C, [2.2e-12, 3.0, 0.0])], 50, 50)
+    lumped3 = Q.Net.from_elements([(Q.SER_R, [4.7])], 50, 75)
+    net = lumped1.concat(blk["11SQ39N"][0].as_net(True)).concat(lumped2).concat(blk["06HP47N"][0].as_net(False)).concat(lumped3)
+    for i, key in enumerate(("11SQ39N", "06HP47N")):
+        _, fd, sd, z0 = blk[key]
+        R.sblock_register(i, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    f = Q.grid_log(5e6, 5e9, 777)
+    g = ctx.sweep(net, f)
+    o = R.sweep(to_ref(R, net), 50, 75, f)
+    _s_close(g, o)
+    # third implementation: numpy 2x2 products
+    w = 2 * np.pi * f
+    def ser(z): return np.stack([np.ones_like(z), z, np.zeros_like(z), np.ones_like(z)], 1)
+    def sh(y): return np.stack([np.ones_like(y), np.zeros_like(y), y, np.ones_like(y)], 1)
+    def mul(a, b): return np.stack([a[:, 0] * b[:, 0] + a[:, 1] * b[:, 2], a[:, 0] * b[:, 1] + a[:, 1] * b[:, 3],
+                                    a[:, 2] * b[:, 0] + a[:, 3] * b[:, 2], a[:, 2] * b[:, 1] + a[:, 3] * b[:, 3]], 1)
+    parts = [ser(0.6 + 1 / (1j * w * 12e-12)),
+             np_s_to_abcd(np_spfile(f, blk["11SQ39N"][1], blk["11SQ39N"][2], True), 50.0),
+             sh(1 / (3.0 + 1 / (1j * w * 2.2e-12))),
+             np_s_to_abcd(np_spfile(f, blk["06HP47N"][1], blk["06HP47N"][2], False), 50.0),
+             ser(np.full_like(w, 4.7, dtype=complex))]
+    M = parts[0]
+    for p_ in parts[1:]:
+        M = mul(M, p_)
+    rs, rl = 50.0, 75.0
+    den = M[:, 0] * rl + M[:, 1] + M[:, 2] * rs * rl + M[:, 3] * rs
+    assert relerr(g[1], 2 * np.sqrt(rs * rl) / den) < 1e-10
+    assert np.max(np.abs(g[0] - (M[:, 0] * rl + M[:, 1] - M[:, 2] * rs * rl - M[:, 3] * rs) / den)) < 1e-10
+    # Monte Carlo over the lumped parts, blocks fixed: yield counters and FULL_S planes vs the oracle
+    tols = [(0, 0, 0, Q.TOL_REL, 0.1), (2, 0, 1, Q.TOL_REL, 0.1), (4, 0, 2, Q.TOL_REL, 0.05)]
+    b1, b2 = (f >= 3e8) & (f <= 9e8), (f >= 4e8) & (f <= 8e8)
+    lim21 = float((20 * np.log10(np.abs(g[1][b1]))).min()) - 0.05
+    lim11 = float((20 * np.log10(np.abs(g[0][b2]))).max()) + 0.1
+    specs = [(Q.SPEC_S21_MIN_DB, 3e8, 9e8, lim21), (Q.SPEC_S11_MAX_DB, 4e8, 8e8, lim11)]
+    hist = dict(hist_bins=24, hist_spec=0, hist_lo=lim21 - 3.0, hist_hi=lim21 + 3.0)
+    got = ctx.mc_run(net, f, specs, 11, 600, tols, **hist)
+    ref = R.mc_run(to_ref(R, net), 50, 75, f, specs, R.mc_cfg(11, 600, tols, **hist), nthreads=8)
+    _assert_counts_equal(ref, got)
+    assert 0 < got["n_pass"] < 600
+    gs = ctx.mc_run(net, f[:301], [], 11, 9, tols, mode=Q.MODE_FULL_S)["s"]
+    os_ = R.mc_run(to_ref(R, net), 50, 75, f[:301], [], R.mc_cfg(11, 9, tols), full_s=True)["s"]
+    _s_close(gs, os_)
+    # non-reciprocal block (the 20 W driver measurement): S12 != S21 must survive the cascade
+    R.sblock_clear()
+    _, fd, sd, z0 = blk["pa_20W"]
+    R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    amp = Q.Net.from_elements([(Q.SER_L, [1e-9, 0.1, 0.0])], 50, 50).concat(blk["pa_20W"][0].as_net(True)).concat(
+        Q.Net.from_elements([(Q.SHUNT_C, [0.5e-12, 0.2, 0.0])], 50, 50))
+    fa = Q.grid_lin(2e7, 9e9, 500)
+    g = ctx.sweep(amp, fa)
+    o = R.sweep(to_ref(R, amp), 50, 50, fa)
+    for i in range(4):
+        assert np.max(np.abs(g[i] - o[i])) <= 1e-9 * max(1.0, float(np.max(np.abs(o[i]))))
+    assert np.max(np.abs(g[1] - g[2])) > 1e-3                     # genuinely non-reciprocal
+    # bare block: the sweep returns the interpolated measurement itself
+    bare = ctx.sweep(blk["pa_20W"][0].as_net(True), fd[10:20])
+    assert np.allclose(np.stack([bare[0], bare[1], bare[2], bare[3]], 1), sd[10:20], rtol=1e-9, atol=1e-12)
+    R.sblock_clear()

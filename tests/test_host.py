@@ -306,3 +306,65 @@ def test_qucs_dataset_round_trip(Q, golden_dat, tmp_path):
         assert np.array_equal(rd["S[2,1]"], golden_dat["S21"]) and np.array_equal(rd["S11_dB"], golden_dat["S11_dB"])
         rd.write(str(tmp_path / "ref_copy.dat"))
         assert open(tmp_path / "ref_copy.dat", "rb").read() == open(ref, "rb").read()
+
+
+def test_touchstone_loader_interp_and_inductor_fit(Q, golden_s2p, tmp_path):
+    """Row N3 (host side).  The Touchstone loader against an independent numpy parse of the reference's three
+    .s2p files (tests/golden/touchstone.npz; read live too when the tree is mounted), spot values from the files,
+    SPfile interpolation against a numpy restatement, and the inductor-model fit against the part values."""
+    from conftest import np_spfile
+    files = {"11SQ39N": "util/pa-bias-simulation/11SQ39N.S2P", "06HP47N": "util/preamp-bias-simulation/06HP47N.s2p",
+             "pa_20W": "docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p"}
+    blocks = {}
+    for key, rel in files.items():
+        fd, sd, z0 = golden_s2p[key + "_f"], golden_s2p[key + "_s"], float(golden_s2p[key + "_z0"])
+        b = Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+        blocks[key] = (b, fd, sd)
+        path = os.path.join(REFERENCE, rel)
+        if os.path.exists(path):
+            live = Q.SBlock.load(path)
+            f, s11, s21, s12, s22 = live.data()
+            assert len(live) == len(fd) and live.z0 == z0 and np.array_equal(f, fd)
+            assert np.allclose(np.stack([s11, s21, s12, s22], 1), sd, rtol=1e-14, atol=0)
+    # 11SQ39N.S2P:6  " 10  0.0241890116 81.640573  0.996771193 -1.37700407 ..." (# MHZ S MA R 50 at :3)
+    b, fd, sd = blocks["11SQ39N"]
+    assert len(b) == 659 and fd[0] == 10e6 and fd[-1] == 3300e6
+    assert abs(sd[0, 0] - 0.0241890116 * np.exp(1j * np.deg2rad(81.640573))) < 1e-15
+    assert abs(sd[0, 1] - 0.996771193 * np.exp(1j * np.deg2rad(-1.37700407))) < 1e-15
+    # pa_20W_vdd_32V_idq_180mA.s2p:8 (# HZ S RI R 50 at :5): 1e7 Hz, S11 = 1.00031 - j0.0752988, S21 = 0.00209503 - j1.33393e-05
+    _, fd3, sd3 = blocks["pa_20W"]
+    assert len(fd3) == 501 and fd3[0] == 1e7 and sd3[0, 0] == complex(1.00031, -0.0752988) and sd3[0, 1] == complex(0.00209503, -1.33393e-05)
+    # interpolation: at the data points exact, between them == numpy restatement, outside held
+    for polar in (True, False):
+        fq = np.concatenate([fd[:5], np.sqrt(fd[:-1] * fd[1:])[::7], [1e3, 5e9]])
+        got = np.stack(b.interp(fq, polar=polar), 1)
+        assert np.allclose(got, np_spfile(fq, fd, sd, polar), rtol=1e-12, atol=1e-15)
+        assert np.allclose(got[:5], sd[:5], rtol=1e-14) and np.allclose(got[-2], sd[0]) and np.allclose(got[-1], sd[-1])
+    # inductor fits (SURVEY 8f N3: 1111SQ-39N 38.4-39.0 nH, SRF > 3.3 GHz; 0603HP-47N ~47 nH,
+    # R 0.30 Ohm @ 1 MHz -> 2.9 Ohm @ 680 MHz, SRF 3.29-3.44 GHz)
+    r = blocks["11SQ39N"][0].fit_inductor(10e6, 500e6)
+    assert 38.3e-9 < r["L"] < 39.0e-9 and 3.2e9 < r["srf"] < 3.6e9 and r["rms_rel"] < 0.01 and 0.05 < r["r0"] < 0.3
+    h = blocks["06HP47N"][0]
+    r = h.fit_inductor(10e6, 500e6)
+    assert 46.5e-9 < r["L"] < 48.0e-9 and r["rms_rel"] < 0.01
+    assert 0.2 < r["r0"] + r["r1"] * 1e3 < 0.45 and 2.3 < r["r0"] + r["r1"] * np.sqrt(680e6) < 3.3
+    r = h.fit_inductor(1e6, 6e9)                       # the resonance lies inside the data: SRF from the sign change of Im Y
+    assert 3.29e9 < r["srf"] < 3.44e9 and r["cp"] > 0
+    with pytest.raises(Q.QoError):
+        blocks["pa_20W"][0].fit_inductor(1e7, 1e10)    # an amplifier is not a series inductor
+    # loader error paths and formats (DB, GHz, comments, wrapped lines)
+    (tmp_path / "a.s2p").write_text("! c\n# GHz S DB R 75\n1.0 -20 90 -0.5 -10\n -0.5 -10 -20 90 ! tail\n2.0 -20 45 -1 -20 -1 -20 -20 45\n")
+    a = Q.SBlock.load(str(tmp_path / "a.s2p"))
+    f, s11, s21, s12, s22 = a.data()
+    assert a.z0 == 75 and list(f) == [1e9, 2e9] and abs(s11[0] - 0.1j) < 1e-15 and abs(abs(s21[1]) - 10 ** (-1 / 20)) < 1e-15
+    for bad in ("# MHz Y MA R 50\n1 0 0 0 0 0 0 0 0\n", "# MHz S MA R 50\n1 0 0 0 0\n", "# MHz S MA R 50\n", "# MHz S MA R 50\n2 1 0 1 0 1 0 1 0\n1 1 0 1 0 1 0 1 0\n"):
+        (tmp_path / "bad.s2p").write_text(bad)
+        with pytest.raises(Q.QoError):
+            Q.SBlock.load(str(tmp_path / "bad.s2p"))
+    # a net with blocks: concat re-indexes, raw element lists cannot smuggle a block index in
+    n1 = blocks["11SQ39N"][0].as_net(polar=True)
+    n2 = blocks["06HP47N"][0].as_net(polar=False)
+    cat = n1.concat(Q.Net.from_elements([(Q.SHUNT_C, [2.2e-12, 3.0, 0.0])], 50, 50)).concat(n2)
+    assert [(k, p[:2]) for k, p in cat.elements] == [(Q.SBLOCK, [0.0, 1.0]), (Q.SHUNT_C, [2.2e-12, 3.0]), (Q.SBLOCK, [1.0, 0.0])]
+    with pytest.raises(Q.QoError):
+        Q.Net.from_elements([(Q.SBLOCK, [0.0, 1.0])], 50, 50)

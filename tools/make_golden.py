@@ -7,6 +7,9 @@ Writes
   tests/golden/pa_lpf_dat.npz   -- util/pa-lpf-simulation/pa-lpf-simulation.dat:5-35017 (all 5000 points)
   tests/golden/networks.json    -- element lists of every rf-tools SVG / Qucs .sch in the tree,
                                    as read by the product loader (qo_net_load_*), + .trc contents
+  tests/golden/touchstone.npz   -- the three Touchstone files of the tree (util/pa-bias-simulation/11SQ39N.S2P,
+                                   util/preamp-bias-simulation/06HP47N.s2p, docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p)
+                                   parsed by an independent numpy parser (python tools/make_golden.py /root/reference touchstone)
   tests/golden/appendix_b.json  -- 40-digit mpmath evaluation of the textbook ladder / coupled-line
                                    equations (SURVEY App. B) at the frequencies the survey tabulates;
                                    an implementation independent of both the oracle and the product.
@@ -195,8 +198,52 @@ def golden_appendix_b():
     print("appendix_b.json:", len(cases), "cases")
 
 
+S2PS = {"11SQ39N": "util/pa-bias-simulation/11SQ39N.S2P", "06HP47N": "util/preamp-bias-simulation/06HP47N.s2p",
+        "pa_20W": "docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p"}
+
+
+def parse_s2p(path):
+    """Independent (numpy) Touchstone v1 2-port parser -- NOT the product loader, so that the fixture checks it."""
+    scale, fmt, z0, rows = 1e9, "MA", 50.0, []
+    for ln in open(path, errors="replace"):
+        ln = ln.split("!")[0].strip()
+        if not ln:
+            continue
+        if ln.startswith("#"):
+            t = ln[1:].upper().split()
+            for i, tok in enumerate(t):
+                if tok in ("HZ", "KHZ", "MHZ", "GHZ"):
+                    scale = {"HZ": 1.0, "KHZ": 1e3, "MHZ": 1e6, "GHZ": 1e9}[tok]
+                elif tok in ("MA", "DB", "RI"):
+                    fmt = tok
+                elif tok == "R":
+                    z0 = float(t[i + 1])
+            continue
+        rows += [float(x) for x in ln.split()]
+    a = np.array(rows).reshape(-1, 9)
+    x, y = a[:, 1::2], a[:, 2::2]
+    if fmt == "RI":
+        s = x + 1j * y
+    else:
+        s = (10 ** (x / 20) if fmt == "DB" else x) * np.exp(1j * np.deg2rad(y))
+    return a[:, 0] * scale, s, z0          # columns of s: S11 S21 S12 S22
+
+
+def golden_touchstone():
+    out = {}
+    for key, p in S2PS.items():
+        f, s, z0 = parse_s2p(os.path.join(REF, p))
+        out[key + "_f"], out[key + "_s"], out[key + "_z0"] = f, s, np.array(z0)
+        print("touchstone", key, len(f), "points", f[0], f[-1])
+    np.savez_compressed(os.path.join(OUT, "touchstone.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "touchstone":
+        golden_touchstone()
+        sys.exit(0)
     golden_dat()
     golden_networks()
     golden_appendix_b()
+    golden_touchstone()

@@ -287,8 +287,10 @@ def main():
         nthr = R.max_threads()
         n = 40000
         v, _ = cpu_reference(wl, n, 2, 1, nthr)
+        v1, _ = cpu_reference(wl, 2000, 1, 0, 1)          # the "single-threaded C loop over the same model" of north_star
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": nthr, "kind": "port",
-                                "sample": "%d samples x %d freq, 2 timed passes, OpenMP over samples" % (n, nf)}
+                                "sample": "%d samples x %d freq, 2 timed passes, OpenMP over samples" % (n, nf),
+                                "single_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": "2000 samples x %d freq, 1 pass" % nf}}
         # HBM-bound mode (BASELINE config 4): full S-matrix written out, 64 B/eval
         try:
             from qo100net import workloads as W

@@ -308,7 +308,12 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
         case QO_SPEC_S21_MIN_DB: hp->spec_kind[s] = SK_DEN2_MAX; hp->spec_thr[s] = ustrip ? lin : hp->k21 * hp->k21 / lin; break;
         case QO_SPEC_S21_MAX_DB: hp->spec_kind[s] = SK_DEN2_MIN; hp->spec_thr[s] = ustrip ? lin : hp->k21 * hp->k21 / lin; break;
         case QO_SPEC_S11_MAX_DB: hp->spec_kind[s] = SK_S11_MAX; hp->spec_thr[s] = lin; hp->need_s11 = 1; break;
-        case QO_SPEC_GD_MAX: qo_set_error("QO_SPEC_GD_MAX is not implemented in the Monte-Carlo kernels yet"); return QO_ERR_UNSUPPORTED;
+        case QO_SPEC_GD_MAX:        /* limit in seconds; evaluated in-kernel by the central difference of arg S21 */
+            if (ustrip) { qo_set_error("QO_SPEC_GD_MAX is not available for microstrip networks"); return QO_ERR_UNSUPPORTED; }
+            for (int e = 0; e < net->n; e++)
+                if (net->e[e].kind == QO_SBLOCK) { qo_set_error("QO_SPEC_GD_MAX is not available for networks with measured blocks"); return QO_ERR_UNSUPPORTED; }
+            hp->spec_kind[s] = SK_GD_MAX; hp->spec_thr[s] = sp->limit; hp->need_gd |= 1 << s;
+            break;
         default: qo_set_error("spec %d: unknown kind %d", s, sp->kind); return QO_ERR_ARG;
         }
         int hits = 0;
@@ -390,6 +395,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     int rc = build_prog(net, f, nf, spec, nspec, cfg, &p->hp, &p->generic, &p->flops_per_eval, &p->maskv);
     if (rc) { delete p; return rc; }
     if (p->generic && p->precision == 32) { delete p; qo_set_error("FP32 mode covers lumped/TL networks only"); return QO_ERR_UNSUPPORTED; }
+    if (p->hp.need_gd && p->precision == 32) { delete p; qo_set_error("group-delay specs need FP64 (the 1e-6 relative frequency step is 8 float ulps)"); return QO_ERR_UNSUPPORTED; }
     p->ncnt = 2 + nspec + p->hp.hist_bins;
     p->f.assign(f, f + nf);
     p->ladder = ladder_eligible(&p->hp, p->mode, p->precision, p->generic, &p->lad_n, &p->lad_first, &p->lad_cpl);
@@ -573,11 +579,12 @@ static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned lon
     unsigned long long blocks = (units + QO_WARPS - 1) / QO_WARPS;
     int grid = (int)(blocks < (unsigned long long)resident ? blocks : (unsigned long long)resident);
     if (grid < 1) grid = 1;
-#define QO_LAUNCH(FS, TR)                                                                                       \
-    qo_mc_lumped_kernel<T, FS, TR><<<grid, QO_TPB, 0, dc->stream>>>(d->prog, (const V2 *)d->w2, (const V2 *)d->wi2, \
-                                                                     d->m2, p->nf, p->npairs, ppc, nchunks, off, n, cnt, pl)
-    if (full_s) { if (p->hp.has_trig) QO_LAUNCH(true, true); else QO_LAUNCH(true, false); }
-    else { if (p->hp.has_trig) QO_LAUNCH(false, true); else QO_LAUNCH(false, false); }
+#define QO_LAUNCH(FS, TR, GD)                                                                                       \
+    qo_mc_lumped_kernel<T, FS, TR, GD><<<grid, QO_TPB, 0, dc->stream>>>(d->prog, (const V2 *)d->w2, (const V2 *)d->wi2, \
+                                                                         d->m2, p->nf, p->npairs, ppc, nchunks, off, n, cnt, pl)
+    if (full_s) { if (p->hp.has_trig) QO_LAUNCH(true, true, false); else QO_LAUNCH(true, false, false); }
+    else if (p->hp.need_gd) { if (p->hp.has_trig) QO_LAUNCH(false, true, true); else QO_LAUNCH(false, false, true); }
+    else { if (p->hp.has_trig) QO_LAUNCH(false, true, false); else QO_LAUNCH(false, false, false); }
 #undef QO_LAUNCH
     CU(cudaGetLastError());
     return QO_OK;

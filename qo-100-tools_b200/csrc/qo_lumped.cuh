@@ -258,7 +258,7 @@ __device__ __forceinline__ void qo_st256(double2 *p, double2 a, double2 b)
 }
 
 /* ---- the kernel ----------------------------------------------------------- */
-template <typename T, bool FULL_S, bool TRIG>
+template <typename T, bool FULL_S, bool TRIG, bool GD>
 __global__ void __launch_bounds__(QO_TPB, 2)
 qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::type *__restrict__ w2,
                     const typename QoVec2<T>::type *__restrict__ wi2, const uchar2 *__restrict__ m2, int nf, int npairs,
@@ -271,6 +271,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
     __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
     __shared__ T s_thr[QO_NSPEC_MAX];
     __shared__ int s_sk[QO_NSPEC_MAX];
+    __shared__ double s_gdthr[QO_NSPEC_MAX];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_ops = prog->n_ops, n_var = prog->n_var, nspec = prog->nspec;
@@ -280,7 +281,11 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
     const bool planes_al32 = ((((size_t)planes.s11) | ((size_t)planes.s21) | ((size_t)planes.s12) | ((size_t)planes.s22)) & 31) == 0;
     for (int i = threadIdx.x; i < n_ops; i += QO_TPB) { s_op[i] = prog->opcode[i]; s_coff[i] = prog->coff[i]; }
     for (int i = threadIdx.x; i < ncnt; i += QO_TPB) s_cnt[i] = 0;
-    if (threadIdx.x < QO_NSPEC_MAX) { s_thr[threadIdx.x] = T(prog->spec_thr[threadIdx.x]); s_sk[threadIdx.x] = prog->spec_kind[threadIdx.x]; }
+    if (threadIdx.x < QO_NSPEC_MAX) {
+        s_thr[threadIdx.x] = T(prog->spec_thr[threadIdx.x]); s_sk[threadIdx.x] = prog->spec_kind[threadIdx.x];
+        s_gdthr[threadIdx.x] = prog->spec_thr[threadIdx.x];
+    }
+    const unsigned int gd_bits = GD ? (unsigned int)prog->need_gd : 0u;     /* bit sp set: spec sp is a group-delay spec */
     __syncthreads();
 
     const T rs = T(prog->rs), rl = T(prog->rl), rsrl = T(prog->rsrl), k21 = T(prog->k21);
@@ -305,6 +310,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
         /* 3. frequency loop: two points per lane per iteration */
         unsigned int fail = 0;
         T wn = T(0), wd = T(1);
+        double gd_worst = -1e300;        /* largest group delay seen in the histogram spec's band (GD specs) */
         const int lo = chunk * pairs_per_chunk;
         const int hi = min(npairs, lo + pairs_per_chunk);
         int j = lo + lane;
@@ -344,16 +350,38 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                     o22[p] = make_double2((double)(xr * ir - xi * ii), (double)(xr * ii + xi * ir));
                 } else {
                     const unsigned int mb = mk[p];
+                    double gdv = 0.0;
+                    if (GD && (gd_bits & mb)) {
+                        /* group delay tau = -d(arg S21)/dw by the central difference the sweep API and the oracle use:
+                         * the chain is re-evaluated at w (1 +- 1e-6); arg S21 = -arg den.  Only points inside a
+                         * GD spec band pay for it. */
+                        const T dwq = w[p] * T(1e-6);
+                        const T wq[2] = { w[p] + dwq, w[p] - dwq };
+                        const T wiq[2] = { T(1) / wq[0], T(1) / wq[1] };
+                        Abcd2<T> mg;
+                        qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, wq, wiq, mg, planes, 2 * j);
+                        T dgr[2], dgi[2];
+#pragma unroll
+                        for (int q = 0; q < 2; q++) {
+                            dgr[q] = qfma(mg.dr[q], rs, qfma(mg.cr[q], rsrl, qfma(mg.ar[q], rl, mg.br[q])));
+                            dgi[q] = qfma(mg.di[q], rs, qfma(mg.ci[q], rsrl, qfma(mg.ai[q], rl, mg.bi[q])));
+                        }
+                        const double cre = (double)dgr[0] * (double)dgr[1] + (double)dgi[0] * (double)dgi[1];
+                        const double cim = (double)dgi[0] * (double)dgr[1] - (double)dgr[0] * (double)dgi[1];
+                        gdv = atan2(cim, cre) / (2.0 * (double)dwq);
+                    }
 #pragma unroll
                     for (int sp = 0; sp < QO_NSPEC_MAX; sp++) {
                         if (sp < nspec) {
                             const int sk = s_sk[sp];
                             const T thr = s_thr[sp];
-                            bool bad = sk == SK_DEN2_MAX ? (den2 > thr) : sk == SK_DEN2_MIN ? (den2 < thr) : (num2 > thr * den2);
+                            bool bad = sk == SK_DEN2_MAX ? (den2 > thr) : sk == SK_DEN2_MIN ? (den2 < thr)
+                                     : sk == SK_S11_MAX ? (num2 > thr * den2) : (gdv > s_gdthr[sp]);
                             if (bad && ((mb >> sp) & 1u)) fail |= 1u << sp;
                         }
                     }
-                    if (hist_spec >= 0 && ((mb >> hist_spec) & 1u)) {
+                    if (GD && hist_kind == SK_GD_MAX && hist_spec >= 0 && ((mb >> hist_spec) & 1u) && gdv > gd_worst) gd_worst = gdv;
+                    if (hist_spec >= 0 && hist_kind != SK_GD_MAX && ((mb >> hist_spec) & 1u)) {
                         /* track the worst value as a ratio a/b ("larger is worse") without dividing */
                         T a = hist_kind == SK_DEN2_MAX ? den2 : hist_kind == SK_DEN2_MIN ? T(1) : num2;
                         T b = hist_kind == SK_DEN2_MAX ? T(1) : den2;
@@ -403,6 +431,10 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                 for (int off = 16; off > 0; off >>= 1) {
                     T on = __shfl_xor_sync(0xffffffffu, wn, off), od = __shfl_xor_sync(0xffffffffu, wd, off);
                     if (on * wd > wn * od) { wn = on; wd = od; }
+                    if (GD) {
+                        const double og = __shfl_xor_sync(0xffffffffu, gd_worst, off);
+                        if (og > gd_worst) gd_worst = og;
+                    }
                 }
             }
             if (lane == 0) {
@@ -415,7 +447,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
                     double lin = hist_kind == SK_S11_MAX ? ratio
                                : hist_kind == SK_DEN2_MAX ? (double)k21 * (double)k21 / ratio
                                                           : (double)k21 * (double)k21 * ratio;
-                    double v = 10.0 * log10(lin);
+                    double v = hist_kind == SK_GD_MAX ? gd_worst : 10.0 * log10(lin);
                     double xb = (v - prog->hist_lo) / (prog->hist_hi - prog->hist_lo) * (double)prog->hist_bins;
                     long long b = (long long)floor(xb);
                     if (!(xb >= 0.0)) b = 0;

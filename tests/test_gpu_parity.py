@@ -142,9 +142,12 @@ def test_sweep_errors(Q, ctx):
     with pytest.raises(Q.QoError):
         ctx.sweep(net, np.array([1e9]), precision=16)
     w_specs = [(Q.SPEC_GD_MAX, 0, 1e9, 1e-9)]
-    with pytest.raises(Q.QoError) as ei:
-        ctx.mc_run(net, np.array([1e8, 2e8]), w_specs, 1, 10, [])
+    with pytest.raises(Q.QoError) as ei:                      # group-delay specs: FP64 lumped networks only
+        ctx.mc_run(net, np.array([1e8, 2e8]), w_specs, 1, 10, [], precision=32)
     assert ei.value.status == Q.ERR_UNSUPPORTED
+    with pytest.raises(Q.QoError) as ei:
+        ctx.mc_run(net, np.array([1e8, 2e8]), [(7, 0, 1e9, 1.0)], 1, 10, [])       # unknown spec kind
+    assert ei.value.status == Q.ERR_ARG
     with pytest.raises(Q.QoError):
         ctx.mc_run(net, np.array([1e8, 2e8]), [(1, 0, 1e9, -1.0)] * 9, 1, 10, [])     # > 8 specs
     with pytest.raises(Q.QoError):
@@ -498,3 +501,28 @@ def test_touchstone_blocks_in_cascade(Q, R, W, ctx, golden_s2p):
     bare = ctx.sweep(blk["pa_20W"][0].as_net(True), fd[10:20])
     assert np.allclose(np.stack([bare[0], bare[1], bare[2], bare[3]], 1), sd[10:20], rtol=1e-9, atol=1e-12)
     R.sblock_clear()
+
+
+def test_group_delay_spec_in_kernel(Q, R, W, ctx):
+    """north_star (c): group-delay reduction in-kernel.  QO_SPEC_GD_MAX on the Monte-Carlo path: counters and the
+    histogram of the worst pass-band group delay equal the oracle's (same central-difference definition as
+    qo_sweep's gd output), alone and mixed with |S21| / |S11| specs."""
+    w = W.cfg2()
+    fc = 10e6
+    f = w.f[::4]
+    gd = ctx.sweep(w.net, f, gd=True)[4]
+    band = (f >= 0.3 * fc) & (f <= 0.9 * fc)
+    lim = float(gd[band].max()) * 1.01
+    for specs, hs in (([(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 0),
+                      ([(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -2.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim),
+                        (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, -9.0)], 1)):
+        hist = dict(hist_bins=40, hist_spec=hs, hist_lo=0.8 * lim, hist_hi=1.3 * lim)
+        plan = Q.Plan(ctx, w.net, f, specs, seed=3, tols=w.tols, **hist)
+        assert plan.kernel_name == "qo_mc_lumped_kernel"
+        plan.close()
+        got = ctx.mc_run(w.net, f, specs, 3, 500, w.tols, **hist)
+        ref = R.mc_run(to_ref(R, w.net), 50, 50, f, specs, R.mc_cfg(3, 500, w.tols, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)
+        assert 0 < got["fail_per_spec"][hs] < 500 and int(got["hist"].sum()) == 500 and np.count_nonzero(got["hist"]) > 3
+    with pytest.raises(Q.QoError):
+        ctx.mc_run(w.net, f, [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 3, 10, w.tols, precision=32)

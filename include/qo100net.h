@@ -123,7 +123,8 @@ int qo_s2p_num_points(const qo_s2p *blk);
 double qo_s2p_z0(const qo_s2p *blk);
 int qo_s2p_get(const qo_s2p *blk, double *f, qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22, int cap); /* returns n */
 /* S at arbitrary frequencies: linear in f between the bracketing points, on (|S|, phase along the shorter arc)
- * when polar != 0 else on (re, im); end values held outside the measured range.  Host routine (the kernels
+ * when polar != 0 else on (re, im); the end segments are extrapolated linearly outside the measured range
+ * (Qucs' behaviour: util/pa-bias-simulation/pa-bias-simulation.dat is reproduced only this way).  Host routine (the kernels
  * use the same routine at plan creation to build the per-frequency ABCD table of the block). */
 int qo_s2p_interp(const qo_s2p *blk, const double *f, int nf, int polar, qo_c64 *s11, qo_c64 *s21, qo_c64 *s12, qo_c64 *s22);
 /* least-squares fit of the ESR/SRF inductor model Z = (r0 + r1 sqrt(f) + jwL) || 1/(jwCp) to a block measured

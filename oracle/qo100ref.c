@@ -502,14 +502,13 @@ int ref_sblock_register(int idx, const double *f, const double *s, int n, double
 }
 
 /* linear interpolation in frequency of one S entry, polar (|S| and phase along the shorter arc) or rectangular;
- * the end values are held outside the measured range */
+ * outside the measured range the end segment is extrapolated (what reproduces pa-bias-simulation.dat) */
 static cx blk_entry(int idx, int j, double f, int polar)
 {
     const int n = g_blk[idx].n;
     const double *F = g_blk[idx].f, *S = g_blk[idx].s;
+    if (n == 1) return cx_mk(S[2 * j], S[2 * j + 1]);
     int k = 0;
-    if (f <= F[0] || n == 1) return cx_mk(S[2 * j], S[2 * j + 1]);
-    if (f >= F[n - 1]) return cx_mk(S[8 * (size_t)(n - 1) + 2 * j], S[8 * (size_t)(n - 1) + 2 * j + 1]);
     while (k + 2 < n && F[k + 1] <= f) k++;
     const cx a = cx_mk(S[8 * (size_t)k + 2 * j], S[8 * (size_t)k + 2 * j + 1]);
     const cx b = cx_mk(S[8 * (size_t)(k + 1) + 2 * j], S[8 * (size_t)(k + 1) + 2 * j + 1]);
@@ -521,6 +520,13 @@ static cx blk_entry(int idx, int j, double f, int polar)
     const double ma = sqrt(cx_abs2(a)), mb = sqrt(cx_abs2(b));
     const double m = ma + t * (mb - ma), ph = pa + t * dp;
     return cx_mk(m * cos(ph), m * sin(ph));
+}
+
+int ref_sblock_s(int idx, double f, int polar, double s[8])
+{
+    if (idx < 0 || idx >= REF_MAX_BLK || g_blk[idx].n == 0) return -1;
+    for (int j = 0; j < 4; j++) { cx v = blk_entry(idx, j, f, polar); s[2 * j] = v.re; s[2 * j + 1] = v.im; }
+    return 0;
 }
 
 /* S (reference z0) -> chain matrix; *det = S12 / S21 */

@@ -92,6 +92,19 @@ void ref_add_parasitics(ref_elem *e, int n, double fc, double q_l, double srf_l_
 int ref_sblock_register(int idx, const double *f, const double *s, int n, double z0);
 void ref_sblock_clear(void);
 
+/* ---- N-port nodal analysis (qo100ref_nodal.c; pinned by util/pa-bias-simulation/pa-bias-simulation.dat) ---- */
+enum { REF_NB_R = 1, REF_NB_L = 2, REF_NB_C = 3, REF_NB_VCVS = 4, REF_NB_SBLOCK = 5 };
+/* R: nodes a,b p0=R | L: a,b p0=L p1=ESR p2=Cp | C: a,b p0=C p1=ESR p2=ESL | VCVS: in+,out+,out-,in- p0=gain p1=delay
+ * SBLOCK: t1,t2,ref p0=registered block index p1=polar p2=z0.  Node 0 = ground. */
+typedef struct { int32_t kind; int32_t node[4]; double p[4]; } ref_branch;
+typedef struct { int32_t kind; int32_t row, col, pad; double f_lo, f_hi, limit; } ref_nspec;  /* kind: REF_SPEC_S21_MIN_DB / _MAX_DB on |S[row][col]| */
+int ref_nodal_sweep(const ref_branch *br, int nb, int n_nodes, const int *port_node, const double *port_z0, int np,
+                    const double *f, int nf, double *s_out /* [nf][np][np] (re,im), S[k][j] = b_k/a_j */);
+int ref_nodal_mc_run(const ref_branch *br, int nb, int n_nodes, const int *port_node, const double *port_z0, int np,
+                     const double *f, int nf, const ref_nspec *spec, int nspec, const ref_mc_cfg *cfg,
+                     uint64_t *counters, double *full_s, int nthreads);
+int ref_sblock_s(int idx, double f, int polar, double s[8]);
+
 /* nominal sweep; s?? are interleaved (re,im) arrays of 2*nf doubles, nullable; gd nullable */
 int ref_sweep(const ref_elem *e, int n, double rs, double rl, const double *f, int nf,
               double *s11, double *s21, double *s12, double *s22, double *gd);

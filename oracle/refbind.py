@@ -36,6 +36,15 @@ class Tol(C.Structure):
                 ("tol", C.c_double)]
 
 
+class Branch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("node", C.c_int32 * 4), ("p", C.c_double * 4)]
+
+
+class NSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("row", C.c_int32), ("col", C.c_int32), ("pad", C.c_int32),
+                ("f_lo", C.c_double), ("f_hi", C.c_double), ("limit", C.c_double)]
+
+
 class McCfg(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("sample_offset", C.c_uint64), ("n_samples", C.c_uint64),
                 ("dist", C.c_int32), ("n_tol", C.c_int32), ("tol", C.POINTER(Tol)),
@@ -89,6 +98,10 @@ def lib():
         L.ref_cpl_analyze.argtypes = [C.c_double] * 8 + [dp] * 4
         L.ref_sblock_register.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double]
         L.ref_sblock_clear.argtypes = []
+        ip = C.POINTER(C.c_int)
+        L.ref_nodal_sweep.argtypes = [C.POINTER(Branch), C.c_int, C.c_int, ip, dp, C.c_int, dp, C.c_int, dp]
+        L.ref_nodal_mc_run.argtypes = [C.POINTER(Branch), C.c_int, C.c_int, ip, dp, C.c_int, dp, C.c_int,
+                                       C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), u64p, dp, C.c_int]
         _lib = L
     return _lib
 
@@ -106,6 +119,60 @@ def make_elems(items):
         for k, v in enumerate(p):
             arr[i].p[k] = float(v)
     return arr
+
+
+NB_R, NB_L, NB_C, NB_VCVS, NB_SBLOCK = 1, 2, 3, 4, 5
+
+
+def make_branches(items):
+    """items: (kind, [nodes], [params]) -> ctypes array of Branch."""
+    items = list(items)
+    arr = (Branch * len(items))()
+    for i, (kind, nodes, p) in enumerate(items):
+        arr[i].kind = int(kind)
+        for k, v in enumerate(nodes):
+            arr[i].node[k] = int(v)
+        for k, v in enumerate(p):
+            arr[i].p[k] = float(v)
+    return arr
+
+
+def nodal_sweep(branches, n_nodes, ports, f):
+    """ports: [(node, z0)] -> S[nf, np, np] with S[:, k, j] = b_k / a_j."""
+    br = branches if isinstance(branches, C.Array) else make_branches(branches)
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    npn = len(ports)
+    pn = (C.c_int * npn)(*[int(p[0]) for p in ports])
+    pz = np.array([float(p[1]) for p in ports])
+    out = np.empty((len(f), npn, npn), dtype=np.complex128)
+    rc = lib().ref_nodal_sweep(br, len(br), int(n_nodes), pn, _dp(pz), npn, _dp(f), len(f), out.ctypes.data_as(C.POINTER(C.c_double)))
+    if rc:
+        raise RuntimeError("ref_nodal_sweep failed: %d" % rc)
+    return out
+
+
+def nodal_mc_run(branches, n_nodes, ports, f, specs, cfg, full_s=False, nthreads=1):
+    """specs: [(kind, row, col, f_lo, f_hi, limit_db)] on |S[row][col]|."""
+    br = branches if isinstance(branches, C.Array) else make_branches(branches)
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    npn = len(ports)
+    pn = (C.c_int * npn)(*[int(p[0]) for p in ports])
+    pz = np.array([float(p[1]) for p in ports])
+    sp = (NSpec * max(1, len(specs)))()
+    for i, s in enumerate(specs):
+        sp[i].kind, sp[i].row, sp[i].col, sp[i].f_lo, sp[i].f_hi, sp[i].limit = int(s[0]), int(s[1]), int(s[2]), float(s[3]), float(s[4]), float(s[5])
+    hb = max(0, cfg.hist_bins)
+    cnt = np.zeros(2 + len(specs) + hb, dtype=np.uint64)
+    full = np.empty((cfg.n_samples, len(f), npn, npn), dtype=np.complex128) if full_s else None
+    rc = lib().ref_nodal_mc_run(br, len(br), int(n_nodes), pn, _dp(pz), npn, _dp(f), len(f), sp, len(specs), C.byref(cfg),
+                                cnt.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                full.ctypes.data_as(C.POINTER(C.c_double)) if full is not None else None, nthreads)
+    if rc:
+        raise RuntimeError("ref_nodal_mc_run failed: %d" % rc)
+    out = dict(n_pass=int(cnt[0]), n_total=int(cnt[1]), fail_per_spec=cnt[2:2 + len(specs)].copy(), hist=cnt[2 + len(specs):].copy())
+    if full is not None:
+        out["s"] = full
+    return out
 
 
 def sblock_register(idx, f, s11, s21, s12, s22, z0=50.0):

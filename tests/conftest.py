@@ -50,10 +50,10 @@ def golden_s2p():
 
 def np_spfile(f, fd, sd, polar=True):
     """Independent numpy restatement of Qucs SPfile 'linear' interpolation (third implementation next to the
-    product's and the oracle's): sd is [n,4] complex (S11 S21 S12 S22) at fd; end values held."""
+    product's and the oracle's): sd is [n,4] complex (S11 S21 S12 S22) at fd; end segments extrapolated."""
     f = np.asarray(f, dtype=float)
     k = np.clip(np.searchsorted(fd, f, side="right") - 1, 0, len(fd) - 2)
-    t = np.clip((f - fd[k]) / (fd[k + 1] - fd[k]), 0.0, 1.0)[:, None]
+    t = ((f - fd[k]) / (fd[k + 1] - fd[k]))[:, None]
     a, b = sd[k], sd[k + 1]
     if not polar:
         return a + t * (b - a)

@@ -334,12 +334,13 @@ def test_touchstone_loader_interp_and_inductor_fit(Q, golden_s2p, tmp_path):
     # pa_20W_vdd_32V_idq_180mA.s2p:8 (# HZ S RI R 50 at :5): 1e7 Hz, S11 = 1.00031 - j0.0752988, S21 = 0.00209503 - j1.33393e-05
     _, fd3, sd3 = blocks["pa_20W"]
     assert len(fd3) == 501 and fd3[0] == 1e7 and sd3[0, 0] == complex(1.00031, -0.0752988) and sd3[0, 1] == complex(0.00209503, -1.33393e-05)
-    # interpolation: at the data points exact, between them == numpy restatement, outside held
+    # interpolation: at the data points exact, between them == numpy restatement, outside: end segment extrapolated
     for polar in (True, False):
         fq = np.concatenate([fd[:5], np.sqrt(fd[:-1] * fd[1:])[::7], [1e3, 5e9]])
         got = np.stack(b.interp(fq, polar=polar), 1)
         assert np.allclose(got, np_spfile(fq, fd, sd, polar), rtol=1e-12, atol=1e-15)
-        assert np.allclose(got[:5], sd[:5], rtol=1e-14) and np.allclose(got[-2], sd[0]) and np.allclose(got[-1], sd[-1])
+        assert np.allclose(got[:5], sd[:5], rtol=1e-14)
+        assert not np.allclose(got[-1], sd[-1], rtol=1e-3) and not np.allclose(got[-2], sd[0], rtol=1e-3)
     # inductor fits (1111SQ-39N 38.4-39.0 nH, SRF > 3.3 GHz; 0603HP-47N ~47 nH,
     # R 0.30 Ohm @ 1 MHz -> 2.9 Ohm @ 680 MHz, SRF 3.29-3.44 GHz)
     r = blocks["11SQ39N"][0].fit_inductor(10e6, 500e6)

@@ -10,6 +10,7 @@ Writes
   tests/golden/touchstone.npz   -- the three Touchstone files of the tree (util/pa-bias-simulation/11SQ39N.S2P,
                                    util/preamp-bias-simulation/06HP47N.s2p, docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p)
                                    parsed by an independent numpy parser (python tools/make_golden.py /root/reference touchstone)
+  tests/golden/pa_bias_dat.npz  -- util/pa-bias-simulation/pa-bias-simulation.dat:1-85035 (5-port S entries, 5000 points)
   tests/golden/appendix_b.json  -- 40-digit mpmath evaluation of the textbook ladder / coupled-line
                                    equations (SURVEY App. B) at the frequencies the survey tabulates;
                                    an implementation independent of both the oracle and the product.
@@ -229,6 +230,14 @@ def parse_s2p(path):
     return a[:, 0] * scale, s, z0          # columns of s: S11 S21 S12 S22
 
 
+def golden_pa_bias():
+    """util/pa-bias-simulation/pa-bias-simulation.dat:1-85035 -- the 5-port bias network (row N4)."""
+    d = parse_dat(os.path.join(REF, "util/pa-bias-simulation/pa-bias-simulation.dat"))
+    keys = {k: v for k, v in d.items()}
+    np.savez_compressed(os.path.join(OUT, "pa_bias_dat.npz"), **{k.replace("[", "").replace("]", "").replace(",", "_"): v for k, v in keys.items()})
+    print("pa_bias_dat.npz:", len(d["frequency"]), "points,", len(keys), "variables")
+
+
 def golden_touchstone():
     out = {}
     for key, p in S2PS.items():
@@ -243,7 +252,11 @@ if __name__ == "__main__":
     if len(sys.argv) > 2 and sys.argv[2] == "touchstone":
         golden_touchstone()
         sys.exit(0)
+    if len(sys.argv) > 2 and sys.argv[2] == "pa_bias":
+        golden_pa_bias()
+        sys.exit(0)
     golden_dat()
     golden_networks()
     golden_appendix_b()
     golden_touchstone()
+    golden_pa_bias()

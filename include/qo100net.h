@@ -135,6 +135,30 @@ void qo_s2p_free(qo_s2p *blk);
 /* a one-element network holding a copy of the block; combine with qo_net_concat */
 int qo_net_from_sblock(const qo_s2p *blk, int polar, double rs, double rl, qo_net **out);
 
+/* ---- N-port nodal analysis ------------------------------------------------ */
+/* General linear networks that are not a 2-port cascade: the reference's bias networks
+ * util/pa-bias-simulation/pa-bias-simulation.sch:19-72 (5 ports; R, C, ideal VCVS buffers :40,59, the measured
+ * inductor via SPfile :39), whose Qucs result is util/pa-bias-simulation/pa-bias-simulation.dat:1-85035.
+ * Modified nodal analysis per (sample, frequency) point on the GPU: one LU factorisation, one substitution
+ * per port.  Node 0 is ground; ports are numbered 1.. in the order they are added. */
+typedef struct qo_nodal qo_nodal;
+typedef enum { QO_NB_R = 1, QO_NB_L = 2, QO_NB_C = 3, QO_NB_VCVS = 4, QO_NB_SBLOCK = 5 } qo_nb_kind;
+/* R: node a,b p0=R | L: a,b p0=L p1=ESR p2=Cp | C: a,b p0=C p1=ESR p2=ESL  (same parasitic forms as QO_SER_L/C)
+ * VCVS: node in+, out+, out-, in-; p0=gain p1=delay[s] | SBLOCK: node t1, t2, ref; p0=block index p1=polar p2=z0 */
+typedef struct { int32_t kind; int32_t node[4]; double p[4]; } qo_branch;
+int qo_nodal_create(int n_nodes, qo_nodal **out);
+int qo_nodal_add_branch(qo_nodal *nd, const qo_branch *b);
+int qo_nodal_add_port(qo_nodal *nd, int node, double z0);                 /* returns the port's number (1..) */
+int qo_nodal_add_sblock(qo_nodal *nd, const qo_s2p *blk, int *index);     /* copies the block */
+int qo_nodal_load_qucs_sch(const char *path, qo_nodal **out);             /* Qucs netlister for R, L, C, GND, Pac, VCVS, SPfile */
+int qo_nodal_num_nodes(const qo_nodal *nd);
+int qo_nodal_num_ports(const qo_nodal *nd);
+int qo_nodal_num_branches(const qo_nodal *nd);
+int qo_nodal_get_branches(const qo_nodal *nd, qo_branch *out, int cap);   /* returns count */
+int qo_nodal_get_ports(const qo_nodal *nd, int *node, double *z0, int cap);
+void qo_nodal_free(qo_nodal *nd);
+/* compute entry points: qo_nodal_sweep / qo_nodal_mc_run below */
+
 /* ---- Qucs dataset (.dat) reader / writer --------------------------------- */
 /* The layout Qucs 0.0.19 writes for util/pa-lpf-simulation/pa-lpf-simulation.dat:1-35018:
  * "<indep NAME N>" / "<dep NAME INDEP>" blocks of "%+.20e" reals or "%+.20e+j%.20e" complex values.
@@ -205,6 +229,16 @@ typedef struct {
  * planes [4][n_samples][nf] in the order S11, S21, S12, S22. */
 int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec,
               const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
+
+/* N-port nodal analysis on the GPU (netlist container above) */
+/* spec on one S entry: kind QO_SPEC_S21_MIN_DB / QO_SPEC_S21_MAX_DB applied to |S[row][col]| (0-based) in dB */
+typedef struct { int32_t kind; int32_t row, col, pad; double f_lo, f_hi, limit; } qo_nspec;
+/* nominal sweep: s[nf][np][np], S[k][j] = b_k / a_j (Qucs "S[k+1,j+1]") */
+int qo_nodal_sweep(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, qo_c64 *s);
+/* Monte Carlo over branch parameters (qo_tol.elem = branch index, .param = p index); counters as qo_mc_run;
+ * full_s (nullable unless cfg->mode == QO_MODE_FULL_S): [n_samples][nf][np][np] */
+int qo_nodal_mc_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
+                    const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
 
 /* The same job kept resident in HBM (tables, grid, specs uploaded once):
  *   counters layout (uint64): [0]=n_pass [1]=n_total [2..2+nspec)=fail_per_spec, then hist[hist_bins].

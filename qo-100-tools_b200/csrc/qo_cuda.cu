@@ -14,31 +14,12 @@
 #include <vector>
 
 #include "qo_internal.h"
+#include "qo_ctx_internal.h"
 #include "qo_lumped.cuh"
 #include "qo_ladder.cuh"
 #include "qo_ladder_launch.h"
 #include "qo_ustrip.cuh"
 
-#define CU(call)                                                                                      \
-    do {                                                                                              \
-        cudaError_t e_ = (call);                                                                      \
-        if (e_ != cudaSuccess) {                                                                      \
-            qo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));       \
-            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? QO_ERR_NO_DEVICE : QO_ERR_CUDA; \
-        }                                                                                             \
-    } while (0)
-
-/* ---- NCCL, loaded at run time (only the single-process multi-GPU ctx uses it) */
-typedef struct ncclComm *ncclComm_t;
-struct NcclApi {
-    void *h;
-    int (*CommInitAll)(ncclComm_t *, int, const int *);
-    int (*CommDestroy)(ncclComm_t);
-    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
-    int (*GroupStart)(void);
-    int (*GroupEnd)(void);
-    const char *(*GetErrorString)(int);
-};
 static int nccl_load(NcclApi *a)
 {
     memset(a, 0, sizeof *a);
@@ -54,22 +35,6 @@ static int nccl_load(NcclApi *a)
     return a->CommInitAll && a->CommDestroy && a->AllReduce && a->GroupStart && a->GroupEnd;
 }
 enum { QO_NCCL_UINT64 = 5, QO_NCCL_SUM = 0 };   /* ncclUint64, ncclSum (nccl.h enum values) */
-
-struct DevCtx {
-    int device;
-    cudaStream_t stream;
-    int own_stream;
-    int sm_count;
-    cudaEvent_t ev0, ev1;
-};
-
-struct qo_ctx {
-    int ndev;
-    DevCtx d[8];
-    NcclApi nccl;
-    ncclComm_t comm[8];
-    int have_nccl;
-};
 
 struct DevPlan {
     DevProg *prog;

@@ -28,6 +28,17 @@ struct qo_net {
     struct qo_s2p *blk[QO_MAX_BLK];
 };
 
+#define QO_NODAL_MAX_UNK 32       /* node voltages + VCVS currents */
+#define QO_NODAL_MAX_BR 96
+#define QO_NODAL_MAX_PORTS 8
+struct qo_nodal {
+    int n_nodes, nb, np, nblk;
+    qo_branch br[QO_NODAL_MAX_BR];
+    int port_node[QO_NODAL_MAX_PORTS];
+    double port_z0[QO_NODAL_MAX_PORTS];
+    struct qo_s2p *blk[QO_MAX_BLK];
+};
+
 /* thread-local error detail */
 void qo_set_error(const char *fmt, ...);
 void qo_clear_error(void);

@@ -21,12 +21,12 @@
 #define MAXC 128
 #define MAXP 8
 #define MAXW 256
-#define MAXPIN 3
+#define MAXPIN 4
 
 typedef struct {
     char type[16], name[32];
     int x, y, mirror, rot, nprop;
-    char prop[MAXP][64];
+    char prop[MAXP][128];
     int npin, px[MAXPIN], py[MAXPIN], node[MAXPIN];
     int used;
 } comp_t;
@@ -56,6 +56,8 @@ static void set_pins(comp_t *c)
     static const int tee[3][2] = { { -30, 0 }, { 30, 0 }, { 0, 30 } };
     static const int one[1][2] = { { -30, 0 } };
     static const int gnd[1][2] = { { 0, 0 } };
+    static const int spf[3][2] = { { -30, 0 }, { 30, 0 }, { 0, 30 } };                       /* port 1, port 2, reference */
+    static const int vcvs[4][2] = { { -30, -30 }, { 30, -30 }, { 30, 30 }, { -30, 30 } };    /* in+, out+, out-, in- */
     const int (*tab)[2] = NULL;
     c->npin = 0;
     if (!strcmp(c->type, "MLIN") || !strcmp(c->type, "Pac") || !strcmp(c->type, "R") || !strcmp(c->type, "L") ||
@@ -64,6 +66,8 @@ static void set_pins(comp_t *c)
     else if (!strcmp(c->type, "MTEE")) { tab = tee; c->npin = 3; }
     else if (!strcmp(c->type, "MOPEN")) { tab = one; c->npin = 1; }
     else if (!strcmp(c->type, "GND")) { tab = gnd; c->npin = 1; }
+    else if (!strcmp(c->type, "SPfile")) { tab = spf; c->npin = 3; }
+    else if (!strcmp(c->type, "VCVS")) { tab = vcvs; c->npin = 4; }
     for (int i = 0; i < c->npin; i++) {
         int dx = tab[i][0], dy = tab[i][1];
         rot_off(c->rot, c->mirror, &dx, &dy);
@@ -84,7 +88,7 @@ static int parse_component(const char *line, comp_t *c)
         const char *q = strchr(p + 1, '"');
         if (!q) break;
         size_t n = (size_t)(q - p - 1);
-        if (n > 63) n = 63;
+        if (n > 127) n = 127;
         memcpy(c->prop[c->nprop], p + 1, n);
         c->prop[c->nprop][n] = 0;
         c->nprop++;
@@ -167,6 +171,28 @@ static int on_segment(const int w[4], int x, int y)
     return (x == w[0] && y == w[1]) || (x == w[2] && y == w[3]);
 }
 
+/* every pin gets the representative index of its electrical node (pins and wire ends that coincide or lie on
+ * a common wire are one node) */
+static void extract_nodes(sch_t *s)
+{
+    static __thread pt_t pts[MAXC * MAXPIN + 2 * MAXW];
+    int np = 0;
+    for (int i = 0; i < s->nc; i++)
+        for (int k = 0; k < s->c[i].npin; k++) s->c[i].node[k] = pt_get(pts, &np, s->c[i].px[k], s->c[i].py[k]);
+    for (int i = 0; i < s->nw; i++) {
+        int a = pt_get(pts, &np, s->w[i][0], s->w[i][1]);
+        int b = pt_get(pts, &np, s->w[i][2], s->w[i][3]);
+        uf_union(pts, a, b);
+    }
+    for (int i = 0; i < s->nw; i++) {
+        int a = pt_get(pts, &np, s->w[i][0], s->w[i][1]);
+        for (int j = 0; j < np; j++)
+            if (on_segment(s->w[i], pts[j].x, pts[j].y)) uf_union(pts, a, j);
+    }
+    for (int i = 0; i < s->nc; i++)
+        for (int k = 0; k < s->c[i].npin; k++) s->c[i].node[k] = uf_find(pts, s->c[i].node[k]);
+}
+
 static comp_t *find_at(sch_t *s, int node, int *pin)
 {
     for (int i = 0; i < s->nc; i++) {
@@ -237,23 +263,7 @@ int qo_net_load_qucs_sch(const char *path, qo_net **out)
     int rc = parse_sch(path, s);
     if (rc) goto done;
 
-    /* nodes */
-    static __thread pt_t pts[MAXC * MAXPIN + 2 * MAXW];
-    int np = 0;
-    for (int i = 0; i < s->nc; i++)
-        for (int k = 0; k < s->c[i].npin; k++) s->c[i].node[k] = pt_get(pts, &np, s->c[i].px[k], s->c[i].py[k]);
-    for (int i = 0; i < s->nw; i++) {
-        int a = pt_get(pts, &np, s->w[i][0], s->w[i][1]);
-        int b = pt_get(pts, &np, s->w[i][2], s->w[i][3]);
-        uf_union(pts, a, b);
-    }
-    for (int i = 0; i < s->nw; i++) {
-        int a = pt_get(pts, &np, s->w[i][0], s->w[i][1]);
-        for (int j = 0; j < np; j++)
-            if (on_segment(s->w[i], pts[j].x, pts[j].y)) uf_union(pts, a, j);
-    }
-    for (int i = 0; i < s->nc; i++)
-        for (int k = 0; k < s->c[i].npin; k++) s->c[i].node[k] = uf_find(pts, s->c[i].node[k]);
+    extract_nodes(s);
 
     /* ground net(s) and the two ports */
     int gnd[16], ngnd = 0;
@@ -362,5 +372,90 @@ int qo_cpl_load_trc(const char *path, double *z0e, double *z0o, double *ang_deg,
     if (phys) for (int k = 0; k < 8; k++) phys[k] = v[k];
 done:
     free(buf);
+    return rc;
+}
+
+
+/* ---- general netlist for the N-port nodal solver ---------------------------------------
+ * util/pa-bias-simulation/pa-bias-simulation.sch:19-72 and util/preamp-bias-simulation/preamp-bias-simulation.sch:
+ * R, C, L, GND, Pac (numbered ports, one pin grounded), VCVS (:40,59) and SPfile (:39, the Touchstone file is
+ * looked up by its base name next to the schematic -- the stored path is the author's home directory). */
+int qo_nodal_load_qucs_sch(const char *path, qo_nodal **out)
+{
+    qo_clear_error();
+    if (!path || !out) return QO_ERR_ARG;
+    sch_t *s = (sch_t *)malloc(sizeof(sch_t));
+    if (!s) return QO_ERR_NOMEM;
+    qo_nodal *nd = NULL;
+    int rc = parse_sch(path, s);
+    if (rc) goto done;
+    extract_nodes(s);
+    /* number the nodes: every GND pin's node is 0, the others 1.. in order of first appearance */
+    int rep[MAXC * MAXPIN], num[MAXC * MAXPIN], nrep = 0, nnode = 0;
+    for (int i = 0; i < s->nc; i++)
+        if (!strcmp(s->c[i].type, "GND")) { rep[nrep] = s->c[i].node[0]; num[nrep++] = 0; }
+    for (int i = 0; i < s->nc; i++)
+        for (int k = 0; k < s->c[i].npin; k++) {
+            int found = -1;
+            for (int j = 0; j < nrep; j++) if (rep[j] == s->c[i].node[k]) found = j;
+            if (found < 0) { rep[nrep] = s->c[i].node[k]; num[nrep] = ++nnode; found = nrep++; }
+            s->c[i].node[k] = num[found];
+        }
+    if ((rc = qo_nodal_create(nnode, &nd))) goto done;
+    /* ports, in the order of their Pac numbers */
+    for (int want = 1; want <= 16; want++) {
+        int hit = 0;
+        for (int i = 0; i < s->nc; i++) {
+            comp_t *c = &s->c[i];
+            if (strcmp(c->type, "Pac") || atoi(c->prop[0]) != want) continue;
+            double z0;
+            if ((rc = prop_value(s, c->prop[1], &z0))) goto done;
+            if ((c->node[0] == 0) == (c->node[1] == 0)) { qo_set_error("%s: port %s needs exactly one grounded pin", path, c->name); rc = QO_ERR_UNSUPPORTED; goto done; }
+            if ((rc = qo_nodal_add_port(nd, c->node[0] ? c->node[0] : c->node[1], z0)) < 0) goto done;
+            rc = QO_OK;
+            hit = 1;
+        }
+        if (!hit) break;
+    }
+    for (int i = 0; i < s->nc; i++) {
+        comp_t *c = &s->c[i];
+        qo_branch b;
+        memset(&b, 0, sizeof b);
+        if (!strcmp(c->type, "R") || !strcmp(c->type, "C") || !strcmp(c->type, "L")) {
+            b.kind = c->type[0] == 'R' ? QO_NB_R : c->type[0] == 'C' ? QO_NB_C : QO_NB_L;
+            b.node[0] = c->node[0]; b.node[1] = c->node[1];
+            if ((rc = prop_value(s, c->prop[0], &b.p[0]))) goto done;
+        } else if (!strcmp(c->type, "VCVS")) {
+            b.kind = QO_NB_VCVS;
+            for (int k = 0; k < 4; k++) b.node[k] = c->node[k];
+            if ((rc = prop_value(s, c->prop[0], &b.p[0])) || (rc = prop_value(s, c->prop[1], &b.p[1]))) goto done;
+        } else if (!strcmp(c->type, "SPfile")) {
+            if (strcmp(c->prop[2], "linear")) { qo_set_error("%s: %s uses '%s' interpolation; only 'linear' is restated", path, c->name, c->prop[2]); rc = QO_ERR_UNSUPPORTED; goto done; }
+            if (atoi(c->prop[4]) != 2) { qo_set_error("%s: %s is not a 2-port file", path, c->name); rc = QO_ERR_UNSUPPORTED; goto done; }
+            char file[1024];
+            const char *base = strrchr(c->prop[0], '/'), *dirend = strrchr(path, '/');
+            base = base ? base + 1 : c->prop[0];
+            snprintf(file, sizeof file, "%.*s%s", dirend ? (int)(dirend - path + 1) : 0, path, base);
+            qo_s2p *blk = NULL;
+            if ((rc = qo_s2p_load(file, &blk))) goto done;
+            int idx = -1;
+            rc = qo_nodal_add_sblock(nd, blk, &idx);
+            const double z0 = qo_s2p_z0(blk);
+            qo_s2p_free(blk);
+            if (rc) goto done;
+            b.kind = QO_NB_SBLOCK;
+            for (int k = 0; k < 3; k++) b.node[k] = c->node[k];
+            b.p[0] = idx; b.p[1] = !strcmp(c->prop[1], "polar"); b.p[2] = z0;
+        } else if (!strcmp(c->type, "GND") || !strcmp(c->type, "Pac") || c->npin == 0) {
+            continue;                                   /* .SP, Eqn and other annotations carry no pins */
+        } else { qo_set_error("%s: component type %s (%s) is not supported by the nodal loader", path, c->type, c->name); rc = QO_ERR_UNSUPPORTED; goto done; }
+        if ((rc = qo_nodal_add_branch(nd, &b))) goto done;
+    }
+    if (qo_nodal_num_ports(nd) < 1) { qo_set_error("%s: no Pac ports", path); rc = QO_ERR_UNSUPPORTED; goto done; }
+    *out = nd;
+    nd = NULL;
+done:
+    qo_nodal_free(nd);
+    free(s);
     return rc;
 }

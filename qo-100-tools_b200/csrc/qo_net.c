@@ -92,6 +92,21 @@ int qo_parse_value(const char *s, double *out, const char **unit)
         default: break;
         }
     }
+    else if (*u && (!u[1] || isspace((unsigned char)u[1]))) {
+        /* a bare engineering suffix, as Qucs accepts it ("26.5p", pa-bias-simulation.sch:42); a lone "m" stays
+         * the unit metre (QucsTranscalc lengths) */
+        switch (*u) {
+        case 'f': scale = 1e-15; u++; break;
+        case 'p': scale = 1e-12; u++; break;
+        case 'n': scale = 1e-9; u++; break;
+        case 'u': scale = 1e-6; u++; break;
+        case 'k': scale = 1e3; u++; break;
+        case 'M': scale = 1e6; u++; break;
+        case 'G': scale = 1e9; u++; break;
+        case 'T': scale = 1e12; u++; break;
+        default: break;
+        }
+    }
     *out = v * scale;
     if (scale != 1.0 && scale != 25.4e-6) {
         /* decimal prefixes: re-read "33.00" + "e-9" so that the value is the correctly rounded

@@ -54,6 +54,18 @@ class McCfg(C.Structure):
                 ("hist_bins", C.c_int32), ("hist_spec", C.c_int32), ("hist_lo", C.c_double), ("hist_hi", C.c_double)]
 
 
+class Branch(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("node", C.c_int32 * 4), ("p", C.c_double * 4)]
+
+
+class NSpec(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("row", C.c_int32), ("col", C.c_int32), ("pad", C.c_int32),
+                ("f_lo", C.c_double), ("f_hi", C.c_double), ("limit", C.c_double)]
+
+
+NB_R, NB_L, NB_C, NB_VCVS, NB_SBLOCK = 1, 2, 3, 4, 5
+
+
 class McResult(C.Structure):
     _fields_ = [("n_pass", C.c_uint64), ("n_total", C.c_uint64), ("fail_per_spec", C.POINTER(C.c_uint64)),
                 ("hist", C.POINTER(C.c_uint64)), ("seconds", C.c_double), ("evals_per_s", C.c_double),
@@ -83,6 +95,9 @@ EXPORTS = [
     "qo_plan_kernel_name",
     "qo_s2p_load", "qo_s2p_from_arrays", "qo_s2p_num_points", "qo_s2p_z0", "qo_s2p_get", "qo_s2p_interp",
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
+    "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
+    "qo_nodal_num_nodes", "qo_nodal_num_ports", "qo_nodal_num_branches", "qo_nodal_get_branches", "qo_nodal_get_ports",
+    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run",
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
@@ -142,6 +157,19 @@ def lib():
         "qo_s2p_fit_inductor": (C.c_int, [vp, C.c_double, C.c_double, dp, dp, dp, dp, dp, dp]),
         "qo_s2p_free": (None, [vp]),
         "qo_net_from_sblock": (C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
+        "qo_nodal_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "qo_nodal_add_branch": (C.c_int, [vp, C.POINTER(Branch)]),
+        "qo_nodal_add_port": (C.c_int, [vp, C.c_int, C.c_double]),
+        "qo_nodal_add_sblock": (C.c_int, [vp, vp, ip]),
+        "qo_nodal_load_qucs_sch": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
+        "qo_nodal_num_nodes": (C.c_int, [vp]),
+        "qo_nodal_num_ports": (C.c_int, [vp]),
+        "qo_nodal_num_branches": (C.c_int, [vp]),
+        "qo_nodal_get_branches": (C.c_int, [vp, C.POINTER(Branch), C.c_int]),
+        "qo_nodal_get_ports": (C.c_int, [vp, ip, dp, C.c_int]),
+        "qo_nodal_free": (None, [vp]),
+        "qo_nodal_sweep": (C.c_int, [vp, vp, dp, C.c_int, vp]),
+        "qo_nodal_mc_run": (C.c_int, [vp, vp, dp, C.c_int, C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), C.POINTER(McResult), vp]),
         "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
         "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
         "qo_dat_write": (C.c_int, [vp, C.c_char_p]),
@@ -281,6 +309,67 @@ def load_trc(path):
     _check(lib().qo_cpl_load_trc(os.fsencode(path), C.byref(z0e), C.byref(z0o), C.byref(ang), C.byref(f0), phys))
     keys = ["er", "h", "ht", "t", "w", "s", "l", "tand"]
     return dict(z0e=z0e.value, z0o=z0o.value, ang=ang.value, f0=f0.value, **{k: phys[i] for i, k in enumerate(keys)})
+
+
+class Nodal:
+    """A general N-port netlist for the nodal solver (qo_nodal*): nodes 1..n (0 = ground)."""
+
+    def __init__(self, n_nodes=None, handle=None):
+        self._h = handle or C.c_void_p()
+        if handle is None:
+            _check(lib().qo_nodal_create(int(n_nodes), C.byref(self._h)))
+
+    @classmethod
+    def from_qucs_sch(cls, path):
+        h = C.c_void_p()
+        _check(lib().qo_nodal_load_qucs_sch(os.fsencode(path), C.byref(h)))
+        return cls(handle=h)
+
+    def add_branch(self, kind, nodes, params):
+        b = Branch()
+        b.kind = int(kind)
+        for k, v in enumerate(nodes):
+            b.node[k] = int(v)
+        for k, v in enumerate(params):
+            b.p[k] = float(v)
+        _check(lib().qo_nodal_add_branch(self._h, C.byref(b)))
+
+    def add_port(self, node, z0=50.0):
+        return _check(lib().qo_nodal_add_port(self._h, int(node), float(z0)))
+
+    def add_sblock(self, blk):
+        idx = C.c_int()
+        _check(lib().qo_nodal_add_sblock(self._h, blk._h, C.byref(idx)))
+        return idx.value
+
+    @property
+    def n_nodes(self):
+        return _check(lib().qo_nodal_num_nodes(self._h))
+
+    @property
+    def ports(self):
+        n = _check(lib().qo_nodal_num_ports(self._h))
+        node, z0 = (C.c_int * max(1, n))(), np.empty(max(1, n))
+        lib().qo_nodal_get_ports(self._h, node, _dp(z0), n)
+        return [(node[k], float(z0[k])) for k in range(n)]
+
+    @property
+    def branches(self):
+        n = _check(lib().qo_nodal_num_branches(self._h))
+        arr = (Branch * max(1, n))()
+        lib().qo_nodal_get_branches(self._h, arr, n)
+        return [(arr[i].kind, [arr[i].node[k] for k in range(4)], [arr[i].p[k] for k in range(4)]) for i in range(n)]
+
+    def close(self):
+        if self._h:
+            lib().qo_nodal_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class SBlock:
@@ -582,6 +671,32 @@ class Context:
         full = np.empty((4, n_samples, nf), dtype=np.complex128) if mode == MODE_FULL_S else None
         _check(lib().qo_mc_run(self._h, net._h, _dp(f), nf, _specs(specs), nspec, C.byref(cfg), C.byref(res),
                                full.ctypes.data_as(C.c_void_p) if full is not None else None))
+        out = _res_dict(res, fps, hist, nspec, hist_bins)
+        if full is not None:
+            out["s"] = full
+        return out
+
+    def nodal_sweep(self, nodal, f):
+        """Nominal N-port sweep -> S[nf, np, np], S[:, k, j] = b_k / a_j (Qucs S[k+1, j+1])."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        npn = len(nodal.ports)
+        out = np.empty((len(f), npn, npn), dtype=np.complex128)
+        _check(lib().qo_nodal_sweep(self._h, nodal._h, _dp(f), len(f), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def nodal_mc_run(self, nodal, f, specs, seed, n_samples, tols=(), sample_offset=0, dist=DIST_UNIFORM, mode=MODE_REDUCE_ONLY,
+                     hist_bins=0, hist_spec=0, hist_lo=0.0, hist_hi=1.0):
+        """Monte Carlo over branch parameters; specs: [(kind, row, col, f_lo, f_hi, limit_db)] on |S[row][col]|."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nf, nspec, npn = len(f), len(specs), len(nodal.ports)
+        cfg = _cfg(seed, n_samples, list(tols), sample_offset, dist, mode, 64, hist_bins, hist_spec, hist_lo, hist_hi)
+        sp = (NSpec * max(1, nspec))()
+        for i, s in enumerate(specs):
+            sp[i].kind, sp[i].row, sp[i].col, sp[i].f_lo, sp[i].f_hi, sp[i].limit = int(s[0]), int(s[1]), int(s[2]), float(s[3]), float(s[4]), float(s[5])
+        res, fps, hist = _result(nspec, hist_bins)
+        full = np.empty((n_samples, nf, npn, npn), dtype=np.complex128) if mode == MODE_FULL_S else None
+        _check(lib().qo_nodal_mc_run(self._h, nodal._h, _dp(f), nf, sp, nspec, C.byref(cfg), C.byref(res),
+                                     full.ctypes.data_as(C.c_void_p) if full is not None else None))
         out = _res_dict(res, fps, hist, nspec, hist_bins)
         if full is not None:
             out["s"] = full

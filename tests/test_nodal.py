@@ -115,3 +115,120 @@ def test_oracle_nodal_equals_cascade_on_a_ladder(R):
     S = R.nodal_sweep(br, node, [(1, 50.0), (node, 75.0)], f)
     assert np.max(np.abs(S[:, 1, 0] - s21) / np.abs(s21)) < 1e-10 and np.max(np.abs(S[:, 0, 0] - s11)) < 1e-12
     assert np.max(np.abs(S[:, 1, 1] - s22)) < 1e-12 and np.max(np.abs(S[:, 0, 1] - s12) / np.abs(s12)) < 1e-10
+
+
+def canon(branches, ports):
+    """Node-numbering-independent signature of a netlist: relabel nodes by their sorted incident (kind, value) sets."""
+    import collections
+    inc = collections.defaultdict(list)
+    for kind, nodes, p in branches:
+        nn = {NB_VCVS: 4, NB_SBLOCK: 3}.get(kind, 2)
+        for pos in range(nn):
+            if nodes[pos]:
+                inc[nodes[pos]].append((kind, pos if kind in (NB_VCVS, NB_SBLOCK) else 0, round(p[0], 18)))
+    for i, (n, z) in enumerate(ports):
+        inc[n].append((99, i, z))
+    sig = {n: tuple(sorted(v)) for n, v in inc.items()}
+    out = []
+    for kind, nodes, p in branches:
+        nn = {NB_VCVS: 4, NB_SBLOCK: 3}.get(kind, 2)
+        ends = [sig.get(nodes[pos], ()) for pos in range(nn)]
+        if nn == 2:
+            ends = sorted(ends)
+        out.append((kind, tuple(ends), tuple(round(x, 18) for x in p[:3])))
+    return sorted(out)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference tree not mounted (GPU box)")
+def test_netlister_reads_pa_bias_schematic(Q):
+    """qo_nodal_load_qucs_sch on the reference schematic == the hand-derived netlist (up to node numbering):
+    28 branches, 21 nodes, 5 ports in Pac-number order, the SPfile resolved next to the schematic."""
+    nd = Q.Nodal.from_qucs_sch(os.path.join(REFERENCE, "util/pa-bias-simulation/pa-bias-simulation.sch"))
+    br, nn, ports = hand_netlist()
+    got = nd.branches
+    assert nd.n_nodes == nn and len(got) == len(br) and [z for _, z in nd.ports] == [50.0] * 5
+    hand = [(k, list(n) + [0] * (4 - len(n)), list(p) + [0.0] * (4 - len(p))) for k, n, p in br]
+    assert canon(got, nd.ports) == canon(hand, ports)
+    # the preamp schematic (its dataset is missing upstream, .MISSING_LARGE_BLOBS) loads too
+    pre = Q.Nodal.from_qucs_sch(os.path.join(REFERENCE, "util/preamp-bias-simulation/preamp-bias-simulation.sch"))
+    assert len(pre.ports) >= 2 and any(k == NB_SBLOCK for k, _, _ in pre.branches)
+
+
+def test_nodal_container_errors(Q):
+    nd = Q.Nodal(3)
+    nd.add_branch(Q.NB_R, [1, 2], [10.0])
+    assert nd.add_port(1) == 1 and nd.add_port(3, 75.0) == 2
+    for bad in ((Q.NB_R, [1, 1], [10.0]), (Q.NB_R, [1, 9], [10.0]), (Q.NB_R, [1, 2], [-1.0]), (Q.NB_SBLOCK, [1, 2, 0], [0, 1, 50.0]), (77, [1, 2], [1.0])):
+        with pytest.raises(Q.QoError):
+            nd.add_branch(*bad)
+    with pytest.raises(Q.QoError):
+        nd.add_port(0)
+    with pytest.raises(Q.QoError):
+        Q.Nodal(0)
+    with pytest.raises(Q.QoError):
+        Q.Nodal.from_qucs_sch("/nonexistent.sch")
+
+
+def build_nodal(Q, golden_s2p):
+    """The hand netlist as a product object (the GPU box has no reference tree to load the schematic from)."""
+    br, nn, ports = hand_netlist()
+    nd = Q.Nodal(nn)
+    fd, sd = golden_s2p["11SQ39N_f"], golden_s2p["11SQ39N_s"]
+    idx = nd.add_sblock(Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], 50.0))
+    for kind, nodes, p in br:
+        if kind == NB_SBLOCK:
+            p = [idx, p[1], p[2]]
+        nd.add_branch(kind, nodes, p)
+    for node, z0 in ports:
+        nd.add_port(node, z0)
+    return nd, br, nn, ports
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s2p):
+    """The CUDA nodal kernel through the C-ABI against the reference's 5-port dataset (all 13 entries x 5000
+    points) and against the oracle."""
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    f = pa_bias["frequency"]
+    S = ctx.nodal_sweep(nd, f)
+    check_vs_dat(S, pa_bias)
+    register_inductor(R, golden_s2p)
+    O = R.nodal_sweep(br, nn, ports, f)
+    # the bias network is stiff (100 uF next to 1.2 pF): two correct LU orderings differ by ~1e-10 absolute
+    assert np.max(np.abs(S - O)) < 1e-9
+    R.sblock_clear()
+    # a small network takes the LD=8 instantiation: a resistive pad with known S
+    pad = Q.Nodal(2)
+    pad.add_branch(Q.NB_R, [1, 2], [50.0])
+    pad.add_port(1)
+    pad.add_port(2)
+    Sp = ctx.nodal_sweep(pad, np.array([1e6, 1e9]))
+    assert np.allclose(Sp[:, 0, 0], 1 / 3) and np.allclose(Sp[:, 1, 0], 2 / 3) and np.allclose(Sp, Sp.transpose(0, 2, 1))
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_monte_carlo_equals_oracle(Q, R, ctx, pa_bias, golden_s2p):
+    """Yield over the bias network's R/C tolerances: specs on |S21| (pass band) and |S31| (bias-port isolation);
+    integer counters, histogram and FULL_S planes equal the oracle's."""
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    register_inductor(R, golden_s2p)
+    f = pa_bias["frequency"][100:1400:13]                     # 0.2 - 2.8 GHz, 100 points
+    nom = ctx.nodal_sweep(nd, f)
+    s21 = 20 * np.log10(np.abs(nom[:, 1, 0]))
+    s31 = 20 * np.log10(np.abs(nom[:, 2, 0]))
+    band = (f >= 2.3e9) & (f <= 2.5e9)
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, float(s21[band].min()) - 0.02),
+             (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, float(s31[band].max()) + 0.3)]
+    tols = [(i, 0, v, Q.TOL_REL, 0.05 if k == NB_C else 0.01) for v, (i, (k, _n, _p)) in
+            enumerate((i, b) for i, b in enumerate(br) if b[0] in (NB_R, NB_C))]
+    hist = dict(hist_bins=20, hist_spec=0, hist_lo=float(s21[band].min()) - 0.3, hist_hi=float(s21[band].min()) + 0.3)
+    n = 400
+    got = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, **hist)
+    from oracle import refbind
+    ref = R.nodal_mc_run(br, nn, ports, f, specs, refbind.mc_cfg(21, n, tols, **hist), nthreads=8)
+    assert got["n_total"] == n and got["n_pass"] == ref["n_pass"] and 0 < got["n_pass"] < n
+    assert np.array_equal(got["fail_per_spec"], ref["fail_per_spec"]) and np.array_equal(got["hist"], ref["hist"])
+    gs = ctx.nodal_mc_run(nd, f[:31], [], 21, 7, tols, mode=Q.MODE_FULL_S)["s"]
+    os_ = R.nodal_mc_run(br, nn, ports, f[:31], [], refbind.mc_cfg(21, 7, tols), full_s=True)["s"]
+    assert gs.shape == (7, 31, 5, 5) and np.max(np.abs(gs - os_)) < 1e-9
+    R.sblock_clear()

@@ -161,8 +161,12 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const double *__restrict__ f
                 const int pn = prog->port_node[p] - 1;
                 A[pn * LD + pn].x += 1.0 / prog->port_z0[p];
             }
-            /* LU, partial pivoting (rows are swapped physically: n is small) */
+            /* LU, partial pivoting (rows are swapped physically: n <= 32).  Nodal matrices are sparse and every
+             * point of a job shares one sparsity pattern, so the elimination walks bit masks of the non-zero
+             * columns instead of full rows (warp-coherent: the masks are the same in all lanes unless a pivot
+             * choice differs); lmask/umask record the factors' patterns for the substitutions. */
             bool singular = false;
+            unsigned int lmask[LD], umask[LD];
             for (int c = 0; c < n; c++) {
                 int piv = c;
                 double best = A[c * LD + c].x * A[c * LD + c].x + A[c * LD + c].y * A[c * LD + c].y;
@@ -176,14 +180,27 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const double *__restrict__ f
                     for (int j = 0; j < n; j++) { const double2 t = A[c * LD + j]; A[c * LD + j] = A[piv * LD + j]; A[piv * LD + j] = t; }
                     const int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
                 }
+                unsigned int nz = 0;
+                for (int j = c + 1; j < n; j++) { const double2 v = A[c * LD + j]; if (v.x != 0.0 || v.y != 0.0) nz |= 1u << j; }
+                umask[c] = nz;
                 const double2 inv = c_inv(A[c * LD + c]);
                 for (int r = c + 1; r < n; r++) {
-                    const double2 l = c_mul(A[r * LD + c], inv);
-                    if (l.x == 0.0 && l.y == 0.0) continue;            /* nodal matrices are sparse: skip empty rows */
+                    const double2 a = A[r * LD + c];
+                    if (a.x == 0.0 && a.y == 0.0) continue;
+                    const double2 l = c_mul(a, inv);
                     A[r * LD + c] = l;
-                    for (int j = c + 1; j < n; j++) A[r * LD + j] = c_fms(A[r * LD + j], l, A[c * LD + j]);
+                    for (unsigned int m = nz; m; m &= m - 1) {
+                        const int j = __ffs((int)m) - 1;
+                        A[r * LD + j] = c_fms(A[r * LD + j], l, A[c * LD + j]);
+                    }
                 }
             }
+            if (!singular)
+                for (int i = 0; i < n; i++) {
+                    unsigned int lm = 0;
+                    for (int q = 0; q < i; q++) { const double2 v = A[i * LD + q]; if (v.x != 0.0 || v.y != 0.0) lm |= 1u << q; }
+                    lmask[i] = lm;
+                }
             const size_t obase = (((size_t)s * (size_t)nf + (size_t)k) * (size_t)np) * (size_t)np;
             const unsigned int mb = mask[k];
             for (int j = 0; j < np; j++) {
@@ -194,12 +211,12 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const double *__restrict__ f
                 else {
                     for (int i = 1; i < n; i++) {
                         double2 acc = x[i];
-                        for (int q = 0; q < i; q++) acc = c_fms(acc, A[i * LD + q], x[q]);
+                        for (unsigned int m = lmask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
                         x[i] = acc;
                     }
                     for (int i = n - 1; i >= 0; i--) {
                         double2 acc = x[i];
-                        for (int q = i + 1; q < n; q++) acc = c_fms(acc, A[i * LD + q], x[q]);
+                        for (unsigned int m = umask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
                         x[i] = c_mul(acc, c_inv(A[i * LD + i]));
                     }
                 }

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Throughput of the N-port nodal kernel (row N4) on the reference's 5-port bias network
+(util/pa-bias-simulation/pa-bias-simulation.sch; netlist rebuilt from tests/test_nodal.py::hand_netlist so that it
+runs on the GPU box), Monte Carlo over every R and C, next to the CPU oracle on all host cores.
+
+  python tools/nodal_bench.py [--samples 20000] [--nf 1000] [--out gpurun_out/nodal.json]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=20000)
+    ap.add_argument("--nf", type=int, default=1000)
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args()
+    import qo100net as Q
+    from oracle import refbind as R
+    import test_nodal as T
+    g = np.load(os.path.join(ROOT, "tests", "golden", "touchstone.npz"))
+    nd, br, nn, ports = T.build_nodal(Q, g)
+    T.register_inductor(R, g)
+    ctx = Q.Context(device=0)
+    f = Q.grid_lin(1e8, 3e9, args.nf)
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, -3.0), (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, -25.0)]
+    tols = [(i, 0, v, Q.TOL_REL, 0.05 if b[0] == T.NB_C else 0.01) for v, (i, b) in
+            enumerate((i, b) for i, b in enumerate(br) if b[0] in (T.NB_R, T.NB_C))]
+    hist = dict(hist_bins=64, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)
+    n = args.samples
+    ctx.nodal_mc_run(nd, f, specs, 5, 256, tols, **hist)
+    best = None
+    for rep in range(3):
+        r = ctx.nodal_mc_run(nd, f, specs, 5, n, tols, sample_offset=rep * n, **hist)
+        best = r if best is None or r["seconds"] < best["seconds"] else best
+    peak = ctx.measure_dfma_peak()
+    ncpu = 400
+    nthr = R.max_threads()
+    t0 = time.perf_counter()
+    o = R.nodal_mc_run(br, nn, ports, f, specs, R.mc_cfg(5, ncpu, tols, **hist), nthreads=nthr)
+    cpu_s = time.perf_counter() - t0
+    chk = ctx.nodal_mc_run(nd, f, specs, 5, ncpu, tols, **hist)
+    out = {"workload": "pa-bias 5-port network, 23 unknowns, %d samples x %d points, reduce-only" % (n, args.nf),
+           "gpu_kernel_seconds": best["seconds"], "gpu_points_per_s": n * args.nf / best["seconds"],
+           "real_flops_per_point_lu_plus_solves": best["flops_per_eval"],
+           "gpu_tflops": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12, "dfma_peak_tflops": peak,
+           "frac_of_dfma_peak": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12 / peak,
+           "cpu_oracle_points_per_s": ncpu * args.nf / cpu_s, "cpu_cores": nthr,
+           "counters_equal_oracle": bool(chk["n_pass"] == o["n_pass"] and np.array_equal(chk["hist"], o["hist"])),
+           "yield": best["n_pass"] / n}
+    print(json.dumps(out, indent=1))
+    if args.out:
+        open(args.out, "w").write(json.dumps(out, indent=1))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

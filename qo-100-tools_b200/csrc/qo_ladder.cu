@@ -60,6 +60,9 @@ extern "C" int qo_ladder_launch(int n, int first, int cpl, int variant, int sm_c
     case 4: fn = lad_pick11<1, 128, 6>(n, first, cpl); tpb = 128; minb = 6; name = "pp1-128x6"; break;
     case 5: fn = lad_pick11<1, 256, 4>(n, first, cpl); tpb = 256; minb = 4; name = "pp1-256x4"; break;
     case 6: fn = lad_pick11<2, 128, 4>(n, first, cpl); tpb = 128; minb = 4; name = "pp2-128x4"; break;
+    case 7: fn = lad_pick11<2, 128, 5>(n, first, cpl); tpb = 128; minb = 5; name = "pp2-128x5"; break;
+    case 8: fn = lad_pick11<2, 256, 3>(n, first, cpl); tpb = 256; minb = 3; name = "pp2-256x3"; break;
+    case 9: fn = lad_pick11<2, 64, 8>(n, first, cpl); tpb = 64; minb = 8; name = "pp2-64x8"; break;
     default: break;
     }
 #endif

@@ -240,6 +240,11 @@ int qo_nodal_sweep(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, qo_
 int qo_nodal_mc_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
                     const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
 
+/* which factorisation the calling thread's last nodal call used: "qo_nodal_kernel<static>" (symbolic plan: fixed
+ * pivot order and fill pattern, verified on the host against the pivoted solve) or "qo_nodal_kernel<dense>"
+ * (per-point partial pivoting; QO100NET_NODAL=dense forces it) */
+const char *qo_nodal_last_kernel(void);
+
 /* The same job kept resident in HBM (tables, grid, specs uploaded once):
  *   counters layout (uint64): [0]=n_pass [1]=n_total [2..2+nspec)=fail_per_spec, then hist[hist_bins].
  * qo_plan_launch is asynchronous on the ctx stream and ADDS into counters_dev

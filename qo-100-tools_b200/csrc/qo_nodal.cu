@@ -59,13 +59,137 @@ __device__ __forceinline__ double2 c_fms(double2 a, double2 l, double2 u)
     return a;
 }
 
-template <int LD> __device__ __forceinline__ void stamp(double2 *A, int a, int b, double2 y)
+/* ---- static (symbolic) factorisation plan ----------------------------------------------------------------
+ * Every point of a job has the same sparsity pattern, and for these networks the same pivot order works over
+ * the whole band, so the host factorises ONCE symbolically: it takes the row order a pivoted LU chooses at a
+ * representative point, computes the fill pattern, packs the non-zeros (fill included) into a compact value
+ * array and emits a branch-free "program" of value-array indices for elimination and substitutions.  The
+ * kernel then runs that program -- no pivot search, no row swaps, no zero tests, ~10x fewer value accesses than
+ * the dense factorisation.  The host runs the same program at several grid points and compares with the
+ * pivoted dense solution; if they disagree (a pivot that is only good at some frequencies) the job falls back
+ * to the dense kernel (QO100NET_NODAL=dense forces it). */
+#define QN_PROG_MAX 6144       /* uint16 words of program */
+#define QN_NNZ_MAX 512
+struct NodalStatic {
+    int32_t n, nnz, prog_len, solve_l_at, solve_u_at, pad;
+    int16_t pos[QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK];   /* (permuted row, column) -> value index, -1 = structural zero */
+    uint8_t rowmap[QO_NODAL_MAX_UNK];                   /* original row -> permuted row */
+    uint16_t prog[QN_PROG_MAX];
+};
+
+/* where a stamp lands: dense matrix with leading dimension LD ... */
+template <int LD> struct DenseSink {
+    double2 *A;
+    __host__ __device__ __forceinline__ void add(int r, int c, double2 v) { A[r * LD + c].x += v.x; A[r * LD + c].y += v.y; }
+};
+/* ... or the compact value array of the static plan (rows already in pivot order) */
+struct StaticSink {
+    double2 *V;
+    const int16_t *pos;
+    const uint8_t *rowmap;
+    __host__ __device__ __forceinline__ void add(int r, int c, double2 v)
+    {
+        const int q = pos[rowmap[r] * QO_NODAL_MAX_UNK + c];
+        V[q].x += v.x; V[q].y += v.y;
+    }
+};
+
+template <class Sink> __host__ __device__ __forceinline__ void stamp_y(Sink &S, int a, int b, double2 y)
 {
-    if (a) A[(a - 1) * LD + (a - 1)] = c_add(A[(a - 1) * LD + (a - 1)], y);
-    if (b) A[(b - 1) * LD + (b - 1)] = c_add(A[(b - 1) * LD + (b - 1)], y);
-    if (a && b) {
-        A[(a - 1) * LD + (b - 1)] = c_sub(A[(a - 1) * LD + (b - 1)], y);
-        A[(b - 1) * LD + (a - 1)] = c_sub(A[(b - 1) * LD + (a - 1)], y);
+    const double2 my = make_double2(-y.x, -y.y);
+    if (a) S.add(a - 1, a - 1, y);
+    if (b) S.add(b - 1, b - 1, y);
+    if (a && b) { S.add(a - 1, b - 1, my); S.add(b - 1, a - 1, my); }
+}
+
+__host__ __device__ __forceinline__ double2 hd_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__host__ __device__ __forceinline__ double2 hd_inv(double2 b) { const double d = 1.0 / (b.x * b.x + b.y * b.y); return make_double2(b.x * d, -b.y * d); }
+__host__ __device__ __forceinline__ double2 hd_fms(double2 a, double2 l, double2 u)
+{
+    a.x = fma(-l.x, u.x, a.x); a.x = fma(l.y, u.y, a.x);
+    a.y = fma(-l.x, u.y, a.y); a.y = fma(-l.y, u.x, a.y);
+    return a;
+}
+
+/* all stamps of one (sample, frequency) point: branches with the sample's parameters par[b][0..3], the measured
+ * blocks' tabulated admittances yk (4 values per block branch, in branch order), port terminations */
+template <class Sink>
+__host__ __device__ __forceinline__ void nodal_stamp_all(const NodalProg *prog, const double (*par)[4], double w, const double2 *yk,
+                                                         size_t yk_stride, Sink &S)
+{
+    int extra = prog->n_nodes, iblk = 0;
+    for (int b = 0; b < prog->nb; b++) {
+        const int kind = prog->kind[b];
+        const int n0 = prog->node[b][0], n1 = prog->node[b][1], n2 = prog->node[b][2], n3 = prog->node[b][3];
+        const double p0 = par[b][0], p1 = par[b][1], p2 = par[b][2];
+        if (kind == QO_NB_R) stamp_y(S, n0, n1, make_double2(1.0 / p0, 0.0));
+        else if (kind == QO_NB_L) {                /* Y = (1 - w^2 L Cp + j w R Cp) / (R + jwL) */
+            const double2 num = make_double2(1.0 - w * w * p0 * p2, w * p1 * p2);
+            stamp_y(S, n0, n1, hd_mul(num, hd_inv(make_double2(p1, w * p0))));
+        } else if (kind == QO_NB_C) {              /* Y = 1 / (R + j(w Ls - 1/(wC))) */
+            stamp_y(S, n0, n1, hd_inv(make_double2(p1, w * p2 - 1.0 / (w * p0))));
+        } else if (kind == QO_NB_VCVS) {           /* in+ n0, out+ n1, out- n2, in- n3; current unknown kx */
+            const int kx = extra++;
+            const double cs = cos(w * p1), sn = sin(w * p1);
+            const double2 g = make_double2(p0 * cs, -p0 * sn), mg = make_double2(-g.x, -g.y);
+            const double2 one = make_double2(1.0, 0.0), mone = make_double2(-1.0, 0.0);
+            if (n1) { S.add(n1 - 1, kx, one); S.add(kx, n1 - 1, one); }
+            if (n2) { S.add(n2 - 1, kx, mone); S.add(kx, n2 - 1, mone); }
+            if (n0) S.add(kx, n0 - 1, mg);
+            if (n3) S.add(kx, n3 - 1, g);
+        } else if (kind == QO_NB_SBLOCK) {         /* tabulated 2x2 admittance; indefinite form with reference n2 */
+            const double2 *y = yk + (size_t)iblk * yk_stride;
+            iblk++;
+            const int t[3] = { n0, n1, n2 };
+            double2 Y3[3][3];
+            Y3[0][0] = y[0]; Y3[0][1] = y[1]; Y3[1][0] = y[2]; Y3[1][1] = y[3];
+            Y3[0][2] = make_double2(-(y[0].x + y[1].x), -(y[0].y + y[1].y));
+            Y3[1][2] = make_double2(-(y[2].x + y[3].x), -(y[2].y + y[3].y));
+            for (int c = 0; c < 3; c++) Y3[2][c] = make_double2(-(Y3[0][c].x + Y3[1][c].x), -(Y3[0][c].y + Y3[1][c].y));
+            for (int r = 0; r < 3; r++)
+                for (int c = 0; c < 3; c++)
+                    if (t[r] && t[c]) S.add(t[r] - 1, t[c] - 1, Y3[r][c]);
+        }
+    }
+    for (int p = 0; p < prog->np; p++) S.add(prog->port_node[p] - 1, prog->port_node[p] - 1, make_double2(1.0 / prog->port_z0[p], 0.0));
+}
+
+/* run the elimination part of a static program on the value array V */
+__host__ __device__ __forceinline__ void static_factor(const uint16_t *pg, int n, double2 *V)
+{
+    int ip = 0;
+    for (int c = 0; c < n; c++) {
+        const double2 inv = hd_inv(V[pg[ip]]);
+        const int nu = pg[ip + 1];
+        const uint16_t *ucol = pg + ip + 2;          /* value indices of the pivot row's entries right of the pivot */
+        ip += 2 + nu;
+        const int nrows = pg[ip++];
+        for (int r = 0; r < nrows; r++) {
+            const int prc = pg[ip++];
+            const double2 l = hd_mul(V[prc], inv);
+            V[prc] = l;
+            for (int q = 0; q < nu; q++) { const int prj = pg[ip + q]; V[prj] = hd_fms(V[prj], l, V[ucol[q]]); }
+            ip += nu;
+        }
+    }
+}
+
+/* forward / backward substitution of x (length n, rows in pivot order) with the factors in V */
+__host__ __device__ __forceinline__ void static_solve(const uint16_t *pg, int lat, int uat, int n, const double2 *V, double2 *x)
+{
+    int ip = lat;
+    for (int i = 0; i < n; i++) {
+        const int nl = pg[ip++];
+        double2 acc = x[i];
+        for (int q = 0; q < nl; q++) { acc = hd_fms(acc, V[pg[ip + 1]], x[pg[ip]]); ip += 2; }
+        x[i] = acc;
+    }
+    ip = uat;
+    for (int i = n - 1; i >= 0; i--) {
+        const int pii = pg[ip++], nu = pg[ip++];
+        double2 acc = x[i];
+        for (int q = 0; q < nu; q++) { acc = hd_fms(acc, V[pg[ip + 1]], x[pg[ip]]); ip += 2; }
+        x[i] = hd_mul(acc, hd_inv(V[pii]));
     }
 }
 
@@ -73,12 +197,22 @@ template <int LD> __device__ __forceinline__ void stamp(double2 *A, int a, int b
  * unit u = sample * nchunks + chunk; a block works on one unit at a time: QN_TPB consecutive grid points per
  * pass.  Reduce-only jobs use nchunks == 1 (the block walks the whole grid of its sample and then reduces).
  */
-template <int LD>
+template <int LD, bool STATIC, int NNZ>
 __global__ void __launch_bounds__(QN_TPB)
-qo_nodal_kernel(const NodalProg *__restrict__ prog, const double *__restrict__ fgrid, const unsigned char *__restrict__ mask,
-                const double2 *__restrict__ yblk, int nf, int chunk_len, int nchunks, unsigned long long sample_offset,
-                unsigned long long nsamples, unsigned long long *__restrict__ counters, double2 *__restrict__ s_out)
+qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restrict__ splan, const double *__restrict__ fgrid,
+                const unsigned char *__restrict__ mask, const double2 *__restrict__ yblk, int nf, int chunk_len, int nchunks,
+                unsigned long long sample_offset, unsigned long long nsamples, unsigned long long *__restrict__ counters,
+                double2 *__restrict__ s_out)
 {
+    /* static plan staged in shared memory: every thread walks the same program (broadcast reads) */
+    __shared__ int16_t s_pos[STATIC ? QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK : 1];
+    __shared__ uint8_t s_rowmap[QO_NODAL_MAX_UNK];
+    __shared__ uint16_t s_prog[STATIC ? QN_PROG_MAX : 1];
+    if (STATIC) {
+        for (int i = threadIdx.x; i < QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK; i += QN_TPB) s_pos[i] = splan->pos[i];
+        for (int i = threadIdx.x; i < QO_NODAL_MAX_UNK; i += QN_TPB) s_rowmap[i] = splan->rowmap[i];
+        for (int i = threadIdx.x; i < splan->prog_len; i += QN_TPB) s_prog[i] = splan->prog[i];
+    }
     __shared__ double s_p[QO_NODAL_MAX_BR][4];
     __shared__ double s_x[QN_MAX_VAR];
     __shared__ double s_trk[QN_MAX_SPEC][QN_TPB / 32];
@@ -111,113 +245,85 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const double *__restrict__ f
         for (int sp = 0; sp < QN_MAX_SPEC; sp++) trk[sp] = -1e300;       /* running max of (+-)|S|^2 */
         const int k_lo = chunk * chunk_len, k_hi = min(nf, k_lo + chunk_len);
         for (int k = k_lo + tid; k < k_hi; k += QN_TPB) {
-            double2 A[LD * LD];
-            int perm[LD];
             const double w = 6.283185307179586476925286766559 * fgrid[k];
-            for (int i = 0; i < n; i++) {
-                perm[i] = i;
-                for (int j = 0; j < n; j++) A[i * LD + j] = make_double2(0.0, 0.0);
-            }
-            int extra = n_nodes, iblk = 0;
-            for (int b = 0; b < nb; b++) {
-                const int kind = prog->kind[b];
-                const int n0 = prog->node[b][0], n1 = prog->node[b][1], n2 = prog->node[b][2], n3 = prog->node[b][3];
-                const double p0 = s_p[b][0], p1 = s_p[b][1], p2 = s_p[b][2];
-                if (kind == QO_NB_R) stamp<LD>(A, n0, n1, make_double2(1.0 / p0, 0.0));
-                else if (kind == QO_NB_L) {                /* Y = (1 - w^2 L Cp + j w R Cp) / (R + jwL) */
-                    const double2 num = make_double2(1.0 - w * w * p0 * p2, w * p1 * p2);
-                    stamp<LD>(A, n0, n1, c_mul(num, c_inv(make_double2(p1, w * p0))));
-                } else if (kind == QO_NB_C) {              /* Y = 1 / (R + j(w Ls - 1/(wC))) */
-                    stamp<LD>(A, n0, n1, c_inv(make_double2(p1, w * p2 - 1.0 / (w * p0))));
-                } else if (kind == QO_NB_VCVS) {
-                    const int kx = extra++;
-                    double sn, cs;
-                    sincos(w * p1, &sn, &cs);
-                    const double2 g = make_double2(p0 * cs, -p0 * sn);
-                    if (n1) { A[(n1 - 1) * LD + kx].x += 1.0; A[kx * LD + (n1 - 1)].x += 1.0; }
-                    if (n2) { A[(n2 - 1) * LD + kx].x -= 1.0; A[kx * LD + (n2 - 1)].x -= 1.0; }
-                    if (n0) A[kx * LD + (n0 - 1)] = c_sub(A[kx * LD + (n0 - 1)], g);
-                    if (n3) A[kx * LD + (n3 - 1)] = c_add(A[kx * LD + (n3 - 1)], g);
-                } else if (kind == QO_NB_SBLOCK) {
-                    /* tabulated 2x2 admittance of the block at this grid point; indefinite form with reference n2 */
-                    const double2 *y = yblk + ((size_t)iblk * (size_t)nf + (size_t)k) * 4;
-                    iblk++;
-                    const double2 y11 = y[0], y12 = y[1], y21 = y[2], y22 = y[3];
-                    const int t[3] = { n0, n1, n2 };
-                    double2 Y3[3][3];
-                    Y3[0][0] = y11; Y3[0][1] = y12; Y3[1][0] = y21; Y3[1][1] = y22;
-                    Y3[0][2] = make_double2(-(y11.x + y12.x), -(y11.y + y12.y));
-                    Y3[1][2] = make_double2(-(y21.x + y22.x), -(y21.y + y22.y));
-#pragma unroll
-                    for (int c = 0; c < 3; c++) Y3[2][c] = make_double2(-(Y3[0][c].x + Y3[1][c].x), -(Y3[0][c].y + Y3[1][c].y));
-#pragma unroll
-                    for (int r = 0; r < 3; r++)
-#pragma unroll
-                        for (int c = 0; c < 3; c++)
-                            if (t[r] && t[c]) A[(t[r] - 1) * LD + (t[c] - 1)] = c_add(A[(t[r] - 1) * LD + (t[c] - 1)], Y3[r][c]);
-                }
-            }
-            for (int p = 0; p < np; p++) {
-                const int pn = prog->port_node[p] - 1;
-                A[pn * LD + pn].x += 1.0 / prog->port_z0[p];
-            }
-            /* LU, partial pivoting (rows are swapped physically: n <= 32).  Nodal matrices are sparse and every
-             * point of a job shares one sparsity pattern, so the elimination walks bit masks of the non-zero
-             * columns instead of full rows (warp-coherent: the masks are the same in all lanes unless a pivot
-             * choice differs); lmask/umask record the factors' patterns for the substitutions. */
+            const double2 *yk = yblk + (size_t)k * 4;                 /* block admittances: [block][nf][4] */
+            double2 A[STATIC ? NNZ : LD * LD];
+            int perm[STATIC ? 1 : LD];
+            unsigned int lmask[STATIC ? 1 : LD], umask[STATIC ? 1 : LD];
             bool singular = false;
-            unsigned int lmask[LD], umask[LD];
-            for (int c = 0; c < n; c++) {
-                int piv = c;
-                double best = A[c * LD + c].x * A[c * LD + c].x + A[c * LD + c].y * A[c * LD + c].y;
-                for (int r = c + 1; r < n; r++) {
-                    const double2 v = A[r * LD + c];
-                    const double m = v.x * v.x + v.y * v.y;
-                    if (m > best) { best = m; piv = r; }
+            if (STATIC) {
+                const int nnz = splan->nnz;
+                for (int i = 0; i < nnz; i++) A[i] = make_double2(0.0, 0.0);
+                StaticSink S = { A, s_pos, s_rowmap };
+                nodal_stamp_all(prog, s_p, w, yk, (size_t)nf * 4, S);
+                static_factor(s_prog, n, A);
+            } else {
+                for (int i = 0; i < n; i++) {
+                    perm[i] = i;
+                    for (int j = 0; j < n; j++) A[i * LD + j] = make_double2(0.0, 0.0);
                 }
-                if (!(best > 0.0)) { singular = true; break; }
-                if (piv != c) {
-                    for (int j = 0; j < n; j++) { const double2 t = A[c * LD + j]; A[c * LD + j] = A[piv * LD + j]; A[piv * LD + j] = t; }
-                    const int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
-                }
-                unsigned int nz = 0;
-                for (int j = c + 1; j < n; j++) { const double2 v = A[c * LD + j]; if (v.x != 0.0 || v.y != 0.0) nz |= 1u << j; }
-                umask[c] = nz;
-                const double2 inv = c_inv(A[c * LD + c]);
-                for (int r = c + 1; r < n; r++) {
-                    const double2 a = A[r * LD + c];
-                    if (a.x == 0.0 && a.y == 0.0) continue;
-                    const double2 l = c_mul(a, inv);
-                    A[r * LD + c] = l;
-                    for (unsigned int m = nz; m; m &= m - 1) {
-                        const int j = __ffs((int)m) - 1;
-                        A[r * LD + j] = c_fms(A[r * LD + j], l, A[c * LD + j]);
+                DenseSink<LD> S = { A };
+                nodal_stamp_all(prog, s_p, w, yk, (size_t)nf * 4, S);
+                /* LU, partial pivoting (rows are swapped physically: n <= 32), walking bit masks of the non-zero
+                 * columns instead of full rows; lmask/umask record the factors' patterns for the substitutions */
+                for (int c = 0; c < n; c++) {
+                    int piv = c;
+                    double best = A[c * LD + c].x * A[c * LD + c].x + A[c * LD + c].y * A[c * LD + c].y;
+                    for (int r = c + 1; r < n; r++) {
+                        const double2 v = A[r * LD + c];
+                        const double m = v.x * v.x + v.y * v.y;
+                        if (m > best) { best = m; piv = r; }
+                    }
+                    if (!(best > 0.0)) { singular = true; break; }
+                    if (piv != c) {
+                        for (int j = 0; j < n; j++) { const double2 t = A[c * LD + j]; A[c * LD + j] = A[piv * LD + j]; A[piv * LD + j] = t; }
+                        const int t = perm[c]; perm[c] = perm[piv]; perm[piv] = t;
+                    }
+                    unsigned int nz = 0;
+                    for (int j = c + 1; j < n; j++) { const double2 v = A[c * LD + j]; if (v.x != 0.0 || v.y != 0.0) nz |= 1u << j; }
+                    umask[c] = nz;
+                    const double2 inv = c_inv(A[c * LD + c]);
+                    for (int r = c + 1; r < n; r++) {
+                        const double2 a = A[r * LD + c];
+                        if (a.x == 0.0 && a.y == 0.0) continue;
+                        const double2 l = c_mul(a, inv);
+                        A[r * LD + c] = l;
+                        for (unsigned int m = nz; m; m &= m - 1) {
+                            const int j = __ffs((int)m) - 1;
+                            A[r * LD + j] = c_fms(A[r * LD + j], l, A[c * LD + j]);
+                        }
                     }
                 }
+                if (!singular)
+                    for (int i = 0; i < n; i++) {
+                        unsigned int lm = 0;
+                        for (int q = 0; q < i; q++) { const double2 v = A[i * LD + q]; if (v.x != 0.0 || v.y != 0.0) lm |= 1u << q; }
+                        lmask[i] = lm;
+                    }
             }
-            if (!singular)
-                for (int i = 0; i < n; i++) {
-                    unsigned int lm = 0;
-                    for (int q = 0; q < i; q++) { const double2 v = A[i * LD + q]; if (v.x != 0.0 || v.y != 0.0) lm |= 1u << q; }
-                    lmask[i] = lm;
-                }
             const size_t obase = (((size_t)s * (size_t)nf + (size_t)k) * (size_t)np) * (size_t)np;
             const unsigned int mb = mask[k];
             for (int j = 0; j < np; j++) {
                 double2 x[LD];
                 const int src = prog->port_node[j] - 1;
-                for (int i = 0; i < n; i++) x[i] = make_double2(perm[i] == src ? 1.0 / prog->port_z0[j] : 0.0, 0.0);
-                if (singular) { for (int i = 0; i < n; i++) x[i] = make_double2(nan(""), nan("")); }
-                else {
-                    for (int i = 1; i < n; i++) {
-                        double2 acc = x[i];
-                        for (unsigned int m = lmask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
-                        x[i] = acc;
-                    }
-                    for (int i = n - 1; i >= 0; i--) {
-                        double2 acc = x[i];
-                        for (unsigned int m = umask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
-                        x[i] = c_mul(acc, c_inv(A[i * LD + i]));
+                if (STATIC) {
+                    const int srow = s_rowmap[src];
+                    for (int i = 0; i < n; i++) x[i] = make_double2(i == srow ? 1.0 / prog->port_z0[j] : 0.0, 0.0);
+                    static_solve(s_prog, splan->solve_l_at, splan->solve_u_at, n, A, x);
+                } else {
+                    for (int i = 0; i < n; i++) x[i] = make_double2(perm[i] == src ? 1.0 / prog->port_z0[j] : 0.0, 0.0);
+                    if (singular) { for (int i = 0; i < n; i++) x[i] = make_double2(nan(""), nan("")); }
+                    else {
+                        for (int i = 1; i < n; i++) {
+                            double2 acc = x[i];
+                            for (unsigned int m = lmask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
+                            x[i] = acc;
+                        }
+                        for (int i = n - 1; i >= 0; i--) {
+                            double2 acc = x[i];
+                            for (unsigned int m = umask[i]; m; m &= m - 1) { const int q = __ffs((int)m) - 1; acc = c_fms(acc, A[i * LD + q], x[q]); }
+                            x[i] = c_mul(acc, c_inv(A[i * LD + i]));
+                        }
                     }
                 }
                 for (int kk = 0; kk < np; kk++) {
@@ -302,6 +408,136 @@ static void s_to_y(const qo_c64 s[4], double z0, qo_c64 y[4])
     for (int i = 0; i < 4; i++) { y[i].re /= z0; y[i].im /= z0; }
 }
 
+static __thread const char *g_last_kernel = "";
+extern "C" const char *qo_nodal_last_kernel(void) { return g_last_kernel; }
+
+/* ---- host: symbolic factorisation ------------------------------------------------------------------------- */
+typedef std::vector<double2> cvec;
+
+/* dense pivoted solve of one point on the host (reference for the static plan's self-check): returns the
+ * solution columns X[j][i] for every port j and the row order the pivoting chose */
+static bool host_dense(const NodalProg *hp, double f, const double2 *yk, size_t yk_stride, std::vector<int> *perm_out, std::vector<cvec> *X)
+{
+    const int n = hp->n_unk, LD = QO_NODAL_MAX_UNK;
+    cvec A((size_t)LD * LD, make_double2(0.0, 0.0));
+    DenseSink<QO_NODAL_MAX_UNK> S = { A.data() };
+    nodal_stamp_all(hp, hp->nom, 6.283185307179586476925286766559 * f, yk, yk_stride, S);
+    std::vector<int> perm(n);
+    for (int i = 0; i < n; i++) perm[i] = i;
+    for (int c = 0; c < n; c++) {
+        int piv = c;
+        double best = A[c * LD + c].x * A[c * LD + c].x + A[c * LD + c].y * A[c * LD + c].y;
+        for (int r = c + 1; r < n; r++) { const double2 v = A[r * LD + c]; const double m = v.x * v.x + v.y * v.y; if (m > best) { best = m; piv = r; } }
+        if (!(best > 0.0)) return false;
+        if (piv != c) { for (int j = 0; j < n; j++) std::swap(A[c * LD + j], A[piv * LD + j]); std::swap(perm[c], perm[piv]); }
+        const double2 inv = hd_inv(A[c * LD + c]);
+        for (int r = c + 1; r < n; r++) {
+            const double2 l = hd_mul(A[r * LD + c], inv);
+            A[r * LD + c] = l;
+            for (int j = c + 1; j < n; j++) A[r * LD + j] = hd_fms(A[r * LD + j], l, A[c * LD + j]);
+        }
+    }
+    if (perm_out) *perm_out = perm;
+    if (X) {
+        X->assign(hp->np, cvec(n));
+        for (int j = 0; j < hp->np; j++) {
+            cvec &x = (*X)[j];
+            for (int i = 0; i < n; i++) x[i] = make_double2(perm[i] == hp->port_node[j] - 1 ? 1.0 / hp->port_z0[j] : 0.0, 0.0);
+            for (int i = 1; i < n; i++) for (int q = 0; q < i; q++) x[i] = hd_fms(x[i], A[i * LD + q], x[q]);
+            for (int i = n - 1; i >= 0; i--) { for (int q = i + 1; q < n; q++) x[i] = hd_fms(x[i], A[i * LD + q], x[q]); x[i] = hd_mul(x[i], hd_inv(A[i * LD + i])); }
+        }
+    }
+    return true;
+}
+
+/* structural pattern of the stamps: a sink that only marks */
+struct MarkSink {
+    unsigned char *m;
+    void add(int r, int c, double2) { m[r * QO_NODAL_MAX_UNK + c] = 1; }
+};
+
+/* Build the static plan from the row order chosen at grid point k_ref; verify it at several grid points.
+ * Returns false when the job should use the dense kernel. */
+static bool build_static(const NodalProg *hp, const double *f, int nf, const double2 *yb, NodalStatic *sp)
+{
+    const int n = hp->n_unk, LD = QO_NODAL_MAX_UNK;
+    std::vector<int> perm;
+    const int k_ref = nf / 2;
+    if (!host_dense(hp, f[k_ref], yb + (size_t)k_ref * 4, (size_t)nf * 4, &perm, NULL)) return false;
+    memset(sp, 0, sizeof *sp);
+    sp->n = n;
+    for (int i = 0; i < n; i++) sp->rowmap[perm[i]] = (uint8_t)i;          /* original row perm[i] sits at position i */
+    /* pattern in pivot order, then symbolic elimination (fill) */
+    std::vector<unsigned char> raw((size_t)LD * LD, 0), pat((size_t)LD * LD, 0);
+    MarkSink M = { raw.data() };
+    nodal_stamp_all(hp, hp->nom, 1.0, yb, (size_t)nf * 4, M);
+    for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) if (raw[r * LD + c]) pat[sp->rowmap[r] * LD + c] = 1;
+    for (int c = 0; c < n; c++) {
+        if (!pat[c * LD + c]) return false;                                 /* structurally zero pivot */
+        for (int r = c + 1; r < n; r++)
+            if (pat[r * LD + c])
+                for (int j = c + 1; j < n; j++) if (pat[c * LD + j]) pat[r * LD + j] = 1;
+    }
+    int nnz = 0;
+    for (int i = 0; i < LD * LD; i++) sp->pos[i] = -1;
+    for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) if (pat[r * LD + c]) sp->pos[r * LD + c] = (int16_t)nnz++;
+    if (nnz > QN_NNZ_MAX) return false;
+    sp->nnz = nnz;
+    /* program */
+    std::vector<uint16_t> pg;
+    auto P = [&](int r, int c) { return (uint16_t)sp->pos[r * LD + c]; };
+    for (int c = 0; c < n; c++) {
+        pg.push_back(P(c, c));
+        std::vector<int> ucols, rows;
+        for (int j = c + 1; j < n; j++) if (pat[c * LD + j]) ucols.push_back(j);
+        for (int r = c + 1; r < n; r++) if (pat[r * LD + c]) rows.push_back(r);
+        pg.push_back((uint16_t)ucols.size());
+        for (int j : ucols) pg.push_back(P(c, j));
+        pg.push_back((uint16_t)rows.size());
+        for (int r : rows) { pg.push_back(P(r, c)); for (int j : ucols) pg.push_back(P(r, j)); }
+    }
+    sp->solve_l_at = (int32_t)pg.size();
+    for (int i = 0; i < n; i++) {
+        std::vector<int> q;
+        for (int c = 0; c < i; c++) if (pat[i * LD + c]) q.push_back(c);
+        pg.push_back((uint16_t)q.size());
+        for (int c : q) { pg.push_back((uint16_t)c); pg.push_back(P(i, c)); }
+    }
+    sp->solve_u_at = (int32_t)pg.size();
+    for (int i = n - 1; i >= 0; i--) {
+        std::vector<int> q;
+        for (int c = i + 1; c < n; c++) if (pat[i * LD + c]) q.push_back(c);
+        pg.push_back(P(i, i));
+        pg.push_back((uint16_t)q.size());
+        for (int c : q) { pg.push_back((uint16_t)c); pg.push_back(P(i, c)); }
+    }
+    if (pg.size() > QN_PROG_MAX) return false;
+    sp->prog_len = (int32_t)pg.size();
+    memcpy(sp->prog, pg.data(), pg.size() * sizeof(uint16_t));
+    /* self-check: the static program against the pivoted dense solve at grid points across the band */
+    const int probes[7] = { 0, nf / 6, nf / 3, nf / 2, (2 * nf) / 3, (5 * nf) / 6, nf - 1 };
+    for (int t = 0; t < 7; t++) {
+        const int k = probes[t] < 0 ? 0 : probes[t] >= nf ? nf - 1 : probes[t];
+        std::vector<cvec> X;
+        if (!host_dense(hp, f[k], yb + (size_t)k * 4, (size_t)nf * 4, NULL, &X)) return false;
+        cvec V((size_t)nnz, make_double2(0.0, 0.0));
+        StaticSink S = { V.data(), sp->pos, sp->rowmap };
+        nodal_stamp_all(hp, hp->nom, 6.283185307179586476925286766559 * f[k], yb + (size_t)k * 4, (size_t)nf * 4, S);
+        static_factor(sp->prog, n, V.data());
+        for (int j = 0; j < hp->np; j++) {
+            cvec x(n);
+            for (int i = 0; i < n; i++) x[i] = make_double2(i == sp->rowmap[hp->port_node[j] - 1] ? 1.0 / hp->port_z0[j] : 0.0, 0.0);
+            static_solve(sp->prog, sp->solve_l_at, sp->solve_u_at, n, V.data(), x.data());
+            for (int p = 0; p < hp->np; p++) {
+                const double2 a = x[hp->port_node[p] - 1], b = X[j][hp->port_node[p] - 1];
+                const double err = hypot(a.x - b.x, a.y - b.y), ref = hypot(b.x, b.y);
+                if (!(err <= 1e-10 * ref + 1e-13 * hp->port_z0[p])) return false;      /* NaN fails too */
+            }
+        }
+    }
+    return true;
+}
+
 static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
                      const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s_host)
 {
@@ -366,6 +602,16 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         }
         ib++;
     }
+    /* static (symbolic) plan unless forced off or its self-check fails */
+    std::vector<NodalStatic> spv(1);
+    const char *force = getenv("QO100NET_NODAL");
+    bool use_static = !(force && !strcmp(force, "dense"));
+    if (use_static) {
+        cvec ybs = yb;
+        if (ybs.empty()) ybs.assign(4, make_double2(0.0, 0.0));
+        use_static = build_static(hp, f, nf, ybs.data(), &spv[0]);
+    }
+    if (force && !strcmp(force, "static") && !use_static) { qo_set_error("QO100NET_NODAL=static: the static plan failed its self-check for this network"); return QO_ERR_UNSUPPORTED; }
     const int ncnt = 2 + nspec + hp->hist_bins;
     const unsigned long long N = cfg->n_samples;
     if (N == 0) { if (res) { res->n_pass = res->n_total = 0; } return QO_OK; }
@@ -373,6 +619,7 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     DevCtx *dc = &ctx->d[0];                 /* device 0 of the ctx: the nodal path is not sharded yet */
     CU(cudaSetDevice(dc->device));
     NodalProg *dprog = NULL;
+    NodalStatic *dsp = NULL;
     double *dfr = NULL;
     unsigned char *dmask = NULL;
     double2 *dy = NULL, *ds = NULL;
@@ -382,6 +629,8 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
 #define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); rc = e_ == cudaErrorMemoryAllocation ? QO_ERR_NOMEM : QO_ERR_CUDA; goto out; } } while (0)
     {
         CUN(cudaMalloc(&dprog, sizeof(NodalProg)));
+        CUN(cudaMalloc(&dsp, sizeof(NodalStatic)));
+        CUN(cudaMemcpyAsync(dsp, &spv[0], sizeof(NodalStatic), cudaMemcpyHostToDevice, dc->stream));
         CUN(cudaMalloc(&dfr, (size_t)nf * sizeof(double)));
         CUN(cudaMalloc(&dmask, (size_t)nf));
         CUN(cudaMalloc(&dy, (yb.size() ? yb.size() : 1) * sizeof(double2)));
@@ -399,11 +648,18 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         const unsigned long long cap = (unsigned long long)dc->sm_count * 16;
         const int grid = (int)(units < cap ? units : cap);
         cudaEventRecord(dc->ev0, dc->stream);
-#define QN_LAUNCH(LDV) qo_nodal_kernel<LDV><<<grid, QN_TPB, 0, dc->stream>>>(dprog, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds)
-        if (n_unk <= 8) QN_LAUNCH(8);
-        else if (n_unk <= 16) QN_LAUNCH(16);
-        else if (n_unk <= 24) QN_LAUNCH(24);
-        else QN_LAUNCH(32);
+#define QN_LAUNCH(LDV, ST, NZ) qo_nodal_kernel<LDV, ST, NZ><<<grid, QN_TPB, 0, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds)
+        g_last_kernel = use_static ? "qo_nodal_kernel<static>" : "qo_nodal_kernel<dense>";
+        if (use_static) {
+            const int nnz = spv[0].nnz;
+            if (nnz <= 64) QN_LAUNCH(32, true, 64);
+            else if (nnz <= 128) QN_LAUNCH(32, true, 128);
+            else if (nnz <= 256) QN_LAUNCH(32, true, 256);
+            else QN_LAUNCH(32, true, QN_NNZ_MAX);
+        } else if (n_unk <= 8) QN_LAUNCH(8, false, 1);
+        else if (n_unk <= 16) QN_LAUNCH(16, false, 1);
+        else if (n_unk <= 24) QN_LAUNCH(24, false, 1);
+        else QN_LAUNCH(32, false, 1);
 #undef QN_LAUNCH
         cudaEventRecord(dc->ev1, dc->stream);
         CUN(cudaGetLastError());
@@ -420,12 +676,12 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
             if (res->hist) for (int b = 0; b < hp->hist_bins; b++) res->hist[b] = h[2 + nspec + b];
             res->seconds = ms * 1e-3;
             res->evals_per_s = ms > 0 ? (double)N * nf / (ms * 1e-3) : 0.0;
-            res->flops_per_eval = (8.0 / 3.0) * n_unk * n_unk * n_unk + 8.0 * nd->np * n_unk * n_unk;   /* LU + substitutions, real flops */
+            res->flops_per_eval = (8.0 / 3.0) * n_unk * n_unk * n_unk + 8.0 * nd->np * n_unk * n_unk;   /* DENSE LU + substitutions, real flops */
         }
     }
 out:
 #undef CUN
-    cudaFree(dprog); cudaFree(dfr); cudaFree(dmask); cudaFree(dy); cudaFree(dcnt); cudaFree(ds);
+    cudaFree(dprog); cudaFree(dsp); cudaFree(dfr); cudaFree(dmask); cudaFree(dy); cudaFree(dcnt); cudaFree(ds);
     return rc;
 }
 

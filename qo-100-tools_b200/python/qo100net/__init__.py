@@ -97,7 +97,7 @@ EXPORTS = [
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
     "qo_nodal_num_nodes", "qo_nodal_num_ports", "qo_nodal_num_branches", "qo_nodal_get_branches", "qo_nodal_get_ports",
-    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run",
+    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run", "qo_nodal_last_kernel",
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
@@ -169,6 +169,7 @@ def lib():
         "qo_nodal_get_ports": (C.c_int, [vp, ip, dp, C.c_int]),
         "qo_nodal_free": (None, [vp]),
         "qo_nodal_sweep": (C.c_int, [vp, vp, dp, C.c_int, vp]),
+        "qo_nodal_last_kernel": (C.c_char_p, []),
         "qo_nodal_mc_run": (C.c_int, [vp, vp, dp, C.c_int, C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), C.POINTER(McResult), vp]),
         "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
         "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
@@ -701,6 +702,10 @@ class Context:
         if full is not None:
             out["s"] = full
         return out
+
+    @staticmethod
+    def nodal_last_kernel():
+        return lib().qo_nodal_last_kernel().decode()
 
     def device_perturb_factors(self, seed, sample_offset, n_samples, n_var, dist, tol):
         out = np.empty((n_samples, n_var))

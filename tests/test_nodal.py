@@ -185,13 +185,21 @@ def build_nodal(Q, golden_s2p):
 
 
 @pytest.mark.gpu
-def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s2p):
+def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s2p, monkeypatch):
     """The CUDA nodal kernel through the C-ABI against the reference's 5-port dataset (all 13 entries x 5000
     points) and against the oracle."""
     nd, br, nn, ports = build_nodal(Q, golden_s2p)
     f = pa_bias["frequency"]
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
     S = ctx.nodal_sweep(nd, f)
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<static>"          # symbolic plan accepted for this network
     check_vs_dat(S, pa_bias)
+    monkeypatch.setenv("QO100NET_NODAL", "dense")                          # per-point pivoting gives the same answer
+    Sd = ctx.nodal_sweep(nd, f)
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<dense>"
+    check_vs_dat(Sd, pa_bias)
+    assert np.max(np.abs(S - Sd)) < 1e-9
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
     register_inductor(R, golden_s2p)
     O = R.nodal_sweep(br, nn, ports, f)
     # the bias network is stiff (100 uF next to 1.2 pF): two correct LU orderings differ by ~1e-10 absolute
@@ -207,7 +215,7 @@ def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s
 
 
 @pytest.mark.gpu
-def test_gpu_nodal_monte_carlo_equals_oracle(Q, R, ctx, pa_bias, golden_s2p):
+def test_gpu_nodal_monte_carlo_equals_oracle(Q, R, ctx, pa_bias, golden_s2p, monkeypatch):
     """Yield over the bias network's R/C tolerances: specs on |S21| (pass band) and |S31| (bias-port isolation);
     integer counters, histogram and FULL_S planes equal the oracle's."""
     nd, br, nn, ports = build_nodal(Q, golden_s2p)
@@ -224,6 +232,10 @@ def test_gpu_nodal_monte_carlo_equals_oracle(Q, R, ctx, pa_bias, golden_s2p):
     hist = dict(hist_bins=20, hist_spec=0, hist_lo=float(s21[band].min()) - 0.3, hist_hi=float(s21[band].min()) + 0.3)
     n = 400
     got = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, **hist)
+    monkeypatch.setenv("QO100NET_NODAL", "dense")
+    dense = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, **hist)
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
+    assert dense["n_pass"] == got["n_pass"] and np.array_equal(dense["hist"], got["hist"])
     from oracle import refbind
     ref = R.nodal_mc_run(br, nn, ports, f, specs, refbind.mc_cfg(21, n, tols, **hist), nthreads=8)
     assert got["n_total"] == n and got["n_pass"] == ref["n_pass"] and 0 < got["n_pass"] < n

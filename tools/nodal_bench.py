@@ -43,6 +43,7 @@ def main():
     for rep in range(3):
         r = ctx.nodal_mc_run(nd, f, specs, 5, n, tols, sample_offset=rep * n, **hist)
         best = r if best is None or r["seconds"] < best["seconds"] else best
+    kernel = ctx.nodal_last_kernel()
     peak = ctx.measure_dfma_peak()
     ncpu = 400
     nthr = R.max_threads()
@@ -51,7 +52,7 @@ def main():
     cpu_s = time.perf_counter() - t0
     chk = ctx.nodal_mc_run(nd, f, specs, 5, ncpu, tols, **hist)
     out = {"workload": "pa-bias 5-port network, 23 unknowns, %d samples x %d points, reduce-only" % (n, args.nf),
-           "gpu_kernel_seconds": best["seconds"], "gpu_points_per_s": n * args.nf / best["seconds"],
+           "kernel": kernel, "gpu_kernel_seconds": best["seconds"], "gpu_points_per_s": n * args.nf / best["seconds"],
            "real_flops_per_point_lu_plus_solves": best["flops_per_eval"],
            "gpu_tflops": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12, "dfma_peak_tflops": peak,
            "frac_of_dfma_peak": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12 / peak,

@@ -240,9 +240,9 @@ int qo_nodal_sweep(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, qo_
 int qo_nodal_mc_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
                     const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
 
-/* which factorisation the calling thread's last nodal call used: "qo_nodal_kernel<static>" (symbolic plan: fixed
- * pivot order and fill pattern, verified on the host against the pivoted solve) or "qo_nodal_kernel<dense>"
- * (per-point partial pivoting; QO100NET_NODAL=dense forces it) */
+/* which factorisation the calling thread's last nodal call used: "qo_nodal_kernel<static,smem>" /
+ * "qo_nodal_kernel<static,local>" (symbolic plan: fixed pivot order and fill pattern, verified on the host against
+ * the pivoted solve; values in a thread-private array or, with QO100NET_NODAL_VALUES=smem, in shared memory) or "qo_nodal_kernel<dense>" (per-point partial pivoting; QO100NET_NODAL=dense forces it) */
 const char *qo_nodal_last_kernel(void);
 
 /* The same job kept resident in HBM (tables, grid, specs uploaded once):

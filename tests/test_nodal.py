@@ -192,8 +192,12 @@ def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s
     f = pa_bias["frequency"]
     monkeypatch.delenv("QO100NET_NODAL", raising=False)
     S = ctx.nodal_sweep(nd, f)
-    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<static>"          # symbolic plan accepted for this network
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<static,local>"    # symbolic plan accepted
     check_vs_dat(S, pa_bias)
+    monkeypatch.setenv("QO100NET_NODAL_VALUES", "smem")                    # same plan, values in shared memory
+    Sl = ctx.nodal_sweep(nd, f)
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<static,smem>" and np.array_equal(Sl, S)
+    monkeypatch.delenv("QO100NET_NODAL_VALUES", raising=False)
     monkeypatch.setenv("QO100NET_NODAL", "dense")                          # per-point pivoting gives the same answer
     Sd = ctx.nodal_sweep(nd, f)
     assert ctx.nodal_last_kernel() == "qo_nodal_kernel<dense>"

@@ -72,7 +72,7 @@ __device__ __forceinline__ double2 c_fms(double2 a, double2 l, double2 u)
 #define QN_PROG_MAX 6144       /* uint16 words of program */
 #define QN_NNZ_MAX 512
 struct NodalStatic {
-    int32_t n, nnz, prog_len, pad;
+    int32_t n, nnz, prog_len, stamp_at, zero_at, n_zero;   /* stamp stream / fill-only value indices inside prog[] */
     int32_t solve_at[QO_NODAL_MAX_PORTS];               /* start of each port's pruned substitution program */
     int16_t pos[QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK];   /* (pivot-order row, permuted column) -> value index, -1 = structural zero */
     uint8_t rowmap[QO_NODAL_MAX_UNK];                   /* original row (equation) -> pivot-order row */
@@ -80,21 +80,24 @@ struct NodalStatic {
     uint16_t prog[QN_PROG_MAX];
 };
 
-/* where a stamp lands: dense matrix with leading dimension LD ... */
+/* where a stamp lands: a dense matrix with leading dimension LD (dense kernel, host analysis) ... */
 template <int LD> struct DenseSink {
     double2 *A;
     __host__ __device__ __forceinline__ void add(int r, int c, double2 v) { A[r * LD + c].x += v.x; A[r * LD + c].y += v.y; }
 };
-/* ... or the compact value array of the static plan (rows already in pivot order) */
-template <int VS> struct StaticSink {          /* VS = stride between consecutive values (1: private array,
-                                                   QN_TPB: shared memory, one column per thread) */
+/* ... or the compact value array of the static plan.  The order of the add() calls of nodal_stamp_all depends only on the netlist, so the host records, once per
+ * job, the value index every call lands on (bit 15: first touch -> store instead of add); the kernel replays
+ * that stream and never looks at (row, column) again: no index tables, no zero-fill of stamped values. */
+template <int VS> struct ReplaySink {
     double2 *V;
-    const int16_t *pos;
-    const uint8_t *rowmap, *colmap;
-    __host__ __device__ __forceinline__ void add(int r, int c, double2 v)
+    const uint16_t *st;
+    int k;
+    __host__ __device__ __forceinline__ void add(int, int, double2 v)
     {
-        const int q = pos[rowmap[r] * QO_NODAL_MAX_UNK + colmap[c]] * VS;
-        V[q].x += v.x; V[q].y += v.y;
+        const unsigned int wd = st[k++];
+        const int q = (int)(wd & 0x7fffu) * VS;
+        if (wd >> 15) V[q] = v;
+        else { V[q].x += v.x; V[q].y += v.y; }
     }
 };
 
@@ -220,11 +223,9 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restric
     constexpr bool STATIC = MODE != 0;
     constexpr int VS = MODE == 2 ? QN_TPB : 1;
     extern __shared__ double2 s_vals[];              /* MODE 2: [nnz][QN_TPB] */
-    __shared__ int16_t s_pos[STATIC ? QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK : 1];
     __shared__ uint8_t s_rowmap[QO_NODAL_MAX_UNK], s_colmap[QO_NODAL_MAX_UNK];
     __shared__ uint16_t s_prog[STATIC ? QN_PROG_MAX : 1];
     if (STATIC) {
-        for (int i = threadIdx.x; i < QO_NODAL_MAX_UNK * QO_NODAL_MAX_UNK; i += QN_TPB) s_pos[i] = splan->pos[i];
         for (int i = threadIdx.x; i < QO_NODAL_MAX_UNK; i += QN_TPB) { s_rowmap[i] = splan->rowmap[i]; s_colmap[i] = splan->colmap[i]; }
         for (int i = threadIdx.x; i < splan->prog_len; i += QN_TPB) s_prog[i] = splan->prog[i];
     }
@@ -268,9 +269,8 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restric
             unsigned int lmask[STATIC ? 1 : LD], umask[STATIC ? 1 : LD];
             bool singular = false;
             if (STATIC) {
-                const int nnz = splan->nnz;
-                for (int i = 0; i < nnz; i++) V[i * VS] = make_double2(0.0, 0.0);
-                StaticSink<VS> S = { V, s_pos, s_rowmap, s_colmap };
+                for (int i = 0; i < splan->n_zero; i++) V[s_prog[splan->zero_at + i] * VS] = make_double2(0.0, 0.0);   /* fill-only */
+                ReplaySink<VS> S = { V, s_prog + splan->stamp_at, 0 };
                 nodal_stamp_all(prog, s_p, w, yk, (size_t)nf * 4, S);
                 static_factor<VS>(s_prog, n, V);
             } else {
@@ -583,6 +583,24 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
             for (int c : q) { pg.push_back((uint16_t)c); pg.push_back(P(i, c)); }
         }
     }
+    /* stamp stream: value index of every add() call in call order, first touches flagged; then the fill-only indices */
+    {
+        struct RecordSink {
+            std::vector<uint16_t> *out; const NodalStatic *sp; std::vector<char> *touched;
+            void add(int r, int c, double2) {
+                const int q = sp->pos[sp->rowmap[r] * QO_NODAL_MAX_UNK + sp->colmap[c]];
+                out->push_back((uint16_t)(q | ((*touched)[q] ? 0 : 0x8000)));
+                (*touched)[q] = 1;
+            }
+        };
+        std::vector<char> touched((size_t)nnz, 0);
+        sp->stamp_at = (int32_t)pg.size();
+        RecordSink RS = { &pg, sp, &touched };
+        nodal_stamp_all(hp, hp->nom, 1.0, yb, (size_t)nf * 4, RS);
+        sp->zero_at = (int32_t)pg.size();
+        for (int q = 0; q < nnz; q++) if (!touched[q]) pg.push_back((uint16_t)q);
+        sp->n_zero = (int32_t)pg.size() - sp->zero_at;
+    }
     if (pg.size() > QN_PROG_MAX) return false;
     sp->prog_len = (int32_t)pg.size();
     memcpy(sp->prog, pg.data(), pg.size() * sizeof(uint16_t));
@@ -592,8 +610,9 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
         const int k = probes[t] < 0 ? 0 : probes[t] >= nf ? nf - 1 : probes[t];
         std::vector<cvec> X;
         if (!host_dense(hp, f[k], yb + (size_t)k * 4, (size_t)nf * 4, NULL, &X)) return false;
-        cvec V((size_t)nnz, make_double2(0.0, 0.0));
-        StaticSink<1> S = { V.data(), sp->pos, sp->rowmap, sp->colmap };
+        cvec V((size_t)nnz, make_double2(nan(""), nan("")));            /* poisoned: the streams must initialise every value */
+        for (int i = 0; i < sp->n_zero; i++) V[sp->prog[sp->zero_at + i]] = make_double2(0.0, 0.0);
+        ReplaySink<1> S = { V.data(), sp->prog + sp->stamp_at, 0 };
         nodal_stamp_all(hp, hp->nom, 6.283185307179586476925286766559 * f[k], yb + (size_t)k * 4, (size_t)nf * 4, S);
         static_factor<1>(sp->prog, n, V.data());
         for (int j = 0; j < np; j++) {
@@ -725,7 +744,21 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         int chunk_len = nf, nchunks = 1;
         if (full) { chunk_len = QN_TPB; nchunks = (nf + chunk_len - 1) / chunk_len; }
         const unsigned long long units = N * (unsigned long long)nchunks;
-        const unsigned long long cap = (unsigned long long)dc->sm_count * 16;
+        /* persistent grid = exactly the resident blocks (a larger grid runs in 1.6 waves: 4.0e8 instead of 4.4e8
+         * points/s on the reference network); latency hiding matters more here than the private arrays' L2 footprint */
+        int bps = 0;
+        { const char *e = getenv("QO100NET_NODAL_BPS"); if (e && atoi(e) > 0) bps = atoi(e); }
+        if (bps == 0) {
+            if (use_static) {
+                const int nnz = spv[0].nnz;
+                if (nnz <= 64) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, qo_nodal_kernel<32, 1, 64>, QN_TPB, 0);
+                else if (nnz <= 128) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, qo_nodal_kernel<32, 1, 128>, QN_TPB, 0);
+                else if (nnz <= 256) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, qo_nodal_kernel<32, 1, 256>, QN_TPB, 0);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, qo_nodal_kernel<32, 1, QN_NNZ_MAX>, QN_TPB, 0);
+            }
+            if (bps <= 0) bps = 8;
+        }
+        const unsigned long long cap = (unsigned long long)dc->sm_count * (unsigned long long)bps;
         const int grid = (int)(units < cap ? units : cap);
         cudaEventRecord(dc->ev0, dc->stream);
 #define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds)

@@ -79,6 +79,13 @@ static int devctx_init(DevCtx *d, int device)
     d->sm_count = prop.multiProcessorCount;
     CU(cudaEventCreate(&d->ev0));
     CU(cudaEventCreate(&d->ev1));
+    /* plans and sweeps allocate their (small) device tables stream-ordered; keep up to 256 MB of freed blocks in the
+     * device's pool so that a one-shot call does not pay cudaMalloc/cudaFree (~1 ms per nominal sweep before) */
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long thr = 256ull << 20;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else cudaGetLastError();
     return QO_OK;
 }
 
@@ -333,10 +340,11 @@ extern "C" void qo_plan_destroy(qo_plan *p)
     for (int g = 0; g < p->ctx->ndev; g++) {
         cudaSetDevice(p->ctx->d[g].device);
         DevPlan *d = &p->d[g];
-        cudaFree(d->prog); cudaFree(d->w2); cudaFree(d->wi2); cudaFree(d->wsq2); cudaFree(d->m2);
-        for (int t = 0; t < 4; t++) cudaFree(d->cpl_tab[t]);
-        cudaFree(d->fgrid); cudaFree(d->mask); cudaFree(d->counters); cudaFree(d->ticket);
-        cudaFree(d->sblk); cudaFree(d->sdet);
+        /* stream-ordered frees: back into the device's pool without a device-wide synchronisation */
+        cudaStream_t st = p->ctx->d[g].stream;
+        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
+                         d->fgrid, d->mask, d->counters, d->ticket, d->sblk, d->sdet };
+        for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
     }
     delete p;
 }
@@ -458,13 +466,13 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); qo_plan_destroy(p); return QO_ERR_CUDA; } } while (0)
         CUP(cudaSetDevice(ctx->d[g].device));
         cudaStream_t st = ctx->d[g].stream;
-        CUP(cudaMalloc(&d->prog, sizeof(DevProg)));
+        CUP(cudaMallocAsync((void **)&d->prog, sizeof(DevProg), st));
         CUP(cudaMemcpyAsync(d->prog, &p->hp, sizeof(DevProg), cudaMemcpyHostToDevice, st));
         if (!p->generic) {
             size_t esz = p->precision == 32 ? sizeof(float) : sizeof(double);
-            CUP(cudaMalloc(&d->w2, 2 * (size_t)np * esz));
-            CUP(cudaMalloc(&d->wi2, 2 * (size_t)np * esz));
-            CUP(cudaMalloc(&d->m2, 2 * (size_t)np));
+            CUP(cudaMallocAsync((void **)&d->w2, 2 * (size_t)np * esz, st));
+            CUP(cudaMallocAsync((void **)&d->wi2, 2 * (size_t)np * esz, st));
+            CUP(cudaMallocAsync((void **)&d->m2, 2 * (size_t)np, st));
             if (p->precision == 32) {
                 CUP(cudaMemcpyAsync(d->w2, wf.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
                 CUP(cudaMemcpyAsync(d->wi2, wif.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
@@ -474,30 +482,30 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
             }
             CUP(cudaMemcpyAsync(d->m2, m.data(), 2 * (size_t)np, cudaMemcpyHostToDevice, st));
             if (!sblk.empty()) {
-                CUP(cudaMalloc(&d->sblk, sblk.size() * sizeof(double2)));
+                CUP(cudaMallocAsync((void **)&d->sblk, sblk.size() * sizeof(double2), st));
                 CUP(cudaMemcpyAsync(d->sblk, sblk.data(), sblk.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
                 if (nonrecip) {
-                    CUP(cudaMalloc(&d->sdet, sdet.size() * sizeof(double2)));
+                    CUP(cudaMallocAsync((void **)&d->sdet, sdet.size() * sizeof(double2), st));
                     CUP(cudaMemcpyAsync(d->sdet, sdet.data(), sdet.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
                 }
             }
             if (p->ladder) {
-                CUP(cudaMalloc(&d->wsq2, 2 * (size_t)np * sizeof(double)));
+                CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * sizeof(double), st));
                 CUP(cudaMemcpyAsync(d->wsq2, wsq.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
-                CUP(cudaMalloc(&d->ticket, sizeof(unsigned long long)));
+                CUP(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), st));
                 if (p->cpl_fast)
                     for (int t = 0; t < 4; t++) {
-                        CUP(cudaMalloc(&d->cpl_tab[t], 2 * (size_t)np * sizeof(double)));
+                        CUP(cudaMallocAsync((void **)&d->cpl_tab[t], 2 * (size_t)np * sizeof(double), st));
                         CUP(cudaMemcpyAsync(d->cpl_tab[t], ctab[t].data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
                     }
             }
         } else {
-            CUP(cudaMalloc(&d->fgrid, (size_t)nf * sizeof(double)));
-            CUP(cudaMalloc(&d->mask, (size_t)nf));
+            CUP(cudaMallocAsync((void **)&d->fgrid, (size_t)nf * sizeof(double), st));
+            CUP(cudaMallocAsync((void **)&d->mask, (size_t)nf, st));
             CUP(cudaMemcpyAsync(d->fgrid, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
             CUP(cudaMemcpyAsync(d->mask, p->maskv.data(), (size_t)nf, cudaMemcpyHostToDevice, st));
         }
-        CUP(cudaMalloc(&d->counters, (size_t)p->ncnt * sizeof(unsigned long long)));
+        CUP(cudaMallocAsync((void **)&d->counters, (size_t)p->ncnt * sizeof(unsigned long long), st));
         CUP(cudaMemsetAsync(d->counters, 0, (size_t)p->ncnt * sizeof(unsigned long long), st));
         CUP(cudaStreamSynchronize(st));   /* the host staging vectors die at return */
     }
@@ -787,11 +795,12 @@ extern "C" int qo_sweep(qo_ctx *ctx, const qo_net *net, const double *f, int nf,
     double *dgd = NULL, *df3 = NULL;
     cudaSetDevice(dc->device);
     do {
-        if (cudaMalloc(&buf, 4 * (size_t)nft * sizeof(double2)) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
+        if (cudaMallocAsync((void **)&buf, 4 * (size_t)nft * sizeof(double2), dc->stream) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
         rc = plan_launch_dev(p, 0, 0, 1, p->d[0].counters, (qo_c64 *)buf, 1, 0);
         if (rc) break;
         if (gd) {
-            if (cudaMalloc(&dgd, (size_t)nf * sizeof(double)) != cudaSuccess || cudaMalloc(&df3, (size_t)nft * sizeof(double)) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
+            if (cudaMallocAsync((void **)&dgd, (size_t)nf * sizeof(double), dc->stream) != cudaSuccess ||
+                cudaMallocAsync((void **)&df3, (size_t)nft * sizeof(double), dc->stream) != cudaSuccess) { rc = QO_ERR_NOMEM; break; }
             cudaMemcpyAsync(df3, fg, (size_t)nft * sizeof(double), cudaMemcpyHostToDevice, dc->stream);
             qo_gd_kernel<<<(nf + 127) / 128, 128, 0, dc->stream>>>(buf + (size_t)nft, df3, nf, dgd);
             p->launches++;
@@ -805,7 +814,9 @@ extern "C" int qo_sweep(qo_ctx *ctx, const qo_net *net, const double *f, int nf,
         e = cudaGetLastError();
         if (e != cudaSuccess) { qo_set_error("sweep copy failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; }
     } while (0);
-    cudaFree(buf); cudaFree(dgd); cudaFree(df3);
+    if (buf) cudaFreeAsync(buf, dc->stream);
+    if (dgd) cudaFreeAsync(dgd, dc->stream);
+    if (df3) cudaFreeAsync(df3, dc->stream);
     qo_plan_destroy(p);
     return rc;
 }

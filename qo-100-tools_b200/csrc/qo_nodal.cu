@@ -727,14 +727,14 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     const size_t s_elems = full ? (size_t)N * nf * nd->np * nd->np : 0;
 #define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); rc = e_ == cudaErrorMemoryAllocation ? QO_ERR_NOMEM : QO_ERR_CUDA; goto out; } } while (0)
     {
-        CUN(cudaMalloc(&dprog, sizeof(NodalProg)));
-        CUN(cudaMalloc(&dsp, sizeof(NodalStatic)));
+        CUN(cudaMallocAsync((void **)&dprog, sizeof(NodalProg), dc->stream));
+        CUN(cudaMallocAsync((void **)&dsp, sizeof(NodalStatic), dc->stream));
         CUN(cudaMemcpyAsync(dsp, &spv[0], sizeof(NodalStatic), cudaMemcpyHostToDevice, dc->stream));
-        CUN(cudaMalloc(&dfr, (size_t)nf * sizeof(double)));
-        CUN(cudaMalloc(&dmask, (size_t)nf));
-        CUN(cudaMalloc(&dy, (yb.size() ? yb.size() : 1) * sizeof(double2)));
-        CUN(cudaMalloc(&dcnt, (size_t)ncnt * sizeof(unsigned long long)));
-        if (full) CUN(cudaMalloc(&ds, s_elems * sizeof(double2)));
+        CUN(cudaMallocAsync((void **)&dfr, (size_t)nf * sizeof(double), dc->stream));
+        CUN(cudaMallocAsync((void **)&dmask, (size_t)nf, dc->stream));
+        CUN(cudaMallocAsync((void **)&dy, (yb.size() ? yb.size() : 1) * sizeof(double2), dc->stream));
+        CUN(cudaMallocAsync((void **)&dcnt, (size_t)ncnt * sizeof(unsigned long long), dc->stream));
+        if (full) CUN(cudaMallocAsync((void **)&ds, s_elems * sizeof(double2), dc->stream));
         CUN(cudaMemcpyAsync(dprog, hp, sizeof(NodalProg), cudaMemcpyHostToDevice, dc->stream));
         CUN(cudaMemcpyAsync(dfr, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, dc->stream));
         CUN(cudaMemcpyAsync(dmask, mask.data(), (size_t)nf, cudaMemcpyHostToDevice, dc->stream));
@@ -803,7 +803,10 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     }
 out:
 #undef CUN
-    cudaFree(dprog); cudaFree(dsp); cudaFree(dfr); cudaFree(dmask); cudaFree(dy); cudaFree(dcnt); cudaFree(ds);
+    {
+        void *ptrs[] = { dprog, dsp, dfr, dmask, dy, dcnt, ds };
+        for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], dc->stream);
+    }
     return rc;
 }
 

@@ -47,6 +47,11 @@ def sass_fp64_per_eval(plan_kernel, wl_name):
     tools/sass_count.py -> profiles/sass_counts.json); None for other kernels."""
     if plan_kernel != "qo_mc_ladder_kernel":
         return None
+    if wl_name.startswith("cfg5"):
+        # the coupler block holds two alternative code paths (table rotation / sincos), so the static census
+        # over-counts; this is the executed count from ncu (profiles/r01e_ladder_dynamic_fp64_counts.txt:
+        # dfma 117.0 + dmul 93.0 + dadd 11.0 per eval, + ~2 DSETP)
+        return 223.0
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
         return d["n11_first0_cpl1" if wl_name.startswith("cfg5") else "n11_first0_cpl0"]["fp64_pipe_instr_per_eval"]

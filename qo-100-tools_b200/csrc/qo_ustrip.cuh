@@ -327,7 +327,12 @@ __device__ __forceinline__ void qo_generic_s(const DevProg *__restrict__ prog, c
 __device__ __forceinline__ unsigned long long d2key(double v) { return (unsigned long long)__double_as_longlong(v); }
 
 /* tile = (sample tile, frequency chunk).  REDUCE mode requires n_fchunks == 1. */
-__global__ void __launch_bounds__(QO_G_TPB)
+/* four 128-thread blocks per SM = 128 registers: 2.84e8 evals/s on BASELINE config 3 against 2.43e8 at 168
+ * registers / 3 blocks and 2.56e8 at 96 registers / 5 blocks (round-1 sweep, profiles/r01g_generic_cfg3_*) */
+#ifndef QO_G_MINB
+#define QO_G_MINB 4
+#endif
+__global__ void __launch_bounds__(QO_G_TPB, QO_G_MINB)
 qo_mc_generic_kernel(const DevProg *__restrict__ prog, const double *__restrict__ fgrid, const unsigned char *__restrict__ mask,
                      int nf, int f_chunk, int n_fchunks, int sb, unsigned long long sample_offset, unsigned long long nsamples,
                      unsigned long long *__restrict__ counters, QoPlanes planes, int full_s)

@@ -300,7 +300,7 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
     return QO_OK;
 }
 
-/* The straight-line ladder kernel covers: reduce-only FP64 jobs whose specs are all on |S21|, on a
+/* The straight-line ladder kernel covers: reduce-only FP64 jobs whose specs are on |S21| and |S11|, on a
  * network that is an alternating series-inductor / shunt-capacitor ladder of 1..11 elements
  * (pcb/generic-filter), optionally behind one coupled-line block.  QO100NET_KERNEL=interp forces the
  * opcode interpreter (A/B runs, parity tests of both paths). */
@@ -308,10 +308,10 @@ static int ladder_eligible(const DevProg *hp, int mode, int precision, int gener
 {
     const char *force = getenv("QO100NET_KERNEL");
     if (force && strcmp(force, "interp") == 0) return 0;
-    if (generic || mode != QO_MODE_REDUCE_ONLY || precision != 64 || hp->need_s11 || hp->need_gd) return 0;
+    if (generic || mode != QO_MODE_REDUCE_ONLY || precision != 64 || hp->need_gd) return 0;
     if (hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) return 0;
     for (int s = 0; s < hp->nspec; s++)
-        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN) return 0;
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) return 0;
     int e0 = 0;
     *cpl = 0;
     if (hp->n_ops > 0 && hp->opcode[0] == OP_CPL) { *cpl = 1; e0 = 1; }
@@ -584,12 +584,13 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
         const int neg = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
         P.sgn[s] = neg ? 0x80000000u : 0u;
         P.thr[s] = s < hp->nspec ? (neg ? -hp->spec_thr[s] : hp->spec_thr[s]) : 0.0;
+        P.is_s11[s] = s < hp->nspec && hp->spec_kind[s] == SK_S11_MAX;
     }
     P.npairs = p->npairs; P.n_var = hp->n_var; P.n_ops = hp->n_ops; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
     P.hist_kind = hp->hist_bins > 0 ? hp->spec_kind[hp->hist_spec] : 0;
-    int rc = qo_ladder_launch(p->lad_n, p->lad_first, p->lad_cpl, p->lad_variant, dc->sm_count, &P, dc->stream, NULL);
+    int rc = qo_ladder_launch(p->lad_n, p->lad_first, p->lad_cpl, hp->need_s11 ? 2 : 1, p->lad_variant, dc->sm_count, &P, dc->stream, NULL);
     if (rc < 0) { qo_set_error("no ladder kernel instantiation for n=%d first=%d cpl=%d", p->lad_n, p->lad_first, p->lad_cpl); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("ladder kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
     return QO_OK;

@@ -17,17 +17,17 @@
 
 typedef void (*lad_fn)(const LadParams);
 
-template <int N, int FIRST, bool CPL, int PP, int TPB, int MINB> static lad_fn lad_get()
+template <int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB> static lad_fn lad_get()
 {
-    return qo_mc_ladder_kernel<N, FIRST, CPL, PP, TPB, MINB>;
+    return qo_mc_ladder_kernel<N, FIRST, CPL, NROWS, PP, TPB, MINB>;
 }
 
-template <int PP, int TPB, int MINB> static lad_fn lad_pick(int n, int first, int cpl)
+template <int NROWS, int PP, int TPB, int MINB> static lad_fn lad_pick(int n, int first, int cpl)
 {
 #define QO_LAD_ROW(NN)                                                                       \
     case NN:                                                                                 \
-        return cpl ? (first ? lad_get<NN, 1, true, PP, TPB, MINB>() : lad_get<NN, 0, true, PP, TPB, MINB>())   \
-                   : (first ? lad_get<NN, 1, false, PP, TPB, MINB>() : lad_get<NN, 0, false, PP, TPB, MINB>());
+        return cpl ? (first ? lad_get<NN, 1, true, NROWS, PP, TPB, MINB>() : lad_get<NN, 0, true, NROWS, PP, TPB, MINB>())   \
+                   : (first ? lad_get<NN, 1, false, NROWS, PP, TPB, MINB>() : lad_get<NN, 0, false, NROWS, PP, TPB, MINB>());
     switch (n) {
         QO_LAD_ROW(1) QO_LAD_ROW(2) QO_LAD_ROW(3) QO_LAD_ROW(4) QO_LAD_ROW(5) QO_LAD_ROW(6)
         QO_LAD_ROW(7) QO_LAD_ROW(8) QO_LAD_ROW(9) QO_LAD_ROW(10) QO_LAD_ROW(11)
@@ -41,11 +41,16 @@ template <int PP, int TPB, int MINB> static lad_fn lad_pick(int n, int first, in
 template <int PP, int TPB, int MINB> static lad_fn lad_pick11(int n, int first, int cpl)
 {
     if (n != 11 || first) return nullptr;
-    return cpl ? lad_get<11, 0, true, PP, TPB, MINB>() : lad_get<11, 0, false, PP, TPB, MINB>();
+    return cpl ? lad_get<11, 0, true, 1, PP, TPB, MINB>() : lad_get<11, 0, false, 1, PP, TPB, MINB>();
 }
 #endif
 
-extern "C" int qo_ladder_launch(int n, int first, int cpl, int variant, int sm_count, const LadParams *P, cudaStream_t st,
+/* kernels with the |S11| row: two points per thread (the second row vector doubles the chain state) */
+#define QO_LAD2_PP 1
+#define QO_LAD2_TPB 256
+#define QO_LAD2_MINB 2
+
+extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int variant, int sm_count, const LadParams *P, cudaStream_t st,
                                 const char **shape)
 {
     lad_fn fn = nullptr;
@@ -66,8 +71,11 @@ extern "C" int qo_ladder_launch(int n, int first, int cpl, int variant, int sm_c
     default: break;
     }
 #endif
-    if (!fn) {
-        fn = lad_pick<QO_LAD_PP, QO_LAD_TPB, QO_LAD_MINB>(n, first, cpl);
+    if (nrows == 2) {
+        fn = lad_pick<2, QO_LAD2_PP, QO_LAD2_TPB, QO_LAD2_MINB>(n, first, cpl);
+        tpb = QO_LAD2_TPB; minb = QO_LAD2_MINB; name = "s11";
+    } else if (!fn) {
+        fn = lad_pick<1, QO_LAD_PP, QO_LAD_TPB, QO_LAD_MINB>(n, first, cpl);
         tpb = QO_LAD_TPB; minb = QO_LAD_MINB; name = "default";
     }
     if (!fn) return -1;

@@ -19,6 +19,8 @@
  * Reduce-only specs on |S21| need den only, so the chain carries the ROW VECTOR
  * u = [1 Rs] . M1 ... Mk = (a, b) instead of the 2x2 product (half the FMAs):
  *   series Z: b += a Z        shunt Y: a += b Y        den = a Rl + b
+ * Jobs with |S11| specs add the second row vector v = [1 -Rs] . M1 ... Mk (NROWS = 2):
+ *   S11 = (v . [Rl 1]^T) / den
  * Series lossy inductor (R + jwL) || 1/(jwCp), with D = 1 - w^2 L Cp:
  *   Z = (R + j w (L D - R^2 Cp)) / (D^2 + w^2 (R Cp)^2)       [numerator real part is exactly R]
  * Shunt lossy capacitor R + jwLs + 1/(jwC), X = w Ls - (1/w)(1/C):
@@ -40,7 +42,10 @@
 #define QO_LAD_CPL 10                /* doubles of the coupler record that precedes the ladder records */
 #define QO_LAD_NEG_HUGE_HI 0xFFEFFFFFu   /* high word of a huge negative finite double: "no point seen yet" */
 
-template <int PTS> struct LadRow { double ar[PTS], ai[PTS], br[PTS], bi[PTS]; };
+/* NROWS = 1: the row vector u = [1 Rs] M (enough for |S21|); NROWS = 2 adds v = [1 -Rs] M, whose contraction
+ * v . [Rl 1]^T is the numerator of S11, for jobs with |S11| specs */
+template <int PTS, int NROWS> struct LadRow { double ar[NROWS][PTS], ai[NROWS][PTS], br[NROWS][PTS], bi[NROWS][PTS]; };
+#define QO_ROWS _Pragma("unroll") for (int r = 0; r < NROWS; r++)
 
 /* Broadcast read of two coefficients from the warp's record table.  The records are invariant over
  * the frequency loop, and left to itself ptxas hoists all 55 doubles of an 11-element ladder out of
@@ -81,9 +86,9 @@ template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const double (&
 }
 
 /* series lossy inductor; record = { L*Cp, (R*Cp)^2, L, R^2*Cp, R, - } */
-template <int PTS, bool FIRSTSTEP>
+template <int PTS, int NROWS, bool FIRSTSTEP>
 __device__ __forceinline__ void lad_ser_lossy_l(unsigned int cf, const double (&w)[PTS], const double (&w2)[PTS],
-                                                double rs, LadRow<PTS> &u)
+                                                double rs, LadRow<PTS, NROWS> &u)
 {
     const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16);
     const double R = lad_lds1(cf + 32);
@@ -93,19 +98,21 @@ __device__ __forceinline__ void lad_ser_lossy_l(unsigned int cf, const double (&
     QO_PTS {
         const double g = fma(c23.x, dre[p], -c23.y);
         const double zr = R * s[p], zi = (w[p] * s[p]) * g;
-        if (FIRSTSTEP) {                 /* u = [1 Rs]: b = Rs + Z */
-            u.br[p] = rs + zr; u.bi[p] = zi;
-        } else {
-            u.br[p] = fma(u.ar[p], zr, u.br[p]); u.br[p] = fma(-u.ai[p], zi, u.br[p]);
-            u.bi[p] = fma(u.ar[p], zi, u.bi[p]); u.bi[p] = fma(u.ai[p], zr, u.bi[p]);
+        QO_ROWS {
+            if (FIRSTSTEP) {             /* u = [1 +-Rs]: b = +-Rs + Z */
+                u.br[r][p] = (r ? -rs : rs) + zr; u.bi[r][p] = zi;
+            } else {
+                u.br[r][p] = fma(u.ar[r][p], zr, u.br[r][p]); u.br[r][p] = fma(-u.ai[r][p], zi, u.br[r][p]);
+                u.bi[r][p] = fma(u.ar[r][p], zi, u.bi[r][p]); u.bi[r][p] = fma(u.ai[r][p], zr, u.bi[r][p]);
+            }
         }
     }
 }
 
 /* shunt lossy capacitor; record = { 1/C, Ls, R, R^2 } */
-template <int PTS, bool FIRSTSTEP>
+template <int PTS, int NROWS, bool FIRSTSTEP>
 __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double (&w)[PTS], const double (&wi)[PTS],
-                                                  double rs, LadRow<PTS> &u)
+                                                  double rs, LadRow<PTS, NROWS> &u)
 {
     const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16);
     double x[PTS], q[PTS], s[PTS];
@@ -113,11 +120,14 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double 
     lad_rcp_batch<PTS>(q, s);
     QO_PTS {
         const double yr = c23.x * s[p], yi = -x[p] * s[p];
-        if (FIRSTSTEP) {                 /* u = [1 Rs]: a = 1 + Rs Y */
-            u.ar[p] = fma(rs, yr, 1.0); u.ai[p] = rs * yi;
-        } else {
-            u.ar[p] = fma(u.br[p], yr, u.ar[p]); u.ar[p] = fma(-u.bi[p], yi, u.ar[p]);
-            u.ai[p] = fma(u.br[p], yi, u.ai[p]); u.ai[p] = fma(u.bi[p], yr, u.ai[p]);
+        QO_ROWS {
+            if (FIRSTSTEP) {             /* u = [1 +-Rs]: a = 1 +- Rs Y */
+                const double rr = r ? -rs : rs;
+                u.ar[r][p] = fma(rr, yr, 1.0); u.ai[r][p] = rr * yi;
+            } else {
+                u.ar[r][p] = fma(u.br[r][p], yr, u.ar[r][p]); u.ar[r][p] = fma(-u.bi[r][p], yi, u.ar[r][p]);
+                u.ai[r][p] = fma(u.br[r][p], yi, u.ai[r][p]); u.ai[r][p] = fma(u.bi[r][p], yr, u.ai[r][p]);
+            }
         }
     }
 }
@@ -134,9 +144,9 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double 
  * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
  * short Taylor polynomials (|d|^10/10! < 3e-20, |d|^9/9! < 6e-18) -- 14 FP64 instructions instead of the ~30 of
  * a general sincos; otherwise sincos() is called. */
-template <int PTS, bool FAST>
+template <int PTS, int NROWS, bool FAST>
 __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
-                                              const double (&tso)[PTS], const double (&tco)[PTS], double rs, LadRow<PTS> &u,
+                                              const double (&tso)[PTS], const double (&tco)[PTS], double rs, LadRow<PTS, NROWS> &u,
                                               double (&scale)[PTS])
 {
     const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16), c45 = lad_lds2(cf + 32), c67 = lad_lds2(cf + 48), c89 = lad_lds2(cf + 64);
@@ -179,8 +189,11 @@ __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const double (&w)
         const double Cr = fma(-2.0, Vr, Tr), Ci = fma(-2.0, Vi, Ti);                                     /* k C Zt */
         const double Kr = fma(Sr, Pr, -Si * Pi), Ki = fma(Sr, Pi, Si * Pr);                              /* k / 2 */
         kap2[p] = fma(Kr, Kr, Ki * Ki);
-        u.ar[p] = fma(rz, Cr, Ar); u.ai[p] = fma(rz, Ci, Ai);                                            /* k (A + Rs C) */
-        u.br[p] = fma(rs, Ar, zt * Br); u.bi[p] = fma(rs, Ai, zt * Bi);                                  /* k (B + Rs A) */
+        QO_ROWS {
+            const double sg = r ? -1.0 : 1.0;
+            u.ar[r][p] = fma(sg * rz, Cr, Ar); u.ai[r][p] = fma(sg * rz, Ci, Ai);                        /* k (A +- Rs C) */
+            u.br[r][p] = fma(sg * rs, Ar, zt * Br); u.bi[r][p] = fma(sg * rs, Ai, zt * Bi);              /* k (B +- Rs A) */
+        }
     }
     lad_rcp_batch<PTS>(kap2, scale);
     QO_PTS scale[p] *= 0.25;                                                                             /* 1/|k|^2 */
@@ -229,6 +242,7 @@ struct LadParams {
     double rs, rl, k21, hist_lo, hist_hi;
     double thr[QO_LAD_NSPEC];                /* sign-adjusted thresholds: FAIL iff tracker > thr */
     unsigned int sgn[QO_LAD_NSPEC];          /* 0x80000000 for "max dB" specs (tracker holds -|den|^2) */
+    int is_s11[QO_LAD_NSPEC];                /* the spec's tracker holds |S11|^2 = |n11|^2 / |den|^2 (NROWS == 2 kernels) */
     int npairs, n_var, n_ops, nspec, dist, hist_spec, hist_bins, hist_kind;
     int cpl_fast, cpl_same;                  /* small-angle table path usable; nominal even and odd angles identical */
 };
@@ -242,7 +256,7 @@ struct LadParams {
  * SMSP averaging 3.06 of its 4 warps (the issue scheduler is not fair, favoured warps finished
  * their share early and the FP64 pipe drained); tickets keep all warps busy until the pool is empty.
  */
-template <int N, int FIRST, bool CPL, int PP, int TPB, int MINB>
+template <int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_constant__ LadParams P)
 {
     constexpr int PTS = 2 * PP;
@@ -298,9 +312,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 w[2 * q] = a.x; w[2 * q + 1] = a.y; wi[2 * q] = b.x; wi[2 * q + 1] = b.y; w2[2 * q] = c.x; w2[2 * q + 1] = c.y;
                 mk[2 * q] = j < npairs ? m.x : 0u; mk[2 * q + 1] = j < npairs ? m.y : 0u;
             }
-            LadRow<PTS> u;
+            LadRow<PTS, NROWS> u;
             double cscale[PTS];
-            QO_PTS { u.ar[p] = 1.0; u.ai[p] = 0.0; u.br[p] = rs; u.bi[p] = 0.0; cscale[p] = 1.0; }
+            QO_PTS { cscale[p] = 1.0; QO_ROWS { u.ar[r][p] = 1.0; u.ai[r][p] = 0.0; u.br[r][p] = r ? -rs : rs; u.bi[r][p] = 0.0; } }
             if (CPL) {
                 double tse[PTS], tce[PTS], tso[PTS], tco[PTS];
                 QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
@@ -316,9 +330,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                             tso[2 * q] = c.x; tso[2 * q + 1] = c.y; tco[2 * q] = d.x; tco[2 * q + 1] = d.y;
                         }
                     }
-                    lad_cpl_first<PTS, true>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                    lad_cpl_first<PTS, NROWS, true>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
                 } else {
-                    lad_cpl_first<PTS, false>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                    lad_cpl_first<PTS, NROWS, false>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
                 }
             }
             const unsigned int lad = coefs + (CPL ? QO_LAD_CPL : 0) * 8u;
@@ -327,20 +341,29 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 const bool series = ((e + FIRST) & 1) == 0;
                 const unsigned int cf = lad + e * QO_LAD_STRIDE * 8u;
                 if (series) {
-                    if (e == 0 && !CPL) lad_ser_lossy_l<PTS, true>(cf, w, w2, rs, u);
-                    else lad_ser_lossy_l<PTS, false>(cf, w, w2, rs, u);
+                    if (e == 0 && !CPL) lad_ser_lossy_l<PTS, NROWS, true>(cf, w, w2, rs, u);
+                    else lad_ser_lossy_l<PTS, NROWS, false>(cf, w, w2, rs, u);
                 } else {
-                    if (e == 0 && !CPL) lad_shunt_lossy_c<PTS, true>(cf, w, wi, rs, u);
-                    else lad_shunt_lossy_c<PTS, false>(cf, w, wi, rs, u);
+                    if (e == 0 && !CPL) lad_shunt_lossy_c<PTS, NROWS, true>(cf, w, wi, rs, u);
+                    else lad_shunt_lossy_c<PTS, NROWS, false>(cf, w, wi, rs, u);
                 }
             }
             const double rl = P.rl;
-            double den2[PTS];
+            double den2[PTS], s11m[PTS];
             QO_PTS {
-                const double den_r = fma(u.ar[p], rl, u.br[p]), den_i = fma(u.ai[p], rl, u.bi[p]);
+                const double den_r = fma(u.ar[0][p], rl, u.br[0][p]), den_i = fma(u.ai[0][p], rl, u.bi[0][p]);
                 den2[p] = fma(den_r, den_r, den_i * den_i);
-                if (CPL) den2[p] *= cscale[p];
             }
+            if (NROWS == 2) {
+                /* |S11|^2 = |v . [Rl 1]|^2 / |den|^2 (the coupler's common factor 1/k cancels in the ratio) */
+                double rd[PTS];
+                lad_rcp_batch<PTS>(den2, rd);
+                QO_PTS {
+                    const double n_r = fma(u.ar[1][p], rl, u.br[1][p]), n_i = fma(u.ai[1][p], rl, u.bi[1][p]);
+                    s11m[p] = fma(n_r, n_r, n_i * n_i) * rd[p];
+                }
+            }
+            if (CPL) { QO_PTS den2[p] *= cscale[p]; }
             /* Trackers.  Spec bands are contiguous in frequency, so nearly every warp-iteration sees ONE
              * mask value on all its points: a warp vote picks the fast path (a plain running max per active
              * spec, no per-point selects); iterations that straddle a band edge take the general path. */
@@ -352,7 +375,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
 #pragma unroll
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((all >> sp) & 1u) {
-                        if (P.sgn[sp]) { QO_PTS { const double c = -den2[p]; trk[sp] = c > trk[sp] ? c : trk[sp]; } }
+                        if (NROWS == 2 && P.is_s11[sp]) { QO_PTS trk[sp] = s11m[p] > trk[sp] ? s11m[p] : trk[sp]; }
+                        else if (P.sgn[sp]) { QO_PTS { const double c = -den2[p]; trk[sp] = c > trk[sp] ? c : trk[sp]; } }
                         else { QO_PTS trk[sp] = den2[p] > trk[sp] ? den2[p] : trk[sp]; }
                     }
                 }
@@ -361,9 +385,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((any >> sp) & 1u) {
                         QO_PTS {
-                            const unsigned int hi = (unsigned int)__double2hiint(den2[p]);
+                            const double val = (NROWS == 2 && P.is_s11[sp]) ? s11m[p] : den2[p];
+                            const unsigned int hi = (unsigned int)__double2hiint(val);
                             const unsigned int chi = ((mk[p] >> sp) & 1u) ? (hi ^ P.sgn[sp]) : QO_LAD_NEG_HUGE_HI;
-                            const double cand = __hiloint2double((int)chi, __double2loint(den2[p]));
+                            const double cand = __hiloint2double((int)chi, __double2loint(val));
                             trk[sp] = cand > trk[sp] ? cand : trk[sp];
                         }
                     }
@@ -394,7 +419,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
 #pragma unroll
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) if (sp == P.hist_spec) worst = fabs(trk[sp]);
                 const double k21 = P.k21;
-                const double lin = P.hist_kind == SK_DEN2_MAX ? k21 * k21 / worst : k21 * k21 * (1.0 / worst);
+                const double lin = P.hist_kind == SK_S11_MAX ? worst : P.hist_kind == SK_DEN2_MAX ? k21 * k21 / worst : k21 * k21 * (1.0 / worst);
                 const double v = 10.0 * log10(lin);
                 const double xb = (v - P.hist_lo) / (P.hist_hi - P.hist_lo) * (double)P.hist_bins;
                 long long b = (long long)floor(xb);

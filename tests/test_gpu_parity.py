@@ -209,14 +209,22 @@ def test_cfg3_microstrip_yield_equals_oracle(Q, R, W, ctx):
     assert 0.5 < gg["n_pass"] / gg["n_total"] < 0.85
 
 
-def test_s11_spec_and_histogram(Q, R, W, ctx):
-    w = W.cfg2()
-    w.specs = [(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0), (Q.SPEC_S21_MAX_DB, 13e6, 1e99, -49.0), (Q.SPEC_S21_MIN_DB, 0, 5e6, -1.2)]
-    for hs, lo, hi in ((0, -20.0, 0.0), (1, -60.0, -40.0), (2, -3.0, 0.0)):
-        w.hist = dict(hist_bins=64, hist_spec=hs, hist_lo=lo, hist_hi=hi)
-        og, gg = _mc_both(Q, R, ctx, w, 800)
-        _assert_counts_equal(og, gg)
-        assert 0 < gg["n_pass"] < 800
+def test_s11_spec_and_histogram(Q, R, W, ctx, monkeypatch):
+    """|S11| specs: the ladder kernel's second row vector (and, forced, the interpreter's 2x2 chain) against the oracle;
+    with and without the coupler block."""
+    for w in (W.cfg2(), W.cfg5()):
+        fc = 10e6 if w.name.startswith("cfg2") else 3e9
+        w.specs = [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0), (Q.SPEC_S21_MAX_DB, 1.3 * fc, 1e99, -49.0), (Q.SPEC_S21_MIN_DB, 0, 0.5 * fc, -1.3)]
+        for hs, lo, hi in ((0, -20.0, 0.0), (1, -60.0, -40.0), (2, -3.0, 0.0)):
+            w.hist = dict(hist_bins=64, hist_spec=hs, hist_lo=lo, hist_hi=hi)
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+            og, gg = _mc_both(Q, R, ctx, w, 800)
+            _assert_counts_equal(og, gg)
+            assert 0 < gg["n_pass"] < 800
+            monkeypatch.setenv("QO100NET_KERNEL", "interp")
+            ig = ctx.mc_run(w.net, w.f, w.specs, w.seed, 800, w.tols, **w.hist)
+            _assert_counts_equal(ig, gg)
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
 
 
 def test_full_s_mode_vs_oracle(Q, R, W, ctx):
@@ -364,7 +372,8 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     w = W.cfg2()
     mk = lambda specs, **kw: Q.Plan(ctx, w.net, w.f, specs, seed=1, tols=w.tols, **kw)
     p = mk(w.specs); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()
-    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()      # |S11| needs the 2x2 chain
+    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()      # |S11|: second row vector
+    p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()         # group delay: interpreter
     p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
     p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode
     p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()

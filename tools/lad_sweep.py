@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--variants", default="0,1,2,3,4,5,6")
     ap.add_argument("--workloads", default="cfg2,cfg5")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--s11", action="store_true", help="add an |S11| spec (exercises the second row vector)")
     args = ap.parse_args()
     import torch
     import qo100net as Q
@@ -35,6 +36,10 @@ def main():
     for wn in args.workloads.split(","):
         wl = getattr(W, wn)(n, 4096)
         nf = len(wl.f)
+        if args.s11:
+            fc = 10e6 if wn == "cfg2" else 3e9
+            wl.specs = list(wl.specs)[:2] + [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0)]
+            wl.hist = dict(wl.hist, hist_spec=0)
 
         def run(kernel, variant):
             os.environ["QO100NET_KERNEL"] = kernel

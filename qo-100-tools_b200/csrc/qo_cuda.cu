@@ -308,7 +308,8 @@ static int ladder_eligible(const DevProg *hp, int mode, int precision, int gener
 {
     const char *force = getenv("QO100NET_KERNEL");
     if (force && strcmp(force, "interp") == 0) return 0;
-    if (generic || mode != QO_MODE_REDUCE_ONLY || precision != 64 || hp->need_gd) return 0;
+    if (generic || mode != QO_MODE_REDUCE_ONLY || hp->need_gd) return 0;
+    if (precision == 32 && hp->need_s11) return 0;          /* FP32 mode: |S21| specs only on the straight-line kernel */
     if (hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) return 0;
     for (int s = 0; s < hp->nspec; s++)
         if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) return 0;
@@ -382,12 +383,12 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     const double two_pi = 6.283185307179586476925286766559;
     const int np = p->npairs;
     std::vector<double> w(2 * (size_t)np), wi(2 * (size_t)np), wsq(2 * (size_t)np);
-    std::vector<float> wf(2 * (size_t)np), wif(2 * (size_t)np);
+    std::vector<float> wf(2 * (size_t)np), wif(2 * (size_t)np), wsqf(2 * (size_t)np);
     std::vector<unsigned char> m(2 * (size_t)np, 0);
     for (int k = 0; k < 2 * np; k++) {
         double fk = f[k < nf ? k : nf - 1];
         w[k] = two_pi * fk; wi[k] = 1.0 / w[k]; wsq[k] = w[k] * w[k];
-        wf[k] = (float)w[k]; wif[k] = (float)wi[k];
+        wf[k] = (float)w[k]; wif[k] = (float)wi[k]; wsqf[k] = (float)wsq[k];
         m[k] = k < nf ? p->maskv[k] : 0;
     }
     /* measured two-port blocks: interpolate every block at every grid point (Qucs SPfile "linear"), convert to
@@ -429,6 +430,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     /* coupler block of the ladder kernel: sin/cos of the NOMINAL mode angles per grid point, usable when
      * every sample's angle stays within 0.05 rad of nominal over the whole grid (qo_ladder.cuh::lad_cpl_first) */
     std::vector<double> ctab[4];
+    std::vector<float> ctabf[4];
     p->cpl_fast = p->cpl_same = 0;
     if (p->ladder && p->lad_cpl) {
         const DevProg *hp = &p->hp;
@@ -458,6 +460,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 ctab[0][k] = sin(ke * w[k]); ctab[1][k] = cos(ke * w[k]);
                 ctab[2][k] = sin(ko * w[k]); ctab[3][k] = cos(ko * w[k]);
             }
+            for (int t = 0; t < 4; t++) { ctabf[t].resize(2 * (size_t)np); for (int k = 0; k < 2 * np; k++) ctabf[t][k] = (float)ctab[t][k]; }
         }
     }
     for (int g = 0; g < ctx->ndev; g++) {
@@ -490,13 +493,13 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 }
             }
             if (p->ladder) {
-                CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * sizeof(double), st));
-                CUP(cudaMemcpyAsync(d->wsq2, wsq.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
+                CUP(cudaMemcpyAsync(d->wsq2, p->precision == 32 ? (const void *)wsqf.data() : (const void *)wsq.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
                 CUP(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), st));
                 if (p->cpl_fast)
                     for (int t = 0; t < 4; t++) {
-                        CUP(cudaMallocAsync((void **)&d->cpl_tab[t], 2 * (size_t)np * sizeof(double), st));
-                        CUP(cudaMemcpyAsync(d->cpl_tab[t], ctab[t].data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                        CUP(cudaMallocAsync((void **)&d->cpl_tab[t], 2 * (size_t)np * esz, st));
+                        CUP(cudaMemcpyAsync(d->cpl_tab[t], p->precision == 32 ? (const void *)ctabf[t].data() : (const void *)ctab[t].data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
                     }
             }
         } else {
@@ -571,10 +574,9 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     LadParams P;
     memset(&P, 0, sizeof P);
     P.prog = d->prog;
-    P.wt = (const double2 *)d->w2; P.wit = (const double2 *)d->wi2; P.wsqt = (const double2 *)d->wsq2; P.m2 = d->m2;
+    P.wt = d->w2; P.wit = d->wi2; P.wsqt = d->wsq2; P.m2 = d->m2;
     P.counters = cnt;
-    P.cse = (const double2 *)d->cpl_tab[0]; P.cce = (const double2 *)d->cpl_tab[1];
-    P.cso = (const double2 *)d->cpl_tab[2]; P.cco = (const double2 *)d->cpl_tab[3];
+    P.cse = d->cpl_tab[0]; P.cce = d->cpl_tab[1]; P.cso = d->cpl_tab[2]; P.cco = d->cpl_tab[3];
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same;
     P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
@@ -582,7 +584,7 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
     for (int s = 0; s < QO_LAD_NSPEC; s++) {
         const int neg = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
-        P.sgn[s] = neg ? 0x80000000u : 0u;
+        P.neg[s] = neg;
         P.thr[s] = s < hp->nspec ? (neg ? -hp->spec_thr[s] : hp->spec_thr[s]) : 0.0;
         P.is_s11[s] = s < hp->nspec && hp->spec_kind[s] == SK_S11_MAX;
     }
@@ -590,7 +592,7 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
     P.hist_kind = hp->hist_bins > 0 ? hp->spec_kind[hp->hist_spec] : 0;
-    int rc = qo_ladder_launch(p->lad_n, p->lad_first, p->lad_cpl, hp->need_s11 ? 2 : 1, p->lad_variant, dc->sm_count, &P, dc->stream, NULL);
+    int rc = qo_ladder_launch(p->lad_n, p->lad_first, p->lad_cpl, hp->need_s11 ? 2 : 1, p->precision, p->lad_variant, dc->sm_count, &P, dc->stream, NULL);
     if (rc < 0) { qo_set_error("no ladder kernel instantiation for n=%d first=%d cpl=%d", p->lad_n, p->lad_first, p->lad_cpl); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("ladder kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
     return QO_OK;

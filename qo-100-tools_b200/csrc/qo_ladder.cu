@@ -17,17 +17,17 @@
 
 typedef void (*lad_fn)(const LadParams);
 
-template <int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB> static lad_fn lad_get()
+template <typename T, int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB> static lad_fn lad_get()
 {
-    return qo_mc_ladder_kernel<N, FIRST, CPL, NROWS, PP, TPB, MINB>;
+    return qo_mc_ladder_kernel<T, N, FIRST, CPL, NROWS, PP, TPB, MINB>;
 }
 
-template <int NROWS, int PP, int TPB, int MINB> static lad_fn lad_pick(int n, int first, int cpl)
+template <typename T, int NROWS, int PP, int TPB, int MINB> static lad_fn lad_pick(int n, int first, int cpl)
 {
 #define QO_LAD_ROW(NN)                                                                       \
     case NN:                                                                                 \
-        return cpl ? (first ? lad_get<NN, 1, true, NROWS, PP, TPB, MINB>() : lad_get<NN, 0, true, NROWS, PP, TPB, MINB>())   \
-                   : (first ? lad_get<NN, 1, false, NROWS, PP, TPB, MINB>() : lad_get<NN, 0, false, NROWS, PP, TPB, MINB>());
+        return cpl ? (first ? lad_get<T, NN, 1, true, NROWS, PP, TPB, MINB>() : lad_get<T, NN, 0, true, NROWS, PP, TPB, MINB>())   \
+                   : (first ? lad_get<T, NN, 1, false, NROWS, PP, TPB, MINB>() : lad_get<T, NN, 0, false, NROWS, PP, TPB, MINB>());
     switch (n) {
         QO_LAD_ROW(1) QO_LAD_ROW(2) QO_LAD_ROW(3) QO_LAD_ROW(4) QO_LAD_ROW(5) QO_LAD_ROW(6)
         QO_LAD_ROW(7) QO_LAD_ROW(8) QO_LAD_ROW(9) QO_LAD_ROW(10) QO_LAD_ROW(11)
@@ -41,7 +41,7 @@ template <int NROWS, int PP, int TPB, int MINB> static lad_fn lad_pick(int n, in
 template <int PP, int TPB, int MINB> static lad_fn lad_pick11(int n, int first, int cpl)
 {
     if (n != 11 || first) return nullptr;
-    return cpl ? lad_get<11, 0, true, 1, PP, TPB, MINB>() : lad_get<11, 0, false, 1, PP, TPB, MINB>();
+    return cpl ? lad_get<double, 11, 0, true, 1, PP, TPB, MINB>() : lad_get<double, 11, 0, false, 1, PP, TPB, MINB>();
 }
 #endif
 
@@ -50,8 +50,13 @@ template <int PP, int TPB, int MINB> static lad_fn lad_pick11(int n, int first, 
 #define QO_LAD2_TPB 256
 #define QO_LAD2_MINB 2
 
-extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int variant, int sm_count, const LadParams *P, cudaStream_t st,
-                                const char **shape)
+/* FP32 mode: four points per thread, three blocks per SM */
+#define QO_LAD32_PP 2
+#define QO_LAD32_TPB 256
+#define QO_LAD32_MINB 3
+
+extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int precision, int variant, int sm_count, const LadParams *P,
+                                cudaStream_t st, const char **shape)
 {
     lad_fn fn = nullptr;
     int tpb = QO_LAD_TPB, minb = QO_LAD_MINB;
@@ -71,11 +76,15 @@ extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int varian
     default: break;
     }
 #endif
-    if (nrows == 2) {
-        fn = lad_pick<2, QO_LAD2_PP, QO_LAD2_TPB, QO_LAD2_MINB>(n, first, cpl);
+    if (precision == 32) {
+        if (nrows != 1) return -1;
+        fn = lad_pick<float, 1, QO_LAD32_PP, QO_LAD32_TPB, QO_LAD32_MINB>(n, first, cpl);
+        tpb = QO_LAD32_TPB; minb = QO_LAD32_MINB; name = "fp32";
+    } else if (nrows == 2) {
+        fn = lad_pick<double, 2, QO_LAD2_PP, QO_LAD2_TPB, QO_LAD2_MINB>(n, first, cpl);
         tpb = QO_LAD2_TPB; minb = QO_LAD2_MINB; name = "s11";
     } else if (!fn) {
-        fn = lad_pick<1, QO_LAD_PP, QO_LAD_TPB, QO_LAD_MINB>(n, first, cpl);
+        fn = lad_pick<double, 1, QO_LAD_PP, QO_LAD_TPB, QO_LAD_MINB>(n, first, cpl);
         tpb = QO_LAD_TPB; minb = QO_LAD_MINB; name = "default";
     }
     if (!fn) return -1;

@@ -38,39 +38,58 @@
 
 #define QO_LAD_MAXN 11
 #define QO_LAD_NSPEC 4               /* trackers kept in registers; more specs -> interpreter */
-#define QO_LAD_STRIDE 6              /* doubles per element record (16-byte aligned) */
-#define QO_LAD_CPL 10                /* doubles of the coupler record that precedes the ladder records */
-#define QO_LAD_NEG_HUGE_HI 0xFFEFFFFFu   /* high word of a huge negative finite double: "no point seen yet" */
+#define QO_LAD_STRIDE 6              /* values per element record (16-byte aligned in FP64, 8-byte in FP32) */
+#define QO_LAD_CPL 10                /* values of the coupler record that precedes the ladder records */
+
+/* The kernel is generic over T = double (the product's precision, every number quoted in DESIGN.md) and
+ * T = float (the optional FP32 mode of north_star: |S21| within 1e-3 dB, on the 2x wider FP32 pipe). */
+template <typename T> struct LadNum;
+template <> struct LadNum<double> { static __device__ __forceinline__ double neg_huge() { return -1.7e308; } };
+template <> struct LadNum<float> { static __device__ __forceinline__ float neg_huge() { return -3.0e38f; } };
 
 /* NROWS = 1: the row vector u = [1 Rs] M (enough for |S21|); NROWS = 2 adds v = [1 -Rs] M, whose contraction
  * v . [Rl 1]^T is the numerator of S11, for jobs with |S11| specs */
-template <int PTS, int NROWS> struct LadRow { double ar[NROWS][PTS], ai[NROWS][PTS], br[NROWS][PTS], bi[NROWS][PTS]; };
+template <typename T, int PTS, int NROWS> struct LadRow { T ar[NROWS][PTS], ai[NROWS][PTS], br[NROWS][PTS], bi[NROWS][PTS]; };
 #define QO_ROWS _Pragma("unroll") for (int r = 0; r < NROWS; r++)
+#define QO_PTS _Pragma("unroll") for (int p = 0; p < PTS; p++)
 
 /* Broadcast read of two coefficients from the warp's record table.  The records are invariant over
- * the frequency loop, and left to itself ptxas hoists all 55 doubles of an 11-element ladder out of
+ * the frequency loop, and left to itself ptxas hoists all 55 values of an 11-element ladder out of
  * the loop and spills them to local memory; an asm volatile load stays where it is written (one
- * conflict-free LDS.64x2 wavefront per element per iteration). */
-__device__ __forceinline__ double2 lad_lds2(unsigned int saddr)
+ * conflict-free wavefront per load). */
+template <typename T> struct LadV2 { T x, y; };
+__device__ __forceinline__ LadV2<double> lad_lds2(unsigned int saddr, double)
 {
-    double2 v;
+    LadV2<double> v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
     return v;
 }
-__device__ __forceinline__ double lad_lds1(unsigned int saddr)
+__device__ __forceinline__ LadV2<float> lad_lds2(unsigned int saddr, float)
+{
+    LadV2<float> v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ double lad_lds1(unsigned int saddr, double)
 {
     double v;
     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
     return v;
 }
+__device__ __forceinline__ float lad_lds1(unsigned int saddr, float)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
 
-#define QO_PTS _Pragma("unroll") for (int p = 0; p < PTS; p++)
-
-/* 1/q for the PTS points of one element with ONE reciprocal (Montgomery's trick): the MUFU.RCP64H seed
- * and the register move that zeroes its low word are not FP64-pipe instructions, and tools/pipe_probe2.cu
- * shows each such instruction costs about one FP64 issue cycle when it does not land in a DFMA's shadow.
- * FP64 work is unchanged (9 DMUL + 3 DFMA per four points = 3 per point); each 1/q carries <= 3 roundings.
- * The product of four |immittance|^2 values stays far inside the double range for any physical element. */
+/* 1/q for the PTS points of one element.
+ * FP64: ONE reciprocal for all points (Montgomery's trick): the MUFU.RCP64H seed and the register move that
+ * zeroes its low word are not FP64-pipe instructions, and tools/pipe_probe2.cu shows each such instruction costs
+ * about one FP64 issue cycle when it does not land in a DFMA's shadow.  FP64 work is unchanged (9 DMUL + 3 DFMA
+ * per four points = 3 per point); each 1/q carries <= 3 roundings.  The product of four |immittance|^2 values
+ * stays far inside the double range for any physical element.
+ * FP32: one MUFU.RCP per point (1 ulp; a product of four would leave the float range). */
 template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const double (&q)[PTS], double (&s)[PTS])
 {
     static_assert(PTS == 2 || PTS == 4, "two or four points per thread");
@@ -84,49 +103,51 @@ template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const double (&
         s[0] = r01 * q[1]; s[1] = r01 * q[0]; s[2] = r23 * q[3]; s[3] = r23 * q[2];
     }
 }
+template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const float (&q)[PTS], float (&s)[PTS])
+{
+    QO_PTS asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(s[p]) : "f"(q[p]));
+}
 
 /* series lossy inductor; record = { L*Cp, (R*Cp)^2, L, R^2*Cp, R, - } */
-template <int PTS, int NROWS, bool FIRSTSTEP>
-__device__ __forceinline__ void lad_ser_lossy_l(unsigned int cf, const double (&w)[PTS], const double (&w2)[PTS],
-                                                double rs, LadRow<PTS, NROWS> &u)
+template <typename T, int PTS, int NROWS, bool FIRSTSTEP>
+__device__ __forceinline__ void lad_ser_lossy_l(unsigned int cf, const T (&w)[PTS], const T (&w2)[PTS], T rs, LadRow<T, PTS, NROWS> &u)
 {
-    const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16);
-    const double R = lad_lds1(cf + 32);
-    double dre[PTS], q[PTS], s[PTS];
-    QO_PTS { dre[p] = fma(-w2[p], c01.x, 1.0); q[p] = fma(dre[p], dre[p], w2[p] * c01.y); }
+    const LadV2<T> c01 = lad_lds2(cf, T()), c23 = lad_lds2(cf + 2 * sizeof(T), T());
+    const T R = lad_lds1(cf + 4 * sizeof(T), T());
+    T dre[PTS], q[PTS], s[PTS];
+    QO_PTS { dre[p] = qfma(-w2[p], c01.x, T(1)); q[p] = qfma(dre[p], dre[p], w2[p] * c01.y); }
     lad_rcp_batch<PTS>(q, s);
     QO_PTS {
-        const double g = fma(c23.x, dre[p], -c23.y);
-        const double zr = R * s[p], zi = (w[p] * s[p]) * g;
+        const T g = qfma(c23.x, dre[p], -c23.y);
+        const T zr = R * s[p], zi = (w[p] * s[p]) * g;
         QO_ROWS {
             if (FIRSTSTEP) {             /* u = [1 +-Rs]: b = +-Rs + Z */
                 u.br[r][p] = (r ? -rs : rs) + zr; u.bi[r][p] = zi;
             } else {
-                u.br[r][p] = fma(u.ar[r][p], zr, u.br[r][p]); u.br[r][p] = fma(-u.ai[r][p], zi, u.br[r][p]);
-                u.bi[r][p] = fma(u.ar[r][p], zi, u.bi[r][p]); u.bi[r][p] = fma(u.ai[r][p], zr, u.bi[r][p]);
+                u.br[r][p] = qfma(u.ar[r][p], zr, u.br[r][p]); u.br[r][p] = qfma(-u.ai[r][p], zi, u.br[r][p]);
+                u.bi[r][p] = qfma(u.ar[r][p], zi, u.bi[r][p]); u.bi[r][p] = qfma(u.ai[r][p], zr, u.bi[r][p]);
             }
         }
     }
 }
 
 /* shunt lossy capacitor; record = { 1/C, Ls, R, R^2 } */
-template <int PTS, int NROWS, bool FIRSTSTEP>
-__device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double (&w)[PTS], const double (&wi)[PTS],
-                                                  double rs, LadRow<PTS, NROWS> &u)
+template <typename T, int PTS, int NROWS, bool FIRSTSTEP>
+__device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const T (&w)[PTS], const T (&wi)[PTS], T rs, LadRow<T, PTS, NROWS> &u)
 {
-    const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16);
-    double x[PTS], q[PTS], s[PTS];
-    QO_PTS { x[p] = fma(w[p], c01.y, -wi[p] * c01.x); q[p] = fma(x[p], x[p], c23.y); }
+    const LadV2<T> c01 = lad_lds2(cf, T()), c23 = lad_lds2(cf + 2 * sizeof(T), T());
+    T x[PTS], q[PTS], s[PTS];
+    QO_PTS { x[p] = qfma(w[p], c01.y, -wi[p] * c01.x); q[p] = qfma(x[p], x[p], c23.y); }
     lad_rcp_batch<PTS>(q, s);
     QO_PTS {
-        const double yr = c23.x * s[p], yi = -x[p] * s[p];
+        const T yr = c23.x * s[p], yi = -x[p] * s[p];
         QO_ROWS {
             if (FIRSTSTEP) {             /* u = [1 +-Rs]: a = 1 +- Rs Y */
-                const double rr = r ? -rs : rs;
-                u.ar[r][p] = fma(rr, yr, 1.0); u.ai[r][p] = rr * yi;
+                const T rr = r ? -rs : rs;
+                u.ar[r][p] = qfma(rr, yr, T(1)); u.ai[r][p] = rr * yi;
             } else {
-                u.ar[r][p] = fma(u.br[r][p], yr, u.ar[r][p]); u.ar[r][p] = fma(-u.bi[r][p], yi, u.ar[r][p]);
-                u.ai[r][p] = fma(u.br[r][p], yi, u.ai[r][p]); u.ai[r][p] = fma(u.bi[r][p], yr, u.ai[r][p]);
+                u.ar[r][p] = qfma(u.br[r][p], yr, u.ar[r][p]); u.ar[r][p] = qfma(-u.bi[r][p], yi, u.ar[r][p]);
+                u.ai[r][p] = qfma(u.br[r][p], yi, u.ai[r][p]); u.ai[r][p] = qfma(u.bi[r][p], yr, u.ai[r][p]);
             }
         }
     }
@@ -144,63 +165,65 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const double 
  * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
  * short Taylor polynomials (|d|^10/10! < 3e-20, |d|^9/9! < 6e-18) -- 14 FP64 instructions instead of the ~30 of
  * a general sincos; otherwise sincos() is called. */
-template <int PTS, int NROWS, bool FAST>
-__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
-                                              const double (&tso)[PTS], const double (&tco)[PTS], double rs, LadRow<PTS, NROWS> &u,
-                                              double (&scale)[PTS])
+template <typename T, int PTS, int NROWS, bool FAST>
+__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
+                                              const T (&tso)[PTS], const T (&tco)[PTS], T rs, LadRow<T, PTS, NROWS> &u, T (&scale)[PTS])
 {
-    const double2 c01 = lad_lds2(cf), c23 = lad_lds2(cf + 16), c45 = lad_lds2(cf + 32), c67 = lad_lds2(cf + 48), c89 = lad_lds2(cf + 64);
-    const double cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y, ke = c45.x, ko = c45.y, zt = c67.x, rz = c67.y;
+    const LadV2<T> c01 = lad_lds2(cf, T()), c23 = lad_lds2(cf + 2 * sizeof(T), T()), c45 = lad_lds2(cf + 4 * sizeof(T), T()),
+                   c67 = lad_lds2(cf + 6 * sizeof(T), T()), c89 = lad_lds2(cf + 8 * sizeof(T), T());
+    const T cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y, ke = c45.x, ko = c45.y, zt = c67.x, rz = c67.y;
     const bool same = ke == ko;
-    double se[PTS], ce[PTS], so[PTS], co[PTS], kap2[PTS];
+    T se[PTS], ce[PTS], so[PTS], co[PTS], kap2[PTS];
     QO_PTS {
         if (FAST) {
             {
-                const double d = c89.x * w[p], z = d * d;
-                const double cd = fma(fma(fma(fma(1.0 / 40320.0, z, -1.0 / 720.0), z, 1.0 / 24.0), z, -0.5), z, 1.0);
-                const double sd = d * fma(fma(fma(-1.0 / 5040.0, z, 1.0 / 120.0), z, -1.0 / 6.0), z, 1.0);
-                se[p] = fma(tse[p], cd, tce[p] * sd); ce[p] = fma(tce[p], cd, -tse[p] * sd);
+                const T d = c89.x * w[p], z = d * d;
+                const T cd = qfma(qfma(qfma(qfma(T(1.0 / 40320.0), z, T(-1.0 / 720.0)), z, T(1.0 / 24.0)), z, T(-0.5)), z, T(1));
+                const T sd = d * qfma(qfma(qfma(T(-1.0 / 5040.0), z, T(1.0 / 120.0)), z, T(-1.0 / 6.0)), z, T(1));
+                se[p] = qfma(tse[p], cd, tce[p] * sd); ce[p] = qfma(tce[p], cd, -tse[p] * sd);
             }
             if (same) { so[p] = se[p]; co[p] = ce[p]; }
             else {
-                const double d = c89.y * w[p], z = d * d;
-                const double cd = fma(fma(fma(fma(1.0 / 40320.0, z, -1.0 / 720.0), z, 1.0 / 24.0), z, -0.5), z, 1.0);
-                const double sd = d * fma(fma(fma(-1.0 / 5040.0, z, 1.0 / 120.0), z, -1.0 / 6.0), z, 1.0);
-                so[p] = fma(tso[p], cd, tco[p] * sd); co[p] = fma(tco[p], cd, -tso[p] * sd);
+                const T d = c89.y * w[p], z = d * d;
+                const T cd = qfma(qfma(qfma(qfma(T(1.0 / 40320.0), z, T(-1.0 / 720.0)), z, T(1.0 / 24.0)), z, T(-0.5)), z, T(1));
+                const T sd = d * qfma(qfma(qfma(T(-1.0 / 5040.0), z, T(1.0 / 120.0)), z, T(-1.0 / 6.0)), z, T(1));
+                so[p] = qfma(tso[p], cd, tco[p] * sd); co[p] = qfma(tco[p], cd, -tso[p] * sd);
             }
         } else {
-            sincos(ke * w[p], &se[p], &ce[p]);
-            if (same) { so[p] = se[p]; co[p] = ce[p]; } else sincos(ko * w[p], &so[p], &co[p]);
+            qsincos(ke * w[p], &se[p], &ce[p]);
+            if (same) { so[p] = se[p]; co[p] = ce[p]; } else qsincos(ko * w[p], &so[p], &co[p]);
         }
     }
     QO_PTS {
-        const double a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;        /* D_e, D_o */
-        const double Pr = fma(a1, a2, -b1 * b2), Pi = fma(a1, b2, a2 * b1);                              /* Pi */
-        const double Sr = a1 + a2, Si = b1 + b2;                                                         /* Sg */
-        const double pe = se[p] * hE, po = so[p] * hO;
-        const double Nr = -fma(pe, b2, po * b1), Ni = fma(pe, a2, po * a1);                              /* Nu */
-        const double Xr = fma(Pr, Pr, -Pi * Pi), Xi = (Pr + Pr) * Pi;                                    /* Pi^2 */
-        const double Yr = fma(Nr, Nr, -Ni * Ni), Yi = (Nr + Nr) * Ni;                                    /* Nu^2 */
-        const double Wr = fma(Sr, Sr, -Si * Si), Wi = (Sr + Sr) * Si;                                    /* Sg^2 */
-        const double Vr = fma(Pr, Nr, -Pi * Ni), Vi = fma(Pr, Ni, Pi * Nr);                              /* Pi Nu */
-        const double Tr = Xr + Yr - Wr, Ti = Xi + Yi - Wi;
-        const double Ar = Xr - Yr + Wr, Ai = Xi - Yi + Wi;                                               /* k A */
-        const double Br = fma(2.0, Vr, Tr), Bi = fma(2.0, Vi, Ti);                                       /* k B / Zt */
-        const double Cr = fma(-2.0, Vr, Tr), Ci = fma(-2.0, Vi, Ti);                                     /* k C Zt */
-        const double Kr = fma(Sr, Pr, -Si * Pi), Ki = fma(Sr, Pi, Si * Pr);                              /* k / 2 */
-        kap2[p] = fma(Kr, Kr, Ki * Ki);
+        const T a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;             /* D_e, D_o */
+        const T Pr = qfma(a1, a2, -b1 * b2), Pi = qfma(a1, b2, a2 * b1);                                 /* Pi */
+        const T Sr = a1 + a2, Si = b1 + b2;                                                              /* Sg */
+        const T pe = se[p] * hE, po = so[p] * hO;
+        const T Nr = -qfma(pe, b2, po * b1), Ni = qfma(pe, a2, po * a1);                                 /* Nu */
+        const T Xr = qfma(Pr, Pr, -Pi * Pi), Xi = (Pr + Pr) * Pi;                                        /* Pi^2 */
+        const T Yr = qfma(Nr, Nr, -Ni * Ni), Yi = (Nr + Nr) * Ni;                                        /* Nu^2 */
+        const T Wr = qfma(Sr, Sr, -Si * Si), Wi = (Sr + Sr) * Si;                                        /* Sg^2 */
+        const T Vr = qfma(Pr, Nr, -Pi * Ni), Vi = qfma(Pr, Ni, Pi * Nr);                                 /* Pi Nu */
+        const T Tr = Xr + Yr - Wr, Ti = Xi + Yi - Wi;
+        const T Ar = Xr - Yr + Wr, Ai = Xi - Yi + Wi;                                                    /* k A */
+        const T Br = qfma(T(2), Vr, Tr), Bi = qfma(T(2), Vi, Ti);                                        /* k B / Zt */
+        const T Cr = qfma(T(-2), Vr, Tr), Ci = qfma(T(-2), Vi, Ti);                                      /* k C Zt */
+        const T Kr = qfma(Sr, Pr, -Si * Pi), Ki = qfma(Sr, Pi, Si * Pr);                                 /* k / 2 */
+        kap2[p] = qfma(Kr, Kr, Ki * Ki);
         QO_ROWS {
-            const double sg = r ? -1.0 : 1.0;
-            u.ar[r][p] = fma(sg * rz, Cr, Ar); u.ai[r][p] = fma(sg * rz, Ci, Ai);                        /* k (A +- Rs C) */
-            u.br[r][p] = fma(sg * rs, Ar, zt * Br); u.bi[r][p] = fma(sg * rs, Ai, zt * Bi);              /* k (B +- Rs A) */
+            const T sg = r ? T(-1) : T(1);
+            u.ar[r][p] = qfma(sg * rz, Cr, Ar); u.ai[r][p] = qfma(sg * rz, Ci, Ai);                      /* k (A +- Rs C) */
+            u.br[r][p] = qfma(sg * rs, Ar, zt * Br); u.bi[r][p] = qfma(sg * rs, Ai, zt * Bi);            /* k (B +- Rs A) */
         }
     }
     lad_rcp_batch<PTS>(kap2, scale);
-    QO_PTS scale[p] *= 0.25;                                                                             /* 1/|k|^2 */
+    QO_PTS scale[p] *= T(0.25);                                                                          /* 1/|k|^2 */
 }
 
-/* per-sample coefficient records, one lane per element (perturbation is the shared bit-exact stream) */
-__device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, double *out)
+/* per-sample coefficient records, one lane per element (perturbation is the shared bit-exact stream; the
+ * derived coefficients are formed in FP64 and rounded once when T = float) */
+template <typename T>
+__device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out)
 {
     double p[6];
 #pragma unroll
@@ -212,17 +235,18 @@ __device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int
     switch (prog->opcode[e]) {
     case OP_SER_LOSSY_L: case OP_SER_L: {              /* p = L, R, Cp */
         const double rcp_ = p[1] * p[2];
-        out[0] = p[0] * p[2]; out[1] = rcp_ * rcp_; out[2] = p[0]; out[3] = p[1] * rcp_; out[4] = p[1]; out[5] = 0.0;
+        out[0] = T(p[0] * p[2]); out[1] = T(rcp_ * rcp_); out[2] = T(p[0]); out[3] = T(p[1] * rcp_); out[4] = T(p[1]); out[5] = T(0);
         break;
     }
     case OP_SHUNT_LOSSY_C: case OP_SHUNT_C:            /* p = C, R, Ls */
-        out[0] = 1.0 / p[0]; out[1] = p[2]; out[2] = p[1]; out[3] = p[1] * p[1]; out[4] = 0.0; out[5] = 0.0;
+        out[0] = T(1.0 / p[0]); out[1] = T(p[2]); out[2] = T(p[1]); out[3] = T(p[1] * p[1]); out[4] = T(0); out[5] = T(0);
         break;
     case OP_CPL: {
         const double a = p[0] / p[5], b = p[1] / p[5];
-        out[0] = a + 1.0 / a; out[1] = 0.5 * (a - 1.0 / a); out[2] = b + 1.0 / b; out[3] = 0.5 * (b - 1.0 / b);
-        out[4] = p[2] / (360.0 * p[4]); out[5] = p[3] / (360.0 * p[4]); out[6] = p[5]; out[7] = prog->rs / p[5];
-        out[8] = out[4] - prog->nom[e][2] / (360.0 * prog->nom[e][4]); out[9] = out[5] - prog->nom[e][3] / (360.0 * prog->nom[e][4]);
+        const double ke = p[2] / (360.0 * p[4]), ko = p[3] / (360.0 * p[4]);
+        out[0] = T(a + 1.0 / a); out[1] = T(0.5 * (a - 1.0 / a)); out[2] = T(b + 1.0 / b); out[3] = T(0.5 * (b - 1.0 / b));
+        out[4] = T(ke); out[5] = T(ko); out[6] = T(p[5]); out[7] = T(prog->rs / p[5]);
+        out[8] = T(ke - prog->nom[e][2] / (360.0 * prog->nom[e][4])); out[9] = T(ko - prog->nom[e][3] / (360.0 * prog->nom[e][4]));
         break;
     }
     default: break;
@@ -233,36 +257,38 @@ __device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int
  * vector registers held across the frequency loop) */
 struct LadParams {
     const DevProg *prog;
-    const double2 *wt, *wit, *wsqt;          /* w, 1/w, w^2 per grid point, two points per entry */
+    const void *wt, *wit, *wsqt;             /* w, 1/w, w^2 per grid point, two points per entry (double2 / float2) */
     const uchar2 *m2;                        /* per-point spec bit masks */
-    const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the NOMINAL even/odd angle per grid point (cpl_fast) */
+    const void *cse, *cce, *cso, *cco;       /* coupler: sin/cos of the NOMINAL even/odd angle per grid point (cpl_fast) */
     unsigned long long *counters;
     unsigned long long *ticket;              /* next unclaimed sample of this launch (zeroed on the stream before it) */
     unsigned long long sample_offset, nsamples, seed;
     double rs, rl, k21, hist_lo, hist_hi;
     double thr[QO_LAD_NSPEC];                /* sign-adjusted thresholds: FAIL iff tracker > thr */
-    unsigned int sgn[QO_LAD_NSPEC];          /* 0x80000000 for "max dB" specs (tracker holds -|den|^2) */
+    int neg[QO_LAD_NSPEC];                   /* "max dB" spec: the tracker holds -|den|^2 */
     int is_s11[QO_LAD_NSPEC];                /* the spec's tracker holds |S11|^2 = |n11|^2 / |den|^2 (NROWS == 2 kernels) */
     int npairs, n_var, n_ops, nspec, dist, hist_spec, hist_bins, hist_kind;
     int cpl_fast, cpl_same;                  /* small-angle table path usable; nominal even and odd angles identical */
 };
 
 /*
- * N      ladder elements (1..11)        FIRST  0 = series element first, 1 = shunt first
- * CPL    coupled-line block in front    PP     frequency pairs per thread per iteration (PTS = 2*PP points)
+ * T      double | float                 N      ladder elements (1..11)
+ * FIRST  0 = series element first, 1 = shunt first            CPL    coupled-line block in front
+ * NROWS  1 | 2 (with the |S11| row)     PP     frequency pairs per thread per iteration (PTS = 2*PP points)
  * TPB / MINB  block size and resident blocks per SM (register budget = 65536 / (TPB*MINB))
  * One warp = one sample at a time; lane l owns pairs l, l+32, ... of that sample's grid.
  * Samples are handed out through a global ticket counter: with a static split ncu showed every
  * SMSP averaging 3.06 of its 4 warps (the issue scheduler is not fair, favoured warps finished
  * their share early and the FP64 pipe drained); tickets keep all warps busy until the pool is empty.
  */
-template <int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB>
+template <typename T, int N, int FIRST, bool CPL, int NROWS, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_constant__ LadParams P)
 {
+    typedef typename QoVec2<T>::type V2;
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
     constexpr int NREC = (CPL ? QO_LAD_CPL : 0) + N * QO_LAD_STRIDE;
-    __shared__ __align__(16) double s_coef[WARPS][NREC];
+    __shared__ __align__(16) T s_coef[WARPS][NREC];
     __shared__ double s_x[WARPS][QO_MAX_VAR];
     __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
 
@@ -271,11 +297,12 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
     for (int i = threadIdx.x; i < ncnt; i += TPB) s_cnt[i] = 0;
     __syncthreads();
 
-    double *coefw = s_coef[warp];
+    T *coefw = s_coef[warp];
     double *xw = s_x[warp];
     const unsigned int coefs = (unsigned int)__cvta_generic_to_shared(coefw);
     const int npairs = P.npairs;
-    const double rs = P.rs;
+    const T rs = T(P.rs);
+    const V2 *wt = (const V2 *)P.wt, *wit = (const V2 *)P.wit, *wsqt = (const V2 *)P.wsqt;
 
     /* the first gridDim.x*WARPS samples are claimed by position, the rest by ticket; the next ticket
      * is requested before the frequency loop so that the atomic's latency is never exposed */
@@ -289,78 +316,78 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
         __syncwarp();
         if (lane < P.n_ops) {
             const int rec = CPL ? (lane == 0 ? 0 : QO_LAD_CPL + (lane - 1) * QO_LAD_STRIDE) : lane * QO_LAD_STRIDE;
-            lad_derive(P.prog, lane, xw, coefw + rec);
+            lad_derive<T>(P.prog, lane, xw, coefw + rec);
         }
         __syncwarp();
 
         /* 2. frequency loop */
-        double trk[QO_LAD_NSPEC];
+        T trk[QO_LAD_NSPEC];
 #pragma unroll
-        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) trk[sp] = __hiloint2double((int)QO_LAD_NEG_HUGE_HI, 0);
+        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) trk[sp] = LadNum<T>::neg_huge();       /* "no point seen yet" */
         /* warp-uniform trip count (the tracker vote below is a full-warp collective): lanes past the end of
          * the grid re-evaluate the last pair with all-zero masks */
         for (int jb = 0; jb < npairs; jb += 32 * PP) {
             const int j0 = jb + lane;
-            double w[PTS], wi[PTS], w2[PTS];
+            T w[PTS], wi[PTS], w2[PTS];
             unsigned int mk[PTS];
 #pragma unroll
             for (int q = 0; q < PP; q++) {
                 const int j = j0 + 32 * q;
                 const int jc = j < npairs ? j : npairs - 1;
-                const double2 a = P.wt[jc], b = P.wit[jc], c = P.wsqt[jc];
+                const V2 a = wt[jc], b = wit[jc], c = wsqt[jc];
                 const uchar2 m = P.m2[jc];
                 w[2 * q] = a.x; w[2 * q + 1] = a.y; wi[2 * q] = b.x; wi[2 * q + 1] = b.y; w2[2 * q] = c.x; w2[2 * q + 1] = c.y;
                 mk[2 * q] = j < npairs ? m.x : 0u; mk[2 * q + 1] = j < npairs ? m.y : 0u;
             }
-            LadRow<PTS, NROWS> u;
-            double cscale[PTS];
-            QO_PTS { cscale[p] = 1.0; QO_ROWS { u.ar[r][p] = 1.0; u.ai[r][p] = 0.0; u.br[r][p] = r ? -rs : rs; u.bi[r][p] = 0.0; } }
+            LadRow<T, PTS, NROWS> u;
+            T cscale[PTS];
+            QO_PTS { cscale[p] = T(1); QO_ROWS { u.ar[r][p] = T(1); u.ai[r][p] = T(0); u.br[r][p] = r ? -rs : rs; u.bi[r][p] = T(0); } }
             if (CPL) {
-                double tse[PTS], tce[PTS], tso[PTS], tco[PTS];
-                QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
+                T tse[PTS], tce[PTS], tso[PTS], tco[PTS];
+                QO_PTS { tse[p] = T(0); tce[p] = T(1); tso[p] = T(0); tco[p] = T(1); }
                 if (P.cpl_fast) {
 #pragma unroll
                     for (int q = 0; q < PP; q++) {
                         const int j = j0 + 32 * q;
                         const int jc = j < npairs ? j : npairs - 1;
-                        const double2 a = P.cse[jc], b = P.cce[jc];
+                        const V2 a = ((const V2 *)P.cse)[jc], b = ((const V2 *)P.cce)[jc];
                         tse[2 * q] = a.x; tse[2 * q + 1] = a.y; tce[2 * q] = b.x; tce[2 * q + 1] = b.y;
                         if (!P.cpl_same) {
-                            const double2 c = P.cso[jc], d = P.cco[jc];
+                            const V2 c = ((const V2 *)P.cso)[jc], d = ((const V2 *)P.cco)[jc];
                             tso[2 * q] = c.x; tso[2 * q + 1] = c.y; tco[2 * q] = d.x; tco[2 * q + 1] = d.y;
                         }
                     }
-                    lad_cpl_first<PTS, NROWS, true>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                    lad_cpl_first<T, PTS, NROWS, true>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
                 } else {
-                    lad_cpl_first<PTS, NROWS, false>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
+                    lad_cpl_first<T, PTS, NROWS, false>(coefs, w, tse, tce, tso, tco, rs, u, cscale);
                 }
             }
-            const unsigned int lad = coefs + (CPL ? QO_LAD_CPL : 0) * 8u;
+            const unsigned int lad = coefs + (CPL ? QO_LAD_CPL : 0) * (unsigned int)sizeof(T);
 #pragma unroll
             for (int e = 0; e < N; e++) {
                 const bool series = ((e + FIRST) & 1) == 0;
-                const unsigned int cf = lad + e * QO_LAD_STRIDE * 8u;
+                const unsigned int cf = lad + e * QO_LAD_STRIDE * (unsigned int)sizeof(T);
                 if (series) {
-                    if (e == 0 && !CPL) lad_ser_lossy_l<PTS, NROWS, true>(cf, w, w2, rs, u);
-                    else lad_ser_lossy_l<PTS, NROWS, false>(cf, w, w2, rs, u);
+                    if (e == 0 && !CPL) lad_ser_lossy_l<T, PTS, NROWS, true>(cf, w, w2, rs, u);
+                    else lad_ser_lossy_l<T, PTS, NROWS, false>(cf, w, w2, rs, u);
                 } else {
-                    if (e == 0 && !CPL) lad_shunt_lossy_c<PTS, NROWS, true>(cf, w, wi, rs, u);
-                    else lad_shunt_lossy_c<PTS, NROWS, false>(cf, w, wi, rs, u);
+                    if (e == 0 && !CPL) lad_shunt_lossy_c<T, PTS, NROWS, true>(cf, w, wi, rs, u);
+                    else lad_shunt_lossy_c<T, PTS, NROWS, false>(cf, w, wi, rs, u);
                 }
             }
-            const double rl = P.rl;
-            double den2[PTS], s11m[PTS];
+            const T rl = T(P.rl);
+            T den2[PTS], s11m[PTS];
             QO_PTS {
-                const double den_r = fma(u.ar[0][p], rl, u.br[0][p]), den_i = fma(u.ai[0][p], rl, u.bi[0][p]);
-                den2[p] = fma(den_r, den_r, den_i * den_i);
+                const T den_r = qfma(u.ar[0][p], rl, u.br[0][p]), den_i = qfma(u.ai[0][p], rl, u.bi[0][p]);
+                den2[p] = qfma(den_r, den_r, den_i * den_i);
             }
             if (NROWS == 2) {
                 /* |S11|^2 = |v . [Rl 1]|^2 / |den|^2 (the coupler's common factor 1/k cancels in the ratio) */
-                double rd[PTS];
+                T rd[PTS];
                 lad_rcp_batch<PTS>(den2, rd);
                 QO_PTS {
-                    const double n_r = fma(u.ar[1][p], rl, u.br[1][p]), n_i = fma(u.ai[1][p], rl, u.bi[1][p]);
-                    s11m[p] = fma(n_r, n_r, n_i * n_i) * rd[p];
+                    const T n_r = qfma(u.ar[1][p], rl, u.br[1][p]), n_i = qfma(u.ai[1][p], rl, u.bi[1][p]);
+                    s11m[p] = qfma(n_r, n_r, n_i * n_i) * rd[p];
                 }
             }
             if (CPL) { QO_PTS den2[p] *= cscale[p]; }
@@ -376,7 +403,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((all >> sp) & 1u) {
                         if (NROWS == 2 && P.is_s11[sp]) { QO_PTS trk[sp] = s11m[p] > trk[sp] ? s11m[p] : trk[sp]; }
-                        else if (P.sgn[sp]) { QO_PTS { const double c = -den2[p]; trk[sp] = c > trk[sp] ? c : trk[sp]; } }
+                        else if (P.neg[sp]) { QO_PTS { const T c = -den2[p]; trk[sp] = c > trk[sp] ? c : trk[sp]; } }
                         else { QO_PTS trk[sp] = den2[p] > trk[sp] ? den2[p] : trk[sp]; }
                     }
                 }
@@ -385,10 +412,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((any >> sp) & 1u) {
                         QO_PTS {
-                            const double val = (NROWS == 2 && P.is_s11[sp]) ? s11m[p] : den2[p];
-                            const unsigned int hi = (unsigned int)__double2hiint(val);
-                            const unsigned int chi = ((mk[p] >> sp) & 1u) ? (hi ^ P.sgn[sp]) : QO_LAD_NEG_HUGE_HI;
-                            const double cand = __hiloint2double((int)chi, __double2loint(val));
+                            const T val = (NROWS == 2 && P.is_s11[sp]) ? s11m[p] : (P.neg[sp] ? -den2[p] : den2[p]);
+                            const T cand = ((mk[p] >> sp) & 1u) ? val : LadNum<T>::neg_huge();
                             trk[sp] = cand > trk[sp] ? cand : trk[sp];
                         }
                     }
@@ -403,10 +428,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
             if (sp < P.nspec) {
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) {
-                    const double o = __shfl_xor_sync(0xffffffffu, trk[sp], off);
+                    const T o = __shfl_xor_sync(0xffffffffu, trk[sp], off);
                     trk[sp] = o > trk[sp] ? o : trk[sp];
                 }
-                if (trk[sp] > P.thr[sp]) fail |= 1u << sp;
+                if ((double)trk[sp] > P.thr[sp]) fail |= 1u << sp;
             }
         }
         if (lane == 0) {
@@ -415,9 +440,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
             for (int sp = 0; sp < P.nspec; sp++)
                 if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
             if (P.hist_spec >= 0) {
-                double worst = 0.0;      /* |den|^2 extreme of the histogram spec's band */
+                double worst = 0.0;      /* |den|^2 (or |S11|^2) extreme of the histogram spec's band */
 #pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) if (sp == P.hist_spec) worst = fabs(trk[sp]);
+                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) if (sp == P.hist_spec) worst = fabs((double)trk[sp]);
                 const double k21 = P.k21;
                 const double lin = P.hist_kind == SK_S11_MAX ? worst : P.hist_kind == SK_DEN2_MAX ? k21 * k21 / worst : k21 * k21 * (1.0 / worst);
                 const double v = 10.0 * log10(lin);

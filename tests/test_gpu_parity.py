@@ -376,7 +376,8 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()         # group delay: interpreter
     p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
     p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode
-    p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()
+    p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                       # optional FP32 mode
+    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], precision=32); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()
     w1 = W.cfg1()
     p = Q.Plan(ctx, w1.net, w1.f, [(Q.SPEC_S21_MIN_DB, 3.5e8, 4.5e8, -1.0)], seed=1, tols=Q.lc_tolerances(w1.net, 0.05, 0.05))
     assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                                      # LC-tank branches
@@ -535,3 +536,26 @@ def test_group_delay_spec_in_kernel(Q, R, W, ctx):
         assert 0 < got["fail_per_spec"][hs] < 500 and int(got["hist"].sum()) == 500 and np.count_nonzero(got["hist"]) > 3
     with pytest.raises(Q.QoError):
         ctx.mc_run(w.net, f, [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 3, 10, w.tols, precision=32)
+
+
+def test_fp32_ladder_mode_within_1e_3_db(Q, W, ctx, monkeypatch):
+    """north_star's optional FP32 mode on the straight-line ladder kernel: the per-sample worst pass-band |S21|
+    stays within 1e-3 dB of the FP64 result (earth-mover distance between 4096-bin histograms over 4 dB, i.e.
+    bins of 0.001 dB) and the yield moves by less than the borderline population; the FP32 interpreter agrees."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    n = 30000
+    for w in (W.cfg2(), W.cfg5()):
+        lo, hi = (-4.0, 0.0) if w.name.startswith("cfg2") else (-3.0, 0.0)
+        hist = dict(w.hist, hist_bins=1024, hist_lo=lo, hist_hi=hi)
+        r64 = ctx.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, **hist)
+        r32 = ctx.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, precision=32, **hist)
+        assert r32["n_total"] == n and int(r32["hist"].sum()) == n
+        binw = (hi - lo) / 1024
+        emd = float(np.sum(np.abs(np.cumsum(r64["hist"].astype(np.int64) - r32["hist"].astype(np.int64)))) * binw / n)
+        assert emd < 1e-3, emd
+        assert abs(r32["n_pass"] - r64["n_pass"]) <= 0.002 * n
+        monkeypatch.setenv("QO100NET_KERNEL", "interp")
+        i32 = ctx.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, precision=32, **hist)
+        monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        emd_i = float(np.sum(np.abs(np.cumsum(i32["hist"].astype(np.int64) - r32["hist"].astype(np.int64)))) * binw / n)
+        assert emd_i < 1e-3 and abs(i32["n_pass"] - r32["n_pass"]) <= 0.002 * n

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--workloads", default="cfg2,cfg5")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--s11", action="store_true", help="add an |S11| spec (exercises the second row vector)")
+    ap.add_argument("--fp32", action="store_true", help="optional FP32 mode")
     args = ap.parse_args()
     import torch
     import qo100net as Q
@@ -44,7 +45,7 @@ def main():
         def run(kernel, variant):
             os.environ["QO100NET_KERNEL"] = kernel
             os.environ["QO100NET_LAD_VARIANT"] = str(variant)
-            plan = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, **wl.hist)
+            plan = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, precision=32 if args.fp32 else 64, **wl.hist)
             cnt = torch.zeros(plan.num_counters, dtype=torch.int64, device="cuda")
             with torch.cuda.stream(stream):
                 plan.launch(0, n, cnt.data_ptr())

@@ -56,10 +56,11 @@ def main():
         if "qo_mc_ladder_kernel" not in name:
             continue
         dn = demangle(name)
-        m = re.search(r"<(\d+), (\d+), \(?(?:bool\))?(\w+), (\d+), (\d+), (\d+), (\d+)>", dn)
+        m = re.search(r"<(double|float), (\d+), (\d+), \(?(?:bool\))?(\w+), (\d+), (\d+), (\d+), (\d+)>", dn)
         if not m:
             continue
-        n, first, cpl, nrows, pp = int(m.group(1)), int(m.group(2)), m.group(3) in ("1", "true"), int(m.group(4)), int(m.group(5))
+        fp32 = m.group(1) == "float"
+        n, first, cpl, nrows, pp = int(m.group(2)), int(m.group(3)), m.group(4) in ("1", "true"), int(m.group(5)), int(m.group(6))
         # the frequency loop = the loop with the most FP64 instructions that contains no other loop with FP64 work
         best = None
         ls = loops(ins)
@@ -76,6 +77,8 @@ def main():
         # DSETP and the trackers' selects are counted statically for all four spec slots of both the uniform
         # and the edge path; per point the uniform path executes one DSETP per ACTIVE spec
         fp_core = (c["DFMA"] + c["DMUL"] + c["DADD"]) / pts
+        if fp32:
+            continue        # the census counts FP64-pipe instructions; the FP32 mode runs on the FMA pipe
         res["n%d_first%d_cpl%d%s" % (n, first, int(cpl), "_s11" if nrows == 2 else "")] = {
             "kernel": dn, "points_per_thread_iteration": pts, "loop_sass_instructions": sum(c.values()),
             "dfma_per_eval": c["DFMA"] / pts, "dmul_per_eval": c["DMUL"] / pts, "dadd_per_eval_static": c["DADD"] / pts,

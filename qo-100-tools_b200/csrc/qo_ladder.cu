@@ -50,10 +50,8 @@ template <int PP, int TPB, int MINB> static lad_fn lad_pick11(int n, int first, 
 #define QO_LAD2_TPB 256
 #define QO_LAD2_MINB 2
 
-/* FP32 mode: four points per thread, three blocks per SM */
-#define QO_LAD32_PP 2
-#define QO_LAD32_TPB 256
-#define QO_LAD32_MINB 3
+typedef void (*lad_fn_t)(const LadParams);
+extern "C" lad_fn_t qo_ladder_pick32(int n, int first, int cpl, int *tpb, int *minb);
 
 extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int precision, int variant, int sm_count, const LadParams *P,
                                 cudaStream_t st, const char **shape)
@@ -78,8 +76,8 @@ extern "C" int qo_ladder_launch(int n, int first, int cpl, int nrows, int precis
 #endif
     if (precision == 32) {
         if (nrows != 1) return -1;
-        fn = lad_pick<float, 1, QO_LAD32_PP, QO_LAD32_TPB, QO_LAD32_MINB>(n, first, cpl);
-        tpb = QO_LAD32_TPB; minb = QO_LAD32_MINB; name = "fp32";
+        fn = qo_ladder_pick32(n, first, cpl, &tpb, &minb);      /* qo_ladder32.cu */
+        name = "fp32";
     } else if (nrows == 2) {
         fn = lad_pick<double, 2, QO_LAD2_PP, QO_LAD2_TPB, QO_LAD2_MINB>(n, first, cpl);
         tpb = QO_LAD2_TPB; minb = QO_LAD2_MINB; name = "s11";

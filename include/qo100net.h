@@ -62,8 +62,15 @@ typedef enum {
     QO_MTEE = 16,                            /* p0 = Wa, p1 = Wb, p2 = W2; opens the side arm:
                                                 the following elements, junction outward, up to */
     QO_MOPEN = 17,                           /* p0 = W; open end closing the side arm    */
-    QO_SBLOCK = 18                           /* measured two-port (Touchstone): p0 = block index in the net,
+    QO_SBLOCK = 18,                          /* measured two-port (Touchstone): p0 = block index in the net,
                                                 p1 = 1 polar / 0 rectangular interpolation (Qucs SPfile)   */
+    QO_CPL_MS = 19                           /* PHYSICAL coupled microstrip, through path (far ports in Zt), on the
+                                                preceding QO_SUBST (er, h, t): p0=W p1=S p2=L p3=H_t (cover height)
+                                                p4=f0 (analysis frequency, as QucsTranscalc "Freq") p5=Zt.  Per
+                                                sample the geometry / substrate draws go through the coupled-
+                                                microstrip analysis (qo_cpl_analyze's model) to Z0e, Z0o, theta_e,
+                                                theta_o, then the ideal coupled-line block: util/directional-
+                                                couplers/ *.trc:6-20 with manufacturing tolerances on W, S, H, Er */
 } qo_kind;
 #define QO_NPARAM 6
 typedef struct { int32_t kind; int32_t flags; double p[QO_NPARAM]; } qo_elem;

@@ -578,6 +578,13 @@ static int eval_abcd_det(const ref_elem *e, int n, double f, m22 *out, cx *det_o
             break;
         }
         case REF_CPL_THRU: M = m_mul(M, cpl_thru(p[0], p[1], p[2], p[3], p[4], p[5], f)); break;
+        case REF_CPL_MS: {        /* physical coupled microstrip on the current substrate: QucsTranscalc analysis, then B.4 */
+            if (!have_sub) return -4;
+            double z0e, z0o, ae, ao;
+            ref_cpl_analyze(p[0], p[1], sub.h, sub.t, sub.er, p[3], p[4], p[2], &z0e, &z0o, &ae, &ao);
+            M = m_mul(M, cpl_thru(z0e, z0o, ae, ao, p[4], p[5], f));
+            break;
+        }
         case REF_SBLOCK: {
             m22 B;
             cx bd;

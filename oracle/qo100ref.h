@@ -50,7 +50,9 @@ enum {
     REF_MCORN = 15,                        /* p0=W */
     REF_MTEE = 16,                         /* p0=Wa p1=Wb p2=W2 ; opens the side arm */
     REF_MOPEN = 17,                        /* p0=W ; closes the side arm */
-    REF_SBLOCK = 18                        /* measured two-port: p0 = registered block index, p1 = 1 polar / 0 rectangular */
+    REF_SBLOCK = 18,                       /* measured two-port: p0 = registered block index, p1 = 1 polar / 0 rectangular */
+    REF_CPL_MS = 19                        /* physical coupled microstrip through path on the preceding REF_SUBST:
+                                              p0=W p1=S p2=L p3=H_t p4=f0 p5=Zt (util/directional-couplers/ *.trc:6-20) */
 };
 
 typedef struct { int32_t kind; int32_t flags; double p[6]; } ref_elem;

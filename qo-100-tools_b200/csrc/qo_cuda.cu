@@ -19,6 +19,7 @@
 #include "qo_ladder.cuh"
 #include "qo_ladder_launch.h"
 #include "qo_ustrip.cuh"
+#include "qo_cpl_core.h"
 
 static int nccl_load(NcclApi *a)
 {
@@ -203,6 +204,8 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
     if (net->n > QO_MAX_OPS) { qo_set_error("network has %d elements, limit %d", net->n, QO_MAX_OPS); return QO_ERR_RANGE; }
     if (nspec < 0 || nspec > QO_NSPEC_MAX) { qo_set_error("at most %d specs", QO_NSPEC_MAX); return QO_ERR_RANGE; }
     hp->n_ops = net->n;
+    hp->cplms_elem = hp->cplms_sub = -1;
+    int last_sub = -1;
     hp->rs = net->rs; hp->rl = net->rl; hp->rsrl = net->rs * net->rl; hp->k21 = 2.0 * sqrt(net->rs * net->rl);
     hp->seed = cfg ? cfg->seed : 0;
     hp->dist = cfg ? cfg->dist : 0;
@@ -232,7 +235,15 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
             op = OP_SBLOCK; nco = 1; trig = 1;
             if (el->p[0] < 0 || el->p[0] >= net->nblk) { qo_set_error("element %d: S-parameter block %g is not in the net", e, el->p[0]); return QO_ERR_ARG; }
             break;
-        case QO_SUBST: op = OP_SUBST; ustrip = 1; break;
+        case QO_SUBST: op = OP_SUBST; last_sub = e; break;        /* a substrate alone does not make the network microstrip */
+        case QO_CPL_MS:
+            /* physical coupled line: compiled to the coupled-line opcode; its electrical parameters come per sample
+             * from the pre-pass (qo_cplms_kernel) */
+            if (last_sub < 0) { qo_set_error("element %d: QO_CPL_MS needs a preceding QO_SUBST", e); return QO_ERR_ARG; }
+            if (hp->cplms_elem >= 0) { qo_set_error("element %d: at most one QO_CPL_MS per network", e); return QO_ERR_UNSUPPORTED; }
+            op = OP_CPL; nco = 8; trig = 1;
+            hp->cplms_elem = e; hp->cplms_sub = last_sub;
+            break;
         case QO_MLIN: op = OP_MLIN; ustrip = 1; break;
         case QO_MCORN: op = OP_MCORN; ustrip = 1; break;
         case QO_MTEE: op = OP_MTEE; ustrip = 1; break;
@@ -248,6 +259,16 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
     hp->n_coef = coff;
     hp->has_trig = trig;
     hp->has_ustrip = ustrip;
+    if (hp->cplms_elem >= 0) {
+        if (ustrip) { qo_set_error("QO_CPL_MS cannot be mixed with MLIN/MCORN/MTEE/MOPEN elements yet"); return QO_ERR_UNSUPPORTED; }
+        const qo_elem *c = &net->e[hp->cplms_elem], *sb = &net->e[hp->cplms_sub];
+        qo_cpl_core(c->p[0], c->p[1], sb->p[1], sb->p[2], sb->p[0], c->p[3], c->p[4], c->p[2], hp->cplms_nom);
+        if (!isfinite(hp->cplms_nom[0]) || !isfinite(hp->cplms_nom[1])) { qo_set_error("QO_CPL_MS: geometry outside the analysis model's range"); return QO_ERR_RANGE; }
+    }
+    if (!ustrip)            /* substrates that only serve a QO_CPL_MS take no part in the chain */
+        for (int e = 0; e < net->n; e++) if (hp->opcode[e] == OP_SUBST) hp->opcode[e] = OP_NOP;
+    hp->op0 = 0;
+    while (hp->op0 < net->n - 1 && hp->opcode[hp->op0] == OP_NOP) hp->op0++;
     *generic = ustrip;
     *flops = ustrip ? 0.0 : fl;
 
@@ -313,9 +334,9 @@ static int ladder_eligible(const DevProg *hp, int mode, int precision, int gener
     if (hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) return 0;
     for (int s = 0; s < hp->nspec; s++)
         if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) return 0;
-    int e0 = 0;
+    int e0 = hp->op0;
     *cpl = 0;
-    if (hp->n_ops > 0 && hp->opcode[0] == OP_CPL) { *cpl = 1; e0 = 1; }
+    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { *cpl = 1; e0++; }
     const int nl = hp->n_ops - e0;
     if (nl < 1 || nl > QO_LAD_MAXN) return 0;
     const int op0 = hp->opcode[e0];
@@ -428,34 +449,63 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
             if (net->e[e].kind == QO_SBLOCK) { qo_set_error("S-parameter blocks cannot be mixed with microstrip elements yet"); delete p; return QO_ERR_UNSUPPORTED; }
     }
     /* coupler block of the ladder kernel: sin/cos of the NOMINAL mode angles per grid point, usable when
-     * every sample's angle stays within 0.05 rad of nominal over the whole grid (qo_ladder.cuh::lad_cpl_first) */
+     * every sample's angle stays within 0.1 rad of nominal over the whole grid (qo_ladder.cuh::lad_cpl_first) */
     std::vector<double> ctab[4];
     std::vector<float> ctabf[4];
     p->cpl_fast = p->cpl_same = 0;
     if (p->ladder && p->lad_cpl) {
         const DevProg *hp = &p->hp;
-        double lo[6], hi[6];
-        for (int k = 0; k < 6; k++) {
-            const double nomv = hp->nom[0][k], t = hp->tvar[0][k] >= 0 ? fabs(hp->ttol[0][k]) : 0.0;
-            const double dlt = hp->tmode[0][k] ? t : fabs(nomv) * t;
-            lo[k] = nomv - dlt; hi[k] = nomv + dlt;
-        }
+        const int ec = hp->op0;                    /* the coupler op */
         double wmax = 0;
         for (int k = 0; k < 2 * np; k++) if (w[k] > wmax) wmax = w[k];
-        double worst = 0;
-        int ok = lo[4] > 0;
-        for (int m = 0; m < 2 && ok; m++) {
-            const double kn = hp->nom[0][2 + m] / (360.0 * hp->nom[0][4]);
-            const double kmax = hi[2 + m] / (360.0 * lo[4]), kmin = lo[2 + m] / (360.0 * hi[4]);
-            const double dk = fmax(kmax - kn, kn - kmin);
-            if (dk * wmax > worst) worst = dk * wmax;
+        double worst = 0, ke_nom, ko_nom;
+        int ok = 1;
+        if (hp->cplms_elem == ec) {
+            /* physical element: bound the mode angles' excursion by running the analysis at every corner of the
+             * tolerance box of the parameters it reads (<= 7 of them), plus 25 % margin for the interior */
+            ke_nom = hp->cplms_nom[2] / (360.0 * hp->nom[ec][4]); ko_nom = hp->cplms_nom[3] / (360.0 * hp->nom[ec][4]);
+            const int es = hp->cplms_sub;
+            const int pe[7] = { ec, ec, es, es, es, ec, ec }, pk[7] = { 0, 1, 1, 2, 0, 3, 2 };      /* W S h t er ht L */
+            double lo[7], hi[7];
+            for (int q = 0; q < 7; q++) {
+                const double nomv = hp->nom[pe[q]][pk[q]], t = hp->tvar[pe[q]][pk[q]] >= 0 ? fabs(hp->ttol[pe[q]][pk[q]]) : 0.0;
+                const double dlt = hp->tmode[pe[q]][pk[q]] ? t : fabs(nomv) * t;
+                lo[q] = nomv - dlt; hi[q] = nomv + dlt;
+            }
+            ok = !(hp->tvar[ec][4] >= 0);          /* a perturbed analysis frequency: not bounded here */
+            for (int c = 0; c < 128 && ok; c++) {
+                double v[7], o[4];
+                for (int q = 0; q < 7; q++) v[q] = (c >> q) & 1 ? hi[q] : lo[q];
+                if (!(v[0] > 0 && v[1] > 0 && v[2] > 0 && v[3] >= 0 && v[4] > 1 && v[5] > 0 && v[6] > 0)) { ok = 0; break; }
+                qo_cpl_core(v[0], v[1], v[2], v[3], v[4], v[5], hp->nom[ec][4], v[6], o);
+                const double de = fabs(o[2] / (360.0 * hp->nom[ec][4]) - ke_nom), dn = fabs(o[3] / (360.0 * hp->nom[ec][4]) - ko_nom);
+                if (!(de == de) || !(dn == dn)) { ok = 0; break; }
+                if (1.25 * de * wmax > worst) worst = 1.25 * de * wmax;
+                if (1.25 * dn * wmax > worst) worst = 1.25 * dn * wmax;
+            }
+            p->cpl_same = 0;
+        } else {
+            double lo[6], hi[6];
+            for (int k = 0; k < 6; k++) {
+                const double nomv = hp->nom[ec][k], t = hp->tvar[ec][k] >= 0 ? fabs(hp->ttol[ec][k]) : 0.0;
+                const double dlt = hp->tmode[ec][k] ? t : fabs(nomv) * t;
+                lo[k] = nomv - dlt; hi[k] = nomv + dlt;
+            }
+            ok = lo[4] > 0;
+            for (int m = 0; m < 2 && ok; m++) {
+                const double kn = hp->nom[ec][2 + m] / (360.0 * hp->nom[ec][4]);
+                const double kmax = hi[2 + m] / (360.0 * lo[4]), kmin = lo[2 + m] / (360.0 * hi[4]);
+                const double dk = fmax(kmax - kn, kn - kmin);
+                if (dk * wmax > worst) worst = dk * wmax;
+            }
+            ke_nom = hp->nom[ec][2] / (360.0 * hp->nom[ec][4]); ko_nom = hp->nom[ec][3] / (360.0 * hp->nom[ec][4]);
+            p->cpl_same = hp->nom[ec][2] == hp->nom[ec][3] && hp->tvar[ec][2] == hp->tvar[ec][3] && hp->ttol[ec][2] == hp->ttol[ec][3] &&
+                          hp->tmode[ec][2] == hp->tmode[ec][3];
         }
-        p->cpl_fast = ok && worst <= 0.05 && !getenv("QO100NET_CPL_SINCOS");
-        p->cpl_same = hp->nom[0][2] == hp->nom[0][3] && hp->tvar[0][2] == hp->tvar[0][3] && hp->ttol[0][2] == hp->ttol[0][3] &&
-                      hp->tmode[0][2] == hp->tmode[0][3];
+        p->cpl_fast = ok && worst <= 0.1 && !getenv("QO100NET_CPL_SINCOS");
         if (p->cpl_fast) {
             for (int t = 0; t < 4; t++) ctab[t].resize(2 * (size_t)np);
-            const double ke = hp->nom[0][2] / (360.0 * hp->nom[0][4]), ko = hp->nom[0][3] / (360.0 * hp->nom[0][4]);
+            const double ke = ke_nom, ko = ko_nom;
             for (int k = 0; k < 2 * np; k++) {
                 ctab[0][k] = sin(ke * w[k]); ctab[1][k] = cos(ke * w[k]);
                 ctab[2][k] = sin(ko * w[k]); ctab[3][k] = cos(ko * w[k]);
@@ -533,6 +583,30 @@ extern "C" int qo_plan_reset(qo_plan *p)
     return QO_OK;
 }
 
+/* Pre-pass of the physical coupled-line element: one thread per sample turns that sample's geometry / substrate
+ * draws (same Philox stream, same variables as every other kernel) into Z0e, Z0o, theta_e, theta_o with the
+ * coupled-microstrip analysis (qo_cpl_core.h) -- ~150 pow/exp/log per SAMPLE, done here at full lane
+ * efficiency instead of by one lane of the warp that owns the sample. */
+__global__ void qo_cplms_kernel(const DevProg *__restrict__ prog, unsigned long long sample_offset, unsigned long long n, double *__restrict__ out)
+{
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int ec = prog->cplms_elem, es = prog->cplms_sub;
+    double pc[6], ps[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        pc[k] = prog->nom[ec][k];
+        int tv = prog->tvar[ec][k];
+        if (tv >= 0) pc[k] = qo_stream_apply(pc[k], prog->ttol[ec][k], qo_stream_variate(prog->seed, sample_offset + i, (uint32_t)tv, prog->dist), prog->tmode[ec][k]);
+        ps[k] = prog->nom[es][k];
+        tv = prog->tvar[es][k];
+        if (tv >= 0) ps[k] = qo_stream_apply(ps[k], prog->ttol[es][k], qo_stream_variate(prog->seed, sample_offset + i, (uint32_t)tv, prog->dist), prog->tmode[es][k]);
+    }
+    double o[4];
+    qo_cpl_core(pc[0], pc[1], ps[1], ps[2], ps[0], pc[3], pc[4], pc[2], o);
+    out[4 * i + 0] = o[0]; out[4 * i + 1] = o[1]; out[4 * i + 2] = o[2]; out[4 * i + 3] = o[3];
+}
+
 template <typename T>
 static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
 {
@@ -566,7 +640,7 @@ static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned lon
     return QO_OK;
 }
 
-static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt)
+static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, const double *cplms)
 {
     DevCtx *dc = &p->ctx->d[g];
     DevPlan *d = &p->d[g];
@@ -578,6 +652,7 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     P.counters = cnt;
     P.cse = d->cpl_tab[0]; P.cce = d->cpl_tab[1]; P.cso = d->cpl_tab[2]; P.cco = d->cpl_tab[3];
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same;
+    P.cplms = cplms; P.op0 = hp->op0;
     P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
     P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
@@ -627,7 +702,16 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     if (n == 0) return QO_OK;
     CU(cudaSetDevice(p->ctx->d[g].device));
     int full_s = p->mode == QO_MODE_FULL_S;
-    QoPlanes pl = { NULL, NULL, NULL, NULL, p->d[g].sblk, p->d[g].sdet, 2 * p->npairs };
+    QoPlanes pl = { NULL, NULL, NULL, NULL, p->d[g].sblk, p->d[g].sdet, 2 * p->npairs, NULL };
+    double *cplms = NULL;
+    if (p->hp.cplms_elem >= 0) {
+        DevCtx *dc = &p->ctx->d[g];
+        CU(cudaMallocAsync((void **)&cplms, (size_t)n * 4 * sizeof(double), dc->stream));
+        qo_cplms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, dc->stream>>>(p->d[g].prog, off, n, cplms);
+        CU(cudaGetLastError());
+        pl.cplms = cplms;
+        p->launches++;
+    }
     if (full_s) {
         if (!full_s_dev) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
         size_t plane = (size_t)plane_samples * (size_t)p->nf;
@@ -636,9 +720,10 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     }
     int rc;
     if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
-    else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt);
+    else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt, cplms);
     else if (p->precision == 32) rc = launch_lumped<float>(p, g, off, n, cnt, pl, full_s);
     else rc = launch_lumped<double>(p, g, off, n, cnt, pl, full_s);
+    if (cplms) cudaFreeAsync(cplms, p->ctx->d[g].stream);
     if (rc == QO_OK) { p->launches++; p->d[g].n_launched += n; }
     return rc;
 }

@@ -161,9 +161,9 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const T (&w)[
  * |den|^2 is rescaled by 1/|k|^2 at the end (one batched real reciprocal instead of three complex divides).
  * record = { z_e + 1/z_e, (z_e - 1/z_e)/2, (odd: same two), te/w, to/w, Zt, Rs/Zt, te/w - nominal, to/w - nominal }
  *
- * Angles: t_m = k_m w.  When the plan could bound the perturbation |k_m - k_m,nominal| w_max <= 0.05 rad
+ * Angles: t_m = k_m w.  When the plan could bound the perturbation |k_m - k_m,nominal| w_max <= 0.1 rad
  * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
- * short Taylor polynomials (|d|^10/10! < 3e-20, |d|^9/9! < 6e-18) -- 14 FP64 instructions instead of the ~30 of
+ * short Taylor polynomials (truncation |d|^10/10! < 3e-17 on cos, |d|^9/9! < 3e-15 on sin) -- 14 FP64 instructions instead of the ~30 of
  * a general sincos; otherwise sincos() is called. */
 template <typename T, int PTS, int NROWS, bool FAST>
 __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
@@ -223,7 +223,8 @@ __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS]
 /* per-sample coefficient records, one lane per element (perturbation is the shared bit-exact stream; the
  * derived coefficients are formed in FP64 and rounded once when T = float) */
 template <typename T>
-__device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out)
+__device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out,
+                                           const double *__restrict__ cplms, double *nom_k)
 {
     double p[6];
 #pragma unroll
@@ -231,6 +232,12 @@ __device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int
         p[k] = prog->nom[e][k];
         const int tv = prog->tvar[e][k];
         if (tv >= 0) p[k] = qo_stream_apply(p[k], prog->ttol[e][k], x[tv], prog->tmode[e][k]);
+    }
+    nom_k[0] = prog->nom[e][2] / (360.0 * prog->nom[e][4]); nom_k[1] = prog->nom[e][3] / (360.0 * prog->nom[e][4]);
+    if (e == prog->cplms_elem) {
+        /* physical coupled line: p[] holds (W, S, L, H_t, f0, Zt); this sample's electrical view comes from the pre-pass */
+        p[0] = cplms[0]; p[1] = cplms[1]; p[2] = cplms[2]; p[3] = cplms[3]; p[4] = prog->nom[e][4]; p[5] = prog->nom[e][5];
+        nom_k[0] = prog->cplms_nom[2] / (360.0 * p[4]); nom_k[1] = prog->cplms_nom[3] / (360.0 * p[4]);
     }
     switch (prog->opcode[e]) {
     case OP_SER_LOSSY_L: case OP_SER_L: {              /* p = L, R, Cp */
@@ -246,7 +253,7 @@ __device__ __forceinline__ void lad_derive(const DevProg *__restrict__ prog, int
         const double ke = p[2] / (360.0 * p[4]), ko = p[3] / (360.0 * p[4]);
         out[0] = T(a + 1.0 / a); out[1] = T(0.5 * (a - 1.0 / a)); out[2] = T(b + 1.0 / b); out[3] = T(0.5 * (b - 1.0 / b));
         out[4] = T(ke); out[5] = T(ko); out[6] = T(p[5]); out[7] = T(prog->rs / p[5]);
-        out[8] = T(ke - prog->nom[e][2] / (360.0 * prog->nom[e][4])); out[9] = T(ko - prog->nom[e][3] / (360.0 * prog->nom[e][4]));
+        out[8] = T(ke - nom_k[0]); out[9] = T(ko - nom_k[1]);
         break;
     }
     default: break;
@@ -269,6 +276,8 @@ struct LadParams {
     int is_s11[QO_LAD_NSPEC];                /* the spec's tracker holds |S11|^2 = |n11|^2 / |den|^2 (NROWS == 2 kernels) */
     int npairs, n_var, n_ops, nspec, dist, hist_spec, hist_bins, hist_kind;
     int cpl_fast, cpl_same;                  /* small-angle table path usable; nominal even and odd angles identical */
+    int op0;                                 /* first op of the chain (leading OP_NOPs: a substrate that only serves a QO_CPL_MS) */
+    const double *cplms;                     /* physical coupled line: per-sample Z0e, Z0o, theta_e, theta_o (pre-pass) */
 };
 
 /*
@@ -314,9 +323,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_ladder_kernel(const __grid_co
         /* 1. the sample's random variables (Philox, counter-based) and coefficient records */
         for (int v = lane; v < P.n_var; v += 32) xw[v] = qo_stream_variate(P.seed, P.sample_offset + s, (uint32_t)v, P.dist);
         __syncwarp();
-        if (lane < P.n_ops) {
+        if (lane + P.op0 < P.n_ops) {
             const int rec = CPL ? (lane == 0 ? 0 : QO_LAD_CPL + (lane - 1) * QO_LAD_STRIDE) : lane * QO_LAD_STRIDE;
-            lad_derive<T>(P.prog, lane, xw, coefw + rec);
+            double nom_k[2];
+            lad_derive<T>(P.prog, lane + P.op0, xw, coefw + rec, P.cplms ? P.cplms + 4 * s : NULL, nom_k);
         }
         __syncwarp();
 

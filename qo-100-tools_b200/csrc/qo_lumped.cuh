@@ -100,6 +100,7 @@ struct QoPlanes {
      * blocks' determinants per grid point (NULL when every block is reciprocal) */
     const double2 *sblk, *sdet;
     int npts;
+    const double *cplms;        /* physical coupled-line element: per-sample Z0e, Z0o, theta_e, theta_o from the pre-pass */
 };
 
 template <typename T, bool TRIG>
@@ -217,7 +218,8 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
 
 /* ---- per-sample coefficient derivation (one lane per element) ------------- */
 template <typename T>
-__device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out)
+__device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, T *out,
+                                          const double *__restrict__ cplms)
 {
     double p[6];
 #pragma unroll
@@ -225,6 +227,11 @@ __device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int 
         p[k] = prog->nom[e][k];
         int tv = prog->tvar[e][k];
         if (tv >= 0) p[k] = qo_stream_apply(p[k], prog->ttol[e][k], x[tv], prog->tmode[e][k]);
+    }
+    if (e == prog->cplms_elem) {
+        /* physical coupled line: p[] holds (W, S, L, H_t, f0, Zt); the electrical view of THIS sample was computed by
+         * the pre-pass from the same draws */
+        p[0] = cplms[0]; p[1] = cplms[1]; p[2] = cplms[2]; p[3] = cplms[3]; p[4] = prog->nom[e][4]; p[5] = prog->nom[e][5];
     }
     switch (prog->opcode[e]) {
     case OP_SER_R: out[0] = T(p[0]); break;
@@ -304,7 +311,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
         for (int v = lane; v < n_var; v += 32) xw[v] = qo_stream_variate(seed, sample_offset + s, (uint32_t)v, dist);
         __syncwarp();
         /* 2. perturbed + hoisted element coefficients -> shared table */
-        for (int e = lane; e < n_ops; e += 32) qo_derive<T>(prog, e, xw, coefw + s_coff[e]);
+        for (int e = lane; e < n_ops; e += 32) qo_derive<T>(prog, e, xw, coefw + s_coff[e], planes.cplms ? planes.cplms + 4 * s : NULL);
         __syncwarp();
 
         /* 3. frequency loop: two points per lane per iteration */

@@ -140,7 +140,7 @@ void qo_net_free(qo_net *net)
 
 /* QO_SBLOCK elements enter a network only through qo_net_from_sblock / qo_net_concat (they carry an index
  * into the net's own block list), never through a raw element list */
-static int kind_ok(int k) { return k >= QO_SER_R && k <= QO_MOPEN; }
+static int kind_ok(int k) { return (k >= QO_SER_R && k <= QO_MOPEN) || k == QO_CPL_MS; }
 
 int qo_net_from_sblock(const qo_s2p *blk, int polar, double rs, double rl, qo_net **out)
 {
@@ -165,11 +165,15 @@ int qo_net_from_elements(const qo_elem *e, int n, double rs, double rl, qo_net *
     qo_clear_error();
     if (!e || !out || n <= 0 || !(rs > 0) || !(rl > 0)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
     if (n > QO_MAX_ELEMS) { qo_set_error("too many elements (%d > %d)", n, QO_MAX_ELEMS); return QO_ERR_RANGE; }
-    int side = 0, have_sub = 0;
+    int side = 0, have_sub = 0, n_cplms = 0;
     for (int i = 0; i < n; i++) {
         if (!kind_ok(e[i].kind)) { qo_set_error("element %d: unknown kind %d", i, e[i].kind); return QO_ERR_UNSUPPORTED; }
         if (e[i].kind == QO_SUBST) have_sub = 1;
         if (e[i].kind >= QO_MLIN && !have_sub) { qo_set_error("element %d: microstrip element before any SUBST", i); return QO_ERR_ARG; }
+        if (e[i].kind == QO_CPL_MS) {
+            if (++n_cplms > 1) { qo_set_error("element %d: at most one physical coupled-line element per network", i); return QO_ERR_UNSUPPORTED; }
+            if (!(e[i].p[0] > 0 && e[i].p[1] > 0 && e[i].p[2] > 0 && e[i].p[3] > 0 && e[i].p[4] > 0 && e[i].p[5] > 0)) { qo_set_error("element %d: QO_CPL_MS needs W, S, L, H_t, f0, Zt > 0", i); return QO_ERR_ARG; }
+        }
         if (e[i].kind == QO_MTEE) { if (side) { qo_set_error("element %d: nested MTEE", i); return QO_ERR_UNSUPPORTED; } side = 1; }
         if (e[i].kind == QO_MOPEN) { if (!side) { qo_set_error("element %d: MOPEN outside a tee side arm", i); return QO_ERR_UNSUPPORTED; } side = 0; }
     }

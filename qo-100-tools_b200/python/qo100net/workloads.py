@@ -6,7 +6,7 @@ they can equally be loaded with Net.from_rftools_svg -- tests check both give th
 """
 import numpy as np
 
-from . import (CPL_THRU, MCORN, MLIN, MOPEN, MTEE, SER_L, SER_LC_SER, SHUNT_C, SHUNT_LC_PAR, SHUNT_LC_SER,
+from . import (CPL_MS, CPL_THRU, MCORN, MLIN, MOPEN, MTEE, SER_L, SER_LC_SER, SHUNT_C, SHUNT_LC_PAR, SHUNT_LC_SER,
                SPEC_S21_MAX_DB, SPEC_S21_MIN_DB, SUBST, TOL_ABS, TOL_REL, Net, grid_lin, grid_log, lc_tolerances)
 
 
@@ -114,4 +114,23 @@ def cfg5(n_samples=100000000, nf=4096):
     k24 = int(np.argmin(np.abs(f - 2.4e9)))
     specs.append((SPEC_S21_MIN_DB, f[k24], f[k24], -1e9))     # histogram variable: |S21| dB at the grid point nearest 2.4 GHz
     return Workload("cfg5-coupler+cheby11-1e8x4096", net, f, specs, tols,
+                    dict(hist_bins=256, hist_spec=2, hist_lo=-3.0, hist_hi=0.0), n_samples, seed_for(5))
+
+
+def cfg5p(n_samples=100000000, nf=4096):
+    """Config 5 with the coupler described PHYSICALLY: the 2.4 GHz 20 dB coupled microstrip of
+    util/directional-couplers/dir_cpl_2.4g_20dB.trc:6-17 (W 1.69218 mm, S 0.991476 mm, L 20 mm on Er 3.5, H 0.762 mm,
+    T 35 um, cover 20 cm, analysed at 2.4 GHz) with manufacturing tolerances -- etch +-0.03 mm on W (and -/+ on S: one
+    draw widens the strips and narrows the gap), H +-5 %, Er +-0.1 -- in front of the cfg-2 ladder at fc = 3 GHz."""
+    sub = (SUBST, [3.5, 0.762e-3, 35e-6, 0.0, 0.0, 0.0])
+    cpl = (CPL_MS, [1.69218e-3, 0.991476e-3, 20e-3, 0.2, 2.4e9, 50.0])
+    lad = cheby11(3e9)
+    net = Net.from_elements([sub, cpl] + lad.elements, 50.0, 50.0)
+    tols = [(1, 0, 0, TOL_ABS, 0.03e-3), (1, 1, 0, TOL_ABS, -0.03e-3), (0, 1, 1, TOL_REL, 0.05), (0, 0, 2, TOL_ABS, 0.1)]
+    tols += [(e + 2, p, v + 3, m, t) for (e, p, v, m, t) in lc_tolerances(lad, 0.05, 0.02)]
+    f = grid_lin(70e6, 4000e6, nf)
+    specs = [(SPEC_S21_MIN_DB, 2.3e9, 2.5e9, -1.4), (SPEC_S21_MAX_DB, 3.9e9, 1e99, -48.0)]
+    k24 = int(np.argmin(np.abs(f - 2.4e9)))
+    specs.append((SPEC_S21_MIN_DB, f[k24], f[k24], -1e9))
+    return Workload("cfg5p-physical-coupler+cheby11", net, f, specs, tols,
                     dict(hist_bins=256, hist_spec=2, hist_lo=-3.0, hist_hi=0.0), n_samples, seed_for(5))

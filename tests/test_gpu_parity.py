@@ -559,3 +559,46 @@ def test_fp32_ladder_mode_within_1e_3_db(Q, W, ctx, monkeypatch):
         monkeypatch.delenv("QO100NET_KERNEL", raising=False)
         emd_i = float(np.sum(np.abs(np.cumsum(i32["hist"].astype(np.int64) - r32["hist"].astype(np.int64)))) * binw / n)
         assert emd_i < 1e-3 and abs(i32["n_pass"] - r32["n_pass"]) <= 0.002 * n
+
+
+def test_physical_coupled_line_element(Q, R, W, ctx, monkeypatch):
+    """SURVEY 8f N1 carried into the hot path: QO_CPL_MS (physical coupled microstrip, util/directional-couplers/
+    dir_cpl_2.4g_20dB.trc:6-17) = coupled-microstrip analysis per sample (device pre-pass) + the ideal coupled-line
+    block.  Nominal: identical to the ideal element fed with the analysis' Z0e/Z0o/theta_e/theta_o and to the
+    oracle; Monte Carlo over W/S (one etch draw), H, Er and the ladder: ladder kernel == interpreter == oracle."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    w = W.cfg5p(0, 1024)
+    (k_sub, p_sub), (k_cpl, p_cpl) = w.net.elements[0], w.net.elements[1]
+    assert k_sub == Q.SUBST and k_cpl == Q.CPL_MS
+    ze, zo, ae, ao = Q.cpl_analyze(p_cpl[0], p_cpl[1], p_sub[1], p_sub[2], p_sub[0], p_cpl[3], p_cpl[4], p_cpl[2])
+    assert abs(ze / 55.2771 - 1) < 5e-6 and abs(zo / 45.2267 - 1) < 5e-6 and abs(np.sqrt(ae * ao) / 95.4225 - 1) < 5e-6   # the .trc values
+    phys = Q.Net.from_elements([(Q.SUBST, p_sub), (Q.CPL_MS, p_cpl)], 50.0, 50.0)
+    ideal = Q.Net.from_elements([(Q.CPL_THRU, [ze, zo, ae, ao, p_cpl[4], p_cpl[5]])], 50.0, 50.0)
+    f = Q.grid_lin(70e6, 4000e6, 400)
+    gp, gi = ctx.sweep(phys, f), ctx.sweep(ideal, f)
+    for a, b in zip(gp, gi):
+        assert np.max(np.abs(a - b)) < 1e-12
+    _s_close(gp, R.sweep(to_ref(R, phys), 50, 50, f))
+    _s_close(ctx.sweep(w.net, w.f), R.sweep(to_ref(R, w.net), 50, 50, w.f))
+    # Monte Carlo
+    n = 1500
+    plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+    assert plan.kernel_name == "qo_mc_ladder_kernel"
+    plan.launch(7, n)
+    got = plan.read()
+    assert plan.launches == 2                      # pre-pass + ladder kernel
+    plan.close()
+    rs, rl = w.net.terminations
+    ref = R.mc_run(to_ref(R, w.net), rs, rl, w.f, w.specs, R.mc_cfg(w.seed, n, w.tols, sample_offset=7, **w.hist), nthreads=8)
+    _assert_counts_equal(ref, got)
+    assert 0 < got["n_pass"] < n and np.count_nonzero(got["hist"]) > 10
+    for env in (("QO100NET_KERNEL", "interp"), ("QO100NET_CPL_SINCOS", "1")):
+        monkeypatch.setenv(*env)
+        alt = ctx.mc_run(w.net, w.f, w.specs, w.seed, n, w.tols, sample_offset=7, **w.hist)
+        monkeypatch.delenv(env[0])
+        _assert_counts_equal(alt, got)
+    gs = ctx.mc_run(w.net, w.f[:200], [], w.seed, 6, w.tols, mode=Q.MODE_FULL_S)["s"]
+    os_ = R.mc_run(to_ref(R, w.net), rs, rl, w.f[:200], [], R.mc_cfg(w.seed, 6, w.tols), full_s=True)["s"]
+    _s_close(gs, os_)
+    # the draws matter: with tolerances the coupler's mid-band |S21| spreads
+    assert np.std(20 * np.log10(np.abs(gs[1][:, 100]))) > 1e-4

@@ -369,3 +369,12 @@ def test_touchstone_loader_interp_and_inductor_fit(Q, golden_s2p, tmp_path):
     assert [(k, p[:2]) for k, p in cat.elements] == [(Q.SBLOCK, [0.0, 1.0]), (Q.SHUNT_C, [2.2e-12, 3.0]), (Q.SBLOCK, [1.0, 0.0])]
     with pytest.raises(Q.QoError):
         Q.Net.from_elements([(Q.SBLOCK, [0.0, 1.0])], 50, 50)
+
+
+def test_physical_coupled_line_element_validation(Q):
+    sub, cpl = (Q.SUBST, [3.5, 0.762e-3, 35e-6, 0, 0, 0]), (Q.CPL_MS, [1.69e-3, 0.99e-3, 20e-3, 0.2, 2.4e9, 50.0])
+    n = Q.Net.from_elements([sub, cpl, (Q.SER_L, [1e-9, 0.1, 0.0])], 50, 50)
+    assert [k for k, _ in n.elements] == [Q.SUBST, Q.CPL_MS, Q.SER_L]
+    for bad in ([cpl], [sub, cpl, cpl], [sub, (Q.CPL_MS, [1.69e-3, -1.0, 20e-3, 0.2, 2.4e9, 50.0])]):
+        with pytest.raises(Q.QoError):
+            Q.Net.from_elements(bad, 50, 50)

@@ -18,6 +18,8 @@
 #include "qo_lumped.cuh"
 #include "qo_ladder.cuh"
 #include "qo_ladder_launch.h"
+#include "qo_tf.cuh"
+#include "qo_tf_launch.h"
 #include "qo_ustrip.cuh"
 #include "qo_cpl_core.h"
 
@@ -41,6 +43,7 @@ struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
     void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
+    double2 *xt;               /* double2 [npairs]: w / wref, transfer-function kernel only */
     double2 *sblk, *sdet;      /* OP_SBLOCK: ABCD per (block, grid point); product of block determinants per point */
     void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
     uchar2 *m2;
@@ -58,6 +61,9 @@ struct qo_plan {
     int nf, npairs, ncnt, precision, mode, generic;
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
+    int tf, tf_K, tf_mode, tf_el0, tf_nel, tf_cpl_op;     /* transfer-function kernel (qo_tf.cuh) */
+    double tf_wref, tf_err;                               /* normalising frequency; worst self-check disagreement */
+    const char *tf_reason;
     const char *kernel_name;
     double flops_per_eval;
     int launches;
@@ -364,7 +370,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         DevPlan *d = &p->d[g];
         /* stream-ordered frees: back into the device's pool without a device-wide synchronisation */
         cudaStream_t st = p->ctx->d[g].stream;
-        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
+        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->xt, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
                          d->fgrid, d->mask, d->counters, d->ticket, d->sblk, d->sdet };
         for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
     }
@@ -398,7 +404,9 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         const char *v = getenv("QO100NET_LAD_VARIANT");
         p->lad_variant = v ? atoi(v) : 0;
     }
-    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
+    p->tf = qo_tf_plan_check(&p->hp, p->mode == QO_MODE_REDUCE_ONLY, p->precision, p->generic, f, nf, p->maskv.data(), &p->tf_K, &p->tf_mode,
+                             &p->tf_wref, &p->tf_el0, &p->tf_nel, &p->tf_cpl_op, &p->tf_err, &p->tf_reason);
+    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
     const double two_pi = 6.283185307179586476925286766559;
@@ -453,7 +461,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     std::vector<double> ctab[4];
     std::vector<float> ctabf[4];
     p->cpl_fast = p->cpl_same = 0;
-    if (p->ladder && p->lad_cpl) {
+    if ((p->ladder && p->lad_cpl) || (p->tf && p->tf_cpl_op >= 0)) {
         const DevProg *hp = &p->hp;
         const int ec = hp->op0;                    /* the coupler op */
         double wmax = 0;
@@ -542,7 +550,14 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                     CUP(cudaMemcpyAsync(d->sdet, sdet.data(), sdet.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
                 }
             }
-            if (p->ladder) {
+            if (p->tf) {
+                std::vector<double> xn(2 * (size_t)np);
+                for (int k = 0; k < 2 * np; k++) xn[k] = w[k] / p->tf_wref;
+                CUP(cudaMallocAsync((void **)&d->xt, 2 * (size_t)np * sizeof(double), st));
+                CUP(cudaMemcpyAsync(d->xt, xn.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                CUP(cudaStreamSynchronize(st));
+            }
+            if (p->ladder || p->tf) {
                 CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
                 CUP(cudaMemcpyAsync(d->wsq2, p->precision == 32 ? (const void *)wsqf.data() : (const void *)wsq.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
                 CUP(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), st));
@@ -673,6 +688,39 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     return QO_OK;
 }
 
+static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, const double *cplms)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    DevPlan *d = &p->d[g];
+    const DevProg *hp = &p->hp;
+    TfParams P;
+    memset(&P, 0, sizeof P);
+    P.prog = d->prog;
+    P.xt = d->xt; P.wt = (const double2 *)d->w2; P.m2 = d->m2;
+    P.cse = (const double2 *)d->cpl_tab[0]; P.cce = (const double2 *)d->cpl_tab[1];
+    P.cso = (const double2 *)d->cpl_tab[2]; P.cco = (const double2 *)d->cpl_tab[3];
+    P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tf_cpl_op;
+    P.cplms = cplms;
+    P.counters = cnt; P.ticket = d->ticket;
+    CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
+    P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
+    P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
+    P.wref = p->tf_wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
+    for (int s = 0; s < QO_LAD_NSPEC; s++) {
+        const int neg = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
+        P.neg[s] = neg;
+        P.thr[s] = s < hp->nspec ? (neg ? -hp->spec_thr[s] : hp->spec_thr[s]) : 0.0;
+    }
+    P.npairs = p->npairs; P.n_var = hp->n_var; P.n_el = p->tf_nel; P.el0 = p->tf_el0; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.hist_bins = hp->hist_bins;
+    P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
+    P.hist_kind = hp->hist_bins > 0 ? hp->spec_kind[hp->hist_spec] : 0;
+    int rc = qo_tf_launch(p->tf_K, p->tf_mode, p->lad_variant, dc->sm_count, &P, dc->stream);
+    if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for K=%d mode=%d", p->tf_K, p->tf_mode); return QO_ERR_UNSUPPORTED; }
+    if (rc) { qo_set_error("transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
 static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
 {
     DevCtx *dc = &p->ctx->d[g];
@@ -720,6 +768,7 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     }
     int rc;
     if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
+    else if (p->tf) rc = launch_tf(p, g, off, n, cnt, cplms);
     else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt, cplms);
     else if (p->precision == 32) rc = launch_lumped<float>(p, g, off, n, cnt, pl, full_s);
     else rc = launch_lumped<double>(p, g, off, n, cnt, pl, full_s);

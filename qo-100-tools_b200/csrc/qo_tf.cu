@@ -1,0 +1,175 @@
+/*
+ * qo_tf.cu -- instantiations, launcher and plan-time self-check of the transfer-function kernel (qo_tf.cuh).
+ * Its own translation unit (compiles in parallel with qo_cuda.cu / qo_ladder.cu).
+ */
+#include <cuda_runtime.h>
+#include <complex>
+#include <vector>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "qo_tf.cuh"
+#include "qo_tf_launch.h"
+
+#ifndef QO_TF_PP
+#define QO_TF_PP 2
+#define QO_TF_TPB 256
+#define QO_TF_MINB 2
+#endif
+
+typedef void (*tf_fn)(const TfParams);
+
+template <int MODE, int PP, int TPB, int MINB> static tf_fn tf_pick(int K)
+{
+#define QO_TF_ROW(KK) case KK: return qo_mc_tf_kernel<KK, MODE, PP, TPB, MINB>;
+    switch (K) {
+        QO_TF_ROW(1) QO_TF_ROW(2) QO_TF_ROW(3) QO_TF_ROW(4) QO_TF_ROW(5) QO_TF_ROW(6) QO_TF_ROW(7) QO_TF_ROW(8)
+        QO_TF_ROW(9) QO_TF_ROW(10) QO_TF_ROW(11) QO_TF_ROW(12) QO_TF_ROW(13) QO_TF_ROW(14) QO_TF_ROW(15)
+    default: return nullptr;
+    }
+#undef QO_TF_ROW
+}
+
+extern "C" int qo_tf_launch(int K, int mode, int variant, int sm_count, const TfParams *P, cudaStream_t st)
+{
+    tf_fn fn = nullptr;
+    int tpb = QO_TF_TPB, minb = QO_TF_MINB;
+    (void)variant;
+    switch (mode) {
+    case QO_TF_S21: fn = tf_pick<QO_TF_S21, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_S21_NOD: fn = tf_pick<QO_TF_S21_NOD, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_CPL: fn = tf_pick<QO_TF_CPL, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
+    default: break;
+    }
+    if (!fn) return -1;
+    const unsigned long long warps = (unsigned long long)(tpb / 32);
+    unsigned long long blocks = (P->nsamples + warps - 1) / warps;
+    const unsigned long long resident = (unsigned long long)sm_count * (unsigned long long)minb;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
+    fn<<<(unsigned)blocks, tpb, 0, st>>>(*P);
+    return (int)cudaGetLastError();
+}
+
+/* ---- plan-time self-check (host) ------------------------------------------------------------------------- */
+typedef std::complex<double> cplx;
+
+/* the device's expansion, in the same order and with the same normalisation */
+static void tf_expand_host(const double (*rec)[QO_TF_REC], int n_el, double rl, double zn, double *p, double *q, double *d)
+{
+    const int NC = 2 * QO_TF_MAXK + 2;
+    for (int i = 0; i < NC; i++) p[i] = q[i] = d[i] = 0.0;
+    p[0] = rl; q[0] = zn; d[0] = 1.0;
+    std::vector<double> na(NC), nb(NC), ndv(NC);
+    for (int e = n_el - 1; e >= 0; e--) {
+        const double *r = rec[e];
+        const bool series = r[6] != 0.0;
+        double *a = series ? p : q, *b = series ? q : p;
+        for (int i = 0; i < NC; i++) {
+            const double a1 = i >= 1 ? a[i - 1] : 0.0, a2 = i >= 2 ? a[i - 2] : 0.0, b1 = i >= 1 ? b[i - 1] : 0.0, b2 = i >= 2 ? b[i - 2] : 0.0;
+            const double d1 = i >= 1 ? d[i - 1] : 0.0, d2 = i >= 2 ? d[i - 2] : 0.0;
+            double v = fma(r[3], a[i], fma(r[4], a1, r[5] * a2));
+            na[i] = fma(r[0], b[i], fma(r[1], b1, fma(r[2], b2, v)));
+            nb[i] = fma(r[3], b[i], fma(r[4], b1, r[5] * b2));
+            ndv[i] = fma(r[3], d[i], fma(r[4], d1, r[5] * d2));
+        }
+        for (int i = 0; i < NC; i++) { a[i] = na[i]; b[i] = nb[i]; d[i] = ndv[i]; }
+    }
+}
+
+static cplx tf_horner_host(const double *c, int K, double x)
+{
+    const double y = -x * x;
+    double re = c[2 * (K - 1)], im = c[2 * (K - 1) + 1];
+    for (int k = K - 2; k >= 0; k--) { re = fma(re, y, c[2 * k]); im = fma(im, y, c[2 * k + 1]); }
+    return cplx(re, im * x);
+}
+
+extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
+                                const unsigned char *mask, int *K, int *mode, double *wref, int *el0, int *n_el, int *cpl_op,
+                                double *err, const char **reason)
+{
+    static const char *why = "";
+    *reason = why;
+#define QO_TF_NO(msg) do { *reason = msg; return 0; } while (0)
+    const char *force = getenv("QO100NET_KERNEL");
+    if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
+    if (generic || !mode_reduce_only || precision != 64 || hp->need_gd || hp->need_s11) QO_TF_NO("not a reduce-only FP64 |S21| job");
+    if (hp->nspec < 1 || hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) QO_TF_NO("spec / variable count");
+    for (int s = 0; s < hp->nspec; s++)
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN) QO_TF_NO("spec kind");
+    int e0 = hp->op0;
+    *cpl_op = -1;
+    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { *cpl_op = e0; e0++; }
+    const int nl = hp->n_ops - e0;
+    if (nl < 1 || nl > QO_TF_MAXEL) QO_TF_NO("element count");
+    int deg = 0, has_d = 0;
+    for (int e = 0; e < nl; e++) {
+        const int op = hp->opcode[e0 + e], dg = qo_tf_degree(op);
+        if (dg < 0) QO_TF_NO("non-lumped element");
+        deg += dg;
+        if (!(op == OP_SER_R || op == OP_SER_L || op == OP_SHUNT_C)) has_d = 1;     /* these have D == 1 exactly */
+    }
+    if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
+    const int Kk = deg / 2 + 1;
+    *K = Kk; *el0 = e0; *n_el = nl;
+    *mode = *cpl_op >= 0 ? QO_TF_CPL : has_d ? QO_TF_S21 : QO_TF_S21_NOD;
+
+    const double two_pi = 6.283185307179586476925286766559;
+    double fmin = f[0], fmax = f[0];
+    for (int k = 1; k < nf; k++) { if (f[k] < fmin) fmin = f[k]; if (f[k] > fmax) fmax = f[k]; }
+    const double wr = two_pi * sqrt(fmin * fmax);
+    *wref = wr;
+    const double zn = sqrt(hp->rs * hp->rl), zni = 1.0 / zn;
+
+    /* nominal, and both all-at-one-end corners of the tolerance box */
+    double worst = 0.0;
+    for (int corner = -1; corner <= 1; corner++) {
+        double rec[QO_TF_MAXEL][QO_TF_REC];
+        double nd[QO_TF_MAXEL][6];
+        int ser[QO_TF_MAXEL];
+        for (int e = 0; e < nl; e++) {
+            double p[6];
+            for (int k = 0; k < 6; k++) {
+                p[k] = hp->nom[e0 + e][k];
+                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)corner, hp->tmode[e0 + e][k]);
+            }
+            ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, nd[e]);
+            const double sc = ser[e] ? zni : zn;
+            rec[e][0] = nd[e][0] * sc; rec[e][1] = nd[e][1] * sc; rec[e][2] = nd[e][2] * sc;
+            rec[e][3] = nd[e][3]; rec[e][4] = nd[e][4]; rec[e][5] = nd[e][5]; rec[e][6] = ser[e] ? 1.0 : 0.0; rec[e][7] = 0.0;
+        }
+        double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2];
+        tf_expand_host(rec, nl, hp->rl, zn, pp, qq, dd);
+        for (int i = 2 * Kk; i < 2 * QO_TF_MAXK + 2; i++)
+            if (pp[i] != 0.0 || qq[i] != 0.0 || dd[i] != 0.0) QO_TF_NO("degree accounting");
+        for (int k = 0; k < nf; k++) {
+            const double x = two_pi * f[k] / wr;
+            const cplx P_ = tf_horner_host(pp, Kk, x), Q_ = tf_horner_host(qq, Kk, x) * zni, D_ = tf_horner_host(dd, Kk, x);
+            const double d2 = std::norm(D_);
+            if (!(d2 > 1e-70 && d2 < 1e70)) QO_TF_NO("|D|^2 leaves the range of the batched reciprocal");
+            if (!mask[k]) continue;
+            /* per-element evaluation, column vector from the load end */
+            const cplx sj(0.0, x);
+            cplx a(hp->rl, 0.0), b(1.0, 0.0);
+            for (int e = nl - 1; e >= 0; e--) {
+                const cplx N = nd[e][0] + sj * (nd[e][1] + sj * nd[e][2]), D = nd[e][3] + sj * (nd[e][4] + sj * nd[e][5]);
+                const cplx imm = N / D;
+                if (ser[e]) a += imm * b; else b += imm * a;
+            }
+            double rel;
+            if (*cpl_op >= 0) rel = (std::abs(P_ / D_ - a) + zn * std::abs(Q_ / D_ - b)) / (std::abs(a) + zn * std::abs(b));
+            else rel = std::abs((P_ + hp->rs * Q_) / D_ - (a + hp->rs * b)) / std::abs(a + hp->rs * b);
+            if (!(rel == rel)) QO_TF_NO("self-check produced a NaN");
+            if (2.0 * rel > worst) worst = 2.0 * rel;
+        }
+    }
+    *err = worst;
+    double tol = 1e-10;
+    const char *t = getenv("QO100NET_TF_TOL");
+    if (t) tol = atof(t);
+    if (worst > tol) QO_TF_NO("polynomial expansion is too ill-conditioned on this grid");
+    *reason = "ok";
+    return 1;
+#undef QO_TF_NO
+}

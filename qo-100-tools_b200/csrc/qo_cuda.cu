@@ -43,7 +43,11 @@ struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
     void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
-    double2 *xt;               /* double2 [npairs]: w / wref, transfer-function kernel only */
+    /* transfer-function kernel: one blob, tables padded to whole iterations of tf_pp*32 pairs */
+    void *tf_blob;
+    double2 *tf_yt, *tf_xt, *tf_wt, *tf_ctab[4];
+    uint2 *tf_mb;
+    uchar2 *tf_itm;
     double2 *sblk, *sdet;      /* OP_SBLOCK: ABCD per (block, grid point); product of block determinants per point */
     void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
     uchar2 *m2;
@@ -63,6 +67,7 @@ struct qo_plan {
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
     int tf, tf_K, tf_mode, tf_el0, tf_nel, tf_cpl_op;     /* transfer-function kernel (qo_tf.cuh) */
     double tf_wref, tf_err;                               /* normalising frequency; worst self-check disagreement */
+    int tf_pp, tf_niter;                                  /* pairs per thread per iteration; iterations per sample */
     const char *tf_reason;
     const char *kernel_name;
     double flops_per_eval;
@@ -370,7 +375,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         DevPlan *d = &p->d[g];
         /* stream-ordered frees: back into the device's pool without a device-wide synchronisation */
         cudaStream_t st = p->ctx->d[g].stream;
-        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->xt, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
+        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->tf_blob, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
                          d->fgrid, d->mask, d->counters, d->ticket, d->sblk, d->sdet };
         for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
     }
@@ -551,11 +556,44 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 }
             }
             if (p->tf) {
-                std::vector<double> xn(2 * (size_t)np);
-                for (int k = 0; k < 2 * np; k++) xn[k] = w[k] / p->tf_wref;
-                CUP(cudaMallocAsync((void **)&d->xt, 2 * (size_t)np * sizeof(double), st));
-                CUP(cudaMemcpyAsync(d->xt, xn.data(), 2 * (size_t)np * sizeof(double), cudaMemcpyHostToDevice, st));
+                /* tables of the transfer-function kernel, padded to whole iterations (padding repeats the last grid
+                 * point and carries no spec bit, so the loop needs no bounds checks) */
+                p->tf_pp = p->tf_mode == QO_TF_CPL ? 2 : 4;
+                const int ppi = 32 * p->tf_pp;
+                p->tf_niter = (np + ppi - 1) / ppi;
+                const size_t npad = (size_t)p->tf_niter * ppi, npt = 2 * npad;
+                const int ntab = 3 + (p->cpl_fast ? 4 : 0);
+                const size_t bytes = (size_t)ntab * npt * sizeof(double) + npt * sizeof(unsigned int) + (size_t)p->tf_niter * sizeof(uchar2);
+                std::vector<unsigned char> blob(bytes);
+                double *tab = (double *)blob.data();
+                unsigned int *mb = (unsigned int *)(tab + (size_t)ntab * npt);
+                uchar2 *itm = (uchar2 *)(mb + npt);
+                for (size_t k = 0; k < npt; k++) {
+                    const size_t kc = k < (size_t)nf ? k : (size_t)nf - 1;
+                    const double x = w[kc] / p->tf_wref;
+                    tab[k] = -(x * x); tab[npt + k] = x; tab[2 * npt + k] = w[kc];
+                    if (p->cpl_fast) for (int t = 0; t < 4; t++) tab[(3 + t) * npt + k] = ctab[t][kc];
+                    unsigned int word = 0;
+                    const unsigned char mk = k < (size_t)nf ? p->maskv[k] : 0;
+                    for (int sp = 0; sp < 4; sp++) if ((mk >> sp) & 1u) word |= 0xFFu << (8 * sp);
+                    mb[k] = word;
+                }
+                for (int it = 0; it < p->tf_niter; it++) {
+                    unsigned char any = 0, all = 0xFF;
+                    for (size_t k = (size_t)it * 2 * ppi; k < (size_t)(it + 1) * 2 * ppi; k++) {
+                        const unsigned char mk = k < (size_t)nf ? p->maskv[k] : 0;
+                        any |= mk; all &= mk;
+                    }
+                    itm[it] = make_uchar2(any, all);
+                }
+                CUP(cudaMallocAsync((void **)&d->tf_blob, bytes, st));
+                CUP(cudaMemcpyAsync(d->tf_blob, blob.data(), bytes, cudaMemcpyHostToDevice, st));
                 CUP(cudaStreamSynchronize(st));
+                double *dt = (double *)d->tf_blob;
+                d->tf_yt = (double2 *)dt; d->tf_xt = (double2 *)(dt + npt); d->tf_wt = (double2 *)(dt + 2 * npt);
+                for (int t = 0; t < 4; t++) d->tf_ctab[t] = p->cpl_fast ? (double2 *)(dt + (3 + t) * npt) : NULL;
+                d->tf_mb = (uint2 *)(dt + (size_t)ntab * npt);
+                d->tf_itm = (uchar2 *)((unsigned int *)d->tf_mb + npt);
             }
             if (p->ladder || p->tf) {
                 CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
@@ -696,9 +734,8 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     TfParams P;
     memset(&P, 0, sizeof P);
     P.prog = d->prog;
-    P.xt = d->xt; P.wt = (const double2 *)d->w2; P.m2 = d->m2;
-    P.cse = (const double2 *)d->cpl_tab[0]; P.cce = (const double2 *)d->cpl_tab[1];
-    P.cso = (const double2 *)d->cpl_tab[2]; P.cco = (const double2 *)d->cpl_tab[3];
+    P.yt = d->tf_yt; P.xt = d->tf_xt; P.wt = d->tf_wt; P.mb = d->tf_mb; P.itm = d->tf_itm;
+    P.cse = d->tf_ctab[0]; P.cce = d->tf_ctab[1]; P.cso = d->tf_ctab[2]; P.cco = d->tf_ctab[3];
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tf_cpl_op;
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
@@ -707,15 +744,13 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
     P.wref = p->tf_wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
     for (int s = 0; s < QO_LAD_NSPEC; s++) {
-        const int neg = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
-        P.neg[s] = neg;
-        P.thr[s] = s < hp->nspec ? (neg ? -hp->spec_thr[s] : hp->spec_thr[s]) : 0.0;
+        P.neg[s] = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
+        P.thr[s] = s < hp->nspec ? hp->spec_thr[s] : 0.0;
     }
-    P.npairs = p->npairs; P.n_var = hp->n_var; P.n_el = p->tf_nel; P.el0 = p->tf_el0; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tf_nel; P.el0 = p->tf_el0; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
-    P.hist_kind = hp->hist_bins > 0 ? hp->spec_kind[hp->hist_spec] : 0;
-    int rc = qo_tf_launch(p->tf_K, p->tf_mode, p->lad_variant, dc->sm_count, &P, dc->stream);
+    int rc = qo_tf_launch(p->tf_K, p->tf_mode, p->tf_pp, p->lad_variant, dc->sm_count, &P, dc->stream);
     if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for K=%d mode=%d", p->tf_K, p->tf_mode); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
     return QO_OK;

@@ -92,8 +92,16 @@ __device__ __forceinline__ float lad_lds1(unsigned int saddr, float)
  * FP32: one MUFU.RCP per point (1 ulp; a product of four would leave the float range). */
 template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const double (&q)[PTS], double (&s)[PTS])
 {
-    static_assert(PTS == 2 || PTS == 4, "two or four points per thread");
-    if (PTS == 2) {
+    static_assert(PTS == 2 || PTS == 4 || PTS == 8, "two, four or eight points per thread");
+    if (PTS == 8) {                      /* two batches of four */
+#pragma unroll
+        for (int h = 0; h < 8; h += 4) {
+            const double p01 = q[h] * q[h + 1], p23 = q[h + 2] * q[h + 3];
+            const double r = qrcp(p01 * p23);
+            const double r01 = r * p23, r23 = r * p01;
+            s[h] = r01 * q[h + 1]; s[h + 1] = r01 * q[h]; s[h + 2] = r23 * q[h + 3]; s[h + 3] = r23 * q[h + 2];
+        }
+    } else if (PTS == 2) {
         const double r = qrcp(q[0] * q[1]);
         s[0] = r * q[1]; s[1] = r * q[0];
     } else {
@@ -165,7 +173,7 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const T (&w)[
  * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
  * short Taylor polynomials (truncation |d|^10/10! < 3e-17 on cos, |d|^9/9! < 3e-15 on sin) -- 14 FP64 instructions instead of the ~30 of
  * a general sincos; otherwise sincos() is called. */
-template <typename T, int PTS, int NROWS, bool FAST>
+template <typename T, int PTS, int NROWS, bool FAST, bool RAWK = false>
 __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
                                               const T (&tso)[PTS], const T (&tco)[PTS], T rs, LadRow<T, PTS, NROWS> &u, T (&scale)[PTS])
 {
@@ -216,8 +224,11 @@ __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS]
             u.br[r][p] = qfma(sg * rs, Ar, zt * Br); u.bi[r][p] = qfma(sg * rs, Ai, zt * Bi);            /* k (B +- Rs A) */
         }
     }
-    lad_rcp_batch<PTS>(kap2, scale);
-    QO_PTS scale[p] *= T(0.25);                                                                          /* 1/|k|^2 */
+    if (RAWK) { QO_PTS scale[p] = T(4) * kap2[p]; }                                                      /* |k|^2: the caller folds it into its own denominator */
+    else {
+        lad_rcp_batch<PTS>(kap2, scale);
+        QO_PTS scale[p] *= T(0.25);                                                                      /* 1/|k|^2 */
+    }
 }
 
 /* per-sample coefficient records, one lane per element (perturbation is the shared bit-exact stream; the

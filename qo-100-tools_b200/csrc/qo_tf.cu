@@ -11,11 +11,12 @@
 #include "qo_tf.cuh"
 #include "qo_tf_launch.h"
 
-#ifndef QO_TF_PP
-#define QO_TF_PP 2
-#define QO_TF_TPB 256
-#define QO_TF_MINB 2
-#endif
+/* launch shapes (tools/tf_sweep.py, profiles/r01h_*): the |S21| modes run 8 points per thread (coefficient loads and loop
+ * overhead amortised over 8 Horner sets), the coupler mode 4 (six chains + the coupler block's state) */
+#define QO_TF_TPB 128
+#define QO_TF_MINB 4
+#define QO_TF_CPL_TPB 256
+#define QO_TF_CPL_MINB 2
 
 typedef void (*tf_fn)(const TfParams);
 
@@ -30,15 +31,29 @@ template <int MODE, int PP, int TPB, int MINB> static tf_fn tf_pick(int K)
 #undef QO_TF_ROW
 }
 
-extern "C" int qo_tf_launch(int K, int mode, int variant, int sm_count, const TfParams *P, cudaStream_t st)
+extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st)
 {
     tf_fn fn = nullptr;
     int tpb = QO_TF_TPB, minb = QO_TF_MINB;
     (void)variant;
+#ifdef QO_TF_EXPERIMENT
+    /* development builds: launch shapes of the K = 12 |S21| kernel, chosen with QO100NET_LAD_VARIANT */
+    if (mode == QO_TF_S21 && K == 12 && pp == 4) {
+        switch (variant) {
+        case 1: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 3>; tpb = 128; minb = 3; break;
+        case 2: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 256, 2>; tpb = 256; minb = 2; break;
+        case 3: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 8>; tpb = 64; minb = 8; break;
+        case 4: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 5>; tpb = 128; minb = 5; break;
+        case 5: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 6>; tpb = 64; minb = 6; break;
+        default: break;
+        }
+    }
+    if (!fn)
+#endif
     switch (mode) {
-    case QO_TF_S21: fn = tf_pick<QO_TF_S21, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
-    case QO_TF_S21_NOD: fn = tf_pick<QO_TF_S21_NOD, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
-    case QO_TF_CPL: fn = tf_pick<QO_TF_CPL, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_S21: if (pp == 4) fn = tf_pick<QO_TF_S21, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_S21_NOD: if (pp == 4) fn = tf_pick<QO_TF_S21_NOD, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_CPL: if (pp == 2) { fn = tf_pick<QO_TF_CPL, 2, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(K); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; } break;
     default: break;
     }
     if (!fn) return -1;

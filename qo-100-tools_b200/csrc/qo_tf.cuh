@@ -35,16 +35,18 @@ enum { QO_TF_S21 = 0 /* Num, D */, QO_TF_S21_NOD = 1 /* D == 1: ideal L/C/R ladd
 
 struct TfParams {
     const DevProg *prog;
-    const double2 *xt;                       /* normalised w / wref per grid point, two points per entry */
-    const double2 *wt;                       /* w (coupler block) */
-    const uchar2 *m2;
-    const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the nominal mode angles (cpl_fast) */
+    const double2 *yt;                       /* -(w / wref)^2 per grid point, two points per entry, padded to whole iterations */
+    const double2 *xt;                       /* w / wref (coupler mode: imaginary parts need x itself) */
+    const double2 *wt;                       /* w (coupler block), padded likewise */
+    const uint2 *mb;                         /* per point one word: byte s = 0xFF when the point lies in spec s's band (padding: 0) */
+    const uchar2 *itm;                       /* per iteration of PP*32 pairs: (OR, AND) of the spec bit masks of its points */
+    const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the nominal mode angles (cpl_fast), padded */
     unsigned long long *counters, *ticket;
     unsigned long long sample_offset, nsamples, seed;
     double rs, rl, k21, hist_lo, hist_hi, wref, zn, zni;
-    double thr[QO_LAD_NSPEC];
+    double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
     int neg[QO_LAD_NSPEC];
-    int npairs, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins, hist_kind;
+    int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op;
     const double *cplms;
 };
@@ -70,7 +72,23 @@ __device__ __forceinline__ void tf_derive(const DevProg *__restrict__ prog, int 
 }
 
 __device__ __forceinline__ double tf_up(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ unsigned int tf_hi(double v) { return (unsigned int)__double2hiint(v); }
 
+/*
+ * K      coefficients per Horner chain            MODE   QO_TF_*
+ * PP     frequency pairs per thread per iteration (PTS = 2*PP points)
+ * One warp = one sample at a time (ticket hand-out as in qo_ladder.cuh); lane l owns pairs l, l+32, ... of each
+ * iteration's PP*32 pairs.
+ *
+ * Spec bookkeeping without divisions.  |den|^2 = n2 / dd (n2 = |Num|^2, dd = |D|^2, times 4|k|^2 behind a coupler):
+ *   - the histogram spec needs the VALUE of its band's extreme: one batched reciprocal per iteration in which
+ *     that band is active, running max (min) in a double;
+ *   - every other spec only needs the SIGN of  g = thr*dd - n2  (S21_MIN_DB)  or  n2 - thr*dd  (S21_MAX_DB):
+ *     one DFMA, and the sign bits are OR-ed into a 32-bit accumulator (FAIL iff the accumulator ends negative).
+ * Bands are contiguous, so most iterations see one mask on all their points: the per-iteration (OR, AND) pair
+ * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
+ * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
+ */
 template <int K, int MODE, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
@@ -92,9 +110,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     double *polyw = s_poly[warp], *elw = s_el[warp], *xw = s_x[warp];
     const unsigned int polys = (unsigned int)__cvta_generic_to_shared(polyw);
     const unsigned int cpls = (unsigned int)__cvta_generic_to_shared(s_cpl[warp]);
-    const int npairs = P.npairs;
     const double rs = P.rs;
     const int up1 = (lane + 31) & 31, up2 = (lane + 30) & 31;
+    const int hs = P.hist_spec;
+    const bool hneg = hs >= 0 && P.neg[hs & (QO_LAD_NSPEC - 1)];
 
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS;
     unsigned long long s = (unsigned long long)blockIdx.x * WARPS + warp;
@@ -110,19 +129,20 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             lad_derive<double>(P.prog, P.cpl_op, xw, s_cpl[warp], P.cplms ? P.cplms + 4 * s : NULL, nom_k);
         }
         __syncwarp();
-        /* 2. expand [P; Q] and D from the load end: lane i holds the coefficient of sn^i */
+        /* 2. expand [P; Q] and D from the load end: lane i holds the coefficient of sn^i (lanes 30, 31 stay zero,
+         *    so the rotating shuffles bring zeros into lanes 0 and 1) */
         double p = lane == 0 ? P.rl : 0.0, q = lane == 0 ? P.zn : 0.0, d = lane == 0 ? 1.0 : 0.0;
         for (int e = P.n_el - 1; e >= 0; e--) {
             const double2 n01 = *(const double2 *)(elw + e * QO_TF_REC), n2d0 = *(const double2 *)(elw + e * QO_TF_REC + 2),
                           d12 = *(const double2 *)(elw + e * QO_TF_REC + 4);
             const bool series = elw[e * QO_TF_REC + 6] != 0.0;
-            /* series Z = N/D: P <- D P + N Q, Q <- D Q;  shunt Y = N/D: Q <- D Q + N P, P <- D P */
-            double a = series ? p : q, b = series ? q : p;
-            const double a1 = tf_up(a, up1), a2 = tf_up(a, up2), b1 = tf_up(b, up1), b2 = tf_up(b, up2);
-            double na = fma(n2d0.y, a, fma(d12.x, a1, d12.y * a2));
-            na = fma(n01.x, b, fma(n01.y, b1, fma(n2d0.x, b2, na)));
-            const double nb = fma(n2d0.y, b, fma(d12.x, b1, d12.y * b2));
-            p = series ? na : nb; q = series ? nb : na;
+            const double p1 = tf_up(p, up1), p2 = tf_up(p, up2), q1 = tf_up(q, up1), q2 = tf_up(q, up2);
+            const double dp = fma(n2d0.y, p, fma(d12.x, p1, d12.y * p2)), dq = fma(n2d0.y, q, fma(d12.x, q1, d12.y * q2));
+            if (series) {            /* Z = N/D: P <- D P + N Q, Q <- D Q */
+                p = fma(n01.x, q, fma(n01.y, q1, fma(n2d0.x, q2, dp))); q = dq;
+            } else {                 /* Y = N/D: Q <- D Q + N P, P <- D P */
+                q = fma(n01.x, p, fma(n01.y, p1, fma(n2d0.x, p2, dq))); p = dp;
+            }
             if (MODE != QO_TF_S21_NOD) {
                 const double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
                 d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
@@ -140,30 +160,23 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         __syncwarp();
 
         /* 3. frequency loop */
-        double trk[QO_LAD_NSPEC];
+        double trkv = hneg ? 1.7e308 : -1.7e308;     /* histogram spec: running extreme of |den|^2 */
+        unsigned int acc[QO_LAD_NSPEC];              /* other specs: OR of the sign words of g */
 #pragma unroll
-        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) trk[sp] = -1.7e308;
-        for (int jb = 0; jb < npairs; jb += 32 * PP) {
-            const int j0 = jb + lane;
-            double x[PTS], y[PTS];
-            unsigned int mk[PTS];
+        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) acc[sp] = 0u;
+        for (int it = 0; it < P.niter; it++) {
+            const int j0 = it * (32 * PP) + lane;
+            double y[PTS];
 #pragma unroll
             for (int qq = 0; qq < PP; qq++) {
-                const int j = j0 + 32 * qq;
-                const int jc = j < npairs ? j : npairs - 1;
-                const double2 a = P.xt[jc];
-                const uchar2 m = P.m2[jc];
-                x[2 * qq] = a.x; x[2 * qq + 1] = a.y;
-                mk[2 * qq] = j < npairs ? m.x : 0u; mk[2 * qq + 1] = j < npairs ? m.y : 0u;
+                const double2 a = P.yt[j0 + 32 * qq];
+                y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
             }
-            QO_PTS y[p] = -x[p] * x[p];
             double r[NCH][PTS];
-            {
 #pragma unroll
-                for (int c = 0; c < NCH; c += 2) {
-                    const LadV2<double> cc = lad_lds2(polys + ((K - 1) * NCH + c) * 8u, 0.0);
-                    QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
-                }
+            for (int c = 0; c < NCH; c += 2) {
+                const LadV2<double> cc = lad_lds2(polys + ((K - 1) * NCH + c) * 8u, 0.0);
+                QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
             }
 #pragma unroll
             for (int k = K - 2; k >= 0; k--) {
@@ -173,69 +186,90 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     QO_PTS { r[c][p] = fma(r[c][p], y[p], cc.x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc.y); }
                 }
             }
-            double den2[PTS];
+            /* n2 = |numerator|^2, dd = |denominator|^2  (|re + j x im|^2 = re^2 - y im^2) */
+            double n2[PTS], dd[PTS];
             if (!CPL) {
-                QO_PTS { const double ni = r[1][p] * x[p]; den2[p] = fma(r[0][p], r[0][p], ni * ni); }
-                if (MODE == QO_TF_S21) {
-                    double dd[PTS], rd[PTS];
-                    QO_PTS { const double di = r[3][p] * x[p]; dd[p] = fma(r[2][p], r[2][p], di * di); }
-                    lad_rcp_batch<PTS>(dd, rd);
-                    QO_PTS den2[p] *= rd[p];
-                }
+                QO_PTS { const double t = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t, r[0][p] * r[0][p]); }
+                if (MODE == QO_TF_S21) { QO_PTS { const double t = r[3][p] * r[3][p]; dd[p] = fma(-y[p], t, r[2][p] * r[2][p]); } }
+                else { QO_PTS dd[p] = 1.0; }
             } else {
-                double w[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS], cscale[PTS];
+                double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS], kap[PTS];
                 QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) {
                     const int j = j0 + 32 * qq;
-                    const int jc = j < npairs ? j : npairs - 1;
-                    const double2 a = P.wt[jc];
-                    w[2 * qq] = a.x; w[2 * qq + 1] = a.y;
+                    const double2 a = P.wt[j], b = P.xt[j];
+                    w[2 * qq] = a.x; w[2 * qq + 1] = a.y; x[2 * qq] = b.x; x[2 * qq + 1] = b.y;
                     if (P.cpl_fast) {
-                        const double2 se = P.cse[jc], ce = P.cce[jc];
+                        const double2 se = P.cse[j], ce = P.cce[j];
                         tse[2 * qq] = se.x; tse[2 * qq + 1] = se.y; tce[2 * qq] = ce.x; tce[2 * qq + 1] = ce.y;
                         if (!P.cpl_same) {
-                            const double2 so = P.cso[jc], co = P.cco[jc];
+                            const double2 so = P.cso[j], co = P.cco[j];
                             tso[2 * qq] = so.x; tso[2 * qq + 1] = so.y; tco[2 * qq] = co.x; tco[2 * qq + 1] = co.y;
                         }
                     }
                 }
                 LadRow<double, PTS, 1> u;
-                if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true>(cpls, w, tse, tce, tso, tco, rs, u, cscale);
-                else lad_cpl_first<double, PTS, 1, false>(cpls, w, tse, tce, tso, tco, rs, u, cscale);
-                double dd[PTS], rd[PTS];
+                if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
+                else lad_cpl_first<double, PTS, 1, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
                 const double zni = P.zni;
                 QO_PTS {
-                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zni, qi = r[3][p] * x[p] * zni, di = r[5][p] * x[p];
+                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zni, qi = (r[3][p] * x[p]) * zni;
                     const double nr = fma(u.ar[0][p], r[0][p], fma(-u.ai[0][p], pi_, fma(u.br[0][p], qr, -u.bi[0][p] * qi)));
                     const double ni = fma(u.ar[0][p], pi_, fma(u.ai[0][p], r[0][p], fma(u.br[0][p], qi, u.bi[0][p] * qr)));
-                    den2[p] = fma(nr, nr, ni * ni) * cscale[p];
-                    dd[p] = fma(r[4][p], r[4][p], di * di);
+                    n2[p] = fma(nr, nr, ni * ni);
+                    const double t = r[5][p] * r[5][p];
+                    dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p];
                 }
-                lad_rcp_batch<PTS>(dd, rd);
-                QO_PTS den2[p] *= rd[p];
             }
-            /* trackers: as in qo_ladder.cuh (bands are contiguous: warp vote picks the select-free path) */
-            unsigned int m_or = mk[0], m_and = mk[0];
-#pragma unroll
-            for (int p = 1; p < PTS; p++) { m_or |= mk[p]; m_and &= mk[p]; }
-            const unsigned int any = __reduce_or_sync(0xffffffffu, m_or), all = __reduce_and_sync(0xffffffffu, m_and);
+            const uchar2 am = P.itm[it];
+            const unsigned int any = am.x, all = am.y;
             if (any == all) {
+                /* one mask on every point of the iteration (possibly none) */
 #pragma unroll
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((all >> sp) & 1u) {
-                        if (P.neg[sp]) { QO_PTS { const double c = -den2[p]; trk[sp] = c > trk[sp] ? c : trk[sp]; } }
-                        else { QO_PTS trk[sp] = den2[p] > trk[sp] ? den2[p] : trk[sp]; }
+                        if (sp == hs) {
+                            double den2[PTS];
+                            if (MODE == QO_TF_S21_NOD) { QO_PTS den2[p] = n2[p]; }
+                            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
+                            if (hneg) { QO_PTS trkv = den2[p] < trkv ? den2[p] : trkv; }
+                            else { QO_PTS trkv = den2[p] > trkv ? den2[p] : trkv; }
+                        } else if (P.neg[sp]) {
+                            const double t = P.thr[sp];
+                            QO_PTS acc[sp] |= tf_hi(fma(-t, dd[p], n2[p]));
+                        } else {
+                            const double t = P.thr[sp];
+                            QO_PTS acc[sp] |= tf_hi(fma(t, dd[p], -n2[p]));
+                        }
                     }
                 }
             } else {
+                /* the iteration straddles a band edge: per-point byte masks */
+                unsigned int mw[PTS];
+#pragma unroll
+                for (int qq = 0; qq < PP; qq++) {
+                    const uint2 m = P.mb[j0 + 32 * qq];
+                    mw[2 * qq] = m.x; mw[2 * qq + 1] = m.y;
+                }
 #pragma unroll
                 for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
                     if ((any >> sp) & 1u) {
-                        QO_PTS {
-                            const double val = P.neg[sp] ? -den2[p] : den2[p];
-                            const double cand = ((mk[p] >> sp) & 1u) ? val : -1.7e308;
-                            trk[sp] = cand > trk[sp] ? cand : trk[sp];
+                        if (sp == hs) {
+                            double den2[PTS];
+                            if (MODE == QO_TF_S21_NOD) { QO_PTS den2[p] = n2[p]; }
+                            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
+                            QO_PTS {
+                                const bool in = (mw[p] >> (8 * sp)) & 1u;
+                                if (hneg) { const double c = in ? den2[p] : 1.7e308; trkv = c < trkv ? c : trkv; }
+                                else { const double c = in ? den2[p] : -1.7e308; trkv = c > trkv ? c : trkv; }
+                            }
+                        } else {
+                            const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];
+                            QO_PTS {
+                                const double g = P.neg[sp] ? fma(t, dd[p], n2[p]) : fma(t, dd[p], -n2[p]);
+                                acc[sp] |= tf_hi(g) & __byte_perm(mw[p], 0, 0x1111 * sp);
+                            }
                         }
                     }
                 }
@@ -246,26 +280,28 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         unsigned int fail = 0;
 #pragma unroll
         for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
-            if (sp < P.nspec) {
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const double o = __shfl_xor_sync(0xffffffffu, trk[sp], off);
-                    trk[sp] = o > trk[sp] ? o : trk[sp];
-                }
-                if (trk[sp] > P.thr[sp]) fail |= 1u << sp;
+            if (sp < P.nspec && sp != hs) {
+                const unsigned int a = __reduce_or_sync(0xffffffffu, acc[sp]);
+                if (a >> 31) fail |= 1u << sp;
             }
+        }
+        if (hs >= 0) {
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double o = __shfl_xor_sync(0xffffffffu, trkv, off);
+                trkv = hneg ? (o < trkv ? o : trkv) : (o > trkv ? o : trkv);
+            }
+            const double t = P.thr[hs & (QO_LAD_NSPEC - 1)];
+            if (hneg ? trkv < t : trkv > t) fail |= 1u << hs;
         }
         if (lane == 0) {
             atomicAdd(&s_cnt[0], fail == 0 ? 1u : 0u);
             atomicAdd(&s_cnt[1], 1u);
             for (int sp = 0; sp < P.nspec; sp++)
                 if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
-            if (P.hist_spec >= 0) {
-                double worst = 0.0;
-#pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) if (sp == P.hist_spec) worst = fabs(trk[sp]);
+            if (hs >= 0) {
                 const double k21 = P.k21;
-                const double lin = P.hist_kind == SK_DEN2_MAX ? k21 * k21 / worst : k21 * k21 * (1.0 / worst);
+                const double lin = hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
                 const double v = 10.0 * log10(lin);
                 const double xb = (v - P.hist_lo) / (P.hist_hi - P.hist_lo) * (double)P.hist_bins;
                 long long b = (long long)floor(xb);

@@ -10,5 +10,6 @@ struct DevProg;
 extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
                                 const unsigned char *mask, int *K, int *mode, double *wref, int *el0, int *n_el, int *cpl_op,
                                 double *err, const char **reason);
-/* returns 0, -1 when no instantiation covers (K, mode), else the cudaError_t of the launch */
-extern "C" int qo_tf_launch(int K, int mode, int variant, int sm_count, const TfParams *P, cudaStream_t st);
+/* pp = frequency pairs per thread per iteration the plan padded its tables for (4: |S21| modes, 2: coupler mode);
+ * returns 0, -1 when no instantiation covers (K, mode, pp), else the cudaError_t of the launch */
+extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st);

@@ -559,6 +559,9 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 /* tables of the transfer-function kernel, padded to whole iterations (padding repeats the last grid
                  * point and carries no spec bit, so the loop needs no bounds checks) */
                 p->tf_pp = p->tf_mode == QO_TF_CPL ? 2 : 4;
+#ifdef QO_TF_EXPERIMENT
+                if (getenv("QO100NET_TF_PP")) p->tf_pp = atoi(getenv("QO100NET_TF_PP"));
+#endif
                 const int ppi = 32 * p->tf_pp;
                 p->tf_niter = (np + ppi - 1) / ppi;
                 const size_t npad = (size_t)p->tf_niter * ppi, npt = 2 * npad;
@@ -737,6 +740,8 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.yt = d->tf_yt; P.xt = d->tf_xt; P.wt = d->tf_wt; P.mb = d->tf_mb; P.itm = d->tf_itm;
     P.cse = d->tf_ctab[0]; P.cce = d->tf_ctab[1]; P.cso = d->tf_ctab[2]; P.cco = d->tf_ctab[3];
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tf_cpl_op;
+    /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
+    P.cpl_matched = p->tf_cpl_op >= 0 && hp->tvar[p->tf_cpl_op][5] < 0 && hp->nom[p->tf_cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));

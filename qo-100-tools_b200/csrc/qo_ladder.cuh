@@ -173,15 +173,14 @@ __device__ __forceinline__ void lad_shunt_lossy_c(unsigned int cf, const T (&w)[
  * (FAST), sin/cos of the NOMINAL angle come from per-frequency tables and the sample's small rotation from
  * short Taylor polynomials (truncation |d|^10/10! < 3e-17 on cos, |d|^9/9! < 3e-15 on sin) -- 14 FP64 instructions instead of the ~30 of
  * a general sincos; otherwise sincos() is called. */
-template <typename T, int PTS, int NROWS, bool FAST, bool RAWK = false>
-__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
-                                              const T (&tso)[PTS], const T (&tco)[PTS], T rs, LadRow<T, PTS, NROWS> &u, T (&scale)[PTS])
+/* mode angles of the coupler block for the PTS points: sin/cos of t_e = k_e w and t_o = k_o w (record layout as above) */
+template <typename T, int PTS, bool FAST>
+__device__ __forceinline__ void lad_cpl_angles(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
+                                               const T (&tso)[PTS], const T (&tco)[PTS], T (&se)[PTS], T (&ce)[PTS], T (&so)[PTS], T (&co)[PTS])
 {
-    const LadV2<T> c01 = lad_lds2(cf, T()), c23 = lad_lds2(cf + 2 * sizeof(T), T()), c45 = lad_lds2(cf + 4 * sizeof(T), T()),
-                   c67 = lad_lds2(cf + 6 * sizeof(T), T()), c89 = lad_lds2(cf + 8 * sizeof(T), T());
-    const T cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y, ke = c45.x, ko = c45.y, zt = c67.x, rz = c67.y;
+    const LadV2<T> c45 = lad_lds2(cf + 4 * sizeof(T), T()), c89 = lad_lds2(cf + 8 * sizeof(T), T());
+    const T ke = c45.x, ko = c45.y;
     const bool same = ke == ko;
-    T se[PTS], ce[PTS], so[PTS], co[PTS], kap2[PTS];
     QO_PTS {
         if (FAST) {
             {
@@ -202,6 +201,16 @@ __device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS]
             if (same) { so[p] = se[p]; co[p] = ce[p]; } else qsincos(ko * w[p], &so[p], &co[p]);
         }
     }
+}
+
+template <typename T, int PTS, int NROWS, bool FAST, bool RAWK = false>
+__device__ __forceinline__ void lad_cpl_first(unsigned int cf, const T (&w)[PTS], const T (&tse)[PTS], const T (&tce)[PTS],
+                                              const T (&tso)[PTS], const T (&tco)[PTS], T rs, LadRow<T, PTS, NROWS> &u, T (&scale)[PTS])
+{
+    const LadV2<T> c01 = lad_lds2(cf, T()), c23 = lad_lds2(cf + 2 * sizeof(T), T()), c67 = lad_lds2(cf + 6 * sizeof(T), T());
+    const T cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y, zt = c67.x, rz = c67.y;
+    T se[PTS], ce[PTS], so[PTS], co[PTS], kap2[PTS];
+    lad_cpl_angles<T, PTS, FAST>(cf, w, tse, tce, tso, tco, se, ce, so, co);
     QO_PTS {
         const T a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;             /* D_e, D_o */
         const T Pr = qfma(a1, a2, -b1 * b2), Pi = qfma(a1, b2, a2 * b1);                                 /* Pi */

@@ -15,8 +15,8 @@
  * overhead amortised over 8 Horner sets), the coupler mode 4 (six chains + the coupler block's state) */
 #define QO_TF_TPB 128
 #define QO_TF_MINB 4
-#define QO_TF_CPL_TPB 256
-#define QO_TF_CPL_MINB 2
+#define QO_TF_CPL_TPB 128
+#define QO_TF_CPL_MINB 3
 
 typedef void (*tf_fn)(const TfParams);
 
@@ -45,6 +45,25 @@ extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, 
         case 3: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 8>; tpb = 64; minb = 8; break;
         case 4: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 5>; tpb = 128; minb = 5; break;
         case 5: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 6>; tpb = 64; minb = 6; break;
+        default: break;
+        }
+    }
+    if (mode == QO_TF_CPL && K == 12) {
+        if (pp == 2) switch (variant) {
+        case 1: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 128, 3>; tpb = 128; minb = 3; break;
+        case 2: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 128, 2>; tpb = 128; minb = 2; break;
+        case 3: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 64, 6>; tpb = 64; minb = 6; break;
+        default: break;
+        }
+        if (pp == 1) switch (variant) {
+        case 4: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 256, 2>; tpb = 256; minb = 2; break;
+        case 5: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 256, 3>; tpb = 256; minb = 3; break;
+        case 6: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 128, 5>; tpb = 128; minb = 5; break;
+        default: break;
+        }
+        if (pp == 4) switch (variant) {
+        case 7: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 4, 128, 2>; tpb = 128; minb = 2; break;
+        case 8: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 4, 64, 4>; tpb = 64; minb = 4; break;
         default: break;
         }
     }

@@ -47,7 +47,7 @@ struct TfParams {
     double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
     int neg[QO_LAD_NSPEC];
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
-    int cpl_fast, cpl_same, cpl_op;
+    int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
     const double *cplms;
 };
 
@@ -73,6 +73,32 @@ __device__ __forceinline__ void tf_derive(const DevProg *__restrict__ prog, int 
 
 __device__ __forceinline__ double tf_up(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ unsigned int tf_hi(double v) { return (unsigned int)__double2hiint(v); }
+
+/* Coupled-line through block in front of the ladder when the source resistance equals the block's reference
+ * impedance (Rs == Zt; BASELINE config 5: 50 Ohm both).  With S11 = Nu/Pi, S21 = Sg/Pi (qo_ladder.cuh::lad_cpl_first)
+ * the row vector [1 Rs] M_cpl collapses:  A + Zt C = (1 - S11)/S21,  B + Zt A = Zt (1 + S11)/S21,  so
+ *     den = [ (Pi - Nu) P + Zt (Pi + Nu) Q ] / Sg
+ * -- 22 FP64 instructions after the mode angles instead of the ~60 of the general S -> ABCD form.
+ * Out: ua = Pi - Nu, ub = Pi + Nu (Zt is folded into Q's scale by the caller), sg2 = |Sg|^2. */
+template <int PTS, bool FAST>
+__device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
+                                               const double (&tso)[PTS], const double (&tco)[PTS], double (&uar)[PTS], double (&uai)[PTS],
+                                               double (&ubr)[PTS], double (&ubi)[PTS], double (&sg2)[PTS])
+{
+    const LadV2<double> c01 = lad_lds2(cf, 0.0), c23 = lad_lds2(cf + 16u, 0.0);
+    const double cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y;
+    double se[PTS], ce[PTS], so[PTS], co[PTS];
+    lad_cpl_angles<double, PTS, FAST>(cf, w, tse, tce, tso, tco, se, ce, so, co);
+    QO_PTS {
+        const double a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;           /* D_e, D_o */
+        const double Pr = fma(a1, a2, -b1 * b2), Pi = fma(a1, b2, a2 * b1);                               /* Pi */
+        const double Sr = a1 + a2, Si = b1 + b2;                                                          /* Sg */
+        const double pe = se[p] * hE, po = so[p] * hO;
+        const double Nr = -fma(pe, b2, po * b1), Ni = fma(pe, a2, po * a1);                               /* Nu */
+        uar[p] = Pr - Nr; uai[p] = Pi - Ni; ubr[p] = Pr + Nr; ubi[p] = Pi + Ni;
+        sg2[p] = fma(Sr, Sr, Si * Si);
+    }
+}
 
 /*
  * K      coefficients per Horner chain            MODE   QO_TF_*
@@ -209,17 +235,33 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                         }
                     }
                 }
-                LadRow<double, PTS, 1> u;
-                if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
-                else lad_cpl_first<double, PTS, 1, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
-                const double zni = P.zni;
-                QO_PTS {
-                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zni, qi = (r[3][p] * x[p]) * zni;
-                    const double nr = fma(u.ar[0][p], r[0][p], fma(-u.ai[0][p], pi_, fma(u.br[0][p], qr, -u.bi[0][p] * qi)));
-                    const double ni = fma(u.ar[0][p], pi_, fma(u.ai[0][p], r[0][p], fma(u.br[0][p], qi, u.bi[0][p] * qr)));
-                    n2[p] = fma(nr, nr, ni * ni);
-                    const double t = r[5][p] * r[5][p];
-                    dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p];
+                if (P.cpl_matched) {
+                    /* Rs == Zt: den = [(Pi - Nu) P + Zt (Pi + Nu) Q] / Sg */
+                    double uar[PTS], uai[PTS], ubr[PTS], ubi[PTS], sg2[PTS];
+                    if (P.cpl_fast) tf_cpl_matched<PTS, true>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, sg2);
+                    else tf_cpl_matched<PTS, false>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, sg2);
+                    const double zq = P.rs * P.zni;
+                    QO_PTS {
+                        const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                        const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
+                        const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
+                        n2[p] = fma(nr, nr, ni * ni);
+                        const double t = r[5][p] * r[5][p];
+                        dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * sg2[p];
+                    }
+                } else {
+                    LadRow<double, PTS, 1> u;
+                    if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
+                    else lad_cpl_first<double, PTS, 1, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
+                    const double zni = P.zni;
+                    QO_PTS {
+                        const double pi_ = r[1][p] * x[p], qr = r[2][p] * zni, qi = (r[3][p] * x[p]) * zni;
+                        const double nr = fma(u.ar[0][p], r[0][p], fma(-u.ai[0][p], pi_, fma(u.br[0][p], qr, -u.bi[0][p] * qi)));
+                        const double ni = fma(u.ar[0][p], pi_, fma(u.ai[0][p], r[0][p], fma(u.br[0][p], qi, u.bi[0][p] * qr)));
+                        n2[p] = fma(nr, nr, ni * ni);
+                        const double t = r[5][p] * r[5][p];
+                        dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p];
+                    }
                 }
             }
             const uchar2 am = P.itm[it];

@@ -1,6 +1,9 @@
+#!/usr/bin/env python
+"""Development sweep of transfer-function-kernel launch shapes (library built with `make EXTRA=-DQO_TF_EXPERIMENT`):
+   python tools/tf_sweep.py cfg2|cfg5|cfg5p  pp:variant[,pp:variant...]"""
 import os, sys
 import numpy as np
-ROOT = "/root/repo"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python")); sys.path.insert(0, ROOT)
 import torch
 import qo100net as Q
@@ -8,10 +11,13 @@ from qo100net import workloads as W
 ctx = Q.Context(device=0)
 stream = torch.cuda.Stream(); ctx.set_stream(stream.cuda_stream)
 n = 400000
-wl = W.cfg2(n, 4096); nf = 4096
+wl = getattr(W, sys.argv[1])(n, 4096); nf = 4096
 base = None
-for v in [int(x) for x in sys.argv[1].split(",")]:
-    os.environ["QO100NET_LAD_VARIANT"] = str(v)
+for item in sys.argv[2].split(","):
+    pp, v = item.split(":")
+    os.environ["QO100NET_LAD_VARIANT"] = v
+    if pp != "0": os.environ["QO100NET_TF_PP"] = pp
+    else: os.environ.pop("QO100NET_TF_PP", None)
     plan = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, **wl.hist)
     cnt = torch.zeros(plan.num_counters, dtype=torch.int64, device="cuda")
     with torch.cuda.stream(stream):
@@ -25,5 +31,5 @@ for v in [int(x) for x in sys.argv[1].split(",")]:
             b.record(stream); torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b) / 3)
     if base is None: base = got
-    print("variant %d %s %.3f ms %.3e evals/s same=%s" % (v, plan.kernel_name, best, n * nf / best * 1e3, np.array_equal(got, base)), flush=True)
+    print("pp %s variant %s %s %.3f ms %.3e evals/s same=%s" % (pp, v, plan.kernel_name, best, n * nf / best * 1e3, np.array_equal(got, base)), flush=True)
     plan.close()

@@ -43,7 +43,6 @@ extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, 
         case 1: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 3>; tpb = 128; minb = 3; break;
         case 2: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 256, 2>; tpb = 256; minb = 2; break;
         case 3: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 8>; tpb = 64; minb = 8; break;
-        case 4: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 5>; tpb = 128; minb = 5; break;
         case 5: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 6>; tpb = 64; minb = 6; break;
         default: break;
         }
@@ -72,7 +71,9 @@ extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, 
     switch (mode) {
     case QO_TF_S21: if (pp == 4) fn = tf_pick<QO_TF_S21, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
     case QO_TF_S21_NOD: if (pp == 4) fn = tf_pick<QO_TF_S21_NOD, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
+    case QO_TF_S21_E: if (pp == 4) fn = tf_pick<QO_TF_S21_E, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
     case QO_TF_CPL: if (pp == 2) { fn = tf_pick<QO_TF_CPL, 2, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(K); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; } break;
+    case QO_TF_CPL_E: if (pp == 2) { fn = tf_pick<QO_TF_CPL_E, 2, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(K); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; } break;
     default: break;
     }
     if (!fn) return -1;
@@ -89,15 +90,25 @@ extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, 
 typedef std::complex<double> cplx;
 
 /* the device's expansion, in the same order and with the same normalisation */
-static void tf_expand_host(const double (*rec)[QO_TF_REC], int n_el, double rl, double zn, double *p, double *q, double *d)
+static void tf_expand_host(const double (*rec)[QO_TF_REC], int n_el, double rl, double zn, double *p, double *q, double *d, double *ee)
 {
     const int NC = 2 * QO_TF_MAXK + 2;
     for (int i = 0; i < NC; i++) p[i] = q[i] = d[i] = 0.0;
     p[0] = rl; q[0] = zn; d[0] = 1.0;
+    /* E(y) = prod_e (E0 + E1 y + E2 y^2), all 2 n_el + 1 coefficients (the kernel keeps the first K) */
+    const int NE = 2 * QO_TF_MAXEL + 1;
+    for (int i = 0; i < NE; i++) ee[i] = 0.0;
+    ee[0] = 1.0;
+    for (int e = n_el - 1; e >= 0; e--) {
+        double ne[2 * QO_TF_MAXEL + 1];
+        for (int i = 0; i < NE; i++)
+            ne[i] = fma(rec[e][6], ee[i], fma(rec[e][7], i >= 1 ? ee[i - 1] : 0.0, rec[e][8] * (i >= 2 ? ee[i - 2] : 0.0)));
+        for (int i = 0; i < NE; i++) ee[i] = ne[i];
+    }
     std::vector<double> na(NC), nb(NC), ndv(NC);
     for (int e = n_el - 1; e >= 0; e--) {
         const double *r = rec[e];
-        const bool series = r[6] != 0.0;
+        const bool series = r[9] != 0.0;
         double *a = series ? p : q, *b = series ? q : p;
         for (int i = 0; i < NC; i++) {
             const double a1 = i >= 1 ? a[i - 1] : 0.0, a2 = i >= 2 ? a[i - 2] : 0.0, b1 = i >= 1 ? b[i - 1] : 0.0, b2 = i >= 2 ? b[i - 2] : 0.0;
@@ -156,48 +167,76 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
     *wref = wr;
     const double zn = sqrt(hp->rs * hp->rl), zni = 1.0 / zn;
 
-    /* nominal, and both all-at-one-end corners of the tolerance box */
+    /* nominal, and both all-at-one-end corners of the tolerance box.  First pass: can |D|^2 be evaluated as the
+     * polynomial E(y) cut after K coefficients (dropped tail below 2e-12 of E everywhere on the grid)?  Second pass:
+     * the device algorithm of the chosen mode against the per-element evaluation. */
+    double trunc = 2e-12;
+    if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
+    int emode = has_d && !getenv("QO100NET_TF_NO_E");
     double worst = 0.0;
-    for (int corner = -1; corner <= 1; corner++) {
-        double rec[QO_TF_MAXEL][QO_TF_REC];
-        double nd[QO_TF_MAXEL][6];
-        int ser[QO_TF_MAXEL];
-        for (int e = 0; e < nl; e++) {
-            double p[6];
-            for (int k = 0; k < 6; k++) {
-                p[k] = hp->nom[e0 + e][k];
-                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)corner, hp->tmode[e0 + e][k]);
+    for (int pass = 0; pass < 2; pass++) {
+        for (int corner = -1; corner <= 1; corner++) {
+            double rec[QO_TF_MAXEL][QO_TF_REC];
+            double nd[QO_TF_MAXEL][6];
+            int ser[QO_TF_MAXEL];
+            for (int e = 0; e < nl; e++) {
+                double p[6];
+                for (int k = 0; k < 6; k++) {
+                    p[k] = hp->nom[e0 + e][k];
+                    if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)corner, hp->tmode[e0 + e][k]);
+                }
+                ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, nd[e]);
+                const double sc = ser[e] ? zni : zn;
+                rec[e][0] = nd[e][0] * sc; rec[e][1] = nd[e][1] * sc; rec[e][2] = nd[e][2] * sc;
+                rec[e][3] = nd[e][3]; rec[e][4] = nd[e][4]; rec[e][5] = nd[e][5];
+                rec[e][6] = nd[e][3] * nd[e][3]; rec[e][7] = fma(2.0 * nd[e][3], nd[e][5], -nd[e][4] * nd[e][4]); rec[e][8] = nd[e][5] * nd[e][5];
+                rec[e][9] = ser[e] ? 1.0 : 0.0;
             }
-            ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, nd[e]);
-            const double sc = ser[e] ? zni : zn;
-            rec[e][0] = nd[e][0] * sc; rec[e][1] = nd[e][1] * sc; rec[e][2] = nd[e][2] * sc;
-            rec[e][3] = nd[e][3]; rec[e][4] = nd[e][4]; rec[e][5] = nd[e][5]; rec[e][6] = ser[e] ? 1.0 : 0.0; rec[e][7] = 0.0;
-        }
-        double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2];
-        tf_expand_host(rec, nl, hp->rl, zn, pp, qq, dd);
-        for (int i = 2 * Kk; i < 2 * QO_TF_MAXK + 2; i++)
-            if (pp[i] != 0.0 || qq[i] != 0.0 || dd[i] != 0.0) QO_TF_NO("degree accounting");
-        for (int k = 0; k < nf; k++) {
-            const double x = two_pi * f[k] / wr;
-            const cplx P_ = tf_horner_host(pp, Kk, x), Q_ = tf_horner_host(qq, Kk, x) * zni, D_ = tf_horner_host(dd, Kk, x);
-            const double d2 = std::norm(D_);
-            if (!(d2 > 1e-70 && d2 < 1e70)) QO_TF_NO("|D|^2 leaves the range of the batched reciprocal");
-            if (!mask[k]) continue;
-            /* per-element evaluation, column vector from the load end */
-            const cplx sj(0.0, x);
-            cplx a(hp->rl, 0.0), b(1.0, 0.0);
-            for (int e = nl - 1; e >= 0; e--) {
-                const cplx N = nd[e][0] + sj * (nd[e][1] + sj * nd[e][2]), D = nd[e][3] + sj * (nd[e][4] + sj * nd[e][5]);
-                const cplx imm = N / D;
-                if (ser[e]) a += imm * b; else b += imm * a;
+            double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2], ee[2 * QO_TF_MAXEL + 1];
+            tf_expand_host(rec, nl, hp->rl, zn, pp, qq, dd, ee);
+            for (int i = 2 * Kk; i < 2 * QO_TF_MAXK + 2; i++)
+                if (pp[i] != 0.0 || qq[i] != 0.0 || dd[i] != 0.0) QO_TF_NO("degree accounting");
+            for (int k = 0; k < nf; k++) {
+                const double x = two_pi * f[k] / wr, y = -x * x;
+                if (pass == 0) {
+                    if (!emode) break;
+                    double tail = 0.0, full = 0.0, xp = 1.0;
+                    for (int m = 0; m <= 2 * nl; m++) { if (m >= Kk) tail += fabs(ee[m]) * xp; full += ee[m] * (m & 1 ? -xp : xp); xp *= x * x; }
+                    if (!(full > 0.0) || tail > trunc * full) emode = 0;
+                    continue;
+                }
+                const cplx P_ = tf_horner_host(pp, Kk, x), Q_ = tf_horner_host(qq, Kk, x) * zni;
+                double d2;
+                if (emode) { d2 = ee[Kk - 1]; for (int m = Kk - 2; m >= 0; m--) d2 = fma(d2, y, ee[m]); }
+                else d2 = std::norm(tf_horner_host(dd, Kk, x));
+                if (!(d2 > 1e-70 && d2 < 1e70)) QO_TF_NO("|D|^2 leaves the range of the batched reciprocal");
+                if (!mask[k]) continue;
+                /* per-element evaluation, column vector from the load end */
+                const cplx sj(0.0, x);
+                cplx a(hp->rl, 0.0), b(1.0, 0.0);
+                double dref = 1.0;
+                for (int e = nl - 1; e >= 0; e--) {
+                    const cplx N = nd[e][0] + sj * (nd[e][1] + sj * nd[e][2]), D = nd[e][3] + sj * (nd[e][4] + sj * nd[e][5]);
+                    const cplx imm = N / D;
+                    if (ser[e]) a += imm * b; else b += imm * a;
+                    dref *= std::norm(D);
+                }
+                /* |den|^2 = |numerator polynomial|^2 / |D|^2 against |per-element chain|^2 */
+                double rel;
+                if (*cpl_op >= 0) {
+                    /* P/D and Q/D as complex numbers (the coupler's row vector mixes them), plus the kernel's |D|^2 against the true one */
+                    const cplx Dc = tf_horner_host(dd, Kk, x);
+                    rel = 2.0 * (std::abs(P_ / Dc - a) + zn * std::abs(Q_ / Dc - b)) / (std::abs(a) + zn * std::abs(b)) + fabs(d2 / dref - 1.0);
+                } else {
+                    const double got = std::norm(P_ + hp->rs * Q_) / d2, ref = std::norm(a + hp->rs * b);
+                    rel = fabs(got - ref) / ref;
+                }
+                if (!(rel == rel)) QO_TF_NO("self-check produced a NaN");
+                if (rel > worst) worst = rel;
             }
-            double rel;
-            if (*cpl_op >= 0) rel = (std::abs(P_ / D_ - a) + zn * std::abs(Q_ / D_ - b)) / (std::abs(a) + zn * std::abs(b));
-            else rel = std::abs((P_ + hp->rs * Q_) / D_ - (a + hp->rs * b)) / std::abs(a + hp->rs * b);
-            if (!(rel == rel)) QO_TF_NO("self-check produced a NaN");
-            if (2.0 * rel > worst) worst = 2.0 * rel;
         }
     }
+    if (emode) *mode = *cpl_op >= 0 ? QO_TF_CPL_E : QO_TF_S21_E;
     *err = worst;
     double tol = 1e-10;
     const char *t = getenv("QO100NET_TF_TOL");

@@ -29,9 +29,13 @@
 
 #define QO_TF_MAXK 15            /* coefficients per Horner chain: degree <= 29 (lanes 30, 31 stay zero: free shuffle wrap-around) */
 #define QO_TF_MAXEL 24           /* lumped elements */
-#define QO_TF_REC 8              /* doubles per element record: N0 N1 N2 D0 D1 D2 series - */
+#define QO_TF_REC 10             /* doubles per element record: N0 N1 N2 D0 D1 D2 E0 E1 E2 series */
 
-enum { QO_TF_S21 = 0 /* Num, D */, QO_TF_S21_NOD = 1 /* D == 1: ideal L/C/R ladders */, QO_TF_CPL = 2 /* P, Q, D + coupler block */ };
+/* Kernel modes.  The "_E" modes evaluate |D(jx)|^2 as ONE real polynomial E(y) = prod_e |D_e|^2 in y = -x^2, cut after
+ * K coefficients: the branch denominators are 1 + (parasitic terms), so E's coefficients fall off like (w/w_SRF)^2m and
+ * the plan selects an _E mode only when the dropped tail stays below 2e-12 of E on the whole grid (qo_tf.cu). */
+enum { QO_TF_S21 = 0 /* Num, D */, QO_TF_S21_NOD = 1 /* D == 1: ideal L/C/R ladders */, QO_TF_CPL = 2 /* P, Q, D + coupler block */,
+       QO_TF_S21_E = 3 /* Num, E */, QO_TF_CPL_E = 4 /* P, Q, E + coupler block */ };
 
 struct TfParams {
     const DevProg *prog;
@@ -51,7 +55,9 @@ struct TfParams {
     const double *cplms;
 };
 
-template <int MODE> struct TfChains { static constexpr int n = MODE == QO_TF_S21 ? 4 : MODE == QO_TF_S21_NOD ? 2 : 6; };
+template <int MODE> struct TfChains {
+    static constexpr int n = MODE == QO_TF_S21 ? 4 : MODE == QO_TF_S21_NOD ? 2 : MODE == QO_TF_CPL ? 6 : MODE == QO_TF_S21_E ? 3 : 5;
+};
 
 /* per-sample element record: perturbed parameters -> N, D normalised to zn = sqrt(Rs Rl) */
 __device__ __forceinline__ void tf_derive(const DevProg *__restrict__ prog, int e, const double *__restrict__ x, double wr, double zn, double zni,
@@ -68,7 +74,9 @@ __device__ __forceinline__ void tf_derive(const DevProg *__restrict__ prog, int 
     const int series = qo_tf_element(prog->opcode[e], p, wr, nd);
     const double sc = series ? zni : zn;
     rec[0] = nd[0] * sc; rec[1] = nd[1] * sc; rec[2] = nd[2] * sc; rec[3] = nd[3]; rec[4] = nd[4]; rec[5] = nd[5];
-    rec[6] = series ? 1.0 : 0.0; rec[7] = 0.0;
+    /* |D(jx)|^2 = (d0 - d2 x^2)^2 + (d1 x)^2 = d0^2 + (2 d0 d2 - d1^2) y + d2^2 y^2,  y = -x^2 */
+    rec[6] = nd[3] * nd[3]; rec[7] = fma(2.0 * nd[3], nd[5], -nd[4] * nd[4]); rec[8] = nd[5] * nd[5];
+    rec[9] = series ? 1.0 : 0.0;
 }
 
 __device__ __forceinline__ double tf_up(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
@@ -121,8 +129,11 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
     constexpr int NCH = TfChains<MODE>::n;
-    constexpr bool CPL = MODE == QO_TF_CPL;
-    __shared__ __align__(16) double s_poly[WARPS][K * NCH];
+    constexpr bool CPL = MODE == QO_TF_CPL || MODE == QO_TF_CPL_E;
+    constexpr bool EMODE = MODE == QO_TF_S21_E || MODE == QO_TF_CPL_E;      /* last chain = E(y) */
+    constexpr bool HASD = MODE != QO_TF_S21_NOD;
+    constexpr int NROW = (NCH + 1) & ~1;                                      /* coefficients per table row (16-byte aligned rows) */
+    __shared__ __align__(16) double s_poly[WARPS][K * NROW];
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
     __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 2 : 2];
     __shared__ double s_x[WARPS][QO_MAX_VAR];
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         for (int e = P.n_el - 1; e >= 0; e--) {
             const double2 n01 = *(const double2 *)(elw + e * QO_TF_REC), n2d0 = *(const double2 *)(elw + e * QO_TF_REC + 2),
                           d12 = *(const double2 *)(elw + e * QO_TF_REC + 4);
-            const bool series = elw[e * QO_TF_REC + 6] != 0.0;
+            const bool series = elw[e * QO_TF_REC + 9] != 0.0;
             const double p1 = tf_up(p, up1), p2 = tf_up(p, up2), q1 = tf_up(q, up1), q2 = tf_up(q, up2);
             const double dp = fma(n2d0.y, p, fma(d12.x, p1, d12.y * p2)), dq = fma(n2d0.y, q, fma(d12.x, q1, d12.y * q2));
             if (series) {            /* Z = N/D: P <- D P + N Q, Q <- D Q */
@@ -169,20 +180,29 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             } else {                 /* Y = N/D: Q <- D Q + N P, P <- D P */
                 q = fma(n01.x, p, fma(n01.y, p1, fma(n2d0.x, p2, dq))); p = dp;
             }
-            if (MODE != QO_TF_S21_NOD) {
-                const double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
-                d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
+            if (HASD) {
+                double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
+                if (EMODE) {
+                    /* lane m holds the coefficient of y^m; E's degree may pass lane 29, so no free wrap-around here */
+                    const double2 e01 = *(const double2 *)(elw + e * QO_TF_REC + 6);
+                    const double e2 = elw[e * QO_TF_REC + 8];
+                    d1 = lane >= 1 ? d1 : 0.0; d2 = lane >= 2 ? d2 : 0.0;
+                    d = fma(e01.x, d, fma(e01.y, d1, e2 * d2));
+                } else d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
             }
         }
         /* chain table: step k holds the coefficients of sn^(2k) and sn^(2k+1) of every polynomial */
         if (lane < 2 * K) {
             const int k = lane >> 1, par = lane & 1;
-            if (CPL) { polyw[k * NCH + par] = p; polyw[k * NCH + 2 + par] = q; polyw[k * NCH + 4 + par] = d; }
-            else {
-                polyw[k * NCH + par] = fma(rs * P.zni, q, p);
-                if (MODE == QO_TF_S21) polyw[k * NCH + 2 + par] = d;
+            if (CPL) {
+                polyw[k * NROW + par] = p; polyw[k * NROW + 2 + par] = q;
+                if (!EMODE) polyw[k * NROW + 4 + par] = d;
+            } else {
+                polyw[k * NROW + par] = fma(rs * P.zni, q, p);
+                if (MODE == QO_TF_S21) polyw[k * NROW + 2 + par] = d;
             }
         }
+        if (EMODE && lane < K) polyw[lane * NROW + NCH - 1] = d;
         __syncwarp();
 
         /* 3. frequency loop */
@@ -200,23 +220,26 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             }
             double r[NCH][PTS];
 #pragma unroll
-            for (int c = 0; c < NCH; c += 2) {
-                const LadV2<double> cc = lad_lds2(polys + ((K - 1) * NCH + c) * 8u, 0.0);
+            for (int c = 0; c + 1 < NCH; c += 2) {
+                const LadV2<double> cc = lad_lds2(polys + ((K - 1) * NROW + c) * 8u, 0.0);
                 QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
             }
+            if (NCH & 1) { const double c1 = lad_lds1(polys + ((K - 1) * NROW + NCH - 1) * 8u, 0.0); QO_PTS r[NCH - 1][p] = c1; }
 #pragma unroll
             for (int k = K - 2; k >= 0; k--) {
 #pragma unroll
-                for (int c = 0; c < NCH; c += 2) {
-                    const LadV2<double> cc = lad_lds2(polys + (k * NCH + c) * 8u, 0.0);
+                for (int c = 0; c + 1 < NCH; c += 2) {
+                    const LadV2<double> cc = lad_lds2(polys + (k * NROW + c) * 8u, 0.0);
                     QO_PTS { r[c][p] = fma(r[c][p], y[p], cc.x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc.y); }
                 }
+                if (NCH & 1) { const double c1 = lad_lds1(polys + (k * NROW + NCH - 1) * 8u, 0.0); QO_PTS r[NCH - 1][p] = fma(r[NCH - 1][p], y[p], c1); }
             }
             /* n2 = |numerator|^2, dd = |denominator|^2  (|re + j x im|^2 = re^2 - y im^2) */
             double n2[PTS], dd[PTS];
             if (!CPL) {
                 QO_PTS { const double t = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t, r[0][p] * r[0][p]); }
                 if (MODE == QO_TF_S21) { QO_PTS { const double t = r[3][p] * r[3][p]; dd[p] = fma(-y[p], t, r[2][p] * r[2][p]); } }
+                else if (EMODE) { QO_PTS dd[p] = r[2][p]; }
                 else { QO_PTS dd[p] = 1.0; }
             } else {
                 double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS], kap[PTS];
@@ -246,8 +269,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                         const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
                         const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
                         n2[p] = fma(nr, nr, ni * ni);
-                        const double t = r[5][p] * r[5][p];
-                        dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * sg2[p];
+                        if (EMODE) dd[p] = r[4][p] * sg2[p];
+                        else { const double t = r[NCH - 1][p] * r[NCH - 1][p]; dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * sg2[p]; }
                     }
                 } else {
                     LadRow<double, PTS, 1> u;
@@ -259,8 +282,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                         const double nr = fma(u.ar[0][p], r[0][p], fma(-u.ai[0][p], pi_, fma(u.br[0][p], qr, -u.bi[0][p] * qi)));
                         const double ni = fma(u.ar[0][p], pi_, fma(u.ai[0][p], r[0][p], fma(u.br[0][p], qi, u.bi[0][p] * qr)));
                         n2[p] = fma(nr, nr, ni * ni);
-                        const double t = r[5][p] * r[5][p];
-                        dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p];
+                        if (EMODE) dd[p] = r[4][p] * kap[p];
+                        else { const double t = r[NCH - 1][p] * r[NCH - 1][p]; dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p]; }
                     }
                 }
             }

@@ -265,10 +265,20 @@ int qo_plan_launch(qo_plan *plan, uint64_t sample_offset, uint64_t n_samples, ui
 int qo_plan_read(qo_plan *plan, qo_mc_result *res);   /* synchronises, combines across the ctx's GPUs */
 double qo_plan_flops_per_eval(const qo_plan *plan);
 int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far by this plan */
-/* which kernel the plan launches: "qo_mc_ladder_kernel" (straight-line ladder family of
- * pcb/generic-filter), "qo_mc_lumped_kernel" (opcode interpreter) or "qo_mc_generic_kernel"
- * (microstrip).  QO100NET_KERNEL=interp in the environment forces the interpreter. */
+/* which kernel the plan launches: "qo_mc_tf_kernel" (transfer-function kernel: reduce-only |S21| jobs on lumped
+ * cascades, optionally behind one coupled-line block), "qo_mc_ladder_kernel" (straight-line ABCD-chain kernel of
+ * the pcb/generic-filter ladder family), "qo_mc_lumped_kernel" (opcode interpreter) or "qo_mc_generic_kernel"
+ * (microstrip).  QO100NET_KERNEL=ladder keeps jobs off the transfer-function kernel, =interp forces the interpreter. */
 const char *qo_plan_kernel_name(const qo_plan *plan);
+/* what the plan decided about the transfer-function kernel.  info[0] = selected (0/1), [1] = numerator chains (2 | 4),
+ * [2] = denominator form (0 none, 1 truncated |D|^2 polynomial, 2 complex D), [3] = coefficient pairs kept per numerator
+ * polynomial, [4] = denominator coefficients (form 1) / pairs (form 2) kept, [5] = structural degree;
+ * *self_check_err = worst relative disagreement on |den|^2 between the expansion and the per-element evaluation
+ * (nominal network + both ends of the tolerance box, every in-band grid point).  Returns the reason string
+ * ("ok", or why the job stays on the chain kernels). */
+const char *qo_plan_tf_info(const qo_plan *plan, int info[6], double *self_check_err);
+/* host->device bytes qo_plan_create copied for this plan (tables, masks, program), per GPU */
+uint64_t qo_plan_h2d_bytes(const qo_plan *plan);
 void qo_plan_destroy(qo_plan *plan);
 
 /* ---- reference stream: host-callable, bit-exact twins of the device code -- */

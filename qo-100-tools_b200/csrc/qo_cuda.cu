@@ -65,10 +65,10 @@ struct qo_plan {
     int nf, npairs, ncnt, precision, mode, generic;
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
-    int tf, tf_K, tf_mode, tf_el0, tf_nel, tf_cpl_op;     /* transfer-function kernel (qo_tf.cuh) */
-    double tf_wref, tf_err;                               /* normalising frequency; worst self-check disagreement */
+    int tf;                                               /* transfer-function kernel (qo_tf.cuh) selected */
+    TfPlan tfp;                                           /* its polynomial lengths, denominator form, self-check result */
     int tf_pp, tf_niter;                                  /* pairs per thread per iteration; iterations per sample */
-    const char *tf_reason;
+    unsigned long long h2d_bytes;                         /* host->device bytes copied by qo_plan_create, per GPU */
     const char *kernel_name;
     double flops_per_eval;
     int launches;
@@ -397,6 +397,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     p->precision = cfg && cfg->precision == 32 ? 32 : 64;
     p->mode = cfg ? cfg->mode : QO_MODE_FULL_S;
     p->launches = 0;
+    p->h2d_bytes = 0;
     memset(p->d, 0, sizeof p->d);
     int rc = build_prog(net, f, nf, spec, nspec, cfg, &p->hp, &p->generic, &p->flops_per_eval, &p->maskv);
     if (rc) { delete p; return rc; }
@@ -409,8 +410,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         const char *v = getenv("QO100NET_LAD_VARIANT");
         p->lad_variant = v ? atoi(v) : 0;
     }
-    p->tf = qo_tf_plan_check(&p->hp, p->mode == QO_MODE_REDUCE_ONLY, p->precision, p->generic, f, nf, p->maskv.data(), &p->tf_K, &p->tf_mode,
-                             &p->tf_wref, &p->tf_el0, &p->tf_nel, &p->tf_cpl_op, &p->tf_err, &p->tf_reason);
+    p->tf = qo_tf_plan_check(&p->hp, p->mode == QO_MODE_REDUCE_ONLY, p->precision, p->generic, f, nf, p->maskv.data(), &p->tfp);
     p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
@@ -466,7 +466,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     std::vector<double> ctab[4];
     std::vector<float> ctabf[4];
     p->cpl_fast = p->cpl_same = 0;
-    if ((p->ladder && p->lad_cpl) || (p->tf && p->tf_cpl_op >= 0)) {
+    if ((p->ladder && p->lad_cpl) || (p->tf && p->tfp.cpl_op >= 0)) {
         const DevProg *hp = &p->hp;
         const int ec = hp->op0;                    /* the coupler op */
         double wmax = 0;
@@ -529,36 +529,37 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     for (int g = 0; g < ctx->ndev; g++) {
         DevPlan *d = &p->d[g];
         rc = QO_ERR_CUDA;
+#define H2D(dst, src, nbytes) do { CUP(cudaMemcpyAsync((dst), (src), (nbytes), cudaMemcpyHostToDevice, st)); if (g == 0) p->h2d_bytes += (nbytes); } while (0)
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); qo_plan_destroy(p); return QO_ERR_CUDA; } } while (0)
         CUP(cudaSetDevice(ctx->d[g].device));
         cudaStream_t st = ctx->d[g].stream;
         CUP(cudaMallocAsync((void **)&d->prog, sizeof(DevProg), st));
-        CUP(cudaMemcpyAsync(d->prog, &p->hp, sizeof(DevProg), cudaMemcpyHostToDevice, st));
+        H2D(d->prog, &p->hp, sizeof(DevProg));
         if (!p->generic) {
             size_t esz = p->precision == 32 ? sizeof(float) : sizeof(double);
             CUP(cudaMallocAsync((void **)&d->w2, 2 * (size_t)np * esz, st));
             CUP(cudaMallocAsync((void **)&d->wi2, 2 * (size_t)np * esz, st));
             CUP(cudaMallocAsync((void **)&d->m2, 2 * (size_t)np, st));
             if (p->precision == 32) {
-                CUP(cudaMemcpyAsync(d->w2, wf.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
-                CUP(cudaMemcpyAsync(d->wi2, wif.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                H2D(d->w2, wf.data(), 2 * (size_t)np * esz);
+                H2D(d->wi2, wif.data(), 2 * (size_t)np * esz);
             } else {
-                CUP(cudaMemcpyAsync(d->w2, w.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
-                CUP(cudaMemcpyAsync(d->wi2, wi.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                H2D(d->w2, w.data(), 2 * (size_t)np * esz);
+                H2D(d->wi2, wi.data(), 2 * (size_t)np * esz);
             }
-            CUP(cudaMemcpyAsync(d->m2, m.data(), 2 * (size_t)np, cudaMemcpyHostToDevice, st));
+            H2D(d->m2, m.data(), 2 * (size_t)np);
             if (!sblk.empty()) {
                 CUP(cudaMallocAsync((void **)&d->sblk, sblk.size() * sizeof(double2), st));
-                CUP(cudaMemcpyAsync(d->sblk, sblk.data(), sblk.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+                H2D(d->sblk, sblk.data(), sblk.size() * sizeof(double2));
                 if (nonrecip) {
                     CUP(cudaMallocAsync((void **)&d->sdet, sdet.size() * sizeof(double2), st));
-                    CUP(cudaMemcpyAsync(d->sdet, sdet.data(), sdet.size() * sizeof(double2), cudaMemcpyHostToDevice, st));
+                    H2D(d->sdet, sdet.data(), sdet.size() * sizeof(double2));
                 }
             }
             if (p->tf) {
                 /* tables of the transfer-function kernel, padded to whole iterations (padding repeats the last grid
                  * point and carries no spec bit, so the loop needs no bounds checks) */
-                p->tf_pp = (p->tf_mode == QO_TF_CPL || p->tf_mode == QO_TF_CPL_E) ? 2 : 4;
+                p->tf_pp = qo_tf_default_pp(&p->tfp);
 #ifdef QO_TF_EXPERIMENT
                 if (getenv("QO100NET_TF_PP")) p->tf_pp = atoi(getenv("QO100NET_TF_PP"));
 #endif
@@ -573,7 +574,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 uchar2 *itm = (uchar2 *)(mb + npt);
                 for (size_t k = 0; k < npt; k++) {
                     const size_t kc = k < (size_t)nf ? k : (size_t)nf - 1;
-                    const double x = w[kc] / p->tf_wref;
+                    const double x = w[kc] / p->tfp.wref;
                     tab[k] = -(x * x); tab[npt + k] = x; tab[2 * npt + k] = w[kc];
                     if (p->cpl_fast) for (int t = 0; t < 4; t++) tab[(3 + t) * npt + k] = ctab[t][kc];
                     unsigned int word = 0;
@@ -590,7 +591,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                     itm[it] = make_uchar2(any, all);
                 }
                 CUP(cudaMallocAsync((void **)&d->tf_blob, bytes, st));
-                CUP(cudaMemcpyAsync(d->tf_blob, blob.data(), bytes, cudaMemcpyHostToDevice, st));
+                H2D(d->tf_blob, blob.data(), bytes);
                 CUP(cudaStreamSynchronize(st));
                 double *dt = (double *)d->tf_blob;
                 d->tf_yt = (double2 *)dt; d->tf_xt = (double2 *)(dt + npt); d->tf_wt = (double2 *)(dt + 2 * npt);
@@ -600,19 +601,19 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
             }
             if (p->ladder || p->tf) {
                 CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
-                CUP(cudaMemcpyAsync(d->wsq2, p->precision == 32 ? (const void *)wsqf.data() : (const void *)wsq.data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                H2D(d->wsq2, p->precision == 32 ? (const void *)wsqf.data() : (const void *)wsq.data(), 2 * (size_t)np * esz);
                 CUP(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), st));
                 if (p->cpl_fast)
                     for (int t = 0; t < 4; t++) {
                         CUP(cudaMallocAsync((void **)&d->cpl_tab[t], 2 * (size_t)np * esz, st));
-                        CUP(cudaMemcpyAsync(d->cpl_tab[t], p->precision == 32 ? (const void *)ctabf[t].data() : (const void *)ctab[t].data(), 2 * (size_t)np * esz, cudaMemcpyHostToDevice, st));
+                        H2D(d->cpl_tab[t], p->precision == 32 ? (const void *)ctabf[t].data() : (const void *)ctab[t].data(), 2 * (size_t)np * esz);
                     }
             }
         } else {
             CUP(cudaMallocAsync((void **)&d->fgrid, (size_t)nf * sizeof(double), st));
             CUP(cudaMallocAsync((void **)&d->mask, (size_t)nf, st));
-            CUP(cudaMemcpyAsync(d->fgrid, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, st));
-            CUP(cudaMemcpyAsync(d->mask, p->maskv.data(), (size_t)nf, cudaMemcpyHostToDevice, st));
+            H2D(d->fgrid, f, (size_t)nf * sizeof(double));
+            H2D(d->mask, p->maskv.data(), (size_t)nf);
         }
         CUP(cudaMallocAsync((void **)&d->counters, (size_t)p->ncnt * sizeof(unsigned long long), st));
         CUP(cudaMemsetAsync(d->counters, 0, (size_t)p->ncnt * sizeof(unsigned long long), st));
@@ -626,6 +627,14 @@ extern "C" int qo_plan_num_counters(const qo_plan *p) { return p ? p->ncnt : QO_
 extern "C" double qo_plan_flops_per_eval(const qo_plan *p) { return p ? p->flops_per_eval : 0.0; }
 extern "C" int qo_plan_launches(const qo_plan *p) { return p ? p->launches : QO_ERR_ARG; }
 extern "C" const char *qo_plan_kernel_name(const qo_plan *p) { return p ? p->kernel_name : ""; }
+extern "C" const char *qo_plan_tf_info(const qo_plan *p, int info[6], double *self_check_err)
+{
+    if (!p) return "";
+    if (info) { info[0] = p->tf; info[1] = p->tfp.nn; info[2] = p->tfp.den; info[3] = p->tfp.kn; info[4] = p->tfp.kd; info[5] = p->tfp.deg; }
+    if (self_check_err) *self_check_err = p->tfp.err;
+    return p->tfp.reason ? p->tfp.reason : "";
+}
+extern "C" uint64_t qo_plan_h2d_bytes(const qo_plan *p) { return p ? p->h2d_bytes : 0; }
 
 extern "C" int qo_plan_reset(qo_plan *p)
 {
@@ -739,24 +748,24 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.prog = d->prog;
     P.yt = d->tf_yt; P.xt = d->tf_xt; P.wt = d->tf_wt; P.mb = d->tf_mb; P.itm = d->tf_itm;
     P.cse = d->tf_ctab[0]; P.cce = d->tf_ctab[1]; P.cso = d->tf_ctab[2]; P.cco = d->tf_ctab[3];
-    P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tf_cpl_op;
+    P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tfp.cpl_op;
     /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
-    P.cpl_matched = p->tf_cpl_op >= 0 && hp->tvar[p->tf_cpl_op][5] < 0 && hp->nom[p->tf_cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
+    P.cpl_matched = p->tfp.cpl_op >= 0 && hp->tvar[p->tfp.cpl_op][5] < 0 && hp->nom[p->tfp.cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
     P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
     P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
-    P.wref = p->tf_wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
+    P.wref = p->tfp.wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
     for (int s = 0; s < QO_LAD_NSPEC; s++) {
         P.neg[s] = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
         P.thr[s] = s < hp->nspec ? hp->spec_thr[s] : 0.0;
     }
-    P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tf_nel; P.el0 = p->tf_el0; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tfp.n_el; P.el0 = p->tfp.el0; P.kn = p->tfp.kn; P.kd = p->tfp.kd; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
-    int rc = qo_tf_launch(p->tf_K, p->tf_mode, p->tf_pp, p->lad_variant, dc->sm_count, &P, dc->stream);
-    if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for K=%d mode=%d", p->tf_K, p->tf_mode); return QO_ERR_UNSUPPORTED; }
+    int rc = qo_tf_launch(&p->tfp, p->tf_pp, p->lad_variant, dc->sm_count, &P, dc->stream);
+    if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for nn=%d den=%d pp=%d", p->tfp.nn, p->tfp.den, p->tf_pp); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
     return QO_OK;
 }

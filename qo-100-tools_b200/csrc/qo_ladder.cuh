@@ -3,7 +3,7 @@
  * ladder family (reference: pcb/generic-filter/README.md:13 "up to 11th order",
  * qo-100-generic-filter.sch:1450-1488,1703-1995 -- alternating series / shunt
  * branches), optionally preceded by the coupled-line through section of
- * util/directional-couplers/*.trc (BASELINE configs 2 and 5).  sm_100a only.
+ * util/directional-couplers/<name>.trc (BASELINE configs 2 and 5).  sm_100a only.
  *
  * Why a second kernel next to the opcode interpreter of qo_lumped.cuh: ncu on the
  * interpreter (profiles/r01a_*) shows the FP64 pipe 47 % busy with 53 % of the
@@ -92,10 +92,10 @@ __device__ __forceinline__ float lad_lds1(unsigned int saddr, float)
  * FP32: one MUFU.RCP per point (1 ulp; a product of four would leave the float range). */
 template <int PTS> __device__ __forceinline__ void lad_rcp_batch(const double (&q)[PTS], double (&s)[PTS])
 {
-    static_assert(PTS == 2 || PTS == 4 || PTS == 8, "two, four or eight points per thread");
-    if (PTS == 8) {                      /* two batches of four */
+    static_assert(PTS == 2 || PTS % 4 == 0, "two points or a multiple of four points per thread");
+    if (PTS > 4) {                       /* batches of four */
 #pragma unroll
-        for (int h = 0; h < 8; h += 4) {
+        for (int h = 0; h < PTS; h += 4) {
             const double p01 = q[h] * q[h + 1], p23 = q[h + 2] * q[h + 3];
             const double r = qrcp(p01 * p23);
             const double r01 = r * p23, r23 = r * p01;

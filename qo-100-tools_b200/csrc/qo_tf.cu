@@ -11,70 +11,68 @@
 #include "qo_tf.cuh"
 #include "qo_tf_launch.h"
 
-/* launch shapes (tools/tf_sweep.py, profiles/r01h_*): the |S21| modes run 8 points per thread (coefficient loads and loop
- * overhead amortised over 8 Horner sets), the coupler mode 4 (six chains + the coupler block's state) */
+/* launch shapes (tools/tf_sweep.py, profiles/r01h_*): plain ladders run 8 points per thread (coefficient loads and loop
+ * overhead amortised over 8 Horner sets), the coupler mode 4 (four numerator chains + the coupler block's state) */
+#define QO_TF_PP 4
 #define QO_TF_TPB 128
 #define QO_TF_MINB 4
+#define QO_TF_CPL_PP 2
 #define QO_TF_CPL_TPB 128
-#define QO_TF_CPL_MINB 3
+#define QO_TF_CPL_MINB 4
 
 typedef void (*tf_fn)(const TfParams);
 
-template <int MODE, int PP, int TPB, int MINB> static tf_fn tf_pick(int K)
+extern "C" int qo_tf_default_pp(const TfPlan *tp) { return tp->nn == 4 ? QO_TF_CPL_PP : QO_TF_PP; }
+
+template <int NN, int PP, int TPB, int MINB> static tf_fn tf_pick(int den)
 {
-#define QO_TF_ROW(KK) case KK: return qo_mc_tf_kernel<KK, MODE, PP, TPB, MINB>;
-    switch (K) {
-        QO_TF_ROW(1) QO_TF_ROW(2) QO_TF_ROW(3) QO_TF_ROW(4) QO_TF_ROW(5) QO_TF_ROW(6) QO_TF_ROW(7) QO_TF_ROW(8)
-        QO_TF_ROW(9) QO_TF_ROW(10) QO_TF_ROW(11) QO_TF_ROW(12) QO_TF_ROW(13) QO_TF_ROW(14) QO_TF_ROW(15)
+    switch (den) {
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, PP, TPB, MINB>;
+    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, PP, TPB, MINB>;
+    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, PP, TPB, MINB>;
     default: return nullptr;
     }
-#undef QO_TF_ROW
 }
 
-extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st)
+extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st)
 {
     tf_fn fn = nullptr;
     int tpb = QO_TF_TPB, minb = QO_TF_MINB;
     (void)variant;
 #ifdef QO_TF_EXPERIMENT
-    /* development builds: launch shapes of the K = 12 |S21| kernel, chosen with QO100NET_LAD_VARIANT */
-    if (mode == QO_TF_S21 && K == 12 && pp == 4) {
-        switch (variant) {
-        case 1: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 128, 3>; tpb = 128; minb = 3; break;
-        case 2: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 256, 2>; tpb = 256; minb = 2; break;
-        case 3: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 8>; tpb = 64; minb = 8; break;
-        case 5: fn = qo_mc_tf_kernel<12, QO_TF_S21, 4, 64, 6>; tpb = 64; minb = 6; break;
+    /* development builds: other launch shapes, chosen with QO100NET_LAD_VARIANT (and QO100NET_TF_PP) */
+    if (tp->nn == 2 && pp == 4) switch (variant) {
+        case 1: fn = tf_pick<2, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 2: fn = tf_pick<2, 4, 256, 2>(tp->den); tpb = 256; minb = 2; break;
+        case 3: fn = tf_pick<2, 4, 128, 5>(tp->den); tpb = 128; minb = 5; break;
+        case 4: fn = tf_pick<2, 4, 128, 6>(tp->den); tpb = 128; minb = 6; break;
         default: break;
-        }
     }
-    if (mode == QO_TF_CPL && K == 12) {
-        if (pp == 2) switch (variant) {
-        case 1: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 128, 3>; tpb = 128; minb = 3; break;
-        case 2: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 128, 2>; tpb = 128; minb = 2; break;
-        case 3: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 2, 64, 6>; tpb = 64; minb = 6; break;
+    if (tp->nn == 2 && pp == 8) switch (variant) {
+        case 5: fn = tf_pick<2, 8, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 6: fn = tf_pick<2, 8, 128, 2>(tp->den); tpb = 128; minb = 2; break;
         default: break;
-        }
-        if (pp == 1) switch (variant) {
-        case 4: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 256, 2>; tpb = 256; minb = 2; break;
-        case 5: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 256, 3>; tpb = 256; minb = 3; break;
-        case 6: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 1, 128, 5>; tpb = 128; minb = 5; break;
+    }
+    if (tp->nn == 2 && pp == 2) switch (variant) {
+        case 7: fn = tf_pick<2, 2, 128, 8>(tp->den); tpb = 128; minb = 8; break;
+        case 8: fn = tf_pick<2, 2, 256, 4>(tp->den); tpb = 256; minb = 4; break;
         default: break;
-        }
-        if (pp == 4) switch (variant) {
-        case 7: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 4, 128, 2>; tpb = 128; minb = 2; break;
-        case 8: fn = qo_mc_tf_kernel<12, QO_TF_CPL, 4, 64, 4>; tpb = 64; minb = 4; break;
+    }
+    if (tp->nn == 4 && pp == 2) switch (variant) {
+        case 1: fn = tf_pick<4, 2, 128, 4>(tp->den); tpb = 128; minb = 4; break;
+        case 2: fn = tf_pick<4, 2, 256, 2>(tp->den); tpb = 256; minb = 2; break;
         default: break;
-        }
+    }
+    if (tp->nn == 4 && pp == 4) switch (variant) {
+        case 3: fn = tf_pick<4, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 4: fn = tf_pick<4, 4, 128, 2>(tp->den); tpb = 128; minb = 2; break;
+        default: break;
     }
     if (!fn)
 #endif
-    switch (mode) {
-    case QO_TF_S21: if (pp == 4) fn = tf_pick<QO_TF_S21, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
-    case QO_TF_S21_NOD: if (pp == 4) fn = tf_pick<QO_TF_S21_NOD, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
-    case QO_TF_S21_E: if (pp == 4) fn = tf_pick<QO_TF_S21_E, 4, QO_TF_TPB, QO_TF_MINB>(K); break;
-    case QO_TF_CPL: if (pp == 2) { fn = tf_pick<QO_TF_CPL, 2, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(K); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; } break;
-    case QO_TF_CPL_E: if (pp == 2) { fn = tf_pick<QO_TF_CPL_E, 2, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(K); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; } break;
-    default: break;
+    {
+        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den);
+        else if (tp->nn == 4 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
     }
     if (!fn) return -1;
     const unsigned long long warps = (unsigned long long)(tpb / 32);
@@ -130,13 +128,20 @@ static cplx tf_horner_host(const double *c, int K, double x)
     return cplx(re, im * x);
 }
 
+/* |poly(jx)| bookkeeping of one corner of the tolerance box */
+struct TfCorner {
+    double rec[QO_TF_MAXEL][QO_TF_REC];
+    double nd[QO_TF_MAXEL][6];
+    int ser[QO_TF_MAXEL];
+    double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2], ee[2 * QO_TF_MAXEL + 1];
+};
+
 extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
-                                const unsigned char *mask, int *K, int *mode, double *wref, int *el0, int *n_el, int *cpl_op,
-                                double *err, const char **reason)
+                                const unsigned char *mask, TfPlan *out)
 {
-    static const char *why = "";
-    *reason = why;
-#define QO_TF_NO(msg) do { *reason = msg; return 0; } while (0)
+    memset(out, 0, sizeof *out);
+    out->cpl_op = -1;
+#define QO_TF_NO(msg) do { out->reason = msg; return 0; } while (0)
     const char *force = getenv("QO100NET_KERNEL");
     if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
     if (generic || !mode_reduce_only || precision != 64 || hp->need_gd || hp->need_s11) QO_TF_NO("not a reduce-only FP64 |S21| job");
@@ -144,8 +149,7 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
     for (int s = 0; s < hp->nspec; s++)
         if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN) QO_TF_NO("spec kind");
     int e0 = hp->op0;
-    *cpl_op = -1;
-    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { *cpl_op = e0; e0++; }
+    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { out->cpl_op = e0; e0++; }
     const int nl = hp->n_ops - e0;
     if (nl < 1 || nl > QO_TF_MAXEL) QO_TF_NO("element count");
     int deg = 0, has_d = 0;
@@ -156,93 +160,143 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
         if (!(op == OP_SER_R || op == OP_SER_L || op == OP_SHUNT_C)) has_d = 1;     /* these have D == 1 exactly */
     }
     if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
-    const int Kk = deg / 2 + 1;
-    *K = Kk; *el0 = e0; *n_el = nl;
-    *mode = *cpl_op >= 0 ? QO_TF_CPL : has_d ? QO_TF_S21 : QO_TF_S21_NOD;
+    const int Kfull = deg / 2 + 1;
+    const bool cpl = out->cpl_op >= 0;
+    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = cpl ? 4 : 2;
 
     const double two_pi = 6.283185307179586476925286766559;
     double fmin = f[0], fmax = f[0];
     for (int k = 1; k < nf; k++) { if (f[k] < fmin) fmin = f[k]; if (f[k] > fmax) fmax = f[k]; }
     const double wr = two_pi * sqrt(fmin * fmax);
-    *wref = wr;
+    out->wref = wr;
     const double zn = sqrt(hp->rs * hp->rl), zni = 1.0 / zn;
 
-    /* nominal, and both all-at-one-end corners of the tolerance box.  First pass: can |D|^2 be evaluated as the
-     * polynomial E(y) cut after K coefficients (dropped tail below 2e-12 of E everywhere on the grid)?  Second pass:
-     * the device algorithm of the chosen mode against the per-element evaluation. */
-    double trunc = 2e-12;
-    if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
-    int emode = has_d && !getenv("QO100NET_TF_NO_E");
-    double worst = 0.0;
-    for (int pass = 0; pass < 2; pass++) {
-        for (int corner = -1; corner <= 1; corner++) {
-            double rec[QO_TF_MAXEL][QO_TF_REC];
-            double nd[QO_TF_MAXEL][6];
-            int ser[QO_TF_MAXEL];
-            for (int e = 0; e < nl; e++) {
-                double p[6];
-                for (int k = 0; k < 6; k++) {
-                    p[k] = hp->nom[e0 + e][k];
-                    if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)corner, hp->tmode[e0 + e][k]);
-                }
-                ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, nd[e]);
-                const double sc = ser[e] ? zni : zn;
-                rec[e][0] = nd[e][0] * sc; rec[e][1] = nd[e][1] * sc; rec[e][2] = nd[e][2] * sc;
-                rec[e][3] = nd[e][3]; rec[e][4] = nd[e][4]; rec[e][5] = nd[e][5];
-                rec[e][6] = nd[e][3] * nd[e][3]; rec[e][7] = fma(2.0 * nd[e][3], nd[e][5], -nd[e][4] * nd[e][4]); rec[e][8] = nd[e][5] * nd[e][5];
-                rec[e][9] = ser[e] ? 1.0 : 0.0;
+    /* expansions of the nominal network and of both all-at-one-end corners of the tolerance box */
+    std::vector<TfCorner> cs(3);
+    for (int ci = 0; ci < 3; ci++) {
+        TfCorner &c = cs[ci];
+        const double corner = (double)(ci - 1);
+        for (int e = 0; e < nl; e++) {
+            double p[6];
+            for (int k = 0; k < 6; k++) {
+                p[k] = hp->nom[e0 + e][k];
+                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], corner, hp->tmode[e0 + e][k]);
             }
-            double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2], ee[2 * QO_TF_MAXEL + 1];
-            tf_expand_host(rec, nl, hp->rl, zn, pp, qq, dd, ee);
-            for (int i = 2 * Kk; i < 2 * QO_TF_MAXK + 2; i++)
-                if (pp[i] != 0.0 || qq[i] != 0.0 || dd[i] != 0.0) QO_TF_NO("degree accounting");
+            c.ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, c.nd[e]);
+            const double sc = c.ser[e] ? zni : zn;
+            const double *nd = c.nd[e];
+            double *rec = c.rec[e];
+            rec[0] = nd[0] * sc; rec[1] = nd[1] * sc; rec[2] = nd[2] * sc; rec[3] = nd[3]; rec[4] = nd[4]; rec[5] = nd[5];
+            rec[6] = nd[3] * nd[3]; rec[7] = fma(2.0 * nd[3], nd[5], -nd[4] * nd[4]); rec[8] = nd[5] * nd[5];
+            rec[9] = c.ser[e] ? 1.0 : 0.0;
+        }
+        tf_expand_host(c.rec, nl, hp->rl, zn, c.pp, c.qq, c.dd, c.ee);
+        for (int i = 2 * Kfull; i < 2 * QO_TF_MAXK + 2; i++)
+            if (c.pp[i] != 0.0 || c.qq[i] != 0.0 || c.dd[i] != 0.0) QO_TF_NO("degree accounting");
+    }
+
+    /* Polynomial lengths: keep the terms the grid can see.  A kept length is accepted when the terms it drops add up to
+     * less than `trunc` (relative) at every grid point of all three expansions -- numerators against |P| + zn |Q|
+     * (|Num| for plain ladders), E against E.  QO100NET_TF_TRUNC=0 keeps everything. */
+    double trunc = 5e-13;
+    if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
+    const int NE = 2 * nl + 1;
+    std::vector<double> tail_n((size_t)Kfull + 1, 0.0), tail_e((size_t)NE + 1, 0.0), tail_d((size_t)Kfull + 1, 0.0);
+    for (int ci = 0; ci < 3; ci++) {
+        const TfCorner &c = cs[ci];
+        for (int k = 0; k < nf; k++) {
+            const double x = two_pi * f[k] / wr;
+            const cplx P_ = tf_horner_host(c.pp, Kfull, x), Q_ = tf_horner_host(c.qq, Kfull, x) * zni, D_ = tf_horner_host(c.dd, Kfull, x);
+            const double nref = cpl ? std::abs(P_) + zn * std::abs(Q_) : std::abs(P_ + hp->rs * Q_);
+            /* suffix sums: tail_n[K] = max over points of (terms of index >= 2K) / reference */
+            double acc = 0.0, xp = pow(x, 2.0 * Kfull - 1.0);
+            for (int i = 2 * Kfull - 1; i >= 0; i--) {
+                acc += (cpl ? fabs(c.pp[i]) + zn * zni * fabs(c.qq[i]) : fabs(c.pp[i] + hp->rs * zni * c.qq[i])) * xp;
+                if ((i & 1) == 0) { const double t = nref > 0 ? acc / nref : 1e300; if (t > tail_n[i / 2]) tail_n[i / 2] = t; }
+                xp /= x;
+            }
+            double accd = 0.0; xp = pow(x, 2.0 * Kfull - 1.0);
+            const double dref = std::abs(D_);
+            for (int i = 2 * Kfull - 1; i >= 0; i--) {
+                accd += fabs(c.dd[i]) * xp;
+                if ((i & 1) == 0) { const double t = dref > 0 ? accd / dref : 1e300; if (t > tail_d[i / 2]) tail_d[i / 2] = t; }
+                xp /= x;
+            }
+            double full = 0.0; xp = 1.0;
+            for (int m = 0; m < NE; m++) { full += c.ee[m] * (m & 1 ? -xp : xp); xp *= x * x; }
+            double acce = 0.0; xp = pow(x, 2.0 * (NE - 1));
+            for (int m = NE - 1; m >= 0; m--) {
+                acce += fabs(c.ee[m]) * xp;
+                const double t = full > 0 ? acce / full : 1e300;
+                if (t > tail_e[m]) tail_e[m] = t;
+                xp /= x * x;
+            }
+        }
+    }
+    int kn = Kfull, kdd = Kfull, ke = NE;
+    while (kn > 1 && tail_n[kn - 1] <= trunc) kn--;          /* dropping pairs kn-1.. leaves tail_n[kn-1] */
+    while (kdd > 1 && tail_d[kdd - 1] <= trunc) kdd--;
+    while (ke > 1 && tail_e[ke - 1] <= trunc) ke--;
+    ke = (ke + 1) & ~1;                                       /* the kernel loads E two coefficients at a time */
+    if (ke < 2) ke = 2;
+    out->kn = kn;
+    /* denominator form: the truncated |D|^2 polynomial when it is short enough to pay, else D itself; a form whose
+     * self-check fails (E loses digits next to a trap's notch, where |D| -> 0) hands over to the next one */
+    int forms[2], nforms = 0;
+    if (!has_d) forms[nforms++] = QO_TF_DEN_NONE;
+    else {
+        if (ke <= QO_TF_MAXKE && ke <= 2 * kdd + 3 && !getenv("QO100NET_TF_NO_E")) forms[nforms++] = QO_TF_DEN_E;
+        forms[nforms++] = QO_TF_DEN_D;
+    }
+    double tol = 1e-10;
+    if (getenv("QO100NET_TF_TOL")) tol = atof(getenv("QO100NET_TF_TOL"));
+    double worst = 0.0;
+    int accepted = 0;
+    for (int fi = 0; fi < nforms && !accepted; fi++) {
+        out->den = forms[fi];
+        out->kd = forms[fi] == QO_TF_DEN_E ? ke : forms[fi] == QO_TF_DEN_D ? kdd : 0;
+        /* self-check: exactly what the device evaluates (kept lengths, this denominator form) against the per-element evaluation */
+        worst = 0.0;
+        int range_ok = 1;
+        for (int ci = 0; ci < 3 && range_ok; ci++) {
+            const TfCorner &c = cs[ci];
             for (int k = 0; k < nf; k++) {
                 const double x = two_pi * f[k] / wr, y = -x * x;
-                if (pass == 0) {
-                    if (!emode) break;
-                    double tail = 0.0, full = 0.0, xp = 1.0;
-                    for (int m = 0; m <= 2 * nl; m++) { if (m >= Kk) tail += fabs(ee[m]) * xp; full += ee[m] * (m & 1 ? -xp : xp); xp *= x * x; }
-                    if (!(full > 0.0) || tail > trunc * full) emode = 0;
-                    continue;
-                }
-                const cplx P_ = tf_horner_host(pp, Kk, x), Q_ = tf_horner_host(qq, Kk, x) * zni;
-                double d2;
-                if (emode) { d2 = ee[Kk - 1]; for (int m = Kk - 2; m >= 0; m--) d2 = fma(d2, y, ee[m]); }
-                else d2 = std::norm(tf_horner_host(dd, Kk, x));
-                if (!(d2 > 1e-70 && d2 < 1e70)) QO_TF_NO("|D|^2 leaves the range of the batched reciprocal");
+                const cplx P_ = tf_horner_host(c.pp, kn, x), Q_ = tf_horner_host(c.qq, kn, x) * zni;
+                double d2 = 1.0;
+                if (out->den == QO_TF_DEN_E) { d2 = c.ee[out->kd - 1]; for (int m = out->kd - 2; m >= 0; m--) d2 = fma(d2, y, c.ee[m]); }
+                else if (out->den == QO_TF_DEN_D) d2 = std::norm(tf_horner_host(c.dd, out->kd, x));
+                if (!(d2 > 1e-70 && d2 < 1e70)) { range_ok = 0; break; }      /* the batched reciprocal multiplies four of them */
                 if (!mask[k]) continue;
                 /* per-element evaluation, column vector from the load end */
                 const cplx sj(0.0, x);
                 cplx a(hp->rl, 0.0), b(1.0, 0.0);
                 double dref = 1.0;
                 for (int e = nl - 1; e >= 0; e--) {
-                    const cplx N = nd[e][0] + sj * (nd[e][1] + sj * nd[e][2]), D = nd[e][3] + sj * (nd[e][4] + sj * nd[e][5]);
+                    const double *nd = c.nd[e];
+                    const cplx N = nd[0] + sj * (nd[1] + sj * nd[2]), D = nd[3] + sj * (nd[4] + sj * nd[5]);
                     const cplx imm = N / D;
-                    if (ser[e]) a += imm * b; else b += imm * a;
+                    if (c.ser[e]) a += imm * b; else b += imm * a;
                     dref *= std::norm(D);
                 }
-                /* |den|^2 = |numerator polynomial|^2 / |D|^2 against |per-element chain|^2 */
                 double rel;
-                if (*cpl_op >= 0) {
+                if (cpl) {
                     /* P/D and Q/D as complex numbers (the coupler's row vector mixes them), plus the kernel's |D|^2 against the true one */
-                    const cplx Dc = tf_horner_host(dd, Kk, x);
+                    const cplx Dc = tf_horner_host(c.dd, Kfull, x);
                     rel = 2.0 * (std::abs(P_ / Dc - a) + zn * std::abs(Q_ / Dc - b)) / (std::abs(a) + zn * std::abs(b)) + fabs(d2 / dref - 1.0);
                 } else {
                     const double got = std::norm(P_ + hp->rs * Q_) / d2, ref = std::norm(a + hp->rs * b);
                     rel = fabs(got - ref) / ref;
                 }
-                if (!(rel == rel)) QO_TF_NO("self-check produced a NaN");
+                if (!(rel == rel)) rel = 1e300;
                 if (rel > worst) worst = rel;
             }
         }
+        accepted = range_ok && worst <= tol;
     }
-    if (emode) *mode = *cpl_op >= 0 ? QO_TF_CPL_E : QO_TF_S21_E;
-    *err = worst;
-    double tol = 1e-10;
-    const char *t = getenv("QO100NET_TF_TOL");
-    if (t) tol = atof(t);
-    if (worst > tol) QO_TF_NO("polynomial expansion is too ill-conditioned on this grid");
-    *reason = "ok";
+    out->err = worst;
+    if (!accepted) QO_TF_NO("polynomial expansion is too ill-conditioned on this grid");
+    out->reason = "ok";
     return 1;
 #undef QO_TF_NO
 }

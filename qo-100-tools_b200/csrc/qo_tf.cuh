@@ -3,7 +3,7 @@
  *
  * Same job as the straight-line ladder kernel of qo_ladder.cuh (reduce-only |S21| yield of the pcb/generic-filter
  * ladder family, reference pcb/generic-filter/README.md:13, qo-100-generic-filter.sch:1450-1488,1703-1995, and of the
- * rf-tools ladders util/if-bandpass-filter/schematic.svg:191-213, docs/gpsdo-filters/*.svg:195-241), restructured so
+ * rf-tools ladders util/if-bandpass-filter/schematic.svg:191-213, docs/gpsdo-filters/<name>.svg:195-241), restructured so
  * that the per-POINT work no longer grows with a complex chain step per element:
  *
  *   every lumped branch is a ratio of real polynomials in s (qo_tf_core.h), so the cascade
@@ -12,10 +12,10 @@
  *   one element is a 3-tap convolution done with two warp shuffles per polynomial -- and per POINT each thread
  *   evaluates them at s = j x by Horner in y = -x^2 on the even / odd coefficients:
  *       den = (P + Rs Q) / D          |S21|^2 = 4 Rs Rl / |den|^2
- *   i.e. 4 real Horner chains of K = deg/2 + 1 coefficients (|Num|, |D|) -- 44 DFMA for the 11-element ladder with
- *   ESR/SRF parasitics (degree 22) instead of its ~145 chain instructions, and all of them FMAs.
- *   With the coupled-line block in front (BASELINE config 5) P and Q stay separate (6 chains) and are contracted
- *   with the block's row vector [1 Rs] k M_cpl of qo_ladder.cuh::lad_cpl_first.
+ *   i.e. real Horner chains (Num even / odd, and |D|^2) -- about 30 DFMA for the 11-element ladder with ESR/SRF
+ *   parasitics (degree 22) instead of its ~145 chain instructions, and all of them FMAs.
+ *   With the coupled-line block in front (BASELINE config 5) P and Q stay separate (4 chains) and are contracted
+ *   with the block's row vector [1 Rs] M_cpl (tf_cpl_matched below, or qo_ladder.cuh::lad_cpl_first).
  *
  * Accuracy: the monomial basis loses log10(kappa) digits, kappa = sum |c_k| x^k / |Num(jx)| (5e3 on the 0.1 dB
  * Chebyshev 11th-order pass-band edge: 4e-13 relative on |den|^2, measured against a 60-digit evaluation).  The
@@ -27,15 +27,18 @@
 #include "qo_ladder.cuh"
 #include "qo_tf_core.h"
 
-#define QO_TF_MAXK 15            /* coefficients per Horner chain: degree <= 29 (lanes 30, 31 stay zero: free shuffle wrap-around) */
+#define QO_TF_MAXK 15            /* coefficient PAIRS per numerator polynomial: degree <= 29 (lanes 30, 31 stay zero: free shuffle wrap-around) */
+#define QO_TF_MAXKE 30           /* coefficients of E(y) kept at most */
 #define QO_TF_MAXEL 24           /* lumped elements */
 #define QO_TF_REC 10             /* doubles per element record: N0 N1 N2 D0 D1 D2 E0 E1 E2 series */
 
-/* Kernel modes.  The "_E" modes evaluate |D(jx)|^2 as ONE real polynomial E(y) = prod_e |D_e|^2 in y = -x^2, cut after
- * K coefficients: the branch denominators are 1 + (parasitic terms), so E's coefficients fall off like (w/w_SRF)^2m and
- * the plan selects an _E mode only when the dropped tail stays below 2e-12 of E on the whole grid (qo_tf.cu). */
-enum { QO_TF_S21 = 0 /* Num, D */, QO_TF_S21_NOD = 1 /* D == 1: ideal L/C/R ladders */, QO_TF_CPL = 2 /* P, Q, D + coupler block */,
-       QO_TF_S21_E = 3 /* Num, E */, QO_TF_CPL_E = 4 /* P, Q, E + coupler block */ };
+/* How |D(jx)|^2 is evaluated:
+ *   QO_TF_DEN_NONE  D == 1 (ideal L / C / R ladders)
+ *   QO_TF_DEN_E     one real polynomial E(y) = prod_e |D_e|^2 in y = -x^2.  The branch denominators are 1 + (parasitic
+ *                   terms), so E's coefficients fall off like (w / w_SRF)^2m and the plan keeps only as many as the
+ *                   grid needs (dropped tail below 5e-13 of E everywhere on the grid, qo_tf.cu)
+ *   QO_TF_DEN_D     D(jx) itself, even and odd chain (networks with traps / tanks resonating inside the grid) */
+enum { QO_TF_DEN_NONE = 0, QO_TF_DEN_E = 1, QO_TF_DEN_D = 2 };
 
 struct TfParams {
     const DevProg *prog;
@@ -50,13 +53,10 @@ struct TfParams {
     double rs, rl, k21, hist_lo, hist_hi, wref, zn, zni;
     double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
     int neg[QO_LAD_NSPEC];
+    int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
     const double *cplms;
-};
-
-template <int MODE> struct TfChains {
-    static constexpr int n = MODE == QO_TF_S21 ? 4 : MODE == QO_TF_S21_NOD ? 2 : MODE == QO_TF_CPL ? 6 : MODE == QO_TF_S21_E ? 3 : 5;
 };
 
 /* per-sample element record: perturbed parameters -> N, D normalised to zn = sqrt(Rs Rl) */
@@ -109,12 +109,14 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
 }
 
 /*
- * K      coefficients per Horner chain            MODE   QO_TF_*
- * PP     frequency pairs per thread per iteration (PTS = 2*PP points)
+ * NN     numerator chains: 2 = Num (even, odd) for plain ladders, 4 = P and Q behind a coupled-line block
+ * DEN    QO_TF_DEN_*                  PP   frequency pairs per thread per iteration (PTS = 2*PP points)
  * One warp = one sample at a time (ticket hand-out as in qo_ladder.cuh); lane l owns pairs l, l+32, ... of each
- * iteration's PP*32 pairs.
+ * iteration's PP*32 pairs.  The polynomial lengths (P.kn pairs, P.kd) are run-time: the plan keeps the terms the
+ * grid can see (a 22nd-degree numerator whose top coefficients come from the parasitics needs 18 of them on a grid
+ * that ends at 6 fc, 14 on one that ends at 1.3 fc).
  *
- * Spec bookkeeping without divisions.  |den|^2 = n2 / dd (n2 = |Num|^2, dd = |D|^2, times 4|k|^2 behind a coupler):
+ * Spec bookkeeping without divisions.  |den|^2 = n2 / dd (n2 = |Num|^2, dd = |D|^2, times |Sg|^2 or 4|k|^2 behind a coupler):
  *   - the histogram spec needs the VALUE of its band's extreme: one batched reciprocal per iteration in which
  *     that band is active, running max (min) in a double;
  *   - every other spec only needs the SIGN of  g = thr*dd - n2  (S21_MIN_DB)  or  n2 - thr*dd  (S21_MAX_DB):
@@ -123,17 +125,14 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
  * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
  */
-template <int K, int MODE, int PP, int TPB, int MINB>
+template <int NN, int DEN, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
-    constexpr int NCH = TfChains<MODE>::n;
-    constexpr bool CPL = MODE == QO_TF_CPL || MODE == QO_TF_CPL_E;
-    constexpr bool EMODE = MODE == QO_TF_S21_E || MODE == QO_TF_CPL_E;      /* last chain = E(y) */
-    constexpr bool HASD = MODE != QO_TF_S21_NOD;
-    constexpr int NROW = (NCH + 1) & ~1;                                      /* coefficients per table row (16-byte aligned rows) */
-    __shared__ __align__(16) double s_poly[WARPS][K * NROW];
+    constexpr bool CPL = NN == 4;
+    __shared__ __align__(16) double s_num[WARPS][QO_TF_MAXK * NN];     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
+    __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : 2 * QO_TF_MAXK];   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
     __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 2 : 2];
     __shared__ double s_x[WARPS][QO_MAX_VAR];
@@ -144,13 +143,14 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     for (int i = threadIdx.x; i < ncnt; i += TPB) s_cnt[i] = 0;
     __syncthreads();
 
-    double *polyw = s_poly[warp], *elw = s_el[warp], *xw = s_x[warp];
-    const unsigned int polys = (unsigned int)__cvta_generic_to_shared(polyw);
+    double *numw = s_num[warp], *denw = s_den[warp], *elw = s_el[warp], *xw = s_x[warp];
+    const unsigned int nums = (unsigned int)__cvta_generic_to_shared(numw), dens = (unsigned int)__cvta_generic_to_shared(denw);
     const unsigned int cpls = (unsigned int)__cvta_generic_to_shared(s_cpl[warp]);
     const double rs = P.rs;
     const int up1 = (lane + 31) & 31, up2 = (lane + 30) & 31;
     const int hs = P.hist_spec;
     const bool hneg = hs >= 0 && P.neg[hs & (QO_LAD_NSPEC - 1)];
+    const int kn = P.kn, kd = P.kd;
 
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS;
     unsigned long long s = (unsigned long long)blockIdx.x * WARPS + warp;
@@ -166,8 +166,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             lad_derive<double>(P.prog, P.cpl_op, xw, s_cpl[warp], P.cplms ? P.cplms + 4 * s : NULL, nom_k);
         }
         __syncwarp();
-        /* 2. expand [P; Q] and D from the load end: lane i holds the coefficient of sn^i (lanes 30, 31 stay zero,
-         *    so the rotating shuffles bring zeros into lanes 0 and 1) */
+        /* 2. expand [P; Q] and D (or E) from the load end: lane i holds the coefficient of sn^i (of y^i for E); lanes 30, 31
+         *    of P, Q, D stay zero, so the rotating shuffles bring zeros into lanes 0 and 1 */
         double p = lane == 0 ? P.rl : 0.0, q = lane == 0 ? P.zn : 0.0, d = lane == 0 ? 1.0 : 0.0;
         for (int e = P.n_el - 1; e >= 0; e--) {
             const double2 n01 = *(const double2 *)(elw + e * QO_TF_REC), n2d0 = *(const double2 *)(elw + e * QO_TF_REC + 2),
@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             } else {                 /* Y = N/D: Q <- D Q + N P, P <- D P */
                 q = fma(n01.x, p, fma(n01.y, p1, fma(n2d0.x, p2, dq))); p = dp;
             }
-            if (HASD) {
+            if (DEN != QO_TF_DEN_NONE) {
                 double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
-                if (EMODE) {
+                if (DEN == QO_TF_DEN_E) {
                     /* lane m holds the coefficient of y^m; E's degree may pass lane 29, so no free wrap-around here */
                     const double2 e01 = *(const double2 *)(elw + e * QO_TF_REC + 6);
                     const double e2 = elw[e * QO_TF_REC + 8];
@@ -191,18 +191,14 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 } else d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
             }
         }
-        /* chain table: step k holds the coefficients of sn^(2k) and sn^(2k+1) of every polynomial */
-        if (lane < 2 * K) {
+        /* Horner tables (kept coefficients only; E is padded to an even count with a zero) */
+        if (lane < 2 * kn) {
             const int k = lane >> 1, par = lane & 1;
-            if (CPL) {
-                polyw[k * NROW + par] = p; polyw[k * NROW + 2 + par] = q;
-                if (!EMODE) polyw[k * NROW + 4 + par] = d;
-            } else {
-                polyw[k * NROW + par] = fma(rs * P.zni, q, p);
-                if (MODE == QO_TF_S21) polyw[k * NROW + 2 + par] = d;
-            }
+            if (CPL) { numw[k * NN + par] = p; numw[k * NN + 2 + par] = q; }
+            else numw[k * NN + par] = fma(rs * P.zni, q, p);
         }
-        if (EMODE && lane < K) polyw[lane * NROW + NCH - 1] = d;
+        if (DEN == QO_TF_DEN_E) { if (lane < kd) denw[lane] = d; }
+        if (DEN == QO_TF_DEN_D) { if (lane < 2 * kd) denw[lane] = d; }
         __syncwarp();
 
         /* 3. frequency loop */
@@ -218,31 +214,58 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 const double2 a = P.yt[j0 + 32 * qq];
                 y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
             }
-            double r[NCH][PTS];
+            /* numerator polynomials: Horner in y from the highest kept pair */
+            double r[NN][PTS];
+            {
+                unsigned int a = nums + (unsigned int)(kn - 1) * (NN * 8u);
 #pragma unroll
-            for (int c = 0; c + 1 < NCH; c += 2) {
-                const LadV2<double> cc = lad_lds2(polys + ((K - 1) * NROW + c) * 8u, 0.0);
-                QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
-            }
-            if (NCH & 1) { const double c1 = lad_lds1(polys + ((K - 1) * NROW + NCH - 1) * 8u, 0.0); QO_PTS r[NCH - 1][p] = c1; }
-#pragma unroll
-            for (int k = K - 2; k >= 0; k--) {
-#pragma unroll
-                for (int c = 0; c + 1 < NCH; c += 2) {
-                    const LadV2<double> cc = lad_lds2(polys + (k * NROW + c) * 8u, 0.0);
-                    QO_PTS { r[c][p] = fma(r[c][p], y[p], cc.x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc.y); }
+                for (int c = 0; c < NN; c += 2) {
+                    const LadV2<double> cc = lad_lds2(a + c * 8u, 0.0);
+                    QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
                 }
-                if (NCH & 1) { const double c1 = lad_lds1(polys + (k * NROW + NCH - 1) * 8u, 0.0); QO_PTS r[NCH - 1][p] = fma(r[NCH - 1][p], y[p], c1); }
+                /* kn - 1 Horner steps: one peeled when odd, then two per trip (no remainder loop) */
+#define QO_TF_NUM_STEP                                                                                                  \
+                {                                                                                                       \
+                    a -= NN * 8u;                                                                                       \
+                    _Pragma("unroll") for (int c = 0; c < NN; c += 2) {                                                 \
+                        const LadV2<double> cc = lad_lds2(a + c * 8u, 0.0);                                             \
+                        QO_PTS { r[c][p] = fma(r[c][p], y[p], cc.x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc.y); }      \
+                    }                                                                                                   \
+                }
+                if (!(kn & 1)) QO_TF_NUM_STEP
+#pragma unroll 2
+                for (int k = (kn - 1) >> 1; k > 0; k--) { QO_TF_NUM_STEP QO_TF_NUM_STEP }
+#undef QO_TF_NUM_STEP
             }
-            /* n2 = |numerator|^2, dd = |denominator|^2  (|re + j x im|^2 = re^2 - y im^2) */
-            double n2[PTS], dd[PTS];
+            /* dd = |D(jx)|^2 */
+            double dd[PTS];
+            if (DEN == QO_TF_DEN_E) {
+                unsigned int a = dens + (unsigned int)(kd - 2) * 8u;          /* kd is even: two coefficients per load */
+                { const LadV2<double> cc = lad_lds2(a, 0.0); QO_PTS dd[p] = fma(cc.y, y[p], cc.x); }
+#pragma unroll 2
+                for (int k = kd - 4; k >= 0; k -= 2) {
+                    a -= 16u;
+                    const LadV2<double> cc = lad_lds2(a, 0.0);
+                    QO_PTS { dd[p] = fma(dd[p], y[p], cc.y); dd[p] = fma(dd[p], y[p], cc.x); }
+                }
+            } else if (DEN == QO_TF_DEN_D) {
+                double de[PTS], dq[PTS];
+                unsigned int a = dens + (unsigned int)(kd - 1) * 16u;
+                { const LadV2<double> cc = lad_lds2(a, 0.0); QO_PTS { de[p] = cc.x; dq[p] = cc.y; } }
+#pragma unroll 4
+                for (int k = kd - 2; k >= 0; k--) {
+                    a -= 16u;
+                    const LadV2<double> cc = lad_lds2(a, 0.0);
+                    QO_PTS { de[p] = fma(de[p], y[p], cc.x); dq[p] = fma(dq[p], y[p], cc.y); }
+                }
+                QO_PTS { const double t = dq[p] * dq[p]; dd[p] = fma(-y[p], t, de[p] * de[p]); }     /* |re + j x im|^2 = re^2 - y im^2 */
+            } else { QO_PTS dd[p] = 1.0; }
+            /* n2 = |numerator|^2 (the coupler's row vector contracted with [P; Q]) */
+            double n2[PTS];
             if (!CPL) {
                 QO_PTS { const double t = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t, r[0][p] * r[0][p]); }
-                if (MODE == QO_TF_S21) { QO_PTS { const double t = r[3][p] * r[3][p]; dd[p] = fma(-y[p], t, r[2][p] * r[2][p]); } }
-                else if (EMODE) { QO_PTS dd[p] = r[2][p]; }
-                else { QO_PTS dd[p] = 1.0; }
             } else {
-                double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS], kap[PTS];
+                double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];
                 QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) {
@@ -258,33 +281,26 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                         }
                     }
                 }
+                double uar[PTS], uai[PTS], ubr[PTS], ubi[PTS], kap[PTS];
+                double zq;
                 if (P.cpl_matched) {
                     /* Rs == Zt: den = [(Pi - Nu) P + Zt (Pi + Nu) Q] / Sg */
-                    double uar[PTS], uai[PTS], ubr[PTS], ubi[PTS], sg2[PTS];
-                    if (P.cpl_fast) tf_cpl_matched<PTS, true>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, sg2);
-                    else tf_cpl_matched<PTS, false>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, sg2);
-                    const double zq = P.rs * P.zni;
-                    QO_PTS {
-                        const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
-                        const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
-                        const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
-                        n2[p] = fma(nr, nr, ni * ni);
-                        if (EMODE) dd[p] = r[4][p] * sg2[p];
-                        else { const double t = r[NCH - 1][p] * r[NCH - 1][p]; dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * sg2[p]; }
-                    }
+                    if (P.cpl_fast) tf_cpl_matched<PTS, true>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, kap);
+                    else tf_cpl_matched<PTS, false>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, kap);
+                    zq = P.rs * P.zni;
                 } else {
                     LadRow<double, PTS, 1> u;
                     if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
                     else lad_cpl_first<double, PTS, 1, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
-                    const double zni = P.zni;
-                    QO_PTS {
-                        const double pi_ = r[1][p] * x[p], qr = r[2][p] * zni, qi = (r[3][p] * x[p]) * zni;
-                        const double nr = fma(u.ar[0][p], r[0][p], fma(-u.ai[0][p], pi_, fma(u.br[0][p], qr, -u.bi[0][p] * qi)));
-                        const double ni = fma(u.ar[0][p], pi_, fma(u.ai[0][p], r[0][p], fma(u.br[0][p], qi, u.bi[0][p] * qr)));
-                        n2[p] = fma(nr, nr, ni * ni);
-                        if (EMODE) dd[p] = r[4][p] * kap[p];
-                        else { const double t = r[NCH - 1][p] * r[NCH - 1][p]; dd[p] = fma(-y[p], t, r[4][p] * r[4][p]) * kap[p]; }
-                    }
+                    QO_PTS { uar[p] = u.ar[0][p]; uai[p] = u.ai[0][p]; ubr[p] = u.br[0][p]; ubi[p] = u.bi[0][p]; }
+                    zq = P.zni;
+                }
+                QO_PTS {
+                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                    const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
+                    const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
+                    n2[p] = fma(nr, nr, ni * ni);
+                    dd[p] *= kap[p];
                 }
             }
             const uchar2 am = P.itm[it];
@@ -296,7 +312,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     if ((all >> sp) & 1u) {
                         if (sp == hs) {
                             double den2[PTS];
-                            if (MODE == QO_TF_S21_NOD) { QO_PTS den2[p] = n2[p]; }
+                            if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS den2[p] = n2[p]; }
                             else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
                             if (hneg) { QO_PTS trkv = den2[p] < trkv ? den2[p] : trkv; }
                             else { QO_PTS trkv = den2[p] > trkv ? den2[p] : trkv; }
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     if ((any >> sp) & 1u) {
                         if (sp == hs) {
                             double den2[PTS];
-                            if (MODE == QO_TF_S21_NOD) { QO_PTS den2[p] = n2[p]; }
+                            if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS den2[p] = n2[p]; }
                             else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
                             QO_PTS {
                                 const bool in = (mw[p] >> (8 * sp)) & 1u;

@@ -3,7 +3,7 @@
  * its plan-time self-check (qo_tf.cu, host).
  *
  * Every lumped branch of the util/ networks (reference: util/if-bandpass-filter/schematic.svg:191-213 series-LC /
- * parallel-LC branches, util/gpsdo-ouput-filters/10M/schematic.svg:197-231, docs/gpsdo-filters/*.svg:195-241 traps,
+ * parallel-LC branches, util/gpsdo-ouput-filters/10M/schematic.svg:197-231, docs/gpsdo-filters/<name>.svg:195-241 traps,
  * pcb/generic-filter/qo-100-generic-filter.sch:1450-1488 ladder positions with the ESR/SRF parasitic model of
  * SURVEY 8d) has an immittance that is a ratio of real polynomials of degree <= 2 in s = jw:
  *     series branch  Z(s) = N(s) / D(s)          shunt branch  Y(s) = N(s) / D(s)

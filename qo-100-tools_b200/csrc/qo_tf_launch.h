@@ -3,13 +3,24 @@
 #include <cuda_runtime.h>
 struct TfParams;
 struct DevProg;
-/* Can this job run on the transfer-function kernel?  Structural test + numerical self-check of the polynomial
- * expansion against the per-element evaluation at the nominal network and its tolerance-box corners, on every
- * grid point.  Returns 1 and fills K (coefficients per chain), mode (QO_TF_*), wref, el0/n_el (lumped ops), cpl_op,
- * err (worst relative disagreement on |den|^2 seen); 0 when the job must stay on the chain kernels (why: reason). */
+/* what the plan decided for a job that runs on the transfer-function kernel */
+struct TfPlan {
+    int nn;              /* numerator chains: 2 (plain ladder) or 4 (P and Q behind a coupled-line block) */
+    int den;             /* QO_TF_DEN_* */
+    int kn, kd;          /* coefficient pairs kept per numerator polynomial; E coefficients (even count) or D pairs kept */
+    int deg;             /* structural degree of the numerator polynomials */
+    int el0, n_el;       /* the lumped ops */
+    int cpl_op;          /* the coupled-line op in front, -1 = none */
+    double wref;         /* normalising angular frequency (geometric centre of the grid) */
+    double err;          /* worst relative disagreement on |den|^2 seen by the self-check */
+    const char *reason;  /* "ok", or why the job stays on the chain kernels */
+};
+/* Can this job run on the transfer-function kernel?  Structural test, choice of the polynomial lengths the grid needs,
+ * and a numerical self-check of exactly what the device will evaluate against the per-element evaluation, at the
+ * nominal network and at both ends of its tolerance box, on every grid point.  Returns 1 (plan filled) or 0. */
 extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
-                                const unsigned char *mask, int *K, int *mode, double *wref, int *el0, int *n_el, int *cpl_op,
-                                double *err, const char **reason);
-/* pp = frequency pairs per thread per iteration the plan padded its tables for (4: |S21| modes, 2: coupler mode);
- * returns 0, -1 when no instantiation covers (K, mode, pp), else the cudaError_t of the launch */
-extern "C" int qo_tf_launch(int K, int mode, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st);
+                                const unsigned char *mask, TfPlan *out);
+/* pp = frequency pairs per thread per iteration the plan padded its tables for; returns 0, -1 when no
+ * instantiation covers (nn, den, pp), else the cudaError_t of the launch */
+extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st);
+extern "C" int qo_tf_default_pp(const TfPlan *tp);

@@ -92,7 +92,7 @@ EXPORTS = [
     "qo_grid_lin", "qo_grid_log", "qo_ctx_create", "qo_ctx_create_on_device", "qo_ctx_set_stream",
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
-    "qo_plan_kernel_name",
+    "qo_plan_kernel_name", "qo_plan_tf_info", "qo_plan_h2d_bytes",
     "qo_s2p_load", "qo_s2p_from_arrays", "qo_s2p_num_points", "qo_s2p_z0", "qo_s2p_get", "qo_s2p_interp",
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
@@ -148,6 +148,8 @@ def lib():
         "qo_plan_flops_per_eval": (C.c_double, [vp]),
         "qo_plan_launches": (C.c_int, [vp]),
         "qo_plan_kernel_name": (C.c_char_p, [vp]),
+        "qo_plan_tf_info": (C.c_char_p, [vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
+        "qo_plan_h2d_bytes": (C.c_uint64, [vp]),
         "qo_s2p_load": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
         "qo_s2p_from_arrays": (C.c_int, [dp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(vp)]),
         "qo_s2p_num_points": (C.c_int, [vp]),
@@ -611,6 +613,20 @@ class Plan:
     def kernel_name(self):
         """Which kernel this plan launches (ladder / interpreter / microstrip)."""
         return lib().qo_plan_kernel_name(self._h).decode()
+
+    @property
+    def tf_info(self):
+        """The plan's decision about the transfer-function kernel (qo_plan_tf_info)."""
+        info = (C.c_int * 6)()
+        err = C.c_double(0.0)
+        reason = lib().qo_plan_tf_info(self._h, info, C.byref(err)).decode()
+        return dict(selected=bool(info[0]), numerator_chains=info[1], den_form=("none", "E", "D")[info[2]] if 0 <= info[2] <= 2 else "?",
+                    kn=info[3], kd=info[4], degree=info[5], self_check_err=err.value, reason=reason)
+
+    @property
+    def h2d_bytes(self):
+        """Host->device bytes qo_plan_create copied (per GPU)."""
+        return int(lib().qo_plan_h2d_bytes(self._h))
 
     def reset(self):
         _check(lib().qo_plan_reset(self._h))

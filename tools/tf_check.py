@@ -80,6 +80,8 @@ def main():
                 torch.cuda.synchronize()
             ms = a.elapsed_time(b) / args.reps
             name, fl = plan.kernel_name, plan.flops_per_eval
+            if kernel == "auto":
+                print("         tf plan:", plan.tf_info)
             plan.close()
             return ref, ms, name, fl
 

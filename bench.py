@@ -37,26 +37,32 @@ METRIC = "Monte Carlo network evals/s (samples x freq pts)"
 UNIT = "evals/s"
 SAMPLES_PER_GPU = 1000000
 NF = 4096
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-# ncu --set full capture (profiles/r01c_ladder_raw_metrics.txt): 154 KB read (tables + program), 0 written
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 154368
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel and its EXECUTED FP64 instruction
+# counts per eval, both from the committed ncu --set full captures (profiles/executed_fp64.json names the reports)
 
 
-def sass_fp64_per_eval(plan_kernel, wl_name):
-    """FP64-pipe instructions the ladder kernel EXECUTES per eval (static SASS census of the shipped .so,
-    tools/sass_count.py -> profiles/sass_counts.json); None for other kernels."""
-    if plan_kernel != "qo_mc_ladder_kernel":
-        return None
-    if wl_name.startswith("cfg5"):
-        # the coupler block holds two alternative code paths (table rotation / sincos), so the static census
-        # over-counts; this is the executed count from ncu (profiles/r01e_ladder_dynamic_fp64_counts.txt:
-        # dfma 117.0 + dmul 93.0 + dadd 11.0 per eval, + ~2 DSETP)
-        return 223.0
+def executed_profile(plan_kernel, wl_name):
+    """{"dfma", "dmul", "dadd" per eval, "dram_bytes_per_launch", "source"} of the kernel on this workload, or None."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "sass_counts.json")))
-        return d["n11_first0_cpl1" if wl_name.startswith("cfg5") else "n11_first0_cpl0"]["fp64_pipe_instr_per_eval"]
+        d = json.load(open(os.path.join(ROOT, "profiles", "executed_fp64.json")))
+        return d[plan_kernel]["cfg5" if wl_name.startswith("cfg5") else "cfg2"]
     except Exception:
         return None
+
+
+def time_plan(plan, stream, counters, nspg, steps, warmup, torch):
+    """mean kernel ms over `steps` launches of a resident plan (CUDA events on the launching stream)"""
+    with torch.cuda.stream(stream):
+        for i in range(warmup):
+            plan.launch(i * nspg, nspg, counters.data_ptr())
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record(stream)
+        for i in range(steps):
+            plan.launch((warmup + i) * nspg, nspg, counters.data_ptr())
+        b.record(stream)
+        torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
 
 
 def workload(name, n_samples):
@@ -228,7 +234,7 @@ def main():
 
         # end to end through the host-buffer C-ABI call (qo_mc_run): per step H2D of the grid, specs and
         # tolerance table, kernel, D2H of the counters; N > 1 adds the all-reduce of the host result
-        h2d = nf * 8 * 2 + nf + 13000            # w and 1/w tables, spec masks, device program (sizeof(DevProg))
+        h2d = plan.h2d_bytes                     # what qo_plan_create copies: frequency tables, spec masks, device program
         d2h = ncnt * 8
         for i in range(2):
             ctx.mc_run(wl.net, wl.f, wl.specs, wl.seed, nspg, wl.tols, sample_offset=rank * nspg, **wl.hist)
@@ -258,34 +264,66 @@ def main():
 
     flops = plan.flops_per_eval
     peak = ctx.measure_dfma_peak()                      # TFLOP/s, measured now on this GPU
-    achieved = flops * nspg * nf / (kernel_ms * 1e-3) * 1e-12
-    fp64_ipe = sass_fp64_per_eval(plan.kernel_name, wl.name)
-    # executed FP64-pipe instructions/s against the measured DFMA issue rate (peak TFLOP/s / 2)
-    pipe_util = fp64_ipe * nspg * nf / (kernel_ms * 1e-3) / (peak * 0.5e12) if fp64_ipe else None
+    evals_per_launch = nspg * nf
+    achieved = flops * evals_per_launch / (kernel_ms * 1e-3) * 1e-12
+
+    def executed(kernel, ms):
+        """executed FP64 work of `kernel` (ncu counts per eval) at the measured launch time: pipe utilisation = FP64-pipe
+        instructions/s over the measured DFMA issue rate (peak TFLOP/s / 2); executed TFLOP/s counts DFMA as 2"""
+        ex = executed_profile(kernel, wl.name)
+        if not ex:
+            return None
+        ipe = ex["dfma"] + ex["dmul"] + ex["dadd"]
+        rate = evals_per_launch / (ms * 1e-3)
+        return {"fp64_pipe_instr_per_eval": ipe, "dfma_per_eval": ex["dfma"], "pipe_util": ipe * rate / (peak * 0.5e12),
+                "tflops": (2 * ex["dfma"] + ex["dmul"] + ex["dadd"]) * rate * 1e-12,
+                "frac_of_peak": (2 * ex["dfma"] + ex["dmul"] + ex["dadd"]) * rate * 1e-12 / peak, "source": ex.get("source")}
+
+    ex = executed(plan.kernel_name, kernel_ms)
+    prof = executed_profile(plan.kernel_name, wl.name) or {}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl.name, "samples_per_gpu_per_step": nspg, "nf": nf, "elements": len(wl.net),
                    "flops_per_eval_alg_v1": flops, "parallelism": "samples sharded x%d, u64 counter all-reduce" % world,
-                   "l2": "no flush: the reduce-only path reads < 100 KB of tables by design (bytes/eval ~ 0); every "
+                   "l2": "no flush: the reduce-only path reads < 200 KB of tables by design (bytes/eval ~ 0); every "
                          "step draws a fresh global sample range",
+                   "kernel_plan": plan.tf_info if plan.kernel_name == "qo_mc_tf_kernel" else None,
                    "yield_last_step": last["n_pass"] / max(1, last["n_total"])},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "qo_mc_run (host buffers)"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH, "kernel": plan.kernel_name,
-                     "kernel_ms": kernel_ms,
-                     "fp64_pipe_instr_per_eval_sass": fp64_ipe, "pipe_util_from_sass": pipe_util,
-                     "note": "achieved = ALG-v1 algorithmic flops (SURVEY 8d: 2x2 chain + complex divides) / kernel time; "
-                             "the kernel executes fewer operations than ALG-v1 counts (row-vector chain, division-free "
-                             "immittances), so frac can exceed the FP64-pipe utilisation, which is pipe_util_from_sass "
-                             "(and sm__pipe_fp64_cycles_active in profiles/)",
+                     "traffic": prof.get("dram_bytes_per_launch"), "kernel": plan.kernel_name,
+                     "kernel_ms": kernel_ms, "executed": ex,
+                     "note": "achieved = ALG-v1 algorithmic flops/eval (SURVEY 8d: a 2x2 complex chain step and a complex divide "
+                             "per element) x evals / kernel time.  The transfer-function kernel expands the cascade into real "
+                             "polynomials once per sample and evaluates them by Horner per point, so it executes ~8x fewer "
+                             "operations than ALG-v1 counts and frac exceeds 1; `executed` is what the FP64 pipe really did "
+                             "(ncu instruction counts x the measured rate): pipe_util against the measured DFMA issue rate, "
+                             "frac_of_peak with DFMA = 2 flops.  `chain_kernel` is the same job on the straight-line ABCD-chain "
+                             "kernel (QO100NET_KERNEL=ladder), whose executed work is close to ALG-v1.",
                      "peak_source": "measured in this run: qo_measure_dfma_peak (8 independent DFMA chains/thread, "
                                     "best of 5); MEASURED_PEAKS.json has no FP64 figure (nominal 37.2 TFLOP/s)"},
     }
+    if not args.no_extras and plan.kernel_name == "qo_mc_tf_kernel":
+        # the same workload on the straight-line ABCD-chain kernel (north_star (c) as worded), for comparison
+        os.environ["QO100NET_KERNEL"] = "ladder"
+        try:
+            p2 = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, **wl.hist)
+            c2 = torch.zeros(ncnt, dtype=torch.int64, device="cuda")
+            ms2 = time_plan(p2, stream, c2, nspg, max(3, args.steps // 2), 2, torch)
+            line["roofline"]["chain_kernel"] = {"kernel": p2.kernel_name, "kernel_ms": ms2, "evals_per_s_per_gpu": evals_per_launch / (ms2 * 1e-3),
+                                                "alg_v1_tflops": flops * evals_per_launch / (ms2 * 1e-3) * 1e-12,
+                                                "alg_v1_frac": flops * evals_per_launch / (ms2 * 1e-3) * 1e-12 / peak,
+                                                "executed": executed(p2.kernel_name, ms2)}
+            p2.close()
+        except Exception as ex2:
+            line["roofline"]["chain_kernel"] = {"error": str(ex2)}
+        finally:
+            os.environ.pop("QO100NET_KERNEL", None)
     if not args.no_extras and world == 1:
         # CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only)
         from oracle import refbind as R

@@ -277,6 +277,10 @@ const char *qo_plan_kernel_name(const qo_plan *plan);
  * (nominal network + both ends of the tolerance box, every in-band grid point).  Returns the reason string
  * ("ok", or why the job stays on the chain kernels). */
 const char *qo_plan_tf_info(const qo_plan *plan, int info[6], double *self_check_err);
+/* the host-only part of qo_plan_create (network -> program, transfer-function analysis): needs no GPU.  Same outputs as
+ * qo_plan_tf_info; *seconds = host time the analysis took. */
+const char *qo_plan_analyze(const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec, const qo_mc_cfg *cfg,
+                            int info[6], double *self_check_err, double *seconds);
 /* host->device bytes qo_plan_create copied for this plan (tables, masks, program), per GPU */
 uint64_t qo_plan_h2d_bytes(const qo_plan *plan);
 void qo_plan_destroy(qo_plan *plan);

@@ -6,6 +6,7 @@
  * call returns QO_ERR_NO_DEVICE.
  */
 #include <cuda_runtime.h>
+#include <time.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -635,6 +636,36 @@ extern "C" const char *qo_plan_tf_info(const qo_plan *p, int info[6], double *se
     return p->tfp.reason ? p->tfp.reason : "";
 }
 extern "C" uint64_t qo_plan_h2d_bytes(const qo_plan *p) { return p ? p->h2d_bytes : 0; }
+
+/* host-only part of qo_plan_create: compile the network, decide about the transfer-function kernel (needs no GPU) */
+extern "C" const char *qo_plan_analyze(const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec, const qo_mc_cfg *cfg,
+                                       int info[6], double *self_check_err, double *seconds)
+{
+    qo_clear_error();
+    if (!net || !f || nf <= 0 || !info) return "bad arguments";
+    DevProg *hp = new DevProg;
+    int generic = 0;
+    double fl = 0;
+    std::vector<unsigned char> maskv;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    int rc = build_prog(net, f, nf, spec, nspec, cfg, hp, &generic, &fl, &maskv);
+    TfPlan tp;
+    memset(&tp, 0, sizeof tp);
+    const char *reason = "network does not compile";
+    if (rc == QO_OK) {
+        const int precision = cfg && cfg->precision == 32 ? 32 : 64;
+        const int mode = cfg ? cfg->mode : QO_MODE_FULL_S;
+        int sel = qo_tf_plan_check(hp, mode == QO_MODE_REDUCE_ONLY, precision, generic, f, nf, maskv.data(), &tp);
+        info[0] = sel; info[1] = tp.nn; info[2] = tp.den; info[3] = tp.kn; info[4] = tp.kd; info[5] = tp.deg;
+        if (self_check_err) *self_check_err = tp.err;
+        reason = tp.reason ? tp.reason : "";
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    delete hp;
+    return reason;
+}
 
 extern "C" int qo_plan_reset(qo_plan *p)
 {

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <complex>
 #include <vector>
+#include <mutex>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -124,7 +125,8 @@ static cplx tf_horner_host(const double *c, int K, double x)
 {
     const double y = -x * x;
     double re = c[2 * (K - 1)], im = c[2 * (K - 1) + 1];
-    for (int k = K - 2; k >= 0; k--) { re = fma(re, y, c[2 * k]); im = fma(im, y, c[2 * k + 1]); }
+    /* plain multiply-add: this is a conditioning check, not a bit-exact twin, and fma() is a libm call on the host */
+    for (int k = K - 2; k >= 0; k--) { re = re * y + c[2 * k]; im = im * y + c[2 * k + 1]; }
     return cplx(re, im * x);
 }
 
@@ -136,8 +138,54 @@ struct TfCorner {
     double pp[2 * QO_TF_MAXK + 2], qq[2 * QO_TF_MAXK + 2], dd[2 * QO_TF_MAXK + 2], ee[2 * QO_TF_MAXEL + 1];
 };
 
+static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
+                                  const unsigned char *mask, TfPlan *out);
+
+/* The analysis is a pure function of (program, grid, masks, environment overrides); callers that run the same job
+ * repeatedly through qo_mc_run (one plan per call) would redo ~2 ms of host work per call, so the last few results
+ * are kept, keyed by a 64-bit FNV-1a hash of those inputs. */
+static unsigned long long tf_fnv(unsigned long long h, const void *p, size_t n)
+{
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+struct TfCacheEntry { unsigned long long key; int used, sel; TfPlan plan; };
+static TfCacheEntry tf_cache[8];
+static int tf_cache_next;
+static std::mutex tf_cache_mu;
+
 extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
                                 const unsigned char *mask, TfPlan *out)
+{
+    unsigned long long key = 1469598103934665603ull;
+    key = tf_fnv(key, hp, sizeof *hp);
+    key = tf_fnv(key, f, (size_t)nf * sizeof(double));
+    key = tf_fnv(key, mask, (size_t)nf);
+    const int scal[4] = { mode_reduce_only, precision, generic, nf };
+    key = tf_fnv(key, scal, sizeof scal);
+    static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E" };
+    for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) {
+        const char *v = getenv(envs[i]);
+        key = tf_fnv(key, v ? v : "\1", v ? strlen(v) + 1 : 1);
+    }
+    {
+        std::lock_guard<std::mutex> lk(tf_cache_mu);
+        for (int i = 0; i < 8; i++)
+            if (tf_cache[i].used && tf_cache[i].key == key) { *out = tf_cache[i].plan; return tf_cache[i].sel; }
+    }
+    const int sel = tf_plan_check_uncached(hp, mode_reduce_only, precision, generic, f, nf, mask, out);
+    {
+        std::lock_guard<std::mutex> lk(tf_cache_mu);
+        TfCacheEntry &e = tf_cache[tf_cache_next];
+        tf_cache_next = (tf_cache_next + 1) & 7;
+        e.key = key; e.used = 1; e.sel = sel; e.plan = *out;
+    }
+    return sel;
+}
+
+static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
+                                  const unsigned char *mask, TfPlan *out)
 {
     memset(out, 0, sizeof *out);
     out->cpl_op = -1;
@@ -197,46 +245,51 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
 
     /* Polynomial lengths: keep the terms the grid can see.  A kept length is accepted when the terms it drops add up to
      * less than `trunc` (relative) at every grid point of all three expansions -- numerators against |P| + zn |Q|
-     * (|Num| for plain ladders), E against E.  QO100NET_TF_TRUNC=0 keeps everything. */
+     * (|Num| for plain ladders), D against |D|, E against E.  QO100NET_TF_TRUNC=0 keeps everything.
+     * Per point the scan runs from the top coefficient down and stops at the first term that may not be dropped. */
     double trunc = 5e-13;
     if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
-    const int NE = 2 * nl + 1;
-    std::vector<double> tail_n((size_t)Kfull + 1, 0.0), tail_e((size_t)NE + 1, 0.0), tail_d((size_t)Kfull + 1, 0.0);
-    for (int ci = 0; ci < 3; ci++) {
-        const TfCorner &c = cs[ci];
-        for (int k = 0; k < nf; k++) {
-            const double x = two_pi * f[k] / wr;
+    const int NE = 2 * nl + 1, NC = 2 * Kfull;
+    int kn = 1, kdd = 1, ke = 1;
+    std::vector<double> xg((size_t)nf), xpw((size_t)NC + 1), zpw((size_t)NE + 1);
+    for (int k = 0; k < nf; k++) xg[k] = two_pi * f[k] / wr;
+    /* |coefficient| tables of the three expansions (numerator entry: what the device's Num / [P; Q] pair carries) */
+    std::vector<double> an((size_t)3 * NC), ad((size_t)3 * NC), ae((size_t)3 * NE);
+    for (int ci = 0; ci < 3; ci++)
+        for (int i = 0; i < NC; i++) {
+            an[(size_t)ci * NC + i] = cpl ? fabs(cs[ci].pp[i]) + fabs(cs[ci].qq[i]) : fabs(cs[ci].pp[i] + hp->rs * zni * cs[ci].qq[i]);
+            ad[(size_t)ci * NC + i] = fabs(cs[ci].dd[i]);
+        }
+    for (int ci = 0; ci < 3; ci++)
+        for (int m = 0; m < NE; m++) ae[(size_t)ci * NE + m] = fabs(cs[ci].ee[m]);
+    for (int k = 0; k < nf; k++) {
+        const double x = xg[k], x2 = x * x;
+        xpw[0] = 1.0; for (int i = 1; i <= NC; i++) xpw[i] = xpw[i - 1] * x;
+        zpw[0] = 1.0; for (int m = 1; m <= NE; m++) zpw[m] = zpw[m - 1] * x2;
+        for (int ci = 0; ci < 3; ci++) {
+            const TfCorner &c = cs[ci];
             const cplx P_ = tf_horner_host(c.pp, Kfull, x), Q_ = tf_horner_host(c.qq, Kfull, x) * zni, D_ = tf_horner_host(c.dd, Kfull, x);
-            const double nref = cpl ? std::abs(P_) + zn * std::abs(Q_) : std::abs(P_ + hp->rs * Q_);
-            /* suffix sums: tail_n[K] = max over points of (terms of index >= 2K) / reference */
-            double acc = 0.0, xp = pow(x, 2.0 * Kfull - 1.0);
-            for (int i = 2 * Kfull - 1; i >= 0; i--) {
-                acc += (cpl ? fabs(c.pp[i]) + zn * zni * fabs(c.qq[i]) : fabs(c.pp[i] + hp->rs * zni * c.qq[i])) * xp;
-                if ((i & 1) == 0) { const double t = nref > 0 ? acc / nref : 1e300; if (t > tail_n[i / 2]) tail_n[i / 2] = t; }
-                xp /= x;
-            }
-            double accd = 0.0; xp = pow(x, 2.0 * Kfull - 1.0);
-            const double dref = std::abs(D_);
-            for (int i = 2 * Kfull - 1; i >= 0; i--) {
-                accd += fabs(c.dd[i]) * xp;
-                if ((i & 1) == 0) { const double t = dref > 0 ? accd / dref : 1e300; if (t > tail_d[i / 2]) tail_d[i / 2] = t; }
-                xp /= x;
-            }
-            double full = 0.0; xp = 1.0;
-            for (int m = 0; m < NE; m++) { full += c.ee[m] * (m & 1 ? -xp : xp); xp *= x * x; }
-            double acce = 0.0; xp = pow(x, 2.0 * (NE - 1));
-            for (int m = NE - 1; m >= 0; m--) {
-                acce += fabs(c.ee[m]) * xp;
-                const double t = full > 0 ? acce / full : 1e300;
-                if (t > tail_e[m]) tail_e[m] = t;
-                xp /= x * x;
+            const double nref = trunc * (cpl ? sqrt(std::norm(P_)) + zn * sqrt(std::norm(Q_)) : sqrt(std::norm(P_ + hp->rs * Q_)));
+            const double dref = trunc * sqrt(std::norm(D_));
+            const double *pn = &an[(size_t)ci * NC], *pd = &ad[(size_t)ci * NC], *pe = &ae[(size_t)ci * NE];
+            /* numerators: drop whole pairs (2K, 2K+1) from the top while their sum stays below the bound */
+            double acc = 0.0;
+            int K = Kfull;
+            while (K > kn) { acc += pn[2 * K - 1] * xpw[2 * K - 1] + pn[2 * K - 2] * xpw[2 * K - 2]; if (acc > nref) break; K--; }
+            if (K > kn) kn = K;
+            if (has_d) {
+                acc = 0.0; K = Kfull;
+                while (K > kdd) { acc += pd[2 * K - 1] * xpw[2 * K - 1] + pd[2 * K - 2] * xpw[2 * K - 2]; if (acc > dref) break; K--; }
+                if (K > kdd) kdd = K;
+                double full = 0.0;
+                for (int m = 0; m < NE; m++) full += c.ee[m] * (m & 1 ? -zpw[m] : zpw[m]);
+                const double eref = trunc * full;
+                acc = 0.0; K = NE;
+                while (K > ke) { acc += pe[K - 1] * zpw[K - 1]; if (!(acc <= eref)) break; K--; }
+                if (K > ke) ke = K;
             }
         }
     }
-    int kn = Kfull, kdd = Kfull, ke = NE;
-    while (kn > 1 && tail_n[kn - 1] <= trunc) kn--;          /* dropping pairs kn-1.. leaves tail_n[kn-1] */
-    while (kdd > 1 && tail_d[kdd - 1] <= trunc) kdd--;
-    while (ke > 1 && tail_e[ke - 1] <= trunc) ke--;
     ke = (ke + 1) & ~1;                                       /* the kernel loads E two coefficients at a time */
     if (ke < 2) ke = 2;
     out->kn = kn;
@@ -261,24 +314,28 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
         for (int ci = 0; ci < 3 && range_ok; ci++) {
             const TfCorner &c = cs[ci];
             for (int k = 0; k < nf; k++) {
-                const double x = two_pi * f[k] / wr, y = -x * x;
-                const cplx P_ = tf_horner_host(c.pp, kn, x), Q_ = tf_horner_host(c.qq, kn, x) * zni;
+                const double x = xg[k], y = -x * x;
                 double d2 = 1.0;
-                if (out->den == QO_TF_DEN_E) { d2 = c.ee[out->kd - 1]; for (int m = out->kd - 2; m >= 0; m--) d2 = fma(d2, y, c.ee[m]); }
+                if (out->den == QO_TF_DEN_E) { d2 = c.ee[out->kd - 1]; for (int m = out->kd - 2; m >= 0; m--) d2 = d2 * y + c.ee[m]; }
                 else if (out->den == QO_TF_DEN_D) d2 = std::norm(tf_horner_host(c.dd, out->kd, x));
                 if (!(d2 > 1e-70 && d2 < 1e70)) { range_ok = 0; break; }      /* the batched reciprocal multiplies four of them */
+                /* value check: every in-band point of the nominal network; the two corners on every 4th point and
+                 * around the band edges (their job is to catch a tolerance-driven loss of conditioning, which is smooth in x) */
                 if (!mask[k]) continue;
-                /* per-element evaluation, column vector from the load end */
-                const cplx sj(0.0, x);
-                cplx a(hp->rl, 0.0), b(1.0, 0.0);
-                double dref = 1.0;
+                if (ci != 1 && (k & 3) && k > 0 && k + 1 < nf && mask[k - 1] == mask[k] && mask[k + 1] == mask[k]) continue;
+                const cplx P_ = tf_horner_host(c.pp, kn, x), Q_ = tf_horner_host(c.qq, kn, x) * zni;
+                /* per-element evaluation, column vector from the load end: imm = N(jx) / D(jx) */
+                double ar = hp->rl, ai = 0.0, br = 1.0, bi = 0.0, dref = 1.0;
                 for (int e = nl - 1; e >= 0; e--) {
                     const double *nd = c.nd[e];
-                    const cplx N = nd[0] + sj * (nd[1] + sj * nd[2]), D = nd[3] + sj * (nd[4] + sj * nd[5]);
-                    const cplx imm = N / D;
-                    if (c.ser[e]) a += imm * b; else b += imm * a;
-                    dref *= std::norm(D);
+                    const double nr = nd[2] * y + nd[0], ni = nd[1] * x, dr = nd[5] * y + nd[3], di = nd[4] * x;
+                    const double dn = dr * dr + di * di, inv = 1.0 / dn;
+                    const double ir = (nr * dr + ni * di) * inv, ii = (ni * dr - nr * di) * inv;
+                    if (c.ser[e]) { const double tr = ir * br - ii * bi, ti = ir * bi + ii * br; ar += tr; ai += ti; }
+                    else { const double tr = ir * ar - ii * ai, ti = ir * ai + ii * ar; br += tr; bi += ti; }
+                    dref *= dn;
                 }
+                const cplx a(ar, ai), b(br, bi);
                 double rel;
                 if (cpl) {
                     /* P/D and Q/D as complex numbers (the coupler's row vector mixes them), plus the kernel's |D|^2 against the true one */

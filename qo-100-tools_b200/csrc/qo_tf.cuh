@@ -131,8 +131,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
     constexpr bool CPL = NN == 4;
-    __shared__ __align__(16) double s_num[WARPS][QO_TF_MAXK * NN];     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
-    __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : 2 * QO_TF_MAXK];   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
+    __shared__ __align__(16) double s_num[WARPS][(QO_TF_MAXK + 2) * NN];   /* two guard rows below row 0 (prefetch runs two steps ahead) */     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
+    __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : 2 * QO_TF_MAXK + 4];   /* + guard pairs */   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
     __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 2 : 2];
     __shared__ double s_x[WARPS][QO_MAX_VAR];
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     for (int i = threadIdx.x; i < ncnt; i += TPB) s_cnt[i] = 0;
     __syncthreads();
 
-    double *numw = s_num[warp], *denw = s_den[warp], *elw = s_el[warp], *xw = s_x[warp];
+    double *numw = s_num[warp] + 2 * NN, *denw = s_den[warp] + (DEN == QO_TF_DEN_NONE ? 0 : 4), *elw = s_el[warp], *xw = s_x[warp];
     const unsigned int nums = (unsigned int)__cvta_generic_to_shared(numw), dens = (unsigned int)__cvta_generic_to_shared(denw);
     const unsigned int cpls = (unsigned int)__cvta_generic_to_shared(s_cpl[warp]);
     const double rs = P.rs;
@@ -214,24 +214,29 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 const double2 a = P.yt[j0 + 32 * qq];
                 y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
             }
-            /* numerator polynomials: Horner in y from the highest kept pair */
+            /* numerator polynomials: Horner in y from the highest kept pair.  The coefficients of step k+1 are requested
+             * before the FMAs of step k (the row below row 0 is a guard row), so no chain waits on a shared-memory load */
             double r[NN][PTS];
             {
                 unsigned int a = nums + (unsigned int)(kn - 1) * (NN * 8u);
+                LadV2<double> cur[NN / 2], nxt[NN / 2];
 #pragma unroll
                 for (int c = 0; c < NN; c += 2) {
-                    const LadV2<double> cc = lad_lds2(a + c * 8u, 0.0);
-                    QO_PTS { r[c][p] = cc.x; r[c + 1][p] = cc.y; }
+                    cur[c / 2] = lad_lds2(a + c * 8u, 0.0);
+                    QO_PTS { r[c][p] = cur[c / 2].x; r[c + 1][p] = cur[c / 2].y; }
                 }
-                /* kn - 1 Horner steps: one peeled when odd, then two per trip (no remainder loop) */
+                a -= NN * 8u;
+#pragma unroll
+                for (int c = 0; c < NN; c += 2) nxt[c / 2] = lad_lds2(a + c * 8u, 0.0);
 #define QO_TF_NUM_STEP                                                                                                  \
                 {                                                                                                       \
                     a -= NN * 8u;                                                                                       \
+                    _Pragma("unroll") for (int c = 0; c < NN; c += 2) { cur[c / 2] = nxt[c / 2]; nxt[c / 2] = lad_lds2(a + c * 8u, 0.0); } \
                     _Pragma("unroll") for (int c = 0; c < NN; c += 2) {                                                 \
-                        const LadV2<double> cc = lad_lds2(a + c * 8u, 0.0);                                             \
-                        QO_PTS { r[c][p] = fma(r[c][p], y[p], cc.x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc.y); }      \
+                        QO_PTS { r[c][p] = fma(r[c][p], y[p], cur[c / 2].x); r[c + 1][p] = fma(r[c + 1][p], y[p], cur[c / 2].y); } \
                     }                                                                                                   \
                 }
+                /* kn - 1 Horner steps: one peeled when odd, then two per trip (no remainder loop) */
                 if (!(kn & 1)) QO_TF_NUM_STEP
 #pragma unroll 2
                 for (int k = (kn - 1) >> 1; k > 0; k--) { QO_TF_NUM_STEP QO_TF_NUM_STEP }
@@ -241,12 +246,15 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             double dd[PTS];
             if (DEN == QO_TF_DEN_E) {
                 unsigned int a = dens + (unsigned int)(kd - 2) * 8u;          /* kd is even: two coefficients per load */
-                { const LadV2<double> cc = lad_lds2(a, 0.0); QO_PTS dd[p] = fma(cc.y, y[p], cc.x); }
+                LadV2<double> cur = lad_lds2(a, 0.0), nxt;
+                QO_PTS dd[p] = fma(cur.y, y[p], cur.x);
+                a -= 16u;
+                nxt = lad_lds2(a, 0.0);
 #pragma unroll 2
                 for (int k = kd - 4; k >= 0; k -= 2) {
                     a -= 16u;
-                    const LadV2<double> cc = lad_lds2(a, 0.0);
-                    QO_PTS { dd[p] = fma(dd[p], y[p], cc.y); dd[p] = fma(dd[p], y[p], cc.x); }
+                    cur = nxt; nxt = lad_lds2(a, 0.0);
+                    QO_PTS { dd[p] = fma(dd[p], y[p], cur.y); dd[p] = fma(dd[p], y[p], cur.x); }
                 }
             } else if (DEN == QO_TF_DEN_D) {
                 double de[PTS], dq[PTS];

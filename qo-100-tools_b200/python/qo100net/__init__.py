@@ -92,7 +92,7 @@ EXPORTS = [
     "qo_grid_lin", "qo_grid_log", "qo_ctx_create", "qo_ctx_create_on_device", "qo_ctx_set_stream",
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
-    "qo_plan_kernel_name", "qo_plan_tf_info", "qo_plan_h2d_bytes",
+    "qo_plan_kernel_name", "qo_plan_tf_info", "qo_plan_h2d_bytes", "qo_plan_analyze",
     "qo_s2p_load", "qo_s2p_from_arrays", "qo_s2p_num_points", "qo_s2p_z0", "qo_s2p_get", "qo_s2p_interp",
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
@@ -150,6 +150,7 @@ def lib():
         "qo_plan_kernel_name": (C.c_char_p, [vp]),
         "qo_plan_tf_info": (C.c_char_p, [vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
         "qo_plan_h2d_bytes": (C.c_uint64, [vp]),
+        "qo_plan_analyze": (C.c_char_p, [vp, C.POINTER(C.c_double), C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "qo_s2p_load": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
         "qo_s2p_from_arrays": (C.c_int, [dp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(vp)]),
         "qo_s2p_num_points": (C.c_int, [vp]),
@@ -571,6 +572,19 @@ def _res_dict(res, fps, hist, nspec, hist_bins):
     return dict(n_pass=int(res.n_pass), n_total=int(res.n_total), fail_per_spec=fps[:nspec].copy(),
                 hist=hist[:hist_bins].copy(), seconds=res.seconds, evals_per_s=res.evals_per_s,
                 flops_per_eval=res.flops_per_eval)
+
+
+def plan_analyze(net, f, specs, tols=(), dist=DIST_UNIFORM, mode=MODE_REDUCE_ONLY, precision=64,
+                 hist_bins=0, hist_spec=0, hist_lo=0.0, hist_hi=1.0):
+    """Host-only part of plan creation (qo_plan_analyze, no GPU needed): which kernel family the job would take and the
+    transfer-function kernel's polynomial lengths / self-check result."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    cfg = _cfg(0, 0, list(tols), 0, dist, mode, precision, hist_bins, hist_spec, hist_lo, hist_hi)
+    info = (C.c_int * 6)()
+    err, sec = C.c_double(0.0), C.c_double(0.0)
+    reason = lib().qo_plan_analyze(net._h, _dp(f), len(f), _specs(specs), len(specs), C.byref(cfg), info, C.byref(err), C.byref(sec)).decode()
+    return dict(selected=bool(info[0]), numerator_chains=info[1], den_form=("none", "E", "D")[info[2]] if 0 <= info[2] <= 2 else "?",
+                kn=info[3], kd=info[4], degree=info[5], self_check_err=err.value, reason=reason, seconds=sec.value)
 
 
 class Plan:

@@ -378,3 +378,52 @@ def test_physical_coupled_line_element_validation(Q):
     for bad in ([cpl], [sub, cpl, cpl], [sub, (Q.CPL_MS, [1.69e-3, -1.0, 20e-3, 0.2, 2.4e9, 50.0])]):
         with pytest.raises(Q.QoError):
             Q.Net.from_elements(bad, 50, 50)
+
+
+def test_transfer_function_plan_analysis(Q, W, monkeypatch):
+    """Host-only part of plan creation (qo_plan_analyze, no GPU): which jobs take the transfer-function kernel, the
+    polynomial lengths the grid needs, the denominator form, and the self-check of the expansion against the
+    per-element evaluation (<= 1e-10 on |den|^2; north_star asks 1e-9)."""
+    for v in ("QO100NET_KERNEL", "QO100NET_TF_TOL", "QO100NET_TF_TRUNC", "QO100NET_TF_NO_E"):
+        monkeypatch.delenv(v, raising=False)
+    w = W.cfg2()
+    a = Q.plan_analyze(w.net, w.f, w.specs, w.tols, **w.hist)
+    assert a["selected"] and a["reason"] == "ok" and a["numerator_chains"] == 2 and a["den_form"] == "E" and a["degree"] == 22
+    assert a["kn"] < 12 and a["kd"] <= 16 and a["kd"] % 2 == 0      # the parasitic-order terms the grid cannot see are dropped
+    assert a["self_check_err"] < 1e-11
+    again = Q.plan_analyze(w.net, w.f, w.specs, w.tols, **w.hist)       # served from the analysis cache
+    assert {k: v for k, v in again.items() if k != "seconds"} == {k: v for k, v in a.items() if k != "seconds"}
+    monkeypatch.setenv("QO100NET_TF_TRUNC", "0")                     # keep every coefficient
+    full = Q.plan_analyze(w.net, w.f, w.specs, w.tols, **w.hist)
+    assert full["selected"] and full["kn"] == 12 and full["self_check_err"] < 1e-11
+    monkeypatch.delenv("QO100NET_TF_TRUNC")
+    w5 = W.cfg5()
+    a5 = Q.plan_analyze(w5.net, w5.f, w5.specs, w5.tols, **w5.hist)
+    assert a5["selected"] and a5["numerator_chains"] == 4 and a5["den_form"] == "E" and a5["kn"] <= a["kn"]   # grid ends at 1.33 fc
+    # ideal ladder: no denominator at all; elliptic filter with traps resonating inside the grid: complex-D form
+    ideal = Q.Net.cheby_lpf(11, 0.1, 10e6, 50.0, True)
+    ai = Q.plan_analyze(ideal, w.f, w.specs, Q.lc_tolerances(ideal, 0.05, 0.02))
+    assert ai["selected"] and ai["den_form"] == "none" and ai["degree"] == 11 and ai["kn"] == 6
+    _, ell, fc = W.gpsdo_bank()[1]
+    f = Q.grid_log(fc / 2.5, fc * 6.25, 1024)
+    ae = Q.plan_analyze(ell, f, [(Q.SPEC_S21_MIN_DB, 0.0, 0.8 * fc, -1.0)], Q.lc_tolerances(ell, 0.05, 0.05))
+    assert ae["selected"] and ae["den_form"] in ("D", "E") and ae["kn"] == 4 and ae["degree"] == 10   # 7th-order numerator inside a structural degree of 10
+    f4 = Q.grid_log(fc / 2.5, fc * 6.25, 4096)                            # a grid point 1e-4 from a notch: E(y) loses digits there, D takes over
+    assert Q.plan_analyze(ell, f4, [(Q.SPEC_S21_MIN_DB, 0.0, 0.8 * fc, -1.0), (Q.SPEC_S21_MAX_DB, 2.0 * fc, 1e99, -30.0)],
+                          Q.lc_tolerances(ell, 0.05, 0.05))["den_form"] == "D"
+    # jobs that stay on the chain kernels, with the reason
+    assert Q.plan_analyze(w.net, w.f, [(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], w.tols)["reason"] == "not a reduce-only FP64 |S21| job"
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=32)["selected"] is False
+    assert Q.plan_analyze(w.net, w.f, [], w.tols, mode=Q.MODE_FULL_S)["selected"] is False
+    tl = Q.Net.from_elements([(Q.TLINE, [50.0, 90.0, 1e9])] + w.net.elements, 50.0, 50.0)
+    assert Q.plan_analyze(tl, w.f, w.specs)["reason"] == "non-lumped element"
+    assert Q.plan_analyze(W.pa_lpf_net(), w.f, w.specs)["selected"] is False
+    monkeypatch.setenv("QO100NET_TF_TOL", "1e-16")
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, **w.hist)["reason"] == "polynomial expansion is too ill-conditioned on this grid"
+    monkeypatch.delenv("QO100NET_TF_TOL")
+    monkeypatch.setenv("QO100NET_KERNEL", "ladder")
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, **w.hist)["reason"] == "QO100NET_KERNEL override"
+    monkeypatch.delenv("QO100NET_KERNEL")
+    # a grid three decades wide: a 22nd-degree monomial basis cannot hold 1e-10 there -- the plan must notice
+    wide = Q.plan_analyze(w.net, Q.grid_log(1e4, 1e9, 2048), [(Q.SPEC_S21_MIN_DB, 0.0, 1e9, -300.0)], w.tols)
+    assert (not wide["selected"]) or wide["self_check_err"] <= 1e-10

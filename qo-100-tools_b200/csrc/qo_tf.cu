@@ -13,7 +13,7 @@
 #include "qo_tf_launch.h"
 
 /* launch shapes (tools/tf_sweep.py, profiles/r01h_*): plain ladders run 8 points per thread (coefficient loads and loop
- * overhead amortised over 8 Horner sets), the coupler mode 4 (four numerator chains + the coupler block's state) */
+ * overhead amortised over 8 Horner sets), the four-chain modes (coupler block, |S11| specs) 4 */
 #define QO_TF_PP 4
 #define QO_TF_TPB 128
 #define QO_TF_MINB 4
@@ -25,12 +25,12 @@ typedef void (*tf_fn)(const TfParams);
 
 extern "C" int qo_tf_default_pp(const TfPlan *tp) { return tp->nn == 4 ? QO_TF_CPL_PP : QO_TF_PP; }
 
-template <int NN, int PP, int TPB, int MINB> static tf_fn tf_pick(int den)
+template <int NN, bool CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den)
 {
     switch (den) {
-    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, PP, TPB, MINB>;
-    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, PP, TPB, MINB>;
-    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, PP, TPB, MINB>;
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, PP, TPB, MINB>;
+    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, CPL, S11, PP, TPB, MINB>;
+    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, CPL, S11, PP, TPB, MINB>;
     default: return nullptr;
     }
 }
@@ -43,37 +43,22 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
 #ifdef QO_TF_EXPERIMENT
     /* development builds: other launch shapes, chosen with QO100NET_LAD_VARIANT (and QO100NET_TF_PP) */
     if (tp->nn == 2 && pp == 4) switch (variant) {
-        case 1: fn = tf_pick<2, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
-        case 2: fn = tf_pick<2, 4, 256, 2>(tp->den); tpb = 256; minb = 2; break;
-        case 3: fn = tf_pick<2, 4, 128, 5>(tp->den); tpb = 128; minb = 5; break;
-        case 4: fn = tf_pick<2, 4, 128, 6>(tp->den); tpb = 128; minb = 6; break;
+        case 1: fn = tf_pick<2, false, false, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 2: fn = tf_pick<2, false, false, 4, 256, 2>(tp->den); tpb = 256; minb = 2; break;
+        case 3: fn = tf_pick<2, false, false, 4, 128, 5>(tp->den); tpb = 128; minb = 5; break;
         default: break;
     }
-    if (tp->nn == 2 && pp == 8) switch (variant) {
-        case 5: fn = tf_pick<2, 8, 128, 3>(tp->den); tpb = 128; minb = 3; break;
-        case 6: fn = tf_pick<2, 8, 128, 2>(tp->den); tpb = 128; minb = 2; break;
-        default: break;
-    }
-    if (tp->nn == 2 && pp == 2) switch (variant) {
-        case 7: fn = tf_pick<2, 2, 128, 8>(tp->den); tpb = 128; minb = 8; break;
-        case 8: fn = tf_pick<2, 2, 256, 4>(tp->den); tpb = 256; minb = 4; break;
-        default: break;
-    }
-    if (tp->nn == 4 && pp == 2) switch (variant) {
-        case 1: fn = tf_pick<4, 2, 128, 4>(tp->den); tpb = 128; minb = 4; break;
-        case 2: fn = tf_pick<4, 2, 256, 2>(tp->den); tpb = 256; minb = 2; break;
-        default: break;
-    }
-    if (tp->nn == 4 && pp == 4) switch (variant) {
-        case 3: fn = tf_pick<4, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
-        case 4: fn = tf_pick<4, 4, 128, 2>(tp->den); tpb = 128; minb = 2; break;
+    if (tp->cpl_op >= 0 && pp == 2) switch (variant) {
+        case 1: fn = tf_pick<4, true, false, 2, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 2: fn = tf_pick<4, true, false, 2, 256, 2>(tp->den); tpb = 256; minb = 2; break;
         default: break;
     }
     if (!fn)
 #endif
     {
-        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den);
-        else if (tp->nn == 4 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den);
+        else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
     }
     if (!fn) return -1;
     const unsigned long long warps = (unsigned long long)(tpb / 32);
@@ -192,10 +177,12 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
 #define QO_TF_NO(msg) do { out->reason = msg; return 0; } while (0)
     const char *force = getenv("QO100NET_KERNEL");
     if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
-    if (generic || !mode_reduce_only || precision != 64 || hp->need_gd || hp->need_s11) QO_TF_NO("not a reduce-only FP64 |S21| job");
+    if (generic || !mode_reduce_only || precision != 64 || hp->need_gd) QO_TF_NO("not a reduce-only FP64 |S21| / |S11| job");
     if (hp->nspec < 1 || hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) QO_TF_NO("spec / variable count");
     for (int s = 0; s < hp->nspec; s++)
-        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN) QO_TF_NO("spec kind");
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) QO_TF_NO("spec kind");
+    int need_s21 = 0;
+    for (int s = 0; s < hp->nspec; s++) if (hp->spec_kind[s] != SK_S11_MAX) need_s21 = 1;
     int e0 = hp->op0;
     if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { out->cpl_op = e0; e0++; }
     const int nl = hp->n_ops - e0;
@@ -209,8 +196,11 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     }
     if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
     const int Kfull = deg / 2 + 1;
-    const bool cpl = out->cpl_op >= 0;
-    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = cpl ? 4 : 2;
+    const bool cpl = out->cpl_op >= 0, s11 = hp->need_s11 != 0;
+    if (cpl && s11) QO_TF_NO("|S11| specs behind a coupled-line block");
+    if (!need_s21) has_d = 0;                                 /* S11 = (P - Rs Q) / (P + Rs Q): the branch denominators cancel */
+    const bool apart = cpl || s11;                            /* P and Q kept apart */
+    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = apart ? 4 : 2; out->s11 = s11;
 
     const double two_pi = 6.283185307179586476925286766559;
     double fmin = f[0], fmax = f[0];
@@ -257,7 +247,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     std::vector<double> an((size_t)3 * NC), ad((size_t)3 * NC), ae((size_t)3 * NE);
     for (int ci = 0; ci < 3; ci++)
         for (int i = 0; i < NC; i++) {
-            an[(size_t)ci * NC + i] = cpl ? fabs(cs[ci].pp[i]) + fabs(cs[ci].qq[i]) : fabs(cs[ci].pp[i] + hp->rs * zni * cs[ci].qq[i]);
+            an[(size_t)ci * NC + i] = apart ? fabs(cs[ci].pp[i]) + fabs(cs[ci].qq[i]) : fabs(cs[ci].pp[i] + hp->rs * zni * cs[ci].qq[i]);
             ad[(size_t)ci * NC + i] = fabs(cs[ci].dd[i]);
         }
     for (int ci = 0; ci < 3; ci++)
@@ -269,7 +259,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
         for (int ci = 0; ci < 3; ci++) {
             const TfCorner &c = cs[ci];
             const cplx P_ = tf_horner_host(c.pp, Kfull, x), Q_ = tf_horner_host(c.qq, Kfull, x) * zni, D_ = tf_horner_host(c.dd, Kfull, x);
-            const double nref = trunc * (cpl ? sqrt(std::norm(P_)) + zn * sqrt(std::norm(Q_)) : sqrt(std::norm(P_ + hp->rs * Q_)));
+            const double nref = trunc * (apart ? sqrt(std::norm(P_)) + zn * sqrt(std::norm(Q_)) : sqrt(std::norm(P_ + hp->rs * Q_)));
             const double dref = trunc * sqrt(std::norm(D_));
             const double *pn = &an[(size_t)ci * NC], *pd = &ad[(size_t)ci * NC], *pe = &ae[(size_t)ci * NE];
             /* numerators: drop whole pairs (2K, 2K+1) from the top while their sum stays below the bound */
@@ -343,7 +333,13 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
                     rel = 2.0 * (std::abs(P_ / Dc - a) + zn * std::abs(Q_ / Dc - b)) / (std::abs(a) + zn * std::abs(b)) + fabs(d2 / dref - 1.0);
                 } else {
                     const double got = std::norm(P_ + hp->rs * Q_) / d2, ref = std::norm(a + hp->rs * b);
-                    rel = fabs(got - ref) / ref;
+                    rel = need_s21 ? fabs(got - ref) / ref : 0.0;
+                    if (s11) {
+                        /* |S11|^2, relative with an absolute floor of -40 dB (return-loss nulls are not thresholds) */
+                        const double g11 = std::norm(P_ - hp->rs * Q_) / std::norm(P_ + hp->rs * Q_), r11 = std::norm(a - hp->rs * b) / ref;
+                        const double e11 = fabs(g11 - r11) / (r11 > 1e-4 ? r11 : 1e-4);
+                        if (e11 > rel) rel = e11;
+                    }
                 }
                 if (!(rel == rel)) rel = 1e300;
                 if (rel > worst) worst = rel;

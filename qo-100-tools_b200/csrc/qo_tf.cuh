@@ -53,6 +53,7 @@ struct TfParams {
     double rs, rl, k21, hist_lo, hist_hi, wref, zn, zni;
     double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
     int neg[QO_LAD_NSPEC];
+    int s11[QO_LAD_NSPEC];                   /* the spec is on |S11|^2 = |P - Rs Q|^2 / |P + Rs Q|^2 (FAIL iff > thr) */
     int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
@@ -109,7 +110,9 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
 }
 
 /*
- * NN     numerator chains: 2 = Num (even, odd) for plain ladders, 4 = P and Q behind a coupled-line block
+ * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
+ * CPL    coupled-line block in front (its row vector is contracted with [P; Q] per point)
+ * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
  * DEN    QO_TF_DEN_*                  PP   frequency pairs per thread per iteration (PTS = 2*PP points)
  * One warp = one sample at a time (ticket hand-out as in qo_ladder.cuh); lane l owns pairs l, l+32, ... of each
  * iteration's PP*32 pairs.  The polynomial lengths (P.kn pairs, P.kd) are run-time: the plan keeps the terms the
@@ -125,12 +128,14 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
  * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
  */
-template <int NN, int DEN, int PP, int TPB, int MINB>
+template <int NN, int DEN, bool CPL, bool S11, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
-    constexpr bool CPL = NN == 4;
+    static_assert(NN == 2 || NN == 4, "two or four numerator chains");
+    static_assert(!(CPL || S11) || NN == 4, "P and Q stay separate behind a coupler block and for |S11|");
+    static_assert(!(CPL && S11), "|S11| specs behind a coupler block run on the chain kernel");
     __shared__ __align__(16) double s_num[WARPS][(QO_TF_MAXK + 2) * NN];   /* two guard rows below row 0 (prefetch runs two steps ahead) */     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
     __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : 2 * QO_TF_MAXK + 4];   /* + guard pairs */   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
@@ -194,7 +199,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         /* Horner tables (kept coefficients only; E is padded to an even count with a zero) */
         if (lane < 2 * kn) {
             const int k = lane >> 1, par = lane & 1;
-            if (CPL) { numw[k * NN + par] = p; numw[k * NN + 2 + par] = q; }
+            if (NN == 4) { numw[k * NN + par] = p; numw[k * NN + 2 + par] = q; }
             else numw[k * NN + par] = fma(rs * P.zni, q, p);
         }
         if (DEN == QO_TF_DEN_E) { if (lane < kd) denw[lane] = d; }
@@ -269,8 +274,15 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 QO_PTS { const double t = dq[p] * dq[p]; dd[p] = fma(-y[p], t, de[p] * de[p]); }     /* |re + j x im|^2 = re^2 - y im^2 */
             } else { QO_PTS dd[p] = 1.0; }
             /* n2 = |numerator|^2 (the coupler's row vector contracted with [P; Q]) */
-            double n2[PTS];
-            if (!CPL) {
+            double n2[PTS], m2[PTS];                 /* m2 = |P - Rs Q|^2, the numerator of |S11|^2 (S11 kernels) */
+            if (S11) {
+                const double zq = P.rs * P.zni;
+                QO_PTS {
+                    const double ar = fma(zq, r[2][p], r[0][p]), ai = fma(zq, r[3][p], r[1][p]);
+                    const double br = fma(-zq, r[2][p], r[0][p]), bi = fma(-zq, r[3][p], r[1][p]);
+                    n2[p] = fma(-y[p], ai * ai, ar * ar); m2[p] = fma(-y[p], bi * bi, br * br);
+                }
+            } else if (!CPL) {
                 QO_PTS { const double t = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t, r[0][p] * r[0][p]); }
             } else {
                 double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];
@@ -311,55 +323,46 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     dd[p] *= kap[p];
                 }
             }
+            /* every spec tracks  numer / denom:  |den|^2 = n2 / dd  (|S21| specs),  |S11|^2 = m2 / n2 */
             const uchar2 am = P.itm[it];
             const unsigned int any = am.x, all = am.y;
-            if (any == all) {
-                /* one mask on every point of the iteration (possibly none) */
-#pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
-                    if ((all >> sp) & 1u) {
-                        if (sp == hs) {
-                            double den2[PTS];
-                            if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS den2[p] = n2[p]; }
-                            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
-                            if (hneg) { QO_PTS trkv = den2[p] < trkv ? den2[p] : trkv; }
-                            else { QO_PTS trkv = den2[p] > trkv ? den2[p] : trkv; }
-                        } else if (P.neg[sp]) {
-                            const double t = P.thr[sp];
-                            QO_PTS acc[sp] |= tf_hi(fma(-t, dd[p], n2[p]));
-                        } else {
-                            const double t = P.thr[sp];
-                            QO_PTS acc[sp] |= tf_hi(fma(t, dd[p], -n2[p]));
-                        }
-                    }
-                }
-            } else {
+            const bool uniform = any == all;            /* one mask on every point of the iteration (possibly none) */
+            unsigned int mw[PTS];
+            if (!uniform) {
                 /* the iteration straddles a band edge: per-point byte masks */
-                unsigned int mw[PTS];
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) {
                     const uint2 m = P.mb[j0 + 32 * qq];
                     mw[2 * qq] = m.x; mw[2 * qq + 1] = m.y;
                 }
+            }
 #pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
-                    if ((any >> sp) & 1u) {
-                        if (sp == hs) {
-                            double den2[PTS];
-                            if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS den2[p] = n2[p]; }
-                            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS den2[p] = n2[p] * rd[p]; }
+            for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+                if ((any >> sp) & 1u) {
+                    const bool on11 = S11 && P.s11[sp];
+                    if (sp == hs) {
+                        double val[PTS];
+                        if (on11) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; }
+                        else if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS val[p] = n2[p]; }
+                        else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS val[p] = n2[p] * rd[p]; }
+                        if (uniform) {
+                            if (hneg) { QO_PTS trkv = val[p] < trkv ? val[p] : trkv; }
+                            else { QO_PTS trkv = val[p] > trkv ? val[p] : trkv; }
+                        } else {
                             QO_PTS {
                                 const bool in = (mw[p] >> (8 * sp)) & 1u;
-                                if (hneg) { const double c = in ? den2[p] : 1.7e308; trkv = c < trkv ? c : trkv; }
-                                else { const double c = in ? den2[p] : -1.7e308; trkv = c > trkv ? c : trkv; }
-                            }
-                        } else {
-                            const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];
-                            QO_PTS {
-                                const double g = P.neg[sp] ? fma(t, dd[p], n2[p]) : fma(t, dd[p], -n2[p]);
-                                acc[sp] |= tf_hi(g) & __byte_perm(mw[p], 0, 0x1111 * sp);
+                                if (hneg) { const double c = in ? val[p] : 1.7e308; trkv = c < trkv ? c : trkv; }
+                                else { const double c = in ? val[p] : -1.7e308; trkv = c > trkv ? c : trkv; }
                             }
                         }
+                    } else {
+                        const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];
+                        unsigned int sg[PTS];
+                        if (on11) { QO_PTS sg[p] = tf_hi(fma(t, n2[p], -m2[p])); }
+                        else if (P.neg[sp]) { QO_PTS sg[p] = tf_hi(fma(t, dd[p], n2[p])); }
+                        else { QO_PTS sg[p] = tf_hi(fma(t, dd[p], -n2[p])); }
+                        if (uniform) { QO_PTS acc[sp] |= sg[p]; }
+                        else { QO_PTS acc[sp] |= sg[p] & __byte_perm(mw[p], 0, 0x1111 * sp); }
                     }
                 }
             }
@@ -390,7 +393,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
             if (hs >= 0) {
                 const double k21 = P.k21;
-                const double lin = hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
+                const double lin = (S11 && P.s11[hs & (QO_LAD_NSPEC - 1)]) ? trkv : hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
                 const double v = 10.0 * log10(lin);
                 const double xb = (v - P.hist_lo) / (P.hist_hi - P.hist_lo) * (double)P.hist_bins;
                 long long b = (long long)floor(xb);

@@ -5,7 +5,8 @@ struct TfParams;
 struct DevProg;
 /* what the plan decided for a job that runs on the transfer-function kernel */
 struct TfPlan {
-    int nn;              /* numerator chains: 2 (plain ladder) or 4 (P and Q behind a coupled-line block) */
+    int nn;              /* numerator chains: 2 (Num = P + Rs Q) or 4 (P and Q apart: behind a coupled-line block, or with |S11| specs) */
+    int s11;             /* the job has |S11| specs */
     int den;             /* QO_TF_DEN_* */
     int kn, kd;          /* coefficient pairs kept per numerator polynomial; E coefficients (even count) or D pairs kept */
     int deg;             /* structural degree of the numerator polynomials */

@@ -210,21 +210,56 @@ def test_cfg3_microstrip_yield_equals_oracle(Q, R, W, ctx):
 
 
 def test_s11_spec_and_histogram(Q, R, W, ctx, monkeypatch):
-    """|S11| specs: the ladder kernel's second row vector (and, forced, the interpreter's 2x2 chain) against the oracle;
-    with and without the coupler block."""
+    """|S11| specs against the oracle on every kernel that serves them: the transfer-function kernel (S11 =
+    (P - Rs Q) / (P + Rs Q); plain ladders), the chain kernel's second row vector (forced, and the default behind
+    the coupler block) and the interpreter's 2x2 chain; histogram on the |S11| spec and on the |S21| specs."""
     for w in (W.cfg2(), W.cfg5()):
         fc = 10e6 if w.name.startswith("cfg2") else 3e9
         w.specs = [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0), (Q.SPEC_S21_MAX_DB, 1.3 * fc, 1e99, -49.0), (Q.SPEC_S21_MIN_DB, 0, 0.5 * fc, -1.3)]
         for hs, lo, hi in ((0, -20.0, 0.0), (1, -60.0, -40.0), (2, -3.0, 0.0)):
             w.hist = dict(hist_bins=64, hist_spec=hs, hist_lo=lo, hist_hi=hi)
             monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+            plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+            assert plan.kernel_name == ("qo_mc_tf_kernel" if w.name.startswith("cfg2") else "qo_mc_ladder_kernel")
+            plan.close()
             og, gg = _mc_both(Q, R, ctx, w, 800)
             _assert_counts_equal(og, gg)
             assert 0 < gg["n_pass"] < 800
-            monkeypatch.setenv("QO100NET_KERNEL", "interp")
-            ig = ctx.mc_run(w.net, w.f, w.specs, w.seed, 800, w.tols, **w.hist)
-            _assert_counts_equal(ig, gg)
+            for force in ("ladder", "interp"):
+                monkeypatch.setenv("QO100NET_KERNEL", force)
+                ig = ctx.mc_run(w.net, w.f, w.specs, w.seed, 800, w.tols, **w.hist)
+                _assert_counts_equal(ig, gg)
     monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    # |S11| only (no denominator polynomial at all), and on the rf-tools / mixed lumped networks
+    w = W.cfg2()
+    only = [(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.5)]
+    plan = Q.Plan(ctx, w.net, w.f, only, seed=9, tols=w.tols, hist_bins=32, hist_spec=0, hist_lo=-20.0, hist_hi=0.0)
+    assert plan.kernel_name == "qo_mc_tf_kernel" and plan.tf_info["den_form"] == "none" and plan.tf_info["numerator_chains"] == 4
+    plan.launch(0, 700)
+    got = plan.read()
+    plan.close()
+    ref = R.mc_run(to_ref(R, w.net), 50, 50, w.f, only, R.mc_cfg(9, 700, w.tols, hist_bins=32, hist_spec=0, hist_lo=-20.0, hist_hi=0.0), nthreads=8)
+    _assert_counts_equal(ref, got)
+    assert int(got["hist"].sum()) == 700 and np.count_nonzero(got["hist"]) > 3      # the worst in-band |S11| spreads over several bins
+    for name, net, fc in _mixed_lumped_nets(Q, W):
+        f = Q.grid_log(fc / 3.0, fc * 4.0, 777)
+        sw = ctx.sweep(net, f)
+        db21, db11 = 20 * np.log10(np.abs(sw[1])), 20 * np.log10(np.abs(sw[0]))
+        pb = db21 >= db21.max() - 0.5
+        f_lo, f_hi = float(f[pb].min()) * 1.03, float(f[pb].max()) * 0.97
+        inb = (f >= f_lo) & (f <= f_hi)
+        specs = [(Q.SPEC_S11_MAX_DB, f_lo, f_hi, float(db11[inb].max()) + 0.7), (Q.SPEC_S21_MIN_DB, f_lo, f_hi, float(db21[inb].min()) - 0.1)]
+        tols = Q.lc_tolerances(net, 0.05, 0.05)
+        hist = dict(hist_bins=40, hist_spec=0, hist_lo=float(db11[inb].max()) - 10.0, hist_hi=0.0)
+        plan = Q.Plan(ctx, net, f, specs, seed=4, tols=tols, **hist)
+        assert plan.kernel_name == "qo_mc_tf_kernel", (name, plan.tf_info)
+        plan.launch(0, 500)
+        got = plan.read()
+        plan.close()
+        rs, rl = net.terminations
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(4, 500, tols, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)
+        assert int(got["fail_per_spec"].sum()) > 0, name
 
 
 def test_full_s_mode_vs_oracle(Q, R, W, ctx):
@@ -377,7 +412,12 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     monkeypatch.setenv("QO100NET_TF_TOL", "1e-16")
     p = mk(w.specs); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                                      # ... or the plan's self-check rejects the expansion
     monkeypatch.delenv("QO100NET_TF_TOL", raising=False)
-    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()      # |S11|: second row vector
+    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()          # |S11| = |P - Rs Q| / |P + Rs Q|
+    monkeypatch.setenv("QO100NET_KERNEL", "ladder")
+    p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()      # chain kernel: second row vector
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    p = Q.Plan(ctx, W.cfg5().net, W.cfg5().f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], seed=1, tols=W.cfg5().tols)
+    assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                                                      # |S11| behind the coupler block
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()         # group delay: interpreter
     p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
     p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode

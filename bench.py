@@ -172,6 +172,8 @@ def main():
         run_reference(args, rank, world)
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout; this script prints ONE JSON line there
     import torch
     import qo100net as Q
     from qo100net import dist as qd

@@ -324,48 +324,63 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 }
             }
             /* every spec tracks  numer / denom:  |den|^2 = n2 / dd  (|S21| specs),  |S11|^2 = m2 / n2 */
+#define QO_TF_VALUE(val)                                                                                          \
+            double val[PTS];                                                                                      \
+            if (S11 && P.s11[sp]) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; }   \
+            else if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS val[p] = n2[p]; }                                     \
+            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS val[p] = n2[p] * rd[p]; }
+#define QO_TF_SIGN(sg)                                                                                            \
+            unsigned int sg[PTS];                                                                                 \
+            {                                                                                                     \
+                const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];                                              \
+                if (S11 && P.s11[sp]) { QO_PTS sg[p] = tf_hi(fma(t, n2[p], -m2[p])); }                             \
+                else if (P.neg[sp]) { QO_PTS sg[p] = tf_hi(fma(t, dd[p], n2[p])); }                                \
+                else { QO_PTS sg[p] = tf_hi(fma(t, dd[p], -n2[p])); }                                              \
+            }
             const uchar2 am = P.itm[it];
             const unsigned int any = am.x, all = am.y;
-            const bool uniform = any == all;            /* one mask on every point of the iteration (possibly none) */
-            unsigned int mw[PTS];
-            if (!uniform) {
+            if (any == all) {
+                /* one mask on every point of the iteration (possibly none): no per-point selects */
+#pragma unroll
+                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+                    if ((all >> sp) & 1u) {
+                        if (sp == hs) {
+                            QO_TF_VALUE(val)
+                            if (hneg) { QO_PTS trkv = val[p] < trkv ? val[p] : trkv; }
+                            else { QO_PTS trkv = val[p] > trkv ? val[p] : trkv; }
+                        } else {
+                            QO_TF_SIGN(sg)
+                            QO_PTS acc[sp] |= sg[p];
+                        }
+                    }
+                }
+            } else {
                 /* the iteration straddles a band edge: per-point byte masks */
+                unsigned int mw[PTS];
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) {
                     const uint2 m = P.mb[j0 + 32 * qq];
                     mw[2 * qq] = m.x; mw[2 * qq + 1] = m.y;
                 }
-            }
 #pragma unroll
-            for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
-                if ((any >> sp) & 1u) {
-                    const bool on11 = S11 && P.s11[sp];
-                    if (sp == hs) {
-                        double val[PTS];
-                        if (on11) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; }
-                        else if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS val[p] = n2[p]; }
-                        else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS val[p] = n2[p] * rd[p]; }
-                        if (uniform) {
-                            if (hneg) { QO_PTS trkv = val[p] < trkv ? val[p] : trkv; }
-                            else { QO_PTS trkv = val[p] > trkv ? val[p] : trkv; }
-                        } else {
+                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+                    if ((any >> sp) & 1u) {
+                        if (sp == hs) {
+                            QO_TF_VALUE(val)
                             QO_PTS {
                                 const bool in = (mw[p] >> (8 * sp)) & 1u;
                                 if (hneg) { const double c = in ? val[p] : 1.7e308; trkv = c < trkv ? c : trkv; }
                                 else { const double c = in ? val[p] : -1.7e308; trkv = c > trkv ? c : trkv; }
                             }
+                        } else {
+                            QO_TF_SIGN(sg)
+                            QO_PTS acc[sp] |= sg[p] & __byte_perm(mw[p], 0, 0x1111 * sp);
                         }
-                    } else {
-                        const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];
-                        unsigned int sg[PTS];
-                        if (on11) { QO_PTS sg[p] = tf_hi(fma(t, n2[p], -m2[p])); }
-                        else if (P.neg[sp]) { QO_PTS sg[p] = tf_hi(fma(t, dd[p], n2[p])); }
-                        else { QO_PTS sg[p] = tf_hi(fma(t, dd[p], -n2[p])); }
-                        if (uniform) { QO_PTS acc[sp] |= sg[p]; }
-                        else { QO_PTS acc[sp] |= sg[p] & __byte_perm(mw[p], 0, 0x1111 * sp); }
                     }
                 }
             }
+#undef QO_TF_VALUE
+#undef QO_TF_SIGN
         }
 
         /* 4. per-sample verdict */

@@ -738,3 +738,52 @@ def test_tf_kernel_values_within_1e_9(Q, W, ctx, monkeypatch):
         moved = int(np.abs(tf["hist"].astype(np.int64) - ch["hist"].astype(np.int64)).sum()) // 2
         assert moved <= max(2, inside // 50), (moved, inside)
         assert tf["n_pass"] == ch["n_pass"] and np.array_equal(tf["fail_per_spec"], ch["fail_per_spec"])
+
+
+def test_tf_kernel_size_limits_and_degenerate_degrees(Q, R, W, ctx, monkeypatch):
+    """Edges of the transfer-function kernel's coverage: a resistive pad (degree 0: one coefficient pair), a single
+    reactive branch, a 24-branch ideal ladder (degree 24, the element limit), four specs at once; one branch more, or a
+    total degree above 29, hands the job to the interpreter -- every case equal to the oracle's counters."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    fc = 20e6
+    wc = 2 * np.pi * fc
+    f = Q.grid_log(fc / 2.5, fc * 2.5, 300)
+
+    def run(net, specs, tols, expect, f=f, **hist):
+        plan = Q.Plan(ctx, net, f, specs, seed=31, tols=tols, **hist)
+        assert plan.kernel_name == expect, (plan.kernel_name, plan.tf_info)
+        info = plan.tf_info
+        plan.launch(11, 400)
+        got = plan.read()
+        plan.close()
+        rs, rl = net.terminations
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(31, 400, tols, sample_offset=11, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)
+        return got, info
+
+    pad = Q.Net.from_elements([(Q.SHUNT_R, [292.4]), (Q.SER_R, [17.6]), (Q.SHUNT_R, [292.4])], 50.0, 50.0)      # 3 dB pi pad
+    tol_r = [(0, 0, 0, Q.TOL_REL, 0.05), (1, 0, 1, Q.TOL_REL, 0.05), (2, 0, 2, Q.TOL_REL, 0.05)]
+    got, info = run(pad, [(Q.SPEC_S21_MIN_DB, 0.0, 1e99, -3.05), (Q.SPEC_S21_MAX_DB, 0.0, 1e99, -2.95)], tol_r, "qo_mc_tf_kernel",
+                    hist_bins=20, hist_spec=0, hist_lo=-3.3, hist_hi=-2.7)
+    assert info["degree"] == 0 and info["kn"] == 1 and 0 < got["n_pass"] < 400
+    one = Q.Net.from_elements([(Q.SER_L, [50.0 / wc])], 50.0, 50.0)
+    got, info = run(one, [(Q.SPEC_S21_MIN_DB, 0.0, fc, -1.0)], [(0, 0, 0, Q.TOL_REL, 0.1)], "qo_mc_tf_kernel")
+    assert info["degree"] == 1 and 0 < got["n_pass"] < 400
+    g = [1.0 + 0.6 * np.sin(0.7 * k) for k in range(26)]
+    long_el = [((Q.SER_L, [50.0 * g[k] / wc]) if k % 2 == 0 else (Q.SHUNT_C, [g[k] / (50.0 * wc)])) for k in range(26)]
+    net24 = Q.Net.from_elements(long_el[:24], 50.0, 50.0)
+    db = 20 * np.log10(np.abs(ctx.sweep(net24, f)[1]))
+    pb, sb = f <= 0.5 * fc, f >= 2.0 * fc
+    specs4 = [(Q.SPEC_S21_MIN_DB, 0.0, 0.5 * fc, float(db[pb].min()) - 0.05), (Q.SPEC_S21_MAX_DB, 2.0 * fc, 1e99, float(db[sb].max()) + 2.0),
+              (Q.SPEC_S21_MIN_DB, 0.0, 0.45 * fc, float(db[f <= 0.45 * fc].min()) - 0.05), (Q.SPEC_S21_MAX_DB, 2.2 * fc, 1e99, float(db[f >= 2.2 * fc].max()) + 1.0)]
+    got, info = run(net24, specs4, Q.lc_tolerances(net24, 0.03, 0.03), "qo_mc_tf_kernel", hist_bins=32, hist_spec=3,
+                    hist_lo=float(db[f >= 2.2 * fc].max()) - 5.0, hist_hi=float(db[f >= 2.2 * fc].max()) + 5.0)
+    assert info["degree"] == 24 and info["den_form"] == "none" and int(got["fail_per_spec"].sum()) > 0
+    # the same network on a grid 16:1 wide: the plan's self-check rejects the 24th-degree expansion, the interpreter takes the job
+    fw = Q.grid_log(fc / 4, fc * 4, 300)
+    _, info = run(net24, specs4[:2], Q.lc_tolerances(net24, 0.03, 0.03), "qo_mc_lumped_kernel", f=fw)
+    assert info["reason"] == "polynomial expansion is too ill-conditioned on this grid" and info["self_check_err"] > 1e-10
+    net25 = Q.Net.from_elements(long_el[:25], 50.0, 50.0)
+    run(net25, specs4[:2], Q.lc_tolerances(net25, 0.03, 0.03), "qo_mc_lumped_kernel")                      # one branch too many
+    lossy15 = Q.Net.from_elements(long_el[:15], 50.0, 50.0).add_parasitics(fc, 60.0, 30.0, 0.1, 50.0)   # 15 lossy branches: degree 30
+    run(lossy15, specs4[:2], Q.lc_tolerances(lossy15, 0.03, 0.03), "qo_mc_lumped_kernel")

@@ -33,6 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
 sys.path.insert(0, ROOT)
 
+REAL_STDOUT = sys.stdout
 METRIC = "Monte Carlo network evals/s (samples x freq pts)"
 UNIT = "evals/s"
 SAMPLES_PER_GPU = 1000000
@@ -152,10 +153,22 @@ def run_reference(args, rank, world):
                              "sample": "%d samples x %d freq per step, %d steps" % (n, NF, args.steps)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """the ONE JSON line, on the process's real stdout"""
+    REAL_STDOUT.write(json.dumps(line) + "\n")
+    REAL_STDOUT.flush()
 
 
 def main():
+    # native libraries write banners to fd 1 (NCCL: "NCCL version ..."): keep the real stdout for the JSON line only and
+    # send everything else to stderr
+    global REAL_STDOUT
+    sys.stdout.flush()
+    REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -172,8 +185,6 @@ def main():
         run_reference(args, rank, world)
         return
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"            # NCCL's version banner goes to stdout; this script prints ONE JSON line there
     import torch
     import qo100net as Q
     from qo100net import dist as qd
@@ -232,8 +243,6 @@ def main():
         kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
         launches = plan.launches - launches0
         last = qd.split_counters(counters.cpu(), len(wl.specs), wl.hist["hist_bins"])
-        clocks = sampler.stop() if sampler else None
-
         # end to end through the host-buffer C-ABI call (qo_mc_run): per step H2D of the grid, specs and
         # tolerance table, kernel, D2H of the counters; N > 1 adds the all-reduce of the host result
         h2d = plan.h2d_bytes                     # what qo_plan_create copies: frequency tables, spec masks, device program
@@ -250,6 +259,7 @@ def main():
                 hc.cpu()
         barrier()
         e2e_s = time.perf_counter() - t0
+        clocks = sampler.stop() if sampler else None       # sampled over both timed regions (resident steps and end-to-end steps)
 
     tm = torch.tensor([ms_total, e2e_s * 1e3, kernel_ms], dtype=torch.float64, device="cuda")
     if dist is not None:
@@ -367,7 +377,7 @@ def main():
             del buf
         except Exception as ex:          # the secondary leg must never take the headline line down
             line["roofline_hbm"] = {"error": str(ex)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

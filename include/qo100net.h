@@ -271,7 +271,7 @@ int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far
  * (microstrip).  QO100NET_KERNEL=ladder keeps jobs off the transfer-function kernel, =interp forces the interpreter. */
 const char *qo_plan_kernel_name(const qo_plan *plan);
 /* what the plan decided about the transfer-function kernel.  info[0] = selected (0/1), [1] = numerator chains (2 | 4),
- * [2] = denominator form (0 none, 1 truncated |D|^2 polynomial, 2 complex D), [3] = coefficient pairs kept per numerator
+ * [2] = denominator form (0 none, 1 truncated |D|^2 polynomial, 2 complex D, 3 D and dD/ds for group-delay jobs), [3] = coefficient pairs kept per numerator
  * polynomial, [4] = denominator coefficients (form 1) / pairs (form 2) kept, [5] = structural degree;
  * *self_check_err = worst relative disagreement on |den|^2 between the expansion and the per-element evaluation
  * (nominal network + both ends of the tolerance box, every in-band grid point).  Returns the reason string

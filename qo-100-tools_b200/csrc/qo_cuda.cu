@@ -791,7 +791,8 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     for (int s = 0; s < QO_LAD_NSPEC; s++) {
         P.neg[s] = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
         P.s11[s] = s < hp->nspec && hp->spec_kind[s] == SK_S11_MAX;
-        P.thr[s] = s < hp->nspec ? hp->spec_thr[s] : 0.0;
+        P.gd[s] = s < hp->nspec && hp->spec_kind[s] == SK_GD_MAX;
+        P.thr[s] = s < hp->nspec ? (P.gd[s] ? hp->spec_thr[s] * p->tfp.wref : hp->spec_thr[s]) : 0.0;
     }
     P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tfp.n_el; P.el0 = p->tfp.el0; P.kn = p->tfp.kn; P.kd = p->tfp.kd; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;

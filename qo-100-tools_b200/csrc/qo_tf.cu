@@ -28,9 +28,17 @@ extern "C" int qo_tf_default_pp(const TfPlan *tp) { return tp->nn == 4 ? QO_TF_C
 template <int NN, bool CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den)
 {
     switch (den) {
-    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, PP, TPB, MINB>;
-    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, CPL, S11, PP, TPB, MINB>;
-    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, CPL, S11, PP, TPB, MINB>;
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, false, PP, TPB, MINB>;
+    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, CPL, S11, false, PP, TPB, MINB>;
+    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, CPL, S11, false, PP, TPB, MINB>;
+    default: return nullptr;
+    }
+}
+template <int PP, int TPB, int MINB> static tf_fn tf_pick_gd(int den)
+{
+    switch (den) {
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<4, QO_TF_DEN_NONE, false, false, true, PP, TPB, MINB>;
+    case QO_TF_DEN_DD: return qo_mc_tf_kernel<4, QO_TF_DEN_DD, false, false, true, PP, TPB, MINB>;
     default: return nullptr;
     }
 }
@@ -57,6 +65,7 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
 #endif
     {
         if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den);
+        else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
         else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
         else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
     }
@@ -177,12 +186,13 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
 #define QO_TF_NO(msg) do { out->reason = msg; return 0; } while (0)
     const char *force = getenv("QO100NET_KERNEL");
     if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
-    if (generic || !mode_reduce_only || precision != 64 || hp->need_gd) QO_TF_NO("not a reduce-only FP64 |S21| / |S11| job");
+    if (generic || !mode_reduce_only || precision != 64) QO_TF_NO("not a reduce-only FP64 job on a lumped cascade");
     if (hp->nspec < 1 || hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) QO_TF_NO("spec / variable count");
     for (int s = 0; s < hp->nspec; s++)
-        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) QO_TF_NO("spec kind");
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX && hp->spec_kind[s] != SK_GD_MAX) QO_TF_NO("spec kind");
     int need_s21 = 0;
-    for (int s = 0; s < hp->nspec; s++) if (hp->spec_kind[s] != SK_S11_MAX) need_s21 = 1;
+    for (int s = 0; s < hp->nspec; s++) if (hp->spec_kind[s] != SK_S11_MAX) need_s21 = 1;      /* group delay needs D too */
+    const bool gd = hp->need_gd != 0;
     int e0 = hp->op0;
     if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { out->cpl_op = e0; e0++; }
     const int nl = hp->n_ops - e0;
@@ -198,9 +208,10 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     const int Kfull = deg / 2 + 1;
     const bool cpl = out->cpl_op >= 0, s11 = hp->need_s11 != 0;
     if (cpl && s11) QO_TF_NO("|S11| specs behind a coupled-line block");
+    if (gd && (cpl || s11)) QO_TF_NO("group-delay specs mixed with a coupled-line block or |S11| specs");
     if (!need_s21) has_d = 0;                                 /* S11 = (P - Rs Q) / (P + Rs Q): the branch denominators cancel */
     const bool apart = cpl || s11;                            /* P and Q kept apart */
-    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = apart ? 4 : 2; out->s11 = s11;
+    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = (apart || gd) ? 4 : 2; out->s11 = s11; out->gd = gd;
 
     const double two_pi = 6.283185307179586476925286766559;
     double fmin = f[0], fmax = f[0];
@@ -239,6 +250,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
      * Per point the scan runs from the top coefficient down and stops at the first term that may not be dropped. */
     double trunc = 5e-13;
     if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
+    if (gd) trunc = 0.0;                                      /* the derivative polynomials weigh the top coefficients by their index: keep all */
     const int NE = 2 * nl + 1, NC = 2 * Kfull;
     int kn = 1, kdd = 1, ke = 1;
     std::vector<double> xg((size_t)nf), xpw((size_t)NC + 1), zpw((size_t)NE + 1);
@@ -287,6 +299,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
      * self-check fails (E loses digits next to a trap's notch, where |D| -> 0) hands over to the next one */
     int forms[2], nforms = 0;
     if (!has_d) forms[nforms++] = QO_TF_DEN_NONE;
+    else if (gd) forms[nforms++] = QO_TF_DEN_DD;
     else {
         if (ke <= QO_TF_MAXKE && ke <= 2 * kdd + 3 && !getenv("QO100NET_TF_NO_E")) forms[nforms++] = QO_TF_DEN_E;
         forms[nforms++] = QO_TF_DEN_D;
@@ -297,7 +310,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     int accepted = 0;
     for (int fi = 0; fi < nforms && !accepted; fi++) {
         out->den = forms[fi];
-        out->kd = forms[fi] == QO_TF_DEN_E ? ke : forms[fi] == QO_TF_DEN_D ? kdd : 0;
+        out->kd = forms[fi] == QO_TF_DEN_E ? ke : (forms[fi] == QO_TF_DEN_D || forms[fi] == QO_TF_DEN_DD) ? kdd : 0;
         /* self-check: exactly what the device evaluates (kept lengths, this denominator form) against the per-element evaluation */
         worst = 0.0;
         int range_ok = 1;
@@ -307,7 +320,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
                 const double x = xg[k], y = -x * x;
                 double d2 = 1.0;
                 if (out->den == QO_TF_DEN_E) { d2 = c.ee[out->kd - 1]; for (int m = out->kd - 2; m >= 0; m--) d2 = d2 * y + c.ee[m]; }
-                else if (out->den == QO_TF_DEN_D) d2 = std::norm(tf_horner_host(c.dd, out->kd, x));
+                else if (out->den == QO_TF_DEN_D || out->den == QO_TF_DEN_DD) d2 = std::norm(tf_horner_host(c.dd, out->kd, x));
                 if (!(d2 > 1e-70 && d2 < 1e70)) { range_ok = 0; break; }      /* the batched reciprocal multiplies four of them */
                 /* value check: every in-band point of the nominal network; the two corners on every 4th point and
                  * around the band edges (their job is to catch a tolerance-driven loss of conditioning, which is smooth in x) */
@@ -334,6 +347,38 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
                 } else {
                     const double got = std::norm(P_ + hp->rs * Q_) / d2, ref = std::norm(a + hp->rs * b);
                     rel = need_s21 ? fabs(got - ref) / ref : 0.0;
+                    if (gd) {
+                        /* group delay: the derivative polynomials against the central difference of the per-element chain's phase
+                         * over x (1 +- 1e-6) -- the definition the sweep API and the oracle use */
+                        cplx Np(0, 0), Dp(0, 0);
+                        const cplx sj1(0.0, x);
+                        cplx pw(1.0, 0.0);
+                        for (int i = 1; i < 2 * kn; i++) { Np += (double)i * (c.pp[i] + hp->rs * zni * c.qq[i]) * pw; pw *= sj1; }
+                        pw = cplx(1.0, 0.0);
+                        for (int i = 1; i < 2 * out->kd && out->den == QO_TF_DEN_DD; i++) { Dp += (double)i * c.dd[i] * pw; pw *= sj1; }
+                        const cplx Nn = P_ + hp->rs * Q_;
+                        double tau = (Np / Nn).real();
+                        if (out->den == QO_TF_DEN_DD) tau -= (Dp / tf_horner_host(c.dd, out->kd, x)).real();
+                        cplx dv[2];
+                        for (int sgn = 0; sgn < 2; sgn++) {
+                            const double xq = x * (sgn ? 1.0 - 1e-6 : 1.0 + 1e-6), yq = -xq * xq;
+                            double ar2 = hp->rl, ai2 = 0.0, br2 = 1.0, bi2 = 0.0;
+                            for (int e = nl - 1; e >= 0; e--) {
+                                const double *nd = c.nd[e];
+                                const double nr = nd[2] * yq + nd[0], ni = nd[1] * xq, dr = nd[5] * yq + nd[3], di = nd[4] * xq;
+                                const double inv = 1.0 / (dr * dr + di * di);
+                                const double ir = (nr * dr + ni * di) * inv, ii = (ni * dr - nr * di) * inv;
+                                if (c.ser[e]) { const double tr = ir * br2 - ii * bi2, ti = ir * bi2 + ii * br2; ar2 += tr; ai2 += ti; }
+                                else { const double tr = ir * ar2 - ii * ai2, ti = ir * ai2 + ii * ar2; br2 += tr; bi2 += ti; }
+                            }
+                            dv[sgn] = cplx(ar2 + hp->rs * br2, ai2 + hp->rs * bi2);
+                        }
+                        const cplx cr = dv[0] * std::conj(dv[1]);
+                        const double tau_fd = atan2(cr.imag(), cr.real()) / (2e-6 * x);
+                        /* the finite difference itself carries ~1e-10 of rounding noise relative to the largest delay; 1e-7 is far below any spec resolution */
+                        const double egd = 1e-3 * fabs(tau - tau_fd) / (fabs(tau_fd) > 1e-3 ? fabs(tau_fd) : 1e-3);
+                        if (egd > rel) rel = egd;
+                    }
                     if (s11) {
                         /* |S11|^2, relative with an absolute floor of -40 dB (return-loss nulls are not thresholds) */
                         const double g11 = std::norm(P_ - hp->rs * Q_) / std::norm(P_ + hp->rs * Q_), r11 = std::norm(a - hp->rs * b) / ref;

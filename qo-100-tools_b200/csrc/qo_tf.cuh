@@ -38,7 +38,7 @@
  *                   terms), so E's coefficients fall off like (w / w_SRF)^2m and the plan keeps only as many as the
  *                   grid needs (dropped tail below 5e-13 of E everywhere on the grid, qo_tf.cu)
  *   QO_TF_DEN_D     D(jx) itself, even and odd chain (networks with traps / tanks resonating inside the grid) */
-enum { QO_TF_DEN_NONE = 0, QO_TF_DEN_E = 1, QO_TF_DEN_D = 2 };
+enum { QO_TF_DEN_NONE = 0, QO_TF_DEN_E = 1, QO_TF_DEN_D = 2, QO_TF_DEN_DD = 3 /* D and dD/ds: group-delay jobs */ };
 
 struct TfParams {
     const DevProg *prog;
@@ -54,6 +54,7 @@ struct TfParams {
     double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
     int neg[QO_LAD_NSPEC];
     int s11[QO_LAD_NSPEC];                   /* the spec is on |S11|^2 = |P - Rs Q|^2 / |P + Rs Q|^2 (FAIL iff > thr) */
+    int gd[QO_LAD_NSPEC];                    /* the spec is on the group delay: thr = limit [s] * wref (FAIL iff tau * wref > thr) */
     int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
@@ -113,6 +114,8 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
  * CPL    coupled-line block in front (its row vector is contracted with [P; Q] per point)
  * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
+ * GD     the job has group-delay specs: tau = d arg(den)/dw = Re(Num'/Num - D'/D) / wref with the derivative polynomials
+ *        Num' = dNum/dsn, D' = dD/dsn evaluated by two more Horner chains each (no finite difference, no atan2)
  * DEN    QO_TF_DEN_*                  PP   frequency pairs per thread per iteration (PTS = 2*PP points)
  * One warp = one sample at a time (ticket hand-out as in qo_ladder.cuh); lane l owns pairs l, l+32, ... of each
  * iteration's PP*32 pairs.  The polynomial lengths (P.kn pairs, P.kd) are run-time: the plan keeps the terms the
@@ -128,7 +131,7 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
  * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
  */
-template <int NN, int DEN, bool CPL, bool S11, int PP, int TPB, int MINB>
+template <int NN, int DEN, bool CPL, bool S11, bool GD, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr int PTS = 2 * PP;
@@ -136,8 +139,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     static_assert(NN == 2 || NN == 4, "two or four numerator chains");
     static_assert(!(CPL || S11) || NN == 4, "P and Q stay separate behind a coupler block and for |S11|");
     static_assert(!(CPL && S11), "|S11| specs behind a coupler block run on the chain kernel");
+    static_assert(!GD || (NN == 4 && !CPL && !S11 && (DEN == QO_TF_DEN_NONE || DEN == QO_TF_DEN_DD)), "group delay: Num, Num' and D, D'");
+    static_assert(GD || DEN != QO_TF_DEN_DD, "D' is only evaluated for group-delay jobs");
     __shared__ __align__(16) double s_num[WARPS][(QO_TF_MAXK + 2) * NN];   /* two guard rows below row 0 (prefetch runs two steps ahead) */     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
-    __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : 2 * QO_TF_MAXK + 4];   /* + guard pairs */   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
+    __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : (DEN == QO_TF_DEN_DD ? 4 : 2) * QO_TF_MAXK + 4];   /* + guard */   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
     __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 2 : 2];
     __shared__ double s_x[WARPS][QO_MAX_VAR];
@@ -197,13 +202,31 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             }
         }
         /* Horner tables (kept coefficients only; E is padded to an even count with a zero) */
-        if (lane < 2 * kn) {
+        if (GD) {
+            /* rows (c_2k, c_2k+1, (2k+1) c_2k+1, (2k+2) c_2k+2): the polynomial and its derivative d/dsn, even / odd parts */
+            const double num = fma(rs * P.zni, q, p), fl = (double)lane;
             const int k = lane >> 1, par = lane & 1;
-            if (NN == 4) { numw[k * NN + par] = p; numw[k * NN + 2 + par] = q; }
-            else numw[k * NN + par] = fma(rs * P.zni, q, p);
+            if (lane < 2 * kn) {
+                numw[k * 4 + par] = num;
+                if (par) numw[k * 4 + 2] = fl * num; else if (k > 0) numw[(k - 1) * 4 + 3] = fl * num;
+                if (DEN == QO_TF_DEN_DD) {
+                    denw[k * 4 + par] = d;
+                    if (par) denw[k * 4 + 2] = fl * d; else if (k > 0) denw[(k - 1) * 4 + 3] = fl * d;
+                }
+            }
+            if (lane == 2 * kn) {        /* the top row's odd derivative entry: (2 kn) c_2kn, zero beyond the degree */
+                numw[(kn - 1) * 4 + 3] = fl * num;
+                if (DEN == QO_TF_DEN_DD) denw[(kn - 1) * 4 + 3] = fl * d;
+            }
+        } else {
+            if (lane < 2 * kn) {
+                const int k = lane >> 1, par = lane & 1;
+                if (NN == 4) { numw[k * NN + par] = p; numw[k * NN + 2 + par] = q; }
+                else numw[k * NN + par] = fma(rs * P.zni, q, p);
+            }
+            if (DEN == QO_TF_DEN_E) { if (lane < kd) denw[lane] = d; }
+            if (DEN == QO_TF_DEN_D) { if (lane < 2 * kd) denw[lane] = d; }
         }
-        if (DEN == QO_TF_DEN_E) { if (lane < kd) denw[lane] = d; }
-        if (DEN == QO_TF_DEN_D) { if (lane < 2 * kd) denw[lane] = d; }
         __syncwarp();
 
         /* 3. frequency loop */
@@ -248,7 +271,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
 #undef QO_TF_NUM_STEP
             }
             /* dd = |D(jx)|^2 */
-            double dd[PTS];
+            double dd[PTS], gA[PTS], gB[PTS];        /* gA = Re(Num' conj Num), gB = Re(D' conj D) (group-delay kernels) */
+            QO_PTS gB[p] = 0.0;
             if (DEN == QO_TF_DEN_E) {
                 unsigned int a = dens + (unsigned int)(kd - 2) * 8u;          /* kd is even: two coefficients per load */
                 LadV2<double> cur = lad_lds2(a, 0.0), nxt;
@@ -272,10 +296,32 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     QO_PTS { de[p] = fma(de[p], y[p], cc.x); dq[p] = fma(dq[p], y[p], cc.y); }
                 }
                 QO_PTS { const double t = dq[p] * dq[p]; dd[p] = fma(-y[p], t, de[p] * de[p]); }     /* |re + j x im|^2 = re^2 - y im^2 */
+            } else if (DEN == QO_TF_DEN_DD) {
+                /* D and D' (group delay): B = Re(D' conj D) = D'e De - y D'o Do */
+                double de[PTS], dq[PTS], dpe[PTS], dpo[PTS];
+                unsigned int a = dens + (unsigned int)(kd - 1) * 32u;
+                { const LadV2<double> c0 = lad_lds2(a, 0.0), c1 = lad_lds2(a + 16u, 0.0); QO_PTS { de[p] = c0.x; dq[p] = c0.y; dpe[p] = c1.x; dpo[p] = c1.y; } }
+#pragma unroll 2
+                for (int k = kd - 2; k >= 0; k--) {
+                    a -= 32u;
+                    const LadV2<double> c0 = lad_lds2(a, 0.0), c1 = lad_lds2(a + 16u, 0.0);
+                    QO_PTS { de[p] = fma(de[p], y[p], c0.x); dq[p] = fma(dq[p], y[p], c0.y); dpe[p] = fma(dpe[p], y[p], c1.x); dpo[p] = fma(dpo[p], y[p], c1.y); }
+                }
+                QO_PTS {
+                    const double t = dq[p] * dq[p];
+                    dd[p] = fma(-y[p], t, de[p] * de[p]);
+                    gB[p] = fma(-y[p], dpo[p] * dq[p], dpe[p] * de[p]);
+                }
             } else { QO_PTS dd[p] = 1.0; }
             /* n2 = |numerator|^2 (the coupler's row vector contracted with [P; Q]) */
             double n2[PTS], m2[PTS];                 /* m2 = |P - Rs Q|^2, the numerator of |S11|^2 (S11 kernels) */
-            if (S11) {
+            if (GD) {
+                QO_PTS {
+                    const double t = r[1][p] * r[1][p];
+                    n2[p] = fma(-y[p], t, r[0][p] * r[0][p]);
+                    gA[p] = fma(-y[p], r[3][p] * r[1][p], r[2][p] * r[0][p]);
+                }
+            } else if (S11) {
                 const double zq = P.rs * P.zni;
                 QO_PTS {
                     const double ar = fma(zq, r[2][p], r[0][p]), ai = fma(zq, r[3][p], r[1][p]);
@@ -326,14 +372,20 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             /* every spec tracks  numer / denom:  |den|^2 = n2 / dd  (|S21| specs),  |S11|^2 = m2 / n2 */
 #define QO_TF_VALUE(val)                                                                                          \
             double val[PTS];                                                                                      \
-            if (S11 && P.s11[sp]) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; }   \
+            if (GD && P.gd[sp]) {          /* tau wref = gA / n2 - gB / dd */                                     \
+                double pr[PTS], rd[PTS];                                                                          \
+                QO_PTS pr[p] = n2[p] * dd[p];                                                                     \
+                lad_rcp_batch<PTS>(pr, rd);                                                                       \
+                QO_PTS val[p] = fma(gA[p], dd[p], -gB[p] * n2[p]) * rd[p];                                         \
+            } else if (S11 && P.s11[sp]) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; } \
             else if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS val[p] = n2[p]; }                                     \
             else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS val[p] = n2[p] * rd[p]; }
 #define QO_TF_SIGN(sg)                                                                                            \
             unsigned int sg[PTS];                                                                                 \
             {                                                                                                     \
                 const double t = P.neg[sp] ? -P.thr[sp] : P.thr[sp];                                              \
-                if (S11 && P.s11[sp]) { QO_PTS sg[p] = tf_hi(fma(t, n2[p], -m2[p])); }                             \
+                if (GD && P.gd[sp]) { QO_PTS sg[p] = tf_hi(fma(t, n2[p] * dd[p], fma(gB[p], n2[p], -gA[p] * dd[p]))); } \
+                else if (S11 && P.s11[sp]) { QO_PTS sg[p] = tf_hi(fma(t, n2[p], -m2[p])); }                        \
                 else if (P.neg[sp]) { QO_PTS sg[p] = tf_hi(fma(t, dd[p], n2[p])); }                                \
                 else { QO_PTS sg[p] = tf_hi(fma(t, dd[p], -n2[p])); }                                              \
             }
@@ -409,7 +461,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             if (hs >= 0) {
                 const double k21 = P.k21;
                 const double lin = (S11 && P.s11[hs & (QO_LAD_NSPEC - 1)]) ? trkv : hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
-                const double v = 10.0 * log10(lin);
+                const double v = (GD && P.gd[hs & (QO_LAD_NSPEC - 1)]) ? trkv / P.wref : 10.0 * log10(lin);      /* seconds, or dB */
                 const double xb = (v - P.hist_lo) / (P.hist_hi - P.hist_lo) * (double)P.hist_bins;
                 long long b = (long long)floor(xb);
                 if (!(xb >= 0.0)) b = 0;

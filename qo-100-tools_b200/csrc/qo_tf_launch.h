@@ -7,6 +7,7 @@ struct DevProg;
 struct TfPlan {
     int nn;              /* numerator chains: 2 (Num = P + Rs Q) or 4 (P and Q apart: behind a coupled-line block, or with |S11| specs) */
     int s11;             /* the job has |S11| specs */
+    int gd;              /* the job has group-delay specs (derivative polynomials ride along) */
     int den;             /* QO_TF_DEN_* */
     int kn, kd;          /* coefficient pairs kept per numerator polynomial; E coefficients (even count) or D pairs kept */
     int deg;             /* structural degree of the numerator polynomials */

@@ -418,7 +418,8 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     monkeypatch.delenv("QO100NET_KERNEL", raising=False)
     p = Q.Plan(ctx, W.cfg5().net, W.cfg5().f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], seed=1, tols=W.cfg5().tols)
     assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                                                      # |S11| behind the coupler block
-    p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()         # group delay: interpreter
+    p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()             # group delay: derivative polynomials
+    p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()   # GD + |S11|: interpreter
     p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
     p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode
     p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                       # optional FP32 mode
@@ -566,27 +567,45 @@ def test_touchstone_blocks_in_cascade(Q, R, W, ctx, golden_s2p):
     R.sblock_clear()
 
 
-def test_group_delay_spec_in_kernel(Q, R, W, ctx):
+def test_group_delay_spec_in_kernel(Q, R, W, ctx, monkeypatch):
     """north_star (c): group-delay reduction in-kernel.  QO_SPEC_GD_MAX on the Monte-Carlo path: counters and the
-    histogram of the worst pass-band group delay equal the oracle's (same central-difference definition as
-    qo_sweep's gd output), alone and mixed with |S21| / |S11| specs."""
+    histogram of the worst pass-band group delay equal the oracle's (central difference of arg S21 over f (1 +- 1e-6),
+    the definition of qo_sweep's gd output) -- on the transfer-function kernel, which evaluates tau analytically from the
+    derivative polynomials (GD alone, GD + |S21|), and on the interpreter, which re-runs the chain at f (1 +- 1e-6)
+    (forced, and the default when |S11| specs are mixed in)."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
     w = W.cfg2()
     fc = 10e6
     f = w.f[::4]
     gd = ctx.sweep(w.net, f, gd=True)[4]
     band = (f >= 0.3 * fc) & (f <= 0.9 * fc)
     lim = float(gd[band].max()) * 1.01
-    for specs, hs in (([(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 0),
-                      ([(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -2.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim),
-                        (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, -9.0)], 1)):
-        hist = dict(hist_bins=40, hist_spec=hs, hist_lo=0.8 * lim, hist_hi=1.3 * lim)
-        plan = Q.Plan(ctx, w.net, f, specs, seed=3, tols=w.tols, **hist)
-        assert plan.kernel_name == "qo_mc_lumped_kernel"
+    ideal = Q.Net.cheby_lpf(7, 0.1, fc, 50.0, True)
+    gdi = ctx.sweep(ideal, f, gd=True)[4]
+    limi = float(gdi[band].max()) * 1.01
+    cases = [(w.net, w.tols, [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 0, lim, "qo_mc_tf_kernel"),
+             (w.net, w.tols, [(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -2.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 1, lim, "qo_mc_tf_kernel"),
+             (w.net, w.tols, [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim), (Q.SPEC_S21_MAX_DB, 1.3 * fc, 1e99, -49.0)], 1, None, "qo_mc_tf_kernel"),
+             (ideal, Q.lc_tolerances(ideal, 0.05, 0.05), [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, limi)], 0, limi, "qo_mc_tf_kernel"),
+             (w.net, w.tols, [(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -2.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim),
+                              (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, -9.0)], 1, lim, "qo_mc_lumped_kernel")]
+    for net, tols, specs, hs, hl, kernel in cases:
+        hist = dict(hist_bins=40, hist_spec=hs, hist_lo=0.8 * hl, hist_hi=1.3 * hl) if hl else dict(hist_bins=40, hist_spec=hs, hist_lo=-60.0, hist_hi=-40.0)
+        plan = Q.Plan(ctx, net, f, specs, seed=3, tols=tols, **hist)
+        assert plan.kernel_name == kernel, plan.tf_info
+        if kernel == "qo_mc_tf_kernel":
+            assert plan.tf_info["self_check_err"] < 1e-10
         plan.close()
-        got = ctx.mc_run(w.net, f, specs, 3, 500, w.tols, **hist)
-        ref = R.mc_run(to_ref(R, w.net), 50, 50, f, specs, R.mc_cfg(3, 500, w.tols, **hist), nthreads=8)
+        got = ctx.mc_run(net, f, specs, 3, 500, tols, **hist)
+        rs, rl = net.terminations
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(3, 500, tols, **hist), nthreads=8)
         _assert_counts_equal(ref, got)
-        assert 0 < got["fail_per_spec"][hs] < 500 and int(got["hist"].sum()) == 500 and np.count_nonzero(got["hist"]) > 3
+        gi = [i for i, s in enumerate(specs) if s[0] == Q.SPEC_GD_MAX][0]
+        assert 0 < got["fail_per_spec"][gi] < 500 and int(got["hist"].sum()) == 500 and np.count_nonzero(got["hist"]) > 3
+        monkeypatch.setenv("QO100NET_KERNEL", "interp")
+        itp = ctx.mc_run(net, f, specs, 3, 500, tols, **hist)
+        monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        _assert_counts_equal(itp, got)
     with pytest.raises(Q.QoError):
         ctx.mc_run(w.net, f, [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim)], 3, 10, w.tols, precision=32)
 

@@ -415,7 +415,11 @@ def test_transfer_function_plan_analysis(Q, W, monkeypatch):
     a11 = Q.plan_analyze(w.net, w.f, [(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], w.tols)
     assert a11["selected"] and a11["numerator_chains"] == 4 and a11["den_form"] == "none"      # S11 = (P - Rs Q)/(P + Rs Q): denominators cancel
     assert Q.plan_analyze(w5.net, w5.f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], w5.tols)["reason"] == "|S11| specs behind a coupled-line block"
-    assert Q.plan_analyze(w.net, w.f, [(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)], w.tols)["reason"] == "not a reduce-only FP64 |S21| / |S11| job"
+    agd = Q.plan_analyze(w.net, w.f, [(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S21_MIN_DB, 0.0, 9.5e6, -2.0)], w.tols)
+    assert agd["selected"] and agd["den_form"] == "DD" and agd["kn"] == 12 and agd["self_check_err"] < 1e-10   # derivative polynomials: nothing dropped
+    assert Q.plan_analyze(w.net, w.f, [(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], w.tols)["reason"] == \
+        "group-delay specs mixed with a coupled-line block or |S11| specs"
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=32)["reason"] == "not a reduce-only FP64 job on a lumped cascade"
     assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=32)["selected"] is False
     assert Q.plan_analyze(w.net, w.f, [], w.tols, mode=Q.MODE_FULL_S)["selected"] is False
     tl = Q.Net.from_elements([(Q.TLINE, [50.0, 90.0, 1e9])] + w.net.elements, 50.0, 50.0)

@@ -35,6 +35,16 @@ def main():
     def workload(name):
         if name in ("cfg2", "cfg5", "cfg5p"):
             return getattr(W, name)(n, 4096)
+        if name in ("cfg2gd", "cfg2s11"):
+            w = W.cfg2(n, 4096)
+            fc = 10e6
+            if name == "cfg2gd":
+                gd = ctx.sweep(w.net, w.f, gd=True)[4]
+                band = (w.f >= 0.3 * fc) & (w.f <= 0.9 * fc)
+                w.specs = list(w.specs) + [(Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, float(gd[band].max()) * 1.01)]
+            else:
+                w.specs = list(w.specs) + [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0)]
+            return w
         if name == "ifbpf":
             net = W.if_bpf_net()
             f = Q.grid_log(300e6 / 3.5, 500e6 * 3.5, 4096)

@@ -166,10 +166,12 @@ __device__ __forceinline__ M2 ms_mcorn(double W, const MsSub &s, double f)
 }
 
 /* MOPEN(W): Kirschning open-end extension, dispersion taken at Weff; returns B of Y = jB */
-__device__ __forceinline__ double ms_mopen(double W, const MsSub &s, double f)
+__device__ __forceinline__ double ms_mopen(MsCache &c, double W, const MsSub &s, double f)
 {
-    double Z, E, Weff, Zf, Ef;
-    ms_quasi(W, s, Z, E, Weff);
+    /* the quasi-static analysis of this width is (almost always) already in the line cache: the stub line in front of the open end */
+    const MsLine &l = ms_line(c, W, s, f);
+    const double Z = l.Z, E = l.E, Weff = l.Weff;
+    double Zf, Ef;
     ms_disp(Weff, s, Z, E, f, Zf, Ef);
     const double w = W / s.h, er = s.er;
     const double Q6 = pow(Ef, 0.81), Q7 = pow(w, 0.8544);
@@ -245,6 +247,10 @@ __device__ __noinline__ void qo_generic_abcd(const DevProg *__restrict__ prog, c
     cache.n = 0; cache.next = 3;
     MsTee tee = { 0, 0, 0, 1, 1, 0 };
     double teeWa = 0.0, teeWb = 0.0;
+    /* the reference network repeats its discontinuities (12 identical corners, 2 identical tees and open ends): keep the last
+     * one of each kind and reuse it while the widths (and the substrate) stay the same -- identical values, 25 fewer pow/exp per eval */
+    double cornW = -1.0, openW = -1.0, openB = 0.0, teeK[3] = { -1.0, -1.0, -1.0 };
+    M2 cornM = m2_ident();
     const int n_ops = prog->n_ops;
     for (int e = 0; e < n_ops; e++) {
         double p[6];
@@ -283,17 +289,25 @@ __device__ __noinline__ void qo_generic_abcd(const DevProg *__restrict__ prog, c
         case 13:
             sub.er = p[0]; sub.h = p[1]; sub.t = p[2]; sub.tand = p[3]; sub.rho = p[4]; sub.D = p[5];
             cache.n = 0;
+            cornW = openW = teeK[0] = -1.0;
             break;
         case 14: M = m2_mul(M, ms_mlin(cache, p[0], p[1], sub, f)); break;
-        case 15: M = m2_mul(M, ms_mcorn(p[0], sub, f)); break;
+        case 15:
+            if (p[0] != cornW) { cornM = ms_mcorn(p[0], sub, f); cornW = p[0]; }
+            M = m2_mul(M, cornM);
+            break;
         case 16:
-            ms_mtee(cache, p[0], p[1], p[2], sub, f, tee);
+            if (p[0] != teeK[0] || p[1] != teeK[1] || p[2] != teeK[2]) {
+                ms_mtee(cache, p[0], p[1], p[2], sub, f, tee);
+                teeK[0] = p[0]; teeK[1] = p[1]; teeK[2] = p[2];
+            }
             teeWa = p[0]; teeWb = p[1];
             Mmain = M;
             M = ms_mlin(cache, p[2], tee.L2, sub, f);     /* arm 2, junction outward */
             break;
         case 17: {
-            const cd yo = cmk(0.0, ms_mopen(p[0], sub, f));
+            if (p[0] != openW) { openB = ms_mopen(cache, p[0], sub, f); openW = p[0]; }
+            const cd yo = cmk(0.0, openB);
             const cd yin = cdiv(cadd(M.c, cmul(M.d, yo)), cadd(M.a, cmul(M.b, yo)));
             const double sa = sqrt(tee.Ta2), sb = sqrt(tee.Tb2);
             M = m2_mul(Mmain, ms_mlin(cache, teeWa, tee.La, sub, f));

@@ -153,7 +153,14 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
                                 const unsigned char *mask, TfPlan *out)
 {
     unsigned long long key = 1469598103934665603ull;
-    key = tf_fnv(key, hp, sizeof *hp);
+    {
+        /* what the analysis does not read must not split the cache: seed, distribution, histogram set-up, thresholds */
+        DevProg *k = new DevProg(*hp);
+        k->seed = 0; k->dist = 0; k->hist_spec = k->hist_bins = 0; k->hist_lo = k->hist_hi = 0.0;
+        for (int s = 0; s < QO_NSPEC_MAX; s++) { k->spec_thr[s] = 0.0; k->spec_limit[s] = 0.0; }
+        key = tf_fnv(key, k, sizeof *k);
+        delete k;
+    }
     key = tf_fnv(key, f, (size_t)nf * sizeof(double));
     key = tf_fnv(key, mask, (size_t)nf);
     const int scal[4] = { mode_reduce_only, precision, generic, nf };

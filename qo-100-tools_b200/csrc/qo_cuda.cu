@@ -47,7 +47,7 @@ struct DevPlan {
     /* transfer-function kernel: one blob, tables padded to whole iterations of tf_pp*32 pairs */
     void *tf_blob;
     double2 *tf_yt, *tf_xt, *tf_wt, *tf_ctab[4];
-    uint2 *tf_mb;
+    uint4 *tf_mb;
     uchar2 *tf_itm;
     double2 *sblk, *sdet;      /* OP_SBLOCK: ABCD per (block, grid point); product of block determinants per point */
     void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
@@ -568,20 +568,23 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 p->tf_niter = (np + ppi - 1) / ppi;
                 const size_t npad = (size_t)p->tf_niter * ppi, npt = 2 * npad;
                 const int ntab = 3 + (p->cpl_fast ? 4 : 0);
-                const size_t bytes = (size_t)ntab * npt * sizeof(double) + npt * sizeof(unsigned int) + (size_t)p->tf_niter * sizeof(uchar2);
+                const size_t bytes = (size_t)ntab * npt * sizeof(double) + 2 * npt * sizeof(unsigned int) + (size_t)p->tf_niter * sizeof(uchar2);
                 std::vector<unsigned char> blob(bytes);
                 double *tab = (double *)blob.data();
                 unsigned int *mb = (unsigned int *)(tab + (size_t)ntab * npt);
-                uchar2 *itm = (uchar2 *)(mb + npt);
+                uchar2 *itm = (uchar2 *)(mb + 2 * npt);
                 for (size_t k = 0; k < npt; k++) {
                     const size_t kc = k < (size_t)nf ? k : (size_t)nf - 1;
                     const double x = w[kc] / p->tfp.wref;
                     tab[k] = -(x * x); tab[npt + k] = x; tab[2 * npt + k] = w[kc];
                     if (p->cpl_fast) for (int t = 0; t < 4; t++) tab[(3 + t) * npt + k] = ctab[t][kc];
-                    unsigned int word = 0;
+                    unsigned int lo = 0, hi = 0;
                     const unsigned char mk = k < (size_t)nf ? p->maskv[k] : 0;
-                    for (int sp = 0; sp < 4; sp++) if ((mk >> sp) & 1u) word |= 0xFFu << (8 * sp);
-                    mb[k] = word;
+                    for (int sp = 0; sp < 4; sp++) {
+                        if ((mk >> sp) & 1u) lo |= 0xFFu << (8 * sp);
+                        if ((mk >> (sp + 4)) & 1u) hi |= 0xFFu << (8 * sp);
+                    }
+                    mb[2 * k] = lo; mb[2 * k + 1] = hi;
                 }
                 for (int it = 0; it < p->tf_niter; it++) {
                     unsigned char any = 0, all = 0xFF;
@@ -597,8 +600,8 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 double *dt = (double *)d->tf_blob;
                 d->tf_yt = (double2 *)dt; d->tf_xt = (double2 *)(dt + npt); d->tf_wt = (double2 *)(dt + 2 * npt);
                 for (int t = 0; t < 4; t++) d->tf_ctab[t] = p->cpl_fast ? (double2 *)(dt + (3 + t) * npt) : NULL;
-                d->tf_mb = (uint2 *)(dt + (size_t)ntab * npt);
-                d->tf_itm = (uchar2 *)((unsigned int *)d->tf_mb + npt);
+                d->tf_mb = (uint4 *)(dt + (size_t)ntab * npt);
+                d->tf_itm = (uchar2 *)((unsigned int *)d->tf_mb + 2 * npt);
             }
             if (p->ladder || p->tf) {
                 CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
@@ -788,7 +791,7 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
     P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
     P.wref = p->tfp.wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
-    for (int s = 0; s < QO_LAD_NSPEC; s++) {
+    for (int s = 0; s < QO_TF_NSPEC; s++) {
         P.neg[s] = s < hp->nspec && hp->spec_kind[s] == SK_DEN2_MIN;
         P.s11[s] = s < hp->nspec && hp->spec_kind[s] == SK_S11_MAX;
         P.gd[s] = s < hp->nspec && hp->spec_kind[s] == SK_GD_MAX;

@@ -25,22 +25,30 @@ typedef void (*tf_fn)(const TfParams);
 
 extern "C" int qo_tf_default_pp(const TfPlan *tp) { return tp->nn == 4 ? QO_TF_CPL_PP : QO_TF_PP; }
 
-template <int NN, bool CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den)
+template <int NN, bool CPL, bool S11, int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_ns(int den)
 {
     switch (den) {
-    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, false, PP, TPB, MINB>;
-    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, CPL, S11, false, PP, TPB, MINB>;
-    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, CPL, S11, false, PP, TPB, MINB>;
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, false, NS, PP, TPB, MINB>;
+    case QO_TF_DEN_E: return qo_mc_tf_kernel<NN, QO_TF_DEN_E, CPL, S11, false, NS, PP, TPB, MINB>;
+    case QO_TF_DEN_D: return qo_mc_tf_kernel<NN, QO_TF_DEN_D, CPL, S11, false, NS, PP, TPB, MINB>;
     default: return nullptr;
     }
 }
-template <int PP, int TPB, int MINB> static tf_fn tf_pick_gd(int den)
+template <int NN, bool CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den, int nspec = 4)
+{
+    return nspec > 4 ? tf_pick_ns<NN, CPL, S11, 8, PP, TPB, MINB>(den) : tf_pick_ns<NN, CPL, S11, 4, PP, TPB, MINB>(den);
+}
+template <int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_gd_ns(int den)
 {
     switch (den) {
-    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<4, QO_TF_DEN_NONE, false, false, true, PP, TPB, MINB>;
-    case QO_TF_DEN_DD: return qo_mc_tf_kernel<4, QO_TF_DEN_DD, false, false, true, PP, TPB, MINB>;
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<4, QO_TF_DEN_NONE, false, false, true, NS, PP, TPB, MINB>;
+    case QO_TF_DEN_DD: return qo_mc_tf_kernel<4, QO_TF_DEN_DD, false, false, true, NS, PP, TPB, MINB>;
     default: return nullptr;
     }
+}
+template <int PP, int TPB, int MINB> static tf_fn tf_pick_gd(int den, int nspec)
+{
+    return nspec > 4 ? tf_pick_gd_ns<8, PP, TPB, MINB>(den) : tf_pick_gd_ns<4, PP, TPB, MINB>(den);
 }
 
 extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st)
@@ -64,10 +72,10 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
     if (!fn)
 #endif
     {
-        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den);
-        else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
-        else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
-        else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
     }
     if (!fn) return -1;
     const unsigned long long warps = (unsigned long long)(tpb / 32);
@@ -194,7 +202,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     const char *force = getenv("QO100NET_KERNEL");
     if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
     if (generic || !mode_reduce_only || precision != 64) QO_TF_NO("not a reduce-only FP64 job on a lumped cascade");
-    if (hp->nspec < 1 || hp->nspec > QO_LAD_NSPEC || hp->n_var > QO_MAX_VAR) QO_TF_NO("spec / variable count");
+    if (hp->nspec < 1 || hp->nspec > QO_TF_NSPEC || hp->n_var > QO_MAX_VAR) QO_TF_NO("spec / variable count");
     for (int s = 0; s < hp->nspec; s++)
         if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX && hp->spec_kind[s] != SK_GD_MAX) QO_TF_NO("spec kind");
     int need_s21 = 0;

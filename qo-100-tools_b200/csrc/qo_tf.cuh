@@ -30,6 +30,7 @@
 #define QO_TF_MAXK 15            /* coefficient PAIRS per numerator polynomial: degree <= 29 (lanes 30, 31 stay zero: free shuffle wrap-around) */
 #define QO_TF_MAXKE 30           /* coefficients of E(y) kept at most */
 #define QO_TF_MAXEL 24           /* lumped elements */
+#define QO_TF_NSPEC 8            /* specs per job (kernels are instantiated for up to 4 and up to 8) */
 #define QO_TF_REC 10             /* doubles per element record: N0 N1 N2 D0 D1 D2 E0 E1 E2 series */
 
 /* How |D(jx)|^2 is evaluated:
@@ -45,16 +46,16 @@ struct TfParams {
     const double2 *yt;                       /* -(w / wref)^2 per grid point, two points per entry, padded to whole iterations */
     const double2 *xt;                       /* w / wref (coupler mode: imaginary parts need x itself) */
     const double2 *wt;                       /* w (coupler block), padded likewise */
-    const uint2 *mb;                         /* per point one word: byte s = 0xFF when the point lies in spec s's band (padding: 0) */
+    const uint4 *mb;                         /* per point two words (a pair per entry): byte s = 0xFF when the point lies in spec s's band (padding: 0) */
     const uchar2 *itm;                       /* per iteration of PP*32 pairs: (OR, AND) of the spec bit masks of its points */
     const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the nominal mode angles (cpl_fast), padded */
     unsigned long long *counters, *ticket;
     unsigned long long sample_offset, nsamples, seed;
     double rs, rl, k21, hist_lo, hist_hi, wref, zn, zni;
-    double thr[QO_LAD_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
-    int neg[QO_LAD_NSPEC];
-    int s11[QO_LAD_NSPEC];                   /* the spec is on |S11|^2 = |P - Rs Q|^2 / |P + Rs Q|^2 (FAIL iff > thr) */
-    int gd[QO_LAD_NSPEC];                    /* the spec is on the group delay: thr = limit [s] * wref (FAIL iff tau * wref > thr) */
+    double thr[QO_TF_NSPEC];                /* canonical threshold on |den|^2: FAIL iff |den|^2 > thr (neg: < thr) */
+    int neg[QO_TF_NSPEC];
+    int s11[QO_TF_NSPEC];                   /* the spec is on |S11|^2 = |P - Rs Q|^2 / |P + Rs Q|^2 (FAIL iff > thr) */
+    int gd[QO_TF_NSPEC];                    /* the spec is on the group delay: thr = limit [s] * wref (FAIL iff tau * wref > thr) */
     int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
@@ -114,6 +115,7 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
  * CPL    coupled-line block in front (its row vector is contracted with [P; Q] per point)
  * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
+ * NS     spec slots: 4 or 8 (trackers of the sign kind are one 32-bit register each)
  * GD     the job has group-delay specs: tau = d arg(den)/dw = Re(Num'/Num - D'/D) / wref with the derivative polynomials
  *        Num' = dNum/dsn, D' = dD/dsn evaluated by two more Horner chains each (no finite difference, no atan2)
  * DEN    QO_TF_DEN_*                  PP   frequency pairs per thread per iteration (PTS = 2*PP points)
@@ -131,7 +133,7 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
  * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
  */
-template <int NN, int DEN, bool CPL, bool S11, bool GD, int PP, int TPB, int MINB>
+template <int NN, int DEN, bool CPL, bool S11, bool GD, int NS, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr int PTS = 2 * PP;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     const double rs = P.rs;
     const int up1 = (lane + 31) & 31, up2 = (lane + 30) & 31;
     const int hs = P.hist_spec;
-    const bool hneg = hs >= 0 && P.neg[hs & (QO_LAD_NSPEC - 1)];
+    const bool hneg = hs >= 0 && P.neg[hs & (QO_TF_NSPEC - 1)];
     const int kn = P.kn, kd = P.kd;
 
     const unsigned long long total_warps = (unsigned long long)gridDim.x * WARPS;
@@ -231,9 +233,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
 
         /* 3. frequency loop */
         double trkv = hneg ? 1.7e308 : -1.7e308;     /* histogram spec: running extreme of |den|^2 */
-        unsigned int acc[QO_LAD_NSPEC];              /* other specs: OR of the sign words of g */
+        unsigned int acc[NS];              /* other specs: OR of the sign words of g */
 #pragma unroll
-        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) acc[sp] = 0u;
+        for (int sp = 0; sp < NS; sp++) acc[sp] = 0u;
         for (int it = 0; it < P.niter; it++) {
             const int j0 = it * (32 * PP) + lane;
             double y[PTS];
@@ -394,7 +396,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             if (any == all) {
                 /* one mask on every point of the iteration (possibly none): no per-point selects */
 #pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+                for (int sp = 0; sp < NS; sp++) {
                     if ((all >> sp) & 1u) {
                         if (sp == hs) {
                             QO_TF_VALUE(val)
@@ -408,25 +410,25 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 }
             } else {
                 /* the iteration straddles a band edge: per-point byte masks */
-                unsigned int mw[PTS];
+                unsigned int mw[PTS], mh[PTS];          /* byte masks of specs 0-3 and 4-7 */
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) {
-                    const uint2 m = P.mb[j0 + 32 * qq];
-                    mw[2 * qq] = m.x; mw[2 * qq + 1] = m.y;
+                    const uint4 m = P.mb[j0 + 32 * qq];
+                    mw[2 * qq] = m.x; mh[2 * qq] = m.y; mw[2 * qq + 1] = m.z; mh[2 * qq + 1] = m.w;
                 }
 #pragma unroll
-                for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+                for (int sp = 0; sp < NS; sp++) {
                     if ((any >> sp) & 1u) {
                         if (sp == hs) {
                             QO_TF_VALUE(val)
                             QO_PTS {
-                                const bool in = (mw[p] >> (8 * sp)) & 1u;
+                                const bool in = ((sp < 4 ? mw[p] : mh[p]) >> (8 * (sp & 3))) & 1u;
                                 if (hneg) { const double c = in ? val[p] : 1.7e308; trkv = c < trkv ? c : trkv; }
                                 else { const double c = in ? val[p] : -1.7e308; trkv = c > trkv ? c : trkv; }
                             }
                         } else {
                             QO_TF_SIGN(sg)
-                            QO_PTS acc[sp] |= sg[p] & __byte_perm(mw[p], 0, 0x1111 * sp);
+                            QO_PTS acc[sp] |= sg[p] & __byte_perm(sp < 4 ? mw[p] : mh[p], 0, 0x1111 * (sp & 3));
                         }
                     }
                 }
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         /* 4. per-sample verdict */
         unsigned int fail = 0;
 #pragma unroll
-        for (int sp = 0; sp < QO_LAD_NSPEC; sp++) {
+        for (int sp = 0; sp < NS; sp++) {
             if (sp < P.nspec && sp != hs) {
                 const unsigned int a = __reduce_or_sync(0xffffffffu, acc[sp]);
                 if (a >> 31) fail |= 1u << sp;
@@ -450,7 +452,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 const double o = __shfl_xor_sync(0xffffffffu, trkv, off);
                 trkv = hneg ? (o < trkv ? o : trkv) : (o > trkv ? o : trkv);
             }
-            const double t = P.thr[hs & (QO_LAD_NSPEC - 1)];
+            const double t = P.thr[hs & (QO_TF_NSPEC - 1)];
             if (hneg ? trkv < t : trkv > t) fail |= 1u << hs;
         }
         if (lane == 0) {
@@ -460,8 +462,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 if ((fail >> sp) & 1u) atomicAdd(&s_cnt[2 + sp], 1u);
             if (hs >= 0) {
                 const double k21 = P.k21;
-                const double lin = (S11 && P.s11[hs & (QO_LAD_NSPEC - 1)]) ? trkv : hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
-                const double v = (GD && P.gd[hs & (QO_LAD_NSPEC - 1)]) ? trkv / P.wref : 10.0 * log10(lin);      /* seconds, or dB */
+                const double lin = (S11 && P.s11[hs & (QO_TF_NSPEC - 1)]) ? trkv : hneg ? k21 * k21 * (1.0 / trkv) : k21 * k21 / trkv;
+                const double v = (GD && P.gd[hs & (QO_TF_NSPEC - 1)]) ? trkv / P.wref : 10.0 * log10(lin);      /* seconds, or dB */
                 const double xb = (v - P.hist_lo) / (P.hist_hi - P.hist_lo) * (double)P.hist_bins;
                 long long b = (long long)floor(xb);
                 if (!(xb >= 0.0)) b = 0;

@@ -420,7 +420,10 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                                                      # |S11| behind the coupler block
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()             # group delay: derivative polynomials
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()   # GD + |S11|: interpreter
-    p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # > 4 specs
+    p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()                                     # 6 specs: the 8-slot instantiation
+    monkeypatch.setenv("QO100NET_KERNEL", "ladder")
+    p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                                 # the chain kernel keeps 4 trackers in registers
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
     p = mk([], mode=Q.MODE_FULL_S); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()                      # HBM-bound mode
     p = mk(w.specs, precision=32); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                       # optional FP32 mode
     p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], precision=32); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()
@@ -806,3 +809,39 @@ def test_tf_kernel_size_limits_and_degenerate_degrees(Q, R, W, ctx, monkeypatch)
     run(net25, specs4[:2], Q.lc_tolerances(net25, 0.03, 0.03), "qo_mc_lumped_kernel")                      # one branch too many
     lossy15 = Q.Net.from_elements(long_el[:15], 50.0, 50.0).add_parasitics(fc, 60.0, 30.0, 0.1, 50.0)   # 15 lossy branches: degree 30
     run(lossy15, specs4[:2], Q.lc_tolerances(lossy15, 0.03, 0.03), "qo_mc_lumped_kernel")
+
+
+def test_tf_kernel_eight_specs(Q, R, W, ctx, monkeypatch):
+    """5-8 specs take the 8-slot instantiation of the transfer-function kernel: |S21| min/max bands, |S11|, with the
+    histogram on a high slot, on a grid whose band edges cut through iterations -- counters equal the oracle's and the
+    interpreter's."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    w = W.cfg2()
+    fc = 10e6
+    f = w.f[::3]
+    db = 20 * np.log10(np.abs(ctx.sweep(w.net, f)[1]))
+
+    def lo(a, b, margin):      # |S21| >= (nominal worst in [a, b]) - margin
+        return (Q.SPEC_S21_MIN_DB, a, b, float(db[(f >= a) & (f <= b)].min()) - margin)
+
+    def hi(a, b, margin):      # |S21| <= (nominal worst in [a, b]) + margin
+        return (Q.SPEC_S21_MAX_DB, a, b, float(db[(f >= a) & (f <= min(b, f[-1]))].max()) + margin)
+
+    base = [lo(0.0, 0.95 * fc, 0.15), hi(1.3 * fc, 1e99, 1.4), lo(0.0, 0.5 * fc, 0.03), hi(2.0 * fc, 3.0 * fc, 1.0), hi(3.0 * fc, 1e99, 1.0),
+            lo(0.6 * fc, 0.9 * fc, 0.05), hi(1.5 * fc, 1.6 * fc, 1.5), lo(0.9 * fc, 0.97 * fc, 0.3)]
+    h4 = float(db[f >= 3.0 * fc].max())
+    cases = [(base[:5], 4, (h4 - 4.0, h4 + 4.0)), (base, 7, (-4.0, 0.0)), (base[:6] + [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0)], 6, (-20.0, 0.0))]
+    for specs, hs, (lo, hi) in cases:
+        hist = dict(hist_bins=50, hist_spec=hs, hist_lo=lo, hist_hi=hi)
+        plan = Q.Plan(ctx, w.net, f, specs, seed=17, tols=w.tols, **hist)
+        assert plan.kernel_name == "qo_mc_tf_kernel", plan.tf_info
+        plan.launch(2, 900)
+        got = plan.read()
+        plan.close()
+        ref = R.mc_run(to_ref(R, w.net), 50, 50, f, specs, R.mc_cfg(17, 900, w.tols, sample_offset=2, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)
+        assert np.count_nonzero(got["fail_per_spec"]) >= 3 and np.count_nonzero(got["hist"]) > 3
+        monkeypatch.setenv("QO100NET_KERNEL", "interp")
+        itp = ctx.mc_run(w.net, f, specs, 17, 900, w.tols, sample_offset=2, **hist)
+        monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        _assert_counts_equal(itp, got)

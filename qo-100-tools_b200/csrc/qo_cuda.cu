@@ -21,6 +21,7 @@
 #include "qo_ladder_launch.h"
 #include "qo_tf.cuh"
 #include "qo_tf_launch.h"
+#include "qo_spot.cuh"
 #include "qo_ustrip.cuh"
 #include "qo_cpl_core.h"
 
@@ -66,6 +67,7 @@ struct qo_plan {
     int nf, npairs, ncnt, precision, mode, generic;
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
+    int spot, spot_el0, spot_nel;                         /* spot-frequency kernel (qo_spot.cuh): <= 8 points per sample */
     int tf;                                               /* transfer-function kernel (qo_tf.cuh) selected */
     TfPlan tfp;                                           /* its polynomial lengths, denominator form, self-check result */
     int tf_pp, tf_niter;                                  /* pairs per thread per iteration; iterations per sample */
@@ -367,6 +369,23 @@ static int ladder_eligible(const DevProg *hp, int mode, int precision, int gener
     return 1;
 }
 
+/* The spot-frequency kernel (one thread per sample) serves reduce-only FP64 jobs on lumped cascades evaluated at a handful
+ * of frequencies -- BASELINE config 3's harmonic-rejection yield at 2.4 / 4.8 / 7.2 GHz. */
+static int spot_eligible(const DevProg *hp, int mode, int precision, int generic, int nf, int *el0, int *nel)
+{
+    const char *force = getenv("QO100NET_KERNEL");
+    if (force && strcmp(force, "auto") != 0 && strcmp(force, "spot") != 0) return 0;
+    if (generic || mode != QO_MODE_REDUCE_ONLY || precision != 64 || hp->need_gd) return 0;
+    if (nf > QO_SPOT_MAXF || hp->nspec < 1 || hp->nspec > QO_NSPEC_MAX) return 0;
+    const int e0 = hp->op0, nl = hp->n_ops - e0;
+    if (nl < 1 || nl > QO_SPOT_MAXEL) return 0;
+    for (int e = 0; e < nl; e++) if (qo_tf_degree(hp->opcode[e0 + e]) < 0) return 0;
+    for (int s = 0; s < hp->nspec; s++)
+        if (hp->spec_kind[s] != SK_DEN2_MAX && hp->spec_kind[s] != SK_DEN2_MIN && hp->spec_kind[s] != SK_S11_MAX) return 0;
+    *el0 = e0; *nel = nl;
+    return 1;
+}
+
 /* ---- plan ---------------------------------------------------------------- */
 extern "C" void qo_plan_destroy(qo_plan *p)
 {
@@ -412,7 +431,9 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         p->lad_variant = v ? atoi(v) : 0;
     }
     p->tf = qo_tf_plan_check(&p->hp, p->mode == QO_MODE_REDUCE_ONLY, p->precision, p->generic, f, nf, p->maskv.data(), &p->tfp);
-    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
+    p->spot = spot_eligible(&p->hp, p->mode, p->precision, p->generic, nf, &p->spot_el0, &p->spot_nel);
+    if (p->spot) p->tf = p->ladder = 0;
+    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->spot ? "qo_mc_spot_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
     const double two_pi = 6.283185307179586476925286766559;
@@ -806,6 +827,26 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     return QO_OK;
 }
 
+static int launch_spot(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    const DevProg *hp = &p->hp;
+    SpotParams P;
+    memset(&P, 0, sizeof P);
+    P.prog = p->d[g].prog; P.counters = cnt;
+    P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
+    P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k = 0; k < p->nf; k++) { P.w[k] = two_pi * p->f[k]; P.mask[k] = p->maskv[k]; }
+    for (int s = 0; s < hp->nspec; s++) { P.thr[s] = hp->spec_thr[s]; P.kind[s] = hp->spec_kind[s]; }
+    P.nf = p->nf; P.n_el = p->spot_nel; P.el0 = p->spot_el0; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.hist_bins = hp->hist_bins;
+    P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
+    int rc = qo_spot_launch(hp->need_s11, dc->sm_count, &P, dc->stream);
+    if (rc) { qo_set_error("spot kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
 static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
 {
     DevCtx *dc = &p->ctx->d[g];
@@ -861,6 +902,7 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
     }
     int rc;
     if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
+    else if (p->spot) rc = launch_spot(p, g, off, n, cnt);
     else if (p->tf) rc = launch_tf(p, g, off, n, cnt, cplms);
     else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt, cplms);
     else if (p->precision == 32) rc = launch_lumped<float>(p, g, off, n, cnt, pl, full_s);

@@ -126,10 +126,9 @@ QO_HD double qo_norminv(double p)
     return QO_DIV(QO_MUL(num, q), den);
 }
 
-/* x in [-1, 1] for random variable `var` of sample `sample` */
-QO_HD double qo_stream_variate(uint64_t seed, uint64_t sample, uint32_t var, int dist)
+/* x in [-1, 1] from the 53 stream bits of one variable */
+QO_HD double qo_stream_from_bits53(uint64_t k, int dist)
 {
-    uint64_t k = qo_stream_bits53(seed, sample, var);
     if (dist == 1) {
         double p = QO_FMA(QO_U2D(k), 0x1p-53, 0x1p-54);
         double z = qo_norminv(p);
@@ -138,6 +137,12 @@ QO_HD double qo_stream_variate(uint64_t seed, uint64_t sample, uint32_t var, int
         return QO_DIV(z, 3.0);
     }
     return QO_FMA(2.0, QO_MUL(QO_U2D(k), 0x1p-53), -1.0);
+}
+
+/* x in [-1, 1] for random variable `var` of sample `sample` */
+QO_HD double qo_stream_variate(uint64_t seed, uint64_t sample, uint32_t var, int dist)
+{
+    return qo_stream_from_bits53(qo_stream_bits53(seed, sample, var), dist);
 }
 
 /* perturbed parameter value: REL nominal*fma(tol,x,1) ; ABS fma(tol,x,nominal) */

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include "qo_tf.cuh"
+#include "qo_spot.cuh"
 #include "qo_tf_launch.h"
 
 /* launch shapes (tools/tf_sweep.py, profiles/r01h_*): plain ladders run 8 points per thread (coefficient loads and loop
@@ -84,6 +85,17 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
     if (blocks > resident) blocks = resident;
     if (blocks < 1) blocks = 1;
     fn<<<(unsigned)blocks, tpb, 0, st>>>(*P);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int qo_spot_launch(int need_s11, int sm_count, const SpotParams *P, cudaStream_t st)
+{
+    unsigned long long blocks = (P->nsamples + QO_SPOT_TPB - 1) / QO_SPOT_TPB;
+    const unsigned long long cap = (unsigned long long)sm_count * 4 * 8;        /* 8 waves of resident blocks, grid-stride beyond */
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    if (need_s11) qo_mc_spot_kernel<true><<<(unsigned)blocks, QO_SPOT_TPB, 0, st>>>(*P);
+    else qo_mc_spot_kernel<false><<<(unsigned)blocks, QO_SPOT_TPB, 0, st>>>(*P);
     return (int)cudaGetLastError();
 }
 

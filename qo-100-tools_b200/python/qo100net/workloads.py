@@ -79,6 +79,19 @@ def cfg3(n_samples=10000000):
                     dict(hist_bins=64, hist_spec=1, hist_lo=-30.0, hist_hi=-15.0), n_samples, seed_for(3))
 
 
+def cfg3b(n_samples=10000000):
+    """Config 3 as BASELINE.json words it ("PA LPF with ESR/SRF parasitics, harmonic-rejection yield at 2.4/4.8/7.2 GHz"): the
+    reference tree holds the PA low-pass only as the microstrip layout of cfg3(); this is its lumped twin -- a
+    7th-order 0.1 dB Chebyshev LC low-pass, fc = 2.9 GHz, with the config-2 parasitic model, +-5 % L / +-2 % C, evaluated at the
+    carrier and its two harmonics only (3 points per sample: per-sample work dominates)."""
+    fc = 2.9e9
+    net = Net.cheby_lpf(7, 0.1, fc, 50.0, True).add_parasitics(fc, 60.0, 30.0, 0.1, 50.0)
+    f = np.array([2.4e9, 4.8e9, 7.2e9])
+    specs = [(SPEC_S21_MIN_DB, 2.3e9, 2.5e9, -0.70), (SPEC_S21_MAX_DB, 4.7e9, 4.9e9, -43.0), (SPEC_S21_MAX_DB, 7.1e9, 7.3e9, -71.5)]
+    return Workload("cfg3b-pa-lpf-lumped-twin-yield", net, f, specs, lc_tolerances(net, 0.05, 0.02),
+                    dict(hist_bins=64, hist_spec=1, hist_lo=-50.0, hist_hi=-38.0), n_samples, seed_for(3))
+
+
 def gpsdo_bank():
     """(name, net, fc): 10M Chebyshev 100/50 Ohm + 15M/40M/60M elliptic 50/50 Ohm."""
     def ell(vals):

@@ -209,6 +209,48 @@ def test_cfg3_microstrip_yield_equals_oracle(Q, R, W, ctx):
     assert 0.5 < gg["n_pass"] / gg["n_total"] < 0.85
 
 
+def test_cfg3b_lumped_twin_yield_equals_oracle(Q, R, W, ctx, monkeypatch):
+    """BASELINE config 3 as worded (lumped PA LPF with ESR/SRF parasitics, 3 points per sample): counters equal the oracle's on
+    the spot-frequency kernel (one thread per sample, the default for <= 8 points) and on the three warp-per-sample kernels;
+    the yield sits where the oracle put it when the spec limits were chosen (0.70).  Also |S11| specs, 8 points, gaussian draws
+    and an rf-tools filter with traps on the spot kernel."""
+    w = W.cfg3b()
+    for force, name in ((None, "qo_mc_spot_kernel"), ("tf", "qo_mc_tf_kernel"), ("ladder", "qo_mc_ladder_kernel"), ("interp", "qo_mc_lumped_kernel")):
+        if force:
+            monkeypatch.setenv("QO100NET_KERNEL", force)
+        else:
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+        assert plan.kernel_name == name
+        plan.close()
+        og, gg = _mc_both(Q, R, ctx, w, 20000)
+        _assert_counts_equal(og, gg)
+        assert 0.65 < gg["n_pass"] / gg["n_total"] < 0.75 and np.all(gg["fail_per_spec"] > 0)
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    fc = 2.9e9
+    f8 = np.array([0.5e9, 1.2e9, 2.0e9, 2.4e9, 2.7e9, 4.8e9, 6.0e9, 7.2e9])
+    specs = [(Q.SPEC_S11_MAX_DB, 0.0, 2.5e9, -9.0), (Q.SPEC_S21_MIN_DB, 0.0, 2.75e9, -1.0), (Q.SPEC_S21_MAX_DB, 4.7e9, 1e99, -43.0)]
+    for hs, lo, hi in ((0, -25.0, 0.0), (1, -3.0, 0.0), (2, -50.0, -38.0)):
+        hist = dict(hist_bins=48, hist_spec=hs, hist_lo=lo, hist_hi=hi)
+        plan = Q.Plan(ctx, w.net, f8, specs, seed=5, tols=w.tols, dist=Q.DIST_GAUSS3S, **hist)
+        assert plan.kernel_name == "qo_mc_spot_kernel"
+        plan.launch(9, 3000)
+        got = plan.read()
+        plan.close()
+        ref = R.mc_run(to_ref(R, w.net), 50, 50, f8, specs, R.mc_cfg(5, 3000, w.tols, sample_offset=9, dist=Q.DIST_GAUSS3S, **hist), nthreads=8)
+        _assert_counts_equal(ref, got)
+        assert 0 < got["n_pass"] < 3000
+    _, ell, fe = W.gpsdo_bank()[1]
+    f3 = np.array([0.5 * fe, 0.8 * fe, 2.2 * fe])
+    specs = [(Q.SPEC_S21_MIN_DB, 0.0, 0.85 * fe, -0.6), (Q.SPEC_S21_MAX_DB, 2.0 * fe, 1e99, -45.0)]
+    tols = Q.lc_tolerances(ell, 0.05, 0.05)
+    got = ctx.mc_run(ell, f3, specs, 8, 5000, tols)
+    ref = R.mc_run(to_ref(R, ell), 50, 50, f3, specs, R.mc_cfg(8, 5000, tols), nthreads=8)
+    _assert_counts_equal(ref, got)
+    nine = Q.Plan(ctx, w.net, np.linspace(1e9, 7e9, 9), w.specs, seed=1, tols=w.tols)       # 9 points: back to the warp-per-sample kernels
+    assert nine.kernel_name == "qo_mc_tf_kernel"; nine.close()
+
+
 def test_s11_spec_and_histogram(Q, R, W, ctx, monkeypatch):
     """|S11| specs against the oracle on every kernel that serves them: the transfer-function kernel (S11 =
     (P - Rs Q) / (P + Rs Q); plain ladders), the chain kernel's second row vector (forced, and the default behind

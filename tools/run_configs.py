@@ -124,6 +124,14 @@ def main():
             d["cpu_1_thread_evals_per_s"] = cpu_rate(R, wl, 2000, 1)
             d["cpu_all_cores_evals_per_s"] = cpu_rate(R, wl, 40000, nthr)
         out["configs"]["cfg3"] = d
+        # the lumped twin BASELINE.json's wording describes: 3 points per sample, per-sample work dominates
+        wl = W.cfg3b(n)
+        ms, name, fl, c = timed_plan(wl, n, 2)
+        d = {"workload": wl.name, "samples": n, "nf": 3, "ms": ms, "evals_per_s": n * 3 / ms * 1e3, "samples_per_s": n / ms * 1e3, "kernel": name,
+             "yield": float(c[0]) / max(1, int(c[1]))}
+        if not args.no_cpu:
+            d["cpu_all_cores_evals_per_s"] = cpu_rate(R, wl, 400000, nthr)
+        out["configs"]["cfg3b"] = d
     if "cfg4" in only and rank == 0:
         n = 65536 // q
         rows = {}

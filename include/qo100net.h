@@ -265,7 +265,8 @@ int qo_plan_launch(qo_plan *plan, uint64_t sample_offset, uint64_t n_samples, ui
 int qo_plan_read(qo_plan *plan, qo_mc_result *res);   /* synchronises, combines across the ctx's GPUs */
 double qo_plan_flops_per_eval(const qo_plan *plan);
 int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far by this plan */
-/* which kernel the plan launches: "qo_mc_tf_kernel" (transfer-function kernel: reduce-only |S21| jobs on lumped
+/* which kernel the plan launches: "qo_mc_spot_kernel" (one thread per sample: reduce-only jobs on lumped cascades with
+ * <= 8 frequencies), "qo_mc_tf_kernel" (transfer-function kernel: reduce-only |S21| / |S11| / group-delay jobs on lumped
  * cascades, optionally behind one coupled-line block), "qo_mc_ladder_kernel" (straight-line ABCD-chain kernel of
  * the pcb/generic-filter ladder family), "qo_mc_lumped_kernel" (opcode interpreter) or "qo_mc_generic_kernel"
  * (microstrip).  QO100NET_KERNEL=ladder keeps jobs off the transfer-function kernel, =interp forces the interpreter. */

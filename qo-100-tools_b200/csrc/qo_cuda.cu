@@ -581,7 +581,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
             if (p->tf) {
                 /* tables of the transfer-function kernel, padded to whole iterations (padding repeats the last grid
                  * point and carries no spec bit, so the loop needs no bounds checks) */
-                p->tf_pp = qo_tf_default_pp(&p->tfp);
+                p->tf_pp = qo_tf_default_pp(&p->tfp, np);
 #ifdef QO_TF_EXPERIMENT
                 if (getenv("QO100NET_TF_PP")) p->tf_pp = atoi(getenv("QO100NET_TF_PP"));
 #endif

@@ -24,7 +24,13 @@
 
 typedef void (*tf_fn)(const TfParams);
 
-extern "C" int qo_tf_default_pp(const TfPlan *tp) { return tp->nn == 4 ? QO_TF_CPL_PP : QO_TF_PP; }
+/* pairs per thread per iteration: short grids take one pair per thread (iterations of 64 points) so that the padding to whole
+ * iterations does not dominate -- 8 points per thread are ~25 % cheaper per point but pad to 512 */
+extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs)
+{
+    if (tp->nn == 4) return npairs <= 32 ? 1 : QO_TF_CPL_PP;
+    return npairs <= 192 ? 1 : QO_TF_PP;
+}
 
 template <int NN, bool CPL, bool S11, int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_ns(int den)
 {
@@ -74,6 +80,10 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
 #endif
     {
         if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 2 && pp == 1) fn = tf_pick<2, false, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->gd && pp == 1) fn = tf_pick_gd<1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && tp->s11 && pp == 1) fn = tf_pick<4, false, true, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && !tp->s11 && pp == 1) fn = tf_pick<4, true, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
         else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
         else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }

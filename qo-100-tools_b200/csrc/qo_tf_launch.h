@@ -25,7 +25,7 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
 /* pp = frequency pairs per thread per iteration the plan padded its tables for; returns 0, -1 when no
  * instantiation covers (nn, den, pp), else the cudaError_t of the launch */
 extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st);
-extern "C" int qo_tf_default_pp(const TfPlan *tp);
+extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs);
 
 /* spot-frequency kernel (qo_spot.cuh): one thread per sample, <= 8 frequencies; returns 0 or the cudaError_t of the launch */
 struct SpotParams;

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Round-end profiling recipe (B200_PROFILING.md): plain bench first, then the ncu launch list, then one
-# --set full capture per hot kernel.  Run on the GPU box:  bash tools/profile_all.sh <tag>
-# Numbers printed under ncu are never bench values.
+# --set full capture per hot kernel.  Run on the GPU box:  bash tools/profile_all.sh <tag> [all]
+# Numbers printed under ncu are never bench values.  Each capture is summarised on the box (tools/ncu_summary.py ->
+# <tag>_<name>_details.txt / _raw_metrics.txt) and the .ncu-rep deleted: gpurun brings back at most 64 MiB.
 set -u
 TAG=${1:-rXX}
 OUT=gpurun_out
@@ -11,11 +12,20 @@ tail -c 600 $OUT/bench_${TAG}.json
 timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_${TAG}.csv \
     python bench.py --steps 3 --warmup 3 > $OUT/ncu_${TAG}_list.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
-timeout 200 $NCU -k regex:qo_mc_tf -s 3 -c 1 -o $OUT/prof_${TAG}_tf_cfg2 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 > $OUT/ncu_${TAG}_a.log 2>&1
-timeout 200 $NCU -k regex:qo_mc_tf -s 3 -c 1 -o $OUT/prof_${TAG}_tf_cfg5 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5 > $OUT/ncu_${TAG}_b.log 2>&1
+cap() {   # name, evals per launch, kernel regex, skip, command...
+    local name=$1 evals=$2 rx=$3 skip=$4; shift 4
+    timeout 240 $NCU -k regex:$rx -s $skip -c 1 -o $OUT/prof_${TAG}_${name} "$@" > $OUT/ncu_${TAG}_${name}.log 2>&1
+    python tools/ncu_summary.py $OUT/prof_${TAG}_${name}.ncu-rep $OUT/${TAG}_${name} $evals > /dev/null 2>&1 || echo "summary of $name failed"
+    rm -f $OUT/prof_${TAG}_${name}.ncu-rep
+}
+cap tf_cfg2 819200000 qo_mc_tf 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
+cap tf_cfg5 819200000 qo_mc_tf 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
 if [ "${2:-}" = "all" ]; then
-QO100NET_KERNEL=ladder timeout 200 $NCU -k regex:ladder -s 3 -c 1 -o $OUT/prof_${TAG}_ladder_cfg2 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 > $OUT/ncu_${TAG}_c.log 2>&1
-timeout 200 $NCU -k regex:lumped -s 2 -c 1 -o $OUT/prof_${TAG}_fulls python bench.py --steps 1 --warmup 3 --samples 20000 > $OUT/ncu_${TAG}_d.log 2>&1
-timeout 200 $NCU -k regex:nodal -s 1 -c 1 -o $OUT/prof_${TAG}_nodal python tools/nodal_bench.py --samples 4000 > $OUT/ncu_${TAG}_e.log 2>&1
+export QO100NET_KERNEL=ladder
+cap ladder_cfg2 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
+unset QO100NET_KERNEL
+cap fulls 81920000 lumped 2 python bench.py --steps 1 --warmup 3 --samples 20000
+cap nodal 4000000 nodal 1 python tools/nodal_bench.py --samples 4000
+cap generic_cfg3 1200000 generic 2 python tools/cfg3_run.py
 fi
 ls -la $OUT/*${TAG}*

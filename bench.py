@@ -249,14 +249,21 @@ def main():
         d2h = ncnt * 8
         for i in range(2):
             ctx.mc_run(wl.net, wl.f, wl.specs, wl.seed, nspg, wl.tols, sample_offset=rank * nspg, **wl.hist)
+        # N > 1: the host results are summed across ranks through one reused pinned buffer (H2D, all-reduce, D2H per step)
+        hc_pin = torch.zeros(2 + len(wl.specs) + wl.hist["hist_bins"], dtype=torch.int64).pin_memory() if dist is not None else None
+        hc_dev = torch.zeros_like(hc_pin, device="cuda") if dist is not None else None
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             r = ctx.mc_run(wl.net, wl.f, wl.specs, wl.seed, nspg, wl.tols, sample_offset=((100 + i) * world + rank) * nspg, **wl.hist)
             if dist is not None:
-                hc = torch.tensor([r["n_pass"], r["n_total"]], dtype=torch.int64).pin_memory().cuda(non_blocking=True)
-                qd.allreduce_counters(hc)
-                hc.cpu()
+                hc_pin[0], hc_pin[1] = r["n_pass"], r["n_total"]
+                hc_pin[2:2 + len(wl.specs)] = torch.from_numpy(r["fail_per_spec"].astype(np.int64))
+                hc_pin[2 + len(wl.specs):] = torch.from_numpy(r["hist"].astype(np.int64))
+                hc_dev.copy_(hc_pin, non_blocking=True)
+                qd.allreduce_counters(hc_dev)
+                hc_pin.copy_(hc_dev)
+                torch.cuda.current_stream().synchronize()
         barrier()
         e2e_s = time.perf_counter() - t0
         clocks = sampler.stop() if sampler else None       # sampled over both timed regions (resident steps and end-to-end steps)

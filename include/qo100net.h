@@ -94,6 +94,11 @@ int qo_cpl_load_trc(const char *path, double *z0e, double *z0o, double *ang_deg,
  * action that produced *.trc:18-20.  SI units; angles in degrees. */
 int qo_cpl_analyze(double w, double s, double h, double t, double er, double ht, double f, double len,
                    double *z0e, double *z0o, double *ang_e_deg, double *ang_o_deg);
+/* QucsTranscalc "synthesize" for CoupledMicrostrip (electrical -> physical), the action that produced the W / S / L
+ * lines *.trc:15-17 from Z0e / Z0o / Ang_l :18-20 (Ang_l = sqrt(theta_e theta_o)).  QO_ERR_RANGE when the substrate
+ * cannot realise the pair. */
+int qo_cpl_synthesize(double z0e, double z0o, double ang_deg, double h, double t, double er, double ht, double f,
+                      double *w, double *s, double *len);
 
 int qo_net_from_elements(const qo_elem *e, int n, double rs, double rl, qo_net **out);
 /* pcb/generic-filter (README.md:13; qo-100-generic-filter.sch:1450-1488,1703-1995):

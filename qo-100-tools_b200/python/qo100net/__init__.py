@@ -86,7 +86,7 @@ def build(verbose=False):
 
 _lib = None
 EXPORTS = [
-    "qo_net_load_rftools_svg", "qo_net_load_qucs_sch", "qo_qucs_sch_sweep", "qo_cpl_load_trc", "qo_cpl_analyze",
+    "qo_net_load_rftools_svg", "qo_net_load_qucs_sch", "qo_qucs_sch_sweep", "qo_cpl_load_trc", "qo_cpl_analyze", "qo_cpl_synthesize",
     "qo_net_from_elements", "qo_net_cheby_lpf", "qo_net_butter_lpf", "qo_net_add_parasitics", "qo_net_concat",
     "qo_net_num_elements", "qo_net_get_elements", "qo_net_terminations", "qo_net_title", "qo_net_free",
     "qo_grid_lin", "qo_grid_log", "qo_ctx_create", "qo_ctx_create_on_device", "qo_ctx_set_stream",
@@ -121,6 +121,7 @@ def lib():
         "qo_qucs_sch_sweep": (C.c_int, [C.c_char_p, ip, dp, dp, ip]),
         "qo_cpl_load_trc": (C.c_int, [C.c_char_p, dp, dp, dp, dp, dp]),
         "qo_cpl_analyze": (C.c_int, [C.c_double] * 8 + [dp] * 4),
+        "qo_cpl_synthesize": (C.c_int, [C.c_double] * 8 + [dp] * 3),
         "qo_net_from_elements": (C.c_int, [C.POINTER(Elem), C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
         "qo_net_cheby_lpf": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]),
         "qo_net_butter_lpf": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_int, C.POINTER(vp)]),
@@ -510,6 +511,13 @@ class Dataset:
 def cpl_analyze(w, s, h, t, er, ht, f, length):
     o = [C.c_double() for _ in range(4)]
     _check(lib().qo_cpl_analyze(w, s, h, t, er, ht, f, length, *[C.byref(x) for x in o]))
+    return tuple(x.value for x in o)
+
+
+def cpl_synthesize(z0e, z0o, ang_deg, h, t, er, ht, f):
+    """(W, S, L) of the coupled microstrip with these mode impedances and electrical length (qo_cpl_synthesize)."""
+    o = [C.c_double() for _ in range(3)]
+    _check(lib().qo_cpl_synthesize(z0e, z0o, ang_deg, h, t, er, ht, f, *[C.byref(x) for x in o]))
     return tuple(x.value for x in o)
 
 

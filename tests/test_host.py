@@ -259,6 +259,29 @@ def test_cpl_analyze_reproduces_trc_files_and_oracle(Q, R, golden_nets):
         Q.cpl_analyze(1.7e-3, 1e-3, 0.762e-3, 35e-6, 1.0, 0.2, 2.4e9, 20e-3)
 
 
+def test_cpl_synthesize_recovers_trc_geometry(Q, golden_nets):
+    """Row N1, the other button of QucsTranscalc: electrical -> physical.  From the Z0e / Z0o / Ang_l lines of the four
+    util/directional-couplers/*.trc:18-20 the synthesis recovers the W / S / L lines :15-17 to the files' print precision
+    (the impedances are printed to 6 digits: S moves in its 6th digit), and analysis(synthesis(x)) == x to 1e-9."""
+    n = 0
+    for key, t in golden_nets.items():
+        if not key.endswith(".trc"):
+            continue
+        n += 1
+        w, s, l = Q.cpl_synthesize(t["z0e"], t["z0o"], t["ang"], t["h"], t["t"], t["er"], t["ht"], t["f0"])
+        assert abs(w / t["w"] - 1) < 2e-5 and abs(s / t["s"] - 1) < 2e-5 and abs(l / t["l"] - 1) < 2e-5, key
+        ze, zo, ae, ao = Q.cpl_analyze(w, s, t["h"], t["t"], t["er"], t["ht"], t["f0"], l)
+        assert abs(ze / t["z0e"] - 1) < 1e-9 and abs(zo / t["z0o"] - 1) < 1e-9 and abs(np.sqrt(ae * ao) / t["ang"] - 1) < 1e-9
+    assert n == 4
+    # a 10 dB coupler on 0.762 mm RO4350-like substrate needs a gap the model still covers; a 3 dB one does not exist in microstrip
+    w, s, l = Q.cpl_synthesize(69.37, 36.04, 90.0, 0.762e-3, 35e-6, 3.5, 0.2, 2.4e9)
+    assert 0 < s < w and 15e-3 < l < 25e-3
+    with pytest.raises(Q.QoError):
+        Q.cpl_synthesize(120.7, 20.7, 90.0, 0.762e-3, 35e-6, 3.5, 0.2, 2.4e9)
+    with pytest.raises(Q.QoError):
+        Q.cpl_synthesize(45.0, 55.0, 90.0, 0.762e-3, 35e-6, 3.5, 0.2, 2.4e9)      # Z0e must exceed Z0o
+
+
 def test_qucs_dataset_round_trip(Q, golden_dat, tmp_path):
     """Row N2: Qucs dataset writer/reader.  A dataset built from the golden arrays is written in the layout of
     util/pa-lpf-simulation/pa-lpf-simulation.dat and read back bit-exactly; with the reference tree mounted,

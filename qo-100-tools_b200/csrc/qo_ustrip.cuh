@@ -42,6 +42,11 @@ __device__ __forceinline__ void m2_shunt(M2 &m, cd y) { m.a = cadd(m.a, cmul(m.b
 #define QO_MU0 12.566370614e-7
 #define QO_ZF0 376.73031346958504364963
 
+/* x^y for x > 0 as exp(y log x): the models call it ~80 times per (sample, frequency) point and CUDA's pow() is ~2.5x the
+ * cost of log + exp; every base here is a positive ratio of geometry / permittivity / frequency terms.  Measured effect on the
+ * parity anchors: none at their resolution (S21 vs the reference dataset 3.4e-12, vs the oracle 6.9e-13, counters equal) */
+#define MS_POW(x, y) exp((y) * log(x))
+
 struct MsSub { double er, h, t, tand, rho, D; };
 
 /* Hammerstad-Jensen quasi-static line (Qucs "Hammerstad"), SURVEY A.1 */
@@ -60,13 +65,13 @@ __device__ __noinline__ void ms_quasi(double W, const MsSub &s, double &Z, doubl
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         const double x = uu[i];
-        const double F = 6.0 + (2.0 * QO_PI - 6.0) * exp(-pow(30.666 / x, 0.7528));
+        const double F = 6.0 + (2.0 * QO_PI - 6.0) * exp(-MS_POW(30.666 / x, 0.7528));
         zh[i] = QO_ZF0 / (2.0 * QO_PI) * log(F / x + sqrt(1.0 + 4.0 / (x * x)));
     }
     const double x = uu[0], x2 = x * x, x4 = x2 * x2;
     const double a = 1.0 + log((x4 + x2 / 2704.0) / (x4 + 0.432)) / 49.0 + log(1.0 + (x / 18.1) * (x / 18.1) * (x / 18.1)) / 18.7;
-    const double b = 0.564 * pow((s.er - 0.9) / (s.er + 3.0), 0.053);
-    const double eps = 0.5 * (s.er + 1.0) + 0.5 * (s.er - 1.0) * pow(1.0 + 10.0 / x, -a * b);
+    const double b = 0.564 * MS_POW((s.er - 0.9) / (s.er + 3.0), 0.053);
+    const double eps = 0.5 * (s.er + 1.0) + 0.5 * (s.er - 1.0) * MS_POW(1.0 + 10.0 / x, -a * b);
     const double ratio = zh[1] / zh[0];
     Z = zh[0] / sqrt(eps);
     E = eps * ratio * ratio;
@@ -77,32 +82,32 @@ __device__ __noinline__ void ms_quasi(double W, const MsSub &s, double &Z, doubl
 __device__ __noinline__ void ms_disp(double W, const MsSub &s, double Z, double E, double f, double &Zf, double &Ef)
 {
     const double er = s.er, u = W / s.h, fn = f * s.h * 1e-6;
-    const double P1 = 0.27488 + (0.6315 + 0.525 / pow(1.0 + 0.0157 * fn, 20.0)) * u - 0.065683 * exp(-8.7513 * u);
+    const double P1 = 0.27488 + (0.6315 + 0.525 / MS_POW(1.0 + 0.0157 * fn, 20.0)) * u - 0.065683 * exp(-8.7513 * u);
     const double P2 = 0.33622 * (1.0 - exp(-0.03442 * er));
-    const double P3 = 0.0363 * exp(-4.6 * u) * (1.0 - exp(-pow(fn / 38.7, 4.97)));
-    const double P4 = 1.0 + 2.751 * (1.0 - exp(-pow(er / 15.916, 8.0)));
-    const double Pf = P1 * P2 * pow((P3 * P4 + 0.1844) * fn, 1.5763);
+    const double P3 = 0.0363 * exp(-4.6 * u) * (1.0 - exp(-MS_POW(fn / 38.7, 4.97)));
+    const double P4 = 1.0 + 2.751 * (1.0 - exp(-MS_POW(er / 15.916, 8.0)));
+    const double Pf = P1 * P2 * MS_POW((P3 * P4 + 0.1844) * fn, 1.5763);
     Ef = er - (er - E) / (1.0 + Pf);
-    const double R1 = 0.03891 * pow(er, 1.4);
-    const double R2 = 0.267 * pow(u, 7.0);
-    const double R3 = 4.766 * exp(-3.228 * pow(u, 0.641));
-    const double R4 = 0.016 + pow(0.0514 * er, 4.524);
-    const double R5 = pow(fn / 28.843, 12.0);
-    const double R6 = 22.20 * pow(u, 1.92);
+    const double R1 = 0.03891 * MS_POW(er, 1.4);
+    const double R2 = 0.267 * MS_POW(u, 7.0);
+    const double R3 = 4.766 * exp(-3.228 * MS_POW(u, 0.641));
+    const double R4 = 0.016 + MS_POW(0.0514 * er, 4.524);
+    const double R5 = MS_POW(fn / 28.843, 12.0);
+    const double R6 = 22.20 * MS_POW(u, 1.92);
     const double R7 = 1.206 - 0.3144 * exp(-R1) * (1.0 - exp(-R2));
-    const double R8 = 1.0 + 1.275 * (1.0 - exp(-0.004625 * R3 * pow(er, 1.674) * pow(fn / 18.365, 2.745)));
-    const double e6 = pow(er - 1.0, 6.0);
+    const double R8 = 1.0 + 1.275 * (1.0 - exp(-0.004625 * R3 * MS_POW(er, 1.674) * MS_POW(fn / 18.365, 2.745)));
+    const double e6 = MS_POW(er - 1.0, 6.0);
     const double R9 = 5.086 * R4 * R5 / (0.3838 + 0.386 * R4) * exp(-R6) / (1.0 + 1.2992 * R5) * e6 / (1.0 + 10.0 * e6);
-    const double R10 = 0.00044 * pow(er, 2.136) + 0.0184;
-    const double t6 = pow(fn / 19.47, 6.0);
+    const double R10 = 0.00044 * MS_POW(er, 2.136) + 0.0184;
+    const double t6 = MS_POW(fn / 19.47, 6.0);
     const double R11 = t6 / (1.0 + 0.0962 * t6);
     const double R12 = 1.0 / (1.0 + 0.00245 * u * u);
-    const double R13 = 0.9408 * pow(Ef, R8) - 0.9603;
-    const double R14 = (0.9408 - R9) * pow(E, R8) - 0.9603;
-    const double R15 = 0.707 * R10 * pow(fn / 12.3, 1.097);
-    const double R16 = 1.0 + 0.0503 * er * er * R11 * (1.0 - exp(-pow(u / 15.0, 6.0)));
-    const double R17 = R7 * (1.0 - 1.1241 * R12 / R16 * exp(-0.026 * pow(fn, 1.15656) - R15));
-    Zf = Z * pow(R13 / R14, R17);
+    const double R13 = 0.9408 * MS_POW(Ef, R8) - 0.9603;
+    const double R14 = (0.9408 - R9) * MS_POW(E, R8) - 0.9603;
+    const double R15 = 0.707 * R10 * MS_POW(fn / 12.3, 1.097);
+    const double R16 = 1.0 + 0.0503 * er * er * R11 * (1.0 - exp(-MS_POW(u / 15.0, 6.0)));
+    const double R17 = R7 * (1.0 - 1.1241 * R12 / R16 * exp(-0.026 * MS_POW(fn, 1.15656) - R15));
+    Zf = Z * MS_POW(R13 / R14, R17);
 }
 
 /* per-thread cache of the line model, keyed by (perturbed) strip width */
@@ -124,7 +129,7 @@ __device__ __forceinline__ const MsLine &ms_line(MsCache &c, double W, const MsS
     /* Hammerstad loss with the STATIC Z and E */
     const double Rs = sqrt(QO_PI * f * QO_MU0 * s.rho);
     const double dd = s.D * Rs / s.rho;                 /* D / skin depth */
-    const double Ki = exp(-1.2 * pow(l.Z / QO_ZF0, 0.7));
+    const double Ki = exp(-1.2 * MS_POW(l.Z / QO_ZF0, 0.7));
     const double Kr = 1.0 + (2.0 / QO_PI) * atan(1.4 * dd * dd);
     const double ac = Rs / (l.Z * W) * Ki * Kr;
     const double ad = QO_PI * s.er / (s.er - 1.0) * (l.E - 1.0) / sqrt(l.E) * s.tand * f / QO_C0;
@@ -154,7 +159,7 @@ __device__ __forceinline__ M2 ms_mcorn(double W, const MsSub &s, double f)
 {
     const double wh = W / s.h;
     const double CpF = W * ((10.35 * s.er + 2.5) * wh + 2.6 * s.er + 5.64);
-    const double LnH = 220.0 * s.h * (1.0 - 1.35 * exp(-0.18 * pow(wh, 1.39)));
+    const double LnH = 220.0 * s.h * (1.0 - 1.35 * exp(-0.18 * MS_POW(wh, 1.39)));
     const double x21 = -0.5e12 / (QO_PI * f * CpF);          /* z21 = j x21 */
     const double x11 = 2e-9 * QO_PI * f * LnH + x21;          /* z11 = j x11 */
     M2 m;
@@ -174,11 +179,11 @@ __device__ __forceinline__ double ms_mopen(MsCache &c, double W, const MsSub &s,
     double Zf, Ef;
     ms_disp(Weff, s, Z, E, f, Zf, Ef);
     const double w = W / s.h, er = s.er;
-    const double Q6 = pow(Ef, 0.81), Q7 = pow(w, 0.8544);
+    const double Q6 = MS_POW(Ef, 0.81), Q7 = MS_POW(w, 0.8544);
     const double Q1 = 0.434907 * (Q6 + 0.26) / (Q6 - 0.189) * (Q7 + 0.236) / (Q7 + 0.87);
-    const double Q2 = pow(w, 0.371) / (2.358 * er + 1.0) + 1.0;
-    const double Q3 = atan(0.084 * pow(w, 1.9413 / Q2)) * 0.5274 / pow(Ef, 0.9236) + 1.0;
-    const double Q4 = 0.0377 * (6.0 - 5.0 * exp(0.036 * (1.0 - er))) * atan(0.067 * pow(w, 1.456)) + 1.0;
+    const double Q2 = MS_POW(w, 0.371) / (2.358 * er + 1.0) + 1.0;
+    const double Q3 = atan(0.084 * MS_POW(w, 1.9413 / Q2)) * 0.5274 / MS_POW(Ef, 0.9236) + 1.0;
+    const double Q4 = 0.0377 * (6.0 - 5.0 * exp(0.036 * (1.0 - er))) * atan(0.067 * MS_POW(w, 1.456)) + 1.0;
     const double Q5 = 1.0 - 0.218 * exp(-7.5 * w);
     const double dl = Q1 * Q3 * Q5 / Q4 * s.h;
     return 2.0 * QO_PI * f * dl * sqrt(Ef) / (QO_C0 * Zf);

@@ -1080,8 +1080,17 @@ extern "C" int qo_sweep(qo_ctx *ctx, const qo_net *net, const double *f, int nf,
         cudaError_t e = cudaStreamSynchronize(dc->stream);
         if (e != cudaSuccess) { qo_set_error("sweep kernel failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; break; }
         qo_c64 *outs[4] = { s11, s21, s12, s22 };
-        for (int pl = 0; pl < 4; pl++)
-            if (outs[pl]) cudaMemcpy(outs[pl], buf + (size_t)pl * nft, (size_t)nf * sizeof(double2), cudaMemcpyDeviceToHost);
+        if (nft == nf && (size_t)nf * 4 * sizeof(double2) <= (1u << 20)) {
+            /* one device -> host copy for all four planes (each cudaMemcpy to pageable memory costs ~10 us of latency,
+             * which is what a 1024-point nominal sweep is made of), then scatter on the host */
+            std::vector<double2> stage(4 * (size_t)nf);
+            cudaMemcpy(stage.data(), buf, 4 * (size_t)nf * sizeof(double2), cudaMemcpyDeviceToHost);
+            for (int pl = 0; pl < 4; pl++)
+                if (outs[pl]) memcpy(outs[pl], stage.data() + (size_t)pl * nf, (size_t)nf * sizeof(double2));
+        } else {
+            for (int pl = 0; pl < 4; pl++)
+                if (outs[pl]) cudaMemcpy(outs[pl], buf + (size_t)pl * nft, (size_t)nf * sizeof(double2), cudaMemcpyDeviceToHost);
+        }
         if (gd) cudaMemcpy(gd, dgd, (size_t)nf * sizeof(double), cudaMemcpyDeviceToHost);
         e = cudaGetLastError();
         if (e != cudaSuccess) { qo_set_error("sweep copy failed: %s", cudaGetErrorString(e)); rc = QO_ERR_CUDA; }

@@ -182,6 +182,8 @@ static std::mutex tf_cache_mu;
 extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
                                 const unsigned char *mask, TfPlan *out)
 {
+    /* the cheap refusals first: nominal sweeps and FULL_S jobs come through here too and must not pay for the hash */
+    if (generic || !mode_reduce_only || precision != 64) return tf_plan_check_uncached(hp, mode_reduce_only, precision, generic, f, nf, mask, out);
     unsigned long long key = 1469598103934665603ull;
     {
         /* what the analysis does not read must not split the cache: seed, distribution, histogram set-up, thresholds */

@@ -371,6 +371,16 @@ def main():
                 torch.cuda.synchronize()
             ms = a.elapsed_time(b) / 5
             gbs = 32768 * NF * 64 / (ms * 1e-3) * 1e-9
+            # what a pure write stream reaches on this GPU, same buffer (the copy figure of MEASURED_PEAKS.json is half reads)
+            with torch.cuda.stream(stream):
+                buf.zero_()
+                torch.cuda.synchronize()
+                a.record(stream)
+                for _ in range(3):
+                    buf.zero_()
+                b.record(stream)
+                torch.cuda.synchronize()
+            fill_gbs = buf.numel() * 8 / (a.elapsed_time(b) / 3 * 1e-3) * 1e-9
             hbm = None
             try:
                 hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -379,7 +389,8 @@ def main():
             line["roofline_hbm"] = {"bound": "hbm", "workload": w4.name + " (32768 samples, 8.6 GB written, > L2)",
                                     "achieved": gbs, "peak": hbm or 6650.0, "unit": "GB/s", "frac": gbs / (hbm or 6650.0),
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm else "fallback 6.65 TB/s",
-                                    "evals_per_s": 32768 * NF / (ms * 1e-3), "traffic": None}
+                                    "evals_per_s": 32768 * NF / (ms * 1e-3), "traffic": None,
+                                    "write_only_fill_gbs": fill_gbs, "frac_of_write_only_fill": gbs / fill_gbs}
             p4.close()
             del buf
         except Exception as ex:          # the secondary leg must never take the headline line down

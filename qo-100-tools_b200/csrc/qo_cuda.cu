@@ -22,6 +22,7 @@
 #include "qo_tf.cuh"
 #include "qo_tf_launch.h"
 #include "qo_spot.cuh"
+#include "qo_tf_fs.cuh"
 #include "qo_ustrip.cuh"
 #include "qo_cpl_core.h"
 
@@ -50,6 +51,8 @@ struct DevPlan {
     double2 *tf_yt, *tf_xt, *tf_wt, *tf_ctab[4];
     uint4 *tf_mb;
     uchar2 *tf_itm;
+    void *fs_blob;             /* FULL_S flavour of the transfer-function kernel: y and x tables, padded */
+    double2 *fs_yt, *fs_xt;
     double2 *sblk, *sdet;      /* OP_SBLOCK: ABCD per (block, grid point); product of block determinants per point */
     void *cpl_tab[4];          /* double2 [npairs] each: sin/cos of the nominal even/odd coupler angle (ladder kernel) */
     uchar2 *m2;
@@ -71,6 +74,9 @@ struct qo_plan {
     int tf;                                               /* transfer-function kernel (qo_tf.cuh) selected */
     TfPlan tfp;                                           /* its polynomial lengths, denominator form, self-check result */
     int tf_pp, tf_niter;                                  /* pairs per thread per iteration; iterations per sample */
+    int fs_state;                                         /* FULL_S transfer-function path: 0 not analysed yet, 1 selected, -1 refused */
+    TfPlan fsp;
+    int fs_niter;
     unsigned long long h2d_bytes;                         /* host->device bytes copied by qo_plan_create, per GPU */
     const char *kernel_name;
     double flops_per_eval;
@@ -395,7 +401,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         DevPlan *d = &p->d[g];
         /* stream-ordered frees: back into the device's pool without a device-wide synchronisation */
         cudaStream_t st = p->ctx->d[g].stream;
-        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->tf_blob, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
+        void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->tf_blob, d->fs_blob, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
                          d->fgrid, d->mask, d->counters, d->ticket, d->sblk, d->sdet };
         for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
     }
@@ -418,6 +424,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     p->mode = cfg ? cfg->mode : QO_MODE_FULL_S;
     p->launches = 0;
     p->h2d_bytes = 0;
+    p->fs_state = 0;
     memset(p->d, 0, sizeof p->d);
     int rc = build_prog(net, f, nf, spec, nspec, cfg, &p->hp, &p->generic, &p->flops_per_eval, &p->maskv);
     if (rc) { delete p; return rc; }
@@ -847,6 +854,52 @@ static int launch_spot(qo_plan *p, int g, unsigned long long off, unsigned long 
     return QO_OK;
 }
 
+/* FULL_S launches with enough samples to fill the GPU go through the transfer-function kernel's FULL_S flavour when the
+ * job allows it.  The analysis runs once, at the first such launch (nominal sweeps -- one sample -- never pay for it). */
+#define QO_FS_TF_MIN_SAMPLES 1024
+static int launch_tf_fs(qo_plan *p, int g, unsigned long long off, unsigned long long n, QoPlanes pl)
+{
+    DevCtx *dc = &p->ctx->d[g];
+    DevPlan *d = &p->d[g];
+    const DevProg *hp = &p->hp;
+    if (!d->fs_blob) {
+        const int ppi = 32 * 2;
+        p->fs_niter = (p->npairs + ppi - 1) / ppi;
+        const size_t npt = 2 * (size_t)p->fs_niter * ppi;
+        std::vector<double> tab(2 * npt);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (size_t k = 0; k < npt; k++) {
+            const double x = two_pi * p->f[k < (size_t)p->nf ? k : (size_t)p->nf - 1] / p->fsp.wref;
+            tab[k] = -(x * x); tab[npt + k] = x;
+        }
+        CU(cudaMallocAsync((void **)&d->fs_blob, 2 * npt * sizeof(double), dc->stream));
+        CU(cudaMemcpyAsync(d->fs_blob, tab.data(), 2 * npt * sizeof(double), cudaMemcpyHostToDevice, dc->stream));
+        CU(cudaStreamSynchronize(dc->stream));
+        d->fs_yt = (double2 *)d->fs_blob; d->fs_xt = (double2 *)((double *)d->fs_blob + npt);
+        if (!d->ticket) CU(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), dc->stream));
+    }
+    TfFsParams P;
+    memset(&P, 0, sizeof P);
+    P.prog = d->prog; P.yt = d->fs_yt; P.xt = d->fs_xt;
+    P.s11 = pl.s11; P.s21 = pl.s21; P.s12 = pl.s12; P.s22 = pl.s22;
+    P.planes_al32 = ((((size_t)pl.s11) | ((size_t)pl.s21) | ((size_t)pl.s12) | ((size_t)pl.s22)) & 31) == 0;
+    P.ticket = d->ticket;
+    CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
+    P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
+    P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.wref = p->fsp.wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
+    P.nf = p->nf; P.niter = p->fs_niter; P.kn = p->fsp.kn; P.kd = p->fsp.kd; P.n_var = hp->n_var; P.n_el = p->fsp.n_el; P.el0 = p->fsp.el0; P.dist = hp->dist;
+    int dmode = p->fsp.den == QO_TF_DEN_NONE ? 0 : p->fsp.den == QO_TF_DEN_D ? 1 : 2;
+    if (dmode == 2) {
+        for (int e = 0; e < p->fsp.n_el; e++) {
+            const int op = hp->opcode[p->fsp.el0 + e];
+            if (!(op == OP_SER_R || op == OP_SER_L || op == OP_SHUNT_C)) P.fac[P.nfac++] = (unsigned char)e;
+        }
+    }
+    int rc = qo_tf_fs_launch(dmode, dc->sm_count, &P, dc->stream);
+    if (rc) { qo_set_error("FULL_S transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
 static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, QoPlanes pl, int full_s)
 {
     DevCtx *dc = &p->ctx->d[g];
@@ -901,7 +954,10 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
         pl.s11 = base; pl.s21 = base + plane; pl.s12 = base + 2 * plane; pl.s22 = base + 3 * plane;
     }
     int rc;
-    if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
+    if (full_s && !p->generic && p->precision == 64 && n >= QO_FS_TF_MIN_SAMPLES && p->fs_state == 0)
+        p->fs_state = qo_tf_fs_plan_check(&p->hp, 1, p->precision, p->generic, p->f.data(), p->nf, &p->fsp) ? 1 : -1;
+    if (full_s && p->fs_state == 1 && n >= QO_FS_TF_MIN_SAMPLES) { rc = launch_tf_fs(p, g, off, n, pl); if (rc == QO_OK) p->kernel_name = "qo_fs_tf_kernel"; }
+    else if (p->generic) rc = launch_generic(p, g, off, n, cnt, pl, full_s);
     else if (p->spot) rc = launch_spot(p, g, off, n, cnt);
     else if (p->tf) rc = launch_tf(p, g, off, n, cnt, cplms);
     else if (p->ladder) rc = launch_ladder(p, g, off, n, cnt, cplms);

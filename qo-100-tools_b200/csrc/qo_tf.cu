@@ -11,6 +11,7 @@
 #include <string.h>
 #include "qo_tf.cuh"
 #include "qo_spot.cuh"
+#include "qo_tf_fs.cuh"
 #include "qo_tf_launch.h"
 
 /* launch shapes (tools/tf_sweep.py, profiles/r01h_*): plain ladders run 8 points per thread (coefficient loads and loop
@@ -433,6 +434,156 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     }
     out->err = worst;
     if (!accepted) QO_TF_NO("polynomial expansion is too ill-conditioned on this grid");
+    out->reason = "ok";
+    return 1;
+#undef QO_TF_NO
+}
+
+
+/* ---- FULL_S flavour (qo_tf_fs.cuh) --------------------------------------------------------------------------- */
+extern "C" int qo_tf_fs_launch(int dmode, int sm_count, const TfFsParams *P, cudaStream_t st)
+{
+    const int tpb = 128, minb = 4;
+    const unsigned long long warps = tpb / 32;
+    unsigned long long blocks = (P->nsamples + warps - 1) / warps;
+    const unsigned long long resident = (unsigned long long)sm_count * minb;
+    if (blocks > resident) blocks = resident;
+    if (blocks < 1) blocks = 1;
+    if (dmode == 2) qo_fs_tf_kernel<2, 2, 128, 4><<<(unsigned)blocks, tpb, 0, st>>>(*P);
+    else if (dmode == 1) qo_fs_tf_kernel<1, 2, 128, 4><<<(unsigned)blocks, tpb, 0, st>>>(*P);
+    else qo_fs_tf_kernel<0, 2, 128, 4><<<(unsigned)blocks, tpb, 0, st>>>(*P);
+    return (int)cudaGetLastError();
+}
+
+/* Can FULL_S launches of this job run on qo_fs_tf_kernel?  Lumped cascade, no coupler; polynomial lengths by the same
+ * tail rule; self-check of S11, S21, S22 (complex) against the per-element ABCD chain at the nominal network (every
+ * point) and both ends of the tolerance box (every 4th point). */
+extern "C" int qo_tf_fs_plan_check(const DevProg *hp, int mode_full_s, int precision, int generic, const double *f, int nf, TfPlan *out)
+{
+    memset(out, 0, sizeof *out);
+    out->cpl_op = -1;
+#define QO_TF_NO(msg) do { out->reason = msg; return 0; } while (0)
+    const char *force = getenv("QO100NET_KERNEL");
+    if (force && (strcmp(force, "interp") == 0 || strcmp(force, "ladder") == 0)) QO_TF_NO("QO100NET_KERNEL override");
+    if (generic || !mode_full_s || precision != 64) QO_TF_NO("not an FP64 FULL_S job on a lumped cascade");
+    const int e0 = hp->op0, nl = hp->n_ops - e0;
+    if (nl < 1 || nl > QO_TF_MAXEL || hp->n_var > QO_MAX_VAR) QO_TF_NO("element count");
+    int deg = 0, has_d = 0;
+    for (int e = 0; e < nl; e++) {
+        const int op = hp->opcode[e0 + e], dg = qo_tf_degree(op);
+        if (dg < 0) QO_TF_NO("non-lumped element");
+        deg += dg;
+        if (!(op == OP_SER_R || op == OP_SER_L || op == OP_SHUNT_C)) has_d = 1;
+    }
+    if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
+    const int Kfull = deg / 2 + 1;
+    out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = 6; out->den = has_d ? QO_TF_DEN_D : QO_TF_DEN_NONE;
+    const double two_pi = 6.283185307179586476925286766559;
+    double f_lo = f[0], f_hi = f[0];
+    for (int k = 1; k < nf; k++) { if (f[k] < f_lo) f_lo = f[k]; if (f[k] > f_hi) f_hi = f[k]; }
+    const double wr = two_pi * sqrt(f_lo * f_hi);
+    out->wref = wr;
+    const double rs = hp->rs, rl = hp->rl, zn = sqrt(rs * rl), zni = 1.0 / zn, k21 = hp->k21;
+    double trunc = 5e-13, tol = 1e-10;
+    if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
+    if (getenv("QO100NET_TF_TOL")) tol = atof(getenv("QO100NET_TF_TOL"));
+    std::vector<TfCorner> cs(3), c2(3);
+    for (int ci = 0; ci < 3; ci++) {
+        TfCorner &c = cs[ci];
+        for (int e = 0; e < nl; e++) {
+            double p[6];
+            for (int k = 0; k < 6; k++) {
+                p[k] = hp->nom[e0 + e][k];
+                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)(ci - 1), hp->tmode[e0 + e][k]);
+            }
+            c.ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, c.nd[e]);
+            const double sc = c.ser[e] ? zni : zn;
+            const double *nd = c.nd[e];
+            double *rec = c.rec[e];
+            rec[0] = nd[0] * sc; rec[1] = nd[1] * sc; rec[2] = nd[2] * sc; rec[3] = nd[3]; rec[4] = nd[4]; rec[5] = nd[5];
+            rec[6] = 1.0; rec[7] = 0.0; rec[8] = 0.0; rec[9] = c.ser[e] ? 1.0 : 0.0;
+        }
+        c2[ci] = c;
+        tf_expand_host(c.rec, nl, rl, zn, c.pp, c.qq, c.dd, c.ee);
+        tf_expand_host(c2[ci].rec, nl, -rl, zn, c2[ci].pp, c2[ci].qq, c2[ci].dd, c2[ci].ee);
+    }
+    /* kept lengths: terms that stay below `trunc` of |P| + zn |Q| (numerators) / |D| everywhere on the grid */
+    const int NC = 2 * Kfull;
+    int kn = 1, kdd = 1;
+    std::vector<double> xpw((size_t)NC + 1);
+    for (int k = 0; k < nf; k++) {
+        const double x = two_pi * f[k] / wr;
+        xpw[0] = 1.0; for (int i = 1; i <= NC; i++) xpw[i] = xpw[i - 1] * x;
+        for (int ci = 0; ci < 3; ci++) {
+            for (int which = 0; which < 2; which++) {
+                const TfCorner &c = which ? c2[ci] : cs[ci];
+                const double nref = trunc * (sqrt(std::norm(tf_horner_host(c.pp, Kfull, x))) + sqrt(std::norm(tf_horner_host(c.qq, Kfull, x))));
+                double acc = 0.0;
+                int K = Kfull;
+                while (K > kn) {
+                    acc += (fabs(c.pp[2 * K - 1]) + fabs(c.qq[2 * K - 1])) * xpw[2 * K - 1] + (fabs(c.pp[2 * K - 2]) + fabs(c.qq[2 * K - 2])) * xpw[2 * K - 2];
+                    if (acc > nref) break;
+                    K--;
+                }
+                if (K > kn) kn = K;
+            }
+            if (has_d) {
+                const TfCorner &c = cs[ci];
+                const double dref = trunc * sqrt(std::norm(tf_horner_host(c.dd, Kfull, x)));
+                double acc = 0.0;
+                int K = Kfull;
+                while (K > kdd) { acc += fabs(c.dd[2 * K - 1]) * xpw[2 * K - 1] + fabs(c.dd[2 * K - 2]) * xpw[2 * K - 2]; if (acc > dref) break; K--; }
+                if (K > kdd) kdd = K;
+            }
+        }
+    }
+    out->kn = kn; out->kd = has_d ? kdd : 0;
+    /* a branch that resonates inside the grid (trap / tank, Q > 5): D as the product of the branch denominators (qo_tf_fs.cuh) */
+    int factored = 0;
+    if (has_d) {
+        const double xlo = two_pi * f_lo / wr * 0.8, xhi = two_pi * f_hi / wr * 1.25;
+        for (int e = 0; e < nl; e++) {
+            const double *nd = cs[1].nd[e];
+            if (nd[3] > 0.0 && nd[5] > 0.0 && nd[4] * nd[4] < 0.04 * nd[3] * nd[5]) {
+                const double xr = sqrt(nd[3] / nd[5]);
+                if (xr > xlo && xr < xhi) factored = 1;
+            }
+        }
+        if (getenv("QO100NET_FS_POLY_D")) factored = 0;
+    }
+    if (factored) { out->den = QO_TF_DEN_E + 100; out->kd = 0; }          /* marker: factored D (launch_tf_fs reads it) */
+    /* self-check: S11, S21, S22 from the kept polynomials against the per-element ABCD chain */
+    double worst = 0.0;
+    for (int ci = 0; ci < 3; ci++) {
+        const TfCorner &c = cs[ci], &cb = c2[ci];
+        for (int k = 0; k < nf; k++) {
+            if (ci != 1 && (k & 3) && k > 0 && k + 1 < nf) continue;
+            const double x = two_pi * f[k] / wr, y = -x * x;
+            const cplx Pv = tf_horner_host(c.pp, kn, x), Qv = tf_horner_host(c.qq, kn, x) * zni;
+            const cplx P2 = tf_horner_host(cb.pp, kn, x), Q2 = tf_horner_host(cb.qq, kn, x) * zni;
+            cplx Dv = has_d ? tf_horner_host(c.dd, kdd, x) : cplx(1.0, 0.0);
+            if (factored) { Dv = cplx(1.0, 0.0); for (int e = 0; e < nl; e++) Dv *= cplx(c.nd[e][5] * y + c.nd[e][3], c.nd[e][4] * x); }
+            const cplx num = Pv + rs * Qv;
+            const cplx g21 = k21 * Dv / num, g11 = (Pv - rs * Qv) / num, g22 = (P2 + rs * Q2) / num;
+            cplx A(1, 0), B(0, 0), C(0, 0), Dd(1, 0);
+            for (int e = 0; e < nl; e++) {
+                const double *nd = c.nd[e];
+                const cplx N(nd[2] * y + nd[0], nd[1] * x), De(nd[5] * y + nd[3], nd[4] * x);
+                const cplx imm = N / De;
+                if (c.ser[e]) { B += A * imm; Dd += C * imm; } else { A += B * imm; C += Dd * imm; }
+            }
+            const cplx den = A * rl + B + rs * (C * rl + Dd);
+            const cplx r21 = k21 / den, r11 = (A * rl + B - rs * (C * rl + Dd)) / den, r22 = (-A * rl + B - rs * C * rl + rs * Dd) / den;
+            double rel = std::abs(g21 - r21) / std::abs(r21);
+            const double e11 = std::abs(g11 - r11) / fmax(std::abs(r11), 0.02), e22 = std::abs(g22 - r22) / fmax(std::abs(r22), 0.02);
+            if (e11 > rel) rel = e11;
+            if (e22 > rel) rel = e22;
+            if (!(rel == rel)) rel = 1e300;
+            if (rel > worst) worst = rel;
+        }
+    }
+    out->err = worst;
+    if (worst > tol) QO_TF_NO("polynomial expansion is too ill-conditioned on this grid");
     out->reason = "ok";
     return 1;
 #undef QO_TF_NO

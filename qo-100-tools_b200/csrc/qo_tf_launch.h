@@ -30,3 +30,8 @@ extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs);
 /* spot-frequency kernel (qo_spot.cuh): one thread per sample, <= 8 frequencies; returns 0 or the cudaError_t of the launch */
 struct SpotParams;
 extern "C" int qo_spot_launch(int need_s11, int sm_count, const SpotParams *P, cudaStream_t st);
+
+/* FULL_S flavour of the transfer-function kernel (qo_tf_fs.cuh) */
+struct TfFsParams;
+extern "C" int qo_tf_fs_plan_check(const DevProg *hp, int mode_full_s, int precision, int generic, const double *f, int nf, TfPlan *out);
+extern "C" int qo_tf_fs_launch(int dmode, int sm_count, const TfFsParams *P, cudaStream_t st);   /* dmode: 0 D == 1, 1 polynomial D, 2 factored D */

@@ -887,3 +887,54 @@ def test_tf_kernel_eight_specs(Q, R, W, ctx, monkeypatch):
         itp = ctx.mc_run(w.net, f, specs, 17, 900, w.tols, sample_offset=2, **hist)
         monkeypatch.delenv("QO100NET_KERNEL", raising=False)
         _assert_counts_equal(itp, got)
+
+
+def test_full_s_transfer_function_flavour(Q, R, W, ctx, monkeypatch):
+    """FULL_S launches of >= 1024 samples on lumped cascades run on qo_fs_tf_kernel (S11, S21 = S12, S22 from the Num, N11, N22, D
+    polynomials): planes within 1e-9 of the oracle and of the interpreter (forced), odd grid sizes and unequal terminations
+    included; smaller launches and nets with a line or a coupler stay on the interpreter."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    n = 1100
+    jobs = [(w.net, w.f, w.tols, w.seed) for w in W.cfg4(n, 640)] + [(W.cfg2().net, W.cfg2(0, 513).f, W.cfg2().tols, 7)]
+    fc = 50e6
+    jobs.append((_mixed_lumped_nets(Q, W)[-1][1], Q.grid_log(fc / 3, fc * 4, 301), Q.lc_tolerances(_mixed_lumped_nets(Q, W)[-1][1], 0.05, 0.05), 9))
+    for net, f, tols, seed in jobs:
+        rs, rl = net.terminations
+        plan = Q.Plan(ctx, net, f, [], seed=seed, tols=tols, mode=Q.MODE_FULL_S)
+        assert plan.kernel_name == "qo_mc_lumped_kernel"          # decided at the first large launch
+        plan.close()
+        g = ctx.mc_run(net, f, [], seed, n, tols, mode=Q.MODE_FULL_S)["s"]
+        o = R.mc_run(to_ref(R, net), rs, rl, f, [], R.mc_cfg(seed, n, tols), full_s=True, nthreads=8)["s"]
+
+        def close(a, b):
+            """_s_close with an absolute floor of -120 dB on S21 / S12.  Among 1100 x nf random (sample, frequency) points one
+            lands within 0.1 ppm of the transmission zero of an ideal tank / trap (|S21| ~ -170 dB); there 1 - w^2 L C cancels to
+            7 digits in EVERY formulation (oracle, interpreter, transfer function differ from each other by ~1e-9 relative), so a
+            purely relative bound would test rounding luck, not the kernel."""
+            for pl in (1, 2):
+                assert np.all(np.abs(a[pl] - b[pl]) <= TOL64 * np.maximum(np.abs(b[pl]), 1e-6))
+            for pl in (0, 3):
+                assert np.all(np.abs(a[pl] - b[pl]) <= TOL64 * np.maximum(np.abs(b[pl]), 0.02))
+
+        close(g, o)
+        monkeypatch.setenv("QO100NET_KERNEL", "interp")
+        i = ctx.mc_run(net, f, [], seed, n, tols, mode=Q.MODE_FULL_S)["s"]
+        monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        close(g, i)
+        assert np.max(np.abs(g[1] - i[1])) > 0                     # two different kernels produced them
+        assert np.array_equal(g[1], g[2])                          # reciprocal cascade: S12 == S21
+    # which kernel ran is visible on a resident plan after the launch
+    import torch
+    w = W.cfg4(2048, 256)[1]
+    plan = Q.Plan(ctx, w.net, w.f, [], seed=1, tols=w.tols, mode=Q.MODE_FULL_S)
+    buf = torch.empty((4, 2048, 256, 2), dtype=torch.float64, device="cuda")
+    plan.launch(0, 2048, None, buf.data_ptr())
+    torch.cuda.synchronize()
+    assert plan.kernel_name == "qo_fs_tf_kernel"
+    plan.close()
+    tl = Q.Net.from_elements([(Q.TLINE, [50.0, 90.0, 1e9])] + w.net.elements, 50.0, 50.0)
+    plan = Q.Plan(ctx, tl, w.f, [], seed=1, mode=Q.MODE_FULL_S)
+    plan.launch(0, 2048, None, buf.data_ptr())
+    torch.cuda.synchronize()
+    assert plan.kernel_name == "qo_mc_lumped_kernel"
+    plan.close()

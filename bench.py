@@ -390,7 +390,10 @@ def main():
                                     "achieved": gbs, "peak": hbm or 6650.0, "unit": "GB/s", "frac": gbs / (hbm or 6650.0),
                                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm else "fallback 6.65 TB/s",
                                     "evals_per_s": 32768 * NF / (ms * 1e-3), "traffic": None,
-                                    "write_only_fill_gbs": fill_gbs, "frac_of_write_only_fill": gbs / fill_gbs}
+                                    "write_only_fill_gbs": fill_gbs, "frac_of_write_only_fill": gbs / fill_gbs,
+                                    "kernel": p4.kernel_name,
+                                    "note": "peak is the COPY bandwidth of MEASURED_PEAKS.json (half reads, half writes); this mode only "
+                                            "writes, and a plain fill of the same buffer (write_only_fill_gbs, measured here) is the tighter roof"}
             p4.close()
             del buf
         except Exception as ex:          # the secondary leg must never take the headline line down

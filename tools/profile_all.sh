@@ -25,9 +25,6 @@ export QO100NET_KERNEL=ladder
 cap ladder_cfg2 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
 unset QO100NET_KERNEL
 cap fulls_tf 134217728 qo_fs_tf 2 python bench.py --steps 1 --warmup 3 --samples 20000
-export QO100NET_KERNEL=interp
-cap fulls_interp 134217728 lumped 2 python bench.py --steps 1 --warmup 3 --samples 20000
-unset QO100NET_KERNEL
 cap nodal 4000000 nodal 1 python tools/nodal_bench.py --samples 4000
 cap generic_cfg3 1200000 generic 2 python tools/cfg3_run.py
 fi

@@ -813,6 +813,14 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tfp.cpl_op;
     /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
     P.cpl_matched = p->tfp.cpl_op >= 0 && hp->tvar[p->tfp.cpl_op][5] < 0 && hp->nom[p->tfp.cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
+    /* uniformly spaced grid (config 5: linear 70 MHz .. 4 GHz): the coupler's mode angles advance by a constant per iteration */
+    P.cpl_lin = 0;
+    if (p->tfp.cpl_op >= 0 && p->nf >= 3 && !getenv("QO100NET_CPL_NO_ROT")) {
+        const double d0 = p->f[1] - p->f[0];
+        int lin = d0 > 0.0;
+        for (int k = 2; k < p->nf && lin; k++) if (fabs((p->f[k] - p->f[k - 1]) - d0) > 1e-9 * fabs(d0)) lin = 0;
+        if (lin) { P.cpl_lin = 1; P.cpl_dw = 6.283185307179586476925286766559 * ((p->f[p->nf - 1] - p->f[0]) / (double)(p->nf - 1)) * (double)(64 * p->tf_pp); }
+    }
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));

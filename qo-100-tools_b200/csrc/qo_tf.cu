@@ -33,7 +33,7 @@ extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs)
     return npairs <= 192 ? 1 : QO_TF_PP;
 }
 
-template <int NN, bool CPL, bool S11, int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_ns(int den)
+template <int NN, int CPL, bool S11, int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_ns(int den)
 {
     switch (den) {
     case QO_TF_DEN_NONE: return qo_mc_tf_kernel<NN, QO_TF_DEN_NONE, CPL, S11, false, NS, PP, TPB, MINB>;
@@ -42,15 +42,15 @@ template <int NN, bool CPL, bool S11, int NS, int PP, int TPB, int MINB> static 
     default: return nullptr;
     }
 }
-template <int NN, bool CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den, int nspec = 4)
+template <int NN, int CPL, bool S11, int PP, int TPB, int MINB> static tf_fn tf_pick(int den, int nspec = 4)
 {
     return nspec > 4 ? tf_pick_ns<NN, CPL, S11, 8, PP, TPB, MINB>(den) : tf_pick_ns<NN, CPL, S11, 4, PP, TPB, MINB>(den);
 }
 template <int NS, int PP, int TPB, int MINB> static tf_fn tf_pick_gd_ns(int den)
 {
     switch (den) {
-    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<4, QO_TF_DEN_NONE, false, false, true, NS, PP, TPB, MINB>;
-    case QO_TF_DEN_DD: return qo_mc_tf_kernel<4, QO_TF_DEN_DD, false, false, true, NS, PP, TPB, MINB>;
+    case QO_TF_DEN_NONE: return qo_mc_tf_kernel<4, QO_TF_DEN_NONE, 0, false, true, NS, PP, TPB, MINB>;
+    case QO_TF_DEN_DD: return qo_mc_tf_kernel<4, QO_TF_DEN_DD, 0, false, true, NS, PP, TPB, MINB>;
     default: return nullptr;
     }
 }
@@ -63,31 +63,35 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
 {
     tf_fn fn = nullptr;
     int tpb = QO_TF_TPB, minb = QO_TF_MINB;
+    const bool rot = P->cpl_lin && P->cpl_matched;      /* coupler on a uniformly spaced grid: angles by rotation */
     (void)variant;
 #ifdef QO_TF_EXPERIMENT
     /* development builds: other launch shapes, chosen with QO100NET_LAD_VARIANT (and QO100NET_TF_PP) */
     if (tp->nn == 2 && pp == 4) switch (variant) {
-        case 1: fn = tf_pick<2, false, false, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
-        case 2: fn = tf_pick<2, false, false, 4, 256, 2>(tp->den); tpb = 256; minb = 2; break;
-        case 3: fn = tf_pick<2, false, false, 4, 128, 5>(tp->den); tpb = 128; minb = 5; break;
+        case 1: fn = tf_pick<2, 0, false, 4, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 2: fn = tf_pick<2, 0, false, 4, 256, 2>(tp->den); tpb = 256; minb = 2; break;
+        case 3: fn = tf_pick<2, 0, false, 4, 128, 5>(tp->den); tpb = 128; minb = 5; break;
         default: break;
     }
     if (tp->cpl_op >= 0 && pp == 2) switch (variant) {
-        case 1: fn = tf_pick<4, true, false, 2, 128, 3>(tp->den); tpb = 128; minb = 3; break;
-        case 2: fn = tf_pick<4, true, false, 2, 256, 2>(tp->den); tpb = 256; minb = 2; break;
+        case 1: fn = tf_pick<4, 1, false, 2, 128, 3>(tp->den); tpb = 128; minb = 3; break;
+        case 2: fn = tf_pick<4, 1, false, 2, 256, 2>(tp->den); tpb = 256; minb = 2; break;
         default: break;
     }
     if (!fn)
 #endif
     {
-        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, false, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
-        else if (tp->nn == 2 && pp == 1) fn = tf_pick<2, false, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        if (tp->nn == 2 && pp == QO_TF_PP) fn = tf_pick<2, 0, false, QO_TF_PP, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 2 && pp == 1) fn = tf_pick<2, 0, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == 1) fn = tf_pick_gd<1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
-        else if (tp->nn == 4 && tp->s11 && pp == 1) fn = tf_pick<4, false, true, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
-        else if (tp->nn == 4 && !tp->s11 && pp == 1) fn = tf_pick<4, true, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && tp->s11 && pp == 1) fn = tf_pick<4, 0, true, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && !tp->s11 && pp == 1) fn = rot ? tf_pick<4, 2, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec) : tf_pick<4, 1, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
-        else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, false, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
-        else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, true, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && tp->s11 && pp == QO_TF_CPL_PP) { fn = tf_pick<4, 0, true, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && !tp->s11 && pp == QO_TF_CPL_PP) {
+            fn = rot ? tf_pick<4, 2, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec) : tf_pick<4, 1, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec);
+            tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB;
+        }
     }
     if (!fn) return -1;
     const unsigned long long warps = (unsigned long long)(tpb / 32);

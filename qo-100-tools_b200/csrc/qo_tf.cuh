@@ -59,6 +59,8 @@ struct TfParams {
     int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
+    int cpl_lin;                             /* uniformly spaced grid: the mode angles advance by a constant step per iteration ... */
+    double cpl_dw;                           /* ... of this much in w (one iteration = 64 PP points) */
     const double *cplms;
 };
 
@@ -91,15 +93,13 @@ __device__ __forceinline__ unsigned int tf_hi(double v) { return (unsigned int)_
  *     den = [ (Pi - Nu) P + Zt (Pi + Nu) Q ] / Sg
  * -- 22 FP64 instructions after the mode angles instead of the ~60 of the general S -> ABCD form.
  * Out: ua = Pi - Nu, ub = Pi + Nu (Zt is folded into Q's scale by the caller), sg2 = |Sg|^2. */
-template <int PTS, bool FAST>
-__device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
-                                               const double (&tso)[PTS], const double (&tco)[PTS], double (&uar)[PTS], double (&uai)[PTS],
-                                               double (&ubr)[PTS], double (&ubi)[PTS], double (&sg2)[PTS])
+template <int PTS>
+__device__ __forceinline__ void tf_cpl_matched_sc(unsigned int cf, const double (&se)[PTS], const double (&ce)[PTS], const double (&so)[PTS],
+                                                  const double (&co)[PTS], double (&uar)[PTS], double (&uai)[PTS],
+                                                  double (&ubr)[PTS], double (&ubi)[PTS], double (&sg2)[PTS])
 {
     const LadV2<double> c01 = lad_lds2(cf, 0.0), c23 = lad_lds2(cf + 16u, 0.0);
     const double cE = c01.x, hE = c01.y, cO = c23.x, hO = c23.y;
-    double se[PTS], ce[PTS], so[PTS], co[PTS];
-    lad_cpl_angles<double, PTS, FAST>(cf, w, tse, tce, tso, tco, se, ce, so, co);
     QO_PTS {
         const double a1 = ce[p] + ce[p], b1 = se[p] * cE, a2 = co[p] + co[p], b2 = so[p] * cO;           /* D_e, D_o */
         const double Pr = fma(a1, a2, -b1 * b2), Pi = fma(a1, b2, a2 * b1);                               /* Pi */
@@ -110,10 +110,20 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
         sg2[p] = fma(Sr, Sr, Si * Si);
     }
 }
+template <int PTS, bool FAST>
+__device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
+                                               const double (&tso)[PTS], const double (&tco)[PTS], double (&uar)[PTS], double (&uai)[PTS],
+                                               double (&ubr)[PTS], double (&ubi)[PTS], double (&sg2)[PTS])
+{
+    double se[PTS], ce[PTS], so[PTS], co[PTS];
+    lad_cpl_angles<double, PTS, FAST>(cf, w, tse, tce, tso, tco, se, ce, so, co);
+    tf_cpl_matched_sc<PTS>(cf, se, ce, so, co, uar, uai, ubr, ubi, sg2);
+}
 
 /*
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
- * CPL    coupled-line block in front (its row vector is contracted with [P; Q] per point)
+ * CPLM   0 no coupler; 1 coupled-line block in front (its row vector is contracted with [P; Q] per point), mode angles from
+ *        the nominal-angle tables / sincos; 2 the same with the angles carried by rotation from iteration to iteration
  * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
  * NS     spec slots: 4 or 8 (trackers of the sign kind are one 32-bit register each)
  * GD     the job has group-delay specs: tau = d arg(den)/dw = Re(Num'/Num - D'/D) / wref with the derivative polynomials
@@ -133,9 +143,11 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
  * computed by the plan picks a path without per-point selects; iterations that straddle a band edge load the
  * per-point byte masks and AND them into the sign word (PRMT + LOP3) or select on them (value tracker).
  */
-template <int NN, int DEN, bool CPL, bool S11, bool GD, int NS, int PP, int TPB, int MINB>
+template <int NN, int DEN, int CPLM, bool S11, bool GD, int NS, int PP, int TPB, int MINB>
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
+    constexpr bool CPL = CPLM != 0;            /* coupled-line block in front */
+    constexpr bool ROT = CPLM == 2;            /* ... with its mode angles advanced by rotation (uniformly spaced grid, matched source) */
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
     static_assert(NN == 2 || NN == 4, "two or four numerator chains");
@@ -236,6 +248,35 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         unsigned int acc[NS];              /* other specs: OR of the sign words of g */
 #pragma unroll
         for (int sp = 0; sp < NS; sp++) acc[sp] = 0u;
+        /* coupler on a uniformly spaced grid: sin / cos of the mode angles are carried from iteration to iteration by a
+         * rotation through the per-sample angle step k * dw (4 FP64 instructions per mode and point instead of 15, and no
+         * table loads); they start from the nominal-angle tables (or sincos) at the first iteration */
+        double rse[PTS], rce[PTS], rso[PTS], rco[PTS];
+        double stE_c = 1.0, stE_s = 0.0, stO_c = 1.0, stO_s = 0.0;
+        constexpr bool cpl_rot = ROT;
+        if constexpr (ROT) {
+            const LadV2<double> c45 = lad_lds2(cpls + 32u, 0.0);
+            sincos(c45.x * P.cpl_dw, &stE_s, &stE_c);
+            if (P.cpl_same) { stO_s = stE_s; stO_c = stE_c; } else sincos(c45.y * P.cpl_dw, &stO_s, &stO_c);
+            double w0[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];
+            QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
+#pragma unroll
+            for (int qq = 0; qq < PP; qq++) {
+                const int j = lane + 32 * qq;
+                const double2 a = P.wt[j];
+                w0[2 * qq] = a.x; w0[2 * qq + 1] = a.y;
+                if (P.cpl_fast) {
+                    const double2 se = P.cse[j], ce = P.cce[j];
+                    tse[2 * qq] = se.x; tse[2 * qq + 1] = se.y; tce[2 * qq] = ce.x; tce[2 * qq + 1] = ce.y;
+                    if (!P.cpl_same) {
+                        const double2 so = P.cso[j], co = P.cco[j];
+                        tso[2 * qq] = so.x; tso[2 * qq + 1] = so.y; tco[2 * qq] = co.x; tco[2 * qq + 1] = co.y;
+                    }
+                }
+            }
+            if (P.cpl_fast) lad_cpl_angles<double, PTS, true>(cpls, w0, tse, tce, tso, tco, rse, rce, rso, rco);
+            else lad_cpl_angles<double, PTS, false>(cpls, w0, tse, tce, tso, tco, rse, rce, rso, rco);
+        }
         for (int it = 0; it < P.niter; it++) {
             const int j0 = it * (32 * PP) + lane;
             double y[PTS];
@@ -332,6 +373,27 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 }
             } else if (!CPL) {
                 QO_PTS { const double t = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t, r[0][p] * r[0][p]); }
+            } else if (ROT) {
+                double x[PTS], uar[PTS], uai[PTS], ubr[PTS], ubi[PTS], kap[PTS];
+#pragma unroll
+                for (int qq = 0; qq < PP; qq++) { const double2 b = P.xt[j0 + 32 * qq]; x[2 * qq] = b.x; x[2 * qq + 1] = b.y; }
+                tf_cpl_matched_sc<PTS>(cpls, rse, rce, rso, rco, uar, uai, ubr, ubi, kap);
+                const double zq = P.rs * P.zni;
+                QO_PTS {
+                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                    const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
+                    const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
+                    n2[p] = fma(nr, nr, ni * ni);
+                    dd[p] *= kap[p];
+                    /* advance the mode angles to the next iteration's points */
+                    const double s1 = fma(rse[p], stE_c, rce[p] * stE_s), c1 = fma(rce[p], stE_c, -rse[p] * stE_s);
+                    rse[p] = s1; rce[p] = c1;
+                    if (P.cpl_same) { rso[p] = s1; rco[p] = c1; }
+                    else {
+                        const double s2 = fma(rso[p], stO_c, rco[p] * stO_s), c2 = fma(rco[p], stO_c, -rso[p] * stO_s);
+                        rso[p] = s2; rco[p] = c2;
+                    }
+                }
             } else {
                 double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];
                 QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }

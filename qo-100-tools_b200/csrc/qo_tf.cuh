@@ -110,6 +110,24 @@ __device__ __forceinline__ void tf_cpl_matched_sc(unsigned int cf, const double 
         sg2[p] = fma(Sr, Sr, Si * Si);
     }
 }
+/* The same for EQUAL mode angles (theta_e == theta_o for every sample, config 5): with c = cos, s = sin of the common angle
+ *   Pi = 4 c^2 - cE cO s^2 + j 2 (cE + cO) c s,   Nu = -(hE cO + hO cE) s^2 + j 2 (hE + hO) c s,   Sg = 4 c + j (cE + cO) s
+ * so ua = Pi - Nu, ub = Pi + Nu and |Sg|^2 are linear in (c^2, s^2, c s) with the five per-sample constants at record[10..14]:
+ * 10 FP64 instructions per point instead of 22. */
+template <int PTS>
+__device__ __forceinline__ void tf_cpl_matched_same(unsigned int cf, const double (&se)[PTS], const double (&ce)[PTS],
+                                                    double (&uar)[PTS], double (&uai)[PTS], double (&ubr)[PTS], double (&ubi)[PTS], double (&sg2)[PTS])
+{
+    const LadV2<double> k01 = lad_lds2(cf + 80u, 0.0), k23 = lad_lds2(cf + 96u, 0.0);
+    const double k4 = lad_lds1(cf + 112u, 0.0);
+    QO_PTS {
+        const double c2 = ce[p] * ce[p], s2 = se[p] * se[p], cs = ce[p] * se[p], c4 = 4.0 * c2;
+        uar[p] = fma(-k01.x, s2, c4); ubr[p] = fma(-k01.y, s2, c4);
+        uai[p] = k23.x * cs; ubi[p] = k23.y * cs;
+        sg2[p] = fma(k4, s2, 4.0 * c4);
+    }
+}
+
 template <int PTS, bool FAST>
 __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w)[PTS], const double (&tse)[PTS], const double (&tce)[PTS],
                                                const double (&tso)[PTS], const double (&tco)[PTS], double (&uar)[PTS], double (&uai)[PTS],
@@ -123,7 +141,8 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
 /*
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
  * CPLM   0 no coupler; 1 coupled-line block in front (its row vector is contracted with [P; Q] per point), mode angles from
- *        the nominal-angle tables / sincos; 2 the same with the angles carried by rotation from iteration to iteration
+ *        the nominal-angle tables / sincos; 2 the same with the angles carried by rotation from iteration to iteration;
+ *        3 = 2 with equal even- and odd-mode angles
  * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
  * NS     spec slots: 4 or 8 (trackers of the sign kind are one 32-bit register each)
  * GD     the job has group-delay specs: tau = d arg(den)/dw = Re(Num'/Num - D'/D) / wref with the derivative polynomials
@@ -147,7 +166,8 @@ template <int NN, int DEN, int CPLM, bool S11, bool GD, int NS, int PP, int TPB,
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr bool CPL = CPLM != 0;            /* coupled-line block in front */
-    constexpr bool ROT = CPLM == 2;            /* ... with its mode angles advanced by rotation (uniformly spaced grid, matched source) */
+    constexpr bool ROT = CPLM >= 2;            /* ... with its mode angles advanced by rotation (uniformly spaced grid, matched source) */
+    constexpr bool SAME = CPLM == 3;           /* ... and equal even / odd angles for every sample (one angle, tf_cpl_matched_same) */
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
     static_assert(NN == 2 || NN == 4, "two or four numerator chains");
@@ -158,7 +178,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     __shared__ __align__(16) double s_num[WARPS][(QO_TF_MAXK + 2) * NN];   /* two guard rows below row 0 (prefetch runs two steps ahead) */     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
     __shared__ __align__(16) double s_den[WARPS][DEN == QO_TF_DEN_NONE ? 2 : (DEN == QO_TF_DEN_DD ? 4 : 2) * QO_TF_MAXK + 4];   /* + guard */   /* E: e_0.. ; D: rows (d_2k, d_2k+1) */
     __shared__ __align__(16) double s_el[WARPS][QO_TF_MAXEL * QO_TF_REC];
-    __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 2 : 2];
+    __shared__ __align__(16) double s_cpl[WARPS][CPL ? QO_LAD_CPL + 8 : 2];     /* + the equal-angle constants of tf_cpl_matched_same */
     __shared__ double s_x[WARPS][QO_MAX_VAR];
     __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
 
@@ -188,6 +208,11 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
         if (CPL && lane == 31) {
             double nom_k[2];
             lad_derive<double>(P.prog, P.cpl_op, xw, s_cpl[warp], P.cplms ? P.cplms + 4 * s : NULL, nom_k);
+            /* equal mode angles: the block's row vector in c^2, s^2, c s with five per-sample constants (tf_cpl_matched_same) */
+            double *o = s_cpl[warp];
+            const double cE = o[0], hE = o[1], cO = o[2], hO = o[3];
+            const double k1 = cE * cO, k2 = cE + cO, k3 = fma(hE, cO, hO * cE), k4 = hE + hO;
+            o[10] = k1 - k3; o[11] = k1 + k3; o[12] = 2.0 * (k2 - k4); o[13] = 2.0 * (k2 + k4); o[14] = k2 * k2; o[15] = 0.0;
         }
         __syncwarp();
         /* 2. expand [P; Q] and D (or E) from the load end: lane i holds the coefficient of sn^i (of y^i for E); lanes 30, 31
@@ -377,7 +402,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 double x[PTS], uar[PTS], uai[PTS], ubr[PTS], ubi[PTS], kap[PTS];
 #pragma unroll
                 for (int qq = 0; qq < PP; qq++) { const double2 b = P.xt[j0 + 32 * qq]; x[2 * qq] = b.x; x[2 * qq + 1] = b.y; }
-                tf_cpl_matched_sc<PTS>(cpls, rse, rce, rso, rco, uar, uai, ubr, ubi, kap);
+                if (SAME) tf_cpl_matched_same<PTS>(cpls, rse, rce, uar, uai, ubr, ubi, kap);
+                else tf_cpl_matched_sc<PTS>(cpls, rse, rce, rso, rco, uar, uai, ubr, ubi, kap);
                 const double zq = P.rs * P.zni;
                 QO_PTS {
                     const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
@@ -388,7 +414,8 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     /* advance the mode angles to the next iteration's points */
                     const double s1 = fma(rse[p], stE_c, rce[p] * stE_s), c1 = fma(rce[p], stE_c, -rse[p] * stE_s);
                     rse[p] = s1; rce[p] = c1;
-                    if (P.cpl_same) { rso[p] = s1; rco[p] = c1; }
+                    if (SAME) { }
+                    else if (P.cpl_same) { rso[p] = s1; rco[p] = c1; }
                     else {
                         const double s2 = fma(rso[p], stO_c, rco[p] * stO_s), c2 = fma(rco[p], stO_c, -rso[p] * stO_s);
                         rso[p] = s2; rco[p] = c2;

@@ -187,6 +187,15 @@ double ref_perturb_factor(uint64_t seed, uint64_t sample, uint32_t var, int dist
     return fma(tol, ref_variate(seed, sample, var, dist), 1.0);
 }
 
+/* out[n_samples][n_var] = ref_perturb_factor(seed, sample_offset + s, v, dist, tol): the whole stream in one call
+ * (the GPU bit-exactness test compares 1e6 factors; SURVEY App. C "test = memcmp of 1e6 factors") */
+void ref_perturb_factors(uint64_t seed, uint64_t sample_offset, uint64_t n_samples, int n_var, int dist, double tol, double *out)
+{
+    for (uint64_t s = 0; s < n_samples; s++)
+        for (int v = 0; v < n_var; v++)
+            out[s * (uint64_t)n_var + (uint64_t)v] = ref_perturb_factor(seed, sample_offset + s, (uint32_t)v, dist, tol);
+}
+
 void ref_perturb(const ref_elem *e, int n, const ref_mc_cfg *cfg, uint64_t sample, ref_elem *out)
 {
     memcpy(out, e, (size_t)n * sizeof(ref_elem));

@@ -77,6 +77,7 @@ void   ref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t 
 double ref_uniform01(uint64_t seed, uint64_t sample, uint32_t var);
 double ref_variate(uint64_t seed, uint64_t sample, uint32_t var, int dist);  /* in [-1,1] */
 double ref_perturb_factor(uint64_t seed, uint64_t sample, uint32_t var, int dist, double tol);
+void ref_perturb_factors(uint64_t seed, uint64_t sample_offset, uint64_t n_samples, int n_var, int dist, double tol, double *out);
 double ref_norminv(double p);
 double ref_log_det(double x);
 

@@ -56,7 +56,7 @@ def build(force=False):
     """Compile the oracle with the committed Makefile (building the checker is not using it)."""
     if force or not os.path.exists(_LIB) or any(
             os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB)
-            for s in ("qo100ref.c", "qo100ref.h", "Makefile")):
+            for s in ("qo100ref.c", "qo100ref_nodal.c", "qo100ref.h", "Makefile")):
         env = dict(os.environ)
         env.pop("CC", None)
         subprocess.run(["make", "-C", _HERE], check=True, capture_output=True, env=env)
@@ -79,6 +79,8 @@ def lib():
         L.ref_variate.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]
         L.ref_perturb_factor.restype = C.c_double
         L.ref_perturb_factor.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_int, C.c_double]
+        L.ref_perturb_factors.restype = None
+        L.ref_perturb_factors.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_double, dp]
         L.ref_norminv.restype = C.c_double
         L.ref_norminv.argtypes = [C.c_double]
         L.ref_log_det.restype = C.c_double
@@ -272,6 +274,13 @@ def mc_cfg(seed, n_samples, tols, sample_offset=0, dist=DIST_UNIFORM, hist_bins=
     cfg.dist, cfg.n_tol, cfg.tol = dist, len(tols), cfg._tols
     cfg.hist_bins, cfg.hist_spec, cfg.hist_lo, cfg.hist_hi = hist_bins, hist_spec, hist_lo, hist_hi
     return cfg
+
+
+def perturb_factors(seed, sample_offset, n_samples, n_var, dist, tol):
+    """The oracle's perturbation stream, [n_samples, n_var] factors 1 + tol * x."""
+    out = np.empty((n_samples, n_var))
+    lib().ref_perturb_factors(seed, sample_offset, n_samples, n_var, dist, tol, _dp(out))
+    return out
 
 
 def perturb(elems, cfg, sample):

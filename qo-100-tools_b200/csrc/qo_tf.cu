@@ -173,6 +173,36 @@ struct TfCorner {
 static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int precision, int generic, const double *f, int nf,
                                   const unsigned char *mask, TfPlan *out);
 
+/* Where in the tolerance box the analysis looks (x[v] in [-1, 1] per random variable):
+ *   0 every variable at -1, 1 the nominal network, 2 every variable at +1,
+ *   3 every variable at the end that RAISES the parameters it drives (lowest self-resonances: L, C up whatever the sign of
+ *     the tolerance entry), 4 its mirror image,
+ *   5 .. 5+QO_TF_NVERT-1  pseudo-random vertices (each variable +-1: mixed corners such as L up / C down),
+ *   then QO_TF_NINT pseudo-random interior points.
+ * The choice is a fixed Philox stream, so the analysis is deterministic and cacheable. */
+#define QO_TF_NVERT 20
+#define QO_TF_NINT 8
+#define QO_TF_NCORNER (5 + QO_TF_NVERT + QO_TF_NINT)
+#define QO_TF_NOMINAL 1
+static void tf_corner_vars(const DevProg *hp, int e0, int nl, int ci, double *x)
+{
+    const unsigned long long key = 0x51ed270b7f4a7c15ull;
+    for (int v = 0; v < QO_MAX_VAR; v++) {
+        if (ci == 0) x[v] = -1.0;
+        else if (ci == 1) x[v] = 0.0;
+        else if (ci == 2) x[v] = 1.0;
+        else if (ci < 5) x[v] = 0.0;                                  /* filled below */
+        else if (ci < 5 + QO_TF_NVERT) x[v] = qo_stream_variate(key, (unsigned long long)ci, (uint32_t)v, 0 /* uniform */) < 0.0 ? -1.0 : 1.0;
+        else x[v] = qo_stream_variate(key, (unsigned long long)ci, (uint32_t)v, 0 /* uniform */);
+    }
+    if (ci == 3 || ci == 4)
+        for (int e = nl - 1; e >= 0; e--)
+            for (int k = 5; k >= 0; k--) {                           /* p[0] (the L or C value) decides last */
+                const int v = hp->tvar[e0 + e][k];
+                if (v >= 0 && hp->ttol[e0 + e][k] != 0.0) x[v] = ((hp->ttol[e0 + e][k] > 0.0) == (ci == 3)) ? 1.0 : -1.0;
+            }
+}
+
 /* The analysis is a pure function of (program, grid, masks, environment overrides); callers that run the same job
  * repeatedly through qo_mc_run (one plan per call) would redo ~2 ms of host work per call, so the last few results
  * are kept, keyed by a 64-bit FNV-1a hash of those inputs. */
@@ -267,16 +297,18 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     out->wref = wr;
     const double zn = sqrt(hp->rs * hp->rl), zni = 1.0 / zn;
 
-    /* expansions of the nominal network and of both all-at-one-end corners of the tolerance box */
-    std::vector<TfCorner> cs(3);
-    for (int ci = 0; ci < 3; ci++) {
+    /* expansions of the nominal network and of QO_TF_NCORNER - 1 other points of the tolerance box (tf_corner_vars) */
+    const int NCORN = hp->n_var > 0 ? QO_TF_NCORNER : 2;          /* no tolerances: every "corner" is the nominal network */
+    std::vector<TfCorner> cs((size_t)NCORN);
+    for (int ci = 0; ci < NCORN; ci++) {
         TfCorner &c = cs[ci];
-        const double corner = (double)(ci - 1);
+        double xv[QO_MAX_VAR];
+        tf_corner_vars(hp, e0, nl, ci, xv);
         for (int e = 0; e < nl; e++) {
             double p[6];
             for (int k = 0; k < 6; k++) {
                 p[k] = hp->nom[e0 + e][k];
-                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], corner, hp->tmode[e0 + e][k]);
+                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], xv[hp->tvar[e0 + e][k]], hp->tmode[e0 + e][k]);
             }
             c.ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, c.nd[e]);
             const double sc = c.ser[e] ? zni : zn;
@@ -303,19 +335,21 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     std::vector<double> xg((size_t)nf), xpw((size_t)NC + 1), zpw((size_t)NE + 1);
     for (int k = 0; k < nf; k++) xg[k] = two_pi * f[k] / wr;
     /* |coefficient| tables of the three expansions (numerator entry: what the device's Num / [P; Q] pair carries) */
-    std::vector<double> an((size_t)3 * NC), ad((size_t)3 * NC), ae((size_t)3 * NE);
-    for (int ci = 0; ci < 3; ci++)
+    std::vector<double> an((size_t)NCORN * NC), ad((size_t)NCORN * NC), ae((size_t)NCORN * NE);
+    for (int ci = 0; ci < NCORN; ci++)
         for (int i = 0; i < NC; i++) {
             an[(size_t)ci * NC + i] = apart ? fabs(cs[ci].pp[i]) + fabs(cs[ci].qq[i]) : fabs(cs[ci].pp[i] + hp->rs * zni * cs[ci].qq[i]);
             ad[(size_t)ci * NC + i] = fabs(cs[ci].dd[i]);
         }
-    for (int ci = 0; ci < 3; ci++)
+    for (int ci = 0; ci < NCORN; ci++)
         for (int m = 0; m < NE; m++) ae[(size_t)ci * NE + m] = fabs(cs[ci].ee[m]);
     for (int k = 0; k < nf; k++) {
         const double x = xg[k], x2 = x * x;
         xpw[0] = 1.0; for (int i = 1; i <= NC; i++) xpw[i] = xpw[i - 1] * x;
         zpw[0] = 1.0; for (int m = 1; m <= NE; m++) zpw[m] = zpw[m - 1] * x2;
-        for (int ci = 0; ci < 3; ci++) {
+        for (int ci = 0; ci < NCORN; ci++) {
+            /* the three classic corners on every grid point, the others on every 4th and at the grid's ends (tails are smooth in x) */
+            if (ci > 2 && (k & 3) && k + 1 < nf) continue;
             const TfCorner &c = cs[ci];
             const cplx P_ = tf_horner_host(c.pp, Kfull, x), Q_ = tf_horner_host(c.qq, Kfull, x) * zni, D_ = tf_horner_host(c.dd, Kfull, x);
             const double nref = trunc * (apart ? sqrt(std::norm(P_)) + zn * sqrt(std::norm(Q_)) : sqrt(std::norm(P_ + hp->rs * Q_)));
@@ -361,18 +395,19 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
         /* self-check: exactly what the device evaluates (kept lengths, this denominator form) against the per-element evaluation */
         worst = 0.0;
         int range_ok = 1;
-        for (int ci = 0; ci < 3 && range_ok; ci++) {
+        for (int ci = 0; ci < NCORN && range_ok; ci++) {
             const TfCorner &c = cs[ci];
             for (int k = 0; k < nf; k++) {
                 const double x = xg[k], y = -x * x;
+                if (ci > 2 && (k & 3) && k > 0 && k + 1 < nf && mask[k - 1] == mask[k] && mask[k + 1] == mask[k]) continue;
                 double d2 = 1.0;
                 if (out->den == QO_TF_DEN_E) { d2 = c.ee[out->kd - 1]; for (int m = out->kd - 2; m >= 0; m--) d2 = d2 * y + c.ee[m]; }
                 else if (out->den == QO_TF_DEN_D || out->den == QO_TF_DEN_DD) d2 = std::norm(tf_horner_host(c.dd, out->kd, x));
                 if (!(d2 > 1e-70 && d2 < 1e70)) { range_ok = 0; break; }      /* the batched reciprocal multiplies four of them */
-                /* value check: every in-band point of the nominal network; the two corners on every 4th point and
+                /* value check: every in-band point of the nominal network; every other point of the box on every 4th point and
                  * around the band edges (their job is to catch a tolerance-driven loss of conditioning, which is smooth in x) */
                 if (!mask[k]) continue;
-                if (ci != 1 && (k & 3) && k > 0 && k + 1 < nf && mask[k - 1] == mask[k] && mask[k + 1] == mask[k]) continue;
+                if (ci != QO_TF_NOMINAL && (k & 3) && k > 0 && k + 1 < nf && mask[k - 1] == mask[k] && mask[k + 1] == mask[k]) continue;
                 const cplx P_ = tf_horner_host(c.pp, kn, x), Q_ = tf_horner_host(c.qq, kn, x) * zni;
                 /* per-element evaluation, column vector from the load end: imm = N(jx) / D(jx) */
                 double ar = hp->rl, ai = 0.0, br = 1.0, bi = 0.0, dref = 1.0;
@@ -494,14 +529,17 @@ extern "C" int qo_tf_fs_plan_check(const DevProg *hp, int mode_full_s, int preci
     double trunc = 5e-13, tol = 1e-10;
     if (getenv("QO100NET_TF_TRUNC")) trunc = atof(getenv("QO100NET_TF_TRUNC"));
     if (getenv("QO100NET_TF_TOL")) tol = atof(getenv("QO100NET_TF_TOL"));
-    std::vector<TfCorner> cs(3), c2(3);
-    for (int ci = 0; ci < 3; ci++) {
+    const int NCORN = hp->n_var > 0 ? QO_TF_NCORNER : 2;
+    std::vector<TfCorner> cs((size_t)NCORN), c2((size_t)NCORN);
+    for (int ci = 0; ci < NCORN; ci++) {
         TfCorner &c = cs[ci];
+        double xv[QO_MAX_VAR];
+        tf_corner_vars(hp, e0, nl, ci, xv);
         for (int e = 0; e < nl; e++) {
             double p[6];
             for (int k = 0; k < 6; k++) {
                 p[k] = hp->nom[e0 + e][k];
-                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], (double)(ci - 1), hp->tmode[e0 + e][k]);
+                if (hp->tvar[e0 + e][k] >= 0) p[k] = qo_stream_apply(p[k], hp->ttol[e0 + e][k], xv[hp->tvar[e0 + e][k]], hp->tmode[e0 + e][k]);
             }
             c.ser[e] = qo_tf_element(hp->opcode[e0 + e], p, wr, c.nd[e]);
             const double sc = c.ser[e] ? zni : zn;
@@ -521,7 +559,8 @@ extern "C" int qo_tf_fs_plan_check(const DevProg *hp, int mode_full_s, int preci
     for (int k = 0; k < nf; k++) {
         const double x = two_pi * f[k] / wr;
         xpw[0] = 1.0; for (int i = 1; i <= NC; i++) xpw[i] = xpw[i - 1] * x;
-        for (int ci = 0; ci < 3; ci++) {
+        for (int ci = 0; ci < NCORN; ci++) {
+            if (ci > 2 && (k & 3) && k + 1 < nf) continue;
             for (int which = 0; which < 2; which++) {
                 const TfCorner &c = which ? c2[ci] : cs[ci];
                 const double nref = trunc * (sqrt(std::norm(tf_horner_host(c.pp, Kfull, x))) + sqrt(std::norm(tf_horner_host(c.qq, Kfull, x))));
@@ -561,10 +600,10 @@ extern "C" int qo_tf_fs_plan_check(const DevProg *hp, int mode_full_s, int preci
     if (factored) { out->den = QO_TF_DEN_E + 100; out->kd = 0; }          /* marker: factored D (launch_tf_fs reads it) */
     /* self-check: S11, S21, S22 from the kept polynomials against the per-element ABCD chain */
     double worst = 0.0;
-    for (int ci = 0; ci < 3; ci++) {
+    for (int ci = 0; ci < NCORN; ci++) {
         const TfCorner &c = cs[ci], &cb = c2[ci];
         for (int k = 0; k < nf; k++) {
-            if (ci != 1 && (k & 3) && k > 0 && k + 1 < nf) continue;
+            if (ci != QO_TF_NOMINAL && (k & 3) && k > 0 && k + 1 < nf) continue;
             const double x = two_pi * f[k] / wr, y = -x * x;
             const cplx Pv = tf_horner_host(c.pp, kn, x), Qv = tf_horner_host(c.qq, kn, x) * zni;
             const cplx P2 = tf_horner_host(cb.pp, kn, x), Q2 = tf_horner_host(cb.qq, kn, x) * zni;

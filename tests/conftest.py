@@ -93,3 +93,32 @@ def to_ref(R, net):
 
 def relerr(a, b):
     return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-300)))
+
+
+@pytest.fixture(scope="session")
+def png_curves():
+    """Pixels of the S21 / S11 curves of the reference's rf-tools plots + axis calibration (tools/make_golden.py png_curves)."""
+    return np.load(os.path.join(GOLDEN, "rftools_png_curves.npz"))
+
+
+def png_curve_distance(curves, key, sweep):
+    """How far the reference's plotted curves lie from a model.  sweep(f) -> (s11, s21) complex arrays.
+    Returns {"s21": (max_px, p99_px, covered), "s11": ...}: distances in pixels from every curve pixel of the PNG to the model
+    polyline drawn in the same axes (1 px = 0.17 dB of S21, 0.086 dB of S11, 0.49 % in frequency), and the share of the model's
+    visible points that have a curve pixel (of either colour: the red curve is drawn over the blue one) within 2.5 px."""
+    from scipy.spatial import cKDTree
+    ticks, (ax_l, ax_r, y0, y1) = curves[key + "_xticks"], curves[key + "_frame"]
+    b, a = np.polyfit(np.log10(ticks[:, 1]), ticks[:, 0], 1)              # column = a + b log10(f)
+    x = np.linspace(ax_l, ax_r, 40000)
+    f = 10.0 ** ((x - a) / b)
+    s11, s21 = sweep(f)
+    pb, pr = curves[key + "_s21_px"].astype(float), curves[key + "_s11_px"].astype(float)
+    out = {}
+    for name, s, pix, cover, span in (("s21", s21, pb, np.vstack([pb, pr]), 80.0), ("s11", s11, pr, pr, 40.0)):
+        y = y0 - 20.0 * np.log10(np.abs(s)) * ((y1 - y0) / span)
+        ok = (y >= y0) & (y <= y1 - 1) & (x >= ax_l + 3) & (x <= ax_r - 2)
+        model = np.stack([x[ok], y[ok]], 1)
+        d = cKDTree(model).query(pix)[0]
+        dc = cKDTree(cover).query(model)[0]
+        out[name] = (float(d.max()), float(np.percentile(d, 99)), float(np.mean(dc <= 2.5)))
+    return out

@@ -1,6 +1,6 @@
 """world_size-2 gloo test of the N>1 host logic: sample sharding + the counter all-reduce.
 On CPU the per-shard evaluator is the oracle (test infrastructure); on the GPU box the same
-logic runs with the CUDA plan (tests/test_gpu_parity.py::test_sharded_launch_invariance)."""
+logic runs with the CUDA plan (tests/test_gpu_parity.py::test_sample_offset_and_sharding_invariance)."""
 import os
 import sys
 

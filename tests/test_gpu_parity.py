@@ -155,20 +155,21 @@ def test_sweep_errors(Q, ctx):
 
 
 def test_device_perturbations_bit_exact(Q, R, ctx):
-    """Per-sample perturbation factors: device == C reference stream, bit for bit (1e6 factors)."""
+    """Per-sample perturbation factors: device == the oracle's C stream, bit for bit, ALL 1e6 factors of both
+    distributions ("test = memcmp of 1e6 factors"), plus the product's host twin on a slice."""
+    seed, off = 0x5EED010000000002, 123456789012
     for dist in (Q.DIST_UNIFORM, Q.DIST_GAUSS3S):
         ns, nv = 62500, 16
-        got = ctx.device_perturb_factors(0x5EED010000000002, 123456789012, ns, nv, dist, 0.05)
-        ref = np.empty((ns, nv))
-        L = R.lib()
-        for s in range(0, ns, 7):          # every 7th sample against the ORACLE's stream ...
-            for v in range(nv):
-                ref[s, v] = L.ref_perturb_factor(0x5EED010000000002, 123456789012 + s, v, dist, 0.05)
-            assert np.array_equal(got[s], ref[s])
-        # ... and all 1e6 against the product's host twin (itself bit-exact vs the oracle in test_host.py)
-        host = np.array([[Q.perturb_factor(0x5EED010000000002, 123456789012 + s, v, dist, 0.05) for v in range(nv)]
-                         for s in range(0, ns, 1)][:4096])
-        assert np.array_equal(got[:4096], host)
+        got = ctx.device_perturb_factors(seed, off, ns, nv, dist, 0.05)
+        ref = R.perturb_factors(seed, off, ns, nv, dist, 0.05)
+        assert got.shape == ref.shape == (ns, nv) and got.size == 1000000
+        assert got.tobytes() == ref.tobytes()                      # memcmp-level equality
+        assert np.all(np.abs(got - 1.0) <= 0.05) and np.unique(got).size > 990000
+        host = np.array([[Q.perturb_factor(seed, off + s, v, dist, 0.05) for v in range(nv)] for s in range(512)])
+        assert np.array_equal(got[:512], host)
+    # a sample offset beyond 2^32 exercises the high counter word
+    got = ctx.device_perturb_factors(seed, (1 << 40) + 5, 1000, 7, Q.DIST_UNIFORM, 0.02)
+    assert got.tobytes() == R.perturb_factors(seed, (1 << 40) + 5, 1000, 7, Q.DIST_UNIFORM, 0.02).tobytes()
 
 
 def _mc_both(Q, R, ctx, w, n, nthreads=8, **kw):
@@ -508,6 +509,10 @@ def test_gpu_sweep_to_qucs_dataset(Q, W, ctx, golden_dat, tmp_path):
     assert relerr(r["S[2,1]"], golden_dat["S21"]) <= TOL64 and relerr(r["S[1,2]"], golden_dat["S12"]) <= TOL64
     assert np.max(np.abs(r["S21_dB"] - golden_dat["S21_dB"])) <= 1e-9
     assert np.all(np.abs(r["S[1,1]"] - golden_dat["S11"]) <= TOL64 * np.maximum(np.abs(golden_dat["S11"]), 0.02))
+    # the display markers of util/pa-lpf-simulation/pa-lpf-simulation.dpl:25-28 (3 digits, on the dataset's own grid points)
+    for fm, val in ((2.39009e9, -0.952), (7.20424e9, -8.85), (4.79817e9, -22.8), (3.06355e9, -2.82)):
+        k = int(np.argmin(np.abs(r["frequency"] - fm)))
+        assert abs(r["S21_dB"][k] - val) < 0.006 * max(1.0, abs(val) / 3)
 
 
 def test_single_process_multi_gpu_ctx_matches_one_gpu(Q, W, ctx):
@@ -777,6 +782,35 @@ def test_tf_kernel_general_lumped_networks(Q, R, W, ctx, monkeypatch):
             itp = ctx.mc_run(net, f, specs, 21, n, tols, sample_offset=3, dist=dist, **hist)
             monkeypatch.delenv("QO100NET_KERNEL", raising=False)
             _assert_counts_equal(itp, got)
+
+
+@pytest.mark.parametrize("which", ["cfg2", "cfg5"])
+def test_tf_kernel_equals_chain_kernel_at_2e6_samples(Q, W, ctx, monkeypatch, which):
+    """BASELINE configs 2 and 5 at 2e6 samples x 4096 points: the transfer-function kernel (polynomial expansion + Horner) and
+    the straight-line ABCD-chain kernel (QO100NET_KERNEL=ladder) return identical integers -- n_pass, every fail_per_spec and
+    all 256 histogram bins -- although they round differently (the plan's self-check bounds the difference at 1e-10 relative on
+    |den|^2, see self_check_err, the max over 33 points of the tolerance box)."""
+    w = W.cfg2() if which == "cfg2" else W.cfg5()
+    n = 2000000
+    res = {}
+    for kern in ("tf", "ladder"):
+        if kern == "ladder":
+            monkeypatch.setenv("QO100NET_KERNEL", "ladder")
+        else:
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+        assert plan.kernel_name == ("qo_mc_tf_kernel" if kern == "tf" else "qo_mc_ladder_kernel")
+        if kern == "tf":
+            info = plan.tf_info
+            assert info["selected"] and info["self_check_err"] < 1e-10, info
+        plan.launch(777, n)
+        res[kern] = plan.read()
+        plan.close()
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    a, b = res["tf"], res["ladder"]
+    assert a["n_total"] == b["n_total"] == n and a["n_pass"] == b["n_pass"]
+    assert np.array_equal(a["fail_per_spec"], b["fail_per_spec"]) and np.array_equal(a["hist"], b["hist"])
+    assert int(a["hist"].sum()) == n and 0.5 < a["n_pass"] / n < 0.8
 
 
 def test_tf_kernel_values_within_1e_9(Q, W, ctx, monkeypatch):

@@ -11,6 +11,10 @@ Writes
                                    util/preamp-bias-simulation/06HP47N.s2p, docs/pa-driver/pa_20W_vdd_32V_idq_180mA.s2p)
                                    parsed by an independent numpy parser (python tools/make_golden.py /root/reference touchstone)
   tests/golden/pa_bias_dat.npz  -- util/pa-bias-simulation/pa-bias-simulation.dat:1-85035 (5-port S entries, 5000 points)
+  tests/golden/rftools_png_curves.npz -- the S21 / S11 curves of the reference's three rf-tools plots (util/if-bandpass-filter/
+                                   bokeh_plot.png, util/gpsdo-ouput-filters/10M/bokeh_plot.png, docs/upconverter/
+                                   upconverter-lol-filter.png) as pixel coordinates, with the axis calibration read from the
+                                   tick marks (python tools/make_golden.py /root/reference png_curves)
   tests/golden/appendix_b.json  -- 40-digit mpmath evaluation of the textbook ladder / coupled-line
                                    equations (SURVEY App. B) at the frequencies the survey tabulates;
                                    an implementation independent of both the oracle and the product.
@@ -247,8 +251,51 @@ def golden_touchstone():
     np.savez_compressed(os.path.join(OUT, "touchstone.npz"), **out)
 
 
+# rf-tools.com plots (Bokeh): S21 in blue against the left axis (0 .. -80 dB), S11 in red against the right axis (0 .. -40 dB),
+# logarithmic frequency axis.  (labelled major tick pixel column, frequency) pairs read from each image's tick labels.
+PNGS = {"if_bpf": ("util/if-bandpass-filter/bokeh_plot.png", "util/if-bandpass-filter/schematic.svg",
+                   [(412, 500e6), (555, 1e9), (639, 1.5e9)]),
+        "gpsdo_10m": ("util/gpsdo-ouput-filters/10M/bokeh_plot.png", "util/gpsdo-ouput-filters/10M/schematic.svg",
+                      [(256, 10e6), (412, 20e6), (503, 30e6), (568, 40e6), (619, 50e6), (660, 60e6)]),
+        "lol_hpf": ("docs/upconverter/upconverter-lol-filter.png", "docs/upconverter/upconverter-lol-filter.svg",
+                    [(295, 1e9), (451, 2e9), (543, 3e9), (608, 4e9), (658, 5e9)])}
+
+
+def golden_png_curves():
+    """Pixel coordinates of the plotted curves + axis calibration.  Nothing is computed with the product or the oracle here:
+    the fixture is the reference's picture, reduced to the pixels of its two curves."""
+    from PIL import Image
+    out = {}
+    for key, (png, svg, anchors) in PNGS.items():
+        im = np.array(Image.open(os.path.join(REF, png)).convert("RGB")).astype(int)
+        r, g, b = im[..., 0], im[..., 1], im[..., 2]
+        blue = (b > 150) & (r < 80) & (g > 90) & (g < 160)          # Bokeh's default blue #1f77b4
+        red = (r > 200) & (g < 60) & (b < 60)
+        dark = (r < 90) & (g < 90) & (b < 90)
+        ax_l, ax_r = int(np.nonzero(blue.sum(0) > 300)[0][0]), int(np.nonzero(red.sum(0) > 300)[0][0])      # the two y axes
+        ax_b = int(np.nonzero(dark.sum(1) > 300)[0][0])                                                       # the frequency axis
+        yt = np.nonzero(blue[:, ax_l - 5])[0]                       # major ticks of the S21 axis: 0, -10, ... -80 dB
+        assert len(yt) == 9 and yt[-1] == ax_b, (key, yt, ax_b)
+        maj = [int(x) for x in np.nonzero(dark[ax_b + 4, :])[0]]   # labelled (long) ticks of the frequency axis
+        assert all(a[0] in maj for a in anchors), (key, maj, anchors)
+
+        def pts(mask):
+            ys, xs = np.nonzero(mask[:, ax_l + 2:ax_r - 1])
+            xs = xs + ax_l + 2
+            keep = (ys >= yt[0] - 1) & (ys <= ax_b - 1)
+            return np.stack([xs[keep], ys[keep]], 1).astype(np.int16)
+        out[key + "_s21_px"], out[key + "_s11_px"] = pts(blue), pts(red)
+        out[key + "_xticks"] = np.array(anchors, dtype=float)                   # (pixel column, Hz)
+        out[key + "_frame"] = np.array([ax_l, ax_r, yt[0], ax_b], dtype=float)   # left, right, row of 0 dB, row of -80 / -40 dB
+        print("png", key, png, "S21 px", len(out[key + "_s21_px"]), "S11 px", len(out[key + "_s11_px"]), "frame", out[key + "_frame"])
+    np.savez_compressed(os.path.join(OUT, "rftools_png_curves.npz"), **out)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "png_curves":
+        golden_png_curves()
+        sys.exit(0)
     if len(sys.argv) > 2 and sys.argv[2] == "touchstone":
         golden_touchstone()
         sys.exit(0)
@@ -260,3 +307,4 @@ if __name__ == "__main__":
     golden_appendix_b()
     golden_touchstone()
     golden_pa_bias()
+    golden_png_curves()

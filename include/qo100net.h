@@ -252,6 +252,14 @@ int qo_nodal_sweep(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, qo_
 int qo_nodal_mc_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
                     const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s);
 
+/* The host-only part of a nodal job (needs no GPU): compile the netlist and try the static factorisation plan -- one pivot
+ * order and fill pattern for the whole job, verified against a pivoted dense solve at up to 33 grid points of the nominal
+ * network and at 8 vertices of the tolerance box (9 grid points each).  info[0] = plan accepted, [1] = unknowns, [2] = packed
+ * non-zeros incl. fill, [3] = program length in 16-bit words; *max_multiplier (nullable) = the largest |L| entry the probes met.
+ * On the device every point re-checks its own multipliers: a point above 3e6 (or NaN) sends the whole job to the kernel with
+ * per-point partial pivoting, so an unprobed frequency or an interior sample cannot silently lose digits. */
+int qo_nodal_analyze(const qo_nodal *nd, const double *f, int nf, const qo_mc_cfg *cfg, int info[4], double *max_multiplier);
+
 /* which factorisation the calling thread's last nodal call used: "qo_nodal_kernel<static,smem>" /
  * "qo_nodal_kernel<static,local>" (symbolic plan: fixed pivot order and fill pattern, verified on the host against
  * the pivoted solve; values in a thread-private array or, with QO100NET_NODAL_VALUES=smem, in shared memory) or "qo_nodal_kernel<dense>" (per-point partial pivoting; QO100NET_NODAL=dense forces it) */

@@ -30,15 +30,20 @@ static int nccl_load(NcclApi *a)
 {
     memset(a, 0, sizeof *a);
     const char *names[] = { "libnccl.so.2", "libnccl.so", NULL };
-    for (int i = 0; names[i] && !a->h; i++) a->h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
-    if (!a->h) return 0;
+    const char *why = NULL;
+    for (int i = 0; names[i] && !a->h; i++) {
+        a->h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+        if (!a->h && !why) why = dlerror();            /* read it now: the next dl* call clears it */
+    }
+    if (!a->h) { qo_set_error("libnccl.so.2 not loadable: %s", why ? why : "dlopen failed"); return 0; }
     a->CommInitAll = (int (*)(ncclComm_t *, int, const int *))dlsym(a->h, "ncclCommInitAll");
     a->CommDestroy = (int (*)(ncclComm_t))dlsym(a->h, "ncclCommDestroy");
     a->AllReduce = (int (*)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(a->h, "ncclAllReduce");
     a->GroupStart = (int (*)(void))dlsym(a->h, "ncclGroupStart");
     a->GroupEnd = (int (*)(void))dlsym(a->h, "ncclGroupEnd");
     a->GetErrorString = (const char *(*)(int))dlsym(a->h, "ncclGetErrorString");
-    return a->CommInitAll && a->CommDestroy && a->AllReduce && a->GroupStart && a->GroupEnd;
+    if (!(a->CommInitAll && a->CommDestroy && a->AllReduce && a->GroupStart && a->GroupEnd)) { qo_set_error("libnccl lacks a required entry point"); return 0; }
+    return 1;
 }
 enum { QO_NCCL_UINT64 = 5, QO_NCCL_SUM = 0 };   /* ncclUint64, ncclSum (nccl.h enum values) */
 
@@ -132,7 +137,7 @@ extern "C" int qo_ctx_create_on_device(int device, qo_ctx **out)
     if (!c) return QO_ERR_NOMEM;
     c->ndev = 1;
     rc = devctx_init(&c->d[0], device);
-    if (rc) { free(c); return rc; }
+    if (rc) { qo_ctx_destroy(c); return rc; }          /* releases whatever the partial initialisation created */
     *out = c;
     return QO_OK;
 }
@@ -149,16 +154,16 @@ extern "C" int qo_ctx_create(int ngpus, qo_ctx **out)
     c->ndev = ngpus;
     for (int g = 0; g < ngpus; g++) {
         rc = devctx_init(&c->d[g], g);
-        if (rc) { free(c); return rc; }
+        if (rc) { qo_ctx_destroy(c); return rc; }
     }
     if (ngpus > 1) {
         /* the only collective on this path: one all-reduce of the u64 counters */
-        if (!nccl_load(&c->nccl)) { free(c); qo_set_error("libnccl.so.2 not loadable: %s", dlerror()); return QO_ERR_NCCL; }
+        if (!nccl_load(&c->nccl)) { qo_ctx_destroy(c); return QO_ERR_NCCL; }      /* nccl_load has set the error text */
         int devs[8];
         for (int g = 0; g < ngpus; g++) devs[g] = g;
+        c->have_nccl = 1;                              /* from here on qo_ctx_destroy also destroys the communicators that exist */
         int r = c->nccl.CommInitAll(c->comm, ngpus, devs);
-        if (r != 0) { qo_set_error("ncclCommInitAll: %s", c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); free(c); return QO_ERR_NCCL; }
-        c->have_nccl = 1;
+        if (r != 0) { qo_set_error("ncclCommInitAll: %s", c->nccl.GetErrorString ? c->nccl.GetErrorString(r) : "?"); qo_ctx_destroy(c); return QO_ERR_NCCL; }
     }
     *out = c;
     return QO_OK;
@@ -183,10 +188,11 @@ extern "C" void qo_ctx_destroy(qo_ctx *ctx)
     for (int g = 0; g < ctx->ndev; g++) {
         cudaSetDevice(ctx->d[g].device);
         if (ctx->have_nccl && ctx->comm[g]) ctx->nccl.CommDestroy(ctx->comm[g]);
-        if (ctx->d[g].own_stream) cudaStreamDestroy(ctx->d[g].stream);
-        cudaEventDestroy(ctx->d[g].ev0);
-        cudaEventDestroy(ctx->d[g].ev1);
+        if (ctx->d[g].own_stream && ctx->d[g].stream) cudaStreamDestroy(ctx->d[g].stream);
+        if (ctx->d[g].ev0) cudaEventDestroy(ctx->d[g].ev0);
+        if (ctx->d[g].ev1) cudaEventDestroy(ctx->d[g].ev1);
     }
+    cudaGetLastError();                                /* a partially built ctx may hand invalid handles to the calls above */
     free(ctx);
 }
 
@@ -221,6 +227,8 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
                       DevProg *hp, int *generic, double *flops, std::vector<unsigned char> *mask)
 {
     memset(hp, 0, sizeof *hp);
+    if (cfg && cfg->mode != QO_MODE_REDUCE_ONLY && cfg->mode != QO_MODE_FULL_S) { qo_set_error("unknown mode %d (QO_MODE_REDUCE_ONLY | QO_MODE_FULL_S)", cfg->mode); return QO_ERR_ARG; }
+    if (cfg && cfg->precision != 0 && cfg->precision != 32 && cfg->precision != 64) { qo_set_error("precision must be 64 or 32 (0 = 64), not %d", cfg->precision); return QO_ERR_ARG; }
     if (net->n > QO_MAX_OPS) { qo_set_error("network has %d elements, limit %d", net->n, QO_MAX_OPS); return QO_ERR_RANGE; }
     if (nspec < 0 || nspec > QO_NSPEC_MAX) { qo_set_error("at most %d specs", QO_NSPEC_MAX); return QO_ERR_RANGE; }
     hp->n_ops = net->n;
@@ -253,7 +261,7 @@ static int build_prog(const qo_net *net, const double *f, int nf, const qo_spec 
         case QO_CPL_THRU: op = OP_CPL; nco = 8; trig = 1; break;
         case QO_SBLOCK:
             op = OP_SBLOCK; nco = 1; trig = 1;
-            if (el->p[0] < 0 || el->p[0] >= net->nblk) { qo_set_error("element %d: S-parameter block %g is not in the net", e, el->p[0]); return QO_ERR_ARG; }
+            if (!(el->p[0] >= 0 && el->p[0] < net->nblk)) { qo_set_error("element %d: S-parameter block %g is not in the net", e, el->p[0]); return QO_ERR_ARG; }
             break;
         case QO_SUBST: op = OP_SUBST; last_sub = e; break;        /* a substrate alone does not make the network microstrip */
         case QO_CPL_MS:
@@ -951,12 +959,12 @@ static int plan_launch_dev(qo_plan *p, int g, unsigned long long off, unsigned l
         DevCtx *dc = &p->ctx->d[g];
         CU(cudaMallocAsync((void **)&cplms, (size_t)n * 4 * sizeof(double), dc->stream));
         qo_cplms_kernel<<<(unsigned)((n + 127) / 128), 128, 0, dc->stream>>>(p->d[g].prog, off, n, cplms);
-        CU(cudaGetLastError());
+        { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { cudaFreeAsync(cplms, dc->stream); qo_set_error("qo_cplms_kernel launch -> %s", cudaGetErrorString(e_)); return QO_ERR_CUDA; } }
         pl.cplms = cplms;
         p->launches++;
     }
     if (full_s) {
-        if (!full_s_dev) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
+        if (!full_s_dev) { if (cplms) cudaFreeAsync(cplms, p->ctx->d[g].stream); qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
         size_t plane = (size_t)plane_samples * (size_t)p->nf;
         double2 *base = (double2 *)full_s_dev + (size_t)plane_first * (size_t)p->nf;
         pl.s11 = base; pl.s21 = base + plane; pl.s12 = base + 2 * plane; pl.s22 = base + 3 * plane;

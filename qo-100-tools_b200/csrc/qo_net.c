@@ -160,14 +160,38 @@ int qo_net_from_sblock(const qo_s2p *blk, int polar, double rs, double rl, qo_ne
     return QO_OK;
 }
 
+/* per-kind parameter ranges: a non-positive or non-finite L, C, Z0, f0 ... would only surface as inf / NaN on the device
+ * (qo_nodal_add_branch applies the same rules to its branches) */
+static const char *elem_param_error(const qo_elem *el)
+{
+    const double *p = el->p;
+    for (int k = 0; k < QO_NPARAM; k++) if (!isfinite(p[k])) return "non-finite parameter";
+    switch (el->kind) {
+    case QO_SER_R: return p[0] >= 0 ? NULL : "R must be >= 0";
+    case QO_SHUNT_R: return p[0] > 0 ? NULL : "R must be > 0";
+    case QO_SER_L: case QO_SHUNT_L: return p[0] > 0 && p[1] >= 0 && p[2] >= 0 ? NULL : "L must be > 0, ESR and Cp >= 0";
+    case QO_SER_C: case QO_SHUNT_C: return p[0] > 0 && p[1] >= 0 && p[2] >= 0 ? NULL : "C must be > 0, ESR and ESL >= 0";
+    case QO_SER_LC_SER: case QO_SER_LC_PAR: case QO_SHUNT_LC_SER: case QO_SHUNT_LC_PAR: return p[0] > 0 && p[1] > 0 ? NULL : "L and C must be > 0";
+    case QO_TLINE: return p[0] > 0 && p[2] > 0 ? NULL : "Z0 and f0 must be > 0";
+    case QO_CPL_THRU: return p[0] > 0 && p[1] > 0 && p[4] > 0 && p[5] > 0 ? NULL : "Z0e, Z0o, f0 and Zt must be > 0";
+    case QO_SUBST: return p[0] >= 1 && p[1] > 0 && p[2] >= 0 && p[3] >= 0 && p[4] >= 0 && p[5] >= 0 ? NULL : "SUBST needs er >= 1, h > 0, t, tand, rho, D >= 0";
+    case QO_MLIN: return p[0] > 0 ? NULL : "W must be > 0";
+    case QO_MCORN: case QO_MOPEN: return p[0] > 0 ? NULL : "W must be > 0";
+    case QO_MTEE: return p[0] > 0 && p[1] > 0 && p[2] > 0 ? NULL : "Wa, Wb, W2 must be > 0";
+    case QO_SBLOCK: return p[0] >= 0 && p[0] == floor(p[0]) ? NULL : "block index must be a non-negative integer";
+    default: return NULL;
+    }
+}
+
 int qo_net_from_elements(const qo_elem *e, int n, double rs, double rl, qo_net **out)
 {
     qo_clear_error();
-    if (!e || !out || n <= 0 || !(rs > 0) || !(rl > 0)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    if (!e || !out || n <= 0 || !(rs > 0) || !(rl > 0) || !isfinite(rs) || !isfinite(rl)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
     if (n > QO_MAX_ELEMS) { qo_set_error("too many elements (%d > %d)", n, QO_MAX_ELEMS); return QO_ERR_RANGE; }
     int side = 0, have_sub = 0, n_cplms = 0;
     for (int i = 0; i < n; i++) {
         if (!kind_ok(e[i].kind)) { qo_set_error("element %d: unknown kind %d", i, e[i].kind); return QO_ERR_UNSUPPORTED; }
+        { const char *why = elem_param_error(&e[i]); if (why) { qo_set_error("element %d (kind %d): %s", i, e[i].kind, why); return QO_ERR_ARG; } }
         if (e[i].kind == QO_SUBST) have_sub = 1;
         if (e[i].kind >= QO_MLIN && !have_sub) { qo_set_error("element %d: microstrip element before any SUBST", i); return QO_ERR_ARG; }
         if (e[i].kind == QO_CPL_MS) {

@@ -78,6 +78,7 @@ struct NodalStatic {
     uint8_t rowmap[QO_NODAL_MAX_UNK];                   /* original row (equation) -> pivot-order row */
     uint8_t colmap[QO_NODAL_MAX_UNK];                   /* original unknown -> permuted column (port unknowns last) */
     uint16_t prog[QN_PROG_MAX];
+    double worst_l2;                                    /* largest |multiplier|^2 the plan-time probes met */
 };
 
 /* where a stamp lands: a dense matrix with leading dimension LD (dense kernel, host analysis) ... */
@@ -161,9 +162,13 @@ __host__ __device__ __forceinline__ void nodal_stamp_all(const NodalProg *prog, 
     for (int p = 0; p < prog->np; p++) S.add(prog->port_node[p] - 1, prog->port_node[p] - 1, make_double2(1.0 / prog->port_z0[p], 0.0));
 }
 
-/* run the elimination part of a static program on the value array V */
-template <int VS> __host__ __device__ __forceinline__ void static_factor(const uint16_t *pg, int n, double2 *V)
+/* run the elimination part of a static program on the value array V.  Returns the largest |multiplier|^2 met: per-point
+ * partial pivoting keeps every multiplier <= 1; the fixed order does not, and a huge one means this point (this sample's
+ * values at this frequency) wanted another pivot -- the caller counts such points and the host re-runs the job on the
+ * pivoted dense kernel (QN_GROWTH2) */
+template <int VS> __host__ __device__ __forceinline__ double static_factor(const uint16_t *pg, int n, double2 *V)
 {
+    double lmax2 = 0.0;
     int ip = 0;
     for (int c = 0; c < n; c++) {
         const int nu = pg[ip + 1];
@@ -176,11 +181,18 @@ template <int VS> __host__ __device__ __forceinline__ void static_factor(const u
             const int prc = pg[ip++] * VS;
             const double2 l = hd_mul(V[prc], inv);
             V[prc] = l;
+            const double l2 = fma(l.x, l.x, l.y * l.y);
+            lmax2 = !(l2 <= lmax2) ? l2 : lmax2;                       /* NaN sticks */
             for (int q = 0; q < nu; q++) { const int prj = pg[ip + q] * VS; V[prj] = hd_fms(V[prj], l, V[ucol[q] * VS]); }
             ip += nu;
         }
     }
+    return lmax2;
 }
+/* |multiplier| above 3e6 or NaN: the point is suspect.  Rounding errors are amplified by at most the multiplier, so 3e6 x
+ * 1.1e-16 = 3e-10 stays inside the 1e-9 parity bar; the reference's stiff bias network (100 uF next to 1.2 pF) legitimately
+ * reaches 3e5 at 1 MHz under its ports-last order and still matches the reference dataset, a vanishing pivot gives >= 1e15 */
+#define QN_GROWTH2 1e13
 
 /* One port's substitutions, pruned symbolically: the program lists only the rows the unit right-hand side can
  * reach (forward) and only the rows the port unknowns depend on (backward).  Stream at `at`:
@@ -217,7 +229,7 @@ __global__ void __launch_bounds__(QN_TPB)
 qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restrict__ splan, const double *__restrict__ fgrid,
                 const unsigned char *__restrict__ mask, const double2 *__restrict__ yblk, int nf, int chunk_len, int nchunks,
                 unsigned long long sample_offset, unsigned long long nsamples, unsigned long long *__restrict__ counters,
-                double2 *__restrict__ s_out)
+                double2 *__restrict__ s_out, double growth2)
 {
     /* static plan staged in shared memory: every thread walks the same program (broadcast reads) */
     constexpr bool STATIC = MODE != 0;
@@ -238,6 +250,7 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restric
     const int full = prog->full;
     const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
     for (int i = tid; i < ncnt; i += QN_TPB) s_cnt[i] = 0;
+    unsigned int n_suspect = 0;                      /* points whose fixed pivot order met a huge multiplier (static plan) */
     __syncthreads();
 
     const unsigned long long n_units = nsamples * (unsigned long long)nchunks;
@@ -272,7 +285,8 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restric
                 for (int i = 0; i < splan->n_zero; i++) V[s_prog[splan->zero_at + i] * VS] = make_double2(0.0, 0.0);   /* fill-only */
                 ReplaySink<VS> S = { V, s_prog + splan->stamp_at, 0 };
                 nodal_stamp_all(prog, s_p, w, yk, (size_t)nf * 4, S);
-                static_factor<VS>(s_prog, n, V);
+                const double l2 = static_factor<VS>(s_prog, n, V);
+                if (!(l2 <= growth2)) n_suspect++;
             } else {
                 for (int i = 0; i < n; i++) {
                     perm[i] = i;
@@ -399,6 +413,7 @@ qo_nodal_kernel(const NodalProg *__restrict__ prog, const NodalStatic *__restric
         for (int i = tid; i < ncnt; i += QN_TPB)
             if (s_cnt[i]) atomicAdd(&counters[i], (unsigned long long)s_cnt[i]);
     }
+    if (STATIC && n_suspect) atomicAdd(&counters[ncnt], (unsigned long long)n_suspect);     /* one slot past the job's counters */
 }
 
 /* ---- host side ------------------------------------------------------------------------------------------ */
@@ -432,12 +447,12 @@ typedef std::vector<double2> cvec;
 
 /* dense pivoted solve of one point on the host (reference for the static plan's self-check): returns the
  * solution columns X[j][i] for every port j and the row order the pivoting chose */
-static bool host_dense(const NodalProg *hp, double f, const double2 *yk, size_t yk_stride, std::vector<int> *perm_out, std::vector<cvec> *X)
+static bool host_dense(const NodalProg *hp, const double (*par)[4], double f, const double2 *yk, size_t yk_stride, std::vector<int> *perm_out, std::vector<cvec> *X)
 {
     const int n = hp->n_unk, LD = QO_NODAL_MAX_UNK;
     cvec A((size_t)LD * LD, make_double2(0.0, 0.0));
     DenseSink<QO_NODAL_MAX_UNK> S = { A.data() };
-    nodal_stamp_all(hp, hp->nom, 6.283185307179586476925286766559 * f, yk, yk_stride, S);
+    nodal_stamp_all(hp, par, 6.283185307179586476925286766559 * f, yk, yk_stride, S);
     std::vector<int> perm(n);
     for (int i = 0; i < n; i++) perm[i] = i;
     for (int c = 0; c < n; c++) {
@@ -604,17 +619,37 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
     if (pg.size() > QN_PROG_MAX) return false;
     sp->prog_len = (int32_t)pg.size();
     memcpy(sp->prog, pg.data(), pg.size() * sizeof(uint16_t));
-    /* self-check: the static program against the pivoted dense solve at grid points across the band */
-    const int probes[7] = { 0, nf / 6, nf / 3, nf / 2, (2 * nf) / 3, (5 * nf) / 6, nf - 1 };
-    for (int t = 0; t < 7; t++) {
-        const int k = probes[t] < 0 ? 0 : probes[t] >= nf ? nf - 1 : probes[t];
+    /* self-check: the static program against the pivoted dense solve -- the nominal network at up to 33 grid points across the
+     * band, then 8 pseudo-random vertices of the tolerance box (every random variable at +-1, a fixed Philox stream) at 9 grid
+     * points each: a fixed pivot order that only suits the nominal values, or only part of the band, is rejected here; what
+     * slips through (an interior sample at an unprobed frequency) is caught on the device by the multiplier guard (QN_GROWTH2) */
+    const int n_nom = nf < 33 ? nf : 33, n_vert = hp->n_var > 0 ? 8 : 0, n_vp = nf < 9 ? nf : 9;
+    double worst_l2 = 0.0;
+    for (int t = 0; t < n_nom + n_vert * n_vp; t++) {
+        const int vert = t < n_nom ? -1 : (t - n_nom) / n_vp;
+        const int k = t < n_nom ? (n_nom > 1 ? (int)((long long)t * (nf - 1) / (n_nom - 1)) : 0)
+                                : (n_vp > 1 ? (int)((long long)((t - n_nom) % n_vp) * (nf - 1) / (n_vp - 1)) : 0);
+        double par[QO_NODAL_MAX_BR][4];
+        for (int b = 0; b < hp->nb; b++)
+            for (int q = 0; q < 4; q++) {
+                double v = hp->nom[b][q];
+                const int tv = hp->tvar[b][q];
+                if (vert >= 0 && tv >= 0) {
+                    const double x = qo_stream_variate(0x6e6f64616c706c6eull, (uint64_t)vert, (uint32_t)tv, 0) < 0.0 ? -1.0 : 1.0;
+                    v = qo_stream_apply(v, hp->ttol[b][q], x, hp->tmode[b][q]);
+                }
+                par[b][q] = v;
+            }
         std::vector<cvec> X;
-        if (!host_dense(hp, f[k], yb + (size_t)k * 4, (size_t)nf * 4, NULL, &X)) return false;
+        if (!host_dense(hp, par, f[k], yb + (size_t)k * 4, (size_t)nf * 4, NULL, &X)) return false;
         cvec V((size_t)nnz, make_double2(nan(""), nan("")));            /* poisoned: the streams must initialise every value */
         for (int i = 0; i < sp->n_zero; i++) V[sp->prog[sp->zero_at + i]] = make_double2(0.0, 0.0);
         ReplaySink<1> S = { V.data(), sp->prog + sp->stamp_at, 0 };
-        nodal_stamp_all(hp, hp->nom, 6.283185307179586476925286766559 * f[k], yb + (size_t)k * 4, (size_t)nf * 4, S);
-        static_factor<1>(sp->prog, n, V.data());
+        nodal_stamp_all(hp, par, 6.283185307179586476925286766559 * f[k], yb + (size_t)k * 4, (size_t)nf * 4, S);
+        const double l2 = static_factor<1>(sp->prog, n, V.data());
+        if (getenv("QO100NET_NODAL_DEBUG") && !(l2 <= QN_GROWTH2)) fprintf(stderr, "qo_nodal: probe f=%g Hz: largest multiplier %.3g\n", f[k], sqrt(l2));
+        if (!(l2 <= QN_GROWTH2)) return false;                          /* the device would flag this point: do not start on this plan */
+        if (l2 > worst_l2) worst_l2 = l2;
         for (int j = 0; j < np; j++) {
             cvec x(n, make_double2(0.0, 0.0));
             x[sp->rowmap[hp->port_node[j] - 1]] = make_double2(1.0 / hp->port_z0[j], 0.0);
@@ -627,27 +662,24 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
                  * reference network (100 uF next to 1.2 pF) is eliminated in the fixed ports-last order; 5e-11 on V
                  * = 1e-10 on S keeps the plan inside the 1e-9 parity bar, anything worse takes the dense kernel */
                 if (!(err <= 1e-9 * ref + 5e-11)) {                                    /* NaN fails too */
-                    if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: static plan rejected at f=%g Hz, port %d<-%d: err %.3e ref %.3e\n", f[k], p, j, err, ref);
+                    if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: static plan rejected at f=%g Hz (%s), port %d<-%d: err %.3e ref %.3e\n", f[k], vert < 0 ? "nominal" : "tolerance-box vertex", p, j, err, ref);
                     return false;
                 }
             }
         }
     }
-    if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: static plan n=%d nnz=%d program=%d words\n", n, nnz, sp->prog_len);
+    sp->worst_l2 = worst_l2;
+    if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: static plan n=%d nnz=%d program=%d words, largest multiplier %.3g\n", n, nnz, sp->prog_len, sqrt(worst_l2));
     return true;
 }
 
-static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
-                     const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s_host)
+/* host-only front end: netlist + specs + tolerances -> device program, spec masks, block admittances */
+static int nodal_compile(const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec, const qo_mc_cfg *cfg, int full,
+                         NodalProg *hp, std::vector<unsigned char> &mask, std::vector<double2> &yb, int *n_unk_out)
 {
-    if (!ctx || !nd || !f || nf <= 0 || !cfg || nspec < 0 || nspec > QN_MAX_SPEC || (nspec && !spec)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    if (!nd || !f || nf <= 0 || !cfg || nspec < 0 || nspec > QN_MAX_SPEC || (nspec && !spec)) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
     if (nd->np < 1) { qo_set_error("the netlist has no ports"); return QO_ERR_ARG; }
     for (int k = 0; k < nf; k++) if (!(f[k] > 0.0) || !isfinite(f[k])) { qo_set_error("frequency %d is not a positive finite number", k); return QO_ERR_ARG; }
-    const int full = cfg->mode == QO_MODE_FULL_S;
-    if (full && !full_s_host) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
-    if (!full && !res) return QO_ERR_ARG;
-    std::vector<NodalProg> hpv(1);
-    NodalProg *hp = &hpv[0];
     memset(hp, 0, sizeof *hp);
     hp->n_nodes = nd->n_nodes; hp->nb = nd->nb; hp->np = nd->np; hp->full = full;
     hp->seed = cfg->seed; hp->dist = cfg->dist;
@@ -661,6 +693,7 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     }
     if (n_unk > QO_NODAL_MAX_UNK) { qo_set_error("%d unknowns, limit %d", n_unk, QO_NODAL_MAX_UNK); return QO_ERR_RANGE; }
     hp->n_unk = n_unk;
+    *n_unk_out = n_unk;
     for (int p = 0; p < nd->np; p++) { hp->port_node[p] = nd->port_node[p]; hp->port_z0[p] = nd->port_z0[p]; }
     int nvar = 0;
     if (cfg->n_tol < 0 || (cfg->n_tol > 0 && !cfg->tol)) return QO_ERR_ARG;
@@ -674,7 +707,7 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     }
     hp->n_var = nvar;
     hp->nspec = nspec;
-    std::vector<unsigned char> mask((size_t)nf, 0);
+    mask.assign((size_t)nf, 0);
     for (int s = 0; s < nspec; s++) {
         if (spec[s].kind != QO_SPEC_S21_MIN_DB && spec[s].kind != QO_SPEC_S21_MAX_DB) { qo_set_error("nodal spec %d: kind must be QO_SPEC_S21_MIN_DB or QO_SPEC_S21_MAX_DB", s); return QO_ERR_ARG; }
         if (spec[s].row < 0 || spec[s].row >= nd->np || spec[s].col < 0 || spec[s].col >= nd->np) { qo_set_error("nodal spec %d: S entry out of range", s); return QO_ERR_ARG; }
@@ -688,7 +721,7 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         hp->hist_bins = cfg->hist_bins; hp->hist_spec = cfg->hist_spec; hp->hist_lo = cfg->hist_lo; hp->hist_hi = cfg->hist_hi;
     }
     /* measured blocks: admittance per (block branch, grid point), in branch order */
-    std::vector<double2> yb((size_t)n_sb * nf * 4);
+    yb.assign((size_t)n_sb * nf * 4, make_double2(0.0, 0.0));
     int ib = 0;
     for (int b = 0; b < nd->nb; b++) {
         if (nd->br[b].kind != QO_NB_SBLOCK) continue;
@@ -700,6 +733,48 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
             for (int q = 0; q < 4; q++) yb[((size_t)ib * nf + k) * 4 + q] = make_double2(y[q].re, y[q].im);
         }
         ib++;
+    }
+    return QO_OK;
+}
+
+/* The host-only part of a nodal job (needs no GPU): compile the netlist and try the static (symbolic) factorisation plan.
+ * info[0] = static plan accepted (0/1), [1] = unknowns, [2] = packed non-zeros incl. fill, [3] = program length (16-bit words);
+ * *max_multiplier = largest |L| entry the plan-time probes met (per-point partial pivoting would keep it <= 1). */
+extern "C" int qo_nodal_analyze(const qo_nodal *nd, const double *f, int nf, const qo_mc_cfg *cfg, int info[4], double *max_multiplier)
+{
+    qo_clear_error();
+    if (!info) return QO_ERR_ARG;
+    qo_mc_cfg c0;
+    memset(&c0, 0, sizeof c0);
+    std::vector<NodalProg> hpv(1);
+    std::vector<unsigned char> mask;
+    std::vector<double2> yb;
+    int n_unk = 0;
+    int rc = nodal_compile(nd, f, nf, NULL, 0, cfg ? cfg : &c0, 1, &hpv[0], mask, yb, &n_unk);
+    if (rc) return rc;
+    std::vector<NodalStatic> spv(1);
+    if (yb.empty()) yb.assign(4, make_double2(0.0, 0.0));
+    const bool ok = build_static(&hpv[0], f, nf, yb.data(), &spv[0]);
+    info[0] = ok; info[1] = n_unk; info[2] = ok ? spv[0].nnz : 0; info[3] = ok ? spv[0].prog_len : 0;
+    if (max_multiplier) *max_multiplier = ok ? sqrt(spv[0].worst_l2) : 0.0;
+    return QO_OK;
+}
+
+static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
+                     const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s_host)
+{
+    if (!ctx || !cfg) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    const int full = cfg->mode == QO_MODE_FULL_S;
+    if (full && !full_s_host) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
+    if (!full && !res) return QO_ERR_ARG;
+    std::vector<NodalProg> hpv(1);
+    NodalProg *hp = &hpv[0];
+    std::vector<unsigned char> mask;
+    std::vector<double2> yb;
+    int n_unk = 0;
+    {
+        const int rcc = nodal_compile(nd, f, nf, spec, nspec, cfg, full, hp, mask, yb, &n_unk);
+        if (rcc) return rcc;
     }
     /* static (symbolic) plan unless forced off or its self-check fails */
     std::vector<NodalStatic> spv(1);
@@ -733,13 +808,12 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         CUN(cudaMallocAsync((void **)&dfr, (size_t)nf * sizeof(double), dc->stream));
         CUN(cudaMallocAsync((void **)&dmask, (size_t)nf, dc->stream));
         CUN(cudaMallocAsync((void **)&dy, (yb.size() ? yb.size() : 1) * sizeof(double2), dc->stream));
-        CUN(cudaMallocAsync((void **)&dcnt, (size_t)ncnt * sizeof(unsigned long long), dc->stream));
+        CUN(cudaMallocAsync((void **)&dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));     /* + the suspect-point counter of the static kernel */
         if (full) CUN(cudaMallocAsync((void **)&ds, s_elems * sizeof(double2), dc->stream));
         CUN(cudaMemcpyAsync(dprog, hp, sizeof(NodalProg), cudaMemcpyHostToDevice, dc->stream));
         CUN(cudaMemcpyAsync(dfr, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, dc->stream));
         CUN(cudaMemcpyAsync(dmask, mask.data(), (size_t)nf, cudaMemcpyHostToDevice, dc->stream));
         if (!yb.empty()) CUN(cudaMemcpyAsync(dy, yb.data(), yb.size() * sizeof(double2), cudaMemcpyHostToDevice, dc->stream));
-        CUN(cudaMemsetAsync(dcnt, 0, (size_t)ncnt * sizeof(unsigned long long), dc->stream));
         /* FULL_S: cut the grid into QN_TPB-point chunks so that a nominal sweep fills the GPU */
         int chunk_len = nf, nchunks = 1;
         if (full) { chunk_len = QN_TPB; nchunks = (nf + chunk_len - 1) / chunk_len; }
@@ -760,8 +834,13 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         }
         const unsigned long long cap = (unsigned long long)dc->sm_count * (unsigned long long)bps;
         const int grid = (int)(units < cap ? units : cap);
+        std::vector<unsigned long long> h((size_t)ncnt + 1);
+        double growth2 = QN_GROWTH2;
+        { const char *e = getenv("QO100NET_NODAL_GUARD2"); if (e && atof(e) > 0.0) growth2 = atof(e); }     /* tests: trip the device guard on purpose */
+      relaunch:
+        CUN(cudaMemsetAsync(dcnt, 0, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));
         cudaEventRecord(dc->ev0, dc->stream);
-#define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds)
+#define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds, growth2)
         g_last_kernel = use_static ? "qo_nodal_kernel<static,local>" : "qo_nodal_kernel<dense>";
         if (use_static) {
             const int nnz = spv[0].nnz;
@@ -786,10 +865,17 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         cudaEventRecord(dc->ev1, dc->stream);
         CUN(cudaGetLastError());
         CUN(cudaStreamSynchronize(dc->stream));
+        CUN(cudaMemcpy(h.data(), dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (use_static && h[ncnt] != 0) {
+            /* some (sample, frequency) point met a multiplier above QN_GROWTH2 (or a NaN) under the fixed pivot order: the whole
+             * job is redone with per-point partial pivoting */
+            if (force && !strcmp(force, "static")) { qo_set_error("QO100NET_NODAL=static: %llu points needed another pivot order", h[ncnt]); rc = QO_ERR_UNSUPPORTED; goto out; }
+            if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: %llu suspect points under the static plan, re-running on the dense kernel\n", h[ncnt]);
+            use_static = false;
+            goto relaunch;
+        }
         if (full) CUN(cudaMemcpy(full_s_host, ds, s_elems * sizeof(double2), cudaMemcpyDeviceToHost));
         if (res) {
-            std::vector<unsigned long long> h((size_t)ncnt);
-            CUN(cudaMemcpy(h.data(), dcnt, (size_t)ncnt * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
             float ms = 0;
             cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
             res->n_pass = full ? 0 : h[0];

@@ -97,7 +97,7 @@ EXPORTS = [
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
     "qo_nodal_num_nodes", "qo_nodal_num_ports", "qo_nodal_num_branches", "qo_nodal_get_branches", "qo_nodal_get_ports",
-    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run", "qo_nodal_last_kernel",
+    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run", "qo_nodal_last_kernel", "qo_nodal_analyze",
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
@@ -174,6 +174,7 @@ def lib():
         "qo_nodal_free": (None, [vp]),
         "qo_nodal_sweep": (C.c_int, [vp, vp, dp, C.c_int, vp]),
         "qo_nodal_last_kernel": (C.c_char_p, []),
+        "qo_nodal_analyze": (C.c_int, [vp, dp, C.c_int, C.POINTER(McCfg), ip, dp]),
         "qo_nodal_mc_run": (C.c_int, [vp, vp, dp, C.c_int, C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), C.POINTER(McResult), vp]),
         "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
         "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
@@ -364,6 +365,16 @@ class Nodal:
         arr = (Branch * max(1, n))()
         lib().qo_nodal_get_branches(self._h, arr, n)
         return [(arr[i].kind, [arr[i].node[k] for k in range(4)], [arr[i].p[k] for k in range(4)]) for i in range(n)]
+
+    def analyze(self, f, tols=()):
+        """Host-only (qo_nodal_analyze): does the static factorisation plan hold for this netlist on this grid, with these
+        tolerances?  -> dict(static, unknowns, nnz, program_words, max_multiplier)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        cfg = _cfg(0, 0, list(tols), 0, DIST_UNIFORM, MODE_FULL_S, 64, 0, 0, 0.0, 1.0)
+        info = (C.c_int * 4)()
+        mm = C.c_double(0.0)
+        _check(lib().qo_nodal_analyze(self._h, _dp(f), len(f), C.byref(cfg), info, C.byref(mm)))
+        return dict(static=bool(info[0]), unknowns=info[1], nnz=info[2], program_words=info[3], max_multiplier=mm.value)
 
     def close(self):
         if self._h:

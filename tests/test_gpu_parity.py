@@ -164,7 +164,7 @@ def test_device_perturbations_bit_exact(Q, R, ctx):
         ref = R.perturb_factors(seed, off, ns, nv, dist, 0.05)
         assert got.shape == ref.shape == (ns, nv) and got.size == 1000000
         assert got.tobytes() == ref.tobytes()                      # memcmp-level equality
-        assert np.all(np.abs(got - 1.0) <= 0.05) and np.unique(got).size > 990000
+        assert np.all(np.abs(got - 1.0) <= 0.05 + 1e-15) and np.unique(got).size > 990000
         host = np.array([[Q.perturb_factor(seed, off + s, v, dist, 0.05) for v in range(nv)] for s in range(512)])
         assert np.array_equal(got[:512], host)
     # a sample offset beyond 2^32 exercises the high counter word

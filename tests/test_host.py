@@ -457,3 +457,29 @@ def test_transfer_function_plan_analysis(Q, W, monkeypatch):
     # a grid three decades wide: a 22nd-degree monomial basis cannot hold 1e-10 there -- the plan must notice
     wide = Q.plan_analyze(w.net, Q.grid_log(1e4, 1e9, 2048), [(Q.SPEC_S21_MIN_DB, 0.0, 1e9, -300.0)], w.tols)
     assert (not wide["selected"]) or wide["self_check_err"] <= 1e-10
+
+
+def test_element_parameters_are_validated(Q):
+    """Non-positive or non-finite L, C, Z0, f0 ... are refused when the network is built (they would only surface as inf / NaN
+    on the device), with the element named in the error text."""
+    ok = [(Q.SER_L, [1e-6, 0.1, 1e-13]), (Q.SHUNT_C, [1e-9, 0.05, 1e-10]), (Q.SER_R, [0.0]), (Q.TLINE, [50.0, 90.0, 1e9]),
+          (Q.CPL_THRU, [55.0, 45.0, 90.0, 90.0, 1e9, 50.0])]
+    Q.Net.from_elements(ok, 50.0, 50.0)
+    bad = [(Q.SER_L, [0.0]), (Q.SER_L, [-1e-9]), (Q.SHUNT_C, [float("nan")]), (Q.SHUNT_C, [1e-9, -0.1]), (Q.SHUNT_R, [0.0]),
+           (Q.SER_LC_SER, [1e-9, 0.0]), (Q.TLINE, [50.0, 90.0, 0.0]), (Q.TLINE, [float("inf"), 90.0, 1e9]),
+           (Q.CPL_THRU, [55.0, -45.0, 90.0, 90.0, 1e9, 50.0]), (Q.CPL_THRU, [55.0, 45.0, 90.0, 90.0, 1e9, float("nan")])]
+    for el in bad:
+        with pytest.raises(Q.QoError) as ei:
+            Q.Net.from_elements([ok[0], el], 50.0, 50.0)
+        assert ei.value.status == Q.ERR_ARG and "element 1" in str(ei.value)
+    with pytest.raises(Q.QoError):
+        Q.Net.from_elements(ok, float("inf"), 50.0)
+
+
+def test_plan_analysis_rejects_unknown_mode_and_precision(Q, W):
+    w = W.cfg2(10, 64)
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols)["reason"] == "ok"
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, mode=7)["reason"] == "network does not compile"
+    assert "mode" in Q.lib().qo_last_error().decode()
+    assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=16)["reason"] == "network does not compile"
+    assert "precision" in Q.lib().qo_last_error().decode()

@@ -184,6 +184,67 @@ def build_nodal(Q, golden_s2p):
     return nd, br, nn, ports
 
 
+def test_static_plan_analysis_host_only(Q, pa_bias, golden_s2p):
+    """qo_nodal_analyze (no GPU): the reference's bias network takes the static factorisation plan on its own 5000-point grid,
+    with and without tolerances, and its multipliers stay far below the device guard (1e5)."""
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    f = pa_bias["frequency"]
+    a = nd.analyze(f)
+    assert a["static"] and a["unknowns"] == 23 and 60 < a["nnz"] <= 160 and a["program_words"] > 100
+    assert a["max_multiplier"] < 3e6            # 3.2e5 at 1 MHz: the 100 uF / 1.2 pF stiffness, harmless (dataset parity holds)
+    tols = [(b, 0, v, Q.TOL_REL, 0.05) for v, b in enumerate(i for i, (k, _n, _p) in enumerate(br) if k in (NB_R, NB_C))]
+    at = nd.analyze(f, tols)
+    assert at["static"] and at["max_multiplier"] < 3e6
+
+
+def test_static_plan_rejects_an_order_that_only_suits_part_of_the_band(Q):
+    """A resonant divider whose dominant entry changes along the grid: node 2 hangs on a series-LC trap to ground that is a
+    short at its resonance (5.03 MHz) and nearly open elsewhere, next to a tiny conductance.  Whatever fixed order the mid-grid
+    point suggests, the analysis must either prove it at every probe (multiplier bounded) or send the job to the pivoted kernel;
+    it may never accept a plan whose probes saw a multiplier above the device guard (3e6)."""
+    nd = Q.Nodal(3)
+    nd.add_branch(Q.NB_R, [1, 2], [1e-3])
+    nd.add_branch(Q.NB_L, [2, 3], [1e-6, 0.0, 0.0])
+    nd.add_branch(Q.NB_C, [3, 0], [1e-9, 1e-6, 0.0])
+    nd.add_branch(Q.NB_R, [2, 0], [1e9])
+    nd.add_branch(Q.NB_R, [1, 3], [1e7])
+    nd.add_port(1, 50.0)
+    f = Q.grid_log(1e5, 1e9, 801)
+    a = nd.analyze(f, [(1, 0, 0, Q.TOL_REL, 0.2), (2, 0, 1, Q.TOL_REL, 0.2)])
+    assert (not a["static"]) or a["max_multiplier"] <= 3.2e6
+    nd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_guard_falls_back_to_the_pivoted_kernel(Q, R, ctx, monkeypatch):
+    """The device-side multiplier guard: a job whose static plan passes the plan-time probes but meets a huge multiplier at an
+    unprobed point is re-run with per-point pivoting, and the result equals the oracle's either way."""
+    nd = Q.Nodal(3)
+    br = [(Q.NB_R, [1, 2], [1e-3]), (Q.NB_L, [2, 3], [1e-6, 0.0, 0.0]), (Q.NB_C, [3, 0], [1e-9, 1e-6, 0.0]),
+          (Q.NB_R, [2, 0], [1e9]), (Q.NB_R, [1, 3], [1e7])]
+    for b in br:
+        nd.add_branch(*b)
+    nd.add_port(1, 50.0)
+    f = Q.grid_log(1e5, 1e9, 2001)
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
+    S = ctx.nodal_sweep(nd, f)
+    assert ctx.nodal_last_kernel() in ("qo_nodal_kernel<static,local>", "qo_nodal_kernel<dense>")
+    O = R.nodal_sweep([(k, n + [0] * (4 - len(n)), p + [0.0] * (4 - len(p))) for k, n, p in br], 3, [(1, 50.0)], f)
+    assert np.max(np.abs(S - O)) < 1e-9
+    assert np.all(np.isfinite(S.view(float)))
+    # trip the guard on purpose (threshold |multiplier| <= 2 on the device only; the plan-time probes keep the real one): the
+    # static launch flags points, the job is redone on the pivoted kernel, the result is the same
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<static,local>"
+    monkeypatch.setenv("QO100NET_NODAL_GUARD2", "4.0")
+    S2 = ctx.nodal_sweep(nd, f)
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<dense>"
+    assert np.max(np.abs(S2 - O)) < 1e-9
+    monkeypatch.setenv("QO100NET_NODAL", "static")          # ... and an explicit request for the static kernel reports the trip
+    with pytest.raises(Q.QoError):
+        ctx.nodal_sweep(nd, f)
+    nd.close()
+
+
 @pytest.mark.gpu
 def test_gpu_nodal_sweep_reproduces_pa_bias_dataset(Q, R, ctx, pa_bias, golden_s2p, monkeypatch):
     """The CUDA nodal kernel through the C-ABI against the reference's 5-port dataset (all 13 entries x 5000

@@ -170,7 +170,8 @@ def test_plot_values_gpu(Q, ctx, golden_nets):
 def test_trc_identities_gpu(Q, ctx, golden_nets):
     def sweep(el, f):
         return ctx.sweep(Q.Net.from_elements(el, 50.0, 50.0), f)[:2]
-    for name in ("dir_cpl_2.4g_20dB", "dir_cpl_2.4g_35dB", "dir_cpl_2.4g_35dB_pa_250W", "dir_cpl_525m_20dB"):
+    # (dir_cpl_2.4g_35dB_pa_250W.trc is not a 50 Ohm design: sqrt(Z0e Z0o) = 50.69, so the matched-line identities do not apply)
+    for name in ("dir_cpl_2.4g_20dB", "dir_cpl_2.4g_35dB", "dir_cpl_525m_20dB"):
         _coupler_checks(sweep, golden_nets["util/directional-couplers/%s.trc" % name])
     t = golden_nets["util/directional-couplers/dir_cpl_2.4g_20dB.trc"]
     s11, s21 = sweep([(12, [t["z0e"], t["z0o"], t["ang"], t["ang"], t["f0"], 50.0])], np.array([2.4e9]))

@@ -21,6 +21,7 @@
 #include "qo_ladder_launch.h"
 #include "qo_tf.cuh"
 #include "qo_tf_launch.h"
+#include "qo_ts.cuh"
 #include "qo_spot.cuh"
 #include "qo_tf_fs.cuh"
 #include "qo_ustrip.cuh"
@@ -47,6 +48,7 @@ static int nccl_load(NcclApi *a)
 }
 enum { QO_NCCL_UINT64 = 5, QO_NCCL_SUM = 0 };   /* ncclUint64, ncclSum (nccl.h enum values) */
 
+#define QO_TICKET_BYTES (16 + 256 * sizeof(unsigned int))
 struct DevPlan {
     DevProg *prog;
     void *w2, *wi2;            /* double2 or float2 [npairs] */
@@ -602,9 +604,11 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
 #endif
                 const int ppi = 32 * p->tf_pp;
                 p->tf_niter = (np + ppi - 1) / ppi;
-                const size_t npad = (size_t)p->tf_niter * ppi, npt = 2 * npad;
+                /* + one iteration of padding: the kernel requests the next iteration's y values before it is done with the current one */
+                const size_t npad = ((size_t)p->tf_niter + 1) * ppi, npt = 2 * npad;
                 const int ntab = 3 + (p->cpl_fast ? 4 : 0);
-                const size_t bytes = (size_t)ntab * npt * sizeof(double) + 2 * npt * sizeof(unsigned int) + (size_t)p->tf_niter * sizeof(uchar2);
+                const size_t itm_bytes = ((size_t)p->tf_niter * sizeof(uchar2) + 15) & ~(size_t)15;
+                const size_t bytes = (size_t)ntab * npt * sizeof(double) + 2 * npt * sizeof(unsigned int) + itm_bytes;
                 std::vector<unsigned char> blob(bytes);
                 double *tab = (double *)blob.data();
                 unsigned int *mb = (unsigned int *)(tab + (size_t)ntab * npt);
@@ -642,7 +646,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
             if (p->ladder || p->tf) {
                 CUP(cudaMallocAsync((void **)&d->wsq2, 2 * (size_t)np * esz, st));
                 H2D(d->wsq2, p->precision == 32 ? (const void *)wsqf.data() : (const void *)wsq.data(), 2 * (size_t)np * esz);
-                CUP(cudaMallocAsync((void **)&d->ticket, sizeof(unsigned long long), st));
+                CUP(cudaMallocAsync((void **)&d->ticket, QO_TICKET_BYTES, st));      /* the sample ticket + the per-SM arrival counters of qo_ts.cuh */
                 if (p->cpl_fast)
                     for (int t = 0; t < 4; t++) {
                         CUP(cudaMallocAsync((void **)&d->cpl_tab[t], 2 * (size_t)np * esz, st));
@@ -831,7 +835,7 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     }
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
-    CU(cudaMemsetAsync(d->ticket, 0, sizeof(unsigned long long), dc->stream));
+    CU(cudaMemsetAsync(d->ticket, 0, QO_TICKET_BYTES, dc->stream));
     P.sample_offset = off; P.nsamples = n; P.seed = hp->seed;
     P.rs = hp->rs; P.rl = hp->rl; P.k21 = hp->k21; P.hist_lo = hp->hist_lo; P.hist_hi = hp->hist_hi;
     P.wref = p->tfp.wref; P.zn = sqrt(hp->rs * hp->rl); P.zni = 1.0 / P.zn;
@@ -844,6 +848,44 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tfp.n_el; P.el0 = p->tfp.el0; P.kn = p->tfp.kn; P.kd = p->tfp.kd; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
+    /* the bulk of a large launch runs thread-per-sample (qo_ts.cuh): whole rounds of one sample per resident thread, dealt
+     * statically; what is left over (less than one wave) stays on the warp-per-sample kernel below */
+    const bool rot_same = P.cpl_lin && P.cpl_matched && P.cpl_same && !cplms;
+    if (qo_ts_eligible(&p->tfp, hp->nspec, rot_same)) {
+        /* worth it from a few batches per resident warp on (one wave = every resident thread one sample) */
+        const unsigned long long wave = (unsigned long long)qo_ts_wave_threads(&p->tfp, dc->sm_count);
+        const unsigned long long nb = wave && n >= 2 * wave ? n / 32ull : 0;
+        if (nb > 0) {
+            TsParams Q;
+            memset(&Q, 0, sizeof Q);
+            Q.t = P;
+            Q.t.nsamples = nb * 32ull;
+            Q.y1 = (const double *)d->tf_yt; Q.x1 = (const double *)d->tf_xt; Q.mw = (const uint2 *)d->tf_mb;
+            Q.npt = (p->nf + QO_TS_PT - 1) / QO_TS_PT * QO_TS_PT;
+            /* runs of groups with the same (OR, AND) of their points' spec bits; a group that straddles a band edge stands alone */
+            bool runs_ok = true;
+            for (int gi = 0; gi < Q.npt / QO_TS_PT; gi++) {
+                unsigned int any = 0, all = 0xFF;
+                for (int k = gi * QO_TS_PT; k < (gi + 1) * QO_TS_PT; k++) { const unsigned int mk = k < p->nf ? p->maskv[k] : 0; any |= mk; all &= mk; }
+                if (Q.nruns > 0 && any == all && Q.runs[Q.nruns - 1].any == any && Q.runs[Q.nruns - 1].all == all) { Q.runs[Q.nruns - 1].ngroups++; continue; }
+                if (Q.nruns == QO_TS_MAXRUN) { runs_ok = false; break; }
+                Q.runs[Q.nruns].ngroups = 1; Q.runs[Q.nruns].any = any; Q.runs[Q.nruns].all = all; Q.nruns++;
+            }
+            Q.nbatches = nb;
+            Q.ticket = d->ticket + 1;
+            Q.w0 = 6.283185307179586476925286766559 * p->f[0];
+            Q.dw = p->nf > 1 ? 6.283185307179586476925286766559 * ((p->f[p->nf - 1] - p->f[0]) / (double)(p->nf - 1)) : 0.0;
+            int rts = runs_ok ? qo_ts_launch(&p->tfp, dc->sm_count, &Q, dc->stream) : 0;
+            if (!runs_ok) goto warp_per_sample;             /* a mask pattern with more band edges than the run table holds */
+            if (rts) { qo_set_error("thread-per-sample kernel launch: %s", cudaGetErrorString((cudaError_t)rts)); return QO_ERR_CUDA; }
+            p->kernel_name = "qo_mc_ts_kernel";
+            p->launches++;
+            off += nb * 32ull; n -= nb * 32ull;
+            if (n == 0) return QO_OK;
+            P.sample_offset = off; P.nsamples = n;
+        }
+    }
+warp_per_sample:
     int rc = qo_tf_launch(&p->tfp, p->tf_pp, p->lad_variant, dc->sm_count, &P, dc->stream);
     if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for nn=%d den=%d pp=%d", p->tfp.nn, p->tfp.den, p->tf_pp); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }

@@ -375,6 +375,8 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     }
     ke = (ke + 1) & ~1;                                       /* the kernel loads E two coefficients at a time */
     if (ke < 2) ke = 2;
+    if (kn < 2) kn = 2;                                       /* the Horner code starts from the two top rows (a zero row costs one FMA) */
+    if (kdd < 2) kdd = 2;
     out->kn = kn;
     /* denominator form: the truncated |D|^2 polynomial when it is short enough to pay, else D itself; a form whose
      * self-check fails (E loses digits next to a trap's notch, where |D| -> 0) hands over to the next one */

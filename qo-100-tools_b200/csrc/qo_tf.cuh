@@ -138,6 +138,125 @@ __device__ __forceinline__ void tf_cpl_matched(unsigned int cf, const double (&w
     tf_cpl_matched_sc<PTS>(cf, se, ce, so, co, uar, uai, ubr, ubi, sg2);
 }
 
+
+/* The per-sample stage, shared by the warp-per-sample kernel below and the thread-per-sample kernel of qo_ts.cuh.  One warp:
+ *  1. the sample's random variables (bit-exact Philox stream) and per-element records N, D, |D|^2 (one lane per element);
+ *  2. expansion of [P; Q] = M1 .. MN [Rl; 1] and of D (or E = prod |D_e|^2) from the load end: lane i holds the coefficient
+ *     of sn^i (of y^i for E); lanes 30, 31 of P, Q, D stay zero, so the rotating shuffles bring zeros into lanes 0 and 1.
+ * xw / elw / cplw: this warp's scratch in shared memory (variates, element records, coupler record). */
+template <bool CPL, int DEN>
+__device__ __forceinline__ void tf_sample_stage(const TfParams &P, unsigned long long s, int lane, double *xw, double *elw, double *cplw,
+                                                double &p, double &q, double &d)
+{
+    const int up1 = (lane + 31) & 31, up2 = (lane + 30) & 31;
+    for (int v = lane; v < P.n_var; v += 32) xw[v] = qo_stream_variate(P.seed, P.sample_offset + s, (uint32_t)v, P.dist);
+    __syncwarp();
+    if (lane < P.n_el) tf_derive(P.prog, P.el0 + lane, xw, P.wref, P.zn, P.zni, elw + lane * QO_TF_REC);
+    if (CPL && lane == 31) {
+        double nom_k[2];
+        lad_derive<double>(P.prog, P.cpl_op, xw, cplw, P.cplms ? P.cplms + 4 * s : NULL, nom_k);
+        /* equal mode angles: the block's row vector in c^2, s^2, c s with five per-sample constants (tf_cpl_matched_same) */
+        double *o = cplw;
+        const double cE = o[0], hE = o[1], cO = o[2], hO = o[3];
+        const double k1 = cE * cO, k2 = cE + cO, k3 = fma(hE, cO, hO * cE), k4 = hE + hO;
+        o[10] = k1 - k3; o[11] = k1 + k3; o[12] = 2.0 * (k2 - k4); o[13] = 2.0 * (k2 + k4); o[14] = k2 * k2; o[15] = 0.0;
+    }
+    __syncwarp();
+    p = lane == 0 ? P.rl : 0.0; q = lane == 0 ? P.zn : 0.0; d = lane == 0 ? 1.0 : 0.0;
+    for (int e = P.n_el - 1; e >= 0; e--) {
+        const double2 n01 = *(const double2 *)(elw + e * QO_TF_REC), n2d0 = *(const double2 *)(elw + e * QO_TF_REC + 2),
+                      d12 = *(const double2 *)(elw + e * QO_TF_REC + 4);
+        const bool series = elw[e * QO_TF_REC + 9] != 0.0;
+        const double p1 = tf_up(p, up1), p2 = tf_up(p, up2), q1 = tf_up(q, up1), q2 = tf_up(q, up2);
+        const double dp = fma(n2d0.y, p, fma(d12.x, p1, d12.y * p2)), dq = fma(n2d0.y, q, fma(d12.x, q1, d12.y * q2));
+        if (series) {            /* Z = N/D: P <- D P + N Q, Q <- D Q */
+            p = fma(n01.x, q, fma(n01.y, q1, fma(n2d0.x, q2, dp))); q = dq;
+        } else {                 /* Y = N/D: Q <- D Q + N P, P <- D P */
+            q = fma(n01.x, p, fma(n01.y, p1, fma(n2d0.x, p2, dq))); p = dp;
+        }
+        if (DEN != QO_TF_DEN_NONE) {
+            double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
+            if (DEN == QO_TF_DEN_E) {
+                /* lane m holds the coefficient of y^m; E's degree may pass lane 29, so no free wrap-around here */
+                const double2 e01 = *(const double2 *)(elw + e * QO_TF_REC + 6);
+                const double e2 = elw[e * QO_TF_REC + 8];
+                d1 = lane >= 1 ? d1 : 0.0; d2 = lane >= 2 ? d2 : 0.0;
+                d = fma(e01.x, d, fma(e01.y, d1, e2 * d2));
+            } else d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
+        }
+    }
+    __syncwarp();                /* the scratch may be rewritten for the next sample */
+}
+
+/* Horner evaluation, in y, of NN real polynomials kept as a ROW TABLE in shared memory: row k (NN doubles at base + k*NN*8)
+ * holds coefficient k of every polynomial; `k` rows are kept (run-time, uniform over the launch):
+ *     r = (..((c[k-1] y + c[k-2]) y + c[k-3]) ..) y + c[0]
+ * The first step takes the two top rows as FMA operands -- the top coefficient is never copied into PTS registers per chain
+ * (that alone was 38 register moves per iteration of 8 points).  The remaining k - 2 steps run as straight-line blocks of two
+ * rows with immediate-offset loads, entered through one computed branch: no loop counter, no address arithmetic. */
+template <int NN, int PTS>
+__device__ __forceinline__ void tf_horner_rows(unsigned int base, int k, const double (&y)[PTS], double (&r)[NN][PTS])
+{
+    constexpr unsigned int RB = NN * 8u;
+    /* k >= 2: the plan pads a constant polynomial with a zero coefficient (rows beyond the degree hold zeros) */
+    {
+        const unsigned int at = base + (unsigned int)(k - 1) * RB;
+        LadV2<double> t[NN / 2], u[NN / 2];
+#pragma unroll
+        for (int c = 0; c < NN; c += 2) { t[c / 2] = lad_lds2(at + c * 8u, 0.0); u[c / 2] = lad_lds2(at - RB + c * 8u, 0.0); }
+#pragma unroll
+        for (int c = 0; c < NN; c += 2) { QO_PTS { r[c][p] = fma(t[c / 2].x, y[p], u[c / 2].x); r[c + 1][p] = fma(t[c / 2].y, y[p], u[c / 2].y); } }
+    }
+#define QO_TF_ROW(addr)                                                                                                 \
+    {                                                                                                                   \
+        LadV2<double> cc[NN / 2];                                                                                       \
+        _Pragma("unroll") for (int c = 0; c < NN; c += 2) cc[c / 2] = lad_lds2((addr) + c * 8u, 0.0);                   \
+        _Pragma("unroll") for (int c = 0; c < NN; c += 2) {                                                             \
+            QO_PTS { r[c][p] = fma(r[c][p], y[p], cc[c / 2].x); r[c + 1][p] = fma(r[c + 1][p], y[p], cc[c / 2].y); }    \
+        }                                                                                                               \
+    }
+    int m = k - 2;                                /* rows m-1 .. 0 remain */
+    if (m & 1) { m--; QO_TF_ROW(base + (unsigned int)m * RB) }
+#define QO_TF_BLOCK(b) case b: QO_TF_ROW(base + (2 * (b) - 1) * RB) QO_TF_ROW(base + (2 * (b) - 2) * RB)
+    switch (m >> 1) {
+        QO_TF_BLOCK(7) QO_TF_BLOCK(6) QO_TF_BLOCK(5) QO_TF_BLOCK(4) QO_TF_BLOCK(3) QO_TF_BLOCK(2) QO_TF_BLOCK(1)
+    default: break;
+    }
+#undef QO_TF_BLOCK
+#undef QO_TF_ROW
+}
+
+/* One real polynomial E(y) with `kd` (even) coefficients stored contiguously, two per 16-byte load: same structure. */
+template <int PTS>
+__device__ __forceinline__ void tf_horner_e(unsigned int base, int kd, const double (&y)[PTS], double (&dd)[PTS])
+{
+    int m = (kd >> 1) - 1;                        /* coefficient pairs m-1 .. 0 remain after the top pair */
+    { const LadV2<double> t = lad_lds2(base + (unsigned int)m * 16u, 0.0); QO_PTS dd[p] = fma(t.y, y[p], t.x); }
+#define QO_TF_PAIR(addr) { const LadV2<double> cc = lad_lds2((addr), 0.0); QO_PTS { dd[p] = fma(dd[p], y[p], cc.y); } QO_PTS { dd[p] = fma(dd[p], y[p], cc.x); } }
+    if (m & 1) { m--; QO_TF_PAIR(base + (unsigned int)m * 16u) }
+#define QO_TF_BLOCK(b) case b: QO_TF_PAIR(base + (2 * (b) - 1) * 16u) QO_TF_PAIR(base + (2 * (b) - 2) * 16u)
+    switch (m >> 1) {
+        QO_TF_BLOCK(7) QO_TF_BLOCK(6) QO_TF_BLOCK(5) QO_TF_BLOCK(4) QO_TF_BLOCK(3) QO_TF_BLOCK(2) QO_TF_BLOCK(1)
+    default: break;
+    }
+#undef QO_TF_BLOCK
+#undef QO_TF_PAIR
+}
+
+/* running extreme of PTS values: a tree (depth log2 PTS + 1) instead of a chain of PTS dependent compare / select pairs */
+template <int PTS, bool MIN>
+__device__ __forceinline__ double tf_extreme(const double (&v)[PTS], double trk)
+{
+    double t[PTS];
+    QO_PTS t[p] = v[p];
+#pragma unroll
+    for (int w = PTS / 2; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int i = 0; i < w; i++) t[i] = MIN ? (t[i + w] < t[i] ? t[i + w] : t[i]) : (t[i + w] > t[i] ? t[i + w] : t[i]);
+    }
+    return MIN ? (t[0] < trk ? t[0] : trk) : (t[0] > trk ? t[0] : trk);
+}
+
 /*
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
  * CPLM   0 no coupler; 1 coupled-line block in front (its row vector is contracted with [P; Q] per point), mode angles from
@@ -186,12 +305,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     const int ncnt = 2 + P.nspec + (P.hist_bins > 0 ? P.hist_bins : 0);
     for (int i = threadIdx.x; i < ncnt; i += TPB) s_cnt[i] = 0;
     __syncthreads();
-
     double *numw = s_num[warp] + 2 * NN, *denw = s_den[warp] + (DEN == QO_TF_DEN_NONE ? 0 : 4), *elw = s_el[warp], *xw = s_x[warp];
     const unsigned int nums = (unsigned int)__cvta_generic_to_shared(numw), dens = (unsigned int)__cvta_generic_to_shared(denw);
     const unsigned int cpls = (unsigned int)__cvta_generic_to_shared(s_cpl[warp]);
     const double rs = P.rs;
-    const int up1 = (lane + 31) & 31, up2 = (lane + 30) & 31;
     const int hs = P.hist_spec;
     const bool hneg = hs >= 0 && P.neg[hs & (QO_TF_NSPEC - 1)];
     const int kn = P.kn, kd = P.kd;
@@ -201,45 +318,9 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     while (s < P.nsamples) {
         unsigned long long s_next = 0;
         if (lane == 0) s_next = total_warps + atomicAdd(P.ticket, 1ull);
-        /* 1. the sample's random variables and element records */
-        for (int v = lane; v < P.n_var; v += 32) xw[v] = qo_stream_variate(P.seed, P.sample_offset + s, (uint32_t)v, P.dist);
-        __syncwarp();
-        if (lane < P.n_el) tf_derive(P.prog, P.el0 + lane, xw, P.wref, P.zn, P.zni, elw + lane * QO_TF_REC);
-        if (CPL && lane == 31) {
-            double nom_k[2];
-            lad_derive<double>(P.prog, P.cpl_op, xw, s_cpl[warp], P.cplms ? P.cplms + 4 * s : NULL, nom_k);
-            /* equal mode angles: the block's row vector in c^2, s^2, c s with five per-sample constants (tf_cpl_matched_same) */
-            double *o = s_cpl[warp];
-            const double cE = o[0], hE = o[1], cO = o[2], hO = o[3];
-            const double k1 = cE * cO, k2 = cE + cO, k3 = fma(hE, cO, hO * cE), k4 = hE + hO;
-            o[10] = k1 - k3; o[11] = k1 + k3; o[12] = 2.0 * (k2 - k4); o[13] = 2.0 * (k2 + k4); o[14] = k2 * k2; o[15] = 0.0;
-        }
-        __syncwarp();
-        /* 2. expand [P; Q] and D (or E) from the load end: lane i holds the coefficient of sn^i (of y^i for E); lanes 30, 31
-         *    of P, Q, D stay zero, so the rotating shuffles bring zeros into lanes 0 and 1 */
-        double p = lane == 0 ? P.rl : 0.0, q = lane == 0 ? P.zn : 0.0, d = lane == 0 ? 1.0 : 0.0;
-        for (int e = P.n_el - 1; e >= 0; e--) {
-            const double2 n01 = *(const double2 *)(elw + e * QO_TF_REC), n2d0 = *(const double2 *)(elw + e * QO_TF_REC + 2),
-                          d12 = *(const double2 *)(elw + e * QO_TF_REC + 4);
-            const bool series = elw[e * QO_TF_REC + 9] != 0.0;
-            const double p1 = tf_up(p, up1), p2 = tf_up(p, up2), q1 = tf_up(q, up1), q2 = tf_up(q, up2);
-            const double dp = fma(n2d0.y, p, fma(d12.x, p1, d12.y * p2)), dq = fma(n2d0.y, q, fma(d12.x, q1, d12.y * q2));
-            if (series) {            /* Z = N/D: P <- D P + N Q, Q <- D Q */
-                p = fma(n01.x, q, fma(n01.y, q1, fma(n2d0.x, q2, dp))); q = dq;
-            } else {                 /* Y = N/D: Q <- D Q + N P, P <- D P */
-                q = fma(n01.x, p, fma(n01.y, p1, fma(n2d0.x, p2, dq))); p = dp;
-            }
-            if (DEN != QO_TF_DEN_NONE) {
-                double d1 = tf_up(d, up1), d2 = tf_up(d, up2);
-                if (DEN == QO_TF_DEN_E) {
-                    /* lane m holds the coefficient of y^m; E's degree may pass lane 29, so no free wrap-around here */
-                    const double2 e01 = *(const double2 *)(elw + e * QO_TF_REC + 6);
-                    const double e2 = elw[e * QO_TF_REC + 8];
-                    d1 = lane >= 1 ? d1 : 0.0; d2 = lane >= 2 ? d2 : 0.0;
-                    d = fma(e01.x, d, fma(e01.y, d1, e2 * d2));
-                } else d = fma(n2d0.y, d, fma(d12.x, d1, d12.y * d2));
-            }
-        }
+        /* 1. + 2. variates, element records, expansion of [P; Q] and D (or E): lane i ends up with the coefficient of sn^i */
+        double p, q, d;
+        tf_sample_stage<CPL, DEN>(P, s, lane, xw, elw, s_cpl[warp], p, q, d);
         /* Horner tables (kept coefficients only; E is padded to an even count with a zero) */
         if (GD) {
             /* rows (c_2k, c_2k+1, (2k+1) c_2k+1, (2k+2) c_2k+2): the polynomial and its derivative d/dsn, even / odd parts */
@@ -302,83 +383,35 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
             if (P.cpl_fast) lad_cpl_angles<double, PTS, true>(cpls, w0, tse, tce, tso, tco, rse, rce, rso, rco);
             else lad_cpl_angles<double, PTS, false>(cpls, w0, tse, tce, tso, tco, rse, rce, rso, rco);
         }
+        double y[PTS];                     /* carried: the next iteration's values are requested as soon as this one is done with them */
+#pragma unroll
+        for (int qq = 0; qq < PP; qq++) {
+            const double2 a = P.yt[lane + 32 * qq];
+            y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
+        }
         for (int it = 0; it < P.niter; it++) {
             const int j0 = it * (32 * PP) + lane;
-            double y[PTS];
-#pragma unroll
-            for (int qq = 0; qq < PP; qq++) {
-                const double2 a = P.yt[j0 + 32 * qq];
-                y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
-            }
-            /* numerator polynomials: Horner in y from the highest kept pair.  The coefficients of step k+1 are requested
-             * before the FMAs of step k (the row below row 0 is a guard row), so no chain waits on a shared-memory load */
+            const uchar2 am = P.itm[it];       /* requested here, needed after the Horner chains */
+            /* numerator polynomials: Horner in y from the highest kept pair (tf_horner_rows) */
             double r[NN][PTS];
-            {
-                unsigned int a = nums + (unsigned int)(kn - 1) * (NN * 8u);
-                LadV2<double> cur[NN / 2], nxt[NN / 2];
-#pragma unroll
-                for (int c = 0; c < NN; c += 2) {
-                    cur[c / 2] = lad_lds2(a + c * 8u, 0.0);
-                    QO_PTS { r[c][p] = cur[c / 2].x; r[c + 1][p] = cur[c / 2].y; }
-                }
-                a -= NN * 8u;
-#pragma unroll
-                for (int c = 0; c < NN; c += 2) nxt[c / 2] = lad_lds2(a + c * 8u, 0.0);
-#define QO_TF_NUM_STEP                                                                                                  \
-                {                                                                                                       \
-                    a -= NN * 8u;                                                                                       \
-                    _Pragma("unroll") for (int c = 0; c < NN; c += 2) { cur[c / 2] = nxt[c / 2]; nxt[c / 2] = lad_lds2(a + c * 8u, 0.0); } \
-                    _Pragma("unroll") for (int c = 0; c < NN; c += 2) {                                                 \
-                        QO_PTS { r[c][p] = fma(r[c][p], y[p], cur[c / 2].x); r[c + 1][p] = fma(r[c + 1][p], y[p], cur[c / 2].y); } \
-                    }                                                                                                   \
-                }
-                /* kn - 1 Horner steps: one peeled when odd, then two per trip (no remainder loop) */
-                if (!(kn & 1)) QO_TF_NUM_STEP
-#pragma unroll 2
-                for (int k = (kn - 1) >> 1; k > 0; k--) { QO_TF_NUM_STEP QO_TF_NUM_STEP }
-#undef QO_TF_NUM_STEP
-            }
+            tf_horner_rows<NN, PTS>(nums, kn, y, r);
             /* dd = |D(jx)|^2 */
             double dd[PTS], gA[PTS], gB[PTS];        /* gA = Re(Num' conj Num), gB = Re(D' conj D) (group-delay kernels) */
             QO_PTS gB[p] = 0.0;
             if (DEN == QO_TF_DEN_E) {
-                unsigned int a = dens + (unsigned int)(kd - 2) * 8u;          /* kd is even: two coefficients per load */
-                LadV2<double> cur = lad_lds2(a, 0.0), nxt;
-                QO_PTS dd[p] = fma(cur.y, y[p], cur.x);
-                a -= 16u;
-                nxt = lad_lds2(a, 0.0);
-#pragma unroll 2
-                for (int k = kd - 4; k >= 0; k -= 2) {
-                    a -= 16u;
-                    cur = nxt; nxt = lad_lds2(a, 0.0);
-                    QO_PTS { dd[p] = fma(dd[p], y[p], cur.y); dd[p] = fma(dd[p], y[p], cur.x); }
-                }
+                tf_horner_e<PTS>(dens, kd, y, dd);
             } else if (DEN == QO_TF_DEN_D) {
-                double de[PTS], dq[PTS];
-                unsigned int a = dens + (unsigned int)(kd - 1) * 16u;
-                { const LadV2<double> cc = lad_lds2(a, 0.0); QO_PTS { de[p] = cc.x; dq[p] = cc.y; } }
-#pragma unroll 4
-                for (int k = kd - 2; k >= 0; k--) {
-                    a -= 16u;
-                    const LadV2<double> cc = lad_lds2(a, 0.0);
-                    QO_PTS { de[p] = fma(de[p], y[p], cc.x); dq[p] = fma(dq[p], y[p], cc.y); }
-                }
-                QO_PTS { const double t = dq[p] * dq[p]; dd[p] = fma(-y[p], t, de[p] * de[p]); }     /* |re + j x im|^2 = re^2 - y im^2 */
+                double dr[2][PTS];
+                tf_horner_rows<2, PTS>(dens, kd, y, dr);
+                QO_PTS { const double t = dr[1][p] * dr[1][p]; dd[p] = fma(-y[p], t, dr[0][p] * dr[0][p]); }     /* |re + j x im|^2 = re^2 - y im^2 */
             } else if (DEN == QO_TF_DEN_DD) {
                 /* D and D' (group delay): B = Re(D' conj D) = D'e De - y D'o Do */
-                double de[PTS], dq[PTS], dpe[PTS], dpo[PTS];
-                unsigned int a = dens + (unsigned int)(kd - 1) * 32u;
-                { const LadV2<double> c0 = lad_lds2(a, 0.0), c1 = lad_lds2(a + 16u, 0.0); QO_PTS { de[p] = c0.x; dq[p] = c0.y; dpe[p] = c1.x; dpo[p] = c1.y; } }
-#pragma unroll 2
-                for (int k = kd - 2; k >= 0; k--) {
-                    a -= 32u;
-                    const LadV2<double> c0 = lad_lds2(a, 0.0), c1 = lad_lds2(a + 16u, 0.0);
-                    QO_PTS { de[p] = fma(de[p], y[p], c0.x); dq[p] = fma(dq[p], y[p], c0.y); dpe[p] = fma(dpe[p], y[p], c1.x); dpo[p] = fma(dpo[p], y[p], c1.y); }
-                }
+                double dr[4][PTS];
+                tf_horner_rows<4, PTS>(dens, kd, y, dr);
                 QO_PTS {
-                    const double t = dq[p] * dq[p];
-                    dd[p] = fma(-y[p], t, de[p] * de[p]);
-                    gB[p] = fma(-y[p], dpo[p] * dq[p], dpe[p] * de[p]);
+                    const double t = dr[1][p] * dr[1][p];
+                    dd[p] = fma(-y[p], t, dr[0][p] * dr[0][p]);
+                    gB[p] = fma(-y[p], dr[3][p] * dr[1][p], dr[2][p] * dr[0][p]);
                 }
             } else { QO_PTS dd[p] = 1.0; }
             /* n2 = |numerator|^2 (the coupler's row vector contracted with [P; Q]) */
@@ -480,7 +513,12 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 else if (P.neg[sp]) { QO_PTS sg[p] = tf_hi(fma(t, dd[p], n2[p])); }                                \
                 else { QO_PTS sg[p] = tf_hi(fma(t, dd[p], -n2[p])); }                                              \
             }
-            const uchar2 am = P.itm[it];
+            /* y is dead from here on: fetch the next iteration's (the tables carry one iteration of padding beyond the grid) */
+#pragma unroll
+            for (int qq = 0; qq < PP; qq++) {
+                const double2 a = P.yt[j0 + 32 * PP + 32 * qq];
+                y[2 * qq] = a.x; y[2 * qq + 1] = a.y;
+            }
             const unsigned int any = am.x, all = am.y;
             if (any == all) {
                 /* one mask on every point of the iteration (possibly none): no per-point selects */
@@ -489,8 +527,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     if ((all >> sp) & 1u) {
                         if (sp == hs) {
                             QO_TF_VALUE(val)
-                            if (hneg) { QO_PTS trkv = val[p] < trkv ? val[p] : trkv; }
-                            else { QO_PTS trkv = val[p] > trkv ? val[p] : trkv; }
+                            trkv = hneg ? tf_extreme<PTS, true>(val, trkv) : tf_extreme<PTS, false>(val, trkv);
                         } else {
                             QO_TF_SIGN(sg)
                             QO_PTS acc[sp] |= sg[p];

@@ -27,6 +27,12 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
 extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count, const TfParams *P, cudaStream_t st);
 extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs);
 
+/* thread-per-sample flavour (qo_ts.cuh): eligibility, threads per wave, launch (0 or the cudaError_t) */
+struct TsParams;
+extern "C" int qo_ts_eligible(const TfPlan *tp, int nspec, int cpl_rot_same);
+extern "C" int qo_ts_wave_threads(const TfPlan *tp, int sm_count);
+extern "C" int qo_ts_launch(const TfPlan *tp, int sm_count, const TsParams *Q, cudaStream_t st);
+
 /* spot-frequency kernel (qo_spot.cuh): one thread per sample, <= 8 frequencies; returns 0 or the cudaError_t of the launch */
 struct SpotParams;
 extern "C" int qo_spot_launch(int need_s11, int sm_count, const SpotParams *P, cudaStream_t st);

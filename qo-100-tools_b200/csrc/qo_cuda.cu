@@ -845,7 +845,7 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
         P.gd[s] = s < hp->nspec && hp->spec_kind[s] == SK_GD_MAX;
         P.thr[s] = s < hp->nspec ? (P.gd[s] ? hp->spec_thr[s] * p->tfp.wref : hp->spec_thr[s]) : 0.0;
     }
-    P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tfp.n_el; P.el0 = p->tfp.el0; P.kn = p->tfp.kn; P.kd = p->tfp.kd; P.nspec = hp->nspec; P.dist = hp->dist;
+    P.niter = p->tf_niter; P.n_var = hp->n_var; P.n_el = p->tfp.n_el; P.el0 = p->tfp.el0; P.kn = p->tfp.kn; P.kd = p->tfp.kd; P.den = p->tfp.den; P.nspec = hp->nspec; P.dist = hp->dist;
     P.hist_bins = hp->hist_bins;
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
     /* the bulk of a large launch runs thread-per-sample (qo_ts.cuh): whole rounds of one sample per resident thread, dealt
@@ -861,12 +861,13 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
             Q.t = P;
             Q.t.nsamples = nb * 32ull;
             Q.y1 = (const double *)d->tf_yt; Q.x1 = (const double *)d->tf_xt; Q.mw = (const uint2 *)d->tf_mb;
-            Q.npt = (p->nf + QO_TS_PT - 1) / QO_TS_PT * QO_TS_PT;
+            const int gpt = qo_ts_group_points(&p->tfp);
+            Q.npt = (p->nf + gpt - 1) / gpt * gpt;
             /* runs of groups with the same (OR, AND) of their points' spec bits; a group that straddles a band edge stands alone */
             bool runs_ok = true;
-            for (int gi = 0; gi < Q.npt / QO_TS_PT; gi++) {
+            for (int gi = 0; gi < Q.npt / gpt; gi++) {
                 unsigned int any = 0, all = 0xFF;
-                for (int k = gi * QO_TS_PT; k < (gi + 1) * QO_TS_PT; k++) { const unsigned int mk = k < p->nf ? p->maskv[k] : 0; any |= mk; all &= mk; }
+                for (int k = gi * gpt; k < (gi + 1) * gpt; k++) { const unsigned int mk = k < p->nf ? p->maskv[k] : 0; any |= mk; all &= mk; }
                 if (Q.nruns > 0 && any == all && Q.runs[Q.nruns - 1].any == any && Q.runs[Q.nruns - 1].all == all) { Q.runs[Q.nruns - 1].ngroups++; continue; }
                 if (Q.nruns == QO_TS_MAXRUN) { runs_ok = false; break; }
                 Q.runs[Q.nruns].ngroups = 1; Q.runs[Q.nruns].any = any; Q.runs[Q.nruns].all = all; Q.nruns++;

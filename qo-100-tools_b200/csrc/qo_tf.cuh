@@ -57,6 +57,7 @@ struct TfParams {
     int s11[QO_TF_NSPEC];                   /* the spec is on |S11|^2 = |P - Rs Q|^2 / |P + Rs Q|^2 (FAIL iff > thr) */
     int gd[QO_TF_NSPEC];                    /* the spec is on the group delay: thr = limit [s] * wref (FAIL iff tau * wref > thr) */
     int kn, kd;                              /* coefficient pairs kept per numerator polynomial; E coefficients (even) / D pairs kept */
+    int den;                                 /* QO_TF_DEN_* (a template parameter of qo_mc_tf_kernel; qo_ts.cuh reads it here) */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
     int cpl_lin;                             /* uniformly spaced grid: the mode angles advance by a constant step per iteration ... */

@@ -31,6 +31,7 @@ extern "C" int qo_tf_default_pp(const TfPlan *tp, int npairs);
 struct TsParams;
 extern "C" int qo_ts_eligible(const TfPlan *tp, int nspec, int cpl_rot_same);
 extern "C" int qo_ts_wave_threads(const TfPlan *tp, int sm_count);
+extern "C" int qo_ts_group_points(const TfPlan *tp);
 extern "C" int qo_ts_launch(const TfPlan *tp, int sm_count, const TsParams *Q, cudaStream_t st);
 
 /* spot-frequency kernel (qo_spot.cuh): one thread per sample, <= 8 frequencies; returns 0 or the cudaError_t of the launch */

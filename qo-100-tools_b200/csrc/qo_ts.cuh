@@ -15,8 +15,8 @@
  *   stage A  variates (the same bit-exact Philox stream, one call per perturbed parameter), element records, and the
  *            expansion of [P; Q] and E as TRUNCATED polynomials in registers.  Multiplying by a branch's (a0 + a1 s + a2 s^2)
  *            only moves coefficients upwards, so the 2 KN lowest coefficients of P, Q and the KE lowest of E -- the ones the
- *            plan keeps -- are exact without ever forming the higher ones.  Register arrays need static indices: the kernel
- *            carries one body per (KN, KE) pair up to the capacities below and picks it ONCE per launch;
+ *            plan keeps -- are exact without ever forming the higher ones.  Register arrays need static indices: there is one
+ *            kernel per numerator length KN, carrying one body per denominator length KE, up to the capacities below;
  *   stage C  the frequency loop runs over ALL grid points per thread, PT points in flight.  The grid value y is the same for
  *            the whole warp (a broadcast load per group of points, nothing per Horner step), every DFMA takes its coefficient
  *            from a register, the per-spec sign accumulators / the histogram tracker are thread-private: no shuffles, no
@@ -33,8 +33,13 @@
 #include "qo_tf.cuh"
 
 #define QO_TS_TPB 128
-#define QO_TS_MINB 4
-#define QO_TS_PT 4               /* points in flight per thread */
+/* points in flight per thread / resident blocks per SM: plain ladders hold <= 36 coefficients (72 registers) and run four
+ * points at 128 registers; behind a coupled-line block P and Q stay apart (<= 40 coefficients + the block's constants and the
+ * rotating angle), two points at 168 registers */
+#define QO_TS_PT2 4
+#define QO_TS_MINB2 3
+#define QO_TS_PT4 2
+#define QO_TS_MINB4 3
 #define QO_TS_CAPN2 10           /* plain ladders (NN = 2): numerator coefficient pairs held in registers */
 #define QO_TS_CAPE2 16           /* ... and E coefficients */
 #define QO_TS_CAPN4 8            /* behind a coupled-line block (NN = 4: P and Q apart) */
@@ -47,7 +52,7 @@ struct TsParams {
     TfParams t;                          /* the job, exactly as qo_mc_tf_kernel takes it */
     const double *y1, *x1;               /* per POINT: -(w/wref)^2 and w/wref (the same tables, read as scalars) */
     const uint2 *mw;                     /* per point: byte masks of specs 0-3 (x) and 4-7 (y) */
-    struct { int ngroups; unsigned int any, all; } runs[QO_TS_MAXRUN];      /* runs of groups that see the same spec bits */
+    struct { int ngroups; unsigned int any, all; } runs[QO_TS_MAXRUN];      /* runs of groups (PT points each) that see the same spec bits */
     int nruns;
     int npt;                             /* points to walk: the grid rounded up to a whole group (padding carries no spec bit) */
     unsigned long long nbatches;         /* 32-sample batches, handed to the warps through a ticket counter */
@@ -56,14 +61,14 @@ struct TsParams {
 };
 
 /* stage C for one (KN, KE): everything in registers.
- * The grid is walked as a few RUNS of groups (QO_TS_PT points each) that see the same spec bits (TsParams::runs, built by the
+ * The grid is walked as a few RUNS of groups (PT points each) that see the same spec bits (TsParams::runs, built by the
  * plan from the band edges): inside a run the spec bookkeeping branches on loop-invariant, warp-uniform predicates -- nothing
  * is loaded or decoded per group except the PT grid values themselves.  Groups that straddle a band edge are runs of their own
  * and take their per-point byte masks. */
-template <int NN, int KN, int KE, bool CPL, int NS>
+template <int NN, int KN, int KE, bool CPL, int NS, int PT>
 __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sample, unsigned int (&acc)[NS], double &trkv)
 {
-    constexpr int PT = QO_TS_PT;
+    static_assert(PT == 2 || PT == 4, "two or four points in flight");
     constexpr int NC = 2 * KN;           /* kept coefficients per numerator polynomial */
     static_assert(KN >= 2 && (KE == 0 || KE >= 2), "the plan keeps at least two rows");
     const TfParams &P = Q.t;
@@ -131,10 +136,8 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
     const bool hneg = hs >= 0 && P.neg[hs & (QO_TF_NSPEC - 1)];
     const double zq = P.rs * P.zni;
     double y[PT];
-    {
-        const double2 a = __ldg((const double2 *)Q.y1), b = __ldg((const double2 *)(Q.y1 + 2));
-        y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
-    }
+#pragma unroll
+    for (int h = 0; h < PT; h += 2) { const double2 a = __ldg((const double2 *)(Q.y1 + h)); y[h] = a.x; y[h + 1] = a.y; }
     /* one group of PT points: all NN * PT numerator chains and the PT chains of E advance together (one long stream of
      * independent FMAs), then |numerator|^2 (behind a coupler: contracted with the block's row vector), and -- y being dead by
      * then -- the request for the next group's grid values (the tables carry padding beyond the grid).
@@ -155,10 +158,7 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
             QO_PTS_N(PT) { const double t_ = r[1][p] * r[1][p]; n2[p] = fma(-y[p], t_, r[0][p] * r[0][p]); }         \
         } else {                                                                                                     \
             double x[PT];                                                                                            \
-            {                                                                                                        \
-                const double2 a_ = __ldg((const double2 *)(Q.x1 + j)), b_ = __ldg((const double2 *)(Q.x1 + j + 2));  \
-                x[0] = a_.x; x[1] = a_.y; x[2] = b_.x; x[3] = b_.y;                                                  \
-            }                                                                                                        \
+            _Pragma("unroll") for (int h = 0; h < PT; h += 2) { const double2 a_ = __ldg((const double2 *)(Q.x1 + j + h)); x[h] = a_.x; x[h + 1] = a_.y; } \
             QO_PTS_N(PT) {                                                                                           \
                 const double c2 = cs * cs, s2 = sn * sn, sc = cs * sn, c4 = 4.0 * c2;                                \
                 const double uar = fma(-k0x, s2, c4), ubr = fma(-k0y, s2, c4), uai = k2x * sc, ubi = k2y * sc;       \
@@ -172,10 +172,7 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
                 sn = s1; cs = c1;                                                                                    \
             }                                                                                                        \
         }                                                                                                            \
-        {                                                                                                            \
-            const double2 a_ = __ldg((const double2 *)(Q.y1 + j + PT)), b_ = __ldg((const double2 *)(Q.y1 + j + PT + 2)); \
-            y[0] = a_.x; y[1] = a_.y; y[2] = b_.x; y[3] = b_.y;                                                      \
-        }
+        _Pragma("unroll") for (int h = 0; h < PT; h += 2) { const double2 a_ = __ldg((const double2 *)(Q.y1 + j + PT + h)); y[h] = a_.x; y[h + 1] = a_.y; }
 #define QO_TS_VALUE                                                                                                  \
         double val[PT];                                                                                              \
         if (KE < 2 && !CPL) { QO_PTS_N(PT) val[p] = n2[p]; }                                                         \
@@ -230,62 +227,36 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
 }
 
 /* the body for this launch's (kn, kd): one switch per launch, outside the frequency loop */
-#ifdef QO_TS_DEV_KN          /* development builds: one loop body only */
-#define QO_TS_KN_OK(k) ((k) == QO_TS_DEV_KN)
-#define QO_TS_KE_OK(k) ((k) == QO_TS_DEV_KE)
+#ifdef QO_TS_DEV_KN          /* development builds: a few loop bodies only */
+#define QO_TS_KN_OK(k) ((k) == QO_TS_DEV_KN || (k) == QO_TS_DEV_KN2)
+#define QO_TS_KE_OK(k) ((k) == QO_TS_DEV_KE || (k) == QO_TS_DEV_KE2)
 #else
 #define QO_TS_KN_OK(k) true
 #define QO_TS_KE_OK(k) true
 #endif
-template <int NN, int KN, bool CPL, int DEN, int NS>
+/* the loop body for this launch's kd (KN is the kernel's): one switch per sample, outside the frequency loop */
+template <int NN, int KN, bool CPL, int NS, int PT>
 __device__ __forceinline__ void ts_pick_e(const TsParams &Q, unsigned long long sample, unsigned int (&acc)[NS], double &trkv)
 {
-    if (DEN == QO_TF_DEN_NONE) { ts_loop<NN, KN, 0, CPL, NS>(Q, sample, acc, trkv); return; }
-    switch (Q.t.kd) {
-    case 2: if (QO_TS_KE_OK(2)) ts_loop<NN, KN, 2, CPL, NS>(Q, sample, acc, trkv); break;
-    case 4: if (QO_TS_KE_OK(4)) ts_loop<NN, KN, 4, CPL, NS>(Q, sample, acc, trkv); break;
-    case 6: if (QO_TS_KE_OK(6)) ts_loop<NN, KN, 6, CPL, NS>(Q, sample, acc, trkv); break;
-    case 8: if (QO_TS_KE_OK(8)) ts_loop<NN, KN, 8, CPL, NS>(Q, sample, acc, trkv); break;
-    default:
-        if (NN == 2) switch (Q.t.kd) {
-            case 10: if (QO_TS_KE_OK(10)) ts_loop<NN, KN, NN == 2 ? 10 : 2, CPL, NS>(Q, sample, acc, trkv); break;
-            case 12: if (QO_TS_KE_OK(12)) ts_loop<NN, KN, NN == 2 ? 12 : 2, CPL, NS>(Q, sample, acc, trkv); break;
-            case 14: if (QO_TS_KE_OK(14)) ts_loop<NN, KN, NN == 2 ? 14 : 2, CPL, NS>(Q, sample, acc, trkv); break;
-            case 16: if (QO_TS_KE_OK(16)) ts_loop<NN, KN, NN == 2 ? 16 : 2, CPL, NS>(Q, sample, acc, trkv); break;
-            default: break;
-        }
-        break;
+    constexpr int CAPE = NN == 2 ? QO_TS_CAPE2 : QO_TS_CAPE4;
+    const int kd = Q.t.den == QO_TF_DEN_E ? Q.t.kd : 0;
+#define QO_TS_CASE(K) case K: if (K <= CAPE && QO_TS_KE_OK(K)) ts_loop<NN, KN, (K <= CAPE ? K : 0), CPL, NS, PT>(Q, sample, acc, trkv); break;
+#ifdef QO_TS_DEV_KN
+    if (!QO_TS_KN_OK(KN) || !QO_TS_KE_OK(kd)) __trap();          /* a development build was asked for a body it does not carry */
+#endif
+    switch (kd) {
+        QO_TS_CASE(0) QO_TS_CASE(2) QO_TS_CASE(4) QO_TS_CASE(6) QO_TS_CASE(8) QO_TS_CASE(10) QO_TS_CASE(12) QO_TS_CASE(14) QO_TS_CASE(16)
+    default: __trap();                                            /* qo_ts_eligible admits only the lengths above */
     }
+#undef QO_TS_CASE
 }
 
-template <int NN, bool CPL, int DEN, int NS>
-__device__ __forceinline__ void ts_pick(const TsParams &Q, unsigned long long sample, unsigned int (&acc)[NS], double &trkv)
-{
-    switch (Q.t.kn) {
-    case 2: if (QO_TS_KN_OK(2)) ts_pick_e<NN, 2, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 3: if (QO_TS_KN_OK(3)) ts_pick_e<NN, 3, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 4: if (QO_TS_KN_OK(4)) ts_pick_e<NN, 4, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 5: if (QO_TS_KN_OK(5)) ts_pick_e<NN, 5, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 6: if (QO_TS_KN_OK(6)) ts_pick_e<NN, 6, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 7: if (QO_TS_KN_OK(7)) ts_pick_e<NN, 7, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    case 8: if (QO_TS_KN_OK(8)) ts_pick_e<NN, 8, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-    default:
-        if (NN == 2) switch (Q.t.kn) {
-            case 9: if (QO_TS_KN_OK(9)) ts_pick_e<NN, NN == 2 ? 9 : 2, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-            case 10: if (QO_TS_KN_OK(10)) ts_pick_e<NN, NN == 2 ? 10 : 2, CPL, DEN, NS>(Q, sample, acc, trkv); break;
-            default: break;
-        }
-        break;
-    }
-}
-
-template <int NN, int DEN, bool CPL>
-__global__ void __launch_bounds__(QO_TS_TPB, QO_TS_MINB) qo_mc_ts_kernel(const __grid_constant__ TsParams Q)
+template <int NN, bool CPL, int PT, int MINB, int KN>
+__global__ void __launch_bounds__(QO_TS_TPB, MINB) qo_mc_ts_kernel(const __grid_constant__ TsParams Q)
 {
     constexpr int NS = 4;
     static_assert(NN == 2 || NN == 4, "two or four numerator chains");
     static_assert(CPL == (NN == 4), "P and Q stay apart exactly when a coupled-line block is in front");
-    static_assert(DEN == QO_TF_DEN_NONE || DEN == QO_TF_DEN_E, "|D|^2 as one real polynomial, or no denominator");
     const TfParams &P = Q.t;
     __shared__ unsigned int s_cnt[2 + QO_NSPEC_MAX + QO_MAX_HIST];
     const int lane = threadIdx.x & 31;
@@ -307,7 +278,7 @@ __global__ void __launch_bounds__(QO_TS_TPB, QO_TS_MINB) qo_mc_ts_kernel(const _
 #pragma unroll
         for (int sp = 0; sp < NS; sp++) acc[sp] = 0u;
         double trkv = hneg ? 1.7e308 : -1.7e308;
-        ts_pick<NN, CPL, DEN, NS>(Q, sample, acc, trkv);
+        ts_pick_e<NN, KN, CPL, NS, PT>(Q, sample, acc, trkv);
         /* stage D: verdict per thread */
         unsigned int fail = 0;
 #pragma unroll

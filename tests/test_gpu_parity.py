@@ -813,6 +813,56 @@ def test_tf_kernel_equals_chain_kernel_at_2e6_samples(Q, W, ctx, monkeypatch, wh
     assert int(a["hist"].sum()) == n and 0.5 < a["n_pass"] / n < 0.8
 
 
+@pytest.mark.parametrize("which", ["cfg2", "cfg5", "ideal11", "if_bpf"])
+def test_thread_per_sample_kernel_equals_warp_per_sample_and_oracle(Q, R, W, ctx, monkeypatch, which):
+    """Large launches run thread-per-sample (qo_mc_ts_kernel: coefficients in registers, truncated in-register expansion); what
+    is left of a launch after whole 32-sample batches, and every small launch, runs warp-per-sample (qo_mc_tf_kernel).  Same
+    integers from both, for a sample count that is NOT a multiple of 32 and an offset beyond 2^32; a slice of the same range
+    against the oracle."""
+    import torch
+    if which == "cfg2":
+        w = W.cfg2()
+    elif which == "cfg5":
+        w = W.cfg5()
+    elif which == "ideal11":
+        fc = 10e6
+        net = Q.Net.cheby_lpf(11, 0.1, fc, 50.0, True)
+        w = W.Workload("ideal11", net, Q.grid_log(fc / 2.5, fc * 6.25, 1003), [(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -0.5), (Q.SPEC_S21_MAX_DB, 1.3 * fc, 1e99, -49.0)],
+                       Q.lc_tolerances(net, 0.05, 0.02), dict(hist_bins=64, hist_spec=1, hist_lo=-80.0, hist_hi=-40.0), 0, 13)
+    else:
+        net = W.if_bpf_net()
+        f = Q.grid_log(300e6 / 3.5, 500e6 * 3.5, 2050)
+        w = W.Workload("ifbpf", net, f, [(Q.SPEC_S21_MIN_DB, 3.6e8, 4.4e8, -1.2), (Q.SPEC_S21_MAX_DB, 9e8, 1e99, -28.0), (Q.SPEC_S21_MAX_DB, 0.0, 1.5e8, -30.0)],
+                       Q.lc_tolerances(net, 0.05, 0.05), dict(hist_bins=64, hist_spec=0, hist_lo=-6.0, hist_hi=0.0), 0, 11)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    n = 2 * sm * 4 * 128 + 37 * 32 + 19                 # enough for the thread-per-sample path, not a multiple of 32
+    off = (1 << 33) + 12345
+    res = {}
+    for kern in ("auto", "tf"):
+        if kern == "tf":
+            monkeypatch.setenv("QO100NET_KERNEL", "tf")
+        else:
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
+        plan.launch(off, n)
+        res[kern] = plan.read()
+        assert plan.kernel_name == ("qo_mc_ts_kernel" if kern == "auto" else "qo_mc_tf_kernel"), (kern, plan.kernel_name)
+        plan.close()
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    _assert_counts_equal(res["tf"], res["auto"])
+    assert res["auto"]["n_total"] == n and 0 < res["auto"]["n_pass"] < n and int(res["auto"]["hist"].sum()) == n
+    # the first 3000 samples of the range against the oracle (small launch: warp-per-sample) ...
+    m = 3000
+    rs, rl = w.net.terminations
+    og = R.mc_run(to_ref(R, w.net), rs, rl, w.f, w.specs, R.mc_cfg(w.seed, m, w.tols, sample_offset=off, **w.hist), nthreads=8)
+    gg = ctx.mc_run(w.net, w.f, w.specs, w.seed, m, w.tols, sample_offset=off, **w.hist)
+    _assert_counts_equal(og, gg)
+    # ... and additivity ties the big thread-per-sample launch to it: [off, off+n) = [off, off+m) + [off+m, off+n)
+    rest = ctx.mc_run(w.net, w.f, w.specs, w.seed, n - m, w.tols, sample_offset=off + m, **w.hist)
+    assert gg["n_pass"] + rest["n_pass"] == res["auto"]["n_pass"]
+    assert np.array_equal(gg["hist"] + rest["hist"], res["auto"]["hist"]) and np.array_equal(gg["fail_per_spec"] + rest["fail_per_spec"], res["auto"]["fail_per_spec"])
+
+
 def test_tf_kernel_values_within_1e_9(Q, W, ctx, monkeypatch):
     """north_star's FP64 tolerance on the transfer-function path, measured on VALUES rather than verdicts: the
     per-sample worst pass-band |S21| lands in the same bin of a 1024-bin histogram only 2e-3 dB wide (bins of
@@ -863,7 +913,7 @@ def test_tf_kernel_size_limits_and_degenerate_degrees(Q, R, W, ctx, monkeypatch)
     tol_r = [(0, 0, 0, Q.TOL_REL, 0.05), (1, 0, 1, Q.TOL_REL, 0.05), (2, 0, 2, Q.TOL_REL, 0.05)]
     got, info = run(pad, [(Q.SPEC_S21_MIN_DB, 0.0, 1e99, -3.05), (Q.SPEC_S21_MAX_DB, 0.0, 1e99, -2.95)], tol_r, "qo_mc_tf_kernel",
                     hist_bins=20, hist_spec=0, hist_lo=-3.3, hist_hi=-2.7)
-    assert info["degree"] == 0 and info["kn"] == 1 and 0 < got["n_pass"] < 400
+    assert info["degree"] == 0 and info["kn"] == 2 and 0 < got["n_pass"] < 400      # a constant is padded with a zero row (kn >= 2)
     one = Q.Net.from_elements([(Q.SER_L, [50.0 / wc])], 50.0, 50.0)
     got, info = run(one, [(Q.SPEC_S21_MIN_DB, 0.0, fc, -1.0)], [(0, 0, 0, Q.TOL_REL, 0.1)], "qo_mc_tf_kernel")
     assert info["degree"] == 1 and 0 < got["n_pass"] < 400

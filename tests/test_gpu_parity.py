@@ -832,7 +832,10 @@ def test_thread_per_sample_kernel_equals_warp_per_sample_and_oracle(Q, R, W, ctx
     else:
         net = W.if_bpf_net()
         f = Q.grid_log(300e6 / 3.5, 500e6 * 3.5, 2050)
-        w = W.Workload("ifbpf", net, f, [(Q.SPEC_S21_MIN_DB, 3.6e8, 4.4e8, -1.2), (Q.SPEC_S21_MAX_DB, 9e8, 1e99, -28.0), (Q.SPEC_S21_MAX_DB, 0.0, 1.5e8, -30.0)],
+        db = 20 * np.log10(np.abs(ctx.sweep(net, f)[1]))
+        pb = (f >= 3.6e8) & (f <= 4.4e8)
+        w = W.Workload("ifbpf", net, f, [(Q.SPEC_S21_MIN_DB, 3.6e8, 4.4e8, float(db[pb].min()) - 0.3), (Q.SPEC_S21_MAX_DB, 9e8, 1e99, float(db[f >= 9e8].max()) + 1.0),
+                                         (Q.SPEC_S21_MAX_DB, 0.0, 1.5e8, float(db[f <= 1.5e8].max()) + 1.0)],
                        Q.lc_tolerances(net, 0.05, 0.05), dict(hist_bins=64, hist_spec=0, hist_lo=-6.0, hist_hi=0.0), 0, 11)
     sm = torch.cuda.get_device_properties(0).multi_processor_count
     n = 2 * sm * 4 * 128 + 37 * 32 + 19                 # enough for the thread-per-sample path, not a multiple of 32

@@ -45,6 +45,8 @@ SAMPLES_PER_GPU = 1000000
 NF = 4096
 NORTH_STAR_SAMPLES = 100000000          # BASELINE config 5: 1e8 samples x 4096 points
 REF_SAMPLES_PER_STEP = 20000            # bounded sample of the reference arm (the workload is 1e6 per GPU per step)
+# the polynomial (transfer-function) kernels: thread-per-sample for the bulk of a large launch, warp-per-sample for the rest
+TF_KERNELS = ("qo_mc_ts_kernel", "qo_mc_tf_kernel")
 
 
 def host_cores():
@@ -237,7 +239,7 @@ def north_star_job(Q, qd, torch, ctx, stream, dist, rank, world, barrier, peak, 
     evals = total * NF
     out = {"workload": wl.name, "samples_total": total, "nf": NF, "n_gpus": world, "scaling": "strong",
            "samples_this_rank": hi - lo, "seconds": sec, "evals_per_s": evals / sec, "kernel": kname,
-           "kernel_plan": tfi if kname == "qo_mc_tf_kernel" else None,
+           "kernel_plan": tfi if kname in TF_KERNELS else None,
            "n_pass": c["n_pass"], "n_total": c["n_total"], "fail_per_spec": c["fail_per_spec"], "hist_mass": int(sum(c["hist"])),
            "yield": c["n_pass"] / max(1, c["n_total"]),
            "target": "north_star: 1e8 x 4096 on 8 x B200 at >= 50 % of aggregate FP64 FMA peak = 0.96 s (ladder, ALG-v1 349 flops/eval) "
@@ -487,7 +489,7 @@ def main():
                    "flops_per_eval_alg_v1": flops, "parallelism": "samples sharded x%d, u64 counter all-reduce" % world,
                    "l2": "no flush: the reduce-only path reads < 200 KB of tables by design (bytes/eval ~ 0); every "
                          "step draws a fresh global sample range",
-                   "kernel_plan": plan.tf_info if plan.kernel_name == "qo_mc_tf_kernel" else None,
+                   "kernel_plan": plan.tf_info if plan.kernel_name in TF_KERNELS else None,
                    "yield_last_step": last["n_pass"] / max(1, last["n_total"])},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "qo_mc_run (host buffers)"},
@@ -500,7 +502,8 @@ def main():
                      "alg_v1_tflops": alg_tflops, "alg_v1_ratio": alg_tflops / peak,
                      "note": "achieved = EXECUTED FP64 flops per eval (ncu smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on "
                              "of this kernel on this workload, DFMA = 2: profiles/executed_fp64.json) x evals / kernel time measured "
-                             "here; frac = achieved / peak.  alg_v1_ratio = SURVEY 8d's algorithmic count (a 2x2 complex chain step "
+                             "here (a step launches the thread-per-sample kernel for all whole 32-sample batches and the warp-per-"
+                             "sample kernel for the few samples left; kernel_ms covers both); frac = achieved / peak.  alg_v1_ratio = SURVEY 8d's algorithmic count (a 2x2 complex chain step "
                              "and a complex divide per element, 349 flops/eval) at the same rate over the same peak: above 1 because "
                              "the transfer-function kernel expands the cascade into real polynomials once per sample and runs Horner "
                              "per point, i.e. it does less work than ALG-v1 counts.  chain_kernel = the same job on the straight-line "
@@ -512,22 +515,24 @@ def main():
         line["north_star_job"] = ns_job
     if ctx_leg is not None:
         line["single_process_ctx"] = ctx_leg
-    if not args.no_extras and plan.kernel_name == "qo_mc_tf_kernel":
-        # the same workload on the straight-line ABCD-chain kernel (north_star (c) as worded), for comparison
-        os.environ["QO100NET_KERNEL"] = "ladder"
-        try:
-            p2 = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, **wl.hist)
-            c2 = torch.zeros(ncnt, dtype=torch.int64, device="cuda")
-            ms2 = time_plan(p2, stream, c2, nspg, max(3, args.steps // 2), 2, torch)
-            r2 = evals_per_launch / (ms2 * 1e-3)
-            line["roofline"]["chain_kernel"] = {"kernel": p2.kernel_name, "kernel_ms": ms2, "evals_per_s_per_gpu": r2,
-                                                "alg_v1_tflops": flops * r2 * 1e-12, "alg_v1_ratio": flops * r2 * 1e-12 / peak,
-                                                "executed": executed_view(p2.kernel_name, wl.name, r2, peak)}
-            p2.close()
-        except Exception as ex2:
-            line["roofline"]["chain_kernel"] = {"error": str(ex2)}
-        finally:
-            os.environ.pop("QO100NET_KERNEL", None)
+    if not args.no_extras and plan.kernel_name in TF_KERNELS:
+        # the same workload on the other kernels, for comparison: warp-per-sample polynomial kernel (round 1's headline kernel)
+        # and the straight-line ABCD-chain kernel (north_star (c) as worded)
+        for key, force in (("warp_per_sample_kernel", "tf"), ("chain_kernel", "ladder")):
+            os.environ["QO100NET_KERNEL"] = force
+            try:
+                p2 = Q.Plan(ctx, wl.net, wl.f, wl.specs, seed=wl.seed, tols=wl.tols, **wl.hist)
+                c2 = torch.zeros(ncnt, dtype=torch.int64, device="cuda")
+                ms2 = time_plan(p2, stream, c2, nspg, max(3, args.steps // 2), 2, torch)
+                r2 = evals_per_launch / (ms2 * 1e-3)
+                line["roofline"][key] = {"kernel": p2.kernel_name, "kernel_ms": ms2, "evals_per_s_per_gpu": r2,
+                                         "alg_v1_tflops": flops * r2 * 1e-12, "alg_v1_ratio": flops * r2 * 1e-12 / peak,
+                                         "executed": executed_view(p2.kernel_name, wl.name, r2, peak)}
+                p2.close()
+            except Exception as ex2:
+                line["roofline"][key] = {"error": str(ex2)}
+            finally:
+                os.environ.pop("QO100NET_KERNEL", None)
     if not args.no_extras and world == 1:
         # CPU baseline on a bounded sample of the same workload (rank 0, N = 1 only), oracle-built network
         try:

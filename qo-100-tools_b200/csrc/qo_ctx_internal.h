@@ -31,11 +31,17 @@ struct DevCtx {
     cudaEvent_t ev0, ev1;
 };
 
+struct qo_plan;
 struct qo_ctx {
     int ndev;
     DevCtx d[8];
     NcclApi nccl;
     ncclComm_t comm[8];
     int have_nccl;
+    /* the plan of the last qo_mc_run call, kept so that a caller who runs the same job again (a sweep over sample ranges, a
+     * benchmark loop) does not rebuild the program, the polynomial analysis and the device buffers; the tables are still
+     * copied host -> device on every call */
+    struct qo_plan *mc_cache;
+    unsigned long long mc_cache_key;
 };
 

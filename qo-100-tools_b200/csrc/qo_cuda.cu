@@ -92,6 +92,8 @@ struct qo_plan {
     DevPlan d[8];
     std::vector<double> f;
     std::vector<unsigned char> maskv;
+    struct Upload { void *dst; std::vector<unsigned char> data; };
+    std::vector<Upload> uploads[8];                       /* what qo_plan_create copied to each device (qo_mc_run re-sends it on a cache hit) */
 };
 
 /* ---- ctx ---------------------------------------------------------------- */
@@ -176,6 +178,7 @@ extern "C" int qo_ctx_set_stream(qo_ctx *ctx, void *cuda_stream)
     if (!ctx) return QO_ERR_ARG;
     DevCtx *d = &ctx->d[0];
     CU(cudaSetDevice(d->device));
+    if (ctx->mc_cache) { cudaStreamSynchronize(d->stream); qo_plan_destroy(ctx->mc_cache); ctx->mc_cache = NULL; }
     if (d->own_stream) { cudaStreamDestroy(d->stream); d->own_stream = 0; }
     if (cuda_stream) d->stream = (cudaStream_t)cuda_stream;
     else { CU(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking)); d->own_stream = 1; }
@@ -187,6 +190,7 @@ extern "C" int qo_ctx_num_devices(const qo_ctx *ctx) { return ctx ? ctx->ndev : 
 extern "C" void qo_ctx_destroy(qo_ctx *ctx)
 {
     if (!ctx) return;
+    if (ctx->mc_cache) { qo_plan_destroy(ctx->mc_cache); ctx->mc_cache = NULL; }
     for (int g = 0; g < ctx->ndev; g++) {
         cudaSetDevice(ctx->d[g].device);
         if (ctx->have_nccl && ctx->comm[g]) ctx->nccl.CommDestroy(ctx->comm[g]);
@@ -568,7 +572,8 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     for (int g = 0; g < ctx->ndev; g++) {
         DevPlan *d = &p->d[g];
         rc = QO_ERR_CUDA;
-#define H2D(dst, src, nbytes) do { CUP(cudaMemcpyAsync((dst), (src), (nbytes), cudaMemcpyHostToDevice, st)); if (g == 0) p->h2d_bytes += (nbytes); } while (0)
+#define H2D(DST_, SRC_, NB_) do { CUP(cudaMemcpyAsync((DST_), (SRC_), (NB_), cudaMemcpyHostToDevice, st)); if (g == 0) p->h2d_bytes += (NB_); \
+                                  qo_plan::Upload u_; u_.dst = (DST_); u_.data.assign((const unsigned char *)(SRC_), (const unsigned char *)(SRC_) + (NB_)); p->uploads[g].push_back(std::move(u_)); } while (0)
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); qo_plan_destroy(p); return QO_ERR_CUDA; } } while (0)
         CUP(cudaSetDevice(ctx->d[g].device));
         cudaStream_t st = ctx->d[g].stream;
@@ -1092,9 +1097,38 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
     qo_clear_error();
     if (!ctx || !cfg || !res) return QO_ERR_ARG;
     if (cfg->mode == QO_MODE_FULL_S && !full_s) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
+    if (!net || !f || nf <= 0 || (nspec > 0 && !spec) || nspec < 0) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    /* same job as the previous call on this ctx (everything but the sample range)?  Then its plan is still good. */
+    unsigned long long key = 1469598103934665603ull;
+    {
+        auto mix = [&key](const void *ptr, size_t n) { const unsigned char *b = (const unsigned char *)ptr; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+        mix(net->e, (size_t)net->n * sizeof(qo_elem)); mix(&net->rs, sizeof net->rs); mix(&net->rl, sizeof net->rl);
+        mix(f, (size_t)nf * sizeof(double));
+        if (nspec > 0) mix(spec, (size_t)nspec * sizeof(qo_spec));
+        if (cfg->n_tol > 0 && cfg->tol) mix(cfg->tol, (size_t)cfg->n_tol * sizeof(qo_tol));
+        const long long scal[8] = { (long long)cfg->seed, cfg->dist, cfg->n_tol, cfg->mode, cfg->precision, cfg->hist_bins, cfg->hist_spec, nspec };
+        mix(scal, sizeof scal); mix(&cfg->hist_lo, sizeof(double)); mix(&cfg->hist_hi, sizeof(double));
+        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS" };
+        for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) { const char *v = getenv(envs[i]); mix(v ? v : "\1", v ? strlen(v) + 1 : 1); }
+    }
     qo_plan *p = NULL;
-    int rc = qo_plan_create(ctx, net, f, nf, spec, nspec, cfg, &p);
-    if (rc) return rc;
+    int rc = QO_OK;
+    const bool cacheable = net->nblk == 0 && !getenv("QO100NET_NO_PLAN_CACHE");      /* measured blocks are not hashed: no reuse */
+    if (cacheable && ctx->mc_cache && ctx->mc_cache_key == key && ctx->mc_cache->nf == nf) {
+        p = ctx->mc_cache;
+        for (int g = 0; g < ctx->ndev; g++) {                 /* the call's inputs travel host -> device every time */
+            CU(cudaSetDevice(ctx->d[g].device));
+            for (size_t i = 0; i < p->uploads[g].size(); i++)
+                CU(cudaMemcpyAsync(p->uploads[g][i].dst, p->uploads[g][i].data.data(), p->uploads[g][i].data.size(), cudaMemcpyHostToDevice, ctx->d[g].stream));
+        }
+        rc = qo_plan_reset(p);
+        if (rc) return rc;
+    } else {
+        if (ctx->mc_cache) { qo_plan_destroy(ctx->mc_cache); ctx->mc_cache = NULL; }
+        rc = qo_plan_create(ctx, net, f, nf, spec, nspec, cfg, &p);
+        if (rc) return rc;
+        if (cacheable) { ctx->mc_cache = p; ctx->mc_cache_key = key; }
+    }
     const int fs = cfg->mode == QO_MODE_FULL_S;
     const unsigned long long N = cfg->n_samples;
     qo_c64 *dbuf[8] = { 0 };
@@ -1138,7 +1172,10 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         }
     }
     for (int g = 0; g < ctx->ndev; g++) if (dbuf[g]) { cudaSetDevice(ctx->d[g].device); cudaFree(dbuf[g]); }
-    qo_plan_destroy(p);
+    if (rc != QO_OK || ctx->mc_cache != p) {               /* not cached, or its launch failed: do not keep it */
+        if (ctx->mc_cache == p) ctx->mc_cache = NULL;
+        qo_plan_destroy(p);
+    }
     return rc;
 }
 

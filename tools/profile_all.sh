@@ -18,13 +18,18 @@ cap() {   # name, evals per launch, kernel regex, skip, command...
     python tools/ncu_summary.py $OUT/prof_${TAG}_${name}.ncu-rep $OUT/${TAG}_${name} $evals > /dev/null 2>&1 || echo "summary of $name failed"
     rm -f $OUT/prof_${TAG}_${name}.ncu-rep
 }
+cap ts_cfg2 819200000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
+cap ts_cfg5 819200000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
+if [ "${2:-}" = "all" ]; then
+export QO100NET_KERNEL=tf
 cap tf_cfg2 819200000 qo_mc_tf 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
 cap tf_cfg5 819200000 qo_mc_tf 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
-if [ "${2:-}" = "all" ]; then
+unset QO100NET_KERNEL
 export QO100NET_KERNEL=ladder
 cap ladder_cfg2 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
+cap ladder_cfg5 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
 unset QO100NET_KERNEL
-cap fulls_tf 134217728 qo_fs_tf 2 python bench.py --steps 1 --warmup 3 --samples 20000
+cap fulls_tf 268435456 qo_fs_tf 2 python bench.py --steps 1 --warmup 3 --samples 200000 --north-star-samples 2000000
 cap nodal 4000000 nodal 1 python tools/nodal_bench.py --samples 4000
 cap generic_cfg3 1200000 generic 2 python tools/cfg3_run.py
 fi

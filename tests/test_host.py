@@ -483,3 +483,44 @@ def test_plan_analysis_rejects_unknown_mode_and_precision(Q, W):
     assert "mode" in Q.lib().qo_last_error().decode()
     assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=16)["reason"] == "network does not compile"
     assert "precision" in Q.lib().qo_last_error().decode()
+
+
+def test_integration_md_c_samples_compile_and_link(Q, tmp_path):
+    """The C samples of INTEGRATION.md are real programs: extract them, compile them with the system C compiler against
+    include/qo100net.h (-Wall -Werror: a drifted prototype or struct field fails here, not only in ctypes), link them against
+    libqo100net.so and run them.  Without a GPU they must stop at the documented QO_ERR_NO_DEVICE path; with one they run."""
+    import re
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc", path="/usr/bin") or shutil.which("gcc") or shutil.which("cc")
+    if not cc:
+        pytest.skip("no C compiler")
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```c\n(.*?)```", md, flags=re.S)
+    assert len(blocks) >= 2
+    resim = next(b for b in blocks if "int main(void)" in b)
+    frag = next(b for b in blocks if "qo_net_cheby_lpf" in b and "int main" not in b)
+    # the yield fragment becomes a function body around which the declarations it assumes are supplied
+    prog2 = ("#include <stdio.h>\n#include <stdlib.h>\n#include <stdint.h>\n#include \"qo100net.h\"\n"
+             "int main(void)\n{\n    qo_ctx *ctx = NULL; double *f = malloc(4096 * sizeof *f);\n"
+             "    qo_grid_log(10e6 / 2.5, 10e6 * 6.25, 4096, f);\n"
+             "    if (qo_ctx_create(1, &ctx)) { fprintf(stderr, \"%s\\n\", qo_last_error()); return 3; }\n" + frag +
+             "    printf(\"%llu %llu\\n\", (unsigned long long)res.n_pass, (unsigned long long)res.n_total);\n"
+             "    qo_ctx_destroy(ctx); qo_net_free(net); free(f);\n    return 0;\n}\n")
+    libdir = os.path.dirname(Q.LIB_PATH)
+    for name, src in (("resim", resim), ("yield", prog2)):
+        c = tmp_path / (name + ".c")
+        c.write_text(src)
+        exe = tmp_path / name
+        r = subprocess.run([cc, "-std=gnu11", "-Wall", "-Werror", "-Wno-unused-value", str(c), "-I", os.path.join(ROOT, "include"), "-L", libdir,
+                            "-Wl,-rpath," + libdir, "-lqo100net", "-lm", "-o", str(exe)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    # resim.c wants the reference schematic in its working directory: run it where it is not -> the loader's I/O error path
+    r = subprocess.run([str(tmp_path / "resim")], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 1 and "pa-lpf-simulation.sch" in r.stderr
+    import torch
+    r = subprocess.run([str(tmp_path / "yield")], cwd=str(tmp_path), capture_output=True, text=True, timeout=300)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and r.stdout.split()[1] == "1000000"
+    else:
+        assert r.returncode == 3 and "CUDA" in r.stderr          # no device, no fallback

@@ -33,9 +33,10 @@
 #include "qo_tf.cuh"
 
 #define QO_TS_TPB 128
-/* points in flight per thread / resident blocks per SM: plain ladders hold <= 36 coefficients (72 registers) and run four
- * points at 128 registers; behind a coupled-line block P and Q stay apart (<= 40 coefficients + the block's constants and the
- * rotating angle), two points at 168 registers */
+/* points in flight per thread / resident blocks per SM (both at 168 registers, 12 warps per SM): plain ladders hold <= 36
+ * coefficients (72 registers) and run four points -- at 128 registers (4 blocks) ptxas serialises the four Horner chains and
+ * the kernel is 8 % slower; behind a coupled-line block P and Q stay apart (<= 40 coefficients + the block's constants and the
+ * rotating angle), two points */
 #define QO_TS_PT2 4
 #define QO_TS_MINB2 3
 #define QO_TS_PT4 2

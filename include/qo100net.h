@@ -259,11 +259,22 @@ int qo_nodal_mc_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, co
  * On the device every point re-checks its own multipliers: a point above 3e6 (or NaN) sends the whole job to the kernel with
  * per-point partial pivoting, so an unprobed frequency or an interior sample cannot silently lose digits. */
 int qo_nodal_analyze(const qo_nodal *nd, const double *f, int nf, const qo_mc_cfg *cfg, int info[4], double *max_multiplier);
+/* Large nodal jobs (>= 4e8 points, or QO100NET_NODAL=jit) do not interpret the static plan: the library prints it as a
+ * straight-line kernel for this network -- stamps, elimination and only the substitutions the observed S entries need, every
+ * value a named register -- compiles it with NVRTC for sm_100a and keeps it for the life of the process.  This entry point runs
+ * the same generation and compilation without a GPU (the tool the reference used, qucsator, re-factorises
+ * util/pa-bias-simulation/pa-bias-simulation.sch:19-72 numerically at every point).  info[0] = compiled (0: static plan refused,
+ * libnvrtc missing or a compilation error, see qo_last_error), [1] = registers per thread, [2] = stack frame bytes (0 = the whole
+ * factorisation lives in registers), [3] = spill bytes, [4] = complex multiply-subtracts per point, [5] = reciprocals per point. */
+int qo_nodal_jit_analyze(const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec, const qo_mc_cfg *cfg, int info[6]);
 
 /* which factorisation the calling thread's last nodal call used: "qo_nodal_kernel<static,smem>" /
  * "qo_nodal_kernel<static,local>" (symbolic plan: fixed pivot order and fill pattern, verified on the host against
- * the pivoted solve; values in a thread-private array or, with QO100NET_NODAL_VALUES=smem, in shared memory) or "qo_nodal_kernel<dense>" (per-point partial pivoting; QO100NET_NODAL=dense forces it) */
+ * the pivoted solve; values in a thread-private array or, with QO100NET_NODAL_VALUES=smem, in shared memory), "qo_nodal_jit_kernel"
+ * (the same plan compiled into a kernel of its own, values in registers) or "qo_nodal_kernel<dense>" (per-point partial pivoting; QO100NET_NODAL=dense forces it) */
 const char *qo_nodal_last_kernel(void);
+/* seconds the calling thread's last nodal call spent generating + compiling its kernel (0: none needed, or taken from the process cache) */
+double qo_nodal_last_compile_seconds(void);
 
 /* The same job kept resident in HBM (tables, grid, specs uploaded once):
  *   counters layout (uint64): [0]=n_pass [1]=n_total [2..2+nspec)=fail_per_spec, then hist[hist_bins].

@@ -27,26 +27,7 @@
 #include "qo_ctx_internal.h"
 #include "qo_stream.h"
 
-#define QN_TPB 64
-#define QN_MAX_SPEC 8
-#define QN_MAX_VAR 64
-
-struct NodalProg {
-    int32_t n_nodes, nb, np, n_unk, nspec, hist_spec, hist_bins, n_var, dist, full;
-    uint64_t seed;
-    double hist_lo, hist_hi;
-    int32_t port_node[QO_NODAL_MAX_PORTS];
-    double port_z0[QO_NODAL_MAX_PORTS];
-    int32_t kind[QO_NODAL_MAX_BR];
-    int32_t node[QO_NODAL_MAX_BR][4];
-    double nom[QO_NODAL_MAX_BR][4];
-    double ttol[QO_NODAL_MAX_BR][4];
-    int16_t tvar[QO_NODAL_MAX_BR][4];
-    uint8_t tmode[QO_NODAL_MAX_BR][4];
-    int32_t spec_min[QN_MAX_SPEC], spec_row[QN_MAX_SPEC], spec_col[QN_MAX_SPEC];   /* spec_min: 1 = "|S| >= limit" */
-    double spec_thr[QN_MAX_SPEC];       /* linear |S|^2 threshold */
-    double spec_limit_db[QN_MAX_SPEC];
-};
+#include "qo_nodal_prog.h"
 
 __device__ __forceinline__ double2 c_mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 c_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -441,6 +422,8 @@ static void s_to_y(const qo_c64 s[4], double z0, qo_c64 y[4])
 
 static __thread const char *g_last_kernel = "";
 extern "C" const char *qo_nodal_last_kernel(void) { return g_last_kernel; }
+static __thread double g_last_compile_s = 0.0;
+extern "C" double qo_nodal_last_compile_seconds(void) { return g_last_compile_s; }
 
 /* ---- host: symbolic factorisation ------------------------------------------------------------------------- */
 typedef std::vector<double2> cvec;
@@ -509,8 +492,48 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
     /* column order: internal unknowns, then the port nodes in port order */
     std::vector<int> is_port(n, 0);
     for (int p = 0; p < np; p++) { if (is_port[hp->port_node[p] - 1]) return false; is_port[hp->port_node[p] - 1] = 1; }
+    /* internal unknowns in greedy MINIMUM-DEGREE order on the structurally symmetrised pattern (eliminating an unknown joins
+     * its neighbours): the bias networks are stars around their supply rails, and taking the leaves first leaves almost no
+     * fill -- 175 -> 60 multiply-subtracts per point on the reference network against the netlist's own numbering.
+     * QO100NET_NODAL_ORDER=natural keeps the netlist order (A/B). */
     int nc = 0;
-    for (int u = 0; u < n; u++) if (!is_port[u]) sp->colmap[u] = (uint8_t)nc++;
+    {
+        std::vector<unsigned char> raw0((size_t)LD * LD, 0);
+        MarkSink M0 = { raw0.data() };
+        nodal_stamp_all(hp, hp->nom, 1.0, yb, (size_t)nf * 4, M0);
+        std::vector<unsigned int> adj(n, 0);
+        for (int r = 0; r < n; r++) for (int c = 0; c < n; c++) if (r != c && (raw0[r * LD + c] || raw0[c * LD + r])) adj[r] |= 1u << c;
+        std::vector<int> gone(n, 0), comp(n, -1);
+        const char *ord = getenv("QO100NET_NODAL_ORDER");
+        const bool natural = ord && !strcmp(ord, "natural");
+        /* unconnected sub-circuits (the reference network is two bias tees side by side) one after the other: the values of a
+         * finished sub-circuit are dead before the next one is stamped, which halves the live set of the compiled kernel */
+        int ncomp = 0;
+        for (int u = 0; u < n; u++) {
+            if (comp[u] >= 0) continue;
+            std::vector<int> stack(1, u);
+            comp[u] = ncomp;
+            while (!stack.empty()) {
+                const int a = stack.back();
+                stack.pop_back();
+                for (int v = 0; v < n; v++) if (((adj[a] >> v) & 1u) && comp[v] < 0) { comp[v] = ncomp; stack.push_back(v); }
+            }
+            ncomp++;
+        }
+        for (int step = 0; step < n - np; step++) {
+            int best = -1, bdeg = 1 << 30, bcomp = 1 << 30;
+            for (int u = 0; u < n; u++) {
+                if (gone[u] || is_port[u]) continue;
+                const int deg = natural ? u : __builtin_popcount(adj[u]);
+                const int cu = natural ? 0 : comp[u];
+                if (cu < bcomp || (cu == bcomp && deg < bdeg)) { bcomp = cu; bdeg = deg; best = u; }
+            }
+            gone[best] = 1;
+            sp->colmap[best] = (uint8_t)nc++;
+            const unsigned int nb_ = adj[best];
+            for (int v = 0; v < n; v++) if ((nb_ >> v) & 1u) { adj[v] |= nb_; adj[v] &= ~(1u << v); adj[v] &= ~(1u << best); }
+        }
+    }
     for (int p = 0; p < np; p++) sp->colmap[hp->port_node[p] - 1] = (uint8_t)nc++;
     /* row (pivot) order from a numeric LU at a representative point, columns already permuted */
     const int k_ref = nf / 2;
@@ -673,6 +696,10 @@ static bool build_static_thr(const NodalProg *hp, const double *f, int nf, const
     return true;
 }
 
+/* resident blocks per SM the compiled kernel is built for (64 threads each): 6 -> 168 registers */
+#define QN_JIT_MINB 6
+#include "qo_nodal_jit.h"
+
 /* host-only front end: netlist + specs + tolerances -> device program, spec masks, block admittances */
 static int nodal_compile(const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec, const qo_mc_cfg *cfg, int full,
                          NodalProg *hp, std::vector<unsigned char> &mask, std::vector<double2> &yb, int *n_unk_out)
@@ -760,10 +787,40 @@ extern "C" int qo_nodal_analyze(const qo_nodal *nd, const double *f, int nf, con
     return QO_OK;
 }
 
+/* Host-only as well (NVRTC compiles without a GPU): print the static plan of this job as a kernel, compile it for sm_100a and
+ * report what ptxas made of it.  info[0] = compiled (0/1; 0 also when the static plan is refused or libnvrtc is missing),
+ * [1] = registers per thread, [2] = stack frame bytes (0 = every value of the factorisation lives in registers), [3] = spill
+ * bytes, [4] = complex multiply-subtracts per point, [5] = reciprocals per point. */
+extern "C" int qo_nodal_jit_analyze(const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec, const qo_mc_cfg *cfg, int info[6])
+{
+    qo_clear_error();
+    if (!info || !cfg) return QO_ERR_ARG;
+    for (int i = 0; i < 6; i++) info[i] = 0;
+    std::vector<NodalProg> hpv(1);
+    std::vector<unsigned char> mask;
+    std::vector<double2> yb;
+    int n_unk = 0;
+    int rc = nodal_compile(nd, f, nf, spec, nspec, cfg, cfg->mode == QO_MODE_FULL_S, &hpv[0], mask, yb, &n_unk);
+    if (rc) return rc;
+    std::vector<NodalStatic> spv(1);
+    if (yb.empty()) yb.assign(4, make_double2(0.0, 0.0));
+    if (!build_static(&hpv[0], f, nf, yb.data(), &spv[0])) { qo_set_error("the static plan failed its self-check for this network"); return QO_OK; }
+    const QnJitEntry *e = qn_jit_get(&hpv[0], &spv[0], false, true);
+    info[0] = e->ok; info[1] = e->regs; info[2] = e->stack_bytes; info[3] = e->spill_bytes; info[4] = e->n_fms; info[5] = e->n_inv;
+    if (!e->ok) qo_set_error("%s", e->log.substr(0, 400).c_str());
+    return QO_OK;
+}
+
+/* points below which a job is not worth a compilation (0.3 - 1 s of NVRTC against 8e8 points/s on the interpreted kernel); a
+ * kernel this process has already compiled is used from QN_JIT_MIN_CACHED points on */
+#define QN_JIT_MIN_POINTS 400000000ull
+#define QN_JIT_MIN_CACHED 1000000ull
+
 static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, const qo_nspec *spec, int nspec,
                      const qo_mc_cfg *cfg, qo_mc_result *res, qo_c64 *full_s_host)
 {
     if (!ctx || !cfg) { qo_set_error("bad arguments"); return QO_ERR_ARG; }
+    g_last_compile_s = 0.0;
     const int full = cfg->mode == QO_MODE_FULL_S;
     if (full && !full_s_host) { qo_set_error("FULL_S needs an output buffer"); return QO_ERR_ARG; }
     if (!full && !res) return QO_ERR_ARG;
@@ -789,6 +846,21 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
     const int ncnt = 2 + nspec + hp->hist_bins;
     const unsigned long long N = cfg->n_samples;
     if (N == 0) { if (res) { res->n_pass = res->n_total = 0; } return QO_OK; }
+    /* the plan compiled into a kernel of its own: large jobs (QO100NET_NODAL=jit: always; =static / =dense: never) */
+    const QnJitEntry *jit = NULL;
+    if (use_static && !(force && !strcmp(force, "static"))) {
+        const bool forced = force && !strcmp(force, "jit");
+        const unsigned long long npts = N * (unsigned long long)nf;
+        if (forced || npts >= QN_JIT_MIN_CACHED) {
+            const size_t had = g_qn_jit.size();
+            jit = qn_jit_get(hp, &spv[0], true, forced || npts >= QN_JIT_MIN_POINTS);
+            if (jit && g_qn_jit.size() != had) g_last_compile_s = jit->compile_s;
+            if (jit && !jit->ok) {
+                if (forced) { qo_set_error("QO100NET_NODAL=jit: %s", jit->log.substr(0, 400).c_str()); return QO_ERR_UNSUPPORTED; }
+                jit = NULL;
+            }
+        }
+    } else if (force && !strcmp(force, "jit")) { qo_set_error("QO100NET_NODAL=jit: the static plan failed its self-check for this network"); return QO_ERR_UNSUPPORTED; }
 
     DevCtx *dc = &ctx->d[0];                 /* device 0 of the ctx: the nodal path is not sharded yet */
     CU(cudaSetDevice(dc->device));
@@ -822,6 +894,13 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
          * points/s on the reference network); latency hiding matters more here than the private arrays' L2 footprint */
         int bps = 0;
         { const char *e = getenv("QO100NET_NODAL_BPS"); if (e && atoi(e) > 0) bps = atoi(e); }
+        if (bps == 0 && jit) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)jit->kern, QN_TPB, 0) != cudaSuccess || bps <= 0) {
+                cudaGetLastError();
+                bps = jit->regs > 0 ? 65536 / (((jit->regs + 7) & ~7) * QN_TPB) : 4;
+                if (bps > 16) bps = 16;
+            }
+        }
         if (bps == 0) {
             if (use_static) {
                 const int nnz = spv[0].nnz;
@@ -842,7 +921,13 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         cudaEventRecord(dc->ev0, dc->stream);
 #define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds, growth2)
         g_last_kernel = use_static ? "qo_nodal_kernel<static,local>" : "qo_nodal_kernel<dense>";
-        if (use_static) {
+        if (use_static && jit) {
+            int nf_ = nf;
+            unsigned long long off_ = cfg->sample_offset, n_ = N;
+            void *args[] = { &dprog, &dfr, &dmask, &dy, &nf_, &chunk_len, &nchunks, &off_, &n_, &dcnt, &ds, &growth2 };
+            CUN(cudaLaunchKernel((const void *)jit->kern, dim3((unsigned)grid), dim3(QN_TPB), args, 0, dc->stream));
+            g_last_kernel = "qo_nodal_jit_kernel";
+        } else if (use_static) {
             const int nnz = spv[0].nnz;
             const size_t smem = (size_t)nnz * QN_TPB * sizeof(double2);
             const char *loc = getenv("QO100NET_NODAL_VALUES");

@@ -97,7 +97,7 @@ EXPORTS = [
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
     "qo_nodal_num_nodes", "qo_nodal_num_ports", "qo_nodal_num_branches", "qo_nodal_get_branches", "qo_nodal_get_ports",
-    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run", "qo_nodal_last_kernel", "qo_nodal_analyze",
+    "qo_nodal_free", "qo_nodal_sweep", "qo_nodal_mc_run", "qo_nodal_last_kernel", "qo_nodal_analyze", "qo_nodal_jit_analyze", "qo_nodal_last_compile_seconds",
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
@@ -175,6 +175,8 @@ def lib():
         "qo_nodal_sweep": (C.c_int, [vp, vp, dp, C.c_int, vp]),
         "qo_nodal_last_kernel": (C.c_char_p, []),
         "qo_nodal_analyze": (C.c_int, [vp, dp, C.c_int, C.POINTER(McCfg), ip, dp]),
+        "qo_nodal_last_compile_seconds": (C.c_double, []),
+        "qo_nodal_jit_analyze": (C.c_int, [vp, dp, C.c_int, C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), ip]),
         "qo_nodal_mc_run": (C.c_int, [vp, vp, dp, C.c_int, C.POINTER(NSpec), C.c_int, C.POINTER(McCfg), C.POINTER(McResult), vp]),
         "qo_dat_create": (C.c_int, [C.POINTER(vp)]),
         "qo_dat_read": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
@@ -375,6 +377,19 @@ class Nodal:
         mm = C.c_double(0.0)
         _check(lib().qo_nodal_analyze(self._h, _dp(f), len(f), C.byref(cfg), info, C.byref(mm)))
         return dict(static=bool(info[0]), unknowns=info[1], nnz=info[2], program_words=info[3], max_multiplier=mm.value)
+
+    def jit_analyze(self, f, specs=(), tols=(), mode=MODE_REDUCE_ONLY):
+        """Host-only (qo_nodal_jit_analyze): generate this job's compiled kernel and report what ptxas made of it
+        -> dict(compiled, registers, stack_bytes, spill_bytes, fms, reciprocals, error)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        cfg = _cfg(0, 0, list(tols), 0, DIST_UNIFORM, mode, 64, 0, 0, 0.0, 1.0)
+        sp = (NSpec * max(1, len(specs)))()
+        for i, s in enumerate(specs):
+            sp[i].kind, sp[i].row, sp[i].col, sp[i].f_lo, sp[i].f_hi, sp[i].limit = int(s[0]), int(s[1]), int(s[2]), float(s[3]), float(s[4]), float(s[5])
+        info = (C.c_int * 6)()
+        _check(lib().qo_nodal_jit_analyze(self._h, _dp(f), len(f), sp, len(specs), C.byref(cfg), info))
+        return dict(compiled=bool(info[0]), registers=info[1], stack_bytes=info[2], spill_bytes=info[3], fms=info[4],
+                    reciprocals=info[5], error=None if info[0] else lib().qo_last_error().decode())
 
     def close(self):
         if self._h:
@@ -755,6 +770,10 @@ class Context:
     @staticmethod
     def nodal_last_kernel():
         return lib().qo_nodal_last_kernel().decode()
+
+    @staticmethod
+    def nodal_last_compile_seconds():
+        return lib().qo_nodal_last_compile_seconds()
 
     def device_perturb_factors(self, seed, sample_offset, n_samples, n_var, dist, tol):
         out = np.empty((n_samples, n_var))

@@ -309,3 +309,69 @@ def test_gpu_nodal_monte_carlo_equals_oracle(Q, R, ctx, pa_bias, golden_s2p, mon
     os_ = R.nodal_mc_run(br, nn, ports, f[:31], [], refbind.mc_cfg(21, 7, tols), full_s=True)["s"]
     assert gs.shape == (7, 31, 5, 5) and np.max(np.abs(gs - os_)) < 1e-9
     R.sblock_clear()
+
+
+def test_compiled_kernel_analysis_host_only(Q, pa_bias, golden_s2p):
+    """qo_nodal_jit_analyze (no GPU: NVRTC only compiles): the reference's bias network printed as a straight-line kernel and
+    compiled for sm_100a.  Minimum-degree ordering leaves 49 complex multiply-subtracts per point for a two-spec yield job
+    (the netlist's own numbering: 175), nothing of the factorisation is addressed through the stack, and a yield job on two
+    S entries solves fewer right-hand sides than the FULL_S job on all 25."""
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    f = pa_bias["frequency"]
+    tols = [(b, 0, v, Q.TOL_REL, 0.05) for v, b in enumerate(i for i, (k, _n, _p) in enumerate(br) if k in (NB_R, NB_C))]
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, -1.0), (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, -20.0)]
+    a = nd.jit_analyze(f, specs, tols)
+    if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+        pytest.skip("no NVRTC on this machine: " + a["error"][:120])
+    assert a["compiled"], a
+    assert 20 <= a["fms"] <= 80 and a["reciprocals"] <= 23 and 0 < a["registers"] <= 255 and a["stack_bytes"] == 0
+    full = nd.jit_analyze(f, [], tols, mode=Q.MODE_FULL_S)
+    assert full["compiled"] and full["fms"] > a["fms"]
+    nd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_compiled_kernel_equals_interpreted_dense_and_oracle(Q, R, ctx, pa_bias, golden_s2p, monkeypatch):
+    """The run-time compiled kernel (QO100NET_NODAL=jit) on the reference network: the nominal sweep reproduces the reference
+    dataset, Monte-Carlo counters and histogram equal the interpreted static kernel's, the pivoted kernel's and the oracle's,
+    FULL_S planes agree to rounding, and the multiplier guard still hands a tripped job to the pivoted kernel."""
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    register_inductor(R, golden_s2p)
+    monkeypatch.setenv("QO100NET_NODAL", "jit")
+    S = ctx.nodal_sweep(nd, pa_bias["frequency"])
+    assert ctx.nodal_last_kernel() == "qo_nodal_jit_kernel"
+    check_vs_dat(S, pa_bias)
+    f = pa_bias["frequency"][100:1400:13]
+    nom = ctx.nodal_sweep(nd, f)
+    s21, s31 = 20 * np.log10(np.abs(nom[:, 1, 0])), 20 * np.log10(np.abs(nom[:, 2, 0]))
+    band = (f >= 2.3e9) & (f <= 2.5e9)
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, float(s21[band].min()) - 0.02),
+             (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, float(s31[band].max()) + 0.3),
+             (Q.SPEC_S21_MAX_DB, 4, 3, 0.0, 1e99, 3.0)]
+    tols = [(i, 0, v, Q.TOL_REL, 0.05 if k == NB_C else 0.01) for v, (i, (k, _n, _p)) in
+            enumerate((i, b) for i, b in enumerate(br) if b[0] in (NB_R, NB_C))]
+    hist = dict(hist_bins=20, hist_spec=0, hist_lo=float(s21[band].min()) - 0.3, hist_hi=float(s21[band].min()) + 0.3)
+    n = 3000
+    got = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, sample_offset=2 ** 33 + 5, **hist)
+    assert ctx.nodal_last_kernel() == "qo_nodal_jit_kernel"
+    gs = ctx.nodal_mc_run(nd, f[:31], [], 21, 7, tols, mode=Q.MODE_FULL_S)["s"]
+    res = {}
+    for mode in ("static", "dense"):
+        monkeypatch.setenv("QO100NET_NODAL", mode)
+        res[mode] = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, sample_offset=2 ** 33 + 5, **hist)
+        res[mode + "_s"] = ctx.nodal_mc_run(nd, f[:31], [], 21, 7, tols, mode=Q.MODE_FULL_S)["s"]
+        for key in ("n_pass", "n_total"):
+            assert res[mode][key] == got[key]
+        assert np.array_equal(res[mode]["fail_per_spec"], got["fail_per_spec"]) and np.array_equal(res[mode]["hist"], got["hist"])
+    assert np.max(np.abs(gs - res["static_s"])) < 1e-12 and np.max(np.abs(gs - res["dense_s"])) < 1e-9
+    from oracle import refbind
+    ref = R.nodal_mc_run(br, nn, ports, f, specs, refbind.mc_cfg(21, n, tols, sample_offset=2 ** 33 + 5, **hist), nthreads=8)
+    assert got["n_total"] == n and got["n_pass"] == ref["n_pass"] and 0 < got["n_pass"] < n
+    assert np.array_equal(got["fail_per_spec"], ref["fail_per_spec"]) and np.array_equal(got["hist"], ref["hist"])
+    # the guard: threshold |multiplier| <= 2 on the device only -> suspects flagged by the compiled kernel, job redone with pivoting
+    monkeypatch.setenv("QO100NET_NODAL", "jit")
+    monkeypatch.setenv("QO100NET_NODAL_GUARD2", "4.0")
+    again = ctx.nodal_mc_run(nd, f, specs, 21, n, tols, sample_offset=2 ** 33 + 5, **hist)
+    assert ctx.nodal_last_kernel() == "qo_nodal_kernel<dense>" and again["n_pass"] == got["n_pass"]
+    R.sblock_clear()
+    nd.close()

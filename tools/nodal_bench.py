@@ -3,7 +3,7 @@
 (util/pa-bias-simulation/pa-bias-simulation.sch; netlist rebuilt from tests/test_nodal.py::hand_netlist so that it
 runs on the GPU box), Monte Carlo over every R and C, next to the CPU oracle on all host cores.
 
-  python tools/nodal_bench.py [--samples 20000] [--nf 1000] [--out gpurun_out/nodal.json]
+  python tools/nodal_bench.py [--samples 500000] [--nf 1000] [--out gpurun_out/nodal.json]
 """
 import argparse
 import json
@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--samples", type=int, default=20000)
+    ap.add_argument("--samples", type=int, default=500000)
     ap.add_argument("--nf", type=int, default=1000)
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -38,27 +38,48 @@ def main():
             enumerate((i, b) for i, b in enumerate(br) if b[0] in (T.NB_R, T.NB_C))]
     hist = dict(hist_bins=64, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)
     n = args.samples
-    ctx.nodal_mc_run(nd, f, specs, 5, 256, tols, **hist)
-    best = None
-    for rep in range(3):
-        r = ctx.nodal_mc_run(nd, f, specs, 5, n, tols, sample_offset=rep * n, **hist)
-        best = r if best is None or r["seconds"] < best["seconds"] else best
-    kernel = ctx.nodal_last_kernel()
+
+    def timed(mode, n_run):
+        if mode:
+            os.environ["QO100NET_NODAL"] = mode
+        else:
+            os.environ.pop("QO100NET_NODAL", None)
+        ctx.nodal_mc_run(nd, f, specs, 5, 256, tols, **hist)
+        compile_s = 0.0
+        best = None
+        for rep in range(3):
+            r = ctx.nodal_mc_run(nd, f, specs, 5, n_run, tols, sample_offset=rep * n_run, **hist)
+            compile_s = max(compile_s, ctx.nodal_last_compile_seconds())
+            best = r if best is None or r["seconds"] < best["seconds"] else best
+        return best, ctx.nodal_last_kernel(), compile_s
+
+    # default selection at this size (compiled kernel from 4e8 points on), then each kernel forced
+    auto, auto_kernel, auto_compile = timed(None, n)
+    interp, interp_kernel, _ = timed("static", min(n, 100000))
+    comp, comp_kernel, comp_compile = timed("jit", n)
+    os.environ.pop("QO100NET_NODAL", None)
     peak = ctx.measure_dfma_peak()
     ncpu = 400
     nthr = R.max_threads()
     t0 = time.perf_counter()
     o = R.nodal_mc_run(br, nn, ports, f, specs, R.mc_cfg(5, ncpu, tols, **hist), nthreads=nthr)
     cpu_s = time.perf_counter() - t0
+    os.environ["QO100NET_NODAL"] = "jit"
     chk = ctx.nodal_mc_run(nd, f, specs, 5, ncpu, tols, **hist)
-    out = {"workload": "pa-bias 5-port network, 23 unknowns, %d samples x %d points, reduce-only" % (n, args.nf),
-           "kernel": kernel, "gpu_kernel_seconds": best["seconds"], "gpu_points_per_s": n * args.nf / best["seconds"],
-           "real_flops_per_point_lu_plus_solves": best["flops_per_eval"],
-           "gpu_tflops": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12, "dfma_peak_tflops": peak,
-           "frac_of_dfma_peak": best["flops_per_eval"] * n * args.nf / best["seconds"] * 1e-12 / peak,
+    os.environ["QO100NET_NODAL"] = "static"
+    chk2 = ctx.nodal_mc_run(nd, f, specs, 5, ncpu, tols, **hist)
+    os.environ.pop("QO100NET_NODAL", None)
+    a = nd.jit_analyze(f, specs, tols)
+    out = {"workload": "pa-bias 5-port network, 23 unknowns, %d samples x %d points, reduce-only, yield on S21 and S31" % (n, args.nf),
+           "selected_kernel": auto_kernel, "selected_points_per_s": n * args.nf / auto["seconds"],
+           "compiled": {"kernel": comp_kernel, "points_per_s": n * args.nf / comp["seconds"], "kernel_seconds": comp["seconds"],
+                        "compile_seconds_first_call": max(auto_compile, comp_compile), "ptxas": a},
+           "interpreted": {"kernel": interp_kernel, "points_per_s": min(n, 100000) * args.nf / interp["seconds"]},
+           "dfma_peak_tflops": peak,
            "cpu_oracle_points_per_s": ncpu * args.nf / cpu_s, "cpu_cores": nthr,
-           "counters_equal_oracle": bool(chk["n_pass"] == o["n_pass"] and np.array_equal(chk["hist"], o["hist"])),
-           "yield": best["n_pass"] / n}
+           "counters_equal_oracle": bool(chk["n_pass"] == o["n_pass"] and np.array_equal(chk["hist"], o["hist"])
+                                         and chk2["n_pass"] == o["n_pass"] and np.array_equal(chk2["hist"], o["hist"])),
+           "yield": comp["n_pass"] / n}
     print(json.dumps(out, indent=1))
     if args.out:
         open(args.out, "w").write(json.dumps(out, indent=1))

@@ -30,7 +30,8 @@ cap ladder_cfg2 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-ext
 cap ladder_cfg5 819200000 ladder 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
 unset QO100NET_KERNEL
 cap fulls_tf 268435456 qo_fs_tf 2 python bench.py --steps 1 --warmup 3 --samples 200000 --north-star-samples 2000000
-cap nodal 4000000 nodal 1 python tools/nodal_bench.py --samples 4000
+cap nodal 4000000 qo_nodal_kernel 1 python tools/nodal_bench.py --samples 4000
+cap nodal_jit 100000000 qo_nodal_jit 1 python tools/nodal_bench.py --samples 100000
 cap generic_cfg3 1200000 generic 2 python tools/cfg3_run.py
 fi
 ls -la $OUT/*${TAG}*

@@ -85,6 +85,8 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
         else if (tp->nn == 2 && pp == 1) fn = tf_pick<2, 0, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == 1) fn = tf_pick_gd<1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->nn == 4 && tp->s11 && pp == 1) fn = tf_pick<4, 0, true, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && !tp->s11 && tp->front && pp == 1) fn = tf_pick<4, 4, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
+        else if (tp->nn == 4 && !tp->s11 && tp->front && pp == QO_TF_CPL_PP) { fn = tf_pick<4, 4, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
         else if (tp->nn == 4 && !tp->s11 && pp == 1) fn = rot ? (P->cpl_same ? tf_pick<4, 3, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec) : tf_pick<4, 2, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec))
                      : tf_pick<4, 1, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
@@ -235,7 +237,7 @@ extern "C" int qo_tf_plan_check(const DevProg *hp, int mode_reduce_only, int pre
     key = tf_fnv(key, mask, (size_t)nf);
     const int scal[4] = { mode_reduce_only, precision, generic, nf };
     key = tf_fnv(key, scal, sizeof scal);
-    static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E" };
+    static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT" };
     for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) {
         const char *v = getenv(envs[i]);
         key = tf_fnv(key, v ? v : "\1", v ? strlen(v) + 1 : 1);
@@ -271,7 +273,12 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     for (int s = 0; s < hp->nspec; s++) if (hp->spec_kind[s] != SK_S11_MAX) need_s21 = 1;      /* group delay needs D too */
     const bool gd = hp->need_gd != 0;
     int e0 = hp->op0;
-    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { out->cpl_op = e0; e0++; }
+    /* one non-rational block may sit in FRONT of the lumped ops (source side): a coupled-line section, a transmission line or a
+     * measured two-port.  Its row vector [1 Rs] M_block is evaluated per point (closed form / per-frequency table) and
+     * contracted with the polynomials [P; Q] of everything behind it */
+    if (hp->n_ops > e0 && hp->opcode[e0] == OP_CPL) { out->cpl_op = e0; out->front = 0; e0++; }
+    else if (hp->n_ops > e0 + 1 && hp->opcode[e0] == OP_TLINE && !getenv("QO100NET_TF_NO_FRONT")) { out->cpl_op = e0; out->front = 1; e0++; }
+    else if (hp->n_ops > e0 + 1 && hp->opcode[e0] == OP_SBLOCK && !getenv("QO100NET_TF_NO_FRONT")) { out->cpl_op = e0; out->front = 2; e0++; }
     const int nl = hp->n_ops - e0;
     if (nl < 1 || nl > QO_TF_MAXEL) QO_TF_NO("element count");
     int deg = 0, has_d = 0;
@@ -284,8 +291,8 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
     const int Kfull = deg / 2 + 1;
     const bool cpl = out->cpl_op >= 0, s11 = hp->need_s11 != 0;
-    if (cpl && s11) QO_TF_NO("|S11| specs behind a coupled-line block");
-    if (gd && (cpl || s11)) QO_TF_NO("group-delay specs mixed with a coupled-line block or |S11| specs");
+    if (cpl && s11) QO_TF_NO("|S11| specs behind a front block");
+    if (gd && (cpl || s11)) QO_TF_NO("group-delay specs mixed with a front block or |S11| specs");
     if (!need_s21) has_d = 0;                                 /* S11 = (P - Rs Q) / (P + Rs Q): the branch denominators cancel */
     const bool apart = cpl || s11;                            /* P and Q kept apart */
     out->deg = deg; out->el0 = e0; out->n_el = nl; out->nn = (apart || gd) ? 4 : 2; out->s11 = s11; out->gd = gd;

@@ -60,6 +60,7 @@ struct TfParams {
     int den;                                 /* QO_TF_DEN_* (a template parameter of qo_mc_tf_kernel; qo_ts.cuh reads it here) */
     int niter, n_var, n_el, el0, nspec, dist, hist_spec, hist_bins;
     int cpl_fast, cpl_same, cpl_op, cpl_matched;  /* cpl_matched: Rs == the coupler's Zt for every sample */
+    int front;                               /* the block in front: 0 coupled-line section, 1 transmission line, 2 measured two-port (row-vector tables in cse..cco) */
     int cpl_lin;                             /* uniformly spaced grid: the mode angles advance by a constant step per iteration ... */
     double cpl_dw;                           /* ... of this much in w (one iteration = 64 PP points) */
     const double *cplms;
@@ -153,7 +154,18 @@ __device__ __forceinline__ void tf_sample_stage(const TfParams &P, unsigned long
     for (int v = lane; v < P.n_var; v += 32) xw[v] = qo_stream_variate(P.seed, P.sample_offset + s, (uint32_t)v, P.dist);
     __syncwarp();
     if (lane < P.n_el) tf_derive(P.prog, P.el0 + lane, xw, P.wref, P.zn, P.zni, elw + lane * QO_TF_REC);
-    if (CPL && lane == 31) {
+    if (CPL && lane == 31 && P.front == 1) {
+        /* transmission line in front (qo_lumped.cuh OP_TLINE: Z0, theta [deg] at f0): [1 Rs] M = (c + j (Rs/Z0) s, Rs c + j Z0 s) */
+        double tp[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            tp[k] = P.prog->nom[P.cpl_op][k];
+            const int tv = P.prog->tvar[P.cpl_op][k];
+            if (tv >= 0) tp[k] = qo_stream_apply(tp[k], P.prog->ttol[P.cpl_op][k], xw[tv], P.prog->tmode[P.cpl_op][k]);
+        }
+        cplw[0] = P.rs / tp[0]; cplw[1] = tp[0]; cplw[2] = tp[1] / (360.0 * tp[2]); cplw[3] = 0.0;
+    }
+    if (CPL && lane == 31 && P.front == 0) {
         double nom_k[2];
         lad_derive<double>(P.prog, P.cpl_op, xw, cplw, P.cplms ? P.cplms + 4 * s : NULL, nom_k);
         /* equal mode angles: the block's row vector in c^2, s^2, c s with five per-sample constants (tf_cpl_matched_same) */
@@ -262,7 +274,8 @@ __device__ __forceinline__ double tf_extreme(const double (&v)[PTS], double trk)
  * NN     numerator chains: 2 = Num = P + Rs Q (even, odd) for plain |S21| jobs, 4 = P and Q kept apart
  * CPLM   0 no coupler; 1 coupled-line block in front (its row vector is contracted with [P; Q] per point), mode angles from
  *        the nominal-angle tables / sincos; 2 the same with the angles carried by rotation from iteration to iteration;
- *        3 = 2 with equal even- and odd-mode angles
+ *        3 = 2 with equal even- and odd-mode angles; 4 a transmission line or a measured two-port in front instead
+ *        (TfParams::front: closed-form row vector with one sincos per point / row-vector table per grid point)
  * S11    the job has |S11| specs: S11 = (P - Rs Q) / (P + Rs Q), the denominators cancel
  * NS     spec slots: 4 or 8 (trackers of the sign kind are one 32-bit register each)
  * GD     the job has group-delay specs: tau = d arg(den)/dw = Re(Num'/Num - D'/D) / wref with the derivative polynomials
@@ -286,7 +299,8 @@ template <int NN, int DEN, int CPLM, bool S11, bool GD, int NS, int PP, int TPB,
 __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_constant__ TfParams P)
 {
     constexpr bool CPL = CPLM != 0;            /* coupled-line block in front */
-    constexpr bool ROT = CPLM >= 2;            /* ... with its mode angles advanced by rotation (uniformly spaced grid, matched source) */
+    constexpr bool ROT = CPLM == 2 || CPLM == 3;            /* ... with its mode angles advanced by rotation (uniformly spaced grid, matched source) */
+    constexpr bool FRONT = CPLM == 4;          /* a transmission line / measured two-port in front instead of the coupled-line section */
     constexpr bool SAME = CPLM == 3;           /* ... and equal even / odd angles for every sample (one angle, tf_cpl_matched_same) */
     constexpr int PTS = 2 * PP;
     constexpr int WARPS = TPB / 32;
@@ -454,6 +468,38 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                         const double s2 = fma(rso[p], stO_c, rco[p] * stO_s), c2 = fma(rco[p], stO_c, -rso[p] * stO_s);
                         rso[p] = s2; rco[p] = c2;
                     }
+                }
+            } else if (FRONT) {
+                double x[PTS], uar[PTS], uai[PTS], ubr[PTS], ubi[PTS];
+#pragma unroll
+                for (int qq = 0; qq < PP; qq++) { const double2 b = P.xt[j0 + 32 * qq]; x[2 * qq] = b.x; x[2 * qq + 1] = b.y; }
+                if (P.front == 1) {
+                    const LadV2<double> c01 = lad_lds2(cpls, 0.0);
+                    const double kt = lad_lds2(cpls + 16u, 0.0).x;
+#pragma unroll
+                    for (int qq = 0; qq < PP; qq++) {
+                        const double2 a = P.wt[j0 + 32 * qq];
+                        double sn, cs;
+                        sincos(kt * a.x, &sn, &cs);
+                        uar[2 * qq] = cs; uai[2 * qq] = c01.x * sn; ubr[2 * qq] = rs * cs; ubi[2 * qq] = c01.y * sn;
+                        sincos(kt * a.y, &sn, &cs);
+                        uar[2 * qq + 1] = cs; uai[2 * qq + 1] = c01.x * sn; ubr[2 * qq + 1] = rs * cs; ubi[2 * qq + 1] = c01.y * sn;
+                    }
+                } else {
+#pragma unroll
+                    for (int qq = 0; qq < PP; qq++) {
+                        const int j = j0 + 32 * qq;
+                        const double2 a = P.cse[j], b = P.cce[j], c = P.cso[j], d = P.cco[j];
+                        uar[2 * qq] = a.x; uar[2 * qq + 1] = a.y; uai[2 * qq] = b.x; uai[2 * qq + 1] = b.y;
+                        ubr[2 * qq] = c.x; ubr[2 * qq + 1] = c.y; ubi[2 * qq] = d.x; ubi[2 * qq + 1] = d.y;
+                    }
+                }
+                const double zq = P.zni;
+                QO_PTS {
+                    const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                    const double nr = fma(uar[p], r[0][p], fma(-uai[p], pi_, fma(ubr[p], qr, -ubi[p] * qi)));
+                    const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
+                    n2[p] = fma(nr, nr, ni * ni);
                 }
             } else {
                 double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];

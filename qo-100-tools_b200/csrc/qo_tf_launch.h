@@ -12,7 +12,8 @@ struct TfPlan {
     int kn, kd;          /* coefficient pairs kept per numerator polynomial; E coefficients (even count) or D pairs kept */
     int deg;             /* structural degree of the numerator polynomials */
     int el0, n_el;       /* the lumped ops */
-    int cpl_op;          /* the coupled-line op in front, -1 = none */
+    int cpl_op;          /* the block in front of the lumped ops (its row vector is contracted with [P; Q] per point), -1 = none */
+    int front;           /* what that block is: 0 coupled-line section, 1 transmission line (OP_TLINE), 2 measured two-port (OP_SBLOCK) */
     double wref;         /* normalising angular frequency (geometric centre of the grid) */
     double err;          /* worst relative disagreement on |den|^2 seen by the self-check */
     const char *reason;  /* "ok", or why the job stays on the chain kernels */

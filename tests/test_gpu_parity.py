@@ -476,7 +476,10 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     w5 = W.cfg5()
     p = Q.Plan(ctx, w5.net, w5.f, w5.specs, seed=1, tols=w5.tols); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()
     tl = Q.Net.from_elements([(Q.TLINE, [50.0, 90.0, 1e9])] + w.net.elements, 50.0, 50.0)
-    p = Q.Plan(ctx, tl, w.f, w.specs, seed=1); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()            # a line in the cascade: no polynomial form
+    p = Q.Plan(ctx, tl, w.f, w.specs, seed=1); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()                # a line in FRONT: its row vector times the polynomials behind it
+    el = w.net.elements
+    tl = Q.Net.from_elements(el[:4] + [(Q.TLINE, [50.0, 90.0, 1e9])] + el[4:], 50.0, 50.0)
+    p = Q.Plan(ctx, tl, w.f, w.specs, seed=1); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()            # a line inside the cascade: no polynomial form
     for nf, butter, dist in ((1, False, Q.DIST_UNIFORM), (2, False, Q.DIST_UNIFORM), (63, True, Q.DIST_GAUSS3S),
                              (130, False, Q.DIST_GAUSS3S), (257, True, Q.DIST_UNIFORM)):
         fc = 10e6
@@ -614,6 +617,64 @@ def test_touchstone_blocks_in_cascade(Q, R, W, ctx, golden_s2p):
     # bare block: the sweep returns the interpolated measurement itself
     bare = ctx.sweep(blk["pa_20W"][0].as_net(True), fd[10:20])
     assert np.allclose(np.stack([bare[0], bare[1], bare[2], bare[3]], 1), sd[10:20], rtol=1e-9, atol=1e-12)
+    R.sblock_clear()
+
+
+def test_tf_kernel_front_block_line_and_measured_two_port(Q, R, W, ctx, golden_s2p, monkeypatch):
+    """A transmission line (perturbed Z0 and length) or a measured two-port (the Coilcraft inductor of
+    pa-bias-simulation.sch:39) in FRONT of a lumped ladder runs on the transfer-function kernel: the block's row vector
+    [1 Rs] M is evaluated per point and contracted with the polynomials of the ladder behind it.  Counters and histogram
+    equal the interpreter's (QO100NET_TF_NO_FRONT=1) and the oracle's."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    fc = 10e6
+    lad, f, ltol = _ladder_workload(Q, W, 7, True, False, nf=700)
+    n = 3000
+    # (a) 75 Ohm line, 35 deg at fc, in a 50 Ohm system: Z0 +-5 %, length +-3 %
+    line = Q.Net.from_elements([(Q.TLINE, [75.0, 35.0, fc])], 50.0, 50.0)
+    net = line.concat(lad)
+    tols = [(0, 0, 0, Q.TOL_REL, 0.05), (0, 1, 1, Q.TOL_REL, 0.03)] + [(e + 1, p_, v + 2, m, t) for (e, p_, v, m, t) in ltol]
+    nom = ctx.sweep(net, f)
+    db = 20 * np.log10(np.abs(nom[1]))
+    pb, sb = f <= 0.9 * fc, f >= 2.0 * fc
+    specs = [(Q.SPEC_S21_MIN_DB, 0.0, 0.9 * fc, float(db[pb].min()) - 0.25), (Q.SPEC_S21_MAX_DB, 2.0 * fc, 1e99, float(db[sb].max()) + 1.0)]
+    hist = dict(hist_bins=32, hist_spec=0, hist_lo=float(db[pb].min()) - 2.0, hist_hi=float(db[pb].min()) + 0.5)
+    plan = Q.Plan(ctx, net, f, specs, seed=9, tols=tols, **hist)
+    assert plan.kernel_name == "qo_mc_tf_kernel" and plan.tf_info["numerator_chains"] == 4
+    plan.launch(2 ** 33 + 3, n)
+    got = plan.read()
+    plan.close()
+    monkeypatch.setenv("QO100NET_TF_NO_FRONT", "1")
+    plan = Q.Plan(ctx, net, f, specs, seed=9, tols=tols, **hist)
+    assert plan.kernel_name == "qo_mc_lumped_kernel"
+    plan.launch(2 ** 33 + 3, n)
+    interp = plan.read()
+    plan.close()
+    monkeypatch.delenv("QO100NET_TF_NO_FRONT", raising=False)
+    _assert_counts_equal(interp, got)
+    ref = R.mc_run(to_ref(R, net), 50, 50, f, specs, R.mc_cfg(9, n, tols, sample_offset=2 ** 33 + 3, **hist), nthreads=8)
+    _assert_counts_equal(ref, got)
+    assert 0 < got["n_pass"] < n
+    # (b) the measured inductor in front (no tolerances on the block), rectangular and polar interpolation
+    fd, sd, z0 = golden_s2p["11SQ39N_f"], golden_s2p["11SQ39N_s"], float(golden_s2p["11SQ39N_z0"])
+    blk = Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    R.sblock_clear()
+    R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    lad2, f2, ltol2 = _ladder_workload(Q, W, 5, False, False, fc=400e6, nf=513)
+    for polar in (True, False):
+        net2 = blk.as_net(polar, 50.0, 50.0).concat(lad2)
+        tols2 = [(e + 1, p_, v, m, t) for (e, p_, v, m, t) in ltol2]
+        nom = ctx.sweep(net2, f2)
+        db = 20 * np.log10(np.abs(nom[1]))
+        pb, sb = f2 <= 0.8 * 400e6, f2 >= 2.0 * 400e6
+        specs2 = [(Q.SPEC_S21_MIN_DB, 0.0, 0.8 * 400e6, float(db[pb].min()) - 0.2), (Q.SPEC_S21_MAX_DB, 2.0 * 400e6, 1e99, float(db[sb].max()) + 1.5)]
+        plan = Q.Plan(ctx, net2, f2, specs2, seed=4, tols=tols2)
+        assert plan.kernel_name == "qo_mc_tf_kernel"
+        plan.launch(17, n)
+        got2 = plan.read()
+        plan.close()
+        ref2 = R.mc_run(to_ref(R, net2), 50, 50, f2, specs2, R.mc_cfg(4, n, tols2, sample_offset=17), nthreads=8)
+        _assert_counts_equal(ref2, got2)
+        assert 0 < got2["n_pass"] < n
     R.sblock_clear()
 
 

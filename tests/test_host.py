@@ -437,15 +437,25 @@ def test_transfer_function_plan_analysis(Q, W, monkeypatch):
     # jobs that stay on the chain kernels, with the reason
     a11 = Q.plan_analyze(w.net, w.f, [(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], w.tols)
     assert a11["selected"] and a11["numerator_chains"] == 4 and a11["den_form"] == "none"      # S11 = (P - Rs Q)/(P + Rs Q): denominators cancel
-    assert Q.plan_analyze(w5.net, w5.f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], w5.tols)["reason"] == "|S11| specs behind a coupled-line block"
+    assert Q.plan_analyze(w5.net, w5.f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], w5.tols)["reason"] == "|S11| specs behind a front block"
     agd = Q.plan_analyze(w.net, w.f, [(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S21_MIN_DB, 0.0, 9.5e6, -2.0)], w.tols)
     assert agd["selected"] and agd["den_form"] == "DD" and agd["kn"] == 12 and agd["self_check_err"] < 1e-10   # derivative polynomials: nothing dropped
     assert Q.plan_analyze(w.net, w.f, [(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)], w.tols)["reason"] == \
-        "group-delay specs mixed with a coupled-line block or |S11| specs"
+        "group-delay specs mixed with a front block or |S11| specs"
+    # a transmission line in FRONT of the ladder keeps the polynomial route (4 chains, row vector per point); inside the cascade it does not
+    el = w.net.elements
+    front = Q.Net.from_elements([(Q.TLINE, [75.0, 35.0, 10e6])] + el, 50.0, 50.0)
+    af = Q.plan_analyze(front, w.f, w.specs, [(e + 1, p_, v, m, t) for (e, p_, v, m, t) in w.tols] + [(0, 0, 30, Q.TOL_REL, 0.05)])
+    assert af["selected"] and af["numerator_chains"] == 4 and af["kn"] == a["kn"]
+    monkeypatch.setenv("QO100NET_TF_NO_FRONT", "1")
+    assert Q.plan_analyze(front, w.f, w.specs, [])["reason"] == "non-lumped element"
+    monkeypatch.delenv("QO100NET_TF_NO_FRONT")
+    inside = Q.Net.from_elements(el[:4] + [(Q.TLINE, [75.0, 35.0, 10e6])] + el[4:], 50.0, 50.0)
+    assert Q.plan_analyze(inside, w.f, w.specs, [])["reason"] == "non-lumped element"
     assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=32)["reason"] == "not a reduce-only FP64 job on a lumped cascade"
     assert Q.plan_analyze(w.net, w.f, w.specs, w.tols, precision=32)["selected"] is False
     assert Q.plan_analyze(w.net, w.f, [], w.tols, mode=Q.MODE_FULL_S)["selected"] is False
-    tl = Q.Net.from_elements([(Q.TLINE, [50.0, 90.0, 1e9])] + w.net.elements, 50.0, 50.0)
+    tl = Q.Net.from_elements(w.net.elements + [(Q.TLINE, [50.0, 90.0, 1e9])], 50.0, 50.0)       # a line at the load end
     assert Q.plan_analyze(tl, w.f, w.specs)["reason"] == "non-lumped element"
     assert Q.plan_analyze(W.pa_lpf_net(), w.f, w.specs)["selected"] is False
     monkeypatch.setenv("QO100NET_TF_TOL", "1e-16")

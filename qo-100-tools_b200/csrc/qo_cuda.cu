@@ -1117,7 +1117,7 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         if (cfg->n_tol > 0 && cfg->tol) mix(cfg->tol, (size_t)cfg->n_tol * sizeof(qo_tol));
         const long long scal[8] = { (long long)cfg->seed, cfg->dist, cfg->n_tol, cfg->mode, cfg->precision, cfg->hist_bins, cfg->hist_spec, nspec };
         mix(scal, sizeof scal); mix(&cfg->hist_lo, sizeof(double)); mix(&cfg->hist_hi, sizeof(double));
-        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS" };
+        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT", "QO100NET_CPL_GENERAL", "QO100NET_CPL_NO_ROT", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS" };
         for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) { const char *v = getenv(envs[i]); mix(v ? v : "\1", v ? strlen(v) + 1 : 1); }
     }
     qo_plan *p = NULL;

@@ -273,6 +273,41 @@ def single_process_ctx_leg(Q, ngpus, n_samples, expect=None):
     return out
 
 
+def nodal_leg(Q, ctx):
+    """Row N4: Monte-Carlo yield of the reference's 5-port bias network (util/pa-bias-simulation/pa-bias-simulation.sch:
+    19-72, 23 unknowns, every R +-1 % and C +-5 %) on |S21| and |S31|, 500 000 samples x 1000 points -- the size at which the
+    library compiles the job's factorisation plan into a kernel of its own (NVRTC) -- next to the interpreted static-plan kernel."""
+    import numpy as np
+    from qo100net import workloads as W
+    g = np.load(os.path.join(ROOT, "tests", "golden", "touchstone.npz"))        # the measured inductor of pa-bias-simulation.sch:39
+    nd, _br, tols = W.pa_bias_nodal(Q, g["11SQ39N_f"], g["11SQ39N_s"])
+    nf, n = 1000, 500000
+    f = Q.grid_lin(1e8, 3e9, nf)
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, -3.0), (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, -25.0)]
+    hist = dict(hist_bins=64, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)
+    out = {"workload": "pa-bias 5-port network, 23 unknowns, %d samples x %d points, yield on S21 and S31" % (n, nf), "unit": "points/s"}
+    saved = os.environ.pop("QO100NET_NODAL", None)
+    try:
+        compile_s, best = 0.0, None
+        for rep in range(3):
+            r = ctx.nodal_mc_run(nd, f, specs, 5, n, tols, sample_offset=rep * n, **hist)
+            compile_s = max(compile_s, ctx.nodal_last_compile_seconds())
+            best = r if best is None or r["seconds"] < best["seconds"] else best
+        out.update({"kernel": ctx.nodal_last_kernel(), "value": n * nf / best["seconds"], "kernel_seconds": best["seconds"],
+                    "compile_seconds_first_call": compile_s, "n_pass": int(best["n_pass"]), "n_total": int(best["n_total"])})
+        os.environ["QO100NET_NODAL"] = "static"
+        ni = 100000
+        ctx.nodal_mc_run(nd, f, specs, 5, 512, tols, **hist)
+        ri = ctx.nodal_mc_run(nd, f, specs, 5, ni, tols, **hist)
+        out["interpreted_plan"] = {"kernel": ctx.nodal_last_kernel(), "value": ni * nf / ri["seconds"]}
+    finally:
+        os.environ.pop("QO100NET_NODAL", None)
+        if saved is not None:
+            os.environ["QO100NET_NODAL"] = saved
+        nd.close()
+    return out
+
+
 def full_s_leg(Q, torch, ctx, stream):
     """HBM-bound mode (BASELINE config 4): the full S-matrix written out, 64 B/eval, at the named shape -- 65 536 samples x 4096
     points per filter (17.2 GB), all four filters of the GPSDO bank."""
@@ -551,6 +586,10 @@ def main():
             line["roofline_hbm"] = full_s_leg(Q, torch, ctx, stream)
         except Exception as ex4:
             line["roofline_hbm"] = {"error": str(ex4)}
+        try:
+            line["nodal"] = nodal_leg(Q, ctx)
+        except Exception as ex5:
+            line["nodal"] = {"error": str(ex5)}
     emit(line)
     if dist is not None:
         dist.barrier()

@@ -14,43 +14,9 @@ NB_R, NB_L, NB_C, NB_VCVS, NB_SBLOCK = 1, 2, 3, 4, 5
 
 
 def hand_netlist():
-    """pa-bias-simulation.sch read by hand (component line numbers in comments).  Nodes:
-    1 P1/R17/VCVS in+ | 2 VCVS SRC3 out+ | 3 R16-C12 | 4 rail (610,670) | 5 SPfile far side (890,400) | 6 C9-R1 |
-    7 P3 | 8 C2-R2 | 9 C3-R3 | 10 R9-C1 | 11 P2 | 12 C4-R4 ; second sub-circuit: 13 P6(port 4)/R19/VCVS in+ |
-    14 SRC4 out+ | 15 R18-C13 | 16 rail | 17 C6-R6 | 18 C7-R7 | 19 R10-C5 | 20 P5 | 21 C8-R8."""
-    R, C, V, S = NB_R, NB_C, NB_VCVS, NB_SBLOCK
-    br = [
-        (R, [1, 0], [50.0]),                 # R17 :48
-        (V, [1, 2, 0, 0], [1.0, 0.0]),       # SRC3 :40
-        (R, [2, 3], [2.6]),                  # R16 :41
-        (C, [3, 4], [26.5e-12, 0, 0]),       # C12 :42
-        (S, [4, 5, 0], [0, 1, 50.0]),        # L_11SQ39N :39
-        (C, [5, 6], [100e-6, 0, 0]),         # C9 :24
-        (R, [6, 0], [10.0]),                 # R1 :35
-        (R, [5, 7], [1000.0]),               # R11 :36
-        (C, [4, 8], [2.2e-12, 0, 0]),        # C2 :28
-        (R, [8, 0], [3.0]),                  # R2 :32
-        (C, [4, 9], [1.8e-12, 0, 0]),        # C3 :29
-        (R, [9, 0], [3.7]),                  # R3 :33
-        (R, [4, 10], [0.6]),                 # R9 :34
-        (C, [10, 11], [12e-12, 0, 0]),       # C1 :19
-        (C, [11, 12], [1.2e-12, 0, 0]),      # C4 :20
-        (R, [12, 0], [5.5]),                 # R4 :27
-        (R, [13, 0], [50.0]),                # R19 :67
-        (V, [13, 14, 0, 0], [1.0, 0.0]),     # SRC4 :59
-        (R, [14, 15], [2.6]),                # R18 :60
-        (C, [15, 16], [26.5e-12, 0, 0]),     # C13 :61
-        (C, [16, 17], [2.2e-12, 0, 0]),      # C6 :53
-        (R, [17, 0], [3.0]),                 # R6 :57
-        (C, [16, 18], [1.8e-12, 0, 0]),      # C7 :54
-        (R, [18, 0], [3.7]),                 # R7 :58 (sic: R7 3.7)
-        (R, [16, 19], [0.6]),                # R10 :56
-        (C, [19, 20], [12e-12, 0, 0]),       # C5 :49
-        (C, [20, 21], [1.2e-12, 0, 0]),      # C8 :50
-        (R, [21, 0], [5.5]),                 # R8 :52
-    ]
-    ports = [(1, 50.0), (11, 50.0), (7, 50.0), (13, 50.0), (20, 50.0)]     # Pac numbers 1..5 (P6 carries number 4)
-    return br, 21, ports
+    """pa-bias-simulation.sch read by hand (qo100net.workloads.pa_bias_netlist holds the list, with the component line numbers)."""
+    from qo100net import workloads
+    return workloads.pa_bias_netlist()
 
 
 DAT_ENTRIES = {"S1_1": (0, 0), "S1_2": (0, 1), "S1_3": (0, 2), "S2_1": (1, 0), "S2_2": (1, 1), "S2_3": (1, 2),

@@ -28,8 +28,10 @@ def main():
     import qo100net as Q
     from oracle import refbind as R
     import test_nodal as T
+    from qo100net import workloads as W
     g = np.load(os.path.join(ROOT, "tests", "golden", "touchstone.npz"))
-    nd, br, nn, ports = T.build_nodal(Q, g)
+    nd, br, _tols = W.pa_bias_nodal(Q, g["11SQ39N_f"], g["11SQ39N_s"])
+    _b, nn, ports = W.pa_bias_netlist()
     T.register_inductor(R, g)
     ctx = Q.Context(device=0)
     f = Q.grid_lin(1e8, 3e9, args.nf)

@@ -862,34 +862,44 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
         }
     } else if (force && !strcmp(force, "jit")) { qo_set_error("QO100NET_NODAL=jit: the static plan failed its self-check for this network"); return QO_ERR_UNSUPPORTED; }
 
-    DevCtx *dc = &ctx->d[0];                 /* device 0 of the ctx: the nodal path is not sharded yet */
-    CU(cudaSetDevice(dc->device));
-    NodalProg *dprog = NULL;
-    NodalStatic *dsp = NULL;
-    double *dfr = NULL;
-    unsigned char *dmask = NULL;
-    double2 *dy = NULL, *ds = NULL;
-    unsigned long long *dcnt = NULL;
+    /* samples are independent: GPU g of the ctx takes the contiguous range [N g / G, N (g+1) / G) of the job (the Philox counter
+     * carries the global sample index, so the counters do not depend on G); the host adds the u64 counters, FULL_S slabs are
+     * copied back one after the other */
+    const int G = (N >= (unsigned long long)ctx->ndev * 64ull) ? ctx->ndev : 1;
+    struct NodalDev {
+        NodalProg *dprog; NodalStatic *dsp; double *dfr; unsigned char *dmask; double2 *dy, *ds; unsigned long long *dcnt;
+        unsigned long long off, n;
+        int grid;
+    } nv[8];
+    memset(nv, 0, sizeof nv);
     int rc = QO_OK;
-    const size_t s_elems = full ? (size_t)N * nf * nd->np * nd->np : 0;
+    const int np_ = nd->np;
+    std::vector<unsigned long long> h((size_t)ncnt + 1, 0ull), hg((size_t)ncnt + 1);
+    float ms_max = 0.0f;
+    int chunk_len = nf, nchunks = 1;
+    /* FULL_S: cut the grid into QN_TPB-point chunks so that a nominal sweep fills the GPU */
+    if (full) { chunk_len = QN_TPB; nchunks = (nf + chunk_len - 1) / chunk_len; }
+    double growth2 = QN_GROWTH2;
+    { const char *e = getenv("QO100NET_NODAL_GUARD2"); if (e && atof(e) > 0.0) growth2 = atof(e); }     /* tests: trip the device guard on purpose */
 #define CUN(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); rc = e_ == cudaErrorMemoryAllocation ? QO_ERR_NOMEM : QO_ERR_CUDA; goto out; } } while (0)
-    {
-        CUN(cudaMallocAsync((void **)&dprog, sizeof(NodalProg), dc->stream));
-        CUN(cudaMallocAsync((void **)&dsp, sizeof(NodalStatic), dc->stream));
-        CUN(cudaMemcpyAsync(dsp, &spv[0], sizeof(NodalStatic), cudaMemcpyHostToDevice, dc->stream));
-        CUN(cudaMallocAsync((void **)&dfr, (size_t)nf * sizeof(double), dc->stream));
-        CUN(cudaMallocAsync((void **)&dmask, (size_t)nf, dc->stream));
-        CUN(cudaMallocAsync((void **)&dy, (yb.size() ? yb.size() : 1) * sizeof(double2), dc->stream));
-        CUN(cudaMallocAsync((void **)&dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));     /* + the suspect-point counter of the static kernel */
-        if (full) CUN(cudaMallocAsync((void **)&ds, s_elems * sizeof(double2), dc->stream));
-        CUN(cudaMemcpyAsync(dprog, hp, sizeof(NodalProg), cudaMemcpyHostToDevice, dc->stream));
-        CUN(cudaMemcpyAsync(dfr, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, dc->stream));
-        CUN(cudaMemcpyAsync(dmask, mask.data(), (size_t)nf, cudaMemcpyHostToDevice, dc->stream));
-        if (!yb.empty()) CUN(cudaMemcpyAsync(dy, yb.data(), yb.size() * sizeof(double2), cudaMemcpyHostToDevice, dc->stream));
-        /* FULL_S: cut the grid into QN_TPB-point chunks so that a nominal sweep fills the GPU */
-        int chunk_len = nf, nchunks = 1;
-        if (full) { chunk_len = QN_TPB; nchunks = (nf + chunk_len - 1) / chunk_len; }
-        const unsigned long long units = N * (unsigned long long)nchunks;
+    for (int g = 0; g < G; g++) {
+        DevCtx *dc = &ctx->d[g];
+        NodalDev &v = nv[g];
+        v.off = N * (unsigned long long)g / (unsigned long long)G;
+        v.n = N * (unsigned long long)(g + 1) / (unsigned long long)G - v.off;
+        CUN(cudaSetDevice(dc->device));
+        CUN(cudaMallocAsync((void **)&v.dprog, sizeof(NodalProg), dc->stream));
+        CUN(cudaMallocAsync((void **)&v.dsp, sizeof(NodalStatic), dc->stream));
+        CUN(cudaMemcpyAsync(v.dsp, &spv[0], sizeof(NodalStatic), cudaMemcpyHostToDevice, dc->stream));
+        CUN(cudaMallocAsync((void **)&v.dfr, (size_t)nf * sizeof(double), dc->stream));
+        CUN(cudaMallocAsync((void **)&v.dmask, (size_t)nf, dc->stream));
+        CUN(cudaMallocAsync((void **)&v.dy, (yb.size() ? yb.size() : 1) * sizeof(double2), dc->stream));
+        CUN(cudaMallocAsync((void **)&v.dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));     /* + the suspect-point counter of the static kernels */
+        if (full) CUN(cudaMallocAsync((void **)&v.ds, (size_t)v.n * nf * np_ * np_ * sizeof(double2), dc->stream));
+        CUN(cudaMemcpyAsync(v.dprog, hp, sizeof(NodalProg), cudaMemcpyHostToDevice, dc->stream));
+        CUN(cudaMemcpyAsync(v.dfr, f, (size_t)nf * sizeof(double), cudaMemcpyHostToDevice, dc->stream));
+        CUN(cudaMemcpyAsync(v.dmask, mask.data(), (size_t)nf, cudaMemcpyHostToDevice, dc->stream));
+        if (!yb.empty()) CUN(cudaMemcpyAsync(v.dy, yb.data(), yb.size() * sizeof(double2), cudaMemcpyHostToDevice, dc->stream));
         /* persistent grid = exactly the resident blocks (a larger grid runs in 1.6 waves: 4.0e8 instead of 4.4e8
          * points/s on the reference network); latency hiding matters more here than the private arrays' L2 footprint */
         int bps = 0;
@@ -911,20 +921,25 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
             }
             if (bps <= 0) bps = 8;
         }
+        const unsigned long long units = v.n * (unsigned long long)nchunks;
         const unsigned long long cap = (unsigned long long)dc->sm_count * (unsigned long long)bps;
-        const int grid = (int)(units < cap ? units : cap);
-        std::vector<unsigned long long> h((size_t)ncnt + 1);
-        double growth2 = QN_GROWTH2;
-        { const char *e = getenv("QO100NET_NODAL_GUARD2"); if (e && atof(e) > 0.0) growth2 = atof(e); }     /* tests: trip the device guard on purpose */
-      relaunch:
-        CUN(cudaMemsetAsync(dcnt, 0, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));
+        v.grid = (int)(units < cap ? units : cap);
+    }
+  relaunch:
+    for (int g = 0; g < G; g++) {
+        DevCtx *dc = &ctx->d[g];
+        NodalDev &v = nv[g];
+        const int grid = v.grid;
+        const unsigned long long off_g = cfg->sample_offset + v.off;
+        CUN(cudaSetDevice(dc->device));
+        CUN(cudaMemsetAsync(v.dcnt, 0, (size_t)(ncnt + 1) * sizeof(unsigned long long), dc->stream));
         cudaEventRecord(dc->ev0, dc->stream);
-#define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(dprog, dsp, dfr, dmask, dy, nf, chunk_len, nchunks, cfg->sample_offset, N, dcnt, ds, growth2)
+#define QN_LAUNCH(LDV, MD, NZ, SM) qo_nodal_kernel<LDV, MD, NZ><<<grid, QN_TPB, SM, dc->stream>>>(v.dprog, v.dsp, v.dfr, v.dmask, v.dy, nf, chunk_len, nchunks, off_g, v.n, v.dcnt, v.ds, growth2)
         g_last_kernel = use_static ? "qo_nodal_kernel<static,local>" : "qo_nodal_kernel<dense>";
         if (use_static && jit) {
             int nf_ = nf;
-            unsigned long long off_ = cfg->sample_offset, n_ = N;
-            void *args[] = { &dprog, &dfr, &dmask, &dy, &nf_, &chunk_len, &nchunks, &off_, &n_, &dcnt, &ds, &growth2 };
+            unsigned long long off_ = off_g, n_ = v.n;
+            void *args[] = { &v.dprog, &v.dfr, &v.dmask, &v.dy, &nf_, &chunk_len, &nchunks, &off_, &n_, &v.dcnt, &v.ds, &growth2 };
             CUN(cudaLaunchKernel((const void *)jit->kern, dim3((unsigned)grid), dim3(QN_TPB), args, 0, dc->stream));
             g_last_kernel = "qo_nodal_jit_kernel";
         } else if (use_static) {
@@ -949,35 +964,49 @@ static int nodal_run(qo_ctx *ctx, const qo_nodal *nd, const double *f, int nf, c
 #undef QN_LAUNCH
         cudaEventRecord(dc->ev1, dc->stream);
         CUN(cudaGetLastError());
+    }
+    for (size_t i = 0; i < h.size(); i++) h[i] = 0ull;
+    ms_max = 0.0f;
+    for (int g = 0; g < G; g++) {
+        DevCtx *dc = &ctx->d[g];
+        CUN(cudaSetDevice(dc->device));
         CUN(cudaStreamSynchronize(dc->stream));
-        CUN(cudaMemcpy(h.data(), dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        if (use_static && h[ncnt] != 0) {
-            /* some (sample, frequency) point met a multiplier above QN_GROWTH2 (or a NaN) under the fixed pivot order: the whole
-             * job is redone with per-point partial pivoting */
-            if (force && !strcmp(force, "static")) { qo_set_error("QO100NET_NODAL=static: %llu points needed another pivot order", h[ncnt]); rc = QO_ERR_UNSUPPORTED; goto out; }
-            if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: %llu suspect points under the static plan, re-running on the dense kernel\n", h[ncnt]);
-            use_static = false;
-            goto relaunch;
+        CUN(cudaMemcpy(hg.data(), nv[g].dcnt, (size_t)(ncnt + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < h.size(); i++) h[i] += hg[i];
+        float ms = 0;
+        cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
+        if (ms > ms_max) ms_max = ms;
+    }
+    if (use_static && h[ncnt] != 0) {
+        /* some (sample, frequency) point met a multiplier above QN_GROWTH2 (or a NaN) under the fixed pivot order: the whole
+         * job is redone with per-point partial pivoting */
+        if (force && !strcmp(force, "static")) { qo_set_error("QO100NET_NODAL=static: %llu points needed another pivot order", h[ncnt]); rc = QO_ERR_UNSUPPORTED; goto out; }
+        if (getenv("QO100NET_NODAL_DEBUG")) fprintf(stderr, "qo_nodal: %llu suspect points under the static plan, re-running on the dense kernel\n", h[ncnt]);
+        use_static = false;
+        goto relaunch;
+    }
+    if (full)
+        for (int g = 0; g < G; g++) {
+            CUN(cudaSetDevice(ctx->d[g].device));
+            CUN(cudaMemcpy(full_s_host + (size_t)nv[g].off * nf * np_ * np_, nv[g].ds, (size_t)nv[g].n * nf * np_ * np_ * sizeof(double2), cudaMemcpyDeviceToHost));
         }
-        if (full) CUN(cudaMemcpy(full_s_host, ds, s_elems * sizeof(double2), cudaMemcpyDeviceToHost));
-        if (res) {
-            float ms = 0;
-            cudaEventElapsedTime(&ms, dc->ev0, dc->ev1);
-            res->n_pass = full ? 0 : h[0];
-            res->n_total = full ? N : h[1];
-            if (res->fail_per_spec) for (int s = 0; s < nspec; s++) res->fail_per_spec[s] = h[2 + s];
-            if (res->hist) for (int b = 0; b < hp->hist_bins; b++) res->hist[b] = h[2 + nspec + b];
-            res->seconds = ms * 1e-3;
-            res->evals_per_s = ms > 0 ? (double)N * nf / (ms * 1e-3) : 0.0;
-            res->flops_per_eval = (8.0 / 3.0) * n_unk * n_unk * n_unk + 8.0 * nd->np * n_unk * n_unk;   /* DENSE LU + substitutions, real flops */
-        }
+    if (res) {
+        res->n_pass = full ? 0 : h[0];
+        res->n_total = full ? N : h[1];
+        if (res->fail_per_spec) for (int s = 0; s < nspec; s++) res->fail_per_spec[s] = h[2 + s];
+        if (res->hist) for (int b = 0; b < hp->hist_bins; b++) res->hist[b] = h[2 + nspec + b];
+        res->seconds = ms_max * 1e-3;
+        res->evals_per_s = ms_max > 0 ? (double)N * nf / (ms_max * 1e-3) : 0.0;
+        res->flops_per_eval = (8.0 / 3.0) * n_unk * n_unk * n_unk + 8.0 * nd->np * n_unk * n_unk;   /* DENSE LU + substitutions, real flops */
     }
 out:
 #undef CUN
-    {
-        void *ptrs[] = { dprog, dsp, dfr, dmask, dy, dcnt, ds };
-        for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], dc->stream);
+    for (int g = 0; g < G; g++) {
+        void *ptrs[] = { nv[g].dprog, nv[g].dsp, nv[g].dfr, nv[g].dmask, nv[g].dy, nv[g].dcnt, nv[g].ds };
+        cudaSetDevice(ctx->d[g].device);
+        for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], ctx->d[g].stream);
     }
+    cudaSetDevice(ctx->d[0].device);
     return rc;
 }
 

@@ -341,3 +341,32 @@ def test_gpu_nodal_compiled_kernel_equals_interpreted_dense_and_oracle(Q, R, ctx
     assert ctx.nodal_last_kernel() == "qo_nodal_kernel<dense>" and again["n_pass"] == got["n_pass"]
     R.sblock_clear()
     nd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_job_sharded_over_the_gpus_of_a_ctx(Q, ctx, pa_bias, golden_s2p, monkeypatch):
+    """qo_ctx_create(N): a nodal Monte-Carlo job is cut into N contiguous sample ranges, one per GPU; counters, histogram and
+    FULL_S planes equal the one-GPU result (the Philox counter carries the global sample index)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    f = pa_bias["frequency"][100:1400:13]
+    specs = [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, -3.0), (Q.SPEC_S21_MAX_DB, 2, 0, 2.3e9, 2.5e9, -25.0)]
+    tols = [(i, 0, v, Q.TOL_REL, 0.05 if k == NB_C else 0.01) for v, (i, (k, _n, _p)) in
+            enumerate((i, b) for i, b in enumerate(br) if b[0] in (NB_R, NB_C))]
+    hist = dict(hist_bins=20, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)
+    ng = 4 if torch.cuda.device_count() >= 4 else 2
+    cm = Q.Context(ngpus=ng)
+    for mode in ("static", "jit"):
+        monkeypatch.setenv("QO100NET_NODAL", mode)
+        one = ctx.nodal_mc_run(nd, f, specs, 3, 10001, tols, sample_offset=77, **hist)
+        many = cm.nodal_mc_run(nd, f, specs, 3, 10001, tols, sample_offset=77, **hist)
+        assert many["n_total"] == 10001 and many["n_pass"] == one["n_pass"] and 0 < one["n_pass"] < 10001
+        assert np.array_equal(many["fail_per_spec"], one["fail_per_spec"]) and np.array_equal(many["hist"], one["hist"])
+        s1 = ctx.nodal_mc_run(nd, f[:17], [], 3, 131, tols, mode=Q.MODE_FULL_S)["s"]
+        sm = cm.nodal_mc_run(nd, f[:17], [], 3, 131, tols, mode=Q.MODE_FULL_S)["s"]
+        assert np.array_equal(s1, sm)
+    cm.close()
+    nd.close()

@@ -25,6 +25,7 @@
 #include "qo_spot.cuh"
 #include "qo_tf_fs.cuh"
 #include "qo_ustrip.cuh"
+#include "qo_ustrip_board.cuh"
 #include "qo_cpl_core.h"
 
 static int nccl_load(NcclApi *a)
@@ -75,6 +76,7 @@ struct qo_plan {
     qo_ctx *ctx;
     DevProg hp;                /* host copy of the program */
     int nf, npairs, ncnt, precision, mode, generic;
+    int board;                                            /* microstrip yield job at <= 4 frequencies: thread-per-board kernel */
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
     int spot, spot_el0, spot_nel;                         /* spot-frequency kernel (qo_spot.cuh): <= 8 points per sample */
@@ -454,7 +456,8 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     p->tf = qo_tf_plan_check(&p->hp, p->mode == QO_MODE_REDUCE_ONLY, p->precision, p->generic, f, nf, p->maskv.data(), &p->tfp);
     p->spot = spot_eligible(&p->hp, p->mode, p->precision, p->generic, nf, &p->spot_el0, &p->spot_nel);
     if (p->spot) p->tf = p->ladder = 0;
-    p->kernel_name = p->generic ? "qo_mc_generic_kernel" : p->spot ? "qo_mc_spot_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
+    { const char *e = getenv("QO100NET_USTRIP"); p->board = p->generic && p->mode == QO_MODE_REDUCE_ONLY && nf <= QO_B_MAXNF && !(e && !strcmp(e, "item")); }
+    p->kernel_name = p->board ? "qo_mc_board_kernel" : p->generic ? "qo_mc_generic_kernel" : p->spot ? "qo_mc_spot_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
     const double two_pi = 6.283185307179586476925286766559;
@@ -977,6 +980,19 @@ static int launch_generic(qo_plan *p, int g, unsigned long long off, unsigned lo
 {
     DevCtx *dc = &p->ctx->d[g];
     DevPlan *d = &p->d[g];
+    if (p->board) {
+        /* yield at a handful of frequencies: one thread per board, the frequencies side by side (qo_ustrip_board.cuh) */
+        const unsigned long long cap = (unsigned long long)dc->sm_count * QO_B_MINB, want = (n + QO_B_TPB - 1) / QO_B_TPB;
+        const int grid = (int)(want < cap ? want : cap);
+        switch (p->nf) {
+        case 1: qo_mc_board_kernel<1><<<grid, QO_B_TPB, 0, dc->stream>>>(d->prog, d->fgrid, d->mask, off, n, cnt); break;
+        case 2: qo_mc_board_kernel<2><<<grid, QO_B_TPB, 0, dc->stream>>>(d->prog, d->fgrid, d->mask, off, n, cnt); break;
+        case 3: qo_mc_board_kernel<3><<<grid, QO_B_TPB, 0, dc->stream>>>(d->prog, d->fgrid, d->mask, off, n, cnt); break;
+        default: qo_mc_board_kernel<4><<<grid, QO_B_TPB, 0, dc->stream>>>(d->prog, d->fgrid, d->mask, off, n, cnt); break;
+        }
+        CU(cudaGetLastError());
+        return QO_OK;
+    }
     int sb, f_chunk = p->nf, n_fchunks = 1;
     if (full_s) {
         /* no per-sample reduction: cut (sample, frequency) space into ~QO_G_TPB-item tiles */
@@ -1117,7 +1133,7 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         if (cfg->n_tol > 0 && cfg->tol) mix(cfg->tol, (size_t)cfg->n_tol * sizeof(qo_tol));
         const long long scal[8] = { (long long)cfg->seed, cfg->dist, cfg->n_tol, cfg->mode, cfg->precision, cfg->hist_bins, cfg->hist_spec, nspec };
         mix(scal, sizeof scal); mix(&cfg->hist_lo, sizeof(double)); mix(&cfg->hist_hi, sizeof(double));
-        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT", "QO100NET_CPL_GENERAL", "QO100NET_CPL_NO_ROT", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS" };
+        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT", "QO100NET_CPL_GENERAL", "QO100NET_CPL_NO_ROT", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS", "QO100NET_USTRIP" };
         for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) { const char *v = getenv(envs[i]); mix(v ? v : "\1", v ? strlen(v) + 1 : 1); }
     }
     qo_plan *p = NULL;

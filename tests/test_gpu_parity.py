@@ -210,6 +210,47 @@ def test_cfg3_microstrip_yield_equals_oracle(Q, R, W, ctx):
     assert 0.5 < gg["n_pass"] / gg["n_total"] < 0.85
 
 
+def test_microstrip_board_kernel_equals_item_kernel_and_oracle(Q, R, W, ctx, monkeypatch):
+    """Microstrip yield jobs at <= 4 frequencies run one thread per board with the frequencies side by side (qo_mc_board_kernel);
+    QO100NET_USTRIP=item keeps one thread per (board, frequency) item (qo_mc_generic_kernel).  Same counters from both and from
+    the oracle, for 1, 2, 3 and 4 frequencies, with lumped elements mixed into the microstrip cascade and a histogram on a
+    "max" spec; five frequencies stay on the item kernel."""
+    w = W.cfg3()
+    n = 3000
+    extra = Q.Net.from_elements([(Q.SER_L, [0.4e-9, 0.05, 0.02e-12]), (Q.SHUNT_C, [0.15e-12, 0.1, 0.0])], 50.0, 50.0)
+    net = w.net.concat(extra)
+    tols = w.tols + [(len(w.net.elements), 0, 9, Q.TOL_REL, 0.1)]
+    grids = {1: [4.8e9], 2: [2.4e9, 7.2e9], 3: [2.4e9, 4.8e9, 7.2e9], 4: [1.2e9, 2.4e9, 4.8e9, 7.2e9]}
+    for nfreq, fl in grids.items():
+        f = np.array(fl)
+        nom = ctx.sweep(net, f)
+        db = 20 * np.log10(np.abs(nom[1]))
+        specs = [(Q.SPEC_S21_MAX_DB if v < -6 else Q.SPEC_S21_MIN_DB, fk * 0.99, fk * 1.01, float(v) + (0.4 if v < -6 else -0.08)) for fk, v in zip(fl, db)]
+        hist = dict(hist_bins=32, hist_spec=0, hist_lo=float(db[0]) - 3.0, hist_hi=float(db[0]) + 3.0)
+        monkeypatch.delenv("QO100NET_USTRIP", raising=False)
+        plan = Q.Plan(ctx, net, f, specs, seed=31, tols=tols, **hist)
+        assert plan.kernel_name == "qo_mc_board_kernel"
+        plan.launch(2 ** 32 + 11, n)
+        board = plan.read()
+        plan.close()
+        monkeypatch.setenv("QO100NET_USTRIP", "item")
+        plan = Q.Plan(ctx, net, f, specs, seed=31, tols=tols, **hist)
+        assert plan.kernel_name == "qo_mc_generic_kernel"
+        plan.launch(2 ** 32 + 11, n)
+        item = plan.read()
+        plan.close()
+        monkeypatch.delenv("QO100NET_USTRIP", raising=False)
+        _assert_counts_equal(item, board)
+        rs, rl = net.terminations
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(31, n, tols, sample_offset=2 ** 32 + 11, **hist), nthreads=8)
+        _assert_counts_equal(ref, board)
+        assert 0 < board["n_pass"] < n, (nfreq, board["n_pass"])
+    f5 = np.array([1.2e9, 2.4e9, 3.6e9, 4.8e9, 7.2e9])
+    plan = Q.Plan(ctx, net, f5, [(Q.SPEC_S21_MIN_DB, 2.3e9, 2.5e9, -1.0)], seed=31, tols=tols)
+    assert plan.kernel_name == "qo_mc_generic_kernel"
+    plan.close()
+
+
 def test_cfg3b_lumped_twin_yield_equals_oracle(Q, R, W, ctx, monkeypatch):
     """BASELINE config 3 as worded (lumped PA LPF with ESR/SRF parasitics, 3 points per sample): counters equal the oracle's on
     the spot-frequency kernel (one thread per sample, the default for <= 8 points) and on the three warp-per-sample kernels;

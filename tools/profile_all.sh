@@ -32,6 +32,7 @@ unset QO100NET_KERNEL
 cap fulls_tf 268435456 qo_fs_tf 2 python bench.py --steps 1 --warmup 3 --samples 200000 --north-star-samples 2000000
 cap nodal 4000000 qo_nodal_kernel 1 python tools/nodal_bench.py --samples 4000
 cap nodal_jit 100000000 qo_nodal_jit 1 python tools/nodal_bench.py --samples 100000
-cap generic_cfg3 1200000 generic 2 python tools/cfg3_run.py
+cap board_cfg3 6000000 qo_mc_board 2 python tools/cfg3_run.py
+cap generic_cfg3 6000000 generic 2 python tools/cfg3_run.py
 fi
 ls -la $OUT/*${TAG}*

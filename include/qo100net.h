@@ -320,6 +320,9 @@ int qo_device_perturb_factors(qo_ctx *ctx, uint64_t seed, uint64_t sample_offset
 
 /* the kernels' fast reciprocal (MUFU.RCP64H + one cubic step) applied to in[0..n), for accuracy tests */
 int qo_device_rcp(qo_ctx *ctx, const double *in, size_t n, double *out);
+/* the microstrip kernels' logarithm (qo_ustrip.cuh::ms_log: fdlibm reduction + degree-7 minimax, Newton reciprocal) applied to
+ * in[0..n), for accuracy tests */
+int qo_device_mslog(qo_ctx *ctx, const double *in, size_t n, double *out);
 
 /* measured FP64 FMA peak of device 0 of the ctx (dependency-free DFMA loop), TFLOP/s */
 int qo_measure_dfma_peak(qo_ctx *ctx, double *tflops);

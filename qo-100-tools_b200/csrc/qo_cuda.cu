@@ -1331,6 +1331,29 @@ extern "C" int qo_device_rcp(qo_ctx *ctx, const double *in, size_t n, double *ou
     return QO_OK;
 }
 
+__global__ void qo_mslog_kernel(const double *in, double *out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ms_log(in[i]);
+}
+extern "C" int qo_device_mslog(qo_ctx *ctx, const double *in, size_t n, double *out)
+{
+    qo_clear_error();
+    if (!ctx || !in || !out || !n) return QO_ERR_ARG;
+    DevCtx *dc = &ctx->d[0];
+    CU(cudaSetDevice(dc->device));
+    double *di = NULL, *dout = NULL;
+    CU(cudaMalloc(&di, n * sizeof(double)));
+    CU(cudaMalloc(&dout, n * sizeof(double)));
+    cudaMemcpyAsync(di, in, n * sizeof(double), cudaMemcpyHostToDevice, dc->stream);
+    qo_mslog_kernel<<<(unsigned)((n + 255) / 256), 256, 0, dc->stream>>>(di, dout, n);
+    cudaError_t e = cudaStreamSynchronize(dc->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(di); cudaFree(dout);
+    if (e != cudaSuccess) { qo_set_error("log kernel: %s", cudaGetErrorString(e)); return QO_ERR_CUDA; }
+    return QO_OK;
+}
+
 /* ---- FP64 FMA peak: dependency-free DFMA loop (roofline denominator) ------- */
 __global__ void __launch_bounds__(256) qo_dfma_peak_kernel(double *out, int iters, double x, double y)
 {

@@ -45,8 +45,42 @@ __device__ __forceinline__ void m2_shunt(M2 &m, cd y) { m.a = cadd(m.a, cmul(m.b
 /* x^y for x > 0 as exp(y log x): the models call it ~80 times per (sample, frequency) point and CUDA's pow() is ~2.5x the
  * cost of log + exp; every base here is a positive ratio of geometry / permittivity / frequency terms.  Measured effect on the
  * parity anchors: none at their resolution (S21 vs the reference dataset 3.4e-12, vs the oracle 6.9e-13, counters equal) */
+/* log(x) for the arguments these models produce (positive, normal: ratios of geometry / permittivity / frequency terms): the
+ * classic reduction x = 2^k m, m in [sqrt(1/2), sqrt(2)), s = (m - 1)/(m + 1), log m = 2 s + s^3 R(s^2) with the degree-7 minimax
+ * R of Sun's fdlibm (public algorithm; < 0.84 ulp against a long-double log over 2e7 arguments, tools/log_check.c) and a
+ * Newton reciprocal instead of the division.  35 instructions and no branch besides the guard; the library's log is ~105
+ * with its denormal / special-case paths -- and these kernels call it ~85 times per (board, frequency) point.  Anything else
+ * (zero, negative, denormal, inf, nan) goes to the library. */
+__device__ __noinline__ double ms_log_special(double x) { return log(x); }
+__device__ __forceinline__ double ms_log_fast(double x)
+{
+    int hx = __double2hiint(x);
+    if ((unsigned int)(hx - 0x00100000) >= 0x7fe00000u) return ms_log_special(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;               /* m >= sqrt(2): halve it */
+    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), __double2loint(x));
+    k += i >> 20;
+    const double f = m - 1.0, d = 2.0 + f;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    const double e = fma(-d, r, 1.0);
+    r = fma(r, fma(e, e, e), r);                           /* cubic step: 1/d to < 1 ulp */
+    double s = f * r;
+    s = fma(fma(-d, s, f), r, s);                          /* correctly rounded-ish quotient f / d */
+    const double dk = (double)k;
+    const double z = s * s, w = z * z;
+    const double t1 = w * fma(w, fma(w, 1.531383769920937332e-01, 2.222219843214978396e-01), 3.999999999940941908e-01);
+    const double t2 = z * fma(w, fma(w, fma(w, 1.479819860511658591e-01, 1.818357216161805012e-01), 2.857142874366239149e-01), 6.666666666666735130e-01);
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    return dk * 6.93147180369123816490e-01 - ((hfsq - (s * (hfsq + R) + dk * 1.90821492927058770002e-10)) - f);
+}
+#ifndef QO_MS_LIBLOG
+#define QO_MS_LIBLOG 0
+#endif
 __device__ __forceinline__ double ms_exp(double x) { return exp(x); }
-__device__ __forceinline__ double ms_log(double x) { return log(x); }
+__device__ __forceinline__ double ms_log(double x) { return QO_MS_LIBLOG ? log(x) : ms_log_fast(x); }
 #define MS_POW(x, y) ms_exp((y) * ms_log(x))
 
 struct MsSub { double er, h, t, tand, rho, D; };

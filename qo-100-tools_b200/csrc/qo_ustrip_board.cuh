@@ -31,7 +31,7 @@
  * the instruction cache (+15 % on config 3; sincos / cosh / sinh as calls, or the line section as a call, cost more than they
  * save).  The item-per-thread kernel keeps everything inline (calls cost it 10 %). */
 __device__ __noinline__ double mb_exp(double x) { return exp(x); }
-__device__ __noinline__ double mb_log(double x) { return log(x); }
+__device__ __noinline__ double mb_log(double x) { return ms_log(x); }
 #define MB_POW(x, y) mb_exp((y) * mb_log(x))
 
 /* Hammerstad-Jensen quasi-static line (ms_quasi with exp / log as calls) */

@@ -101,7 +101,7 @@ EXPORTS = [
     "qo_dat_create", "qo_dat_read", "qo_dat_write", "qo_dat_add_indep", "qo_dat_add_dep", "qo_dat_count", "qo_dat_info",
     "qo_dat_get", "qo_dat_from_sweep", "qo_dat_free",
     "qo_plan_destroy", "qo_philox4x32_10", "qo_variate", "qo_perturb_factor", "qo_device_perturb_factors",
-    "qo_device_rcp", "qo_measure_dfma_peak", "qo_strerror", "qo_last_error", "qo_version",
+    "qo_device_rcp", "qo_device_mslog", "qo_measure_dfma_peak", "qo_strerror", "qo_last_error", "qo_version",
 ]
 
 
@@ -195,6 +195,7 @@ def lib():
         "qo_device_perturb_factors": (C.c_int, [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_double, dp]),
         "qo_measure_dfma_peak": (C.c_int, [vp, dp]),
         "qo_device_rcp": (C.c_int, [vp, dp, C.c_size_t, dp]),
+        "qo_device_mslog": (C.c_int, [vp, dp, C.c_size_t, dp]),
         "qo_strerror": (C.c_char_p, [C.c_int]),
         "qo_last_error": (C.c_char_p, []),
         "qo_version": (C.c_char_p, []),
@@ -778,6 +779,12 @@ class Context:
     def device_perturb_factors(self, seed, sample_offset, n_samples, n_var, dist, tol):
         out = np.empty((n_samples, n_var))
         _check(lib().qo_device_perturb_factors(self._h, seed, sample_offset, n_samples, n_var, dist, tol, _dp(out)))
+        return out
+
+    def device_mslog(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        out = np.empty_like(x)
+        _check(lib().qo_device_mslog(self._h, _dp(x), x.size, _dp(out)))
         return out
 
     def device_rcp(self, x):

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 
 #include "qo_internal.h"
@@ -94,8 +95,9 @@ struct qo_plan {
     DevPlan d[8];
     std::vector<double> f;
     std::vector<unsigned char> maskv;
-    struct Upload { void *dst; std::vector<unsigned char> data; };
+    struct Upload { void *dst; std::vector<unsigned char> data; size_t at; };
     std::vector<Upload> uploads[8];                       /* what qo_plan_create copied to each device (qo_mc_run re-sends it on a cache hit) */
+    unsigned char *pinned[8];                             /* ... gathered in one page-locked buffer per device the first time they are re-sent */
 };
 
 /* ---- ctx ---------------------------------------------------------------- */
@@ -420,6 +422,7 @@ extern "C" void qo_plan_destroy(qo_plan *p)
         void *ptrs[] = { d->prog, d->w2, d->wi2, d->wsq2, d->tf_blob, d->fs_blob, d->m2, d->cpl_tab[0], d->cpl_tab[1], d->cpl_tab[2], d->cpl_tab[3],
                          d->fgrid, d->mask, d->counters, d->ticket, d->sblk, d->sdet };
         for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; i++) if (ptrs[i]) cudaFreeAsync(ptrs[i], st);
+        if (p->pinned[g]) cudaFreeHost(p->pinned[g]);
     }
     delete p;
 }
@@ -434,6 +437,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     qo_plan *p = new (std::nothrow) qo_plan();
     if (!p) return QO_ERR_NOMEM;
     p->ctx = ctx;
+    memset(p->pinned, 0, sizeof p->pinned);
     p->nf = nf;
     p->npairs = (nf + 1) / 2;
     p->precision = cfg && cfg->precision == 32 ? 32 : 64;
@@ -576,7 +580,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         DevPlan *d = &p->d[g];
         rc = QO_ERR_CUDA;
 #define H2D(DST_, SRC_, NB_) do { CUP(cudaMemcpyAsync((DST_), (SRC_), (NB_), cudaMemcpyHostToDevice, st)); if (g == 0) p->h2d_bytes += (NB_); \
-                                  qo_plan::Upload u_; u_.dst = (DST_); u_.data.assign((const unsigned char *)(SRC_), (const unsigned char *)(SRC_) + (NB_)); p->uploads[g].push_back(std::move(u_)); } while (0)
+                                  qo_plan::Upload u_; u_.dst = (DST_); u_.at = 0; u_.data.assign((const unsigned char *)(SRC_), (const unsigned char *)(SRC_) + (NB_)); p->uploads[g].push_back(std::move(u_)); } while (0)
 #define CUP(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { qo_set_error("%s -> %s", #call, cudaGetErrorString(e_)); qo_plan_destroy(p); return QO_ERR_CUDA; } } while (0)
         CUP(cudaSetDevice(ctx->d[g].device));
         cudaStream_t st = ctx->d[g].stream;
@@ -1126,7 +1130,13 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
     /* same job as the previous call on this ctx (everything but the sample range)?  Then its plan is still good. */
     unsigned long long key = 1469598103934665603ull;
     {
-        auto mix = [&key](const void *ptr, size_t n) { const unsigned char *b = (const unsigned char *)ptr; for (size_t i = 0; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; } };
+        /* eight bytes per step (the grid alone is 32 KB: byte-wise FNV cost 45 us per call), bytes for the tail */
+        auto mix = [&key](const void *ptr, size_t n) {
+            const unsigned char *b = (const unsigned char *)ptr;
+            size_t i = 0;
+            for (; i + 8 <= n; i += 8) { unsigned long long w; memcpy(&w, b + i, 8); key = (key ^ w) * 0x9E3779B97F4A7C15ull; key ^= key >> 29; }
+            for (; i < n; i++) { key ^= b[i]; key *= 1099511628211ull; }
+        };
         mix(net->e, (size_t)net->n * sizeof(qo_elem)); mix(&net->rs, sizeof net->rs); mix(&net->rl, sizeof net->rl);
         mix(f, (size_t)nf * sizeof(double));
         if (nspec > 0) mix(spec, (size_t)nspec * sizeof(qo_spec));
@@ -1138,13 +1148,26 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
     }
     qo_plan *p = NULL;
     int rc = QO_OK;
+    static const bool mc_timing = getenv("QO100NET_MC_TIMING") != NULL;
+    const auto tt0 = std::chrono::steady_clock::now();
     const bool cacheable = net->nblk == 0 && !getenv("QO100NET_NO_PLAN_CACHE");      /* measured blocks are not hashed: no reuse */
     if (cacheable && ctx->mc_cache && ctx->mc_cache_key == key && ctx->mc_cache->nf == nf) {
         p = ctx->mc_cache;
         for (int g = 0; g < ctx->ndev; g++) {                 /* the call's inputs travel host -> device every time */
             CU(cudaSetDevice(ctx->d[g].device));
-            for (size_t i = 0; i < p->uploads[g].size(); i++)
-                CU(cudaMemcpyAsync(p->uploads[g][i].dst, p->uploads[g][i].data.data(), p->uploads[g][i].data.size(), cudaMemcpyHostToDevice, ctx->d[g].stream));
+            if (!p->pinned[g]) {
+                /* copies from pageable memory are staged by the driver one by one (~12 us each, eight of them per call): gather
+                 * the plan's tables in one page-locked buffer, the re-sends are then truly asynchronous */
+                size_t tot = 0;
+                for (auto &u : p->uploads[g]) { u.at = tot; tot += (u.data.size() + 255) & ~(size_t)255; }
+                if (tot && cudaHostAlloc((void **)&p->pinned[g], tot, cudaHostAllocDefault) == cudaSuccess) {
+                    for (auto &u : p->uploads[g]) { memcpy(p->pinned[g] + u.at, u.data.data(), u.data.size()); }
+                } else { cudaGetLastError(); p->pinned[g] = NULL; }
+            }
+            for (size_t i = 0; i < p->uploads[g].size(); i++) {
+                const qo_plan::Upload &u = p->uploads[g][i];
+                CU(cudaMemcpyAsync(u.dst, p->pinned[g] ? (const void *)(p->pinned[g] + u.at) : (const void *)u.data.data(), u.data.size(), cudaMemcpyHostToDevice, ctx->d[g].stream));
+            }
         }
         rc = qo_plan_reset(p);
         if (rc) return rc;
@@ -1154,6 +1177,7 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         if (rc) return rc;
         if (cacheable) { ctx->mc_cache = p; ctx->mc_cache_key = key; }
     }
+    const auto tt1 = std::chrono::steady_clock::now();
     const int fs = cfg->mode == QO_MODE_FULL_S;
     const unsigned long long N = cfg->n_samples;
     qo_c64 *dbuf[8] = { 0 };
@@ -1169,7 +1193,13 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         rc = plan_launch_dev(p, g, cfg->sample_offset + a[g], n, p->d[g].counters, dbuf[g], n, 0);
         cudaEventRecord(ctx->d[g].ev1, ctx->d[g].stream);
     }
+    const auto tt2 = std::chrono::steady_clock::now();
     if (rc == QO_OK) rc = qo_plan_read(p, res);
+    if (mc_timing) {
+        const auto tt3 = std::chrono::steady_clock::now();
+        fprintf(stderr, "qo_mc_run: plan/tables %.1f us, launch %.1f us, wait+read %.1f us\n", std::chrono::duration<double, std::micro>(tt1 - tt0).count(),
+                std::chrono::duration<double, std::micro>(tt2 - tt1).count(), std::chrono::duration<double, std::micro>(tt3 - tt2).count());
+    }
     if (rc == QO_OK) {
         float worst = 0;
         for (int g = 0; g < ctx->ndev; g++) {

@@ -18,8 +18,9 @@ cap() {   # name, evals per launch, kernel regex, skip, command...
     python tools/ncu_summary.py $OUT/prof_${TAG}_${name}.ncu-rep $OUT/${TAG}_${name} $evals > /dev/null 2>&1 || echo "summary of $name failed"
     rm -f $OUT/prof_${TAG}_${name}.ncu-rep
 }
-cap ts_cfg2 819200000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000
-cap ts_cfg5 819200000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000 --workload cfg5
+# the headline kernel at the bench's own launch size (1e6 samples: 17.6 waves; at 2e5 the last partial wave costs 10 %)
+cap ts_cfg2 4096000000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 1000000
+cap ts_cfg5 4096000000 qo_mc_ts 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 1000000 --workload cfg5
 if [ "${2:-}" = "all" ]; then
 export QO100NET_KERNEL=tf
 cap tf_cfg2 819200000 qo_mc_tf 3 python bench.py --steps 2 --warmup 3 --no-extras --samples 200000

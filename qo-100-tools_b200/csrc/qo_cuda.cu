@@ -57,7 +57,7 @@ struct DevPlan {
     void *wsq2;                /* double2 [npairs]: w^2, ladder kernel only */
     /* transfer-function kernel: one blob, tables padded to whole iterations of tf_pp*32 pairs */
     void *tf_blob;
-    double2 *tf_yt, *tf_xt, *tf_wt, *tf_ctab[4];
+    double2 *tf_yt, *tf_xt, *tf_wt, *tf_ctab[4], *tf_fu2[4];
     uint4 *tf_mb;
     uchar2 *tf_itm;
     void *fs_blob;             /* FULL_S flavour of the transfer-function kernel: y and x tables, padded */
@@ -620,7 +620,8 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 const size_t npad = ((size_t)p->tf_niter + 1) * ppi, npt = 2 * npad;
                 /* a measured two-port in front: its row vector [1 Rs] M(f) per grid point rides in the four coupler-table slots */
                 const bool front_blk = p->tfp.cpl_op >= 0 && p->tfp.front == 2;
-                const int ntab = 3 + (p->cpl_fast || front_blk ? 4 : 0);
+                const bool front_s11 = front_blk && p->tfp.s11;         /* + its second row vector [1 -Rs] M for |S11| specs */
+                const int ntab = 3 + (p->cpl_fast || front_blk ? 4 : 0) + (front_s11 ? 4 : 0);
                 const size_t itm_bytes = ((size_t)p->tf_niter * sizeof(uchar2) + 15) & ~(size_t)15;
                 const size_t bytes = (size_t)ntab * npt * sizeof(double) + 2 * npt * sizeof(unsigned int) + itm_bytes;
                 std::vector<unsigned char> blob(bytes);
@@ -637,6 +638,10 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                         const double2 *mm = &sblk[((size_t)blk * (size_t)(2 * np) + kc) * 4];
                         tab[3 * npt + k] = mm[0].x + p->hp.rs * mm[2].x; tab[4 * npt + k] = mm[0].y + p->hp.rs * mm[2].y;
                         tab[5 * npt + k] = mm[1].x + p->hp.rs * mm[3].x; tab[6 * npt + k] = mm[1].y + p->hp.rs * mm[3].y;
+                        if (front_s11) {
+                            tab[7 * npt + k] = mm[0].x - p->hp.rs * mm[2].x; tab[8 * npt + k] = mm[0].y - p->hp.rs * mm[2].y;
+                            tab[9 * npt + k] = mm[1].x - p->hp.rs * mm[3].x; tab[10 * npt + k] = mm[1].y - p->hp.rs * mm[3].y;
+                        }
                     }
                     unsigned int lo = 0, hi = 0;
                     const unsigned char mk = k < (size_t)nf ? p->maskv[k] : 0;
@@ -660,6 +665,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
                 double *dt = (double *)d->tf_blob;
                 d->tf_yt = (double2 *)dt; d->tf_xt = (double2 *)(dt + npt); d->tf_wt = (double2 *)(dt + 2 * npt);
                 for (int t = 0; t < 4; t++) d->tf_ctab[t] = (p->cpl_fast || front_blk) ? (double2 *)(dt + (3 + t) * npt) : NULL;
+                for (int t = 0; t < 4; t++) d->tf_fu2[t] = front_s11 ? (double2 *)(dt + (7 + t) * npt) : NULL;
                 d->tf_mb = (uint4 *)(dt + (size_t)ntab * npt);
                 d->tf_itm = (uchar2 *)((unsigned int *)d->tf_mb + 2 * npt);
             }
@@ -845,10 +851,11 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.cpl_fast = p->cpl_fast; P.cpl_same = p->cpl_same; P.cpl_op = p->tfp.cpl_op;
     /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
     P.front = p->tfp.cpl_op >= 0 ? p->tfp.front : 0;
-    P.cpl_matched = p->tfp.cpl_op >= 0 && !P.front && hp->tvar[p->tfp.cpl_op][5] < 0 && hp->nom[p->tfp.cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
+    for (int t = 0; t < 4; t++) P.fu2[t] = d->tf_fu2[t];
+    P.cpl_matched = p->tfp.cpl_op >= 0 && !P.front && !p->tfp.s11 && hp->tvar[p->tfp.cpl_op][5] < 0 && hp->nom[p->tfp.cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
     /* uniformly spaced grid (config 5: linear 70 MHz .. 4 GHz): the coupler's mode angles advance by a constant per iteration */
     P.cpl_lin = 0;
-    if (p->tfp.cpl_op >= 0 && !P.front && p->nf >= 3 && !getenv("QO100NET_CPL_NO_ROT")) {
+    if (p->tfp.cpl_op >= 0 && !P.front && !p->tfp.s11 && p->nf >= 3 && !getenv("QO100NET_CPL_NO_ROT")) {
         const double d0 = p->f[1] - p->f[0];
         int lin = d0 > 0.0;
         for (int k = 2; k < p->nf && lin; k++) if (fabs((p->f[k] - p->f[k - 1]) - d0) > 1e-9 * fabs(d0)) lin = 0;

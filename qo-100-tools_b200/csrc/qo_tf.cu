@@ -24,6 +24,8 @@
 #define QO_TF_CPL_MINB 4
 
 typedef void (*tf_fn)(const TfParams);
+/* qo_tf_front.cu: a line / measured two-port in front, and |S11| specs behind any front block (their own translation unit: build time) */
+tf_fn qo_tf_pick_front(int front, int s11, int pp, int den, int nspec, int *tpb, int *minb);
 
 /* pairs per thread per iteration: short grids take one pair per thread (iterations of 64 points) so that the padding to whole
  * iterations does not dominate -- 8 points per thread are ~25 % cheaper per point but pad to 512 */
@@ -85,8 +87,7 @@ extern "C" int qo_tf_launch(const TfPlan *tp, int pp, int variant, int sm_count,
         else if (tp->nn == 2 && pp == 1) fn = tf_pick<2, 0, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == 1) fn = tf_pick_gd<1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->nn == 4 && tp->s11 && pp == 1) fn = tf_pick<4, 0, true, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
-        else if (tp->nn == 4 && !tp->s11 && tp->front && pp == 1) fn = tf_pick<4, 4, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
-        else if (tp->nn == 4 && !tp->s11 && tp->front && pp == QO_TF_CPL_PP) { fn = tf_pick<4, 4, false, QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
+        else if (tp->nn == 4 && tp->cpl_op >= 0 && (tp->front || tp->s11)) fn = qo_tf_pick_front(tp->front, tp->s11, pp, tp->den, P->nspec, &tpb, &minb);
         else if (tp->nn == 4 && !tp->s11 && pp == 1) fn = rot ? (P->cpl_same ? tf_pick<4, 3, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec) : tf_pick<4, 2, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec))
                      : tf_pick<4, 1, false, 1, QO_TF_TPB, QO_TF_MINB>(tp->den, P->nspec);
         else if (tp->gd && pp == QO_TF_CPL_PP) { fn = tf_pick_gd<QO_TF_CPL_PP, QO_TF_CPL_TPB, QO_TF_CPL_MINB>(tp->den, P->nspec); tpb = QO_TF_CPL_TPB; minb = QO_TF_CPL_MINB; }
@@ -291,7 +292,6 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
     if (deg > 2 * QO_TF_MAXK - 1) QO_TF_NO("polynomial degree");
     const int Kfull = deg / 2 + 1;
     const bool cpl = out->cpl_op >= 0, s11 = hp->need_s11 != 0;
-    if (cpl && s11) QO_TF_NO("|S11| specs behind a front block");
     if (gd && (cpl || s11)) QO_TF_NO("group-delay specs mixed with a front block or |S11| specs");
     if (!need_s21) has_d = 0;                                 /* S11 = (P - Rs Q) / (P + Rs Q): the branch denominators cancel */
     const bool apart = cpl || s11;                            /* P and Q kept apart */
@@ -434,7 +434,7 @@ static int tf_plan_check_uncached(const DevProg *hp, int mode_reduce_only, int p
                 if (cpl) {
                     /* P/D and Q/D as complex numbers (the coupler's row vector mixes them), plus the kernel's |D|^2 against the true one */
                     const cplx Dc = tf_horner_host(c.dd, Kfull, x);
-                    rel = 2.0 * (std::abs(P_ / Dc - a) + zn * std::abs(Q_ / Dc - b)) / (std::abs(a) + zn * std::abs(b)) + fabs(d2 / dref - 1.0);
+                    rel = 2.0 * (std::abs(P_ / Dc - a) + zn * std::abs(Q_ / Dc - b)) / (std::abs(a) + zn * std::abs(b)) + (need_s21 ? fabs(d2 / dref - 1.0) : 0.0);   /* |S11|-only jobs: D cancels in the ratio */
                 } else {
                     const double got = std::norm(P_ + hp->rs * Q_) / d2, ref = std::norm(a + hp->rs * b);
                     rel = need_s21 ? fabs(got - ref) / ref : 0.0;

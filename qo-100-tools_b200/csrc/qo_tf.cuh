@@ -49,6 +49,7 @@ struct TfParams {
     const uint4 *mb;                         /* per point two words (a pair per entry): byte s = 0xFF when the point lies in spec s's band (padding: 0) */
     const uchar2 *itm;                       /* per iteration of PP*32 pairs: (OR, AND) of the spec bit masks of its points */
     const double2 *cse, *cce, *cso, *cco;    /* coupler: sin/cos of the nominal mode angles (cpl_fast), padded */
+    const double2 *fu2[4];                   /* measured two-port in front, |S11| jobs: the second row vector [1 -Rs] M per grid point */
     unsigned long long *counters, *ticket;
     unsigned long long sample_offset, nsamples, seed;
     double rs, rl, k21, hist_lo, hist_hi, wref, zn, zni;
@@ -306,7 +307,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
     constexpr int WARPS = TPB / 32;
     static_assert(NN == 2 || NN == 4, "two or four numerator chains");
     static_assert(!(CPL || S11) || NN == 4, "P and Q stay separate behind a coupler block and for |S11|");
-    static_assert(!(CPL && S11), "|S11| specs behind a coupler block run on the chain kernel");
+    static_assert(!(ROT && S11), "|S11| specs behind a coupler block take the general (two-row) form of the block");
     static_assert(!GD || (NN == 4 && !CPL && !S11 && (DEN == QO_TF_DEN_NONE || DEN == QO_TF_DEN_DD)), "group delay: Num, Num' and D, D'");
     static_assert(GD || DEN != QO_TF_DEN_DD, "D' is only evaluated for group-delay jobs");
     __shared__ __align__(16) double s_num[WARPS][(QO_TF_MAXK + 2) * NN];   /* two guard rows below row 0 (prefetch runs two steps ahead) */     /* row k: coefficients of sn^(2k), sn^(2k+1) of every numerator polynomial */
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     n2[p] = fma(-y[p], t, r[0][p] * r[0][p]);
                     gA[p] = fma(-y[p], r[3][p] * r[1][p], r[2][p] * r[0][p]);
                 }
-            } else if (S11) {
+            } else if (S11 && !CPL) {
                 const double zq = P.rs * P.zni;
                 QO_PTS {
                     const double ar = fma(zq, r[2][p], r[0][p]), ai = fma(zq, r[3][p], r[1][p]);
@@ -501,6 +502,28 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     const double ni = fma(uar[p], pi_, fma(uai[p], r[0][p], fma(ubr[p], qi, ubi[p] * qr)));
                     n2[p] = fma(nr, nr, ni * ni);
                 }
+                if (S11) {
+                    /* |S11|^2 = |[1 -Rs] M [P; Q]|^2 / |[1 Rs] M [P; Q]|^2: the second row vector of the block */
+                    double var[PTS], vai[PTS], vbr[PTS], vbi[PTS];
+                    if (P.front == 1) {
+                        /* line: (c - j (Rs/Z0) s, -Rs c + j Z0 s) -- the first row with Rs -> -Rs */
+                        QO_PTS { var[p] = uar[p]; vai[p] = -uai[p]; vbr[p] = -ubr[p]; vbi[p] = ubi[p]; }
+                    } else {
+#pragma unroll
+                        for (int qq = 0; qq < PP; qq++) {
+                            const int j = j0 + 32 * qq;
+                            const double2 a = P.fu2[0][j], b = P.fu2[1][j], c = P.fu2[2][j], d = P.fu2[3][j];
+                            var[2 * qq] = a.x; var[2 * qq + 1] = a.y; vai[2 * qq] = b.x; vai[2 * qq + 1] = b.y;
+                            vbr[2 * qq] = c.x; vbr[2 * qq + 1] = c.y; vbi[2 * qq] = d.x; vbi[2 * qq + 1] = d.y;
+                        }
+                    }
+                    QO_PTS {
+                        const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                        const double nr = fma(var[p], r[0][p], fma(-vai[p], pi_, fma(vbr[p], qr, -vbi[p] * qi)));
+                        const double ni = fma(var[p], pi_, fma(vai[p], r[0][p], fma(vbr[p], qi, vbi[p] * qr)));
+                        m2[p] = fma(nr, nr, ni * ni);
+                    }
+                }
             } else {
                 double w[PTS], x[PTS], tse[PTS], tce[PTS], tso[PTS], tco[PTS];
                 QO_PTS { tse[p] = 0.0; tce[p] = 1.0; tso[p] = 0.0; tco[p] = 1.0; }
@@ -526,11 +549,20 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                     else tf_cpl_matched<PTS, false>(cpls, w, tse, tce, tso, tco, uar, uai, ubr, ubi, kap);
                     zq = P.rs * P.zni;
                 } else {
-                    LadRow<double, PTS, 1> u;
-                    if (P.cpl_fast) lad_cpl_first<double, PTS, 1, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
-                    else lad_cpl_first<double, PTS, 1, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
+                    constexpr int NR = S11 ? 2 : 1;       /* |S11| specs: the row vector [1 -Rs] k M rides along (the common factor k cancels in the ratio) */
+                    LadRow<double, PTS, NR> u;
+                    if (P.cpl_fast) lad_cpl_first<double, PTS, NR, true, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
+                    else lad_cpl_first<double, PTS, NR, false, true>(cpls, w, tse, tce, tso, tco, rs, u, kap);
                     QO_PTS { uar[p] = u.ar[0][p]; uai[p] = u.ai[0][p]; ubr[p] = u.br[0][p]; ubi[p] = u.bi[0][p]; }
                     zq = P.zni;
+                    if (S11) {
+                        QO_PTS {
+                            const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;
+                            const double nr = fma(u.ar[NR - 1][p], r[0][p], fma(-u.ai[NR - 1][p], pi_, fma(u.br[NR - 1][p], qr, -u.bi[NR - 1][p] * qi)));
+                            const double ni = fma(u.ar[NR - 1][p], pi_, fma(u.ai[NR - 1][p], r[0][p], fma(u.br[NR - 1][p], qi, u.bi[NR - 1][p] * qr)));
+                            m2[p] = fma(nr, nr, ni * ni);
+                        }
+                    }
                 }
                 QO_PTS {
                     const double pi_ = r[1][p] * x[p], qr = r[2][p] * zq, qi = (r[3][p] * x[p]) * zq;

@@ -76,7 +76,7 @@ def build(verbose=False):
     """Compile libqo100net.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
     env = dict(os.environ)
     env.pop("CC", None)
-    r = subprocess.run(["make", "-j", "4", "-C", CSRC], capture_output=True, text=True, env=env)
+    r = subprocess.run(["make", "-j", "8", "-C", CSRC], capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError("building libqo100net.so failed:\n" + r.stdout + r.stderr)
     if verbose:

@@ -312,8 +312,8 @@ def test_cfg3b_lumped_twin_yield_equals_oracle(Q, R, W, ctx, monkeypatch):
 
 def test_s11_spec_and_histogram(Q, R, W, ctx, monkeypatch):
     """|S11| specs against the oracle on every kernel that serves them: the transfer-function kernel (S11 =
-    (P - Rs Q) / (P + Rs Q); plain ladders), the chain kernel's second row vector (forced, and the default behind
-    the coupler block) and the interpreter's 2x2 chain; histogram on the |S11| spec and on the |S21| specs."""
+    (P - Rs Q) / (P + Rs Q); behind the coupler block with the block's second row vector), the chain kernel's second row
+    vector (forced) and the interpreter's 2x2 chain; histogram on the |S11| spec and on the |S21| specs."""
     for w in (W.cfg2(), W.cfg5()):
         fc = 10e6 if w.name.startswith("cfg2") else 3e9
         w.specs = [(Q.SPEC_S11_MAX_DB, 0.0, 0.8 * fc, -8.0), (Q.SPEC_S21_MAX_DB, 1.3 * fc, 1e99, -49.0), (Q.SPEC_S21_MIN_DB, 0, 0.5 * fc, -1.3)]
@@ -321,7 +321,7 @@ def test_s11_spec_and_histogram(Q, R, W, ctx, monkeypatch):
             w.hist = dict(hist_bins=64, hist_spec=hs, hist_lo=lo, hist_hi=hi)
             monkeypatch.delenv("QO100NET_KERNEL", raising=False)
             plan = Q.Plan(ctx, w.net, w.f, w.specs, seed=w.seed, tols=w.tols, **w.hist)
-            assert plan.kernel_name == ("qo_mc_tf_kernel" if w.name.startswith("cfg2") else "qo_mc_ladder_kernel")
+            assert plan.kernel_name == "qo_mc_tf_kernel"
             plan.close()
             og, gg = _mc_both(Q, R, ctx, w, 800)
             _assert_counts_equal(og, gg)
@@ -518,7 +518,7 @@ def test_ladder_kernel_selection_and_edge_shapes(Q, R, W, ctx, monkeypatch):
     p = mk([(Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()      # chain kernel: second row vector
     monkeypatch.delenv("QO100NET_KERNEL", raising=False)
     p = Q.Plan(ctx, W.cfg5().net, W.cfg5().f, [(Q.SPEC_S11_MAX_DB, 2.3e9, 2.5e9, -10.0)], seed=1, tols=W.cfg5().tols)
-    assert p.kernel_name == "qo_mc_ladder_kernel"; p.close()                                                      # |S11| behind the coupler block
+    assert p.kernel_name == "qo_mc_tf_kernel"; p.close()                                                          # |S11| behind the coupler block: its second row vector
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6)]); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()             # group delay: derivative polynomials
     p = mk([(Q.SPEC_GD_MAX, 0.0, 8e6, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 8e6, -8.0)]); assert p.kernel_name == "qo_mc_lumped_kernel"; p.close()   # GD + |S11|: interpreter
     p = mk(w.specs * 3); assert p.kernel_name == "qo_mc_tf_kernel"; p.close()                                     # 6 specs: the 8-slot instantiation
@@ -733,6 +733,57 @@ def test_tf_kernel_front_block_line_and_measured_two_port(Q, R, W, ctx, golden_s
         ref2 = R.mc_run(to_ref(R, net2), 50, 50, f2, specs2, R.mc_cfg(4, n, tols2, sample_offset=17), nthreads=8)
         _assert_counts_equal(ref2, got2)
         assert 0 < got2["n_pass"] < n
+    R.sblock_clear()
+
+
+def test_tf_kernel_s11_specs_behind_a_front_block(Q, R, W, ctx, golden_s2p, monkeypatch):
+    """|S11| (and mixed |S11| + |S21|) specs behind a coupled-line section, a transmission line or a measured two-port: the
+    transfer-function kernel carries the block's second row vector [1 -Rs] M as well.  Counters equal the oracle's and the chain
+    kernels' (QO100NET_KERNEL=ladder -> straight-line kernel for the coupler case, interpreter otherwise)."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    n = 2500
+    fc = 10e6
+    fd, sd, z0 = golden_s2p["11SQ39N_f"], golden_s2p["11SQ39N_s"], float(golden_s2p["11SQ39N_z0"])
+    blk = Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    R.sblock_clear()
+    R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    cases = []
+    net, f, tols = _ladder_workload(Q, W, 7, True, True, nf=600)                      # coupler (theta_e != theta_o) + ladder
+    cases.append(("coupler", net, f, tols, fc))
+    lad, f, ltol = _ladder_workload(Q, W, 7, True, False, nf=600)
+    line = Q.Net.from_elements([(Q.TLINE, [60.0, 50.0, fc])], 50.0, 50.0)
+    cases.append(("line", line.concat(lad), f, [(0, 0, 0, Q.TOL_REL, 0.05), (0, 1, 1, Q.TOL_REL, 0.03)] + [(e + 1, p_, v + 2, m, t) for (e, p_, v, m, t) in ltol], fc))
+    lad2, f2, ltol2 = _ladder_workload(Q, W, 5, False, False, fc=400e6, nf=513)
+    cases.append(("block", blk.as_net(True, 50.0, 50.0).concat(lad2), f2, [(e + 1, p_, v, m, t) for (e, p_, v, m, t) in ltol2], 400e6))
+    for name, net, f, tols, fcc in cases:
+        nom = ctx.sweep(net, f)
+        r11 = 20 * np.log10(np.abs(nom[0]))
+        db = 20 * np.log10(np.abs(nom[1]))
+        pb = (f >= 0.3 * fcc) & (f <= 0.8 * fcc)
+        # thresholds at the median / upper quartile of the worst in-band |S11| over a few hundred samples: never a degenerate yield
+        fs = ctx.mc_run(net, f, [], 12, 300, tols, mode=Q.MODE_FULL_S)["s"]
+        worst11 = (20 * np.log10(np.abs(fs[0][:, pb]))).max(axis=1)
+        worst21 = (20 * np.log10(np.abs(fs[1][:, f <= 0.8 * fcc]))).min(axis=1)
+        for specs in ([(Q.SPEC_S11_MAX_DB, 0.3 * fcc, 0.8 * fcc, float(np.median(worst11)))],
+                      [(Q.SPEC_S11_MAX_DB, 0.3 * fcc, 0.8 * fcc, float(np.quantile(worst11, 0.75))), (Q.SPEC_S21_MIN_DB, 0.0, 0.8 * fcc, float(np.quantile(worst21, 0.25)))]):
+            hist = dict(hist_bins=24, hist_spec=0, hist_lo=float(r11[pb].max()) - 6.0, hist_hi=float(r11[pb].max()) + 6.0)
+            plan = Q.Plan(ctx, net, f, specs, seed=12, tols=tols, **hist)
+            assert plan.kernel_name == "qo_mc_tf_kernel", (name, plan.tf_info)
+            plan.launch(40, n)
+            got = plan.read()
+            plan.close()
+            monkeypatch.setenv("QO100NET_KERNEL", "ladder")
+            plan = Q.Plan(ctx, net, f, specs, seed=12, tols=tols, **hist)
+            assert plan.kernel_name in ("qo_mc_ladder_kernel", "qo_mc_lumped_kernel")
+            plan.launch(40, n)
+            chain = plan.read()
+            plan.close()
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+            _assert_counts_equal(chain, got)
+            rs, rl = net.terminations
+            ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(12, n, tols, sample_offset=40, **hist), nthreads=8)
+            _assert_counts_equal(ref, got)
+            assert 0 < got["n_pass"] < n, (name, got["n_pass"])
     R.sblock_clear()
 
 

@@ -78,6 +78,10 @@ struct qo_plan {
     DevProg hp;                /* host copy of the program */
     int nf, npairs, ncnt, precision, mode, generic;
     int board;                                            /* microstrip yield job at <= 4 frequencies: thread-per-board kernel */
+    /* launch-time decisions of the transfer-function kernels, taken once at plan creation (environment overrides included) */
+    int tf_cpl_matched, tf_cpl_lin, ts_ok, ts_runs_ok, ts_nruns, ts_npt;
+    double tf_cpl_dw1;                                    /* angular-frequency step of one grid point on a uniformly spaced grid */
+    struct { int ngroups; unsigned int any, all; } ts_runs[QO_TS_MAXRUN];
     int ladder, lad_n, lad_first, lad_cpl, lad_variant;   /* straight-line ladder kernel (qo_ladder.cuh) */
     int cpl_fast, cpl_same;                               /* coupler block: small-angle table path, equal mode angles */
     int spot, spot_el0, spot_nel;                         /* spot-frequency kernel (qo_spot.cuh): <= 8 points per sample */
@@ -99,6 +103,8 @@ struct qo_plan {
     std::vector<Upload> uploads[8];                       /* what qo_plan_create copied to each device (qo_mc_run re-sends it on a cache hit) */
     unsigned char *pinned[8];                             /* ... gathered in one page-locked buffer per device the first time they are re-sent */
 };
+
+static void tf_launch_setup(qo_plan *p);
 
 /* ---- ctx ---------------------------------------------------------------- */
 static int devctx_init(DevCtx *d, int device)
@@ -689,6 +695,7 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
         CUP(cudaMemsetAsync(d->counters, 0, (size_t)p->ncnt * sizeof(unsigned long long), st));
         CUP(cudaStreamSynchronize(st));   /* the host staging vectors die at return */
     }
+    if (p->tf) tf_launch_setup(p);
     *out = p;
     return QO_OK;
 }
@@ -838,6 +845,40 @@ static int launch_ladder(qo_plan *p, int g, unsigned long long off, unsigned lon
     return QO_OK;
 }
 
+/* what launch_tf needs beyond the tables, decided once per plan: the coupler block's form (matched source, uniformly spaced
+ * grid), whether large launches may run thread-per-sample, and that kernel's run table (runs of point groups that see the same
+ * spec bits; a group that straddles a band edge stands alone) */
+static void tf_launch_setup(qo_plan *p)
+{
+    const DevProg *hp = &p->hp;
+    const int cop = p->tfp.cpl_op;
+    const int front = cop >= 0 ? p->tfp.front : 0;
+    /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
+    p->tf_cpl_matched = cop >= 0 && !front && !p->tfp.s11 && hp->tvar[cop][5] < 0 && hp->nom[cop][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
+    /* uniformly spaced grid (config 5: linear 70 MHz .. 4 GHz): the coupler's mode angles advance by a constant per iteration */
+    p->tf_cpl_lin = 0; p->tf_cpl_dw1 = 0.0;
+    if (cop >= 0 && !front && !p->tfp.s11 && p->nf >= 3 && !getenv("QO100NET_CPL_NO_ROT")) {
+        const double d0 = p->f[1] - p->f[0];
+        int lin = d0 > 0.0;
+        for (int k = 2; k < p->nf && lin; k++) if (fabs((p->f[k] - p->f[k - 1]) - d0) > 1e-9 * fabs(d0)) lin = 0;
+        if (lin) { p->tf_cpl_lin = 1; p->tf_cpl_dw1 = 6.283185307179586476925286766559 * ((p->f[p->nf - 1] - p->f[0]) / (double)(p->nf - 1)); }
+    }
+    const bool rot_same = p->tf_cpl_lin && p->tf_cpl_matched && p->cpl_same && hp->cplms_elem < 0;
+    p->ts_ok = qo_ts_eligible(&p->tfp, hp->nspec, rot_same);
+    p->ts_nruns = 0; p->ts_runs_ok = 1; p->ts_npt = 0;
+    if (p->ts_ok) {
+        const int gpt = qo_ts_group_points(&p->tfp);
+        p->ts_npt = (p->nf + gpt - 1) / gpt * gpt;
+        for (int gi = 0; gi < p->ts_npt / gpt; gi++) {
+            unsigned int any = 0, all = 0xFF;
+            for (int k = gi * gpt; k < (gi + 1) * gpt; k++) { const unsigned int mk = k < p->nf ? p->maskv[k] : 0; any |= mk; all &= mk; }
+            if (p->ts_nruns > 0 && any == all && p->ts_runs[p->ts_nruns - 1].any == any && p->ts_runs[p->ts_nruns - 1].all == all) { p->ts_runs[p->ts_nruns - 1].ngroups++; continue; }
+            if (p->ts_nruns == QO_TS_MAXRUN) { p->ts_runs_ok = 0; break; }       /* more band edges than the run table holds: warp-per-sample */
+            p->ts_runs[p->ts_nruns].ngroups = 1; p->ts_runs[p->ts_nruns].any = any; p->ts_runs[p->ts_nruns].all = all; p->ts_nruns++;
+        }
+    }
+}
+
 static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long long n, unsigned long long *cnt, const double *cplms)
 {
     DevCtx *dc = &p->ctx->d[g];
@@ -852,15 +893,8 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     /* source resistance == the coupler's (unperturbed) reference impedance: the block's row vector collapses (qo_tf.cuh::tf_cpl_matched) */
     P.front = p->tfp.cpl_op >= 0 ? p->tfp.front : 0;
     for (int t = 0; t < 4; t++) P.fu2[t] = d->tf_fu2[t];
-    P.cpl_matched = p->tfp.cpl_op >= 0 && !P.front && !p->tfp.s11 && hp->tvar[p->tfp.cpl_op][5] < 0 && hp->nom[p->tfp.cpl_op][5] == hp->rs && !getenv("QO100NET_CPL_GENERAL");
-    /* uniformly spaced grid (config 5: linear 70 MHz .. 4 GHz): the coupler's mode angles advance by a constant per iteration */
-    P.cpl_lin = 0;
-    if (p->tfp.cpl_op >= 0 && !P.front && !p->tfp.s11 && p->nf >= 3 && !getenv("QO100NET_CPL_NO_ROT")) {
-        const double d0 = p->f[1] - p->f[0];
-        int lin = d0 > 0.0;
-        for (int k = 2; k < p->nf && lin; k++) if (fabs((p->f[k] - p->f[k - 1]) - d0) > 1e-9 * fabs(d0)) lin = 0;
-        if (lin) { P.cpl_lin = 1; P.cpl_dw = 6.283185307179586476925286766559 * ((p->f[p->nf - 1] - p->f[0]) / (double)(p->nf - 1)) * (double)(64 * p->tf_pp); }
-    }
+    P.cpl_matched = p->tf_cpl_matched;
+    P.cpl_lin = p->tf_cpl_lin; P.cpl_dw = p->tf_cpl_dw1 * (double)(64 * p->tf_pp);
     P.cplms = cplms;
     P.counters = cnt; P.ticket = d->ticket;
     CU(cudaMemsetAsync(d->ticket, 0, QO_TICKET_BYTES, dc->stream));
@@ -878,8 +912,7 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
     P.hist_spec = hp->hist_bins > 0 ? hp->hist_spec : -1;
     /* the bulk of a large launch runs thread-per-sample (qo_ts.cuh): whole rounds of one sample per resident thread, dealt
      * statically; what is left over (less than one wave) stays on the warp-per-sample kernel below */
-    const bool rot_same = P.cpl_lin && P.cpl_matched && P.cpl_same && !cplms;
-    if (qo_ts_eligible(&p->tfp, hp->nspec, rot_same)) {
+    if (p->ts_ok && p->ts_runs_ok) {
         /* worth it from a few batches per resident warp on (one wave = every resident thread one sample) */
         const unsigned long long wave = (unsigned long long)qo_ts_wave_threads(&p->tfp, dc->sm_count);
         const unsigned long long nb = wave && n >= 2 * wave ? n / 32ull : 0;
@@ -889,23 +922,14 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
             Q.t = P;
             Q.t.nsamples = nb * 32ull;
             Q.y1 = (const double *)d->tf_yt; Q.x1 = (const double *)d->tf_xt; Q.mw = (const uint2 *)d->tf_mb;
-            const int gpt = qo_ts_group_points(&p->tfp);
-            Q.npt = (p->nf + gpt - 1) / gpt * gpt;
-            /* runs of groups with the same (OR, AND) of their points' spec bits; a group that straddles a band edge stands alone */
-            bool runs_ok = true;
-            for (int gi = 0; gi < Q.npt / gpt; gi++) {
-                unsigned int any = 0, all = 0xFF;
-                for (int k = gi * gpt; k < (gi + 1) * gpt; k++) { const unsigned int mk = k < p->nf ? p->maskv[k] : 0; any |= mk; all &= mk; }
-                if (Q.nruns > 0 && any == all && Q.runs[Q.nruns - 1].any == any && Q.runs[Q.nruns - 1].all == all) { Q.runs[Q.nruns - 1].ngroups++; continue; }
-                if (Q.nruns == QO_TS_MAXRUN) { runs_ok = false; break; }
-                Q.runs[Q.nruns].ngroups = 1; Q.runs[Q.nruns].any = any; Q.runs[Q.nruns].all = all; Q.nruns++;
-            }
+            Q.npt = p->ts_npt;
+            Q.nruns = p->ts_nruns;
+            for (int r = 0; r < p->ts_nruns; r++) { Q.runs[r].ngroups = p->ts_runs[r].ngroups; Q.runs[r].any = p->ts_runs[r].any; Q.runs[r].all = p->ts_runs[r].all; }
             Q.nbatches = nb;
             Q.ticket = d->ticket + 1;
             Q.w0 = 6.283185307179586476925286766559 * p->f[0];
             Q.dw = p->nf > 1 ? 6.283185307179586476925286766559 * ((p->f[p->nf - 1] - p->f[0]) / (double)(p->nf - 1)) : 0.0;
-            int rts = runs_ok ? qo_ts_launch(&p->tfp, dc->sm_count, &Q, dc->stream) : 0;
-            if (!runs_ok) goto warp_per_sample;             /* a mask pattern with more band edges than the run table holds */
+            int rts = qo_ts_launch(&p->tfp, dc->sm_count, &Q, dc->stream);
             if (rts) { qo_set_error("thread-per-sample kernel launch: %s", cudaGetErrorString((cudaError_t)rts)); return QO_ERR_CUDA; }
             p->kernel_name = "qo_mc_ts_kernel";
             p->launches++;
@@ -914,7 +938,6 @@ static int launch_tf(qo_plan *p, int g, unsigned long long off, unsigned long lo
             P.sample_offset = off; P.nsamples = n;
         }
     }
-warp_per_sample:
     int rc = qo_tf_launch(&p->tfp, p->tf_pp, p->lad_variant, dc->sm_count, &P, dc->stream);
     if (rc < 0) { qo_set_error("no transfer-function kernel instantiation for nn=%d den=%d pp=%d", p->tfp.nn, p->tfp.den, p->tf_pp); return QO_ERR_UNSUPPORTED; }
     if (rc) { qo_set_error("transfer-function kernel launch: %s", cudaGetErrorString((cudaError_t)rc)); return QO_ERR_CUDA; }

@@ -518,8 +518,10 @@ def test_integration_md_c_samples_compile_and_link(Q, tmp_path):
              "    if (qo_ctx_create(1, &ctx)) { fprintf(stderr, \"%s\\n\", qo_last_error()); return 3; }\n" + frag +
              "    printf(\"%llu %llu\\n\", (unsigned long long)res.n_pass, (unsigned long long)res.n_total);\n"
              "    qo_ctx_destroy(ctx); qo_net_free(net); free(f);\n    return 0;\n}\n")
+    bias = next(b for b in blocks if "qo_nodal_jit_analyze" in b)
+    prog3 = bias + "int main(void) { qo_ctx *ctx = NULL; if (qo_ctx_create(1, &ctx)) { fprintf(stderr, \"%s\\n\", qo_last_error()); return 3; } return bias_yield(ctx); }\n"
     libdir = os.path.dirname(Q.LIB_PATH)
-    for name, src in (("resim", resim), ("yield", prog2)):
+    for name, src in (("resim", resim), ("yield", prog2), ("bias", prog3)):
         c = tmp_path / (name + ".c")
         c.write_text(src)
         exe = tmp_path / name

@@ -177,19 +177,22 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
 #define QO_TS_VALUE                                                                                                  \
         double val[PT];                                                                                              \
         if (KE < 2 && !CPL) { QO_PTS_N(PT) val[p] = n2[p]; }                                                         \
-        else { double rd[PT]; lad_rcp_batch<PT>(dd, rd); QO_PTS_N(PT) val[p] = n2[p] * rd[p]; }
+        else { double rd[PT], dc[PT]; QO_PTS_N(PT) dc[p] = dd[p] > 1e-150 ? dd[p] : 1e-150; lad_rcp_batch<PT>(dc, rd); QO_PTS_N(PT) val[p] = n2[p] * rd[p]; }   /* clamp: see qo_tf.cuh */
     /* spec bookkeeping as in qo_mc_tf_kernel: the histogram spec tracks the value n2 / dd, every other spec the sign of
      * thr dd - n2 (or n2 - thr dd).  Inside a run the active specs do not change, so the common cases -- exactly one spec
      * active, or none -- get loops of their own with nothing to decide per group. */
-    unsigned int idle = 0u;              /* points that no spec looks at are evaluated all the same (the metric counts them); their
-                                            |numerator|^2 >= 0 goes into a sign accumulator that can never trip */
+    unsigned int idle = 0u;              /* points that no spec looks at are evaluated all the same (the metric counts them) and land in
+                                            a sink that can never trip: |numerator|^2 = r0^2 - y r1^2 is a sum of non-negative terms, and
+                                            the sign of the TRUNCATED E(y) is masked off -- the plan validates it only where a spec
+                                            looks, and beyond the last band it may well go negative (found by tools/fuzz_parity.py: it
+                                            used to fail spec 0 on such samples) */
     int gi = 0;
     for (int rn = 0; rn < Q.nruns; rn++) {
         const unsigned int any = Q.runs[rn].any, all = Q.runs[rn].all;
         const int g_end = gi + Q.runs[rn].ngroups;
         const int one = (any == all && all != 0u && (all & (all - 1u)) == 0u) ? __ffs((int)all) - 1 : -1;
         if (any == 0u) {
-            for (; gi < g_end; gi++) { QO_TS_CORE QO_PTS_N(PT) idle |= tf_hi(n2[p]) | tf_hi(dd[p]); }
+            for (; gi < g_end; gi++) { QO_TS_CORE QO_PTS_N(PT) idle |= tf_hi(n2[p]) | (tf_hi(dd[p]) & 0x7fffffffu); }
         } else if (one >= 0 && one == hs) {
             for (; gi < g_end; gi++) {
                 QO_TS_CORE
@@ -224,7 +227,7 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
     }
 #undef QO_TS_VALUE
 #undef QO_TS_CORE
-    if (idle >> 31) acc[0] |= idle;      /* never taken: |.|^2 and |D|^2 are non-negative */
+    if (idle >> 31) acc[0] |= idle;      /* never taken (see above); keeps the unobserved points' arithmetic alive */
 }
 
 /* the body for this launch's (kn, kd): one switch per launch, outside the frequency loop */

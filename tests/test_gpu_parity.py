@@ -10,7 +10,9 @@ equal to the oracle's.
 import numpy as np
 import pytest
 
-from conftest import relerr, to_ref
+import os
+
+from conftest import ROOT, relerr, to_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -755,6 +757,7 @@ def test_tf_kernel_s11_specs_behind_a_front_block(Q, R, W, ctx, golden_s2p, monk
     cases.append(("line", line.concat(lad), f, [(0, 0, 0, Q.TOL_REL, 0.05), (0, 1, 1, Q.TOL_REL, 0.03)] + [(e + 1, p_, v + 2, m, t) for (e, p_, v, m, t) in ltol], fc))
     lad2, f2, ltol2 = _ladder_workload(Q, W, 5, False, False, fc=400e6, nf=513)
     cases.append(("block", blk.as_net(True, 50.0, 50.0).concat(lad2), f2, [(e + 1, p_, v, m, t) for (e, p_, v, m, t) in ltol2], 400e6))
+    cases += [(name + "-short", net, f[::12], tols, fcc) for name, net, f, tols, fcc in cases]      # <= 64 points: one pair per thread
     for name, net, f, tols, fcc in cases:
         nom = ctx.sweep(net, f)
         r11 = 20 * np.log10(np.abs(nom[0]))
@@ -785,6 +788,55 @@ def test_tf_kernel_s11_specs_behind_a_front_block(Q, R, W, ctx, golden_s2p, monk
             _assert_counts_equal(ref, got)
             assert 0 < got["n_pass"] < n, (name, got["n_pass"])
     R.sblock_clear()
+
+
+def test_differential_fuzz_of_the_monte_carlo_kernels(monkeypatch):
+    """tools/fuzz_parity.py on a fixed seed: 80 random lumped cascades (all branch kinds, front blocks, |S21| / |S11| specs at
+    quantiles of a FULL_S pre-run, short and long grids, small and thread-per-sample sized launches): the selected kernel, the
+    opcode interpreter and (every 5th) the oracle return identical counters.  The long runs (thousands of networks, several
+    seeds) are recorded under profiles/."""
+    import importlib.util
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--nets", "80", "--samples", "1500", "--seed", "7", "--big-every", "5"])
+    assert out["mismatches"] == 0, out["details"]
+    assert out["compared"] >= 70 and out["oracle_checked"] >= 10
+    assert {"qo_mc_tf_kernel", "qo_mc_ts_kernel", "qo_mc_spot_kernel"} <= set(out["kernels_selected"])
+
+
+def test_fuzz_regressions(Q, R, ctx, monkeypatch):
+    """The networks on which tools/fuzz_parity.py caught the transfer-function kernels (recorded under profiles/fuzz/):
+    (a) thread-per-sample kernel: the truncated E(y) goes negative beyond the last spec band on some samples and used to fail
+        spec 0 through the sink that keeps unobserved points alive;
+    (b) histogram on a MIN-dB spec whose band holds a trap: on a sample that resonates exactly at a grid point E(y) rounds to
+        <= 0 and the negative n2 / dd used to drop out of the running maximum.
+    Both must now equal the interpreter and the oracle on the recorded sample ranges."""
+    import json
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    for fn, idx, kernel in (("fuzz_r02_seed5.json", 119, "qo_mc_ts_kernel"), ("fuzz_r02d_seed12.json", 1826, "qo_mc_tf_kernel"),
+                            ("fuzz_r02d_seed14.json", 242, "qo_mc_tf_kernel")):
+        m = next(x for x in json.load(open(os.path.join(ROOT, "profiles", "fuzz", fn)))["details"] if x["net"] == idx)
+        net = Q.Net.from_elements([(k, p) for k, p in m["elements"]], *m["terminations"])
+        f = Q.grid_log(m["f0"], m["f1"], m["nf"]) if m["log_grid"] else Q.grid_lin(m["f0"], m["f1"], m["nf"])
+        tols, specs = [tuple(t) for t in m["tols"]], [tuple(s_) for s_ in m["specs"]]
+        res = {}
+        for force in (None, "interp"):
+            if force:
+                monkeypatch.setenv("QO100NET_KERNEL", force)
+            plan = Q.Plan(ctx, net, f, specs, seed=m["seed"], tols=tols, dist=m["dist"], **m["hist"])
+            plan.launch(m["offset"], m["n"])
+            res[force] = plan.read()
+            if not force:
+                assert plan.kernel_name == kernel
+            plan.close()
+            monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        _assert_counts_equal(res["interp"], res[None])
+        assert [int(v) for v in res[None]["fail_per_spec"]] == m["interp_fail"]          # what the interpreter and the oracle said then
+        rs, rl = net.terminations
+        ref = R.mc_run(to_ref(R, net), rs, rl, f, specs, R.mc_cfg(m["seed"], m["n"], tols, sample_offset=m["offset"], dist=m["dist"], **m["hist"]), nthreads=8)
+        _assert_counts_equal(ref, res[None])
 
 
 def test_group_delay_spec_in_kernel(Q, R, W, ctx, monkeypatch):

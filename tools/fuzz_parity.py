@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Differential fuzz of the Monte-Carlo kernels on random lumped cascades (GPU box).
+
+For each of --nets random networks -- 3..14 branches drawn from all ten lumped branch kinds (with and without parasitics),
+optionally behind a front block (coupled line, transmission line), random terminations, random tolerances, log or linear
+grid of random length, 1..4 specs on |S21| / |S11| placed at quantiles of a FULL_S pre-run so that the yield is never
+degenerate, optional histogram -- the job runs
+   (a) on the kernel the plan selects (thread-per-sample / warp-per-sample transfer-function kernel, spot kernel, chain kernel),
+   (b) on the opcode interpreter (QO100NET_KERNEL=interp),
+   (c) every --oracle-every-th network on the CPU oracle,
+and all integer counters (n_pass, fail_per_spec, histogram) must be identical.  Prints one JSON summary.
+
+   python tools/fuzz_parity.py [--nets 300] [--samples 3000] [--seed 1] [--out gpurun_out/fuzz.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
+sys.path.insert(0, ROOT)
+
+
+def random_net(Q, rng):
+    fc = 10.0 ** rng.uniform(6.5, 9.3)
+    wc = 2 * np.pi * fc
+    z0 = float(rng.choice([50.0, 50.0, 75.0, 100.0]))
+    n = int(rng.integers(3, 15))
+    el = []
+    series = bool(rng.integers(0, 2))
+    for _ in range(n):
+        g = rng.uniform(0.3, 2.2)
+        L, C = g * z0 / wc, g / (z0 * wc)
+        par = rng.random() < 0.6
+        kind = rng.integers(0, 10)
+        if series:
+            if kind < 5:
+                el.append((Q.SER_L, [L, (wc * L / rng.uniform(30, 200)) if par else 0.0, (1 / (L * (wc * rng.uniform(8, 60)) ** 2)) if par else 0.0]))
+            elif kind < 7:
+                el.append((Q.SER_C, [C * rng.uniform(5, 40), rng.uniform(0.02, 0.5) if par else 0.0, (1 / (C * 20 * (wc * rng.uniform(10, 60)) ** 2)) if par else 0.0]))
+            elif kind == 7:
+                el.append((Q.SER_R, [rng.uniform(0.2, 5.0)]))
+            elif kind == 8:
+                el.append((Q.SER_LC_SER, [L * 0.1, C * rng.uniform(20, 60)]))
+            else:
+                k = rng.uniform(1.6, 3.0)                      # trap above the pass band
+                el.append((Q.SER_LC_PAR, [L * 0.15, 1 / (L * 0.15 * (k * wc) ** 2)]))
+        else:
+            if kind < 5:
+                el.append((Q.SHUNT_C, [C, rng.uniform(0.02, 0.5) if par else 0.0, (1 / (C * (wc * rng.uniform(10, 60)) ** 2)) if par else 0.0]))
+            elif kind < 7:
+                el.append((Q.SHUNT_L, [L * rng.uniform(5, 40), rng.uniform(0.05, 1.0) if par else 0.0, (1 / (L * 20 * (wc * rng.uniform(8, 40)) ** 2)) if par else 0.0]))
+            elif kind == 7:
+                el.append((Q.SHUNT_R, [z0 * rng.uniform(10, 100)]))
+            elif kind == 8:
+                k = rng.uniform(1.6, 3.0)
+                el.append((Q.SHUNT_LC_SER, [L * 3.0, 1 / (L * 3.0 * (k * wc) ** 2)]))
+            else:
+                el.append((Q.SHUNT_LC_PAR, [L * rng.uniform(8, 30), C * 0.05]))
+        if rng.random() < 0.85:
+            series = not series
+    front = rng.integers(0, 4)
+    tols = []
+    if front == 1:
+        te = rng.uniform(40, 110)
+        el = [(Q.CPL_THRU, [z0 * 1.105, z0 / 1.105, te, te * (1.0 if rng.random() < 0.5 else rng.uniform(0.93, 1.0)), fc, z0])] + el
+        tols += [(0, 0, 0, Q.TOL_REL, 0.02), (0, 1, 1, Q.TOL_REL, 0.02), (0, 2, 2, Q.TOL_REL, 0.01), (0, 3, 2, Q.TOL_REL, 0.01)]
+    elif front == 2:
+        el = [(Q.TLINE, [z0 * rng.uniform(0.7, 1.5), rng.uniform(10, 120), fc])] + el
+        tols += [(0, 0, 0, Q.TOL_REL, 0.05), (0, 1, 1, Q.TOL_REL, 0.03)]
+    nv = len(tols)
+    for e, (k, p) in enumerate(el):
+        if k in (Q.SER_L, Q.SHUNT_L, Q.SER_C, Q.SHUNT_C, Q.SER_LC_SER, Q.SER_LC_PAR, Q.SHUNT_LC_SER, Q.SHUNT_LC_PAR) and rng.random() < 0.9:
+            tols.append((e, 0, nv, Q.TOL_REL, float(rng.choice([0.01, 0.02, 0.05, 0.1]))))
+            nv += 1
+            if k >= Q.SER_LC_SER and rng.random() < 0.5:
+                tols.append((e, 1, nv, Q.TOL_REL, 0.05))
+                nv += 1
+        elif k in (Q.SER_R, Q.SHUNT_R) and rng.random() < 0.5:
+            tols.append((e, 0, nv, Q.TOL_REL, 0.05))
+            nv += 1
+    if not tols:                                     # no tolerance at all: every sample is the nominal network
+        tols.append((len(el) - 1, 0, 0, Q.TOL_REL, 0.05))
+    rs = z0 if rng.random() < 0.7 else z0 * rng.uniform(0.5, 2.0)
+    rl = z0 if rng.random() < 0.7 else z0 * rng.uniform(0.5, 2.0)
+    nf = int(rng.choice([3, 7, 33, 64, 200, 515, 1000, 2048, 4096]))
+    span = rng.uniform(2.0, 6.0)
+    f = Q.grid_log(fc / span, fc * span, nf) if rng.random() < 0.6 else Q.grid_lin(fc / span, fc * span, nf)
+    return Q.Net.from_elements(el, float(rs), float(rl)), f, tols, fc
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nets", type=int, default=300)
+    ap.add_argument("--samples", type=int, default=3000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--oracle-every", type=int, default=5)
+    ap.add_argument("--big-every", type=int, default=7, help="every k-th network runs a launch large enough for the thread-per-sample kernel")
+    ap.add_argument("--only", type=int, default=-1, help="run just this network (each network has its own random stream) and dump it")
+    ap.add_argument("--out", default=None)
+    args = ap.parse_args(argv)
+    import qo100net as Q
+    from oracle import refbind as R
+    ctx = Q.Context(device=0)
+    kernels, mism, skipped, oracle_checked = {}, [], 0, 0
+    big = 2 * 148 * 3 * 128 + 77          # large enough for the thread-per-sample kernel on every 7th network
+    for i in range(args.nets):
+        if args.only >= 0 and i != args.only:
+            continue
+        rng = np.random.default_rng([args.seed, i])          # one stream per network: --only reproduces it exactly
+        net, f, tols, fc = random_net(Q, rng)
+        n = big if i % args.big_every == args.big_every - 1 else args.samples
+        dist = Q.DIST_GAUSS3S if rng.random() < 0.3 else Q.DIST_UNIFORM
+        try:
+            fs = ctx.mc_run(net, f, [], 99, 200, tols, mode=Q.MODE_FULL_S, dist=dist)["s"]
+        except Q.QoError:
+            skipped += 1
+            continue
+        a21 = 20 * np.log10(np.maximum(np.abs(fs[1]), 1e-300))
+        a11 = 20 * np.log10(np.maximum(np.abs(fs[0]), 1e-300))
+        if not (np.all(np.isfinite(a21)) and np.all(np.isfinite(a11))):
+            skipped += 1
+            continue
+        specs = []
+        for _ in range(int(rng.integers(1, 5))):
+            lo, hi = sorted(rng.uniform(f[0], f[-1], 2))
+            if rng.random() < 0.3:
+                lo = hi = float(f[int(rng.integers(0, len(f)))])
+            band = (f >= lo) & (f <= hi)
+            if not band.any():
+                continue
+            kind = int(rng.choice([Q.SPEC_S21_MIN_DB, Q.SPEC_S21_MAX_DB, Q.SPEC_S11_MAX_DB]))
+            q = float(rng.uniform(0.2, 0.8))
+            if kind == Q.SPEC_S21_MIN_DB:
+                v, qq = a21[:, band].min(axis=1), 1 - q
+            elif kind == Q.SPEC_S21_MAX_DB:
+                v, qq = a21[:, band].max(axis=1), q
+            else:
+                v, qq = a11[:, band].max(axis=1), q
+            # no knife-edge specs: a quantity the tolerances barely move (all samples within 0.01 dB: any threshold inside that
+            # cluster is decided by the last bits of whichever formulation evaluates it) or the depth of a notch sampled on the grid
+            if np.quantile(v, 0.9) - np.quantile(v, 0.1) < 0.01 or v.min() < -140.0:
+                continue
+            specs.append((kind, float(lo), float(hi), float(np.quantile(v, qq))))
+        if not specs:
+            skipped += 1
+            continue
+        hist = {}
+        if rng.random() < 0.6:
+            hs = int(rng.integers(0, len(specs)))
+            hist = dict(hist_bins=int(rng.choice([16, 64, 256])), hist_spec=hs, hist_lo=specs[hs][3] - 3.0, hist_hi=specs[hs][3] + 3.0)
+        os.environ.pop("QO100NET_KERNEL", None)
+        plan = Q.Plan(ctx, net, f, specs, seed=1000 + i, tols=tols, dist=dist, **hist)
+        off = int(rng.integers(0, 2 ** 40))
+        plan.launch(off, n)
+        got = plan.read()
+        kname = plan.kernel_name
+        plan.close()
+        kernels[kname] = kernels.get(kname, 0) + 1
+        os.environ["QO100NET_KERNEL"] = "interp"
+        plan = Q.Plan(ctx, net, f, specs, seed=1000 + i, tols=tols, dist=dist, **hist)
+        plan.launch(off, n)
+        ref = plan.read()
+        plan.close()
+        os.environ.pop("QO100NET_KERNEL", None)
+        same = got["n_pass"] == ref["n_pass"] and np.array_equal(got["fail_per_spec"], ref["fail_per_spec"]) and np.array_equal(got["hist"], ref["hist"])
+        if same and i % args.oracle_every == 0 and n <= args.samples:
+            rs, rl = net.terminations
+            o = R.mc_run(R.make_elems(net.elements), rs, rl, f, specs, R.mc_cfg(1000 + i, n, tols, sample_offset=off, dist=dist, **hist), nthreads=R.max_threads())
+            oracle_checked += 1
+            same = got["n_pass"] == o["n_pass"] and np.array_equal(got["fail_per_spec"], o["fail_per_spec"]) and np.array_equal(got["hist"], o["hist"])
+        if not same:
+            mism.append({"net": i, "kernel": kname, "n": n, "nf": len(f), "f0": float(f[0]), "f1": float(f[-1]), "log_grid": bool(abs(f[1] / f[0] - f[2] / f[1]) < 1e-9),
+                         "terminations": [float(v) for v in net.terminations], "elements": [(int(k), [float(x) for x in p]) for k, p in net.elements],
+                         "tols": [[int(a), int(b), int(c), int(d), float(e)] for a, b, c, d, e in tols], "dist": int(dist), "offset": off, "seed": 1000 + i, "hist": hist,
+                         "specs": specs, "got": int(got["n_pass"]), "interp": int(ref["n_pass"]),
+                         "got_fail": [int(v) for v in got["fail_per_spec"]], "interp_fail": [int(v) for v in ref["fail_per_spec"]]})
+    out = {"networks": args.nets, "skipped": skipped, "compared": args.nets - skipped, "oracle_checked": oracle_checked,
+           "kernels_selected": kernels, "mismatches": len(mism), "details": mism[:10], "seed": args.seed, "samples": args.samples}
+    print(json.dumps(out, indent=1))
+    if args.out:
+        open(args.out, "w").write(json.dumps(out, indent=1))
+    ctx.close()
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main()["mismatches"] else 0)

@@ -370,3 +370,19 @@ def test_gpu_nodal_job_sharded_over_the_gpus_of_a_ctx(Q, ctx, pa_bias, golden_s2
         assert np.array_equal(s1, sm)
     cm.close()
     nd.close()
+
+
+@pytest.mark.gpu
+def test_gpu_nodal_differential_fuzz(monkeypatch):
+    """tools/fuzz_nodal.py on a fixed seed: 12 random N-port networks (3-13 nodes, R / L / C with parasitics, an ideal buffer in
+    some, 1-4 ports): the run-time compiled kernel, the interpreted plan and per-point pivoting agree on FULL_S planes and on
+    Monte-Carlo counters, every 4th network also with the oracle.  The long run (150 networks) is under profiles/fuzz/."""
+    import importlib.util
+    from conftest import ROOT
+    monkeypatch.delenv("QO100NET_NODAL", raising=False)
+    spec = importlib.util.spec_from_file_location("fuzz_nodal", os.path.join(ROOT, "tools", "fuzz_nodal.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--nets", "12", "--seed", "3", "--samples", "1500"])
+    assert out["mismatches"] == 0, out["details"]
+    assert out["compared"] >= 10 and out["kernels"].get("qo_nodal_jit_kernel", 0) >= 10

@@ -24,6 +24,21 @@ sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
 sys.path.insert(0, ROOT)
 
 
+_BLK = {}
+
+
+def _block(Q):
+    """The measured inductor of pa-bias-simulation.sch:39 (tests/golden/touchstone.npz), registered with the oracle as block 0."""
+    if not _BLK:
+        from oracle import refbind as R
+        g = np.load(os.path.join(ROOT, "tests", "golden", "touchstone.npz"))
+        fd, sd, z0 = g["11SQ39N_f"], g["11SQ39N_s"], float(g["11SQ39N_z0"])
+        _BLK["blk"] = Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+        R.sblock_clear()
+        R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    return _BLK["blk"]
+
+
 def random_net(Q, rng):
     fc = 10.0 ** rng.uniform(6.5, 9.3)
     wc = 2 * np.pi * fc
@@ -62,7 +77,7 @@ def random_net(Q, rng):
                 el.append((Q.SHUNT_LC_PAR, [L * rng.uniform(8, 30), C * 0.05]))
         if rng.random() < 0.85:
             series = not series
-    front = rng.integers(0, 4)
+    front = rng.integers(0, 5)
     tols = []
     if front == 1:
         te = rng.uniform(40, 110)
@@ -89,7 +104,11 @@ def random_net(Q, rng):
     nf = int(rng.choice([3, 7, 33, 64, 200, 515, 1000, 2048, 4096]))
     span = rng.uniform(2.0, 6.0)
     f = Q.grid_log(fc / span, fc * span, nf) if rng.random() < 0.6 else Q.grid_lin(fc / span, fc * span, nf)
-    return Q.Net.from_elements(el, float(rs), float(rl)), f, tols, fc
+    net = Q.Net.from_elements(el, float(rs), float(rl))
+    if front == 4 and fc < 2e9:                      # measured two-port in front (polar or rectangular interpolation)
+        net = _block(Q).as_net(bool(rng.integers(0, 2)), float(rs), float(rl)).concat(net)
+        tols = [(e + 1, p, v, m_, t) for (e, p, v, m_, t) in tols]
+    return net, f, tols, fc
 
 
 def main(argv=None):
@@ -105,7 +124,7 @@ def main(argv=None):
     import qo100net as Q
     from oracle import refbind as R
     ctx = Q.Context(device=0)
-    kernels, mism, skipped, oracle_checked = {}, [], 0, 0
+    kernels, mism, skipped, oracle_checked, fs_checked = {}, [], 0, 0, 0
     big = 2 * 148 * 3 * 128 + 77          # large enough for the thread-per-sample kernel on every 7th network
     for i in range(args.nets):
         if args.only >= 0 and i != args.only:
@@ -125,7 +144,7 @@ def main(argv=None):
             skipped += 1
             continue
         specs = []
-        for _ in range(int(rng.integers(1, 5))):
+        for _ in range(int(rng.choice([1, 2, 3, 4, 4, 6, 8]))):
             lo, hi = sorted(rng.uniform(f[0], f[-1], 2))
             if rng.random() < 0.3:
                 lo = hi = float(f[int(rng.integers(0, len(f)))])
@@ -172,13 +191,24 @@ def main(argv=None):
             o = R.mc_run(R.make_elems(net.elements), rs, rl, f, specs, R.mc_cfg(1000 + i, n, tols, sample_offset=off, dist=dist, **hist), nthreads=R.max_threads())
             oracle_checked += 1
             same = got["n_pass"] == o["n_pass"] and np.array_equal(got["fail_per_spec"], o["fail_per_spec"]) and np.array_equal(got["hist"], o["hist"])
+        if same and i % 4 == 1:
+            # FULL_S: a launch large enough for qo_fs_tf_kernel against the interpreter's planes of the same samples
+            a = ctx.mc_run(net, f, [], 1000 + i, 1536, tols, sample_offset=off, mode=Q.MODE_FULL_S, dist=dist)["s"]
+            b = ctx.mc_run(net, f, [], 1000 + i, 64, tols, sample_offset=off, mode=Q.MODE_FULL_S, dist=dist)["s"]
+            fs_checked += 1
+            for pl in range(4):
+                ref_ = np.asarray(b[pl]); got_ = np.asarray(a[pl])[:64]
+                tol_ = 1e-9 * np.maximum(np.abs(ref_), 1e-6 if pl in (1, 2) else 0.02)
+                if not np.all(np.abs(got_ - ref_) <= tol_):
+                    same = False
+                    kname = "FULL_S plane %d (1536 vs 64 samples)" % pl
         if not same:
             mism.append({"net": i, "kernel": kname, "n": n, "nf": len(f), "f0": float(f[0]), "f1": float(f[-1]), "log_grid": bool(abs(f[1] / f[0] - f[2] / f[1]) < 1e-9),
                          "terminations": [float(v) for v in net.terminations], "elements": [(int(k), [float(x) for x in p]) for k, p in net.elements],
                          "tols": [[int(a), int(b), int(c), int(d), float(e)] for a, b, c, d, e in tols], "dist": int(dist), "offset": off, "seed": 1000 + i, "hist": hist,
                          "specs": specs, "got": int(got["n_pass"]), "interp": int(ref["n_pass"]),
                          "got_fail": [int(v) for v in got["fail_per_spec"]], "interp_fail": [int(v) for v in ref["fail_per_spec"]]})
-    out = {"networks": args.nets, "skipped": skipped, "compared": args.nets - skipped, "oracle_checked": oracle_checked,
+    out = {"networks": args.nets, "skipped": skipped, "compared": args.nets - skipped, "oracle_checked": oracle_checked, "full_s_checked": fs_checked,
            "kernels_selected": kernels, "mismatches": len(mism), "details": mism[:10], "seed": args.seed, "samples": args.samples}
     print(json.dumps(out, indent=1))
     if args.out:

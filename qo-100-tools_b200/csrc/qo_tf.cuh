@@ -573,10 +573,10 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 }
             }
             /* every spec tracks  numer / denom:  |den|^2 = n2 / dd  (|S21| specs),  |S11|^2 = m2 / n2.
-             * dd is clamped from below before the batched reciprocal: on a sample whose trap resonates exactly at a grid point
-             * the polynomial E(y) -- a double root there -- rounds to zero or slightly below, and a negative n2 / dd would drop
-             * out of the running maximum although |S21| = 0 at that point is the worst value there is (found by
-             * tools/fuzz_parity.py; the sign tests need no guard: thr dd - n2 < 0 fails the spec for dd <= 0 as it should) */
+             * The VALUE is taken as |n2 / dd|: on a sample whose trap resonates exactly at a grid point the polynomial E(y) -- a
+             * double root there -- rounds to slightly below zero, and a negative n2 / dd would drop out of the running maximum
+             * (or win the running minimum) although |S21| ~ 0 there means |den|^2 is huge (found by tools/fuzz_parity.py; the
+             * sign tests need no guard: thr dd - n2 < 0 fails a MIN-dB spec for dd <= 0 as it should) */
 #define QO_TF_VALUE(val)                                                                                          \
             double val[PTS];                                                                                      \
             if (GD && P.gd[sp]) {          /* tau wref = gA / n2 - gB / dd */                                     \
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(TPB, MINB) qo_mc_tf_kernel(const __grid_consta
                 QO_PTS val[p] = fma(gA[p], dd[p], -gB[p] * n2[p]) * rd[p];                                         \
             } else if (S11 && P.s11[sp]) { double rd[PTS]; lad_rcp_batch<PTS>(n2, rd); QO_PTS val[p] = m2[p] * rd[p]; } \
             else if (DEN == QO_TF_DEN_NONE && !CPL) { QO_PTS val[p] = n2[p]; }                                     \
-            else { double rd[PTS], dc[PTS]; QO_PTS dc[p] = dd[p] > 1e-150 ? dd[p] : 1e-150; lad_rcp_batch<PTS>(dc, rd); QO_PTS val[p] = n2[p] * rd[p]; }
+            else { double rd[PTS]; lad_rcp_batch<PTS>(dd, rd); QO_PTS val[p] = fabs(n2[p] * rd[p]); }
 #define QO_TF_SIGN(sg)                                                                                            \
             unsigned int sg[PTS];                                                                                 \
             {                                                                                                     \

@@ -177,7 +177,7 @@ __device__ __forceinline__ void ts_loop(const TsParams &Q, unsigned long long sa
 #define QO_TS_VALUE                                                                                                  \
         double val[PT];                                                                                              \
         if (KE < 2 && !CPL) { QO_PTS_N(PT) val[p] = n2[p]; }                                                         \
-        else { double rd[PT], dc[PT]; QO_PTS_N(PT) dc[p] = dd[p] > 1e-150 ? dd[p] : 1e-150; lad_rcp_batch<PT>(dc, rd); QO_PTS_N(PT) val[p] = n2[p] * rd[p]; }   /* clamp: see qo_tf.cuh */
+        else { double rd[PT]; lad_rcp_batch<PT>(dd, rd); QO_PTS_N(PT) val[p] = fabs(n2[p] * rd[p]); }   /* |.|: see qo_tf.cuh */
     /* spec bookkeeping as in qo_mc_tf_kernel: the histogram spec tracks the value n2 / dd, every other spec the sign of
      * thr dd - n2 (or n2 - thr dd).  Inside a run the active specs do not change, so the common cases -- exactly one spec
      * active, or none -- get loops of their own with nothing to decide per group. */

@@ -198,7 +198,7 @@ def main(argv=None):
             fs_checked += 1
             for pl in range(4):
                 ref_ = np.asarray(b[pl]); got_ = np.asarray(a[pl])[:64]
-                tol_ = 1e-9 * np.maximum(np.abs(ref_), 1e-6 if pl in (1, 2) else 0.02)
+                tol_ = 1e-9 * np.maximum(np.abs(ref_), 1e-5 if pl in (1, 2) else 0.02)      # -100 dB floor: next to an ideal trap's zero every formulation is down to ~1e-15 absolute
                 if not np.all(np.abs(got_ - ref_) <= tol_):
                     same = False
                     kname = "FULL_S plane %d (1536 vs 64 samples)" % pl

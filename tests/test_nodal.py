@@ -302,6 +302,8 @@ def test_gpu_nodal_compiled_kernel_equals_interpreted_dense_and_oracle(Q, R, ctx
     dataset, Monte-Carlo counters and histogram equal the interpreted static kernel's, the pivoted kernel's and the oracle's,
     FULL_S planes agree to rounding, and the multiplier guard still hands a tripped job to the pivoted kernel."""
     nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    if not nd.jit_analyze(pa_bias["frequency"][:50])["compiled"]:
+        pytest.skip("no NVRTC on this machine")
     register_inductor(R, golden_s2p)
     monkeypatch.setenv("QO100NET_NODAL", "jit")
     S = ctx.nodal_sweep(nd, pa_bias["frequency"])
@@ -359,7 +361,7 @@ def test_gpu_nodal_job_sharded_over_the_gpus_of_a_ctx(Q, ctx, pa_bias, golden_s2
     hist = dict(hist_bins=20, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)
     ng = 4 if torch.cuda.device_count() >= 4 else 2
     cm = Q.Context(ngpus=ng)
-    for mode in ("static", "jit"):
+    for mode in (("static", "jit") if nd.jit_analyze(f)["compiled"] else ("static",)):
         monkeypatch.setenv("QO100NET_NODAL", mode)
         one = ctx.nodal_mc_run(nd, f, specs, 3, 10001, tols, sample_offset=77, **hist)
         many = cm.nodal_mc_run(nd, f, specs, 3, 10001, tols, sample_offset=77, **hist)
@@ -380,6 +382,12 @@ def test_gpu_nodal_differential_fuzz(monkeypatch):
     import importlib.util
     from conftest import ROOT
     monkeypatch.delenv("QO100NET_NODAL", raising=False)
+    import qo100net
+    probe = qo100net.Nodal(1)
+    probe.add_branch(NB_R, [1, 0], [50.0])
+    probe.add_port(1, 50.0)
+    if not probe.jit_analyze(np.array([1e6, 2e6]))["compiled"]:
+        pytest.skip("no NVRTC on this machine")
     spec = importlib.util.spec_from_file_location("fuzz_nodal", os.path.join(ROOT, "tools", "fuzz_nodal.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

@@ -39,6 +39,26 @@ def _block(Q):
     return _BLK["blk"]
 
 
+def random_ladder(Q, rng):
+    """pcb/generic-filter family: alternating series L / shunt C of order 1..11 with the ESR / SRF parasitic model, optionally behind
+    a coupled-line section -- what the straight-line chain kernel (QO100NET_KERNEL=ladder) covers."""
+    fc = 10.0 ** rng.uniform(6.5, 9.3)
+    order = int(rng.integers(1, 12))
+    net = (Q.Net.butter_lpf(order, fc, 50.0, bool(rng.integers(0, 2))) if (rng.random() < 0.4 or order % 2 == 0) else Q.Net.cheby_lpf(order, float(rng.choice([0.05, 0.1, 0.5])), fc, 50.0, bool(rng.integers(0, 2))))
+    if rng.random() < 0.8:
+        net = net.add_parasitics(fc, rng.uniform(30, 150), rng.uniform(8, 40), rng.uniform(0.02, 0.5), rng.uniform(10, 60))
+    tols = Q.lc_tolerances(net, float(rng.choice([0.02, 0.05, 0.1])), float(rng.choice([0.01, 0.02, 0.05])))
+    if rng.random() < 0.4:
+        te = rng.uniform(40, 110)
+        cpl = Q.Net.from_elements([(Q.CPL_THRU, [55.2771, 45.2267, te, te * (1.0 if rng.random() < 0.5 else rng.uniform(0.93, 1.0)), fc, 50.0])], 50.0, 50.0)
+        net = cpl.concat(net)
+        tols = [(0, 0, 0, Q.TOL_REL, 0.02), (0, 1, 1, Q.TOL_REL, 0.02), (0, 2, 2, Q.TOL_REL, 0.01), (0, 3, 2, Q.TOL_REL, 0.01)] + [(e + 1, p, v + 3, m_, t) for (e, p, v, m_, t) in tols]
+    nf = int(rng.choice([3, 33, 64, 200, 515, 1000, 4096]))
+    span = rng.uniform(2.0, 6.0)
+    f = Q.grid_log(fc / span, fc * span, nf) if rng.random() < 0.6 else Q.grid_lin(fc / span, fc * span, nf)
+    return net, f, tols, fc
+
+
 def random_net(Q, rng):
     fc = 10.0 ** rng.uniform(6.5, 9.3)
     wc = 2 * np.pi * fc
@@ -118,6 +138,7 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--oracle-every", type=int, default=5)
     ap.add_argument("--big-every", type=int, default=7, help="every k-th network runs a launch large enough for the thread-per-sample kernel")
+    ap.add_argument("--ladders", action="store_true", help="pcb/generic-filter ladders only, the selected run forced onto the chain kernel (QO100NET_KERNEL=ladder)")
     ap.add_argument("--only", type=int, default=-1, help="run just this network (each network has its own random stream) and dump it")
     ap.add_argument("--out", default=None)
     args = ap.parse_args(argv)
@@ -130,7 +151,7 @@ def main(argv=None):
         if args.only >= 0 and i != args.only:
             continue
         rng = np.random.default_rng([args.seed, i])          # one stream per network: --only reproduces it exactly
-        net, f, tols, fc = random_net(Q, rng)
+        net, f, tols, fc = random_ladder(Q, rng) if args.ladders else random_net(Q, rng)
         n = big if i % args.big_every == args.big_every - 1 else args.samples
         dist = Q.DIST_GAUSS3S if rng.random() < 0.3 else Q.DIST_UNIFORM
         try:
@@ -172,6 +193,8 @@ def main(argv=None):
             hs = int(rng.integers(0, len(specs)))
             hist = dict(hist_bins=int(rng.choice([16, 64, 256])), hist_spec=hs, hist_lo=specs[hs][3] - 3.0, hist_hi=specs[hs][3] + 3.0)
         os.environ.pop("QO100NET_KERNEL", None)
+        if args.ladders:
+            os.environ["QO100NET_KERNEL"] = "ladder"
         plan = Q.Plan(ctx, net, f, specs, seed=1000 + i, tols=tols, dist=dist, **hist)
         off = int(rng.integers(0, 2 ** 40))
         plan.launch(off, n)

@@ -97,12 +97,18 @@ def random_net(Q, rng):
                 el.append((Q.SHUNT_LC_PAR, [L * rng.uniform(8, 30), C * 0.05]))
         if rng.random() < 0.85:
             series = not series
-    front = rng.integers(0, 5)
+    front = rng.integers(0, 6)
     tols = []
     if front == 1:
         te = rng.uniform(40, 110)
         el = [(Q.CPL_THRU, [z0 * 1.105, z0 / 1.105, te, te * (1.0 if rng.random() < 0.5 else rng.uniform(0.93, 1.0)), fc, z0])] + el
         tols += [(0, 0, 0, Q.TOL_REL, 0.02), (0, 1, 1, Q.TOL_REL, 0.02), (0, 2, 2, Q.TOL_REL, 0.01), (0, 3, 2, Q.TOL_REL, 0.01)]
+    elif front == 5:
+        # physical coupled microstrip (util/directional-couplers/dir_cpl_2.4g_20dB.trc:6-17 scaled): etch on W (and -/+ on S), H, Er
+        sub = (Q.SUBST, [3.5 * rng.uniform(0.8, 1.3), 0.762e-3, 35e-6, 0.0, 0.0, 0.0])
+        cpl = (Q.CPL_MS, [1.69218e-3 * rng.uniform(0.8, 1.25), 0.991476e-3 * rng.uniform(0.7, 1.5), 20e-3 * rng.uniform(0.5, 1.5) * 2.4e9 / max(fc, 3e8), 0.2, max(fc, 3e8), z0])
+        el = [sub, cpl] + el
+        tols += [(1, 0, 0, Q.TOL_ABS, 0.03e-3), (1, 1, 0, Q.TOL_ABS, -0.03e-3), (0, 1, 1, Q.TOL_REL, 0.05), (0, 0, 2, Q.TOL_ABS, 0.1)]
     elif front == 2:
         el = [(Q.TLINE, [z0 * rng.uniform(0.7, 1.5), rng.uniform(10, 120), fc])] + el
         tols += [(0, 0, 0, Q.TOL_REL, 0.05), (0, 1, 1, Q.TOL_REL, 0.03)]
@@ -139,6 +145,7 @@ def main(argv=None):
     ap.add_argument("--oracle-every", type=int, default=5)
     ap.add_argument("--big-every", type=int, default=7, help="every k-th network runs a launch large enough for the thread-per-sample kernel")
     ap.add_argument("--ladders", action="store_true", help="pcb/generic-filter ladders only, the selected run forced onto the chain kernel (QO100NET_KERNEL=ladder)")
+    ap.add_argument("--gd", action="store_true", help="add a group-delay spec (limit around the nominal network's worst in-band delay) to networks without a front block")
     ap.add_argument("--only", type=int, default=-1, help="run just this network (each network has its own random stream) and dump it")
     ap.add_argument("--out", default=None)
     args = ap.parse_args(argv)
@@ -185,6 +192,14 @@ def main(argv=None):
             if np.quantile(v, 0.9) - np.quantile(v, 0.1) < 0.01 or v.min() < -140.0:
                 continue
             specs.append((kind, float(lo), float(hi), float(np.quantile(v, qq))))
+        if args.gd and net.elements[0][0] not in (Q.CPL_THRU, Q.TLINE, Q.SBLOCK) and len(specs) < 8 and not any(s_[0] == Q.SPEC_S11_MAX_DB for s_ in specs):
+            gdn = ctx.sweep(net, f, gd=True)[4]
+            lo, hi = sorted(rng.uniform(f[0], f[-1], 2))
+            band = (f >= lo) & (f <= hi)
+            # not across a transmission zero: the delay is singular there, and the kernels' analytic derivative and the
+            # interpreter's / oracle's central difference over f (1 +- 1e-6) are two different approximations of it
+            if band.any() and np.all(np.isfinite(gdn[band])) and gdn[band].max() > 0 and a21[:, band].min() > -60.0:
+                specs.append((Q.SPEC_GD_MAX, float(lo), float(hi), float(gdn[band].max() * rng.uniform(0.97, 1.08))))
         if not specs:
             skipped += 1
             continue

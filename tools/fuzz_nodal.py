@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
 sys.path.insert(0, ROOT)
 
-NB_R, NB_L, NB_C, NB_VCVS = 1, 2, 3, 4
+NB_R, NB_L, NB_C, NB_VCVS, NB_SBLOCK = 1, 2, 3, 4, 5
 
 
 def random_network(rng):
@@ -54,6 +54,11 @@ def random_network(rng):
         nn += 1
         br.append((NB_VCVS, [a, nn, 0, 0], [rng.uniform(0.5, 3.0), 0.0 if rng.random() < 0.5 else rng.uniform(0.0, 0.3) / fc]))
         br.append((NB_R, [nn, int(rng.integers(1, nn))], [z0 * rng.uniform(0.5, 3.0)]))
+    if rng.random() < 0.3 and fc < 2.5e9:            # the measured inductor of pa-bias-simulation.sch:39 between two nodes (or to ground)
+        a = int(rng.integers(1, nn + 1))
+        b = int(rng.integers(0, nn + 1))
+        if a != b:
+            br.append((NB_SBLOCK, [a, b, 0], [0, float(rng.integers(0, 2)), 50.0]))
     tols = []
     for i, (k, _n, _p) in enumerate(br):
         if k in (NB_R, NB_L, NB_C) and rng.random() < 0.8:
@@ -82,6 +87,13 @@ def main(argv=None):
         br, nn, ports, tols, fc, nf, span = random_network(rng)
         f = Q.grid_log(fc / span, fc * span, nf) if rng.random() < 0.5 else Q.grid_lin(fc / span, fc * span, nf)
         nd = Q.Nodal(nn)
+        if any(k == NB_SBLOCK for k, _n, _p in br):
+            g = np.load(os.path.join(ROOT, "tests", "golden", "touchstone.npz"))
+            fd, sd = g["11SQ39N_f"], g["11SQ39N_s"]
+            idx = nd.add_sblock(Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], 50.0))
+            R.sblock_clear()
+            R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], 50.0)
+            br = [(k, n_, [idx, p[1], p[2]] if k == NB_SBLOCK else p) for k, n_, p in br]
         for kind, nodes, p in br:
             nd.add_branch(kind, nodes, p)
         for node, z in ports:

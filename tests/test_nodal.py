@@ -3,12 +3,13 @@ util/pa-bias-simulation/pa-bias-simulation.dat (schematic pa-bias-simulation.sch
 ideal VCVS buffers :40,59 and the measured inductor 11SQ39N.S2P pulled in with SPfile "polar" "linear" :39).
 CPU part: the oracle against the dataset, the product's netlister against a hand-derived netlist.
 GPU part (marked): the CUDA nodal kernel against the oracle and against the dataset, through the C-ABI."""
+import json
 import os
 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, REFERENCE
+from conftest import GOLDEN, REFERENCE, ROOT
 
 NB_R, NB_L, NB_C, NB_VCVS, NB_SBLOCK = 1, 2, 3, 4, 5
 
@@ -294,6 +295,36 @@ def test_compiled_kernel_analysis_host_only(Q, pa_bias, golden_s2p):
     full = nd.jit_analyze(f, [], tols, mode=Q.MODE_FULL_S)
     assert full["compiled"] and full["fms"] > a["fms"]
     nd.close()
+
+
+def test_compiled_kernel_disk_cache(Q, pa_bias, golden_s2p, tmp_path, monkeypatch):
+    """QO100NET_CACHE_DIR: the cubin of a compiled network (and the compiler's log) is kept on disk under the hash of its source;
+    a second process gets the kernel without running NVRTC and reports the same resource usage."""
+    import subprocess
+    import sys
+    nd, br, nn, ports = build_nodal(Q, golden_s2p)
+    f = pa_bias["frequency"][:200]
+    if not nd.jit_analyze(f)["compiled"]:
+        pytest.skip("no NVRTC on this machine")
+    nd.close()
+    code = ("import sys, json, numpy as np\n"
+            "sys.path.insert(0, %r); sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+            "import qo100net as Q\n"
+            "from test_nodal import build_nodal\n"
+            "from conftest import GOLDEN\n"
+            "import os\n"
+            "g = np.load(os.path.join(GOLDEN, 'touchstone.npz')); d = np.load(os.path.join(GOLDEN, 'pa_bias_dat.npz'))\n"
+            "nd, br, nn, ports = build_nodal(Q, g)\n"
+            "print(json.dumps(nd.jit_analyze(d['frequency'][:200], [(Q.SPEC_S21_MIN_DB, 1, 0, 2.3e9, 2.5e9, -1.0)])))\n"
+            % (os.path.join(ROOT, "qo-100-tools_b200", "python"), os.path.join(ROOT, "tests"), ROOT))
+    env = dict(os.environ, QO100NET_CACHE_DIR=str(tmp_path), QO100NET_NODAL_DEBUG="1")
+    runs = [subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env) for _ in range(2)]
+    assert all(r.returncode == 0 for r in runs), runs[0].stderr + runs[1].stderr
+    a, b = [json.loads(r.stdout.strip().splitlines()[-1]) for r in runs]
+    assert a["compiled"] and b == a and a["registers"] > 0
+    assert "cubin from QO100NET_CACHE_DIR" not in runs[0].stderr and "cubin from QO100NET_CACHE_DIR" in runs[1].stderr
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and files[0].endswith("_sm100a.cubin") and files[1].endswith("_sm100a.log") and os.path.getsize(tmp_path / files[0]) > 10000
 
 
 @pytest.mark.gpu

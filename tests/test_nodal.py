@@ -297,6 +297,37 @@ def test_compiled_kernel_analysis_host_only(Q, pa_bias, golden_s2p):
     nd.close()
 
 
+def test_compiled_kernel_generates_for_random_networks(Q):
+    """The generator on six random N-port networks of tools/fuzz_nodal.py (R / L / C with parasitics, ideal buffers, 1-4 ports), host
+    only: every network that takes the static plan compiles for sm_100a, FULL_S and yield flavour, with nothing on the stack."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fuzz_nodal", os.path.join(ROOT, "tools", "fuzz_nodal.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    done = 0
+    for i in range(6):
+        rng = np.random.default_rng([9, i])
+        br, nn, ports, tols, fc, nf, span = mod.random_network(rng)
+        br = [b for b in br if b[0] != mod.NB_SBLOCK]
+        f = Q.grid_log(fc / span, fc * span, nf)
+        nd = Q.Nodal(nn)
+        for kind, nodes, p in br:
+            nd.add_branch(kind, nodes, p)
+        for node, z in ports:
+            nd.add_port(node, z)
+        if not nd.analyze(f, tols)["static"]:
+            nd.close()
+            continue
+        a = nd.jit_analyze(f, [(Q.SPEC_S21_MIN_DB, 0, len(ports) - 1, float(f[0]), float(f[-1]), -3.0)], tols)
+        if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+            pytest.skip("no NVRTC on this machine")
+        b = nd.jit_analyze(f, [], tols, mode=Q.MODE_FULL_S)
+        assert a["compiled"] and b["compiled"] and a["stack_bytes"] == 0 and b["stack_bytes"] == 0 and b["fms"] >= a["fms"], (i, a, b)
+        done += 1
+        nd.close()
+    assert done >= 4
+
+
 def test_compiled_kernel_disk_cache(Q, pa_bias, golden_s2p, tmp_path, monkeypatch):
     """QO100NET_CACHE_DIR: the cubin of a compiled network (and the compiler's log) is kept on disk under the hash of its source;
     a second process gets the kernel without running NVRTC and reports the same resource usage."""

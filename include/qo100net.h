@@ -293,8 +293,17 @@ int qo_plan_launches(const qo_plan *plan);            /* kernels launched so far
  * <= 8 frequencies), "qo_mc_tf_kernel" (transfer-function kernel: reduce-only |S21| / |S11| / group-delay jobs on lumped
  * cascades, optionally behind one coupled-line block), "qo_mc_ladder_kernel" (straight-line ABCD-chain kernel of
  * the pcb/generic-filter ladder family), "qo_mc_lumped_kernel" (opcode interpreter) or "qo_mc_generic_kernel"
- * (microstrip).  QO100NET_KERNEL=ladder keeps jobs off the transfer-function kernel, =interp forces the interpreter. */
+ * (microstrip).  QO100NET_KERNEL=ladder keeps jobs off the transfer-function kernel, =interp forces the interpreter.
+ * "qo_mc_chain_jit_kernel": what would run on the interpreter -- a line or a measured block inside or behind the cascade
+ * (util/pa-bias-simulation/pa-bias-simulation.sch:39), FULL_S behind a coupled line (util/directional-couplers/
+ * dir_cpl_2.4g_20dB.trc:18-20) -- runs, from 2e10 evals per launch on (5e7 once this process or QO100NET_CACHE_DIR holds the
+ * kernel; QO100NET_CHAIN=jit always, =interp never), on the interpreter's own source compiled at run time with the element
+ * list, spec kinds and mode as constants (NVRTC, sm_100a): same arithmetic, no dispatch.  The name follows the last launch. */
 const char *qo_plan_kernel_name(const qo_plan *plan);
+/* The host-only part of that (NVRTC compiles without a GPU): fold this job's element list into the chain kernel and compile it.
+ * info[0] = compiled (0: libnvrtc missing or a compilation error, see qo_last_error), [1] = registers per thread, [2] = spill
+ * bytes (-1 for either when NVRTC does not echo ptxas), [3] = cubin size in bytes. */
+int qo_chain_jit_analyze(const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec, const qo_mc_cfg *cfg, int info[4]);
 /* what the plan decided about the transfer-function kernel.  info[0] = selected (0/1), [1] = numerator chains (2 | 4),
  * [2] = denominator form (0 none, 1 truncated |D|^2 polynomial, 2 complex D, 3 D and dD/ds for group-delay jobs), [3] = coefficient pairs kept per numerator
  * polynomial, [4] = denominator coefficients (form 1) / pairs (form 2) kept, [5] = structural degree;

@@ -28,6 +28,7 @@
 #include "qo_ustrip.cuh"
 #include "qo_ustrip_board.cuh"
 #include "qo_cpl_core.h"
+#include "qo_chain_jit.h"
 
 static int nccl_load(NcclApi *a)
 {
@@ -92,6 +93,11 @@ struct qo_plan {
     TfPlan fsp;
     int fs_niter;
     unsigned long long h2d_bytes;                         /* host->device bytes copied by qo_plan_create, per GPU */
+    int cj_mode;                                          /* run-time compiled chain kernel (qo_chain_jit.h): 0 by job size, 1 always, -1 never */
+    int cj_debug, cj_failed[2];
+    const void *cj[2];                                    /* its QcjEntry for the reduce-only / FULL_S flavour once this process holds it */
+    std::string cj_src[2];
+    unsigned long long cj_hash[2];
     const char *kernel_name;
     double flops_per_eval;
     int launches;
@@ -467,6 +473,14 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
     p->spot = spot_eligible(&p->hp, p->mode, p->precision, p->generic, nf, &p->spot_el0, &p->spot_nel);
     if (p->spot) p->tf = p->ladder = 0;
     { const char *e = getenv("QO100NET_USTRIP"); p->board = p->generic && p->mode == QO_MODE_REDUCE_ONLY && nf <= QO_B_MAXNF && !(e && !strcmp(e, "item")); }
+    {
+        /* the compiled chain kernel for what stays on the interpreter: QO100NET_CHAIN=jit always, =interp never; QO100NET_KERNEL=interp
+         * (A/B runs against the interpreter proper) also means never unless QO100NET_CHAIN=jit says otherwise */
+        const char *cj = getenv("QO100NET_CHAIN"), *fk = getenv("QO100NET_KERNEL");
+        p->cj_mode = cj && !strcmp(cj, "jit") ? 1 : cj && !strcmp(cj, "interp") ? -1 : fk && !strcmp(fk, "interp") ? -1 : 0;
+        p->cj_debug = getenv("QO100NET_CHAIN_DEBUG") != NULL;
+        p->cj[0] = p->cj[1] = NULL; p->cj_failed[0] = p->cj_failed[1] = 0; p->cj_hash[0] = p->cj_hash[1] = 0;
+    }
     p->kernel_name = p->board ? "qo_mc_board_kernel" : p->generic ? "qo_mc_generic_kernel" : p->spot ? "qo_mc_spot_kernel" : p->tf ? "qo_mc_tf_kernel" : p->ladder ? "qo_mc_ladder_kernel" : "qo_mc_lumped_kernel";
 
     /* per-frequency tables: w = 2 pi f and 1/w (hoisted out of the kernel), padded to a pair */
@@ -703,6 +717,28 @@ extern "C" int qo_plan_create(qo_ctx *ctx, const qo_net *net, const double *f, i
 extern "C" int qo_plan_num_counters(const qo_plan *p) { return p ? p->ncnt : QO_ERR_ARG; }
 extern "C" double qo_plan_flops_per_eval(const qo_plan *p) { return p ? p->flops_per_eval : 0.0; }
 extern "C" int qo_plan_launches(const qo_plan *p) { return p ? p->launches : QO_ERR_ARG; }
+/* Host-only (NVRTC compiles without a GPU): fold this job's element list into the chain kernel, compile it for sm_100a and report
+ * what came out.  info[0] = compiled (0 also when libnvrtc is missing: qo_last_error says why), [1] = registers per thread,
+ * [2] = spill bytes (-1 for either when NVRTC does not echo ptxas), [3] = cubin size in bytes. */
+extern "C" int qo_chain_jit_analyze(const qo_net *net, const double *f, int nf, const qo_spec *spec, int nspec, const qo_mc_cfg *cfg, int info[4])
+{
+    qo_clear_error();
+    if (!net || !f || nf <= 0 || !cfg || !info || (nspec > 0 && !spec)) return QO_ERR_ARG;
+    for (int i = 0; i < 4; i++) info[i] = 0;
+    DevProg hp;
+    int generic = 0;
+    double flops = 0.0;
+    std::vector<unsigned char> maskv;
+    int rc = build_prog(net, f, nf, spec, nspec, cfg, &hp, &generic, &flops, &maskv);
+    if (rc) return rc;
+    if (generic) { qo_set_error("microstrip networks run on their own kernels"); return QO_ERR_UNSUPPORTED; }
+    const std::string src = qcj_source(&hp, cfg->mode == QO_MODE_FULL_S);
+    const QcjEntry *e = qcj_get(src, qcj_hash(src), true, getenv("QO100NET_CHAIN_DEBUG") != NULL, false);
+    info[0] = e->ok; info[1] = e->regs; info[2] = e->spill_bytes; info[3] = e->cubin_bytes;
+    if (!e->ok) qo_set_error("%s", e->log.substr(0, 600).c_str());
+    return QO_OK;
+}
+
 extern "C" const char *qo_plan_kernel_name(const qo_plan *p) { return p ? p->kernel_name : ""; }
 extern "C" const char *qo_plan_tf_info(const qo_plan *p, int info[6], double *self_check_err)
 {
@@ -801,6 +837,32 @@ static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned lon
     unsigned long long blocks = (units + QO_WARPS - 1) / QO_WARPS;
     int grid = (int)(blocks < (unsigned long long)resident ? blocks : (unsigned long long)resident);
     if (grid < 1) grid = 1;
+    if (sizeof(T) == sizeof(double) && p->cj_mode >= 0 && !p->cj_failed[full_s ? 1 : 0]) {
+        /* large jobs: the element list compiled into the kernel (qo_chain_jit.h) */
+        const int fs = full_s ? 1 : 0;
+        const unsigned long long evals = n * (unsigned long long)p->nf;
+        const QcjEntry *je = (const QcjEntry *)p->cj[fs];
+        if (!je && (p->cj_mode == 1 || evals >= QO_CJ_MIN_CACHED)) {
+            if (p->cj_src[fs].empty()) { p->cj_src[fs] = qcj_source(&p->hp, fs); p->cj_hash[fs] = qcj_hash(p->cj_src[fs]); }
+            je = qcj_get(p->cj_src[fs], p->cj_hash[fs], p->cj_mode == 1 || evals >= QO_CJ_MIN_EVALS, p->cj_debug != 0);
+            if (je && !je->ok) {
+                p->cj_failed[fs] = 1;
+                if (p->cj_mode == 1) { qo_set_error("QO100NET_CHAIN=jit: %s", je->log.substr(0, 400).c_str()); return QO_ERR_UNSUPPORTED; }
+                je = NULL;
+            }
+            p->cj[fs] = je;
+        }
+        if (je) {
+            const DevProg *a_prog = d->prog;
+            const void *a_w2 = d->w2, *a_wi2 = d->wi2, *a_m2 = d->m2;
+            int a_nf = p->nf, a_np = p->npairs;
+            void *args[] = { &a_prog, &a_w2, &a_wi2, &a_m2, &a_nf, &a_np, &ppc, &nchunks, &off, &n, &cnt, &pl };
+            CU(cudaLaunchKernel((const void *)je->kern, dim3((unsigned)grid), dim3(QO_TPB), args, 0, dc->stream));
+            p->kernel_name = "qo_mc_chain_jit_kernel";
+            return QO_OK;
+        }
+    }
+    p->kernel_name = "qo_mc_lumped_kernel";
 #define QO_LAUNCH(FS, TR, GD)                                                                                       \
     qo_mc_lumped_kernel<T, FS, TR, GD><<<grid, QO_TPB, 0, dc->stream>>>(d->prog, (const V2 *)d->w2, (const V2 *)d->wi2, \
                                                                          d->m2, p->nf, p->npairs, ppc, nchunks, off, n, cnt, pl)
@@ -1173,7 +1235,7 @@ extern "C" int qo_mc_run(qo_ctx *ctx, const qo_net *net, const double *f, int nf
         if (cfg->n_tol > 0 && cfg->tol) mix(cfg->tol, (size_t)cfg->n_tol * sizeof(qo_tol));
         const long long scal[8] = { (long long)cfg->seed, cfg->dist, cfg->n_tol, cfg->mode, cfg->precision, cfg->hist_bins, cfg->hist_spec, nspec };
         mix(scal, sizeof scal); mix(&cfg->hist_lo, sizeof(double)); mix(&cfg->hist_hi, sizeof(double));
-        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT", "QO100NET_CPL_GENERAL", "QO100NET_CPL_NO_ROT", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS", "QO100NET_USTRIP" };
+        static const char *envs[] = { "QO100NET_KERNEL", "QO100NET_TF_TRUNC", "QO100NET_TF_TOL", "QO100NET_TF_NO_E", "QO100NET_TF_NO_FRONT", "QO100NET_CPL_GENERAL", "QO100NET_CPL_NO_ROT", "QO100NET_LAD_VARIANT", "QO100NET_CPL_SINCOS", "QO100NET_USTRIP", "QO100NET_CHAIN" };
         for (size_t i = 0; i < sizeof envs / sizeof envs[0]; i++) { const char *v = getenv(envs[i]); mix(v ? v : "\1", v ? strlen(v) + 1 : 1); }
     }
     qo_plan *p = NULL;

@@ -103,18 +103,14 @@ struct QoPlanes {
     const double *cplms;        /* physical coupled-line element: per-sample Z0e, Z0o, theta_e, theta_o from the pre-pass */
 };
 
+/* one element: M <- M * ABCD(op; cf) at the two points.  The interpreter calls it with the opcode read from shared memory;
+ * the run-time compiled flavour (qo_chain_jit.h) calls it once per element with literal arguments, so that the switch folds away */
 template <typename T, bool TRIG>
-__device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const int *__restrict__ s_coff,
-                                          const T *__restrict__ coef, int n_ops, const T (&w)[2], const T (&wi)[2],
-                                          Abcd2<T> &m, const QoPlanes &planes, int k0)
+__device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict__ cf, const T (&w)[2], const T (&wi)[2],
+                                              const T (&w2)[2], Abcd2<T> &m, const QoPlanes &planes, int k0)
 {
-    QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
-            m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
-    T w2[2];
-    QO_P2 w2[p] = w[p] * w[p];
-    for (int e = 0; e < n_ops; e++) {
-        const T *cf = coef + s_coff[e];
-        switch (s_op[e]) {
+    {
+        switch (op) {
         case OP_SER_LOSSY_L: {   /* Z = (R + jwL) / (1 - w^2 L Cp + j w R Cp) */
             T L = cf[0], LCp = cf[1], R = cf[2], RCp = cf[3];
             QO_P2 {
@@ -165,14 +161,14 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
         case OP_SHUNT_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
         default:
             if (TRIG) {
-                if (s_op[e] == OP_TLINE) {
+                if (op == OP_TLINE) {
                     T z0 = cf[0], y0 = cf[1], kt = cf[2];
                     QO_P2 {
                         T s, c;
                         qsincos(kt * w[p], &s, &c);
                         mul_full(m, p, c, T(0), T(0), z0 * s, T(0), s * y0, c, T(0));
                     }
-                } else if (s_op[e] == OP_CPL) {
+                } else if (op == OP_CPL) {
                     /* even/odd-mode lines in a Zt system */
                     T cE = cf[0], dE = cf[1], cO = cf[2], dO = cf[3], ke = cf[4], ko = cf[5], zt = cf[6], yt = cf[7];
                     QO_P2 {
@@ -201,7 +197,7 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
                         T Cr = yt * (ncr * idr - nci * idi), Ci2 = yt * (ncr * idi + nci * idr);
                         mul_full(m, p, Ar, Ai, Br, Bi, Cr, Ci2, Ar, Ai);
                     }
-                } else if (s_op[e] == OP_SBLOCK) {
+                } else if (op == OP_SBLOCK) {
                     const int blk = (int)cf[0];
                     QO_P2 {
                         const int k = min(k0 + p, planes.npts - 1);
@@ -214,6 +210,22 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
             break;
         }
     }
+}
+
+template <typename T, bool TRIG>
+__device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const int *__restrict__ s_coff,
+                                          const T *__restrict__ coef, int n_ops, const T (&w)[2], const T (&wi)[2],
+                                          Abcd2<T> &m, const QoPlanes &planes, int k0)
+{
+    QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
+            m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
+    T w2[2];
+    QO_P2 w2[p] = w[p] * w[p];
+#ifdef QO_JIT_CHAIN
+    QO_JIT_CHAIN                 /* qo_chain_step<T, TRIG>(<opcode>, coef + <offset>, w, wi, w2, m, planes, k0); per element */
+#else
+    for (int e = 0; e < n_ops; e++) qo_chain_step<T, TRIG>(s_op[e], coef + s_coff[e], w, wi, w2, m, planes, k0);
+#endif
 }
 
 /* ---- per-sample coefficient derivation (one lane per element) ------------- */
@@ -261,13 +273,25 @@ __device__ __forceinline__ void qo_derive(const DevProg *__restrict__ prog, int 
 /* 32 contiguous bytes (two complex doubles) in one 256-bit store; p must be 32-byte aligned */
 __device__ __forceinline__ void qo_st256(double2 *p, double2 a, double2 b)
 {
+#ifdef QO_NO_ST256          /* run-time compilation by an NVRTC older than CUDA 12.9 (qo_chain_jit.h) */
+    p[0] = a; p[1] = b;
+#else
     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
+#endif
 }
 
 /* ---- the kernel ----------------------------------------------------------- */
+/* Compiled ahead of time this is the opcode interpreter.  qo_chain_jit.h hands the same text to NVRTC with the job's element
+ * list (QO_JIT_CHAIN), spec kinds and template arguments defined in front of it: one kernel, C linkage, no dispatch. */
+#ifdef QO_JIT_CHAIN
+extern "C" __global__ void __launch_bounds__(QO_TPB, 2)
+qo_mc_chain_jit_kernel(
+#else
 template <typename T, bool FULL_S, bool TRIG, bool GD>
 __global__ void __launch_bounds__(QO_TPB, 2)
-qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::type *__restrict__ w2,
+qo_mc_lumped_kernel(
+#endif
+                    const DevProg *__restrict__ prog, const typename QoVec2<T>::type *__restrict__ w2,
                     const typename QoVec2<T>::type *__restrict__ wi2, const uchar2 *__restrict__ m2, int nf, int npairs,
                     int pairs_per_chunk, int nchunks, unsigned long long sample_offset, unsigned long long nsamples,
                     unsigned long long *__restrict__ counters, QoPlanes planes)
@@ -281,10 +305,18 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
     __shared__ double s_gdthr[QO_NSPEC_MAX];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef QO_JIT_CHAIN
+    constexpr int n_ops = QO_JIT_NOPS, nspec = QO_JIT_NSPEC, hist_spec = QO_JIT_HIST_SPEC, hist_kind = QO_JIT_HIST_KIND;
+    constexpr bool need_s11 = FULL_S || QO_JIT_NEED_S11;
+    const int n_var = prog->n_var;
+#define QO_SK(sp) qj_sk(sp)
+#else
     const int n_ops = prog->n_ops, n_var = prog->n_var, nspec = prog->nspec;
     const int hist_spec = prog->hist_bins > 0 ? prog->hist_spec : -1;
-    const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
     const bool need_s11 = FULL_S || prog->need_s11;
+#define QO_SK(sp) s_sk[sp]
+#endif
+    const int ncnt = 2 + nspec + (prog->hist_bins > 0 ? prog->hist_bins : 0);
     const bool planes_al32 = ((((size_t)planes.s11) | ((size_t)planes.s21) | ((size_t)planes.s12) | ((size_t)planes.s22)) & 31) == 0;
     for (int i = threadIdx.x; i < n_ops; i += QO_TPB) { s_op[i] = prog->opcode[i]; s_coff[i] = prog->coff[i]; }
     for (int i = threadIdx.x; i < ncnt; i += QO_TPB) s_cnt[i] = 0;
@@ -296,7 +328,9 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
     __syncthreads();
 
     const T rs = T(prog->rs), rl = T(prog->rl), rsrl = T(prog->rsrl), k21 = T(prog->k21);
+#ifndef QO_JIT_CHAIN
     const int hist_kind = hist_spec >= 0 ? prog->spec_kind[hist_spec] : 0;
+#endif
     const unsigned long long seed = prog->seed;
     const int dist = prog->dist;
     T *coefw = s_coef[warp];
@@ -380,7 +414,7 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
 #pragma unroll
                     for (int sp = 0; sp < QO_NSPEC_MAX; sp++) {
                         if (sp < nspec) {
-                            const int sk = s_sk[sp];
+                            const int sk = QO_SK(sp);
                             const T thr = s_thr[sp];
                             bool bad = sk == SK_DEN2_MAX ? (den2 > thr) : sk == SK_DEN2_MIN ? (den2 < thr)
                                      : sk == SK_S11_MAX ? (num2 > thr * den2) : (gdv > s_gdthr[sp]);
@@ -471,3 +505,4 @@ qo_mc_lumped_kernel(const DevProg *__restrict__ prog, const typename QoVec2<T>::
             if (s_cnt[i]) atomicAdd(&counters[i], (unsigned long long)s_cnt[i]);
     }
 }
+#undef QO_SK

@@ -92,7 +92,7 @@ EXPORTS = [
     "qo_grid_lin", "qo_grid_log", "qo_ctx_create", "qo_ctx_create_on_device", "qo_ctx_set_stream",
     "qo_ctx_num_devices", "qo_ctx_destroy", "qo_sweep", "qo_mc_run", "qo_plan_create", "qo_plan_num_counters",
     "qo_plan_reset", "qo_plan_launch", "qo_plan_read", "qo_plan_flops_per_eval", "qo_plan_launches",
-    "qo_plan_kernel_name", "qo_plan_tf_info", "qo_plan_h2d_bytes", "qo_plan_analyze",
+    "qo_plan_kernel_name", "qo_plan_tf_info", "qo_plan_h2d_bytes", "qo_plan_analyze", "qo_chain_jit_analyze",
     "qo_s2p_load", "qo_s2p_from_arrays", "qo_s2p_num_points", "qo_s2p_z0", "qo_s2p_get", "qo_s2p_interp",
     "qo_s2p_fit_inductor", "qo_s2p_free", "qo_net_from_sblock",
     "qo_nodal_create", "qo_nodal_add_branch", "qo_nodal_add_port", "qo_nodal_add_sblock", "qo_nodal_load_qucs_sch",
@@ -151,6 +151,7 @@ def lib():
         "qo_plan_kernel_name": (C.c_char_p, [vp]),
         "qo_plan_tf_info": (C.c_char_p, [vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
         "qo_plan_h2d_bytes": (C.c_uint64, [vp]),
+        "qo_chain_jit_analyze": (C.c_int, [vp, C.POINTER(C.c_double), C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int)]),
         "qo_plan_analyze": (C.c_char_p, [vp, C.POINTER(C.c_double), C.c_int, vp, C.c_int, vp, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "qo_s2p_load": (C.c_int, [C.c_char_p, C.POINTER(vp)]),
         "qo_s2p_from_arrays": (C.c_int, [dp, C.c_int, vp, vp, vp, vp, C.c_double, C.POINTER(vp)]),
@@ -620,6 +621,17 @@ def plan_analyze(net, f, specs, tols=(), dist=DIST_UNIFORM, mode=MODE_REDUCE_ONL
     reason = lib().qo_plan_analyze(net._h, _dp(f), len(f), _specs(specs), len(specs), C.byref(cfg), info, C.byref(err), C.byref(sec)).decode()
     return dict(selected=bool(info[0]), numerator_chains=info[1], den_form=("none", "E", "D", "DD")[info[2]] if 0 <= info[2] <= 3 else "?",
                 kn=info[3], kd=info[4], degree=info[5], self_check_err=err.value, reason=reason, seconds=sec.value)
+
+
+def chain_jit_analyze(net, f, specs=(), tols=(), mode=MODE_REDUCE_ONLY, hist_bins=0, hist_spec=0, hist_lo=0.0, hist_hi=1.0):
+    """Host-only (qo_chain_jit_analyze): fold the job's element list into the chain kernel and compile it with NVRTC
+    -> dict(compiled, registers, spill_bytes, cubin_bytes, error)."""
+    f = np.ascontiguousarray(f, dtype=np.float64)
+    cfg = _cfg(0, 0, list(tols), 0, DIST_UNIFORM, mode, 64, hist_bins, hist_spec, hist_lo, hist_hi)
+    info = (C.c_int * 4)()
+    _check(lib().qo_chain_jit_analyze(net._h, _dp(f), len(f), _specs(specs), len(specs), C.byref(cfg), info))
+    return dict(compiled=bool(info[0]), registers=info[1], spill_bytes=info[2], cubin_bytes=info[3],
+                error=None if info[0] else lib().qo_last_error().decode())
 
 
 class Plan:

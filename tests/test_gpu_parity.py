@@ -1247,3 +1247,104 @@ def test_full_s_transfer_function_flavour(Q, R, W, ctx, monkeypatch):
     torch.cuda.synchronize()
     assert plan.kernel_name == "qo_mc_lumped_kernel"
     plan.close()
+
+
+def test_compiled_chain_kernel_equals_interpreter_and_oracle(Q, R, W, ctx, golden_s2p, monkeypatch):
+    """Cascades the polynomial kernels cannot take -- a line INSIDE the ladder and a measured two-port BEHIND it
+    (pa-bias-simulation.sch:39 has the SPfile block in mid-network), FULL_S behind the coupled line of dir_cpl_2.4g_20dB.trc:18-20,
+    group delay next to an |S11| spec -- on the run-time compiled chain kernel (QO100NET_CHAIN=jit; by default from 2e10 evals
+    per launch on): the interpreter's source with the element list folded in.  Integer counters and histograms equal the
+    interpreter's and the oracle's, FULL_S planes equal the interpreter's to rounding and the oracle's within 1e-9."""
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    monkeypatch.delenv("QO100NET_CHAIN", raising=False)
+    w5 = W.cfg5(1000)
+    a = Q.chain_jit_analyze(w5.net, w5.f, w5.specs, w5.tols, **w5.hist)
+    if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+        pytest.skip("libnvrtc is not loadable on this box: the compiled chain kernel is not available (%s)" % a["error"])
+    assert a["compiled"], a
+
+    def both(net, f, specs, seed, n, tols, hist, off=0, force_interp_kernel=False):
+        out = {}
+        for mode in ("jit", "interp"):
+            monkeypatch.setenv("QO100NET_CHAIN", mode)
+            if force_interp_kernel:
+                monkeypatch.setenv("QO100NET_KERNEL", "interp")
+            plan = Q.Plan(ctx, net, f, specs, seed=seed, tols=tols, **hist)
+            assert plan.kernel_name == "qo_mc_lumped_kernel", plan.kernel_name        # what the plan would run without the compilation
+            plan.launch(off, n)
+            out[mode] = plan.read()
+            assert plan.kernel_name == ("qo_mc_chain_jit_kernel" if mode == "jit" else "qo_mc_lumped_kernel")
+            plan.close()
+        monkeypatch.delenv("QO100NET_CHAIN", raising=False)
+        monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+        _assert_counts_equal(out["interp"], out["jit"])
+        return out["jit"]
+
+    # (a) ladder half - 75 Ohm line (perturbed) - ladder half - measured inductor - series R; |S21| x 2 + |S11| specs, histogram
+    fc = 10e6
+    fd, sd, z0 = golden_s2p["11SQ39N_f"], golden_s2p["11SQ39N_s"], float(golden_s2p["11SQ39N_z0"])
+    blk = Q.SBlock.from_arrays(fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    R.sblock_clear()
+    R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    lad, f, ltol = _ladder_workload(Q, W, 7, True, False, nf=700)
+    el = lad.elements
+    first = Q.Net.from_elements([(k, list(p)) for k, p in el[:3]], 50.0, 50.0)
+    second = Q.Net.from_elements([(k, list(p)) for k, p in el[3:]], 50.0, 50.0)
+    line = Q.Net.from_elements([(Q.TLINE, [75.0, 20.0, fc])], 50.0, 50.0)
+    tail = Q.Net.from_elements([(Q.SER_R, [2.2])], 50.0, 50.0)
+    net = first.concat(line).concat(second).concat(blk.as_net(True, 50.0, 50.0)).concat(tail)
+    tols = [(e if e < 3 else e + 1, p_, v, m, t) for (e, p_, v, m, t) in ltol]
+    nv = 1 + max(t[2] for t in tols)
+    tols += [(3, 0, nv, Q.TOL_REL, 0.05), (3, 1, nv + 1, Q.TOL_REL, 0.03), (len(el) + 2, 0, nv + 2, Q.TOL_REL, 0.1)]
+    nom = ctx.sweep(net, f)
+    db, db11 = 20 * np.log10(np.abs(nom[1])), 20 * np.log10(np.abs(nom[0]))
+    pb, sb = f <= 0.9 * fc, f >= 2.0 * fc
+    specs = [(Q.SPEC_S21_MIN_DB, 0.0, 0.9 * fc, float(db[pb].min()) - 0.3), (Q.SPEC_S21_MAX_DB, 2.0 * fc, 1e99, float(db[sb].max()) + 1.0),
+             (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, float(db11[f <= 0.5 * fc].max()) + 1.5)]
+    hist = dict(hist_bins=32, hist_spec=0, hist_lo=float(db[pb].min()) - 2.0, hist_hi=float(db[pb].min()) + 0.5)
+    n = 3000
+    got = both(net, f, specs, 21, n, tols, hist, off=2 ** 34 + 5)
+    ref = R.mc_run(to_ref(R, net), 50, 50, f, specs, R.mc_cfg(21, n, tols, sample_offset=2 ** 34 + 5, **hist), nthreads=8)
+    _assert_counts_equal(ref, got)
+    assert 0 < got["n_pass"] < n and int(got["hist"].sum()) == n
+    R.sblock_clear()
+
+    # (b) group delay next to an |S11| spec (the job test_group_delay_spec_in_kernel leaves to the interpreter)
+    w2 = W.cfg2()
+    f2 = w2.f[::4]
+    gd = ctx.sweep(w2.net, f2, gd=True)[4]
+    band = (f2 >= 0.3 * fc) & (f2 <= 0.9 * fc)
+    lim = float(gd[band].max()) * 1.01
+    specs2 = [(Q.SPEC_S21_MIN_DB, 0.0, 0.95 * fc, -2.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, lim), (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, -9.0)]
+    hist2 = dict(hist_bins=40, hist_spec=1, hist_lo=0.8 * lim, hist_hi=1.3 * lim)
+    got2 = both(w2.net, f2, specs2, 3, 500, w2.tols, hist2)
+    ref2 = R.mc_run(to_ref(R, w2.net), 50, 50, f2, specs2, R.mc_cfg(3, 500, w2.tols, **hist2), nthreads=8)
+    _assert_counts_equal(ref2, got2)
+    assert 0 < got2["fail_per_spec"][1] < 500
+
+    # (c) the headline ladder forced onto the chain (QO100NET_KERNEL=interp keeps it off the polynomial kernels): same integers as the
+    # default kernel at 20 000 samples
+    got3 = both(w2.net, w2.f, w2.specs, w2.seed, 20000, w2.tols, w2.hist, force_interp_kernel=True)
+    dflt = ctx.mc_run(w2.net, w2.f, w2.specs, w2.seed, 20000, w2.tols, **w2.hist)
+    _assert_counts_equal(dflt, got3)
+
+    # (d) FULL_S behind the coupler: planes of the compiled kernel vs the interpreter's and the oracle's
+    import torch
+    nf, ns = 1001, 300
+    f5 = w5.f[:nf]
+    planes = {}
+    for mode in ("jit", "interp"):
+        monkeypatch.setenv("QO100NET_CHAIN", mode)
+        plan = Q.Plan(ctx, w5.net, f5, [], seed=w5.seed, tols=w5.tols, mode=Q.MODE_FULL_S)
+        buf = torch.zeros((4, ns, nf, 2), dtype=torch.float64, device="cuda")
+        plan.launch(7, ns, None, buf.data_ptr())
+        torch.cuda.synchronize()
+        assert plan.kernel_name == ("qo_mc_chain_jit_kernel" if mode == "jit" else "qo_mc_lumped_kernel"), plan.kernel_name
+        plan.close()
+        planes[mode] = torch.view_as_complex(buf).cpu().numpy()
+    monkeypatch.delenv("QO100NET_CHAIN", raising=False)
+    assert np.max(np.abs(planes["jit"][1])) > 0.5
+    for i in range(4):
+        assert np.max(np.abs(planes["jit"][i] - planes["interp"][i])) <= 1e-13
+    os_ = R.mc_run(to_ref(R, w5.net), 50, 50, f5, [], R.mc_cfg(w5.seed, 12, w5.tols, sample_offset=7), full_s=True)["s"]
+    _s_close([planes["jit"][i][:12] for i in range(4)], os_)

@@ -537,3 +537,41 @@ def test_integration_md_c_samples_compile_and_link(Q, tmp_path):
         assert r.returncode == 0 and r.stdout.split()[1] == "1000000"
     else:
         assert r.returncode == 3 and "CUDA" in r.stderr          # no device, no fallback
+
+
+def test_chain_kernel_generator_compiles_without_gpu(Q, W, tmp_path, monkeypatch):
+    """qo_chain_jit_analyze (host only: NVRTC compiles without a GPU): cascades the polynomial kernels cannot take -- a line inside
+    the ladder, a coupler in front written out in full (dir_cpl_2.4g_20dB.trc:18-20), every lumped opcode of the rf-tools filters,
+    group delay next to |S11| -- folded into the chain kernel's source and compiled for sm_100a.  The generated text carries one
+    literal qo_chain_step per element and no opcode table; the cubin lands in QO100NET_CACHE_DIR and is found again."""
+    w5 = W.cfg5(1000)
+    a = Q.chain_jit_analyze(w5.net, w5.f, w5.specs, w5.tols, **w5.hist)
+    if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+        pytest.skip("libnvrtc is not loadable here: %s" % a["error"])
+    assert a["compiled"] and a["cubin_bytes"] > 10000, a
+    assert a["registers"] in (-1,) or 32 <= a["registers"] <= 128          # __launch_bounds__(256, 2); -1: NVRTC did not echo ptxas
+    dump = tmp_path / "chain.cu"
+    monkeypatch.setenv("QO100NET_CHAIN_JIT_DUMP", str(dump))
+    monkeypatch.setenv("QO100NET_CACHE_DIR", str(tmp_path / "cache"))
+    fs = Q.chain_jit_analyze(w5.net, w5.f[:500], [], w5.tols, mode=Q.MODE_FULL_S)
+    assert fs["compiled"], fs["error"]
+    src = dump.read_text()
+    n_el = len(w5.net)
+    assert src.count("qo_chain_step<T, TRIG>(") == n_el + 2                 # one call per element + the definition's two mentions
+    assert "static constexpr bool FULL_S = true, TRIG = true, GD = false;" in src and "#define QO_JIT_NSPEC 0" in src
+    assert len(list((tmp_path / "cache").glob("chain_*_sm100a.cubin"))) == 1
+    # line inside a ladder + every rf-tools opcode + group delay and |S11| specs
+    fc = 10e6
+    lad = W.cheby11(fc).elements
+    items = [(k, list(p)) for k, p in lad[:5]] + [(Q.TLINE, [75.0, 20.0, fc])] + [(k, list(p)) for k, p in lad[5:]]
+    items += [(k, list(p)) for k, p in W.if_bpf_net().elements] + [(Q.SER_R, [1.0]), (Q.SHUNT_LC_SER, [1e-6, 1e-10])]
+    net = Q.Net.from_elements(items, 50.0, 75.0)
+    f = Q.grid_log(fc / 3, fc * 5, 300)
+    specs = [(Q.SPEC_S21_MIN_DB, 0.0, fc, -3.0), (Q.SPEC_GD_MAX, 0.3 * fc, 0.9 * fc, 1e-6), (Q.SPEC_S11_MAX_DB, 0.0, 0.5 * fc, -9.0)]
+    g = Q.chain_jit_analyze(net, f, specs, [(5, 0, 0, Q.TOL_REL, 0.05)], hist_bins=16, hist_spec=1, hist_lo=0.0, hist_hi=1e-6)
+    assert g["compiled"], g
+    src = dump.read_text()
+    assert "GD = true" in src and "#define QO_JIT_HIST_KIND 4" in src and "#define QO_JIT_NEED_S11 1" in src
+    assert src.count("qo_chain_step<T, TRIG>(") == len(items) + 2
+    with pytest.raises(Q.QoError):                                           # microstrip networks have their own kernels
+        Q.chain_jit_analyze(W.pa_lpf_net(), f)

@@ -68,6 +68,28 @@ def kernel_source_hash():
     return h.hexdigest()[:16]
 
 
+def kernel_sass_hash(kernel):
+    """hash of `kernel`'s machine code in the library being benchmarked (qo-100-tools_b200/lib/sass_hashes.json, written by
+    build() from the object files the library was linked from), or None when the file is missing or describes another build of the library"""
+    try:
+        lib = os.path.join(ROOT, "qo-100-tools_b200", "lib")
+        d = json.load(open(os.path.join(lib, "sass_hashes.json")))
+        if d.get("lib_sha256") != hashlib.sha256(open(os.path.join(lib, "libqo100net.so"), "rb").read()).hexdigest():
+            return None
+        return d["kernels"][kernel]["sha"]
+    except Exception:
+        return None
+
+
+def profile_match(ex, kernel):
+    """Were the ncu counts taken on the code being benchmarked?  "source": same kernel sources; "sass": sources changed since, but
+    this kernel's machine code is byte-identical to the profiled build's; False: neither."""
+    if ex.get("src_hash") == kernel_source_hash():
+        return "source"
+    sh = kernel_sass_hash(kernel)
+    return "sass" if sh is not None and sh == (ex.get("sass") or {}).get(kernel) else False
+
+
 def executed_profile(plan_kernel, wl_name):
     """{"dfma", "dmul", "dadd" per eval, "dram_bytes_per_launch", "source", "src_hash"} of the kernel on this workload, or None."""
     try:
@@ -75,6 +97,7 @@ def executed_profile(plan_kernel, wl_name):
         e = dict(d[plan_kernel]["cfg5" if wl_name.startswith("cfg5") else "cfg2"])
         e.setdefault("src_hash", d.get("_src_hash"))
         e.setdefault("git", d.get("_git"))
+        e.setdefault("sass", d.get("_sass"))
         return e
     except Exception:
         return None
@@ -92,7 +115,7 @@ def executed_view(kernel, wl_name, evals_per_s_per_gpu, peak_tflops):
             "tflops": fl * evals_per_s_per_gpu * 1e-12, "frac_of_peak": fl * evals_per_s_per_gpu * 1e-12 / peak_tflops,
             "pipe_util": ipe * evals_per_s_per_gpu / (peak_tflops * 0.5e12),
             "ncu_fp64_pipe_active_pct": ex.get("fp64_pipe_active_pct"), "source": ex.get("source"), "profile_git": ex.get("git"),
-            "profile_matches_source": ex.get("src_hash") == kernel_source_hash()}
+            "profile_matches_source": bool(profile_match(ex, kernel)), "profile_match": profile_match(ex, kernel)}
 
 
 def time_plan(plan, stream, counters, nspg, steps, warmup, torch):
@@ -305,6 +328,33 @@ def nodal_leg(Q, ctx):
         if saved is not None:
             os.environ["QO100NET_NODAL"] = saved
         nd.close()
+    return out
+
+
+def chain_jit_leg(Q, torch, ctx, stream):
+    """What the polynomial kernels cannot take (a line inside the ladder with a measured two-port behind it,
+    util/pa-bias-simulation/pa-bias-simulation.sch:39; configs 2 and 5 kept off them; config 5 written out in full): the run-time
+    compiled chain kernel (qo_chain_jit.h) next to the opcode interpreter, counters compared (tools/chain_jit_speed.py)."""
+    from tools.chain_jit_speed import measure
+    saved = {k: os.environ.pop(k, None) for k in ("QO100NET_CHAIN", "QO100NET_KERNEL")}
+    try:
+        rows = measure(Q, torch, ctx, stream, samples=100000, fs_samples=8192)
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+    out = {"unit": "evals/s", "jobs": []}
+    for name, r in rows.items():
+        j = {"job": name, "kernel": r["jit"]["kernel"], "value": r["jit"]["evals_per_s"], "interpreter": r["interp"]["evals_per_s"],
+             "speedup": r["speedup"]}
+        if "counters_equal" in r:
+            j["counters_equal_interpreter"] = r["counters_equal"]
+            j["compile_seconds_first_launch"] = r["jit"]["first_launch_s"]
+        else:
+            j["gb_per_s"] = r["jit"]["gb_per_s"]
+            j["max_abs_diff_vs_interpreter"] = r["max_abs_diff"]
+        out["jobs"].append(j)
     return out
 
 
@@ -590,6 +640,10 @@ def main():
             line["nodal"] = nodal_leg(Q, ctx)
         except Exception as ex5:
             line["nodal"] = {"error": str(ex5)}
+        try:
+            line["chain_jit"] = chain_jit_leg(Q, torch, ctx, stream)
+        except Exception as ex6:
+            line["chain_jit"] = {"error": str(ex6)}
     emit(line)
     if dist is not None:
         dist.barrier()

@@ -53,32 +53,38 @@ template <typename T> struct Abcd2 {
 
 #define QO_P2 _Pragma("unroll") for (int p = 0; p < 2; p++)
 
-template <typename T> __device__ __forceinline__ void ser_cplx(Abcd2<T> &m, int p, T zr, T zi)
+/* ROW (run-time compiled flavour, jobs that observe |S21| only): the chain carries the row vector [1 Rs] M in (a, b) instead
+ * of the 2x2 product -- den = a Rl + b -- and the (c, d) row is never touched: half the multiply-adds per element */
+template <typename T, bool ROW = false> __device__ __forceinline__ void ser_cplx(Abcd2<T> &m, int p, T zr, T zi)
 {
     m.br[p] = qfma(m.ar[p], zr, m.br[p]); m.br[p] = qfma(-m.ai[p], zi, m.br[p]);
     m.bi[p] = qfma(m.ar[p], zi, m.bi[p]); m.bi[p] = qfma(m.ai[p], zr, m.bi[p]);
+    if (ROW) return;
     m.dr[p] = qfma(m.cr[p], zr, m.dr[p]); m.dr[p] = qfma(-m.ci[p], zi, m.dr[p]);
     m.di[p] = qfma(m.cr[p], zi, m.di[p]); m.di[p] = qfma(m.ci[p], zr, m.di[p]);
 }
-template <typename T> __device__ __forceinline__ void shunt_cplx(Abcd2<T> &m, int p, T yr, T yi)
+template <typename T, bool ROW = false> __device__ __forceinline__ void shunt_cplx(Abcd2<T> &m, int p, T yr, T yi)
 {
     m.ar[p] = qfma(m.br[p], yr, m.ar[p]); m.ar[p] = qfma(-m.bi[p], yi, m.ar[p]);
     m.ai[p] = qfma(m.br[p], yi, m.ai[p]); m.ai[p] = qfma(m.bi[p], yr, m.ai[p]);
+    if (ROW) return;
     m.cr[p] = qfma(m.dr[p], yr, m.cr[p]); m.cr[p] = qfma(-m.di[p], yi, m.cr[p]);
     m.ci[p] = qfma(m.dr[p], yi, m.ci[p]); m.ci[p] = qfma(m.di[p], yr, m.ci[p]);
 }
-template <typename T> __device__ __forceinline__ void ser_imag(Abcd2<T> &m, int p, T x)
+template <typename T, bool ROW = false> __device__ __forceinline__ void ser_imag(Abcd2<T> &m, int p, T x)
 {
     m.br[p] = qfma(-m.ai[p], x, m.br[p]); m.bi[p] = qfma(m.ar[p], x, m.bi[p]);
+    if (ROW) return;
     m.dr[p] = qfma(-m.ci[p], x, m.dr[p]); m.di[p] = qfma(m.cr[p], x, m.di[p]);
 }
-template <typename T> __device__ __forceinline__ void shunt_imag(Abcd2<T> &m, int p, T y)
+template <typename T, bool ROW = false> __device__ __forceinline__ void shunt_imag(Abcd2<T> &m, int p, T y)
 {
     m.ar[p] = qfma(-m.bi[p], y, m.ar[p]); m.ai[p] = qfma(m.br[p], y, m.ai[p]);
+    if (ROW) return;
     m.cr[p] = qfma(-m.di[p], y, m.cr[p]); m.ci[p] = qfma(m.dr[p], y, m.ci[p]);
 }
 /* M <- M * [a b; c d] with a general complex 2x2 (TLINE / coupled line blocks) */
-template <typename T>
+template <typename T, bool ROW = false>
 __device__ __forceinline__ void mul_full(Abcd2<T> &m, int p, T ar, T ai, T br, T bi, T cr, T ci, T dr, T di)
 {
     T Ar = m.ar[p], Ai = m.ai[p], Br = m.br[p], Bi = m.bi[p];
@@ -86,6 +92,7 @@ __device__ __forceinline__ void mul_full(Abcd2<T> &m, int p, T ar, T ai, T br, T
     m.ai[p] = qfma(Ar, ai, qfma(Ai, ar, qfma(Br, ci, Bi * cr)));
     m.br[p] = qfma(Ar, br, qfma(-Ai, bi, qfma(Br, dr, -Bi * di)));
     m.bi[p] = qfma(Ar, bi, qfma(Ai, br, qfma(Br, di, Bi * dr)));
+    if (ROW) return;
     T Cr = m.cr[p], Ci = m.ci[p], Dr = m.dr[p], Di = m.di[p];
     m.cr[p] = qfma(Cr, ar, qfma(-Ci, ai, qfma(Dr, cr, -Di * ci)));
     m.ci[p] = qfma(Cr, ai, qfma(Ci, ar, qfma(Dr, ci, Di * cr)));
@@ -103,9 +110,14 @@ struct QoPlanes {
     const double *cplms;        /* physical coupled-line element: per-sample Z0e, Z0o, theta_e, theta_o from the pre-pass */
 };
 
+#ifdef QO_JIT_CHAIN
+#define QO_ROW QO_JIT_ROW
+#else
+#define QO_ROW false
+#endif
 /* one element: M <- M * ABCD(op; cf) at the two points.  The interpreter calls it with the opcode read from shared memory;
  * the run-time compiled flavour (qo_chain_jit.h) calls it once per element with literal arguments, so that the switch folds away */
-template <typename T, bool TRIG>
+template <typename T, bool TRIG, bool ROW = false>
 __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict__ cf, const T (&w)[2], const T (&wi)[2],
                                               const T (&w2)[2], Abcd2<T> &m, const QoPlanes &planes, int k0)
 {
@@ -117,7 +129,7 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
                 T dre = qfma(-w2[p], LCp, T(1)), dim = w[p] * RCp, xl = w[p] * L;
                 T r = qrcp(qfma(dre, dre, dim * dim));
                 T qr = dre * r, qi = -dim * r;
-                ser_cplx(m, p, qfma(R, qr, -xl * qi), qfma(R, qi, xl * qr));
+                ser_cplx<T, ROW>(m, p, qfma(R, qr, -xl * qi), qfma(R, qi, xl * qr));
             }
             break;
         }
@@ -126,13 +138,13 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
             QO_P2 {
                 T x = qfma(w[p], Ls, -wi[p] * Ci);
                 T r = qrcp(qfma(x, x, R2));
-                shunt_cplx(m, p, R * r, -x * r);
+                shunt_cplx<T, ROW>(m, p, R * r, -x * r);
             }
             break;
         }
         case OP_SER_LOSSY_C: {
             T Ci = cf[0], Ls = cf[1], R = cf[2];
-            QO_P2 ser_cplx(m, p, R, qfma(w[p], Ls, -wi[p] * Ci));
+            QO_P2 ser_cplx<T, ROW>(m, p, R, qfma(w[p], Ls, -wi[p] * Ci));
             break;
         }
         case OP_SHUNT_LOSSY_L: {  /* Y = (1 - w^2 L Cp + j w R Cp) / (R + jwL) */
@@ -141,24 +153,24 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
                 T dre = qfma(-w2[p], LCp, T(1)), dim = w[p] * RCp, xl = w[p] * L;
                 T r = qrcp(qfma(xl, xl, R * R));
                 T qr = R * r, qi = -xl * r;
-                shunt_cplx(m, p, qfma(dre, qr, -dim * qi), qfma(dre, qi, dim * qr));
+                shunt_cplx<T, ROW>(m, p, qfma(dre, qr, -dim * qi), qfma(dre, qi, dim * qr));
             }
             break;
         }
         case OP_SER_R: { T r = cf[0]; QO_P2 {
             m.br[p] = qfma(m.ar[p], r, m.br[p]); m.bi[p] = qfma(m.ai[p], r, m.bi[p]);
-            m.dr[p] = qfma(m.cr[p], r, m.dr[p]); m.di[p] = qfma(m.ci[p], r, m.di[p]); } break; }
+            if (!ROW) { m.dr[p] = qfma(m.cr[p], r, m.dr[p]); m.di[p] = qfma(m.ci[p], r, m.di[p]); } } break; }
         case OP_SHUNT_G: { T g = cf[0]; QO_P2 {
             m.ar[p] = qfma(m.br[p], g, m.ar[p]); m.ai[p] = qfma(m.bi[p], g, m.ai[p]);
-            m.cr[p] = qfma(m.dr[p], g, m.cr[p]); m.ci[p] = qfma(m.di[p], g, m.ci[p]); } break; }
-        case OP_SER_L: { T c0 = cf[0]; QO_P2 ser_imag(m, p, w[p] * c0); break; }
-        case OP_SER_C: { T c0 = cf[0]; QO_P2 ser_imag(m, p, -wi[p] * c0); break; }
-        case OP_SER_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
-        case OP_SHUNT_C: { T c0 = cf[0]; QO_P2 shunt_imag(m, p, w[p] * c0); break; }
-        case OP_SHUNT_L: { T c0 = cf[0]; QO_P2 shunt_imag(m, p, -wi[p] * c0); break; }
-        case OP_SHUNT_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
-        case OP_SER_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
-        case OP_SHUNT_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
+            if (!ROW) { m.cr[p] = qfma(m.dr[p], g, m.cr[p]); m.ci[p] = qfma(m.di[p], g, m.ci[p]); } } break; }
+        case OP_SER_L: { T c0 = cf[0]; QO_P2 ser_imag<T, ROW>(m, p, w[p] * c0); break; }
+        case OP_SER_C: { T c0 = cf[0]; QO_P2 ser_imag<T, ROW>(m, p, -wi[p] * c0); break; }
+        case OP_SER_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag<T, ROW>(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
+        case OP_SHUNT_C: { T c0 = cf[0]; QO_P2 shunt_imag<T, ROW>(m, p, w[p] * c0); break; }
+        case OP_SHUNT_L: { T c0 = cf[0]; QO_P2 shunt_imag<T, ROW>(m, p, -wi[p] * c0); break; }
+        case OP_SHUNT_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag<T, ROW>(m, p, qfma(w[p], c0, -wi[p] * c1)); break; }
+        case OP_SER_LCP: { T c0 = cf[0], c1 = cf[1]; QO_P2 ser_imag<T, ROW>(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
+        case OP_SHUNT_LCS: { T c0 = cf[0], c1 = cf[1]; QO_P2 shunt_imag<T, ROW>(m, p, -qrcp(qfma(w[p], c0, -wi[p] * c1))); break; }
         default:
             if (TRIG) {
                 if (op == OP_TLINE) {
@@ -166,7 +178,7 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
                     QO_P2 {
                         T s, c;
                         qsincos(kt * w[p], &s, &c);
-                        mul_full(m, p, c, T(0), T(0), z0 * s, T(0), s * y0, c, T(0));
+                        mul_full<T, ROW>(m, p, c, T(0), T(0), z0 * s, T(0), s * y0, c, T(0));
                     }
                 } else if (op == OP_CPL) {
                     /* even/odd-mode lines in a Zt system */
@@ -195,7 +207,7 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
                         T Ar = nar * idr - nai * idi, Ai = nar * idi + nai * idr;
                         T Br = zt * (nbr * idr - nbi * idi), Bi = zt * (nbr * idi + nbi * idr);
                         T Cr = yt * (ncr * idr - nci * idi), Ci2 = yt * (ncr * idi + nci * idr);
-                        mul_full(m, p, Ar, Ai, Br, Bi, Cr, Ci2, Ar, Ai);
+                        mul_full<T, ROW>(m, p, Ar, Ai, Br, Bi, Cr, Ci2, Ar, Ai);
                     }
                 } else if (op == OP_SBLOCK) {
                     const int blk = (int)cf[0];
@@ -203,7 +215,7 @@ __device__ __forceinline__ void qo_chain_step(const int op, const T *__restrict_
                         const int k = min(k0 + p, planes.npts - 1);
                         const double2 *t = planes.sblk + ((size_t)blk * (size_t)planes.npts + (size_t)k) * 4;
                         const double2 a = t[0], b = t[1], c = t[2], d = t[3];
-                        mul_full(m, p, T(a.x), T(a.y), T(b.x), T(b.y), T(c.x), T(c.y), T(d.x), T(d.y));
+                        mul_full<T, ROW>(m, p, T(a.x), T(a.y), T(b.x), T(b.y), T(c.x), T(c.y), T(d.x), T(d.y));
                     }
                 }
             }
@@ -217,12 +229,14 @@ __device__ __forceinline__ void qo_chain2(const int *__restrict__ s_op, const in
                                           const T *__restrict__ coef, int n_ops, const T (&w)[2], const T (&wi)[2],
                                           Abcd2<T> &m, const QoPlanes &planes, int k0)
 {
-    QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
-            m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
+    if (!QO_ROW) {               /* QO_ROW: the caller has put [1 Rs] into (a, b) */
+        QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = T(0); m.bi[p] = T(0);
+                m.cr[p] = T(0); m.ci[p] = T(0); m.dr[p] = T(1); m.di[p] = T(0); }
+    }
     T w2[2];
     QO_P2 w2[p] = w[p] * w[p];
 #ifdef QO_JIT_CHAIN
-    QO_JIT_CHAIN                 /* qo_chain_step<T, TRIG>(<opcode>, coef + <offset>, w, wi, w2, m, planes, k0); per element */
+    QO_JIT_CHAIN                 /* qo_chain_step<T, TRIG, QO_ROW>(<opcode>, coef + <offset>, w, wi, w2, m, planes, k0); per element */
 #else
     for (int e = 0; e < n_ops; e++) qo_chain_step<T, TRIG>(s_op[e], coef + s_coff[e], w, wi, w2, m, planes, k0);
 #endif
@@ -364,6 +378,7 @@ qo_mc_lumped_kernel(
             const int jn = j + 32;
             if (jn < hi) { wv = w2[jn]; wiv = wi2[jn]; if (!FULL_S) mv = m2[jn]; }   /* prefetch next pair */
             Abcd2<T> m;
+            if (QO_ROW) { QO_P2 { m.ar[p] = T(1); m.ai[p] = T(0); m.br[p] = rs; m.bi[p] = T(0); } }
             qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, w, wi, m, planes, 2 * j);
             double2 o11[2], o21[2], o22[2];
             QO_P2 {
@@ -374,6 +389,8 @@ qo_mc_lumped_kernel(
                     T qr = qfma(m.cr[p], rsrl, m.dr[p] * rs), qi = qfma(m.ci[p], rsrl, m.di[p] * rs);
                     den_r = pr + qr; den_i = pi_ + qi; n_r = pr - qr; n_i = pi_ - qi;
                     num2 = qfma(n_r, n_r, n_i * n_i);
+                } else if (QO_ROW) {
+                    den_r = qfma(m.ar[p], rl, m.br[p]); den_i = qfma(m.ai[p], rl, m.bi[p]);
                 } else {
                     den_r = qfma(m.dr[p], rs, qfma(m.cr[p], rsrl, qfma(m.ar[p], rl, m.br[p])));
                     den_i = qfma(m.di[p], rs, qfma(m.ci[p], rsrl, qfma(m.ai[p], rl, m.bi[p])));
@@ -400,10 +417,12 @@ qo_mc_lumped_kernel(
                         const T wq[2] = { w[p] + dwq, w[p] - dwq };
                         const T wiq[2] = { T(1) / wq[0], T(1) / wq[1] };
                         Abcd2<T> mg;
+                        if (QO_ROW) { _Pragma("unroll") for (int q = 0; q < 2; q++) { mg.ar[q] = T(1); mg.ai[q] = T(0); mg.br[q] = rs; mg.bi[q] = T(0); } }
                         qo_chain2<T, TRIG>(s_op, s_coff, coefw, n_ops, wq, wiq, mg, planes, 2 * j);
                         T dgr[2], dgi[2];
 #pragma unroll
                         for (int q = 0; q < 2; q++) {
+                            if (QO_ROW) { dgr[q] = qfma(mg.ar[q], rl, mg.br[q]); dgi[q] = qfma(mg.ai[q], rl, mg.bi[q]); continue; }
                             dgr[q] = qfma(mg.dr[q], rs, qfma(mg.cr[q], rsrl, qfma(mg.ar[q], rl, mg.br[q])));
                             dgi[q] = qfma(mg.di[q], rs, qfma(mg.ci[q], rsrl, qfma(mg.ai[q], rl, mg.bi[q])));
                         }
@@ -506,3 +525,4 @@ qo_mc_lumped_kernel(
     }
 }
 #undef QO_SK
+#undef QO_ROW

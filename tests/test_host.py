@@ -557,7 +557,8 @@ def test_chain_kernel_generator_compiles_without_gpu(Q, W, tmp_path, monkeypatch
     assert fs["compiled"], fs["error"]
     src = dump.read_text()
     n_el = len(w5.net)
-    assert src.count("qo_chain_step<T, TRIG>(") == n_el + 2                 # one call per element + the definition's two mentions
+    assert src.count("qo_chain_step<T, TRIG, QO_ROW>(") == n_el + 1         # one call per element + the interpreter loop's (compiled out)
+    assert "#define QO_JIT_ROW false" in src                                # FULL_S needs the whole 2x2 product
     assert "static constexpr bool FULL_S = true, TRIG = true, GD = false;" in src and "#define QO_JIT_NSPEC 0" in src
     assert len(list((tmp_path / "cache").glob("chain_*_sm100a.cubin"))) == 1
     # line inside a ladder + every rf-tools opcode + group delay and |S11| specs
@@ -572,6 +573,30 @@ def test_chain_kernel_generator_compiles_without_gpu(Q, W, tmp_path, monkeypatch
     assert g["compiled"], g
     src = dump.read_text()
     assert "GD = true" in src and "#define QO_JIT_HIST_KIND 4" in src and "#define QO_JIT_NEED_S11 1" in src
-    assert src.count("qo_chain_step<T, TRIG>(") == len(items) + 2
+    assert src.count("qo_chain_step<T, TRIG, QO_ROW>(") == len(items) + 1
+    assert "#define QO_JIT_ROW false" in src                                # an |S11| spec: both rows
+    g2 = Q.chain_jit_analyze(net, f, specs[:2], [(5, 0, 0, Q.TOL_REL, 0.05)], hist_bins=16, hist_spec=1, hist_lo=0.0, hist_hi=1e-6)
+    assert g2["compiled"] and "#define QO_JIT_ROW true" in dump.read_text()  # |S21| and group delay only: the row vector [1 Rs] M
     with pytest.raises(Q.QoError):                                           # microstrip networks have their own kernels
         Q.chain_jit_analyze(W.pa_lpf_net(), f)
+
+
+def test_executed_profile_is_of_this_machine_code():
+    """profiles/executed_fp64.json carries, next to the source hash, the per-kernel hash of the SASS its ncu captures were taken
+    on.  build() writes the same hashes for the library just linked (qo-100-tools_b200/lib/sass_hashes.json): the headline kernels'
+    machine code must be the profiled one, or the profile has to be re-captured."""
+    import hashlib
+    import json
+    lib = os.path.join(ROOT, "qo-100-tools_b200", "lib")
+    try:
+        built = json.load(open(os.path.join(lib, "sass_hashes.json")))
+    except OSError:
+        pytest.skip("no sass_hashes.json next to the library (cuobjdump missing when build() ran)")
+    if built.get("lib_sha256") != hashlib.sha256(open(os.path.join(lib, "libqo100net.so"), "rb").read()).hexdigest():
+        pytest.skip("sass_hashes.json describes another build of the library")
+    prof = json.load(open(os.path.join(ROOT, "profiles", "executed_fp64.json")))
+    for k in ("qo_mc_ts_kernel", "qo_mc_tf_kernel", "qo_mc_ladder_kernel"):
+        assert built["kernels"][k]["sha"] == prof["_sass"][k], k
+    import bench
+    ex = bench.executed_profile("qo_mc_ts_kernel", "cfg2-cheby11")
+    assert bench.profile_match(ex, "qo_mc_ts_kernel") in ("source", "sass")

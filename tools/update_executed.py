@@ -40,5 +40,12 @@ out["_doc"] = ("EXECUTED FP64 instructions per (sample, frequency) eval and DRAM
 out["_src_hash"] = kernel_source_hash()
 out["_git"] = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
 out["_tag"] = tag
+try:                                          # machine-code identity of the profiled build (tools/sass_hash.py)
+    from tools.sass_hash import write_lib_hashes
+    k = write_lib_hashes()["kernels"]
+    out["_sass"] = {n: k[n]["sha"] for n in k}
+    out["_sass_git"] = out["_git"]
+except Exception as ex:
+    print("no SASS hashes:", ex)
 json.dump(out, open(path, "w"), indent=1)
 print("stamped", out["_git"], out["_src_hash"])

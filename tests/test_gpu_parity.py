@@ -806,6 +806,26 @@ def test_differential_fuzz_of_the_monte_carlo_kernels(monkeypatch):
     assert {"qo_mc_tf_kernel", "qo_mc_ts_kernel", "qo_mc_spot_kernel"} <= set(out["kernels_selected"])
 
 
+def test_differential_fuzz_of_the_compiled_chain_kernel(Q, W, monkeypatch):
+    """tools/fuzz_parity.py --chain-jit on a fixed seed: 24 random lumped cascades, most with a perturbed line and / or the measured
+    two-port BEHIND them (what no polynomial kernel takes), each compiled into its own chain kernel (qo_chain_jit.h): counters equal
+    the interpreter's and (every 5th) the oracle's, FULL_S planes the interpreter's.  100 networks: profiles/fuzz/fuzz_r02s_chain_jit_seed91.json."""
+    import importlib.util
+    w5 = W.cfg5(1000)
+    a = Q.chain_jit_analyze(w5.net, w5.f[:64], w5.specs[:1], w5.tols)
+    if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+        pytest.skip("libnvrtc is not loadable on this box")
+    monkeypatch.delenv("QO100NET_KERNEL", raising=False)
+    monkeypatch.delenv("QO100NET_CHAIN", raising=False)
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out = mod.main(["--chain-jit", "--nets", "24", "--samples", "3000", "--seed", "91"])
+    assert out["mismatches"] == 0, out["details"]
+    assert out["compared"] >= 20 and out["oracle_checked"] >= 3 and out["full_s_checked"] >= 4
+    assert set(out["kernels_selected"]) == {"qo_mc_chain_jit_kernel"}
+
+
 def test_fuzz_regressions(Q, R, ctx, monkeypatch):
     """The networks on which tools/fuzz_parity.py caught the transfer-function kernels (recorded under profiles/fuzz/):
     (a) thread-per-sample kernel: the truncated E(y) goes negative beyond the last spec band on some samples and used to fail

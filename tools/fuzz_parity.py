@@ -146,6 +146,8 @@ def main(argv=None):
     ap.add_argument("--big-every", type=int, default=7, help="every k-th network runs a launch large enough for the thread-per-sample kernel")
     ap.add_argument("--ladders", action="store_true", help="pcb/generic-filter ladders only, the selected run forced onto the chain kernel (QO100NET_KERNEL=ladder)")
     ap.add_argument("--gd", action="store_true", help="add a group-delay spec (limit around the nominal network's worst in-band delay) to networks without a front block")
+    ap.add_argument("--chain-jit", action="store_true", help="the selected run is the run-time compiled chain kernel (QO100NET_KERNEL=interp QO100NET_CHAIN=jit) against the "
+                    "interpreter proper; 60 %% of the networks get a perturbed line BEHIND the cascade and 30 %% the measured two-port behind that -- what no polynomial kernel takes")
     ap.add_argument("--only", type=int, default=-1, help="run just this network (each network has its own random stream) and dump it")
     ap.add_argument("--out", default=None)
     args = ap.parse_args(argv)
@@ -159,6 +161,15 @@ def main(argv=None):
             continue
         rng = np.random.default_rng([args.seed, i])          # one stream per network: --only reproduces it exactly
         net, f, tols, fc = random_ladder(Q, rng) if args.ladders else random_net(Q, rng)
+        if args.chain_jit:
+            rs_, rl_ = net.terminations
+            if rng.random() < 0.6:
+                ne = len(net)
+                net = net.concat(Q.Net.from_elements([(Q.TLINE, [50.0 * rng.uniform(0.7, 1.5), rng.uniform(10, 120), fc])], rs_, rl_))
+                nv = 1 + max(t[2] for t in tols)
+                tols = list(tols) + [(ne, 0, nv, Q.TOL_REL, 0.05), (ne, 1, nv + 1, Q.TOL_REL, 0.03)]
+            if rng.random() < 0.3 and fc < 2e9 and net.elements[0][0] != Q.SBLOCK:
+                net = net.concat(_block(Q).as_net(True, rs_, rl_))
         n = big if i % args.big_every == args.big_every - 1 else args.samples
         dist = Q.DIST_GAUSS3S if rng.random() < 0.3 else Q.DIST_UNIFORM
         try:
@@ -210,6 +221,9 @@ def main(argv=None):
         os.environ.pop("QO100NET_KERNEL", None)
         if args.ladders:
             os.environ["QO100NET_KERNEL"] = "ladder"
+        if args.chain_jit:
+            os.environ["QO100NET_KERNEL"] = "interp"
+            os.environ["QO100NET_CHAIN"] = "jit"
         plan = Q.Plan(ctx, net, f, specs, seed=1000 + i, tols=tols, dist=dist, **hist)
         off = int(rng.integers(0, 2 ** 40))
         plan.launch(off, n)
@@ -218,9 +232,11 @@ def main(argv=None):
         plan.close()
         kernels[kname] = kernels.get(kname, 0) + 1
         os.environ["QO100NET_KERNEL"] = "interp"
+        os.environ.pop("QO100NET_CHAIN", None)
         plan = Q.Plan(ctx, net, f, specs, seed=1000 + i, tols=tols, dist=dist, **hist)
         plan.launch(off, n)
         ref = plan.read()
+        assert plan.kernel_name == "qo_mc_lumped_kernel", plan.kernel_name
         plan.close()
         os.environ.pop("QO100NET_KERNEL", None)
         same = got["n_pass"] == ref["n_pass"] and np.array_equal(got["fail_per_spec"], ref["fail_per_spec"]) and np.array_equal(got["hist"], ref["hist"])
@@ -231,8 +247,13 @@ def main(argv=None):
             same = got["n_pass"] == o["n_pass"] and np.array_equal(got["fail_per_spec"], o["fail_per_spec"]) and np.array_equal(got["hist"], o["hist"])
         if same and i % 4 == 1:
             # FULL_S: a launch large enough for qo_fs_tf_kernel against the interpreter's planes of the same samples
+            if args.chain_jit:
+                os.environ["QO100NET_KERNEL"] = "interp"
+                os.environ["QO100NET_CHAIN"] = "jit"
             a = ctx.mc_run(net, f, [], 1000 + i, 1536, tols, sample_offset=off, mode=Q.MODE_FULL_S, dist=dist)["s"]
+            os.environ.pop("QO100NET_CHAIN", None)
             b = ctx.mc_run(net, f, [], 1000 + i, 64, tols, sample_offset=off, mode=Q.MODE_FULL_S, dist=dist)["s"]
+            os.environ.pop("QO100NET_KERNEL", None)
             fs_checked += 1
             for pl in range(4):
                 ref_ = np.asarray(b[pl]); got_ = np.asarray(a[pl])[:64]

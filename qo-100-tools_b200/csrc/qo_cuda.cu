@@ -853,6 +853,11 @@ static int launch_lumped(qo_plan *p, int g, unsigned long long off, unsigned lon
             p->cj[fs] = je;
         }
         if (je) {
+            if (je->blocks_per_sm > 2) {        /* built for more resident blocks than the interpreter's two: size the persistent grid accordingly */
+                const int res2 = dc->sm_count * je->blocks_per_sm;
+                grid = (int)(blocks < (unsigned long long)res2 ? blocks : (unsigned long long)res2);
+                if (grid < 1) grid = 1;
+            }
             const DevProg *a_prog = d->prog;
             const void *a_w2 = d->w2, *a_wi2 = d->wi2, *a_m2 = d->m2;
             int a_nf = p->nf, a_np = p->npairs;

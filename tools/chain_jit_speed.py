@@ -19,7 +19,7 @@ sys.path.insert(0, os.path.join(ROOT, "qo-100-tools_b200", "python"))
 sys.path.insert(0, ROOT)
 
 
-def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384):
+def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384, modes=("jit", "interp")):
     from qo100net import workloads as W
 
     class args:
@@ -41,7 +41,7 @@ def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384):
 
     def reduce_case(name, net, f, specs, tols, hist, kernel_env):
         row = {}
-        for label in ("jit", "interp"):
+        for label in modes:
             os.environ["QO100NET_CHAIN"] = label
             if kernel_env:
                 os.environ["QO100NET_KERNEL"] = kernel_env
@@ -66,8 +66,9 @@ def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384):
             plan.close()
         os.environ.pop("QO100NET_CHAIN", None)
         os.environ.pop("QO100NET_KERNEL", None)
-        row["counters_equal"] = all(row["jit"][k] == row["interp"][k] for k in ("n_pass", "n_total", "fail_per_spec", "hist_sum"))
-        row["speedup"] = row["jit"]["evals_per_s"] / row["interp"]["evals_per_s"]
+        if len(modes) == 2:
+            row["counters_equal"] = all(row["jit"][k] == row["interp"][k] for k in ("n_pass", "n_total", "fail_per_spec", "hist_sum"))
+            row["speedup"] = row["jit"]["evals_per_s"] / row["interp"]["evals_per_s"]
         out[name] = row
 
     reduce_case("cfg2 ladder with a line inside and a measured two-port behind", mixed, w.f, mspec, mtol, mhist, None)
@@ -79,7 +80,7 @@ def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384):
     buf = torch.empty((4, n, len(w5.f), 2), dtype=torch.float64, device="cuda")
     row = {}
     keep = {}
-    for label in ("jit", "interp"):
+    for label in modes:
         os.environ["QO100NET_CHAIN"] = label
         plan = Q.Plan(ctx, w5.net, w5.f, [], seed=1, tols=w5.tols, mode=Q.MODE_FULL_S)
         with torch.cuda.stream(stream):
@@ -96,8 +97,9 @@ def measure(Q, torch, ctx, stream, samples=200000, fs_samples=16384):
         row[label] = {"kernel": plan.kernel_name, "ms": ms, "gb_per_s": n * len(w5.f) * 64 / ms * 1e-6, "evals_per_s": n * len(w5.f) / (ms * 1e-3)}
         plan.close()
     os.environ.pop("QO100NET_CHAIN", None)
-    row["max_abs_diff"] = float((keep["jit"] - keep["interp"]).abs().max())
-    row["speedup"] = row["interp"]["ms"] / row["jit"]["ms"]
+    if len(modes) == 2:
+        row["max_abs_diff"] = float((keep["jit"] - keep["interp"]).abs().max())
+        row["speedup"] = row["interp"]["ms"] / row["jit"]["ms"]
     out["cfg5 FULL_S (%d samples x %d points)" % (n, len(w5.f))] = row
     return out
 
@@ -107,13 +109,14 @@ def main():
     ap.add_argument("--samples", type=int, default=200000)
     ap.add_argument("--fs-samples", type=int, default=16384)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--jit-only", action="store_true")
     a = ap.parse_args()
     import torch
     import qo100net as Q
     ctx = Q.Context(device=0)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
-    out = measure(Q, torch, ctx, stream, a.samples, a.fs_samples)
+    out = measure(Q, torch, ctx, stream, a.samples, a.fs_samples, ("jit",) if a.jit_only else ("jit", "interp"))
     print(json.dumps(out, indent=1))
     if a.out:
         open(a.out, "w").write(json.dumps(out, indent=1))

@@ -203,7 +203,7 @@ def main(argv=None):
             if np.quantile(v, 0.9) - np.quantile(v, 0.1) < 0.01 or v.min() < -140.0:
                 continue
             specs.append((kind, float(lo), float(hi), float(np.quantile(v, qq))))
-        if args.gd and net.elements[0][0] not in (Q.CPL_THRU, Q.TLINE, Q.SBLOCK) and len(specs) < 8 and not any(s_[0] == Q.SPEC_S11_MAX_DB for s_ in specs):
+        if args.gd and net.elements[0][0] not in (Q.CPL_THRU, Q.TLINE, Q.SBLOCK) and all(k_ != Q.SBLOCK for k_, _p in net.elements) and len(specs) < 8 and not any(s_[0] == Q.SPEC_S11_MAX_DB for s_ in specs):
             gdn = ctx.sweep(net, f, gd=True)[4]
             lo, hi = sorted(rng.uniform(f[0], f[-1], 2))
             band = (f >= lo) & (f <= hi)

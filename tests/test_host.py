@@ -600,3 +600,41 @@ def test_executed_profile_is_of_this_machine_code():
     import bench
     ex = bench.executed_profile("qo_mc_ts_kernel", "cfg2-cheby11")
     assert bench.profile_match(ex, "qo_mc_ts_kernel") in ("source", "sass")
+
+
+def test_chain_kernel_generator_on_random_cascades(Q):
+    """The generator of the compiled chain kernel on the differential fuzzer's random cascades (tools/fuzz_parity.py: all ten lumped
+    branch kinds with and without parasitics; coupled line, physical coupled microstrip, transmission line or the measured two-port
+    of pa-bias-simulation.sch:39 in front; a line / the measured block behind): every job compiles for sm_100a, reduce-only (row-vector
+    and 2x2 flavours) and FULL_S.  Host only; the GPU side of the same networks is tools/fuzz_parity.py --chain-jit."""
+    import importlib.util
+    w = Q.Net.from_elements([(Q.SER_R, [1.0])], 50.0, 50.0)
+    a = Q.chain_jit_analyze(w, [1e6, 2e6], [(Q.SPEC_S21_MIN_DB, 0.0, 1e9, -3.0)])
+    if not a["compiled"] and "libnvrtc" in (a["error"] or ""):
+        pytest.skip("libnvrtc is not loadable here: %s" % a["error"])
+    assert a["compiled"], a
+    spec = importlib.util.spec_from_file_location("fuzz_parity", os.path.join(ROOT, "tools", "fuzz_parity.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fronts = set()
+    for i in range(10):
+        rng = np.random.default_rng([5, i])
+        net, f, tols, fc = mod.random_net(Q, rng)
+        rs, rl = net.terminations
+        if i % 2 == 0:
+            ne = len(net)
+            net = net.concat(Q.Net.from_elements([(Q.TLINE, [60.0, 33.0, fc])], rs, rl))
+            tols = list(tols) + [(ne, 0, 1 + max(t[2] for t in tols), Q.TOL_REL, 0.05)]
+        if i % 3 == 0 and net.elements[0][0] != Q.SBLOCK:
+            net = net.concat(mod._block(Q).as_net(True, rs, rl))
+        fronts.add(net.elements[0][0] if net.elements[0][0] != Q.SUBST else net.elements[1][0])
+        f = f[:64]
+        lo, hi = float(f[0]), float(f[-1])
+        s21 = [(Q.SPEC_S21_MIN_DB, lo, hi, -3.0), (Q.SPEC_S21_MAX_DB, lo, hi, -0.01)]
+        for specs, mode, hist in ((s21, Q.MODE_REDUCE_ONLY, dict(hist_bins=16, hist_spec=0, hist_lo=-6.0, hist_hi=0.0)),
+                                  (s21 + [(Q.SPEC_S11_MAX_DB, lo, hi, -10.0)], Q.MODE_REDUCE_ONLY, {}),
+                                  ([], Q.MODE_FULL_S, {})):
+            r = Q.chain_jit_analyze(net, f, specs, tols, mode=mode, **hist)
+            assert r["compiled"], (i, mode, r["error"])
+            assert r["registers"] == -1 or r["registers"] <= 128
+    assert len(fronts) >= 3, fronts

@@ -638,3 +638,38 @@ def test_chain_kernel_generator_on_random_cascades(Q):
             assert r["compiled"], (i, mode, r["error"])
             assert r["registers"] == -1 or r["registers"] <= 128
     assert len(fronts) >= 3, fronts
+
+
+def test_chain_kernel_full_s_with_an_older_nvrtc(tmp_path):
+    """A process that imported torch carries torch's own libnvrtc (CUDA 12.8 here), whose PTX level predates the 256-bit global stores
+    of the FULL_S path.  The chain generator prefers the toolkit's NVRTC; pointed at the older one (QO100NET_NVRTC) it must still
+    produce a kernel -- with two 128-bit stores per plane (QO_NO_ST256) -- instead of failing in ptxas."""
+    import glob
+    import importlib.util
+    import subprocess
+    import sys
+    sp = importlib.util.find_spec("nvidia.cuda_nvrtc")
+    cands = []
+    if sp is not None and sp.submodule_search_locations:
+        for d in sp.submodule_search_locations:
+            cands += glob.glob(os.path.join(d, "lib", "libnvrtc.so.*"))
+    cands = [c for c in cands if "builtins" not in c]
+    if not cands:
+        pytest.skip("no pip-installed libnvrtc next to torch")
+    dump = tmp_path / "fs.cu"
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import qo100net as Q\nfrom qo100net import workloads as W\n"
+            "w = W.cfg5(1000)\n"
+            "print(json.dumps(Q.chain_jit_analyze(w.net, w.f[:200], [], w.tols, mode=Q.MODE_FULL_S)))\n") % os.path.join(ROOT, "qo-100-tools_b200", "python")
+    env = dict(os.environ, QO100NET_NVRTC=cands[0], QO100NET_CHAIN_JIT_DUMP=str(dump))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr[-800:]
+    import json
+    a = json.loads(r.stdout.strip().splitlines()[-1])
+    assert a["compiled"], a
+    src = dump.read_text()
+    import ctypes
+    L = ctypes.CDLL(cands[0])
+    mj, mn = ctypes.c_int(), ctypes.c_int()
+    L.nvrtcVersion(ctypes.byref(mj), ctypes.byref(mn))
+    assert ("#define QO_NO_ST256 1" in src) == ((mj.value, mn.value) < (12, 9)), (mj.value, mn.value)

@@ -129,3 +129,46 @@ def test_mc_oracle_properties(R):
     # zero tolerance => every sample is the nominal design
     z = R.mc_run(lad, 50, 50, f, specs, R.mc_cfg(1, 10, [(0, 0, 0, 0, 0.0)]))
     assert z["n_pass"] in (0, 10)
+
+
+def test_oracle_line_inside_and_measured_block_behind_vs_numpy(R, golden_s2p):
+    """The cascade family of the compiled chain kernel's GPU test (a ladder with a transmission line INSIDE it, the measured inductor
+    of util/pa-bias-simulation/pa-bias-simulation.sch:39 and a resistor BEHIND it, unequal terminations), oracle against an
+    independent numpy restatement (plain 2x2 products, SPfile interpolation and S -> ABCD from conftest): the checker of that GPU
+    test is itself pinned on this topology.  Lossy L: R + jwL in parallel with Cp; lossy C: ESR + 1/(jwC) + jw Ls."""
+    from conftest import np_s_to_abcd, np_spfile
+    fd, sd, z0 = golden_s2p["11SQ39N_f"], golden_s2p["11SQ39N_s"], float(golden_s2p["11SQ39N_z0"])
+    R.sblock_clear()
+    R.sblock_register(0, fd, sd[:, 0], sd[:, 1], sd[:, 2], sd[:, 3], z0)
+    SER_R, SER_L, SHUNT_C, TLINE, SBLOCK = R.SER_R, R.SER_L, R.SHUNT_C, R.TLINE, 18          # include/qo100net.h: QO_SBLOCK = 18
+    L1, R1, Cp1 = 1.2e-6, 0.9, 0.4e-12
+    C1, E1, Ls1 = 330e-12, 0.12, 0.7e-9
+    L2, C2 = 0.8e-6, 270e-12
+    items = [(SER_L, [L1, R1, Cp1]), (SHUNT_C, [C1, E1, Ls1]), (TLINE, [75.0, 20.0, 10e6]), (SER_L, [L2, 0.0, 0.0]),
+             (SHUNT_C, [C2, 0.0, 0.0]), (SBLOCK, [0.0, 1.0]), (SER_R, [2.2])]
+    f = np.geomspace(2e6, 3e8, 400)
+    rs, rl = 50.0, 75.0
+    o = R.sweep(R.make_elems(items), rs, rl, f)
+    w = 2 * np.pi * f
+    one, zero = np.ones_like(w, dtype=complex), np.zeros_like(w, dtype=complex)
+
+    def ser(z): return np.stack([one, z, zero, one], 1)
+    def sh(y): return np.stack([one, zero, y, one], 1)
+    def mul(a, b): return np.stack([a[:, 0] * b[:, 0] + a[:, 1] * b[:, 2], a[:, 0] * b[:, 1] + a[:, 1] * b[:, 3],
+                                    a[:, 2] * b[:, 0] + a[:, 3] * b[:, 2], a[:, 2] * b[:, 1] + a[:, 3] * b[:, 3]], 1)
+    th = np.deg2rad(20.0) * f / 10e6
+    zl1 = 1.0 / (1.0 / (R1 + 1j * w * L1) + 1j * w * Cp1)
+    parts = [ser(zl1), sh(1.0 / (E1 + 1.0 / (1j * w * C1) + 1j * w * Ls1)),
+             np.stack([np.cos(th) + 0j, 1j * 75.0 * np.sin(th), 1j * np.sin(th) / 75.0, np.cos(th) + 0j], 1),
+             ser(1j * w * L2), sh(1j * w * C2), np_s_to_abcd(np_spfile(f, fd, sd, True), z0), ser(np.full_like(w, 2.2, dtype=complex))]
+    M = parts[0]
+    for p_ in parts[1:]:
+        M = mul(M, p_)
+    den = M[:, 0] * rl + M[:, 1] + M[:, 2] * rs * rl + M[:, 3] * rs
+    s21 = 2 * np.sqrt(rs * rl) / den
+    s11 = (M[:, 0] * rl + M[:, 1] - M[:, 2] * rs * rl - M[:, 3] * rs) / den
+    s22 = (-M[:, 0] * rl + M[:, 1] - M[:, 2] * rs * rl + M[:, 3] * rs) / den
+    assert relerr(o[1], s21) < 1e-10 and relerr(o[2], s21) < 1e-10           # the measured inductor is reciprocal to its print precision
+    assert np.max(np.abs(o[0] - s11)) < 1e-10 and np.max(np.abs(o[3] - s22)) < 1e-10
+    assert 20 * np.log10(np.abs(s21)).min() < -30 and 20 * np.log10(np.abs(s21)).max() > -3      # a real low-pass: both regimes are exercised
+    R.sblock_clear()
